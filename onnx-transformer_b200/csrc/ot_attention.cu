@@ -1,0 +1,363 @@
+// ot_attention_q8: fused quantized multi-head attention (attention.py:23-36 as exported).
+//
+// One CTA per (sentence b, tile of QT queries); warp h owns head h.  The sentence's int8 K and V rows (all 8
+// heads) and their per-token scales are staged once in shared memory; scores are exact int32 dot products
+// (dp4a) scaled in the canonical fp32 order  S = fl(fl(float(dot)*sq[i])*sk[j]) / 8 ; masked keys get -1e9;
+// softmax uses warp-shuffle row reductions; P is quantized to rint(127 p); the context is accumulated in
+// fp32 as  sum_j (pq_j/127) * (sv_j * vq[j,d])  (the V scale sits on the contraction axis, so this product is
+// not an int8 GEMM -- SURVEY.md 0.6).  Because the CTA ends up owning complete 512-feature rows it also
+// performs the per-token RowQuant that feeds the O-projection, and, for the decoder, appends the step's new
+// K/V rows to the persistent KV cache.
+#include "ot_common.h"
+
+namespace ot {
+
+constexpr int kHeads = 8;
+constexpr int kDk = 64;
+constexpr int kDm = kHeads * kDk;   // 512
+constexpr int kKPitch = kDm + 16;   // padded K row pitch: conflict-free 128-bit reads across keys
+constexpr int kMaxTk = 192;
+constexpr int kKeysPerLane = kMaxTk / 32;
+
+struct AttnArgs {
+  const int8_t* q; int64_t ldq; const float* sq; int64_t sq_stride;
+  int8_t* k; int8_t* v; int64_t ldk; float* sk; float* sv; int64_t skv_stride;
+  const int8_t* k_new; const int8_t* v_new; int64_t ld_new; const float* sk_new; const float* sv_new; int64_t snew_stride;
+  int B, Tq, Tk, Tk_cap, mask_kind;
+  const uint8_t* key_mask; int64_t mask_stride;
+  int q_pos0;
+  const int32_t* step_dev;
+  float* ctx; int64_t ld_ctx;
+  int8_t* ctx_q; float* ctx_s;
+  uint8_t* probs_q;
+  OtFault fault;
+};
+
+enum { OPERAND_Q = 0, OPERAND_K = 1, OPERAND_P = 2, OPERAND_V = 3, OPERAND_SCORES = 4, OPERAND_CTX = 5 };
+
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float patch_f32(const OtFault& f, float v) {
+  uint32_t bits = __float_as_uint(v);
+  if (f.mode == OT_FAULT_RANDOM_BITFLIP) bits ^= (1u << f.bit);
+  else bits = f.value_bits;
+  const float r = __uint_as_float(bits);
+  return (r != r) ? 0.0f : r;
+}
+
+template <int QT>
+__global__ void __launch_bounds__(256, 1) attention_q8_kernel(const AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int step = a.step_dev ? *a.step_dev : 0;
+  const int Tk = a.step_dev ? step + a.Tq : a.Tk;
+  const int q_pos0 = a.step_dev ? step : a.q_pos0;
+  const int Tk_pad = (Tk + 31) & ~31;
+
+  int8_t* Ks = reinterpret_cast<int8_t*>(smem);                        // [Tk][kKPitch]
+  int8_t* Vs = Ks + static_cast<size_t>(Tk_pad) * kKPitch;            // [Tk][512]
+  int8_t* Qs = Vs + static_cast<size_t>(Tk_pad) * kDm;                // [QT][512]
+  float* Cs = reinterpret_cast<float*>(Qs + QT * kDm);                // [QT][512] fp32 context tile
+  float* Pw = Cs + QT * kDm;                                          // [8][Tk_pad] quantized probabilities / 127
+  float* sks = Pw + kHeads * Tk_pad;                                  // [Tk_pad]
+  float* svs = sks + Tk_pad;                                          // [Tk_pad]
+  uint8_t* keep = reinterpret_cast<uint8_t*>(svs + Tk_pad);           // [Tk_pad] key-padding mask
+
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * QT;
+  const int nq = min(QT, a.Tq - q0);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int new0 = (a.k_new != nullptr) ? Tk - a.Tq : Tk;  // keys >= new0 come from this step's projections
+  const bool writer = (blockIdx.x == 0);
+
+  // ---- stage K, V (16-byte chunks), scales, mask, Q tile
+  for (int idx = tid; idx < Tk * (kDm / 16); idx += blockDim.x) {
+    const int j = idx >> 5, c = idx & 31;
+    uint4 kk, vv;
+    if (j >= new0) {
+      const int64_t src = (static_cast<int64_t>(b) * a.Tq + (j - new0)) * a.ld_new + c * 16;
+      kk = *reinterpret_cast<const uint4*>(a.k_new + src);
+      vv = *reinterpret_cast<const uint4*>(a.v_new + src);
+      if (writer) {
+        const int64_t dst = (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + c * 16;
+        *reinterpret_cast<uint4*>(a.k + dst) = kk;
+        *reinterpret_cast<uint4*>(a.v + dst) = vv;
+      }
+    } else {
+      const int64_t src = (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + c * 16;
+      kk = *reinterpret_cast<const uint4*>(a.k + src);
+      vv = *reinterpret_cast<const uint4*>(a.v + src);
+    }
+    *reinterpret_cast<uint4*>(Ks + j * kKPitch + c * 16) = kk;
+    *reinterpret_cast<uint4*>(Vs + j * kDm + c * 16) = vv;
+  }
+  for (int j = tid; j < Tk_pad; j += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    uint8_t kp = 0;
+    if (j < Tk) {
+      if (j >= new0) {
+        const int64_t src = (static_cast<int64_t>(b) * a.Tq + (j - new0)) * a.snew_stride;
+        s1 = a.sk_new[src];
+        s2 = a.sv_new[src];
+        if (writer) {
+          const int64_t dst = (static_cast<int64_t>(b) * a.Tk_cap + j) * a.skv_stride;
+          a.sk[dst] = s1;
+          a.sv[dst] = s2;
+        }
+      } else {
+        const int64_t src = (static_cast<int64_t>(b) * a.Tk_cap + j) * a.skv_stride;
+        s1 = a.sk[src];
+        s2 = a.sv[src];
+      }
+      kp = (a.mask_kind == 1) ? a.key_mask[static_cast<int64_t>(b) * a.mask_stride + j] : 1;
+    }
+    sks[j] = s1;
+    svs[j] = s2;
+    keep[j] = kp;
+  }
+  for (int idx = tid; idx < nq * (kDm / 16); idx += blockDim.x) {
+    const int i = idx >> 5, c = idx & 31;
+    *reinterpret_cast<uint4*>(Qs + i * kDm + c * 16) =
+        *reinterpret_cast<const uint4*>(a.q + (static_cast<int64_t>(b) * a.Tq + q0 + i) * a.ldq + c * 16);
+  }
+  __syncthreads();
+
+  // ---- fault context (App. D); operand selector in fault.reserved
+  const OtFault& f = a.fault;
+  const bool has_fault = f.mode != OT_FAULT_NONE;
+  int fb = -1, fh = -1, fi = -1, fj = -1, fd = -1, fdelta = 0, fw0 = 0, fw1 = 0;
+  if (has_fault) {
+    const int64_t idx = f.flat_index;
+    const int wl = f.window_len;
+    switch (f.reserved) {
+      case OPERAND_Q: {  // Round tensor [B,Tq,512]
+        fb = static_cast<int>(idx / (static_cast<int64_t>(a.Tq) * kDm));
+        fi = static_cast<int>((idx / kDm) % a.Tq);
+        fh = static_cast<int>(idx % kDm) / kDk; fd = static_cast<int>(idx % kDm) % kDk;
+        fw0 = wl > 0 ? f.window_start : 0; fw1 = wl > 0 ? min(Tk, f.window_start + wl) : Tk;       // key window
+      } break;
+      case OPERAND_K: case OPERAND_V: {  // Round tensor [B,Tk,512]
+        fb = static_cast<int>(idx / (static_cast<int64_t>(Tk) * kDm));
+        fj = static_cast<int>((idx / kDm) % Tk);
+        fh = static_cast<int>(idx % kDm) / kDk; fd = static_cast<int>(idx % kDm) % kDk;
+        fw0 = wl > 0 ? f.window_start : 0; fw1 = wl > 0 ? min(a.Tq, f.window_start + wl) : a.Tq;   // query window
+      } break;
+      case OPERAND_P: case OPERAND_SCORES: {  // [B,8,Tq,Tk]
+        fj = static_cast<int>(idx % Tk);
+        fi = static_cast<int>((idx / Tk) % a.Tq);
+        fh = static_cast<int>((idx / (static_cast<int64_t>(Tk) * a.Tq)) % kHeads);
+        fb = static_cast<int>(idx / (static_cast<int64_t>(Tk) * a.Tq * kHeads));
+        fw0 = wl > 0 ? f.window_start : 0; fw1 = wl > 0 ? min(kDk, f.window_start + wl) : kDk;     // feature window
+      } break;
+      default: {  // OPERAND_CTX: [B,8,Tq,64]
+        fd = static_cast<int>(idx % kDk);
+        fi = static_cast<int>((idx / kDk) % a.Tq);
+        fh = static_cast<int>((idx / (static_cast<int64_t>(kDk) * a.Tq)) % kHeads);
+        fb = static_cast<int>(idx / (static_cast<int64_t>(kDk) * a.Tq * kHeads));
+      } break;
+    }
+  }
+  const bool fault_here = has_fault && fb == b && fh == warp;
+
+  // ---- per head (warp) and query: scores -> softmax -> quantized P -> context
+  const int h = warp;
+  float* P = Pw + h * Tk_pad;
+  for (int iq = 0; iq < nq; ++iq) {
+    const int i = q0 + iq;
+    const float sqi = a.sq[(static_cast<int64_t>(b) * a.Tq + i) * a.sq_stride];
+    uint32_t qw[16];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint4 t = *reinterpret_cast<const uint4*>(Qs + iq * kDm + h * kDk + w * 16);
+      qw[4 * w] = t.x; qw[4 * w + 1] = t.y; qw[4 * w + 2] = t.z; qw[4 * w + 3] = t.w;
+    }
+    float sc[kKeysPerLane];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int kk = 0; kk < kKeysPerLane; ++kk) {
+      const int j = kk * 32 + lane;
+      sc[kk] = -INFINITY;
+      if (kk * 32 < Tk && j < Tk) {
+        int dot = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint4 t = *reinterpret_cast<const uint4*>(Ks + j * kKPitch + h * kDk + w * 16);
+          dot = __dp4a(static_cast<int>(qw[4 * w]), static_cast<int>(t.x), dot);
+          dot = __dp4a(static_cast<int>(qw[4 * w + 1]), static_cast<int>(t.y), dot);
+          dot = __dp4a(static_cast<int>(qw[4 * w + 2]), static_cast<int>(t.z), dot);
+          dot = __dp4a(static_cast<int>(qw[4 * w + 3]), static_cast<int>(t.w), dot);
+        }
+        if (fault_here) {
+          if (f.reserved == OPERAND_Q && f.mode == OT_FAULT_INPUT && i == fi && j >= fw0 && j < fw1) {
+            const int qv = Qs[iq * kDm + h * kDk + fd];
+            dot += (flip_int8_bit(qv, f.bit) - qv) * Ks[j * kKPitch + h * kDk + fd];
+          } else if (f.reserved == OPERAND_K && f.mode == OT_FAULT_WEIGHT && j == fj && i >= fw0 && i < fw1) {
+            const int kv = Ks[j * kKPitch + h * kDk + fd];
+            dot += Qs[iq * kDm + h * kDk + fd] * (flip_int8_bit(kv, f.bit) - kv);
+          }
+        }
+        float s = __fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), sks[j]);   // MatMul_k_out0
+        if (fault_here && f.reserved == OPERAND_SCORES && i == fi && j == fj) s = patch_f32(f, s);
+        s = __fdiv_rn(s, 8.0f);                                              // / sqrt(d_k)
+        const bool visible = keep[j] && (a.mask_kind != 2 || j <= q_pos0 + i);
+        sc[kk] = visible ? s : -1e9f;                                        // masked_fill(mask == 0, -1e9)
+        mx = fmaxf(mx, sc[kk]);
+      }
+    }
+    mx = warp_max_f(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < kKeysPerLane; ++kk) {
+      const int j = kk * 32 + lane;
+      if (kk * 32 < Tk && j < Tk) {
+        sc[kk] = expf(__fsub_rn(sc[kk], mx));
+        sum += sc[kk];
+      }
+    }
+    sum = warp_sum_f(sum);
+#pragma unroll
+    for (int kk = 0; kk < kKeysPerLane; ++kk) {
+      const int j = kk * 32 + lane;
+      if (kk * 32 < Tk_pad) {
+        float pq = 0.f;
+        if (j < Tk) {
+          pq = rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f));             // Round(Mul(p,127))
+          if (a.probs_q) a.probs_q[((static_cast<int64_t>(b) * kHeads + h) * a.Tq + i) * Tk + j] = static_cast<uint8_t>(pq);
+        }
+        P[j] = pq;                                                          // integer-valued, 0..127
+      }
+    }
+    __syncwarp();
+
+    // context: lane owns features 2*lane, 2*lane+1 of this head
+    float acc0 = 0.f, acc1 = 0.f;
+    const int d0 = 2 * lane;
+    const bool p_fault = fault_here && f.reserved == OPERAND_P && f.mode == OT_FAULT_INPUT && i == fi;
+    const bool v_fault = fault_here && f.reserved == OPERAND_V && f.mode == OT_FAULT_WEIGHT && i >= fw0 && i < fw1;
+    for (int j = 0; j < Tk; ++j) {
+      float pq = P[j];
+      float pq0 = pq, pq1 = pq;
+      if (p_fault && j == fj) {
+        const float pf = static_cast<float>(flip_int8_bit(static_cast<int>(pq), f.bit));
+        if (d0 >= fw0 && d0 < fw1) pq0 = pf;
+        if (d0 + 1 >= fw0 && d0 + 1 < fw1) pq1 = pf;
+      } else if (pq == 0.f) {
+        continue;  // exact zero contribution (warp-uniform branch)
+      }
+      const char2 vv = *reinterpret_cast<const char2*>(Vs + j * kDm + h * kDk + d0);
+      int v0 = vv.x, v1 = vv.y;
+      if (v_fault && j == fj) {
+        if (d0 == fd) v0 = flip_int8_bit(v0, f.bit);
+        if (d0 + 1 == fd) v1 = flip_int8_bit(v1, f.bit);
+      }
+      const float svj = svs[j];
+      acc0 = fmaf(__fdiv_rn(pq0, 127.0f), __fmul_rn(__int2float_rn(v0), svj), acc0);
+      acc1 = fmaf(__fdiv_rn(pq1, 127.0f), __fmul_rn(__int2float_rn(v1), svj), acc1);
+    }
+    if (fault_here && f.reserved == OPERAND_CTX && i == fi) {
+      if (d0 == fd) acc0 = patch_f32(f, acc0);
+      if (d0 + 1 == fd) acc1 = patch_f32(f, acc1);
+    }
+    *reinterpret_cast<float2*>(Cs + iq * kDm + h * kDk + d0) = make_float2(acc0, acc1);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- merge heads (Transpose + Reshape are free: Cs is already [query][512]); optional RowQuant (a7)
+  for (int iq = warp; iq < nq; iq += 8) {
+    const int64_t row = static_cast<int64_t>(b) * a.Tq + q0 + iq;
+    float4 v[4];
+    float amax = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      v[t] = *reinterpret_cast<const float4*>(Cs + iq * kDm + (t * 32 + lane) * 4);
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[t].x), fabsf(v[t].y)), fmaxf(fabsf(v[t].z), fabsf(v[t].w))));
+    }
+    if (a.ctx) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) *reinterpret_cast<float4*>(a.ctx + row * a.ld_ctx + (t * 32 + lane) * 4) = v[t];
+    }
+    if (a.ctx_q) {
+      const float s = __fdiv_rn(fmaxf(warp_max_f(amax), 1e-5f), 127.0f);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int q0i = __float2int_rn(rintf(__fdiv_rn(v[t].x, s))), q1i = __float2int_rn(rintf(__fdiv_rn(v[t].y, s)));
+        const int q2i = __float2int_rn(rintf(__fdiv_rn(v[t].z, s))), q3i = __float2int_rn(rintf(__fdiv_rn(v[t].w, s)));
+        const uint32_t w = (static_cast<uint32_t>(q0i) & 0xFFu) | ((static_cast<uint32_t>(q1i) & 0xFFu) << 8) |
+                           ((static_cast<uint32_t>(q2i) & 0xFFu) << 16) | ((static_cast<uint32_t>(q3i) & 0xFFu) << 24);
+        *reinterpret_cast<uint32_t*>(a.ctx_q + row * kDm + (t * 32 + lane) * 4) = w;
+      }
+      if (lane == 0) a.ctx_s[row] = s;
+    }
+  }
+}
+
+template <int QT>
+static size_t attn_smem_bytes(int Tk) {
+  const int Tk_pad = (Tk + 31) & ~31;
+  return static_cast<size_t>(Tk_pad) * kKPitch + static_cast<size_t>(Tk_pad) * kDm + QT * kDm + QT * kDm * 4 +
+         static_cast<size_t>(kHeads) * Tk_pad * 4 + 2 * Tk_pad * 4 + Tk_pad;
+}
+
+template <int QT>
+static int launch_attention(const AttnArgs& a, int tk_max, cudaStream_t stream) {
+  const size_t smem = attn_smem_bytes<QT>(tk_max);
+  OT_REQUIRE(smem <= 227 * 1024, "attention tile does not fit in shared memory");
+  auto kernel = attention_q8_kernel<QT>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  dim3 grid((a.Tq + QT - 1) / QT, a.B, 1);
+  kernel<<<grid, 256, smem, stream>>>(a);
+  OT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OT_OK;
+}
+
+}  // namespace ot
+
+using namespace ot;
+
+extern "C" int ot_attention_q8(const int8_t* q, int64_t ldq, const float* sq, int64_t sq_stride,
+                               int8_t* k, int8_t* v, int64_t ldk, float* sk, float* sv, int64_t skv_stride,
+                               const int8_t* k_new, const int8_t* v_new, int64_t ld_new, const float* sk_new,
+                               const float* sv_new, int64_t snew_stride,
+                               int B, int H, int Tq, int Tk, int Tk_cap, int mask_kind, const uint8_t* key_mask,
+                               int64_t mask_stride, int q_pos0, const int32_t* step_dev,
+                               float* ctx, int64_t ld_ctx, int8_t* ctx_q, float* ctx_s, uint8_t* probs_q,
+                               const OtFault* fault, void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(q && sq && k && v && sk && sv, "null operand");
+  OT_REQUIRE(H == kHeads, "this build is specialised for 8 heads of 64 features (model.py:15-16)");
+  OT_REQUIRE(B > 0 && Tq > 0, "empty problem");
+  OT_REQUIRE(ldq % 16 == 0 && ldk % 16 == 0 && (k_new == nullptr || ld_new % 16 == 0), "row pitches must be multiples of 16");
+  OT_REQUIRE(mask_kind >= 0 && mask_kind <= 2 && (mask_kind != 1 || key_mask), "bad mask");
+  OT_REQUIRE((ctx_q == nullptr) == (ctx_s == nullptr), "ctx_q and ctx_s go together");
+  OT_REQUIRE(ctx || ctx_q, "no output requested");
+  OT_REQUIRE((k_new == nullptr) == (v_new == nullptr) && (k_new == nullptr || (sk_new && sv_new)), "k_new/v_new/sk_new/sv_new go together");
+  const int tk_max = step_dev ? Tk_cap : Tk;  // with a device-side step the launch is sized for the cache capacity
+  OT_REQUIRE(tk_max > 0 && tk_max <= kMaxTk && Tk <= Tk_cap, "Tk must be in (0, 192] and <= Tk_cap");
+  OT_REQUIRE(probs_q == nullptr || step_dev == nullptr, "probs_q needs a host-side Tk");
+  AttnArgs a = {};
+  a.q = q; a.ldq = ldq; a.sq = sq; a.sq_stride = sq_stride;
+  a.k = k; a.v = v; a.ldk = ldk; a.sk = sk; a.sv = sv; a.skv_stride = skv_stride;
+  a.k_new = k_new; a.v_new = v_new; a.ld_new = ld_new; a.sk_new = sk_new; a.sv_new = sv_new; a.snew_stride = snew_stride;
+  a.B = B; a.Tq = Tq; a.Tk = Tk; a.Tk_cap = Tk_cap; a.mask_kind = mask_kind;
+  a.key_mask = key_mask; a.mask_stride = mask_stride; a.q_pos0 = q_pos0; a.step_dev = step_dev;
+  a.ctx = ctx; a.ld_ctx = ld_ctx; a.ctx_q = ctx_q; a.ctx_s = ctx_s; a.probs_q = probs_q;
+  if (fault) a.fault = *fault; else a.fault.mode = OT_FAULT_NONE;
+  cudaStream_t s = as_stream(stream);
+  if (Tq == 1) return launch_attention<1>(a, tk_max, s);
+  if (Tq <= 16 || tk_max > 128) return launch_attention<16>(a, tk_max, s);
+  return launch_attention<32>(a, tk_max, s);
+}

@@ -1,0 +1,627 @@
+// ot_linear_w8a8 / ot_linear_w4a8: int8 x int8 -> int32 GEMM on the 5th-generation tensor cores.
+//
+//   D[M,N] = A[M,K] * W[N,K]^T            (both operands K-major, exactly the layout the reference's
+//                                           `x_hat @ w_hat.T` has after its Round nodes; quant_linear.py:117)
+//
+// Per CTA: one 128 x BLOCK_N output tile.  Warp 0 = TMA producer (one elected lane), warp 1 = TMEM
+// allocator + tcgen05.mma issuer (one elected lane), warps 2..5 = epilogue (one thread per accumulator
+// row = TMEM lane).  A/B k-blocks of 128 bytes are staged by cp.async.bulk.tensor into 128B-swizzled
+// shared memory, consumed by tcgen05.mma.kind::i8 (M=128, N=BLOCK_N, K=32 per instruction), with the
+// int32 accumulators living in TMEM.  The epilogue reads TMEM with tcgen05.ld and applies, in the
+// canonical fp32 order of SURVEY.md App. A,
+//     y = fl(fl(float(acc) * sx[m]) * sw[n]) + bias[n] ; ReLU ; + residual
+// and optionally the per-row abs-max requant (a10).  For the requant the CTAs that share a row group form a
+// thread-block cluster and exchange their per-row maxima through distributed shared memory, so the
+// fp32 tensor never touches HBM.  Fault hooks (App. D) patch the accumulator / output of the one
+// affected row or column in the epilogue.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <mutex>
+#include <unordered_map>
+
+#include "ot_common.h"
+#include "ot_ptx.cuh"
+
+namespace ot {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 128;  // int8 elements == bytes: one 128-byte swizzle row
+constexpr int kUmmaK = 32;    // kind::i8 consumes 32 bytes of K per instruction
+constexpr int kGemmThreads = 192;
+constexpr int kMaxCluster = 8;
+
+struct GemmArgs {
+  int M, N, K;
+  const int8_t* A;
+  int64_t lda;
+  const int8_t* W;  // int8 [N,K] (w8) or packed nibbles [N,K/2] (w4)
+  int64_t ldw;
+  const float* row_scale;
+  const float* col_scale;
+  const float* bias;
+  const float* residual;
+  int64_t ldr;
+  int relu;
+  int out_kind;
+  void* out;
+  int64_t ldo;
+  float* out_scale;
+  int cluster_n;  // CTAs per quant group (OT_OUT_Q8), else 1
+  int w4;         // W is int4-packed: unpack in shared memory
+  OtFault fault;
+};
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = kBlockM * kBlockK;
+  static constexpr int B_BYTES = BLOCK_N * kBlockK;
+  static constexpr int B4_BYTES = BLOCK_N * kBlockK / 2;  // packed int4 staging (w4 path)
+  static constexpr int TILE_BYTES = STAGES * (A_BYTES + B_BYTES);
+  static constexpr int BAR_OFF = TILE_BYTES;                       // full[S], empty[S], tmem_full, unpacked[S]
+  static constexpr int SLOT_OFF = BAR_OFF + (3 * STAGES + 1) * 8;  // TMEM base address slot
+  static constexpr int ROWMAX_OFF = SLOT_OFF + 16;                 // float [kMaxCluster][128]
+  static constexpr int B4_OFF = ROWMAX_OFF + kMaxCluster * kBlockM * 4;
+  static constexpr int TOTAL_W8 = B4_OFF + 1024;  // + slack for the 1024-byte alignment of the tile base
+  static constexpr int TOTAL_W4 = B4_OFF + STAGES * B4_BYTES + 1024;
+};
+
+// Fault context resolved once per thread.
+struct FaultCtx {
+  int mode;
+  int row;    // affected output row   (INPUT) / row of the flipped output element
+  int col;    // affected output column (WEIGHT) / column of the flipped output element
+  int k;      // contraction index of the flipped operand element
+  int delta;  // q' - q
+  int w0, w1; // affected window [w0, w1) along columns (INPUT) or rows (WEIGHT)
+};
+
+__device__ __forceinline__ int load_w_elem(const GemmArgs& g, int n, int k) {
+  if (!g.w4) return g.W[static_cast<int64_t>(n) * g.ldw + k];
+  uint8_t byte = reinterpret_cast<const uint8_t*>(g.W)[static_cast<int64_t>(n) * g.ldw + (k >> 1)];
+  int nib = (k & 1) ? (byte >> 4) : (byte & 0xF);
+  return (nib ^ 8) - 8;
+}
+
+__device__ __forceinline__ FaultCtx resolve_fault(const GemmArgs& g) {
+  FaultCtx f;
+  f.mode = g.fault.mode;
+  f.row = f.col = f.k = -1;
+  f.delta = 0;
+  f.w0 = 0;
+  f.w1 = 0;
+  if (f.mode == OT_FAULT_INPUT) {
+    f.row = static_cast<int>(g.fault.flat_index / g.K);
+    f.k = static_cast<int>(g.fault.flat_index % g.K);
+    int q = g.A[static_cast<int64_t>(f.row) * g.lda + f.k];
+    f.delta = flip_int8_bit(q, g.fault.bit) - q;
+    f.w0 = g.fault.window_len > 0 ? g.fault.window_start : 0;
+    f.w1 = g.fault.window_len > 0 ? min(g.N, g.fault.window_start + g.fault.window_len) : g.N;
+  } else if (f.mode == OT_FAULT_WEIGHT) {
+    f.col = static_cast<int>(g.fault.flat_index / g.K);
+    f.k = static_cast<int>(g.fault.flat_index % g.K);
+    int q = load_w_elem(g, f.col, f.k);
+    f.delta = flip_int8_bit(q, g.fault.bit) - q;
+    f.w0 = g.fault.window_len > 0 ? g.fault.window_start : 0;
+    f.w1 = g.fault.window_len > 0 ? min(g.M, g.fault.window_start + g.fault.window_len) : g.M;
+  } else if (f.mode != OT_FAULT_NONE) {
+    f.row = static_cast<int>(g.fault.flat_index / g.N);
+    f.col = static_cast<int>(g.fault.flat_index % g.N);
+  }
+  return f;
+}
+
+// Integer-domain operand faults: acc[i,j] += (q'-q) * other_operand (SURVEY.md App. D, rank-1 update).
+__device__ __forceinline__ void patch_acc(const GemmArgs& g, const FaultCtx& f, int row, int col0, int (&acc)[32]) {
+  if (f.mode == OT_FAULT_INPUT) {
+    if (row != f.row) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      int col = col0 + j;
+      if (col >= f.w0 && col < f.w1) acc[j] += f.delta * load_w_elem(g, col, f.k);
+    }
+  } else if (f.mode == OT_FAULT_WEIGHT) {
+    if (f.col < col0 || f.col >= col0 + 32 || row < f.w0 || row >= f.w1) return;
+    int a = g.A[static_cast<int64_t>(row) * g.lda + f.k];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j == f.col) acc[j] += a * f.delta;
+  } else if (f.mode == OT_FAULT_ACC_BITFLIP) {
+    if (row != f.row || f.col < col0 || f.col >= col0 + 32) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j == f.col) acc[j] ^= (1 << g.fault.bit);
+  }
+}
+
+// fp32 output faults on the MatMul result (before the bias Add): inject_utils/layers.py:18-33.
+__device__ __forceinline__ float patch_out(const GemmArgs& g, const FaultCtx& f, int row, int col, float v) {
+  if (row != f.row || col != f.col) return v;
+  uint32_t bits = __float_as_uint(v);
+  if (f.mode == OT_FAULT_RANDOM_BITFLIP) bits ^= (1u << g.fault.bit);
+  else if (f.mode == OT_FAULT_RANDOM) bits = g.fault.value_bits;
+  else return v;
+  float r = __uint_as_float(bits);
+  return (r != r) ? 0.0f : r;  // NaN -> 0 (bin2fp32)
+}
+
+// y = fl(fl(float(acc)*sx)*sw) [fault] + bias ; relu ; + residual   -- no FMA contraction anywhere.
+__device__ __forceinline__ float dequant_one(const GemmArgs& g, const FaultCtx& f, int acc, float sx, int row, int col) {
+  float v = __int2float_rn(acc);
+  v = __fmul_rn(v, sx);
+  if (g.col_scale) v = __fmul_rn(v, __ldg(g.col_scale + col));
+  if (f.mode >= OT_FAULT_RANDOM_BITFLIP) v = patch_out(g, f, row, col, v);
+  if (g.bias) v = __fadd_rn(v, __ldg(g.bias + col));
+  if (g.relu) v = fmaxf(v, 0.0f);
+  if (g.residual) v = __fadd_rn(__ldg(g.residual + static_cast<int64_t>(row) * g.ldr + col), v);
+  return v;
+}
+
+template <int BLOCK_N, int STAGES, bool W4>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs g) {
+  using L = GemmSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * L::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint64_t* unpacked_bar = bars + 2 * STAGES + 1;  // w4 only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::SLOT_OFF);
+  float* rowmax_x = reinterpret_cast<float*>(smem + L::ROWMAX_OFF);
+  uint8_t* sB4 = smem + L::B4_OFF;
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) / 32, 0);
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x;
+  const int m_blk = blockIdx.y;
+  const int num_k_blocks = (g.K + kBlockK - 1) / kBlockK;
+
+  if (warp_idx == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp_idx == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+        mbar_init(smem_u32(&unpacked_bar[s]), 128);
+      }
+      mbar_init(smem_u32(tmem_full_bar), 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  // With a cluster, every CTA must have started before its shared memory is written remotely.
+  if (g.cluster_n > 1) cluster_sync_all();
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        if (W4) {
+          mbar_arrive_expect_tx(fb, L::A_BYTES + L::B4_BYTES);
+          tma_load_2d(smem_u32(sA + s * L::A_BYTES), &tmap_a, fb, kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d(smem_u32(sB4 + s * L::B4_BYTES), &tmap_b, fb, kb * (kBlockK / 2), n_blk * BLOCK_N);
+        } else {
+          mbar_arrive_expect_tx(fb, L::A_BYTES + L::B_BYTES);
+          tma_load_2d(smem_u32(sA + s * L::A_BYTES), &tmap_a, fb, kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d(smem_u32(sB + s * L::B_BYTES), &tmap_b, fb, kb * kBlockK, n_blk * BLOCK_N);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_i8(kBlockM, BLOCK_N);
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        if (W4) mbar_wait(smem_u32(&unpacked_bar[s]), phase);
+        else mbar_wait(smem_u32(&full_bar[s]), phase);
+        tc_fence_after();
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + s * L::A_BYTES));
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sB + s * L::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          // advancing K inside the 128-byte swizzle atom = +32 bytes on the (>>4 encoded) start address
+          mma_i8_ss(tmem_base, a_desc + static_cast<uint64_t>(k * (kUmmaK >> 4)),
+                    b_desc + static_cast<uint64_t>(k * (kUmmaK >> 4)), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        mma_commit(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs have read it
+      }
+      mma_commit(smem_u32(tmem_full_bar));    // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (also the int4 unpackers) =====================
+    const int quarter = warp_idx & 3;                   // TMEM lanes this warp may touch: [32q, 32q+32)
+    const int row_in_tile = quarter * 32 + lane;
+    const int row = m_blk * kBlockM + row_in_tile;
+    const bool row_ok = row < g.M;
+    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+
+    if (W4) {
+      // Unpack packed int4 weights (low nibble = even k) to int8 directly into the swizzled MMA layout.
+      // One epilogue thread handles 16 packed bytes (32 k-values) at a time = two 16-byte int8 chunks.
+      const int t = (warp_idx - 2) * 32 + lane;  // 0..127
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), phase);
+        const uint8_t* src = sB4 + s * L::B4_BYTES;  // [BLOCK_N][64] bytes, dense (no swizzle: 64-byte rows)
+        uint8_t* dst = sB + s * L::B_BYTES;
+        for (int item = t; item < BLOCK_N * 4; item += 128) {
+          const int n = item >> 2;        // weight row within the tile
+          const int c = item & 3;         // 16-byte packed chunk -> int8 chunks 2c, 2c+1
+          const uint4 p = *reinterpret_cast<const uint4*>(src + n * 64 + c * 16);
+          const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+          uint32_t o[8];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            // 8 nibbles -> 8 sign-extended bytes: (nib ^ 8) - 8 per byte
+            uint32_t lo = pw[w] & 0x0F0F0F0Fu;          // even k
+            uint32_t hi = (pw[w] >> 4) & 0x0F0F0F0Fu;   // odd k
+            lo = __vsub4(lo ^ 0x08080808u, 0x08080808u);
+            hi = __vsub4(hi ^ 0x08080808u, 0x08080808u);
+            // interleave bytes: k order = lo0,hi0,lo1,hi1 | lo2,hi2,lo3,hi3
+            o[2 * w] = __byte_perm(lo, hi, 0x5140);
+            o[2 * w + 1] = __byte_perm(lo, hi, 0x7362);
+          }
+          // 128B swizzle: 16-byte chunk index is XORed with (row % 8)
+          const int ch0 = (2 * c) ^ (n & 7);
+          const int ch1 = (2 * c + 1) ^ (n & 7);
+          *reinterpret_cast<uint4*>(dst + n * 128 + ch0 * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(dst + n * 128 + ch1 * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(smem_u32(&unpacked_bar[s]));
+      }
+    }
+
+    mbar_wait(smem_u32(tmem_full_bar), 0);
+    tc_fence_after();
+
+    const FaultCtx f = resolve_fault(g);
+    const float sx = (g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f;
+    const int col_base = n_blk * BLOCK_N;
+
+    if (g.out_kind == OT_OUT_I32) {
+      int* out = reinterpret_cast<int*>(g.out);
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr_row + c, r);
+        tmem_wait_ld();
+        int acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = static_cast<int>(r[j]);
+        if (f.mode != OT_FAULT_NONE && row_ok) patch_acc(g, f, row, col_base + c, acc);
+        if (row_ok) {
+          int4* dst = reinterpret_cast<int4*>(out + static_cast<int64_t>(row) * g.ldo + col_base + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_int4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+      }
+    } else if (g.out_kind == OT_OUT_F32) {
+      float* out = reinterpret_cast<float*>(g.out);
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr_row + c, r);
+        tmem_wait_ld();
+        int acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = static_cast<int>(r[j]);
+        if (f.mode != OT_FAULT_NONE && row_ok) patch_acc(g, f, row, col_base + c, acc);
+        if (row_ok) {
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = dequant_one(g, f, acc[j], sx, row, col_base + c + j);
+          float4* dst = reinterpret_cast<float4*>(out + static_cast<int64_t>(row) * g.ldo + col_base + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        }
+      }
+    } else {
+      // OT_OUT_Q8, pass 1: per-row abs-max over this CTA's BLOCK_N columns, broadcast to the cluster.
+      float amax = 0.0f;
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr_row + c, r);
+        tmem_wait_ld();
+        int acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = static_cast<int>(r[j]);
+        if (f.mode != OT_FAULT_NONE && row_ok) patch_acc(g, f, row, col_base + c, acc);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(dequant_one(g, f, acc[j], sx, row, col_base + c + j)));
+        }
+      }
+      const uint32_t my_rank = g.cluster_n > 1 ? cluster_ctarank() : 0u;
+      const uint32_t slot = smem_u32(rowmax_x + my_rank * kBlockM + row_in_tile);
+      if (g.cluster_n > 1) {
+        for (int peer = 0; peer < g.cluster_n; ++peer) st_shared_cluster_f32(mapa_shared(slot, peer), amax);
+      } else {
+        rowmax_x[row_in_tile] = amax;
+      }
+    }
+  }
+
+  if (g.out_kind == OT_OUT_Q8) {
+    // every thread of every CTA in the cluster: make the row maxima visible
+    if (g.cluster_n > 1) cluster_sync_all();
+    else __syncthreads();
+
+    if (warp_idx >= 2) {
+      const int quarter = warp_idx & 3;
+      const int row_in_tile = quarter * 32 + lane;
+      const int row = m_blk * kBlockM + row_in_tile;
+      const bool row_ok = row < g.M;
+      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      const FaultCtx f = resolve_fault(g);
+      const float sx = (g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f;
+      const int col_base = n_blk * BLOCK_N;
+
+      float amax = 0.0f;
+      for (int p = 0; p < g.cluster_n; ++p) amax = fmaxf(amax, rowmax_x[p * kBlockM + row_in_tile]);
+      // RowQuant (quant_linear.py:31-43): s = max(amax, 1e-5)/127 ; q = rint(y / s)
+      const float s = __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f);
+      const int group = n_blk / g.cluster_n;
+      const int groups_per_row = (g.N / BLOCK_N) / g.cluster_n;
+      if (row_ok && (n_blk % g.cluster_n) == 0) g.out_scale[static_cast<int64_t>(row) * groups_per_row + group] = s;
+
+      int8_t* out = reinterpret_cast<int8_t*>(g.out);
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr_row + c, r);
+        tmem_wait_ld();
+        int acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = static_cast<int>(r[j]);
+        if (f.mode != OT_FAULT_NONE && row_ok) patch_acc(g, f, row, col_base + c, acc);
+        if (row_ok) {
+          uint32_t packed[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const float y = dequant_one(g, f, acc[4 * j + b], sx, row, col_base + c + 4 * j + b);
+              const int q = __float2int_rn(rintf(__fdiv_rn(y, s)));
+              w |= (static_cast<uint32_t>(q) & 0xFFu) << (8 * b);
+            }
+            packed[j] = w;
+          }
+          uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * g.ldo + col_base + c);
+          dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows, box_cols;
+  int swizzle;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && swizzle == o.swizzle;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1315423911u ^ k.rows;
+    h = h * 1315423911u ^ k.cols;
+    h = h * 1315423911u ^ k.ld;
+    h = h * 1315423911u ^ (static_cast<size_t>(k.box_rows) << 20 | k.box_cols << 4 | k.swizzle);
+    return h;
+  }
+};
+
+// 2-D byte tensor [rows, cols] with row pitch ld; box = [box_rows, box_cols]; cached per (ptr, shape).
+static int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                          uint32_t box_cols, bool swizzle128) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, rows, cols, ld, box_rows, box_cols, swizzle128 ? 1 : 0};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return OT_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return OT_ECUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %llu cols %llu ld %llu box %u x %u)", (int)r, ptr,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+    return OT_ECUDA;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return OT_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool W4>
+static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
+  using L = GemmSmem<BLOCK_N, STAGES>;
+  CUtensorMap ta, tb;
+  int rc = get_tensor_map(&ta, g.A, g.M, g.K, g.lda, kBlockM, kBlockK, true);
+  if (rc) return rc;
+  if (W4) rc = get_tensor_map(&tb, g.W, g.N, g.K / 2, g.ldw, BLOCK_N, kBlockK / 2, false);
+  else rc = get_tensor_map(&tb, g.W, g.N, g.K, g.ldw, BLOCK_N, kBlockK, true);
+  if (rc) return rc;
+
+  auto kernel = gemm_i8_kernel<BLOCK_N, STAGES, W4>;
+  const int smem = W4 ? L::TOTAL_W4 : L::TOTAL_W8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.N / BLOCK_N, (g.M + kBlockM - 1) / kBlockM, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = g.cluster_n;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, g));
+  count_launch();
+  return OT_OK;
+}
+
+template <bool W4>
+static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
+  const int m_tiles = (g.M + kBlockM - 1) / kBlockM;
+  int block_n;
+  if (g.out_kind == OT_OUT_Q8) {
+    // the CTAs of one quant group form a cluster of <= 8: BLOCK_N >= group/8; prefer more CTAs when M is small
+    OT_REQUIRE(quant_group > 0 && g.N % quant_group == 0, "quant_group must divide N");
+    OT_REQUIRE(quant_group % 64 == 0 && quant_group <= 2048, "quant_group must be a multiple of 64 and <= 2048");
+    // largest admissible BLOCK_N that still gives >= one CTA per SM; for tiny M the smallest admissible one
+    int best = -1;
+    for (int bn : {256, 128, 64, 32}) {
+      if (quant_group % bn != 0 || quant_group / bn > kMaxCluster) continue;
+      best = bn;
+      if (static_cast<int64_t>(m_tiles) * (g.N / bn) >= 148) break;
+    }
+    OT_REQUIRE(best > 0, "no admissible tile for quant_group");
+    block_n = best;
+    g.cluster_n = quant_group / block_n;
+  } else {
+    int best = 32;
+    for (int bn : {256, 128, 64, 32}) {
+      if (g.N % bn != 0) continue;
+      best = bn;
+      if (static_cast<int64_t>(m_tiles) * (g.N / bn) >= 148) break;
+    }
+    block_n = best;
+    g.cluster_n = 1;
+  }
+  switch (block_n) {
+    case 256: return launch_gemm<256, 3, W4>(g, stream);
+    case 128: return launch_gemm<128, 4, W4>(g, stream);
+    case 64: return launch_gemm<64, 4, W4>(g, stream);
+    default: return launch_gemm<32, 4, W4>(g, stream);
+  }
+}
+
+static int linear_common(bool w4, const int8_t* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                         const float* row_scale, const float* col_scale, const float* bias, const float* residual, int64_t ldr,
+                         int relu, int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group, const OtFault* fault,
+                         void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(A && W && out, "null operand");
+  OT_REQUIRE(M > 0 && N > 0 && K > 0, "empty problem");
+  OT_REQUIRE(N % 32 == 0, "N must be a multiple of 32");
+  OT_REQUIRE(K % 16 == 0 && lda % 16 == 0 && ldw % 16 == 0, "K and row pitches must be multiples of 16 bytes (TMA)");
+  OT_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "operands must be 16-byte aligned");
+  OT_REQUIRE(out_kind >= OT_OUT_I32 && out_kind <= OT_OUT_Q8, "bad out_kind");
+  OT_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
+  if (out_kind == OT_OUT_Q8) {
+    OT_REQUIRE(out_scale != nullptr, "OT_OUT_Q8 needs out_scale");
+    OT_REQUIRE(ldo % 16 == 0, "int8 out pitch must be a multiple of 16");
+  } else {
+    OT_REQUIRE(ldo % 4 == 0, "out pitch must be a multiple of 4 elements");
+  }
+  if (w4) OT_REQUIRE(K % 32 == 0, "w4 needs K % 32 == 0");
+  GemmArgs g = {};
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = lda;
+  g.W = reinterpret_cast<const int8_t*>(W); g.ldw = ldw;
+  g.row_scale = row_scale; g.col_scale = col_scale; g.bias = bias;
+  g.residual = residual; g.ldr = ldr;
+  g.relu = relu; g.out_kind = out_kind;
+  g.out = out; g.ldo = ldo; g.out_scale = out_scale;
+  g.cluster_n = 1;
+  g.w4 = w4 ? 1 : 0;
+  if (fault) {
+    g.fault = *fault;
+    if (fault->mode == OT_FAULT_INPUT) OT_REQUIRE(fault->flat_index >= 0 && fault->flat_index < (int64_t)M * K && fault->bit >= 0 && fault->bit < 8, "INPUT fault out of range");
+    if (fault->mode == OT_FAULT_WEIGHT) OT_REQUIRE(fault->flat_index >= 0 && fault->flat_index < (int64_t)N * K && fault->bit >= 0 && fault->bit < 8, "WEIGHT fault out of range");
+    if (fault->mode >= OT_FAULT_RANDOM_BITFLIP) OT_REQUIRE(fault->flat_index >= 0 && fault->flat_index < (int64_t)M * N && fault->bit >= 0 && fault->bit < 32, "output fault out of range");
+  } else {
+    g.fault.mode = OT_FAULT_NONE;
+  }
+  cudaStream_t s = as_stream(stream);
+  return w4 ? dispatch_gemm<true>(g, quant_group, s) : dispatch_gemm<false>(g, quant_group, s);
+}
+
+}  // namespace ot
+
+extern "C" int ot_linear_w8a8(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K,
+                              const float* row_scale, const float* col_scale, const float* bias, const float* residual,
+                              int64_t ldr, int relu, int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group,
+                              const OtFault* fault, void* stream) {
+  return ot::linear_common(false, A, lda, W, ldw, M, N, K, row_scale, col_scale, bias, residual, ldr, relu, out_kind, out, ldo,
+                           out_scale, quant_group, fault, stream);
+}
+
+extern "C" int ot_linear_w4a8(const int8_t* A, int64_t lda, const uint8_t* W4, int64_t ldw, int M, int N, int K,
+                              const float* row_scale, const float* col_scale, const float* bias, const float* residual,
+                              int64_t ldr, int relu, int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group,
+                              const OtFault* fault, void* stream) {
+  return ot::linear_common(true, A, lda, W4, ldw, M, N, K, row_scale, col_scale, bias, residual, ldr, relu, out_kind, out, ldo,
+                           out_scale, quant_group, fault, stream);
+}

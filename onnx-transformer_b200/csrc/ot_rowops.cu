@@ -1,0 +1,258 @@
+// Row-local, HBM-bound kernels: LayerNorm(+quant), RowQuant, residual Add, embedding+PE, int4 unpack,
+// greedy-loop token append.  One warp per row, 128-bit coalesced accesses, warp-shuffle reductions.
+// fp32 op order follows SURVEY.md App. A (the order of the ops the reference exports); compiled with
+// -fmad=false, explicit *_rn intrinsics where the order matters for bit-exact integer results.
+#include "ot_common.h"
+
+namespace ot {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// RowQuant of quant_linear.py:31-43: s = max(amax, 1e-5) / 127 ; q = rint(x / s).
+__device__ __forceinline__ float quant_scale(float amax) { return __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f); }
+__device__ __forceinline__ int quant_one(float x, float s) { return __float2int_rn(rintf(__fdiv_rn(x, s))); }
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+  return (static_cast<uint32_t>(a) & 0xFFu) | ((static_cast<uint32_t>(b) & 0xFFu) << 8) |
+         ((static_cast<uint32_t>(c) & 0xFFu) << 16) | ((static_cast<uint32_t>(d) & 0xFFu) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (layer_norm.py:12-15 as exported): mu = mean(x); d = x-mu; v = mean(d*d)*n/(n-1);
+// y = (a*d)/(sqrt(v)+eps) + b ; optional RowQuant of y.   VEC = n / 128 float4 per lane.
+template <int VEC>
+__global__ void __launch_bounds__(256) layernorm_quant_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int64_t rows, int n, float eps,
+                                                              float* __restrict__ y_out, int8_t* __restrict__ q_out,
+                                                              float* __restrict__ s_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * n);
+  float4 v[VEC];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = __ldg(xr + i * 32 + lane);
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float nf = static_cast<float>(n);
+  const float mu = __fdiv_rn(warp_sum(sum), nf);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i].x = __fsub_rn(v[i].x, mu);
+    v[i].y = __fsub_rn(v[i].y, mu);
+    v[i].z = __fsub_rn(v[i].z, mu);
+    v[i].w = __fsub_rn(v[i].w, mu);
+    sq += (__fmul_rn(v[i].x, v[i].x) + __fmul_rn(v[i].y, v[i].y)) + (__fmul_rn(v[i].z, v[i].z) + __fmul_rn(v[i].w, v[i].w));
+  }
+  float var = __fdiv_rn(warp_sum(sq), nf);                    // ReduceMean(d*d)
+  var = __fdiv_rn(__fmul_rn(var, nf), nf - 1.0f);            // * N / (N-1)
+  const float denom = __fadd_rn(__fsqrt_rn(var), eps);       // sqrt + eps (eps added to std)
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 g = __ldg(g4 + i * 32 + lane);
+    const float4 b = __ldg(b4 + i * 32 + lane);
+    v[i].x = __fadd_rn(__fdiv_rn(__fmul_rn(g.x, v[i].x), denom), b.x);
+    v[i].y = __fadd_rn(__fdiv_rn(__fmul_rn(g.y, v[i].y), denom), b.y);
+    v[i].z = __fadd_rn(__fdiv_rn(__fmul_rn(g.z, v[i].z), denom), b.z);
+    v[i].w = __fadd_rn(__fdiv_rn(__fmul_rn(g.w, v[i].w), denom), b.w);
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+  }
+  if (y_out) {
+    float4* yr = reinterpret_cast<float4*>(y_out + row * n);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) yr[i * 32 + lane] = v[i];
+  }
+  if (q_out) {
+    const float s = quant_scale(warp_max(amax));
+    uint32_t* qr = reinterpret_cast<uint32_t*>(q_out + row * n);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      qr[i * 32 + lane] = pack4(quant_one(v[i].x, s), quant_one(v[i].y, s), quant_one(v[i].z, s), quant_one(v[i].w, s));
+    if (lane == 0) s_out[row] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RowQuant over groups of `group` columns; one warp per (row, group); two passes over L1/L2-resident data.
+__global__ void __launch_bounds__(256) rowquant_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int n, int group,
+                                                       int8_t* __restrict__ q, float* __restrict__ s_out,
+                                                       float* __restrict__ xhat) {
+  const int lane = threadIdx.x & 31;
+  const int groups = n / group;
+  const int64_t item = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= rows * groups) return;
+  const int64_t row = item / groups;
+  const int gidx = static_cast<int>(item % groups);
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx + static_cast<int64_t>(gidx) * group);
+  const int nvec = group >> 2;
+  float amax = 0.f;
+  for (int i = lane; i < nvec; i += 32) {
+    const float4 v = __ldg(xr + i);
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  const float s = quant_scale(warp_max(amax));
+  uint32_t* qr = reinterpret_cast<uint32_t*>(q + row * n + static_cast<int64_t>(gidx) * group);
+  float4* hr = xhat ? reinterpret_cast<float4*>(xhat + row * n + static_cast<int64_t>(gidx) * group) : nullptr;
+  for (int i = lane; i < nvec; i += 32) {
+    const float4 v = __ldg(xr + i);
+    const int a = quant_one(v.x, s), b = quant_one(v.y, s), c = quant_one(v.z, s), d = quant_one(v.w, s);
+    qr[i] = pack4(a, b, c, d);
+    if (hr) hr[i] = make_float4(__fmul_rn(__int2float_rn(a), s), __fmul_rn(__int2float_rn(b), s),
+                                __fmul_rn(__int2float_rn(c), s), __fmul_rn(__int2float_rn(d), s));
+  }
+  if (lane == 0) s_out[row * groups + gidx] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) residual_add_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                           float4* __restrict__ out, int64_t nvec) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 u = __ldg(a + i), v = __ldg(b + i);
+    out[i] = make_float4(__fadd_rn(u.x, v.x), __fadd_rn(u.y, v.y), __fadd_rn(u.z, v.z), __fadd_rn(u.w, v.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[r,:] = table[id_r,:] * scale + pe[pos_r,:]   (embeddings.py:13, positional_encodings.py:24)
+__global__ void __launch_bounds__(128) embed_pe_kernel(const int64_t* __restrict__ ids, int64_t ids_stride,
+                                                       const float* __restrict__ table, const float* __restrict__ pe,
+                                                       int64_t rows, int seq_len, int d, int pos0,
+                                                       const int32_t* __restrict__ pos_dev, float scale, float* __restrict__ out) {
+  const int64_t row = blockIdx.x;
+  if (row >= rows) return;
+  const int dyn = pos_dev ? *pos_dev : 0;
+  const int64_t id = pos_dev ? ids[row * ids_stride + dyn] : ids[row * ids_stride];
+  const int pos = (pos_dev ? dyn : pos0) + static_cast<int>(row % seq_len);
+  const float4* t = reinterpret_cast<const float4*>(table + id * d);
+  const float4* p = reinterpret_cast<const float4*>(pe + static_cast<int64_t>(pos) * d);
+  float4* o = reinterpret_cast<float4*>(out + row * d);
+  for (int i = threadIdx.x; i < (d >> 2); i += blockDim.x) {
+    const float4 e = __ldg(t + i), q = __ldg(p + i);
+    o[i] = make_float4(__fadd_rn(__fmul_rn(e.x, scale), q.x), __fadd_rn(__fmul_rn(e.y, scale), q.y),
+                       __fadd_rn(__fmul_rn(e.z, scale), q.z), __fadd_rn(__fmul_rn(e.w, scale), q.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unpack_int4_kernel(const uint8_t* __restrict__ w4, int8_t* __restrict__ w8, int64_t nbytes) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nbytes;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint8_t b = w4[i];
+    const int lo = ((b & 0xF) ^ 8) - 8, hi = ((b >> 4) ^ 8) - 8;
+    reinterpret_cast<uint16_t*>(w8)[i] = static_cast<uint16_t>((lo & 0xFF) | ((hi & 0xFF) << 8));
+  }
+}
+
+// ys[b, step+1] = next[b]; step++  (greedy_decode: parallelized_inject_onnx_transformer.py:753-758)
+__global__ void append_token_kernel(int64_t* __restrict__ ys, int64_t ld, const int64_t* __restrict__ next, int B,
+                                    int32_t* __restrict__ step_dev) {
+  const int step = *step_dev;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) ys[static_cast<int64_t>(b) * ld + step + 1] = next[b];
+  __syncthreads();
+  if (threadIdx.x == 0) *step_dev = step + 1;
+}
+
+}  // namespace ot
+
+using namespace ot;
+
+extern "C" int ot_layernorm_quant(const float* x, const float* gamma, const float* beta, int64_t rows, int n, float eps,
+                                  float* y_out, int8_t* q_out, float* s_out, void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(x && gamma && beta && rows >= 0, "null operand");
+  OT_REQUIRE(n % 128 == 0 && n >= 128 && n <= 2048, "n must be a multiple of 128 in [128, 2048]");
+  OT_REQUIRE((q_out == nullptr) == (s_out == nullptr), "q_out and s_out go together");
+  if (rows == 0) return OT_OK;
+  const int warps = 8;
+  const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
+  cudaStream_t s = as_stream(stream);
+#define OT_LN_CASE(V)                                                                                            \
+  case V:                                                                                                        \
+    layernorm_quant_kernel<V><<<grid, warps * 32, 0, s>>>(x, gamma, beta, rows, n, eps, y_out, q_out, s_out);    \
+    break;
+  switch (n / 128) {
+    OT_LN_CASE(1) OT_LN_CASE(2) OT_LN_CASE(3) OT_LN_CASE(4) OT_LN_CASE(5) OT_LN_CASE(6) OT_LN_CASE(7) OT_LN_CASE(8)
+    OT_LN_CASE(9) OT_LN_CASE(10) OT_LN_CASE(11) OT_LN_CASE(12) OT_LN_CASE(13) OT_LN_CASE(14) OT_LN_CASE(15) OT_LN_CASE(16)
+    default: OT_REQUIRE(false, "unsupported n");
+  }
+#undef OT_LN_CASE
+  OT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OT_OK;
+}
+
+extern "C" int ot_rowquant(const float* x, int64_t ldx, int64_t rows, int n, int group, int8_t* q, float* s, float* xhat,
+                           void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(x && q && s && rows >= 0, "null operand");
+  OT_REQUIRE(group > 0 && n % group == 0 && group % 4 == 0 && ldx % 4 == 0, "group must divide n and be a multiple of 4");
+  if (rows == 0) return OT_OK;
+  const int64_t items = rows * (n / group);
+  const int warps = 8;
+  rowquant_kernel<<<static_cast<unsigned>((items + warps - 1) / warps), warps * 32, 0, as_stream(stream)>>>(x, ldx, rows, n, group,
+                                                                                                          q, s, xhat);
+  OT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OT_OK;
+}
+
+extern "C" int ot_residual_add(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(a && b && out && n >= 0 && n % 4 == 0, "n must be a multiple of 4");
+  if (n == 0) return OT_OK;
+  const int64_t nvec = n / 4;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>((nvec + 255) / 256, 148 * 16));
+  residual_add_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+                                                           reinterpret_cast<float4*>(out), nvec);
+  OT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OT_OK;
+}
+
+extern "C" int ot_embed_pe(const int64_t* ids, int64_t ids_stride, const float* table, const float* pe, int64_t rows, int seq_len,
+                           int d, int pos0, const int32_t* pos_dev, float scale, float* out, void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(ids && table && pe && out && rows >= 0 && seq_len > 0 && d % 4 == 0, "bad embed_pe arguments");
+  if (rows == 0) return OT_OK;
+  embed_pe_kernel<<<static_cast<unsigned>(rows), 128, 0, as_stream(stream)>>>(ids, ids_stride, table, pe, rows, seq_len, d, pos0,
+                                                                             pos_dev, scale, out);
+  OT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OT_OK;
+}
+
+extern "C" int ot_unpack_int4(const uint8_t* W4, int8_t* W8, int64_t rows, int64_t cols, void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(W4 && W8 && rows >= 0 && cols % 2 == 0, "cols must be even");
+  const int64_t nbytes = rows * cols / 2;
+  if (nbytes == 0) return OT_OK;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>((nbytes + 255) / 256, 148 * 16));
+  unpack_int4_kernel<<<grid, 256, 0, as_stream(stream)>>>(W4, W8, nbytes);
+  OT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OT_OK;
+}
+
+extern "C" int ot_append_token(int64_t* ys, int64_t ld_ys, const int64_t* next_ids, int B, int32_t* step_dev, void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(ys && next_ids && step_dev && B > 0, "bad append_token arguments");
+  append_token_kernel<<<1, 256, 0, as_stream(stream)>>>(ys, ld_ys, next_ids, B, step_dev);
+  OT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OT_OK;
+}

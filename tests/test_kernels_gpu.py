@@ -1,0 +1,267 @@
+"""GPU parity tests of the C-ABI kernels against the numpy oracle (oracle/intexact.py) on identical seeded inputs.
+
+Bars (north star): int32 accumulators and requantized int8 tensors bit-exact; fp32 epilogues bit-exact (same op
+order, no FMA); float reductions (LayerNorm, softmax, P.V) within 1e-3 relative (observed ~1e-6).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import intexact as ox
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    from onnx_transformer_b200 import kernels
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return kernels
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rand_i8(rng, shape):
+    return rng.integers(-127, 128, size=shape, dtype=np.int8)
+
+
+@pytest.mark.parametrize("M,N,K_", [(64, 512, 512), (128, 512, 512), (200, 1536, 512), (64, 2048, 512), (64, 512, 2048),
+                                    (1000, 512, 2048), (4096, 2048, 512), (4096, 512, 2048), (1, 512, 512), (300, 96, 144)])
+def test_gemm_int32_bit_exact(K, M, N, K_):
+    rng = np.random.default_rng(M * 7 + N * 3 + K_)
+    a, w = rand_i8(rng, (M, K_)), rand_i8(rng, (N, K_))
+    out = K.linear_w8a8(dev(a), dev(w), out_kind=K.OUT_I32).cpu().numpy()
+    ref = ox.int_matmul(a, w)
+    assert out.dtype == np.int32 and np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("M,N,K_,relu,res", [(64, 512, 512, False, True), (257, 2048, 512, True, False), (4096, 512, 2048, False, True),
+                                             (64, 1536, 512, False, False)])
+def test_gemm_fp32_epilogue_bit_exact(K, M, N, K_, relu, res):
+    rng = np.random.default_rng(11 + M + N)
+    a, w = rand_i8(rng, (M, K_)), rand_i8(rng, (N, K_))
+    sx = rng.uniform(1e-3, 5e-2, size=M).astype(np.float32)
+    sw = rng.uniform(1e-4, 1e-2, size=N).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    r = rng.normal(size=(M, N)).astype(np.float32) if res else None
+    out = K.linear_w8a8(dev(a), dev(w), row_scale=dev(sx), col_scale=dev(sw), bias=dev(b), residual=dev(r) if res else None, relu=relu,
+                        out_kind=K.OUT_F32).cpu().numpy()
+    ref = ox.linear_w8a8(a, sx, w, sw, b, relu, r)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("M,N,K_,group,relu", [(64, 1536, 512, 512, False), (64, 2048, 512, 2048, True), (4096, 1536, 512, 512, False),
+                                               (4096, 2048, 512, 2048, True), (130, 512, 2048, 512, False), (64, 1024, 512, 512, False)])
+def test_gemm_fused_requant_bit_exact(K, M, N, K_, group, relu):
+    rng = np.random.default_rng(5 + M + N + group)
+    a, w = rand_i8(rng, (M, K_)), rand_i8(rng, (N, K_))
+    sx = rng.uniform(1e-3, 5e-2, size=M).astype(np.float32)
+    sw = rng.uniform(1e-4, 1e-2, size=N).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    q, s = K.linear_w8a8(dev(a), dev(w), row_scale=dev(sx), col_scale=dev(sw), bias=dev(b), relu=relu, out_kind=K.OUT_Q8,
+                         quant_group=group)
+    y = ox.linear_w8a8(a, sx, w, sw, b, relu)
+    qr, sr = ox.group_quant(y, group)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), sr.view(np.uint32))
+    assert np.array_equal(q.cpu().numpy(), qr)
+
+
+def test_gemm_w4_bit_exact(K):
+    rng = np.random.default_rng(3)
+    M, N, K_ = 192, 512, 512
+    a = rand_i8(rng, (M, K_))
+    w = rng.integers(-8, 8, size=(N, K_), dtype=np.int8)
+    packed = ((w[:, 0::2].astype(np.uint8) & 0xF) | ((w[:, 1::2].astype(np.uint8) & 0xF) << 4)).astype(np.uint8)
+    assert np.array_equal(K.unpack_int4(dev(packed)).cpu().numpy(), w)
+    out = K.linear_w8a8(dev(a), dev(packed), out_kind=K.OUT_I32, w4=True).cpu().numpy()
+    assert np.array_equal(out, ox.int_matmul(a, w))
+
+
+def test_gemm_faults(K):
+    rng = np.random.default_rng(9)
+    M, N, K_ = 96, 512, 512
+    a, w = rand_i8(rng, (M, K_)), rand_i8(rng, (N, K_))
+    golden = ox.int_matmul(a, w)
+    # INPUT fault at A[i,k], bit 6, 16-column window
+    i, k, bit = 37, 211, 6
+    f = K.make_fault(K.FAULT_INPUT, flat_index=i * K_ + k, bit=bit, window_start=32, window_len=16)
+    out = K.linear_w8a8(dev(a), dev(w), out_kind=K.OUT_I32, fault=f).cpu().numpy()
+    ref = golden.copy()
+    delta = ox.flip_int8_bit(int(a[i, k]), bit) - int(a[i, k])
+    ref[i, 32:48] += delta * w[32:48, k].astype(np.int32)
+    assert np.array_equal(out, ref)
+    # WEIGHT fault at W[n,k], whole column
+    n, k, bit = 300, 5, 7
+    f = K.make_fault(K.FAULT_WEIGHT, flat_index=n * K_ + k, bit=bit)
+    out = K.linear_w8a8(dev(a), dev(w), out_kind=K.OUT_I32, fault=f).cpu().numpy()
+    ref = golden.copy()
+    delta = ox.flip_int8_bit(int(w[n, k]), bit) - int(w[n, k])
+    ref[:, n] += a[:, k].astype(np.int32) * delta
+    assert np.array_equal(out, ref)
+    # RANDOM_BITFLIP on the fp32 MatMul output (before bias)
+    sx = rng.uniform(1e-3, 5e-2, size=M).astype(np.float32)
+    sw = rng.uniform(1e-4, 1e-2, size=N).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    r_, c_, bit = 5, 77, 30
+    f = K.make_fault(K.FAULT_RANDOM_BITFLIP, flat_index=r_ * N + c_, bit=bit)
+    out = K.linear_w8a8(dev(a), dev(w), row_scale=dev(sx), col_scale=dev(sw), bias=dev(b), out_kind=K.OUT_F32, fault=f).cpu().numpy()
+    mm = ox.linear_epilogue(golden, sx, sw)
+    mm[r_, c_] = ox.float32_bit_flip(mm[r_, c_], bit)
+    ref = (mm + b.reshape(1, -1)).astype(np.float32)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("rows,n,group", [(64, 512, 512), (4096, 2048, 2048), (100, 1536, 512), (7, 512, 64)])
+def test_rowquant_bit_exact(K, rows, n, group):
+    rng = np.random.default_rng(rows + n)
+    x = (rng.normal(size=(rows, n)) * rng.uniform(0.01, 10, size=(rows, 1))).astype(np.float32)
+    x[0, :] = 0.0  # clamp path
+    q, s = K.rowquant(dev(x), group)
+    qr, sr = ox.group_quant(x, group)
+    assert np.array_equal(s.cpu().numpy().reshape(rows, -1).view(np.uint32), sr.view(np.uint32))
+    assert np.array_equal(q.cpu().numpy(), qr)
+
+
+def test_layernorm_quant(K):
+    rng = np.random.default_rng(0)
+    rows, n = 777, 512
+    x = rng.normal(size=(rows, n)).astype(np.float32) * 3 + 1
+    g = rng.normal(size=n).astype(np.float32)
+    b = rng.normal(size=n).astype(np.float32)
+    y, q, s = K.layernorm_quant(dev(x), dev(g), dev(b), want_y=True, want_q=True)
+    y = y.cpu().numpy()
+    ref = ox.layer_norm(x, g, b)
+    np.testing.assert_allclose(y, ref, rtol=1e-3, atol=1e-5)   # float tolerance class of the north star
+    assert np.max(np.abs(y - ref)) < 1e-5
+    # the fused quantization must be the exact RowQuant of the kernel's own y
+    qr, sr = ox.row_quant(y)
+    assert np.array_equal(q.cpu().numpy(), qr)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), sr.reshape(-1).view(np.uint32))
+
+
+def test_residual_embed(K):
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=(64, 512)).astype(np.float32)
+    b = rng.normal(size=(64, 512)).astype(np.float32)
+    assert np.array_equal(K.residual_add(dev(a), dev(b)).cpu().numpy(), a + b)
+    lut = rng.normal(size=(100, 512)).astype(np.float32)
+    pe = ox.positional_encoding(80)
+    ids = rng.integers(0, 100, size=(4, 9))
+    out = K.embed_pe(dev(ids.reshape(-1)), dev(lut), dev(pe), seq_len=9).cpu().numpy().reshape(4, 9, 512)
+    assert np.array_equal(out, ox.embed(ids, lut, pe))
+
+
+def _attn_inputs(rng, B, Tq, Tk):
+    qq, kq, vq = rand_i8(rng, (B, Tq, 512)), rand_i8(rng, (B, Tk, 512)), rand_i8(rng, (B, Tk, 512))
+    sq = rng.uniform(0.005, 0.02, size=(B, Tq)).astype(np.float32)
+    sk = rng.uniform(0.005, 0.02, size=(B, Tk)).astype(np.float32)
+    sv = rng.uniform(0.005, 0.02, size=(B, Tk)).astype(np.float32)
+    return qq, sq, kq, sk, vq, sv
+
+
+def _check_attn(ctx, pq, ref_ctx, ref_pq, ref_p):
+    diff = pq.astype(np.int32) - ref_pq.astype(np.int32)
+    assert np.max(np.abs(diff)) <= 1
+    bad = diff != 0
+    # any disagreement must sit on a rounding boundary of 127 p (float softmax within tolerance)
+    if bad.any():
+        frac = (ref_p * 127.0)[bad] % 1.0
+        assert np.all(np.abs(frac - 0.5) < 1e-3)
+        assert bad.mean() < 1e-3
+    np.testing.assert_allclose(ctx, ref_ctx, rtol=1e-3, atol=2e-3 if bad.any() else 1e-5)
+
+
+@pytest.mark.parametrize("B,Tq,Tk,mask", [(3, 64, 64, "pad"), (2, 37, 37, "causal"), (2, 1, 50, "none"), (2, 128, 128, "pad"), (5, 1, 72, "pad")])
+def test_attention(K, B, Tq, Tk, mask):
+    rng = np.random.default_rng(B * 100 + Tq + Tk)
+    qq, sq, kq, sk, vq, sv = _attn_inputs(rng, B, Tq, Tk)
+    key_mask = None
+    if mask == "pad":
+        lens = rng.integers(max(1, Tk // 3), Tk + 1, size=B)
+        key_mask = (np.arange(Tk)[None, :] < lens[:, None]).astype(np.uint8)
+    ctx, cq, cs, probs = K.attention_q8(dev(qq), dev(sq), dev(kq), dev(vq), dev(sk), dev(sv), B=B, Tq=Tq, Tk=Tk,
+                                        mask_kind={"none": 0, "pad": 1, "causal": 2}[mask],
+                                        key_mask=dev(key_mask) if key_mask is not None else None,
+                                        want_ctx=True, want_q=True, want_probs=True)
+    ctx = ctx.cpu().numpy().reshape(B, Tq, 512)
+    probs = probs.cpu().numpy()
+    for b in range(B):
+        rc, rpq, rp = ox.attention(qq[b], sq[b], kq[b], sk[b], vq[b], sv[b], key_mask[b] if key_mask is not None else None,
+                                   causal=(mask == "causal"), return_all=True)
+        _check_attn(ctx[b], probs[b], rc, rpq, rp)
+    # fused RowQuant of the context == oracle RowQuant of the kernel's own fp32 context (bit-exact)
+    qr, sr = ox.row_quant(ctx.reshape(B * Tq, 512))
+    assert np.array_equal(cq.cpu().numpy(), qr)
+    assert np.array_equal(cs.cpu().numpy().view(np.uint32), sr.reshape(-1).view(np.uint32))
+
+
+def test_attention_kv_cache_append(K):
+    """Decode-style: Tq=1, cache of capacity 72 holding t keys, the new key/value appended by the kernel."""
+    rng = np.random.default_rng(42)
+    B, cap, t = 4, 72, 17
+    qq, sq, kq, sk, vq, sv = _attn_inputs(rng, B, 1, t + 1)
+    kc = np.zeros((B, cap, 512), np.int8); vc = np.zeros((B, cap, 512), np.int8)
+    skc = np.zeros((B, cap), np.float32); svc = np.zeros((B, cap), np.float32)
+    kc[:, :t], vc[:, :t], skc[:, :t], svc[:, :t] = kq[:, :t], vq[:, :t], sk[:, :t], sv[:, :t]
+    kcd, vcd, skd, svd = dev(kc), dev(vc), dev(skc), dev(svc)
+    step = torch.tensor([t], dtype=torch.int32, device="cuda")
+    ctx, _, _, _ = K.attention_q8(dev(qq), dev(sq), kcd, vcd, skd, svd, B=B, Tq=1, Tk=t + 1, Tk_cap=cap,
+                                  k_new=dev(kq[:, t:]), v_new=dev(vq[:, t:]), sk_new=dev(sk[:, t:]), sv_new=dev(sv[:, t:]), ld_new=512,
+                                  mask_kind=2, step_dev=step)
+    ctx = ctx.cpu().numpy().reshape(B, 1, 512)
+    for b in range(B):
+        rc = ox.attention(qq[b], sq[b], kq[b], sk[b], vq[b], sv[b], causal=True, q_pos0=t)
+        np.testing.assert_allclose(ctx[b], rc, rtol=1e-3, atol=2e-3)
+    assert np.array_equal(kcd.cpu().numpy()[:, t], kq[:, t]) and np.array_equal(vcd.cpu().numpy()[:, t], vq[:, t])
+    assert np.array_equal(skd.cpu().numpy()[:, t], sk[:, t]) and np.array_equal(svd.cpu().numpy()[:, t], sv[:, t])
+
+
+def test_generator_argmax(K):
+    rng = np.random.default_rng(8)
+    rows, d, vocab = 64, 512, 4444
+    h = rng.normal(size=(rows, d)).astype(np.float32)
+    W = (rng.normal(size=(vocab, d)) * 0.05).astype(np.float32)
+    b = rng.normal(size=vocab).astype(np.float32) * 0.1
+    ids, logp, margin, logits = K.generator_argmax(dev(h), dev(W), dev(b), want_logp=True, want_margin=True)
+    ref_ids, ref_logits = ox.generator(h, W, b)
+    np.testing.assert_allclose(logits.cpu().numpy(), ref_logits, rtol=1e-4, atol=1e-4)
+    srt = np.sort(ref_logits, axis=-1)
+    safe = (srt[:, -1] - srt[:, -2]) > 1e-3
+    assert np.array_equal(ids.cpu().numpy()[safe], ref_ids[safe])
+    ref_logp = ref_logits - np.log(np.sum(np.exp(ref_logits - ref_logits.max(-1, keepdims=True)), -1, keepdims=True)) - ref_logits.max(-1, keepdims=True)
+    np.testing.assert_allclose(logp.cpu().numpy(), ref_logp, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(margin.cpu().numpy(), srt[:, -1] - srt[:, -2], atol=1e-4)
+
+
+def test_elementwise_family(K):
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(2, 8, 5, 7)).astype(np.float32)
+    y = rng.normal(size=(1, 8, 1, 7)).astype(np.float32)
+    xd, yd = dev(x), dev(y)
+    assert np.array_equal(K.unary("Abs", xd).cpu().numpy(), np.abs(x))
+    assert np.array_equal(K.unary("Relu", xd).cpu().numpy(), np.maximum(x, 0))
+    assert np.array_equal(K.unary("Round", dev(x * 10)).cpu().numpy(), np.rint(x * 10))
+    assert np.array_equal(K.unary("Sqrt", dev(np.abs(x))).cpu().numpy(), np.sqrt(np.abs(x)))
+    for op, fn in [("Add", np.add), ("Sub", np.subtract), ("Mul", np.multiply), ("Div", np.divide)]:
+        assert np.array_equal(K.binary(op, xd, yd).cpu().numpy(), fn(x, y).astype(np.float32)), op
+        assert np.array_equal(K.binary(op, yd, xd).cpu().numpy(), fn(y, x).astype(np.float32)), op
+    assert np.array_equal(K.clip(xd, 1e-5, 3.4e38).cpu().numpy(), np.clip(x, np.float32(1e-5), np.float32(3.4e38)))
+    assert np.array_equal(K.reduce_last("ReduceMax", dev(np.abs(x))).cpu().numpy(), np.abs(x).max(-1, keepdims=True))
+    np.testing.assert_allclose(K.reduce_last("ReduceMean", xd).cpu().numpy(), x.mean(-1, keepdims=True), rtol=1e-5, atol=1e-6)
+    sm = np.exp(x - x.max(-1, keepdims=True)); sm /= sm.sum(-1, keepdims=True)
+    np.testing.assert_allclose(K.softmax_last(xd).cpu().numpy(), sm, rtol=1e-5, atol=1e-7)
+    cond = rng.integers(0, 2, size=(2, 1, 1, 7)).astype(bool)
+    assert np.array_equal(K.where_scalar(dev(cond), -1e9, xd).cpu().numpy(), np.where(cond, np.float32(-1e9), x))
+    m = rng.integers(0, 2, size=(3, 1, 9)).astype(np.int64)
+    assert np.array_equal(K.equal_scalar_i64(dev(m), 0).cpu().numpy(), m == 0)
+    assert np.array_equal(K.cast(dev(cond), torch.int64).cpu().numpy(), cond.astype(np.int64))
+    assert np.array_equal(K.cast(dev(x * 50), torch.int8).cpu().numpy(), (x * 50).astype(np.int8))
+    assert np.array_equal(K.transpose(xd, (0, 2, 1, 3)).cpu().numpy(), x.transpose(0, 2, 1, 3))
+    assert np.array_equal(K.transpose(xd, (0, 2, 3, 1)).cpu().numpy(), x.transpose(0, 2, 3, 1))
+    a = rng.normal(size=(2, 8, 33, 64)).astype(np.float32)
+    b = rng.normal(size=(2, 8, 64, 47)).astype(np.float32)
+    np.testing.assert_allclose(K.matmul_f32(dev(a), dev(b)).cpu().numpy(), a @ b, rtol=1e-4, atol=1e-4)
+    w = rng.normal(size=(64, 20)).astype(np.float32)
+    np.testing.assert_allclose(K.matmul_f32(dev(a), dev(w)).cpu().numpy(), a @ w, rtol=1e-4, atol=1e-4)
