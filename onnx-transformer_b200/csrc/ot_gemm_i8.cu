@@ -59,8 +59,9 @@ struct GemmSmem {
   static constexpr int TILE_BYTES = STAGES * (A_BYTES + B_BYTES);
   static constexpr int BAR_OFF = TILE_BYTES;                       // full[S], empty[S], tmem_full, unpacked[S]
   static constexpr int SLOT_OFF = BAR_OFF + (3 * STAGES + 1) * 8;  // TMEM base address slot
-  static constexpr int ROWMAX_OFF = SLOT_OFF + 16;                 // float [kMaxCluster][128]
-  static constexpr int B4_OFF = ROWMAX_OFF + kMaxCluster * kBlockM * 4;
+  static constexpr int ROWMAX_OFF = BAR_OFF + 256;                 // float [kMaxCluster][128]
+  static constexpr int B4_OFF = ROWMAX_OFF + kMaxCluster * kBlockM * 4;  // 128-byte aligned (TMA destination)
+  static_assert((3 * STAGES + 1) * 8 + 16 <= 256, "barrier block overflows its 256-byte slot");
   static constexpr int TOTAL_W8 = B4_OFF + 1024;  // + slack for the 1024-byte alignment of the tile base
   static constexpr int TOTAL_W4 = B4_OFF + STAGES * B4_BYTES + 1024;
 };
