@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- decoded tokens/s of the int8 Transformer-base greedy-decode hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port) on host cores
+
+Workload = BASELINE.json configs[1]: 8-bit Transformer-base (6+6 layers, d512, h8, ff2048, vocab 5337/4444),
+random-init weights (seed 0), synthetic source batch of 64 sentences x 64 tokens per GPU, 71 greedy steps.
+A "step" is one pass of the hot path over one batch: encoder + cross-K/V projection + 71 greedy decoder steps ->
+64*71 decoded tokens per GPU.  N > 1: one process per GPU (torchrun), sentences sharded by rank (weak scaling),
+the only collective is the all_gather of the token ids.
+
+One JSON line on rank 0: value (inputs resident in HBM), e2e (host buffers, H2D/D2H inside the timed region),
+roofline of the dominant kernel family (measured live with CUDA events), cpu_baseline (oracle port on the host).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "decoded tokens/s (int8 Transformer-base, bs64)"
+UNIT = "tokens/s"
+B_DEFAULT, S_DEFAULT, MAX_LEN = 64, 64, 72
+
+
+# ----------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def reader():
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+        self.thread = threading.Thread(target=reader, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.samples:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_reference_sample(batch: int, src_len: int, greedy_steps: int, seed: int = 0):
+    """Time the oracle port of the reference algorithm on the host cores: fp32 MatMul of de-quantized operands
+    ("ref-float"), weight fake-quant recomputed every call, decoder re-run on the FULL prefix each step -- exactly
+    the work the reference's executor does, minus its per-node session overhead.  Returns (tokens/s, seconds)."""
+    from onnx_transformer_b200 import weights as W
+    from oracle import model as om
+    fw = W.init_float_weights(seed)
+    w = om.get_quantized(fw, None, 6)
+    ids, mask = W.synthetic_tokens(seed, batch, src_len)
+    t0 = time.perf_counter()
+    om.greedy_decode(w, ids, mask, greedy_steps + 1, 0, "ref-float", 6, kv_cache=False)
+    dt = time.perf_counter() - t0
+    return batch * greedy_steps / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_b, sample_steps = 16, 8
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_sample(2, args.src_len, 2)
+    vals, secs = [], []
+    for _ in range(args.steps):
+        v, dt = cpu_reference_sample(sample_b, args.src_len, sample_steps)
+        vals.append(v); secs.append(dt)
+    value = float(np.mean(vals))
+    sample = ("oracle port (numpy, ref-float, full-prefix recompute, BLAS threads=%d): %d sentences x %d src tokens, first %d of 71 greedy steps "
+              "per timed step; early steps have the shortest prefixes, so this over-states the CPU's full-run rate" % (cores, sample_b, args.src_len, sample_steps))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean(secs) * 1e3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "cfg2: greedy decode, batch 64 x src 64, 71 steps (bounded CPU sample)", "batch": args.batch,
+                                            "src_len": args.src_len, "greedy_steps": MAX_LEN - 1},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- kernel-family probe
+def probe_decode_families(eng, ws, B, S, reps=20):
+    """Average device time (CUDA events on the launching stream) and algorithmic bytes of each kernel family of ONE
+    greedy step at a mid-run prefix length, each family launched back to back in isolation."""
+    import torch
+    from onnx_transformer_b200 import kernels as K
+    D, FF, nl = 512, 2048, eng.n_layers
+    T = 36
+    ws["step"].fill_(T - 1)
+    L = eng.dec[0]
+    x, nxt = ws["x"][0], ws["x"][1]
+    fam = {}
+
+    def timed(name, fn, launches, bytes_per_launch):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (reps * launches)
+        fam[name] = {"us_per_launch": us, "launches_per_step": launches * (nl if name != "generator" else 1), "bytes_per_launch": bytes_per_launch}
+
+    def gemms():
+        eng._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], lambda t: None)
+        K.linear_w8a8(ws["cq"], L["o"].wq, row_scale=ws["cs"], col_scale=L["o"].sw, bias=L["o"].bias, residual=x, out_kind=K.OUT_F32, out=nxt)
+        K.linear_w8a8(ws["xq"], L["cq"].wq, row_scale=ws["sx"], col_scale=L["cq"].sw, bias=L["cq"].bias, out_kind=K.OUT_Q8, quant_group=D,
+                      out=ws["q2"], out_scale=ws["sq2"])
+        K.linear_w8a8(ws["cq"], L["co"].wq, row_scale=ws["cs"], col_scale=L["co"].sw, bias=L["co"].bias, residual=x, out_kind=K.OUT_F32, out=nxt)
+        K.linear_w8a8(ws["xq"], L["w1"].wq, row_scale=ws["sx"], col_scale=L["w1"].sw, bias=L["w1"].bias, relu=True, out_kind=K.OUT_Q8,
+                      quant_group=FF, out=ws["hq"], out_scale=ws["sh"])
+        K.linear_w8a8(ws["hq"], L["w2"].wq, row_scale=ws["sh"], col_scale=L["w2"].sw, bias=L["w2"].bias, residual=x, out_kind=K.OUT_F32, out=nxt)
+
+    # algorithmic bytes of the 6 GEMMs of one decoder layer-step: int8 weights (3,670,016 B) + operands/results
+    w_bytes = 3 * D * D + 3 * D * D + 2 * D * FF
+    io_bytes = B * (D + 3 * D + 3 * 4) + 3 * B * (D + D * 4 + D * 4) - B * D * 4 + B * (D + D + 4) + B * (D + FF + 4) + B * (FF + 2 * D * 4)
+    timed("gemm_i8", gemms, 6, (w_bytes + io_bytes + 4 * (3 * D + 3 * D + FF + D) * 2) / 6.0)
+
+    def attn():
+        K.attention_q8(ws["qkv"], ws["sqkv"], ws["kc"][0], ws["vc"][0], ws["skc"][0], ws["svc"][0], B=B, Tq=1, Tk=1, Tk_cap=eng.max_len,
+                       ldq=3 * D, sq_stride=3, ldk=D, skv_stride=1, k_new=ws["qkv"][:, D:], v_new=ws["qkv"][:, 2 * D:],
+                       sk_new=ws["sqkv"][:, 1:], sv_new=ws["sqkv"][:, 2:], ld_new=3 * D, snew_stride=3, mask_kind=2, step_dev=ws["step"],
+                       want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"])
+        K.attention_q8(ws["q2"], ws["sq2"], ws["ckv"][:, 0:], ws["ckv"][:, D:], ws["sckv"][:, 0:], ws["sckv"][:, 1:], B=B, Tq=1, Tk=S, Tk_cap=S,
+                       ldq=D, sq_stride=1, ldk=2 * D * nl, skv_stride=2 * nl, mask_kind=1, key_mask=ws["mask"], mask_stride=S,
+                       want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"])
+
+    attn_bytes = B * (T * 2 * D + T * 8 + D + 2 * D + D + 4) + B * (S * 2 * D + S * 8 + S + D + D + 4)
+    timed("attention_q8", attn, 2, attn_bytes / 2.0)
+
+    def lns():
+        for key in ("ln1", "ln2", "ln3"):
+            K.layernorm_quant(x, L[key][0], L[key][1], want_q=True, q=ws["xq"], s=ws["sx"])
+
+    timed("layernorm_quant", lns, 3, B * (D * 4 + D + 4) + 2 * D * 4)
+
+    def gen():
+        K.generator_argmax(ws["hout"], eng.gen_w, eng.gen_b, next_ids=ws["next"], scratch=ws["logits"])
+
+    timed("generator", gen, 2, (eng.vocab * D * 4 + B * D * 4 + 2 * B * eng.vocab * 4) / 2.0)
+    ws["step"].zero_()
+    return fam
+
+
+# ----------------------------------------------------------------------------------------------- main (GPU arm)
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=B_DEFAULT)
+    ap.add_argument("--src-len", type=int, default=S_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from onnx_transformer_b200 import kernels as K
+    from onnx_transformer_b200 import weights as W
+    from onnx_transformer_b200.engine import QuantizedTransformer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, S = args.batch, args.src_len
+    eng = QuantizedTransformer(W.init_float_weights(0), n_layers=6, max_len=MAX_LEN)
+    ids_np, mask_np = W.synthetic_tokens(1000 + rank, B, S)          # each rank: its own shard of sentences
+    ids, mask = torch.from_numpy(ids_np).to(dev), torch.from_numpy(mask_np).to(dev)
+    ids_pin, mask_pin = torch.from_numpy(ids_np).pin_memory(), torch.from_numpy(mask_np).pin_memory()
+    ys_pin = torch.empty((B, MAX_LEN), dtype=torch.int64).pin_memory()
+    gathered = torch.empty((world * B, MAX_LEN), dtype=torch.int64, device=dev) if world > 1 else None
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def one_step():
+        ys = eng.greedy_decode(ids, mask)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, ys)   # the path's only collective: result gather
+        return ys
+
+    def one_step_e2e():
+        d_ids = ids_pin.to(dev, non_blocking=True)
+        d_mask = mask_pin.to(dev, non_blocking=True)
+        ys = eng.greedy_decode(d_ids, d_mask)
+        ys_pin.copy_(ys, non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, ys)
+        return ys
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed_loop(fn, steps):
+        total_ms = 0.0
+        for _ in range(steps):
+            flush.zero_()                                # evict L2 between timed iterations (untimed)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            total_ms += e0.elapsed_time(e1)
+        return total_ms
+
+    for _ in range(args.warmup):
+        one_step()
+    sync_all()
+    ws = eng._dec_workspace(B, S)
+    launches_per_graph = ws.get("graph_launches", 0)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0, r0 = K._lib.launch_count(), eng.graph_replays
+    sync_all()
+    total_ms = timed_loop(one_step, args.steps)
+    sync_all()
+    launches = (K._lib.launch_count() - l0) + (eng.graph_replays - r0) * launches_per_graph
+    clocks = sampler.stop()
+    e2e_ms = timed_loop(one_step_e2e, args.steps)
+    sync_all()
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    tokens = world * B * (MAX_LEN - 1) * args.steps
+    value = tokens / (total_ms * 1e-3)
+    e2e_value = tokens / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        fam = probe_decode_families(eng, ws, B, S)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        share = {k: v["us_per_launch"] * v["launches_per_step"] for k, v in fam.items()}
+        dom = max(share, key=share.get)
+        achieved = fam[dom]["bytes_per_launch"] / (fam[dom]["us_per_launch"] * 1e-6) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                    "us_per_launch": fam[dom]["us_per_launch"], "algorithmic_bytes_per_launch": fam[dom]["bytes_per_launch"],
+                    "families_us_per_step": share}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            v, dt = cpu_reference_sample(16, S, 8)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "oracle port (numpy ref-float, full-prefix recompute, %d BLAS threads): 16 sentences x %d src tokens, first 8 of 71 "
+                             "greedy steps, %.1f s" % (cores, S, dt)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+                "data": "synthetic",
+                "config": {"workload": "cfg2: 8-bit Transformer-base greedy decode, batch 64 x src len 64 per GPU, 71 steps, KV cache",
+                           "batch_per_gpu": B, "src_len": S, "greedy_steps": MAX_LEN - 1, "parallelism": "sentence-sharded x%d" % world,
+                           "l2": "512 MB flush between timed iterations"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes + mask_np.nbytes), "d2h_bytes_per_step": int(B * MAX_LEN * 8)},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
