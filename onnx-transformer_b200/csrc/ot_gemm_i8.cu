@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <mutex>
+#include <stdlib.h>
 #include <unordered_map>
 
 #include "ot_common.h"
@@ -60,7 +61,8 @@ struct GemmSmem {
   static constexpr int BAR_OFF = TILE_BYTES;                       // full[S], empty[S], tmem_full, unpacked[S]
   static constexpr int SLOT_OFF = BAR_OFF + (3 * STAGES + 1) * 8;  // TMEM base address slot
   static constexpr int ROWMAX_OFF = BAR_OFF + 256;                 // float [kMaxCluster][128]
-  static constexpr int B4_OFF = ROWMAX_OFF + kMaxCluster * kBlockM * 4;  // 128-byte aligned (TMA destination)
+  static constexpr int COLP_OFF = ROWMAX_OFF + kMaxCluster * kBlockM * 4;  // float col_scale[BLOCK_N], bias[BLOCK_N]
+  static constexpr int B4_OFF = COLP_OFF + 2 * 256 * 4;                    // 128-byte aligned (TMA destination)
   static_assert((3 * STAGES + 1) * 8 + 16 <= 256, "barrier block overflows its 256-byte slot");
   static constexpr int TOTAL_W8 = B4_OFF + 1024;  // + slack for the 1024-byte alignment of the tile base
   static constexpr int TOTAL_W4 = B4_OFF + STAGES * B4_BYTES + 1024;
@@ -83,7 +85,7 @@ __device__ __forceinline__ int load_w_elem(const GemmArgs& g, int n, int k) {
   return (nib ^ 8) - 8;
 }
 
-__device__ __forceinline__ FaultCtx resolve_fault(const GemmArgs& g) {
+__device__ __noinline__ FaultCtx resolve_fault(const GemmArgs& g) {
   FaultCtx f;
   f.mode = g.fault.mode;
   f.row = f.col = f.k = -1;
@@ -112,30 +114,29 @@ __device__ __forceinline__ FaultCtx resolve_fault(const GemmArgs& g) {
 }
 
 // Integer-domain operand faults: acc[i,j] += (q'-q) * other_operand (SURVEY.md App. D, rank-1 update).
-__device__ __forceinline__ void patch_acc(const GemmArgs& g, const FaultCtx& f, int row, int col0, int (&acc)[32]) {
+// Out of line and scalar: the fault path is taken by at most one row / column per launch and must not bloat or slow
+// the fault-free epilogue.
+__device__ __noinline__ int patch_acc_one(const GemmArgs& g, const FaultCtx& f, int row, int col, int acc) {
   if (f.mode == OT_FAULT_INPUT) {
-    if (row != f.row) return;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      int col = col0 + j;
-      if (col >= f.w0 && col < f.w1) acc[j] += f.delta * load_w_elem(g, col, f.k);
-    }
+    if (row == f.row && col >= f.w0 && col < f.w1) acc += f.delta * load_w_elem(g, col, f.k);
   } else if (f.mode == OT_FAULT_WEIGHT) {
-    if (f.col < col0 || f.col >= col0 + 32 || row < f.w0 || row >= f.w1) return;
-    int a = g.A[static_cast<int64_t>(row) * g.lda + f.k];
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j == f.col) acc[j] += a * f.delta;
+    if (col == f.col && row >= f.w0 && row < f.w1) acc += static_cast<int>(g.A[static_cast<int64_t>(row) * g.lda + f.k]) * f.delta;
   } else if (f.mode == OT_FAULT_ACC_BITFLIP) {
-    if (row != f.row || f.col < col0 || f.col >= col0 + 32) return;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j == f.col) acc[j] ^= (1 << g.fault.bit);
+    if (row == f.row && col == f.col) acc ^= (1 << g.fault.bit);
   }
+  return acc;
+}
+template <int CW>
+__device__ __forceinline__ void patch_acc(const GemmArgs& g, const FaultCtx& f, int row, int col0, int (&acc)[CW]) {
+  // only the affected row (INPUT / ACC) or the chunk holding the affected column (WEIGHT) does any work
+  const bool hit = (f.mode == OT_FAULT_WEIGHT) ? (f.col >= col0 && f.col < col0 + CW) : (row == f.row);
+  if (!hit) return;
+#pragma unroll
+  for (int j = 0; j < CW; ++j) acc[j] = patch_acc_one(g, f, row, col0 + j, acc[j]);
 }
 
 // fp32 output faults on the MatMul result (before the bias Add): inject_utils/layers.py:18-33.
-__device__ __forceinline__ float patch_out(const GemmArgs& g, const FaultCtx& f, int row, int col, float v) {
+__device__ __noinline__ float patch_out(const GemmArgs& g, const FaultCtx& f, int row, int col, float v) {
   if (row != f.row || col != f.col) return v;
   uint32_t bits = __float_as_uint(v);
   if (f.mode == OT_FAULT_RANDOM_BITFLIP) bits ^= (1u << g.fault.bit);
@@ -146,15 +147,71 @@ __device__ __forceinline__ float patch_out(const GemmArgs& g, const FaultCtx& f,
 }
 
 // y = fl(fl(float(acc)*sx)*sw) [fault] + bias ; relu ; + residual   -- no FMA contraction anywhere.
-__device__ __forceinline__ float dequant_one(const GemmArgs& g, const FaultCtx& f, int acc, float sx, int row, int col) {
-  float v = __int2float_rn(acc);
-  v = __fmul_rn(v, sx);
-  if (g.col_scale) v = __fmul_rn(v, __ldg(g.col_scale + col));
-  if (f.mode >= OT_FAULT_RANDOM_BITFLIP) v = patch_out(g, f, row, col, v);
-  if (g.bias) v = __fadd_rn(v, __ldg(g.bias + col));
-  if (g.relu) v = fmaxf(v, 0.0f);
-  if (g.residual) v = __fadd_rn(__ldg(g.residual + static_cast<int64_t>(row) * g.ldr + col), v);
-  return v;
+// Column parameters come from shared memory (staged once per CTA); flags are CTA-uniform and applied as selects so the
+// 16 element chains of a chunk stay branch-free and interleave.
+struct EpiFlags {
+  bool has_bias, relu, out_fault;
+};
+
+__device__ __forceinline__ float finish_one(const EpiFlags& e, float v, float bias) {
+  const float vb = __fadd_rn(v, bias);
+  v = e.has_bias ? vb : v;
+  const float vr = fmaxf(v, 0.0f);
+  return e.relu ? vr : v;
+}
+
+// One kCW-column chunk of one accumulator row: TMEM -> registers -> fp32 values y[kCW] (residual included).
+// The chunk is narrow and the chunk loops are NOT unrolled, keeping the executed instruction footprint of a launch small.
+constexpr int kCW = 16;
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const FaultCtx& f, const EpiFlags& e, uint32_t taddr, int row,
+                                               bool row_ok, int col0, int c, const float* s_cs, const float* s_bias, float sx,
+                                               float (&y)[kCW]) {
+  float4 res[kCW / 4];
+  const bool has_res = g.residual != nullptr && row_ok;
+  if (has_res) {
+    const float4* rp = reinterpret_cast<const float4*>(g.residual + static_cast<int64_t>(row) * g.ldr + col0 + c);
+#pragma unroll
+    for (int j = 0; j < kCW / 4; ++j) res[j] = __ldg(rp + j);
+  }
+  uint32_t r[kCW];
+  tmem_ld_32x16(taddr + c, r);
+  tmem_wait_ld();
+  int acc[kCW];
+#pragma unroll
+  for (int j = 0; j < kCW; ++j) acc[j] = static_cast<int>(r[j]);
+  if (f.mode != OT_FAULT_NONE && row_ok) patch_acc<kCW>(g, f, row, col0 + c, acc);
+  float mm[kCW];
+#pragma unroll
+  for (int j = 0; j < kCW; ++j) mm[j] = __fmul_rn(__fmul_rn(__int2float_rn(acc[j]), sx), s_cs[c + j]);   // MatMul_k_out0
+  if (e.out_fault && row == f.row && f.col >= col0 + c && f.col < col0 + c + kCW) {
+#pragma unroll
+    for (int j = 0; j < kCW; ++j)
+      if (col0 + c + j == f.col) mm[j] = patch_out(g, f, row, f.col, mm[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kCW; ++j) y[j] = finish_one(e, mm[j], s_bias[c + j]);
+  if (has_res) {
+#pragma unroll
+    for (int j = 0; j < kCW / 4; ++j) {
+      y[4 * j] = __fadd_rn(res[j].x, y[4 * j]);
+      y[4 * j + 1] = __fadd_rn(res[j].y, y[4 * j + 1]);
+      y[4 * j + 2] = __fadd_rn(res[j].z, y[4 * j + 2]);
+      y[4 * j + 3] = __fadd_rn(res[j].w, y[4 * j + 3]);
+    }
+  }
+}
+
+// rint(y / s) with the quotient rounded exactly like IEEE division, without the per-element div.rn expansion (whose
+// special-case path is taken for every zero dividend -- half of a ReLU output).  q1 = y*r corrected by one FMA residual
+// step (r = RN(1/s)) is within 1 ulp of RN(y/s); the integer result can only differ when q1 sits within 2^-16 of a
+// half-integer, and exactly then the true IEEE division decides.  |y/s| <= 127 by construction of s.
+__device__ __forceinline__ int quant_exact(float y, float s, float r) {
+  const float q0 = __fmul_rn(y, r);
+  const float rem = __fmaf_rn(-q0, s, y);
+  const float q1 = __fmaf_rn(rem, r, q0);
+  float n = rintf(q1);
+  if (fabsf(fabsf(q1 - n) - 0.5f) < 1.52587890625e-05f) n = rintf(__fdiv_rn(y, s));
+  return __float2int_rn(n);
 }
 
 template <int BLOCK_N, int STAGES, bool W4>
@@ -174,6 +231,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* unpacked_bar = bars + 2 * STAGES + 1;  // w4 only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::SLOT_OFF);
   float* rowmax_x = reinterpret_cast<float*>(smem + L::ROWMAX_OFF);
+  float* s_cs = reinterpret_cast<float*>(smem + L::COLP_OFF);
+  float* s_bias = s_cs + 256;
   uint8_t* sB4 = smem + L::B4_OFF;
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) / 32, 0);
@@ -296,64 +355,63 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
 
-    mbar_wait(smem_u32(tmem_full_bar), 0);
-    tc_fence_after();
-
+    // Stage the per-column epilogue parameters once per CTA (overlaps the main loop), then wait for the accumulator.
+    {
+      const int t = (warp_idx - 2) * 32 + lane;
+      for (int c = t; c < BLOCK_N; c += 128) {
+        s_cs[c] = g.col_scale ? __ldg(g.col_scale + n_blk * BLOCK_N + c) : 1.0f;
+        s_bias[c] = g.bias ? __ldg(g.bias + n_blk * BLOCK_N + c) : 0.0f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+    }
     const FaultCtx f = resolve_fault(g);
+    const EpiFlags e = {g.bias != nullptr, g.relu != 0, f.mode == OT_FAULT_RANDOM_BITFLIP || f.mode == OT_FAULT_RANDOM};
     const float sx = (g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f;
     const int col_base = n_blk * BLOCK_N;
 
+    mbar_wait(smem_u32(tmem_full_bar), 0);
+    tc_fence_after();
+
     if (g.out_kind == OT_OUT_I32) {
       int* out = reinterpret_cast<int*>(g.out);
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr_row + c, r);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += kCW) {
+        uint32_t r[kCW];
+        tmem_ld_32x16(taddr_row + c, r);
         tmem_wait_ld();
-        int acc[32];
+        int acc[kCW];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = static_cast<int>(r[j]);
-        if (f.mode != OT_FAULT_NONE && row_ok) patch_acc(g, f, row, col_base + c, acc);
+        for (int j = 0; j < kCW; ++j) acc[j] = static_cast<int>(r[j]);
+        if (f.mode != OT_FAULT_NONE && row_ok) patch_acc<kCW>(g, f, row, col_base + c, acc);
         if (row_ok) {
           int4* dst = reinterpret_cast<int4*>(out + static_cast<int64_t>(row) * g.ldo + col_base + c);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_int4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          for (int j = 0; j < kCW / 4; ++j) dst[j] = make_int4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         }
       }
     } else if (g.out_kind == OT_OUT_F32) {
       float* out = reinterpret_cast<float*>(g.out);
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr_row + c, r);
-        tmem_wait_ld();
-        int acc[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = static_cast<int>(r[j]);
-        if (f.mode != OT_FAULT_NONE && row_ok) patch_acc(g, f, row, col_base + c, acc);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += kCW) {
+        float y[kCW];
+        epilogue_chunk(g, f, e, taddr_row, row, row_ok, col_base, c, s_cs, s_bias, sx, y);
         if (row_ok) {
-          float y[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = dequant_one(g, f, acc[j], sx, row, col_base + c + j);
           float4* dst = reinterpret_cast<float4*>(out + static_cast<int64_t>(row) * g.ldo + col_base + c);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          for (int j = 0; j < kCW / 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
         }
       }
     } else {
       // OT_OUT_Q8, pass 1: per-row abs-max over this CTA's BLOCK_N columns, broadcast to the cluster.
       float amax = 0.0f;
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr_row + c, r);
-        tmem_wait_ld();
-        int acc[32];
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += kCW) {
+        float y[kCW];
+        epilogue_chunk(g, f, e, taddr_row, row, row_ok, col_base, c, s_cs, s_bias, sx, y);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = static_cast<int>(r[j]);
-        if (f.mode != OT_FAULT_NONE && row_ok) patch_acc(g, f, row, col_base + c, acc);
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(dequant_one(g, f, acc[j], sx, row, col_base + c + j)));
-        }
+        for (int j = 0; j < kCW; ++j) amax = fmaxf(amax, fabsf(y[j]));
       }
+      if (!row_ok) amax = 0.0f;
       const uint32_t my_rank = g.cluster_n > 1 ? cluster_ctarank() : 0u;
       const uint32_t slot = smem_u32(rowmax_x + my_rank * kBlockM + row_in_tile);
       if (g.cluster_n > 1) {
@@ -376,6 +434,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool row_ok = row < g.M;
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       const FaultCtx f = resolve_fault(g);
+      const EpiFlags e = {g.bias != nullptr, g.relu != 0, f.mode == OT_FAULT_RANDOM_BITFLIP || f.mode == OT_FAULT_RANDOM};
       const float sx = (g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f;
       const int col_base = n_blk * BLOCK_N;
 
@@ -383,35 +442,29 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int p = 0; p < g.cluster_n; ++p) amax = fmaxf(amax, rowmax_x[p * kBlockM + row_in_tile]);
       // RowQuant (quant_linear.py:31-43): s = max(amax, 1e-5)/127 ; q = rint(y / s)
       const float s = __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f);
+      const float s_rcp = __frcp_rn(s);
       const int group = n_blk / g.cluster_n;
       const int groups_per_row = (g.N / BLOCK_N) / g.cluster_n;
       if (row_ok && (n_blk % g.cluster_n) == 0) g.out_scale[static_cast<int64_t>(row) * groups_per_row + group] = s;
 
       int8_t* out = reinterpret_cast<int8_t*>(g.out);
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr_row + c, r);
-        tmem_wait_ld();
-        int acc[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = static_cast<int>(r[j]);
-        if (f.mode != OT_FAULT_NONE && row_ok) patch_acc(g, f, row, col_base + c, acc);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += kCW) {
+        float y[kCW];
+        epilogue_chunk(g, f, e, taddr_row, row, row_ok, col_base, c, s_cs, s_bias, sx, y);
         if (row_ok) {
-          uint32_t packed[8];
+          uint32_t packed[kCW / 4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < kCW / 4; ++j) {
             uint32_t w = 0;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-              const float y = dequant_one(g, f, acc[4 * j + b], sx, row, col_base + c + 4 * j + b);
-              const int q = __float2int_rn(rintf(__fdiv_rn(y, s)));
+              const int q = quant_exact(y[4 * j + b], s, s_rcp);
               w |= (static_cast<uint32_t>(q) & 0xFFu) << (8 * b);
             }
             packed[j] = w;
           }
-          uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * g.ldo + col_base + c);
-          dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * g.ldo + col_base + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
       }
     }
@@ -559,6 +612,14 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
     }
     block_n = best;
     g.cluster_n = 1;
+  }
+  if (const char* force = getenv("OT_GEMM_FORCE_BN")) {   // tuning / profiling aid only
+    const int bn = atoi(force);
+    if ((bn == 32 || bn == 64 || bn == 128 || bn == 256) && g.N % bn == 0 &&
+        (g.out_kind != OT_OUT_Q8 || (quant_group % bn == 0 && quant_group / bn <= kMaxCluster))) {
+      block_n = bn;
+      g.cluster_n = g.out_kind == OT_OUT_Q8 ? quant_group / bn : 1;
+    }
   }
   switch (block_n) {
     case 256: return launch_gemm<256, 3, W4>(g, stream);

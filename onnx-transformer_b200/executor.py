@@ -1,0 +1,456 @@
+"""Drop-in for the reference's custom node-by-node ONNX executor, served by CUDA handlers.
+
+Same entry points, argument meaning and hook behaviour as onnx_optimized_inference.py:
+    run_module:297  inference:214  execute_node:18  expand_node_inputs_outputs:236  get_weight_dict:273  prepare_inference:282
+(and the `inject_operations.py` variants through `inject_input=` aliases at the bottom).
+
+Differences, all forced by the B200 design:
+  * `weight_dict` values are torch CUDA tensors (numpy inputs are uploaded on entry); every intermediate is still kept
+    under its ONNX tensor name, plus the reference's side-channel key "delta_4d".
+  * a node is not wrapped into a one-node ModelProto + onnxruntime session (onnx_optimized_inference.py:33-54): its
+    op_type selects a handler that launches one kernel of libot_b200.so.  There is no CPU fallback: an op without a
+    CUDA handler raises.
+  * `MatMul` whose operands are de-quantized int8 tensors (Round -> Mul(scale) [-> Transpose]) runs as the tcgen05 int8
+    GEMM with the scales applied in the epilogue (int-exact factorisation); any other MatMul (attention
+    products in the un-fused walk, fault deltas) runs as the fp32 kernel, i.e. literally the reference's arithmetic.
+  * the random draws of the fault hooks can be supplied in inject_parameters["rng_draws"] (faults.Draws).
+  * graph files: `.otg` archives written by save_graph (the reference's .onnx files are not in its snapshot).
+"""
+from __future__ import annotations
+
+import io
+import json
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import faults
+from . import kernels as K
+from .graph import Attribute, Graph, Initializer, Node, ValueInfo
+
+META_KEY = "__ot_int8__"   # side table: tensor name -> int8 provenance (never an ONNX tensor name)
+FLOAT_MAX = 3.4e38          # onnx_optimized_inference.py:252
+
+
+# ---------------------------------------------------------------------------------------------- graph files
+def save_graph(graph: Graph, path: str) -> None:
+    nodes = [dict(name=n.name, op_type=n.op_type, input=n.input, output=n.output,
+                  attribute=[dict(name=a.name, f=a.f, i=a.i, ints=a.ints) for a in n.attribute]) for n in graph.node]
+    meta = dict(name=graph.name, node=nodes, roles=graph.roles,
+                input=[dict(name=v.name, shape=list(v.shape), dtype=v.dtype) for v in graph.input],
+                output=[dict(name=v.name, shape=list(v.shape), dtype=v.dtype) for v in graph.output],
+                value_info=[v.name for v in graph.value_info], initializer=[i.name for i in graph.initializer])
+    arrays = {"init_%d" % k: i.array for k, i in enumerate(graph.initializer)}
+    with open(path, "wb") as f:
+        np.savez(f, __meta__=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **arrays)
+
+
+def load_graph(path: str) -> Graph:
+    with open(path, "rb") as f:
+        z = np.load(io.BytesIO(f.read()))
+    meta = json.loads(bytes(z["__meta__"]).decode())
+    g = Graph(meta["name"])
+    g.node = [Node(n["name"], n["op_type"], list(n["input"]), list(n["output"]),
+                   [Attribute(a["name"], a["f"], a["i"], a["ints"]) for a in n["attribute"]]) for n in meta["node"]]
+    g.roles = meta.get("roles", {})
+    g.input = [ValueInfo(v["name"], tuple(v["shape"]), v["dtype"]) for v in meta["input"]]
+    g.output = [ValueInfo(v["name"], tuple(v["shape"]), v["dtype"]) for v in meta["output"]]
+    g.value_info = [ValueInfo(n, ()) for n in meta["value_info"]]
+    g.initializer = [Initializer(n, z["init_%d" % k]) for k, n in enumerate(meta["initializer"])]
+    return g
+
+
+def _as_graph(module_path_or_graph) -> Graph:
+    if isinstance(module_path_or_graph, str):
+        return load_graph(module_path_or_graph)
+    return module_path_or_graph
+
+
+def _to_device(value):
+    if isinstance(value, torch.Tensor):
+        return value.cuda() if not value.is_cuda else value
+    arr = np.asarray(value)
+    if arr.dtype == np.float64:
+        arr = arr.astype(np.float32)
+    return torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+
+
+# ---------------------------------------------------------------------------------------------- op handlers
+def _meta(weight_dict) -> dict:
+    return weight_dict.setdefault(META_KEY, {})
+
+
+def _scalar(t: torch.Tensor):
+    return t.numel() == 1
+
+
+def _h_unary(op):
+    def run(node, ins, wd):
+        return K.unary(op, ins[0])
+    return run
+
+
+def _h_binary(op):
+    def run(node, ins, wd):
+        a, b = ins[0], ins[1]
+        if a.dtype != torch.float32 or b.dtype != torch.float32:
+            raise K.OtError("%s: only float32 operands have a CUDA handler (got %s, %s)" % (node.name, a.dtype, b.dtype))
+        out = K.binary(op, a, b)
+        if op == "Mul":
+            # de-quantization Mul(Round_out, scale): remember the int8 tensor and its per-row scale
+            m = _meta(wd)
+            for q_name, s_t in ((node.input[0], b), (node.input[1], a)):
+                src = m.get(q_name)
+                if src is not None and src[0] == "q" and s_t.dim() >= 1 and s_t.shape[-1] == 1 and s_t.numel() == src[1].numel() // src[1].shape[-1]:
+                    m[node.output[0]] = ("qs", src[1], s_t.reshape(-1).contiguous())
+        return out
+    return run
+
+
+def _h_round(node, ins, wd):
+    out = K.unary("Round", ins[0])
+    # integer-valued result: keep an int8 copy for the tensor-core path (values of dialect A lie in [-127, 127])
+    _meta(wd)[node.output[0]] = ("q", K.cast(out, torch.int8))
+    return out
+
+
+def _h_clip(node, ins, wd):
+    lo = float(ins[1].item()) if len(ins) > 1 and ins[1] is not None else -FLOAT_MAX
+    hi = float(ins[2].item()) if len(ins) > 2 and ins[2] is not None else FLOAT_MAX
+    return K.clip(ins[0], lo, hi)
+
+
+def _h_reduce(op):
+    def run(node, ins, wd):
+        axes = node.attr("axes", [-1])
+        if list(axes) not in ([-1], [ins[0].dim() - 1]):
+            raise K.OtError("%s: only reductions over the last axis have a CUDA handler" % node.name)
+        return K.reduce_last(op, ins[0], keepdims=bool(node.attr("keepdims", 1)))
+    return run
+
+
+def _h_softmax(node, ins, wd):
+    axis = node.attr("axis", -1)
+    if axis not in (-1, ins[0].dim() - 1):
+        raise K.OtError("%s: Softmax over a non-last axis has no CUDA handler" % node.name)
+    return K.softmax_last(ins[0])
+
+
+def _h_where(node, ins, wd):
+    cond, a, x = ins
+    if not _scalar(a):
+        raise K.OtError("%s: Where with a tensor `X` operand has no CUDA handler" % node.name)
+    return K.where_scalar(cond, float(a.item()), x)
+
+
+def _h_equal(node, ins, wd):
+    x, c = ins
+    if x.dtype != torch.int64 or not _scalar(c):
+        raise K.OtError("%s: Equal is implemented for int64 tensor == scalar" % node.name)
+    return K.equal_scalar_i64(x, int(c.item()))
+
+
+_ONNX_DTYPE = {1: torch.float32, 7: torch.int64, 9: torch.bool, 3: torch.int8, 6: torch.int32, 2: torch.uint8}
+
+
+def _h_cast(node, ins, wd):
+    to = _ONNX_DTYPE[int(node.attr("to"))]
+    x = ins[0]
+    if x.dtype == to:
+        out = x.clone()      # same-type Cast (e.g. the float Cast after Round in attention.py:34): a copy
+        m = _meta(wd)
+        if node.input[0] in m:
+            m[node.output[0]] = m[node.input[0]]
+        return out
+    return K.cast(x, to)
+
+
+def _h_transpose(node, ins, wd):
+    perm = list(node.attr("perm"))
+    x = ins[0]
+    m = _meta(wd)
+    src = m.get(node.input[0])
+    if src is not None and src[0] == "qs" and perm == [1, 0] and x.dim() == 2:
+        m[node.output[0]] = ("qsT", src[1], src[2])       # weight: keep the K-major int8 tensor, no data movement needed
+    if x.dtype == torch.bool:
+        return K.transpose(x.view(torch.uint8).to(torch.int32), perm).to(torch.bool)
+    return K.transpose(x, perm)
+
+
+def _h_reshape(node, ins, wd):
+    shape = [int(v) for v in ins[1].tolist()]
+    x = ins[0]
+    shape = [x.shape[i] if s == 0 else s for i, s in enumerate(shape)]
+    out = x.reshape(shape)
+    m = _meta(wd)
+    src = m.get(node.input[0])
+    if src is not None and src[0] == "qs" and out.shape[-1] == x.shape[-1]:
+        m[node.output[0]] = src                               # leading dims regrouped only: rows unchanged
+    return out
+
+
+def _h_unsqueeze(node, ins, wd):
+    axes = node.attr("axes")
+    if axes is None and len(ins) > 1:
+        axes = [int(v) for v in ins[1].tolist()]
+    out = ins[0]
+    for ax in sorted(int(a) for a in axes):
+        out = out.unsqueeze(ax)
+    return out
+
+
+def _h_matmul(node, ins, wd):
+    a, b = ins
+    m = _meta(wd)
+    ma, mb = m.get(node.input[0]), m.get(node.input[1])
+    if ma is not None and mb is not None and ma[0] == "qs" and mb[0] == "qsT" and b.dim() == 2:
+        aq, sa = ma[1].reshape(-1, ma[1].shape[-1]), ma[2]
+        wq, sw = mb[1], mb[2]
+        out = K.linear_w8a8(aq.contiguous(), wq.contiguous(), row_scale=sa, col_scale=sw, out_kind=K.OUT_F32)
+        return out.reshape(tuple(a.shape[:-1]) + (wq.shape[0],))
+    return K.matmul_f32(a, b)
+
+
+def _h_matmul_integer(node, ins, wd):
+    """ONNX MatMulInteger(A int8 [M,K], B int8 [K,N], a_zero_point, b_zero_point) -> int32, zero points folded on the
+    host side only when they are zero (dialect B uses zero_point = 0)."""
+    a, b = ins[0], ins[1]
+    for zp in ins[2:]:
+        if zp is not None and int(zp.abs().max().item()) != 0:
+            raise K.OtError("%s: non-zero zero points are not used by either dialect" % node.name)
+    bt = K.transpose(b.to(torch.int32), [1, 0]).to(torch.int8) if b.dim() == 2 else None
+    if bt is None or a.dtype != torch.int8:
+        raise K.OtError("%s: MatMulInteger expects int8 [.., K] x int8 [K, N]" % node.name)
+    out = K.linear_w8a8(a.reshape(-1, a.shape[-1]).contiguous(), bt.contiguous(), out_kind=K.OUT_I32)
+    return out.reshape(tuple(a.shape[:-1]) + (bt.shape[0],))
+
+
+def _h_quantize_linear(node, ins, wd):
+    """ONNX QuantizeLinear(x, scale, zero_point=0): saturate(round(x / scale)) -> int8 (dialect B)."""
+    x, s = ins[0], ins[1]
+    q = K.clip(K.unary("Round", K.binary("Div", x, s)), -128.0, 127.0)
+    out = K.cast(q, torch.int8)
+    _meta(wd)[node.output[0]] = ("q", out)
+    return out
+
+
+def _h_dequantize_linear(node, ins, wd):
+    x, s = ins[0], ins[1]
+    xf = K.cast(x, torch.float32) if x.dtype != torch.float32 else x
+    out = K.binary("Mul", xf, s)
+    if x.dtype == torch.int8 and s.dim() >= 1 and s.shape[-1] == 1 and s.numel() == x.numel() // x.shape[-1]:
+        _meta(wd)[node.output[0]] = ("qs", x, s.reshape(-1).contiguous())
+    return out
+
+
+def _h_shape(node, ins, wd):
+    return torch.tensor(list(ins[0].shape), dtype=torch.int64, device=ins[0].device)
+
+
+def _h_gather(node, ins, wd):
+    if ins[0].dim() != 1:
+        raise K.OtError("%s: Gather is implemented for shape vectors only" % node.name)
+    return ins[0][ins[1].long()]
+
+
+def _h_reduce_prod(node, ins, wd):
+    return ins[0].prod().reshape(1) if node.attr("keepdims", 1) else ins[0].prod()
+
+
+HANDLERS = {
+    "Abs": _h_unary("Abs"), "Relu": _h_unary("Relu"), "Sqrt": _h_unary("Sqrt"), "Round": _h_round,
+    "Add": _h_binary("Add"), "Sub": _h_binary("Sub"), "Mul": _h_binary("Mul"), "Div": _h_binary("Div"),
+    "Clip": _h_clip, "ReduceMax": _h_reduce("ReduceMax"), "ReduceMean": _h_reduce("ReduceMean"), "Softmax": _h_softmax,
+    "Where": _h_where, "Equal": _h_equal, "Cast": _h_cast, "Transpose": _h_transpose, "Reshape": _h_reshape,
+    "Unsqueeze": _h_unsqueeze, "MatMul": _h_matmul, "MatMulInteger": _h_matmul_integer,
+    "QuantizeLinear": _h_quantize_linear, "DequantizeLinear": _h_dequantize_linear,
+    "Shape": _h_shape, "Gather": _h_gather, "ReduceProd": _h_reduce_prod,
+}
+
+
+def run_node(node, input_tensors: List[Optional[torch.Tensor]], weight_dict) -> torch.Tensor:
+    """Execute one node on explicit inputs (the equivalent of execute_onnx on the one-node model)."""
+    handler = HANDLERS.get(node.op_type)
+    if handler is None:
+        raise K.OtError("no CUDA handler for op %r (node %s): this executor has no CPU fallback" % (node.op_type, node.name))
+    return handler(node, input_tensors, weight_dict)
+
+
+# ---------------------------------------------------------------------------------------------- reference API
+def expand_node_inputs_outputs(graph, node, weight_dict, module):
+    """onnx_optimized_inference.py:236-271.  Returns (inputs, outputs, seconds): the value-info records of the node's
+    operands / results.  The missing third Clip operand is added as max = 3.4e38 (:248-252); the decoder's dynamic
+    dimensions need no patching here because tensors carry their own shapes."""
+    start = time.time()
+    names_in = [n for n in node.input if n]
+    known = {v.name: v for v in list(graph.input) + list(graph.output) + list(graph.value_info)}
+    inits = {i.name for i in graph.initializer}
+    added_inputs = [known.get(n) or ValueInfo(n, ()) for n in names_in if n in known or n in inits or n in weight_dict]
+    added_outputs = [known.get(n) or ValueInfo(n, ()) for n in node.output]
+    if "Clip" in node.name and len([n for n in node.input if n]) < 3:
+        extra = ValueInfo(node.input[0][:-1] + "2", ())
+        added_inputs.append(extra)
+        if extra.name not in weight_dict:
+            weight_dict[extra.name] = torch.tensor(FLOAT_MAX, dtype=torch.float32, device="cuda")
+    return added_inputs, added_outputs, time.time() - start
+
+
+def _gather_inputs(node, weight_dict, added_inputs):
+    ins = []
+    for pos, name in enumerate(node.input):
+        if name == "":
+            if node.op_type == "Clip" and pos == 2:
+                ins.append(weight_dict[added_inputs[-1].name])   # the patched-in max operand
+            else:
+                ins.append(None)
+            continue
+        ins.append(weight_dict[name])
+    return ins
+
+
+def execute_node(node, main_graph, final_output_node, weight_dict, module, inject_parameters=None):
+    """onnx_optimized_inference.py:18-212: run the node, store its result under its tensor name, then apply the fault
+    hooks: RANDOM / RANDOM_BITFLIP on the target MatMul's output (:59-72); INPUT / WEIGHT / INPUT16 / WEIGHT16 along the
+    faulty_trace (:74-204) -- perturb_quantizer on the first trace node (inject_utils/layers.py:87-142), re-execution of the
+    following nodes on `delta_4d`, window selection and `out += delta` on the last one."""
+    added_inputs, added_outputs, list_operation_time = expand_node_inputs_outputs(main_graph, node, weight_dict, module)
+    ins = _gather_inputs(node, weight_dict, added_inputs)
+    out = run_node(node, ins, weight_dict)
+    tensor_output_name = node.output[0]
+    weight_dict[tensor_output_name] = out
+    output_tensors = {tensor_output_name: out}
+    p = inject_parameters
+
+    if p and ("RANDOM" in p["inject_type"]) and (node.name == p["faulty_operation_name"]):
+        draws = faults.Draws(p)
+        target_indices = draws.indices("target_indices", out.shape)
+        golden_value = float(out[tuple(target_indices)].item())
+        if "BITFLIP" in p["inject_type"]:
+            faulty_value = faults.float32_bit_flip_value(golden_value, draws.randint("flip_bit", 0, 32))
+        else:
+            faulty_value = faults.delta_init_value(draws.bits32("random_bits"))
+        out[tuple(target_indices)] = faulty_value           # in place, like the reference (:68)
+        _meta(weight_dict).pop(tensor_output_name, None)
+
+    if p and (module in p["targetted_module"]) and p["faulty_trace"] and (node.name == p["faulty_trace"][0]) and \
+            (p["inject_type"] in ["INPUT", "WEIGHT", "INPUT16", "WEIGHT16"]):
+        faulty_operation = p["faulty_trace"][0]
+        draws = faults.Draws(p)
+        if p["faulty_tensor_name"] in node.input:
+            # first node of the trace consumes the integer tensor: build the one-hot perturbation
+            assert p["faulty_quantizer_name"] == p["faulty_trace"][0]
+            _perturb_quantizer(node, ins, weight_dict, p["faulty_tensor_name"], p["faulty_bit_position"], draws)
+            p["intermediate_output_name"] = tensor_output_name
+        else:
+            pos = None
+            for k, name in enumerate(node.input):
+                if name == p["intermediate_output_name"]:
+                    pos = k
+            assert pos is not None
+            delta_ins = list(ins)
+            delta_ins[pos] = weight_dict["delta_4d"]
+            scratch = {META_KEY: {}}                          # the delta carries no int8 provenance: fp32 kernels
+            weight_dict["delta_4d"] = run_node(node, delta_ins, scratch)
+            p["intermediate_output_name"] = tensor_output_name
+
+        if faulty_operation == p["faulty_operation_name"]:
+            assert len(p["faulty_trace"]) == 1
+            delta = weight_dict["delta_4d"]
+            if p["inject_type"] == "INPUT16":
+                delta = _window(delta, axis=3, length=16, start_key="window_start", draws=draws, random_len=False)
+            elif p["inject_type"] == "WEIGHT16":
+                delta = _window(delta, axis=2, length=16, start_key="window_start", draws=draws, random_len=True)
+            weight_dict["delta_4d"] = delta
+            faulty = K.binary("Add", weight_dict[tensor_output_name], delta)
+            weight_dict[tensor_output_name] = faulty
+            output_tensors[tensor_output_name] = faulty
+            _meta(weight_dict).pop(tensor_output_name, None)
+        p["faulty_trace"] = p["faulty_trace"][1:]
+    return output_tensors, weight_dict, list_operation_time
+
+
+def _perturb_quantizer(node, ins, weight_dict, faulty_tensor_name, faulty_bit_position, draws):
+    """inject_utils/layers.py:87-142: flip one bit of one random element of the integer tensor (int_bit_flip :70-84), run
+    the de-quantizing node on the one-hot tensor holding the faulty value, and turn the result into a delta by
+    subtracting the golden de-quantized value at that index."""
+    golden = weight_dict[faulty_tensor_name]
+    idx = tuple(draws.indices("target_indices", golden.shape))
+    q = int(golden[idx].item())                                # np.int8(tensor)[idx]
+    faulty_value = faults.flip_int8_bit(q, faulty_bit_position)
+    assert -128 <= faulty_value <= 127
+    one_hot = torch.zeros_like(golden)
+    one_hot[idx] = float(faulty_value)
+    pos = list(node.input).index(faulty_tensor_name)
+    pert_ins = list(ins)
+    pert_ins[pos] = one_hot
+    delta = run_node(node, pert_ins, {META_KEY: {}})
+    dequantized = weight_dict[node.output[0]]
+    delta[idx] = delta[idx] - dequantized[idx]
+    weight_dict["delta_4d"] = delta
+
+
+def _window(delta: torch.Tensor, axis: int, length: int, start_key: str, draws, random_len: bool) -> torch.Tensor:
+    """onnx_optimized_inference.py:111-179: keep only a 16-aligned window of the delta along `axis` (shape[3] for INPUT16,
+    shape[2] for WEIGHT16 -- 4-D attention outputs only, as in the reference), at the coordinates of the first non-zero."""
+    if delta.dim() < 4:
+        raise IndexError("INPUT16/WEIGHT16 index shape[%d]: only 4-D MatMul outputs are supported (as in the reference)" % axis)
+    shape = list(delta.shape)
+    blocks = shape[axis] // 16
+    start = 0 if blocks == 0 else draws.randint(start_key, 0, blocks)
+    start *= 16
+    n = length
+    out = torch.zeros_like(delta)
+    nz = torch.nonzero(delta)
+    if nz.shape[0] == 0:
+        return out
+    if random_len:
+        n = draws.randint("window_len", 1, 16)
+    index = [int(v) for v in nz[0].tolist()]
+    index[axis] = start
+    for i in range(n):
+        if i >= shape[axis]:
+            break
+        out[tuple(index)] = delta[tuple(index)]
+        index[axis] += 1
+        if index[axis] >= shape[axis]:
+            break
+    return out
+
+
+def inference(main_graph, weight_dict, module, inject_parameters=None):
+    """onnx_optimized_inference.py:214-234: walk graph.node in order; returns the LAST node's {name: tensor} and the dict."""
+    output_tensors = None
+    for node in main_graph.node:
+        output_tensors, weight_dict, _ = execute_node(node, main_graph, node.output[0], weight_dict, module, inject_parameters)
+    return output_tensors, weight_dict
+
+
+def get_weight_dict(module_path):
+    """onnx_optimized_inference.py:273-280: (graph, {initializer name: tensor})."""
+    graph = _as_graph(module_path)
+    return graph, {i.name: _to_device(i.array) for i in graph.initializer}
+
+
+def prepare_inference(module_path, module_input_values):
+    """onnx_optimized_inference.py:282-295: (weight_dict incl. the graph inputs, graph)."""
+    graph, weight_dict = get_weight_dict(module_path)
+    init_names = {i.name for i in graph.initializer}
+    for v in graph.input:
+        if v.name not in init_names:
+            weight_dict[v.name] = _to_device(module_input_values[v.name])
+    return weight_dict, graph
+
+
+def run_module(module, input_values, module_filepath, module_weight_dict, module_graph, inject_parameters=None):
+    """onnx_optimized_inference.py:297-304."""
+    for input_name in list(input_values.keys()):
+        module_weight_dict[input_name] = _to_device(input_values[input_name])
+    module_weight_dict.pop(META_KEY, None)
+    return inference(module_graph, module_weight_dict, module, inject_parameters)
+
+
+def to_numpy(tensors: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
+    """Convenience for callers that index the reference's numpy outputs."""
+    return {k: v.detach().cpu().numpy() for k, v in tensors.items() if isinstance(v, torch.Tensor)}

@@ -1,0 +1,271 @@
+"""ORACLE (test infrastructure, never imported by the product): numpy restatement of the reference's custom
+node-by-node ONNX executor and its fault hooks.
+
+Follows onnx_optimized_inference.py:18-212 (execute_node: run one node, store every intermediate, RANDOM /
+RANDOM_BITFLIP hook :59-72, INPUT/WEIGHT[16] trace hook :74-204), :214-234 (inference), :236-271
+(expand_node_inputs_outputs: the missing Clip max = 3.4e38), :273-304 (get_weight_dict, prepare_inference,
+run_module) and inject_utils/layers.py:70-142 (int_bit_flip, perturb_quantizer).  The third-party call
+`qonnx.core.onnx_exec.execute_onnx(one-node model)` (-> onnxruntime CPU EP; neither package is installable here,
+versions unpinned: SURVEY.md 8c) is restated per op from the ONNX opset-13 operator specification: fp32 IEEE
+arithmetic, Round = half-to-even, Softmax over `axis`, MatMul = fp32 matrix product.
+
+mode = "ref-float": every MatMul is an fp32 product of the de-quantized operands (the reference as is).
+mode = "int-exact": a MatMul whose operands are Round -> Mul(scale) [-> Transpose] chains is evaluated as the exact
+integer contraction followed by fl(fl(float(acc)*s_row)*s_col) (the factorisation the CUDA GEMM implements).
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import intexact as ox
+
+F32 = np.float32
+FLOAT_MAX = 3.4e38
+_ONNX_DTYPE = {1: np.float32, 7: np.int64, 9: np.bool_, 3: np.int8, 6: np.int32, 2: np.uint8}
+
+
+class Draws:
+    """Explicit random draws of a trial (same contract as the product's faults.Draws)."""
+
+    def __init__(self, p: dict):
+        self.given = dict(p.get("rng_draws") or {})
+        self.used = p.setdefault("rng_draws_used", {})
+
+    def indices(self, key, shape):
+        idx = [int(i) for i in self.given[key]] if key in self.given else [int(np.random.randint(0, d)) for d in shape]
+        self.used[key] = idx
+        return idx
+
+    def randint(self, key, lo, hi):
+        v = int(self.given[key]) if key in self.given else int(np.random.randint(lo, hi))
+        self.used[key] = v
+        return v
+
+    def bits32(self, key):
+        v = int(self.given[key]) if key in self.given else int("".join(str(np.random.randint(0, 2)) for _ in range(32)), 2)
+        self.used[key] = v
+        return v
+
+
+def _attr(node, name, default=None):
+    for a in node.attribute:
+        if a.name == name:
+            if a.ints is not None:
+                return list(a.ints)
+            return a.i if a.i is not None else a.f
+    return default
+
+
+def run_node(node, ins: List[Optional[np.ndarray]], prov: Optional[dict] = None, mode: str = "ref-float") -> np.ndarray:
+    """ONNX opset-13 semantics of one node on numpy arrays.  `prov` tracks int8 provenance for int-exact MatMuls."""
+    op = node.op_type
+    prov = prov if prov is not None else {}
+    x = ins[0]
+    if op == "Abs":
+        return np.abs(x)
+    if op == "Relu":
+        return np.maximum(x, F32(0))
+    if op == "Sqrt":
+        return np.sqrt(x).astype(F32)
+    if op == "Round":
+        out = np.rint(x).astype(F32)
+        prov[node.output[0]] = ("q", out)
+        return out
+    if op in ("Add", "Sub", "Mul", "Div"):
+        a, b = ins[0], ins[1]
+        out = {"Add": np.add, "Sub": np.subtract, "Mul": np.multiply, "Div": np.divide}[op](a, b).astype(F32)
+        if op == "Mul":
+            for qn, s in ((node.input[0], b), (node.input[1], a)):
+                src = prov.get(qn)
+                if src is not None and src[0] == "q" and s.ndim >= 1 and s.shape[-1] == 1 and s.size == src[1].size // src[1].shape[-1]:
+                    prov[node.output[0]] = ("qs", src[1], s.reshape(-1))
+        return out
+    if op == "Clip":
+        lo = F32(ins[1]) if len(ins) > 1 and ins[1] is not None else F32(-FLOAT_MAX)
+        hi = F32(ins[2]) if len(ins) > 2 and ins[2] is not None else F32(FLOAT_MAX)
+        return np.minimum(np.maximum(x, lo), hi).astype(F32)
+    if op == "ReduceMax":
+        return np.max(x, axis=tuple(_attr(node, "axes", [-1])), keepdims=bool(_attr(node, "keepdims", 1)))
+    if op == "ReduceMean":
+        ax = tuple(_attr(node, "axes", [-1]))
+        return (np.sum(x.astype(np.float64), axis=ax, keepdims=bool(_attr(node, "keepdims", 1))) / np.prod([x.shape[a] for a in ax])).astype(F32)
+    if op == "Softmax":
+        ax = _attr(node, "axis", -1)
+        m = np.max(x, axis=ax, keepdims=True)
+        e = np.exp((x - m).astype(F32).astype(np.float64))
+        return (e / np.sum(e, axis=ax, keepdims=True)).astype(F32)
+    if op == "Where":
+        return np.where(ins[0], ins[1], ins[2]).astype(F32)
+    if op == "Equal":
+        return np.equal(ins[0], ins[1])
+    if op == "Cast":
+        out = x.astype(_ONNX_DTYPE[int(_attr(node, "to"))])
+        if out.dtype == x.dtype and node.input[0] in prov:
+            prov[node.output[0]] = prov[node.input[0]]
+        return out
+    if op == "Transpose":
+        perm = _attr(node, "perm")
+        src = prov.get(node.input[0])
+        if src is not None and src[0] == "qs" and perm == [1, 0] and x.ndim == 2:
+            prov[node.output[0]] = ("qsT", src[1], src[2])
+        return np.ascontiguousarray(np.transpose(x, perm))
+    if op == "Reshape":
+        shape = [int(v) for v in ins[1]]
+        shape = [x.shape[i] if s == 0 else s for i, s in enumerate(shape)]
+        out = x.reshape(shape)
+        src = prov.get(node.input[0])
+        if src is not None and src[0] == "qs" and out.shape[-1] == x.shape[-1]:
+            prov[node.output[0]] = src
+        return out
+    if op == "Unsqueeze":
+        out = x
+        for ax in sorted(int(a) for a in _attr(node, "axes")):
+            out = np.expand_dims(out, ax)
+        return out
+    if op == "MatMul":
+        a, b = ins[0], ins[1]
+        pa, pb = prov.get(node.input[0]), prov.get(node.input[1])
+        if mode == "int-exact" and pa is not None and pb is not None and pa[0] == "qs" and pb[0] == "qsT" and b.ndim == 2:
+            aq = pa[1].reshape(-1, pa[1].shape[-1]).astype(np.int8)
+            acc = ox.int_matmul(aq, pb[1].astype(np.int8))
+            out = ox.linear_epilogue(acc, pa[2], pb[2])
+            return out.reshape(a.shape[:-1] + (pb[1].shape[0],))
+        return np.matmul(a, b).astype(F32)
+    raise NotImplementedError("oracle: op %s" % op)
+
+
+# ---------------------------------------------------------------------------------------------- reference API
+def expand_node_inputs_outputs(graph, node, weight_dict, module):
+    """onnx_optimized_inference.py:236-271."""
+    start = time.time()
+    added_inputs = [n for n in node.input if n]
+    if "Clip" in node.name and len(added_inputs) < 3:
+        extra = node.input[0][:-1] + "2"                     # :250  name[:-1] + "2"
+        weight_dict[extra] = np.array(FLOAT_MAX, dtype=F32)  # :251
+        added_inputs.append(extra)
+    return added_inputs, list(node.output), time.time() - start
+
+
+def _inputs(node, weight_dict, added):
+    ins = []
+    for pos, name in enumerate(node.input):
+        if name == "":
+            ins.append(weight_dict[added[-1]] if (node.op_type == "Clip" and pos == 2) else None)
+        else:
+            ins.append(weight_dict[name])
+    return ins
+
+
+def execute_node(node, main_graph, final_output_node, weight_dict, module, inject_parameters=None, mode="ref-float"):
+    """onnx_optimized_inference.py:18-212."""
+    prov = weight_dict.setdefault("__prov__", {})
+    added, _, op_time = expand_node_inputs_outputs(main_graph, node, weight_dict, module)
+    ins = _inputs(node, weight_dict, added)
+    out = run_node(node, ins, prov, mode)
+    name = node.output[0]
+    weight_dict[name] = out
+    output_tensors = {name: out}
+    p = inject_parameters
+
+    if p and ("RANDOM" in p["inject_type"]) and (node.name == p["faulty_operation_name"]):       # :59-72
+        d = Draws(p)
+        idx = tuple(d.indices("target_indices", out.shape))
+        if "BITFLIP" in p["inject_type"]:
+            faulty = ox.float32_bit_flip(out[idx], d.randint("flip_bit", 0, 32))
+        else:
+            faulty = ox.bits_to_float32(d.bits32("random_bits"))
+        out[idx] = faulty
+        prov.pop(name, None)
+
+    if p and (module in p["targetted_module"]) and p["faulty_trace"] and (node.name == p["faulty_trace"][0]) and \
+            (p["inject_type"] in ["INPUT", "WEIGHT", "INPUT16", "WEIGHT16"]):                     # :74
+        faulty_operation = p["faulty_trace"][0]
+        d = Draws(p)
+        if p["faulty_tensor_name"] in node.input:                                                 # :78-81
+            assert p["faulty_quantizer_name"] == p["faulty_trace"][0]
+            golden = weight_dict[p["faulty_tensor_name"]]
+            idx = tuple(d.indices("target_indices", golden.shape))                                # layers.py:73
+            faulty_value = ox.flip_int8_bit(int(np.int8(golden[idx])), p["faulty_bit_position"])  # layers.py:72,77
+            assert -128 <= faulty_value <= 127
+            one_hot = np.zeros(golden.shape, dtype=golden.dtype)                                  # layers.py:105-107
+            one_hot[idx] = faulty_value
+            pert = list(ins)
+            pert[list(node.input).index(p["faulty_tensor_name"])] = one_hot
+            delta = run_node(node, pert, {}, "ref-float").copy()                                  # layers.py:134-135
+            delta[idx] = delta[idx] - weight_dict[name][idx]                                      # layers.py:139-140
+            weight_dict["delta_4d"] = delta
+            p["intermediate_output_name"] = name
+        else:                                                                                     # :84-104
+            pos = [k for k, n in enumerate(node.input) if n == p["intermediate_output_name"]]
+            assert pos
+            pert = list(ins)
+            pert[pos[-1]] = weight_dict["delta_4d"]
+            weight_dict["delta_4d"] = run_node(node, pert, {}, "ref-float")
+            p["intermediate_output_name"] = name
+        if faulty_operation == p["faulty_operation_name"]:                                        # :107-199
+            assert len(p["faulty_trace"]) == 1
+            delta = weight_dict["delta_4d"]
+            if p["inject_type"] == "INPUT16":
+                delta = _window(delta, 3, d, random_len=False)
+            elif p["inject_type"] == "WEIGHT16":
+                delta = _window(delta, 2, d, random_len=True)
+            weight_dict["delta_4d"] = delta
+            faulty = np.add(weight_dict[name], delta).astype(F32)                                 # :191
+            weight_dict[name] = faulty
+            output_tensors[name] = faulty
+            prov.pop(name, None)
+        p["faulty_trace"] = p["faulty_trace"][1:]                                                 # :204
+    return output_tensors, weight_dict, op_time
+
+
+def _window(delta, axis, d, random_len):
+    """onnx_optimized_inference.py:111-139 (INPUT16: shape[3]) / :156-179 (WEIGHT16: shape[2], randint(1,16) rows)."""
+    shape = list(delta.shape)
+    blocks = shape[axis] // 16
+    start = 0 if blocks == 0 else d.randint("window_start", 0, blocks)
+    start *= 16
+    out = np.zeros(delta.shape, dtype=F32)
+    nz = np.nonzero(delta)
+    if len(nz[0]) == 0:
+        return out
+    n = d.randint("window_len", 1, 16) if random_len else 16
+    index = [int(a[0]) for a in nz]
+    index[axis] = start
+    for i in range(n):
+        if i >= shape[axis] or index[axis] >= shape[axis]:
+            break
+        out[tuple(index)] = delta[tuple(index)]
+        index[axis] += 1
+    return out
+
+
+def inference(main_graph, weight_dict, module, inject_parameters=None, mode="ref-float"):
+    """onnx_optimized_inference.py:214-234."""
+    output_tensors = None
+    for node in main_graph.node:
+        output_tensors, weight_dict, _ = execute_node(node, main_graph, node.output[0], weight_dict, module, inject_parameters, mode)
+    return output_tensors, weight_dict
+
+
+def get_weight_dict(graph):
+    """onnx_optimized_inference.py:273-280."""
+    return graph, {i.name: np.array(i.array) for i in graph.initializer}
+
+
+def prepare_inference(graph, module_input_values):
+    """onnx_optimized_inference.py:282-295."""
+    graph, wd = get_weight_dict(graph)
+    for v in graph.input:
+        wd[v.name] = np.asarray(module_input_values[v.name])
+    return wd, graph
+
+
+def run_module(module, input_values, module_filepath, module_weight_dict, module_graph, inject_parameters=None, mode="ref-float"):
+    """onnx_optimized_inference.py:297-304."""
+    for k in list(input_values.keys()):
+        module_weight_dict[k] = np.asarray(input_values[k])
+    module_weight_dict.pop("__prov__", None)
+    return inference(module_graph, module_weight_dict, module, inject_parameters, mode)
