@@ -1,0 +1,231 @@
+"""Fault-injection campaign driver on the fused engine: the B200 counterpart of
+parallelized_inject_onnx_transformer.py:789-861 (load_trained_model: target files x fault models x bit positions),
+:446-493 (run_model_example: sentence draw + worker pool), :305-409 (check_outputs: golden and faulty greedy decode,
+sentence BLEU, one CSV row per trial) -- SURVEY.md 8f item 1.
+
+Differences by design:
+  * a trial is an explicit record (sentence id, target, fault model, bit, element index, window, bit pattern) drawn
+    from np.random.default_rng(seed) -- the reference draws from the unseeded global np.random inside the hooks -- so
+    every trial can be replayed and compared trial-for-trial with the oracle;
+  * the golden decode of a sentence is computed once and cached (the reference decodes golden + faulty per trial);
+    for a Decoder target the encoder memory is reused as well, and only the injection step runs outside the CUDA graph;
+  * there are no ./separated/*.onnx temp files (the reference's three-segment graph cut and its file race,
+    :411-444, :583): the fault is applied inside the epilogue of the target kernel;
+  * trials are sharded over ranks (rank r takes trials r::N); the only collective is the gather of the result records.
+
+CSV schema (results_fault_injection/results.csv, 5-column rows): op,golden_bleu,faulty_bleu,bit,type ; "op,0,0,bit,type"
+when the output has no </s> (:379-383).  With synthetic data there is no reference translation, so the golden output
+itself serves as the BLEU reference (golden BLEU = 1.0; faulty BLEU < 1.0 iff the decoded sentence changed).
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+from collections import Counter
+from dataclasses import asdict, dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import weights as W
+
+FAULT_MODELS = ["INPUT", "WEIGHT", "INPUT16", "WEIGHT16", "RANDOM", "RANDOM_BITFLIP"]   # :805
+ENC_TARGETS = ["qk", "pv", "ffn1", "ffn2"]                                              # input/encoder/*.json
+DEC_TARGETS = ["qk", "pv", "cqk", "cpv", "ffn1", "ffn2"]                                # input/decoder/*.json
+D, FF, H, DK = 512, 2048, 8, 64
+
+
+@dataclass
+class Trial:
+    trial_id: int
+    sentence: int
+    module: str          # "Encoder" | "Decoder"
+    layer: int
+    target: str          # role name (graph.py)
+    op_name: str         # reference node name, e.g. "MatMul_28"
+    inject_type: str
+    bit: int             # 0..7 for operand faults; fp32 bit 0..31 for RANDOM_BITFLIP
+    flat_index: int
+    window_start: int = 0
+    window_len: int = 0
+    value_bits: int = 0
+
+
+def _tensor_shape(module: str, target: str, operand: str, S: int, T: int):
+    """Shape of the faulty tensor in the reference's layout for one sentence (B = 1, like the reference's trials)."""
+    Tq = S if module == "Encoder" else T
+    Tk = S if (module == "Encoder" or target in ("cqk", "cpv")) else T
+    if target in ("qk", "cqk"):
+        return {"input": (1, Tq, D), "weight": (1, Tk, D), "output": (1, H, Tq, Tk)}[operand]
+    if target in ("pv", "cpv"):
+        return {"input": (1, H, Tq, Tk), "weight": (1, Tk, D), "output": (1, H, Tq, DK)}[operand]
+    if target == "ffn1":
+        return {"input": (1, Tq, D), "weight": (FF, D), "output": (1, Tq, FF)}[operand]
+    if target == "ffn2":
+        return {"input": (1, Tq, FF), "weight": (D, FF), "output": (1, Tq, D)}[operand]
+    raise ValueError(target)
+
+
+def make_trials(n: int, seed: int, n_sentences: int, src_len: int, modules: Sequence[str] = ("Encoder", "Decoder"), n_layers: int = 6) -> List[Trial]:
+    """cfg5: trials = (sentence id, target, inject_type, bit, element index, window) from default_rng(seed).
+    Decoder trials inject at greedy step 0 (target_inference_number = 1, :832), i.e. with T = 1."""
+    from .graph import decoder_matmul_name, encoder_matmul_name
+    rng = np.random.default_rng(seed)
+    trials = []
+    for tid in range(n):
+        module = modules[int(rng.integers(0, len(modules)))]
+        layer = int(rng.integers(0, n_layers))
+        targets = ENC_TARGETS if module == "Encoder" else DEC_TARGETS
+        target = targets[int(rng.integers(0, len(targets)))]
+        ftype = FAULT_MODELS[int(rng.integers(0, len(FAULT_MODELS)))]
+        if ftype in ("INPUT16", "WEIGHT16") and target in ("ffn1", "ffn2"):
+            ftype = ftype[:-2]          # the *16 windows index shape[3]/shape[2] of a 4-D output: attention MatMuls only
+        operand = "input" if ftype.startswith("INPUT") else ("weight" if ftype.startswith("WEIGHT") else "output")
+        shape = _tensor_shape(module, target, operand, src_len, 1)
+        idx = [int(rng.integers(0, d)) for d in shape]
+        flat = int(np.ravel_multi_index(idx, shape))
+        out_shape = _tensor_shape(module, target, "output", src_len, 1)
+        bit = int(rng.integers(0, 32)) if ftype == "RANDOM_BITFLIP" else int(rng.integers(0, 8))
+        ws, wl = 0, 0
+        if ftype == "INPUT16":
+            blocks = out_shape[3] // 16
+            ws, wl = (16 * int(rng.integers(0, blocks)) if blocks else 0), 16
+        elif ftype == "WEIGHT16":
+            blocks = out_shape[2] // 16
+            ws, wl = (16 * int(rng.integers(0, blocks)) if blocks else 0), int(rng.integers(1, 16))
+        name = (encoder_matmul_name if module == "Encoder" else decoder_matmul_name)(layer, target)
+        trials.append(Trial(tid, int(rng.integers(0, n_sentences)), module, layer, target, name, ftype, bit, flat, ws, wl,
+                            int(rng.integers(0, 2 ** 32)) if ftype == "RANDOM" else 0))
+    return trials
+
+
+# ---------------------------------------------------------------------------------------------- BLEU (nltk method4)
+def sentence_bleu_method4(reference: Sequence[int], hypothesis: Sequence[int]) -> float:
+    """nltk.translate.bleu_score.sentence_bleu([reference], hypothesis, smoothing_function=SmoothingFunction().method4)
+    (the call at parallelized_inject_onnx_transformer.py:393-397) on token sequences: uniform 4-gram weights, brevity
+    penalty, method4 smoothing (zero n-gram matches are replaced by 1 / (2^k * K / ln(len(hyp)))), K = 5."""
+    hyp_len, ref_len = len(hypothesis), len(reference)
+    if hyp_len == 0:
+        return 0.0
+    p_num, p_den = [], []
+    for n in range(1, 5):
+        h = Counter(tuple(hypothesis[i:i + n]) for i in range(hyp_len - n + 1))
+        r = Counter(tuple(reference[i:i + n]) for i in range(ref_len - n + 1))
+        p_num.append(sum(min(c, r[g]) for g, c in h.items()))
+        p_den.append(max(1, sum(h.values())))
+    if p_num[0] == 0:
+        return 0.0
+    bp = 1.0 if hyp_len > ref_len else math.exp(1 - ref_len / hyp_len)
+    incvnt = 1
+    p = []
+    for num, den in zip(p_num, p_den):
+        if num == 0 and hyp_len > 1:
+            numerator = 1 / (2 ** incvnt * 5 / math.log(hyp_len))
+            p.append(numerator / den)
+            incvnt += 1
+        else:
+            p.append(num / den)
+    if min(p) <= 0:
+        return 0.0
+    return bp * math.exp(sum(0.25 * math.log(x) for x in p))
+
+
+def _sentence(ys: np.ndarray) -> Optional[List[int]]:
+    """Tokens between <s> and the first </s> (:376-386); None when there is no </s>."""
+    toks = [int(t) for t in ys if int(t) != W.PAD_ID]
+    if W.EOS_ID not in toks:
+        return None
+    return toks[1:toks.index(W.EOS_ID)]
+
+
+def classify(golden: np.ndarray, faulty: np.ndarray) -> Dict[str, object]:
+    """Outcome of one trial: masked (faulty BLEU == golden BLEU), changed, or no-EOS (the "op,0,0,bit,type" row)."""
+    g, f = _sentence(golden), _sentence(faulty)
+    if g is None or f is None:
+        return {"outcome": "no-EOS", "golden_bleu": 0, "faulty_bleu": 0, "tokens_equal": bool(np.array_equal(golden, faulty))}
+    gb, fb = sentence_bleu_method4(g, g), sentence_bleu_method4(g, f)
+    return {"outcome": "masked" if gb == fb else "changed", "golden_bleu": gb, "faulty_bleu": fb,
+            "tokens_equal": bool(np.array_equal(golden, faulty))}
+
+
+def csv_row(trial: Trial, result: Dict[str, object]) -> str:
+    bit = None if "RANDOM" in trial.inject_type else trial.bit
+    return "%s,%s,%s,%s,%s\n" % (trial.op_name, result["golden_bleu"], result["faulty_bleu"], bit, trial.inject_type)
+
+
+# ---------------------------------------------------------------------------------------------- runner
+def run_trials(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials: List[Trial], csv_path: Optional[str] = None,
+               rank: int = 0, world: int = 1) -> List[Dict[str, object]]:
+    """Golden decode of all sentences in one batch, then one faulty decode per trial of this rank's shard."""
+    import torch
+    from .engine import FaultSpec
+    dev = engine.dev
+    ids = torch.from_numpy(src_ids).to(dev)
+    mask = torch.from_numpy(src_mask).to(dev)
+    golden = engine.greedy_decode(ids, mask).cpu().numpy()
+    memory_cache: Dict[int, "torch.Tensor"] = {}
+    out = []
+    done = set()
+    if csv_path and os.path.exists(csv_path + ".ids"):
+        done = {int(x) for x in open(csv_path + ".ids").read().split()}     # resume: skip trial ids already written
+    for trial in trials[rank::world]:
+        if trial.trial_id in done:
+            continue
+        b = trial.sentence
+        spec = FaultSpec(trial.module, trial.layer, trial.target, trial.inject_type, trial.bit, trial.flat_index, trial.window_start,
+                         trial.window_len, trial.value_bits, step=0)
+        memory = None
+        if trial.module == "Decoder":
+            if b not in memory_cache:
+                memory_cache[b] = engine.encode(ids[b:b + 1], mask[b:b + 1]).clone()
+            memory = memory_cache[b]
+        faulty = engine.greedy_decode(ids[b:b + 1], mask[b:b + 1], fault=spec, memory=memory).cpu().numpy()[0]
+        res = classify(golden[b], faulty)
+        res.update(asdict(trial))
+        out.append(res)
+        if csv_path:
+            with open(csv_path, "a") as f:
+                f.write(csv_row(trial, res))
+            with open(csv_path + ".ids", "a") as f:
+                f.write("%d\n" % trial.trial_id)
+    return out
+
+
+def main(argv=None):
+    """Same three flags as the reference (parallelized_inject_onnx_transformer.py:47-52) plus --gpus/--batch/--seed/--trials."""
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--directory_name", default="input/encoder")
+    ap.add_argument("--module", default="Encoder")
+    ap.add_argument("--experiment_output_name", default="results_fault_injection/results.csv")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--src-len", type=int, default=64)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--trials", type=int, default=100)
+    args = ap.parse_args(argv)
+    import torch
+    import torch.distributed as dist
+    from .engine import QuantizedTransformer
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        dist.init_process_group("nccl")
+    eng = QuantizedTransformer(W.init_float_weights(args.seed))
+    ids, mask = W.synthetic_tokens(args.seed, args.batch, args.src_len)
+    trials = make_trials(args.trials, args.seed, args.batch, args.src_len, modules=(args.module,))
+    os.makedirs(os.path.dirname(args.experiment_output_name) or ".", exist_ok=True)
+    path = args.experiment_output_name if world == 1 else "%s.rank%d" % (args.experiment_output_name, rank)
+    res = run_trials(eng, ids, mask, trials, path, rank, world)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [(r["trial_id"], r["outcome"]) for r in res])
+        res_all = sorted(x for part in gathered for x in part)
+        dist.destroy_process_group()
+    else:
+        res_all = sorted((r["trial_id"], r["outcome"]) for r in res)
+    if rank == 0:
+        print(Counter(o for _, o in res_all))
+
+
+if __name__ == "__main__":
+    main()

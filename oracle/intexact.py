@@ -88,10 +88,20 @@ def group_quant(y: np.ndarray, group: int):
     return q.reshape(m, n), s.reshape(m, n // group)
 
 
-def attention(qq, sq, kq, sk, vq, sv, key_mask=None, causal=False, q_pos0=0, return_all=False):
+def apply_output_fault(value, fault):
+    """RANDOM_BITFLIP / RANDOM on one fp32 element (inject_utils/layers.py:18-33)."""
+    if fault["type"] == "RANDOM_BITFLIP":
+        return float32_bit_flip(value, fault["bit"])
+    return bits_to_float32(fault["value_bits"])
+
+
+def attention(qq, sq, kq, sk, vq, sv, key_mask=None, causal=False, q_pos0=0, return_all=False, fault=None):
     """attention.py:23-36 per sentence.  qq int8 [Tq,512], kq/vq int8 [Tk,512], sq [Tq], sk/sv [Tk].
     scores = fl(fl(float(dot) * sq[i]) * sk[j]) / 8 ; masked_fill(mask==0, -1e9) ; softmax ; pq = rint(127 p) ;
     ctx = sum_j (pq/127) * (sv[j] * vq[j, :])  accumulated in float64 (tolerance class).
+    `fault` (optional, one sentence): dict(target "qk"|"pv", type, bit, index=(...), window_start, window_len, value_bits) in
+    the integer-domain form of SURVEY.md App. D: an operand fault replaces q by q' = flip(q) for the affected output
+    window only (INPUT: one query row x key/feature window; WEIGHT: one key column / feature x query window).
     Returns ctx fp32 [Tq,512] (heads merged, attention.py:65-66) and, if return_all, (ctx, pq uint8 [8,Tq,Tk], p)."""
     Tq, Tk = qq.shape[0], kq.shape[0]
     H, dk = 8, 64
@@ -106,10 +116,27 @@ def attention(qq, sq, kq, sk, vq, sv, key_mask=None, causal=False, q_pos0=0, ret
         visible &= np.asarray(key_mask).astype(bool).reshape(1, Tk)
     if causal:
         visible &= (np.arange(Tk)[None, :] <= (q_pos0 + np.arange(Tq))[:, None])
+    ft = fault["type"] if fault else None
     for h in range(H):
         sl = slice(h * dk, (h + 1) * dk)
         dot = int_matmul(qq[:, sl], kq[:, sl])
-        s = ((dot.astype(F32) * sq).astype(F32) * sk).astype(F32) / F32(8.0)
+        if fault and fault["target"] == "qk" and ft.startswith(("INPUT", "WEIGHT")):
+            _, t, c = fault["index"]                       # Round tensor [1, T, 512]
+            if c // dk == h:
+                d = c % dk
+                if ft.startswith("INPUT"):
+                    q0 = int(qq[t, h * dk + d]); delta = flip_int8_bit(q0, fault["bit"]) - q0
+                    w0, w1 = (fault["window_start"], min(Tk, fault["window_start"] + fault["window_len"])) if fault["window_len"] > 0 else (0, Tk)
+                    dot[t, w0:w1] += delta * kq[w0:w1, h * dk + d].astype(np.int32)
+                else:
+                    k0 = int(kq[t, h * dk + d]); delta = flip_int8_bit(k0, fault["bit"]) - k0
+                    w0, w1 = (fault["window_start"], min(Tq, fault["window_start"] + fault["window_len"])) if fault["window_len"] > 0 else (0, Tq)
+                    dot[w0:w1, t] += qq[w0:w1, h * dk + d].astype(np.int32) * delta
+        mm = ((dot.astype(F32) * sq).astype(F32) * sk).astype(F32)
+        if fault and fault["target"] == "qk" and ft.startswith("RANDOM") and fault["index"][1] == h:
+            _, _, i, j = fault["index"]
+            mm[i, j] = apply_output_fault(mm[i, j], fault)
+        s = mm / F32(8.0)
         s = np.where(visible, s, F32(-1e9)).astype(F32)
         m = np.max(s, axis=-1, keepdims=True)
         e = np.exp((s - m).astype(F32).astype(np.float64))
@@ -117,7 +144,25 @@ def attention(qq, sq, kq, sk, vq, sv, key_mask=None, causal=False, q_pos0=0, ret
         pq = np.rint((p.astype(F32) * QMAX).astype(F32))
         phat = (pq.astype(F32) / QMAX).astype(F32)
         vhat = (vq[:, sl].astype(F32) * sv).astype(F32)
-        ctx[:, sl] = (phat.astype(np.float64) @ vhat.astype(np.float64)).astype(F32)
+        c_h = (phat.astype(np.float64) @ vhat.astype(np.float64))
+        if fault and fault["target"] == "pv":
+            if ft.startswith("INPUT") and fault["index"][1] == h:      # P tensor [1,8,Tq,Tk]
+                _, _, i, j = fault["index"]
+                pf = F32(flip_int8_bit(int(pq[i, j]), fault["bit"])) / QMAX
+                w0, w1 = (fault["window_start"], min(dk, fault["window_start"] + fault["window_len"])) if fault["window_len"] > 0 else (0, dk)
+                c_h[i, w0:w1] += (np.float64(pf) - np.float64(phat[i, j])) * vhat[j, w0:w1].astype(np.float64)
+            elif ft.startswith("WEIGHT") and fault["index"][2] // dk == h:   # V Round tensor [1,Tk,512]
+                _, j, c = fault["index"]
+                d = c % dk
+                v0 = int(vq[j, h * dk + d]); vf = flip_int8_bit(v0, fault["bit"])
+                w0, w1 = (fault["window_start"], min(Tq, fault["window_start"] + fault["window_len"])) if fault["window_len"] > 0 else (0, Tq)
+                dv = np.float64(F32(F32(vf) * sv[j, 0])) - np.float64(vhat[j, d])
+                c_h[w0:w1, d] += phat[w0:w1, j].astype(np.float64) * dv
+        c_h = c_h.astype(F32)
+        if fault and fault["target"] == "pv" and ft.startswith("RANDOM") and fault["index"][1] == h:
+            _, _, i, d = fault["index"]
+            c_h[i, d] = apply_output_fault(c_h[i, d], fault)
+        ctx[:, sl] = c_h
         pq_all[h] = pq.astype(np.uint8)
         p_all[h] = p
     if return_all:

@@ -80,7 +80,7 @@ class Trace(dict):
 
 
 def _linear(w, prefix: str, x: np.ndarray, mode: str, relu=False, residual=None, quantize_output=False, cap=None, cap_name=None,
-            xq_sx=None):
+            xq_sx=None, fault=None):
     """W8A8Linear.forward (quant_linear.py:111-119): act RowQuant, weight RowQuant (recomputed), F.linear, [output quant]."""
     shape = x.shape
     x2 = x.reshape(-1, shape[-1])
@@ -89,7 +89,20 @@ def _linear(w, prefix: str, x: np.ndarray, mode: str, relu=False, residual=None,
     bias = w[prefix + ".bias"]
     if mode == "int-exact":
         acc = ox.int_matmul(xq, wq)
+        if fault is not None and fault["type"].startswith(("INPUT", "WEIGHT")):
+            # integer-domain rank-1 update of SURVEY.md App. D
+            K_ = xq.shape[1]
+            r, k = divmod(int(fault["flat_index"]), K_)
+            if fault["type"].startswith("INPUT"):
+                q0 = int(xq[r, k]); delta = ox.flip_int8_bit(q0, fault["bit"]) - q0
+                acc[r, :] += delta * wq[:, k].astype(np.int32)
+            else:
+                q0 = int(wq[r, k]); delta = ox.flip_int8_bit(q0, fault["bit"]) - q0
+                acc[:, r] += xq[:, k].astype(np.int32) * delta
         mm = ox.linear_epilogue(acc, sx, sw)
+        if fault is not None and fault["type"].startswith("RANDOM"):
+            r, c = divmod(int(fault["flat_index"]), mm.shape[1])
+            mm[r, c] = ox.apply_output_fault(mm[r, c], fault)
     else:
         mm = (ox.dequant(xq, sx) @ ox.dequant(wq, sw).T).astype(F32)
     if cap is not None and cap_name:
@@ -107,14 +120,17 @@ def _linear(w, prefix: str, x: np.ndarray, mode: str, relu=False, residual=None,
     return y
 
 
-def _attention(qq, sq, kq, sk, vq, sv, mask, mode: str, causal=False, q_pos0=0):
+def _attention(qq, sq, kq, sk, vq, sv, mask, mode: str, causal=False, q_pos0=0, fault=None):
     """attention.py:23-36 for a batch.  qq [B,Tq,512] int8, sq [B,Tq,1]; mask: bool [B,1,Tk] or None."""
     B, Tq, _ = qq.shape
     out = np.zeros((B, Tq, D_MODEL), dtype=F32)
     for b in range(B):
         km = mask[b, 0] if mask is not None else None
         if mode == "int-exact":
-            out[b] = ox.attention(qq[b], sq[b].reshape(-1), kq[b], sk[b].reshape(-1), vq[b], sv[b].reshape(-1), km, causal, q_pos0)
+            fb = None
+            if fault is not None and fault["index"][0] == b:
+                fb = fault
+            out[b] = ox.attention(qq[b], sq[b].reshape(-1), kq[b], sk[b].reshape(-1), vq[b], sv[b].reshape(-1), km, causal, q_pos0, fault=fb)
         else:
             out[b] = _attention_ref_float(qq[b], sq[b], kq[b], sk[b], vq[b], sv[b], km, causal, q_pos0)
     return out
@@ -145,21 +161,23 @@ def _norm(w, prefix, x):
 
 
 # ------------------------------------------------------------------------------------------------ encoder / decoder
-def encode(w, src_emb: np.ndarray, src_mask: Optional[np.ndarray], mode: str = "int-exact", n_layers: int = 6, cap: Optional[Trace] = None):
+def encode(w, src_emb: np.ndarray, src_mask: Optional[np.ndarray], mode: str = "int-exact", n_layers: int = 6, cap: Optional[Trace] = None,
+           fault: Optional[dict] = None):
     """Encoder.forward (encoder.py:14-18) on embedded input [B,S,512]; returns memory [B,S,512]."""
     x = src_emb.astype(F32)
     for l in range(n_layers):
         p = "encoder.layers.%d" % l
+        f = (lambda *t: fault if (fault is not None and fault["module"] == "Encoder" and fault["layer"] == l and fault["target"] in t) else None)  # noqa: E731
         ln = _norm(w, p + ".sublayer.0.norm", x)
         shared = ox.row_quant(ln.reshape(-1, D_MODEL))       # Q,K,V share one quantization of the LN output
         qq, sq = _linear(w, p + ".self_attn.linears.0", ln, mode, quantize_output=True, xq_sx=shared, cap=cap, cap_name="enc%d.q" % l)
         kq, sk = _linear(w, p + ".self_attn.linears.1", ln, mode, quantize_output=True, xq_sx=shared)
         vq, sv = _linear(w, p + ".self_attn.linears.2", ln, mode, quantize_output=True, xq_sx=shared)
-        ctx = _attention(qq, sq, kq, sk, vq, sv, src_mask, mode)
+        ctx = _attention(qq, sq, kq, sk, vq, sv, src_mask, mode, fault=f("qk", "pv"))
         x = _linear(w, p + ".self_attn.linears.3", ctx, mode, residual=x).reshape(x.shape)
         ln = _norm(w, p + ".sublayer.1.norm", x)
-        h = _linear(w, p + ".feed_forward.w_1", ln, mode, relu=True)
-        x = _linear(w, p + ".feed_forward.w_2", h, mode, residual=x).reshape(x.shape)
+        h = _linear(w, p + ".feed_forward.w_1", ln, mode, relu=True, fault=f("ffn1"))
+        x = _linear(w, p + ".feed_forward.w_2", h, mode, residual=x, fault=f("ffn2")).reshape(x.shape)
         if cap is not None:
             cap["enc%d.out" % l] = x.copy()
             cap["enc%d.qq" % l] = qq
@@ -178,7 +196,7 @@ def cross_kv(w, memory: np.ndarray, mode: str = "int-exact", n_layers: int = 6):
 
 
 def decode(w, tgt_emb: np.ndarray, memory: np.ndarray, src_mask, mode: str = "int-exact", n_layers: int = 6, ckv=None,
-           self_kv=None, pos0: int = 0):
+           self_kv=None, pos0: int = 0, fault: Optional[dict] = None):
     """Decoder.forward (decoder.py:13-16) on embedded target prefix [B,T,512] with the causal mask
     (subsequent_mask, utils.py:10-14).  With `self_kv` (list of per-layer dicts) only the new positions are given in
     tgt_emb (starting at pos0) and the keys/values of earlier positions come from / are appended to the cache:
@@ -187,6 +205,12 @@ def decode(w, tgt_emb: np.ndarray, memory: np.ndarray, src_mask, mode: str = "in
     ckv = ckv if ckv is not None else cross_kv(w, memory, mode, n_layers)
     for l in range(n_layers):
         p = "decoder.layers.%d" % l
+
+        def f(*t, _l=l):
+            if fault is None or fault["module"] != "Decoder" or fault["layer"] != _l or fault["target"] not in t:
+                return None
+            # the attention oracle addresses faults by the reference's target names qk / pv
+            return dict(fault, target={"cqk": "qk", "cpv": "pv"}.get(fault["target"], fault["target"]))
         ln = _norm(w, p + ".sublayer.0.norm", x)
         shared = ox.row_quant(ln.reshape(-1, D_MODEL))
         qq, sq = _linear(w, p + ".self_attn.linears.0", ln, mode, quantize_output=True, xq_sx=shared)
@@ -198,27 +222,27 @@ def decode(w, tgt_emb: np.ndarray, memory: np.ndarray, src_mask, mode: str = "in
                 kq = np.concatenate([c["k"], kq], axis=1); sk = np.concatenate([c["sk"], sk], axis=1)
                 vq = np.concatenate([c["v"], vq], axis=1); sv = np.concatenate([c["sv"], sv], axis=1)
             c["k"], c["sk"], c["v"], c["sv"] = kq, sk, vq, sv
-        ctx = _attention(qq, sq, kq, sk, vq, sv, None, mode, causal=True, q_pos0=pos0)
+        ctx = _attention(qq, sq, kq, sk, vq, sv, None, mode, causal=True, q_pos0=pos0, fault=f("qk", "pv"))
         x = _linear(w, p + ".self_attn.linears.3", ctx, mode, residual=x).reshape(x.shape)
         ln = _norm(w, p + ".sublayer.1.norm", x)
         cq, scq = _linear(w, p + ".src_attn.linears.0", ln, mode, quantize_output=True)
         (ckq, sck), (cvq, scv) = ckv[l]
-        ctx = _attention(cq, scq, ckq, sck, cvq, scv, src_mask, mode)
+        ctx = _attention(cq, scq, ckq, sck, cvq, scv, src_mask, mode, fault=f("cqk", "cpv"))
         x = _linear(w, p + ".src_attn.linears.3", ctx, mode, residual=x).reshape(x.shape)
         ln = _norm(w, p + ".sublayer.2.norm", x)
-        h = _linear(w, p + ".feed_forward.w_1", ln, mode, relu=True)
-        x = _linear(w, p + ".feed_forward.w_2", h, mode, residual=x).reshape(x.shape)
+        h = _linear(w, p + ".feed_forward.w_1", ln, mode, relu=True, fault=f("ffn1"))
+        x = _linear(w, p + ".feed_forward.w_2", h, mode, residual=x, fault=f("ffn2")).reshape(x.shape)
     return _norm(w, "decoder.norm", x)
 
 
 def greedy_decode(w, src_ids: np.ndarray, src_mask: np.ndarray, max_len: int = 72, start_symbol: int = 0, mode: str = "int-exact",
-                  n_layers: int = 6, kv_cache: bool = True, return_margins: bool = False, pe=None):
+                  n_layers: int = 6, kv_cache: bool = True, return_margins: bool = False, pe=None, fault: Optional[dict] = None):
     """greedy_decode (parallelized_inject_onnx_transformer.py:536-758, batched as batch_output.py:659-672):
     memory = encode(src); ys = [<s>]; 71 x { out = decode(ys); next = argmax(generator(out[:, -1])); ys = cat }.
     No early stop at </s>.  kv_cache=False re-runs the full prefix every step exactly as the reference does."""
     B = src_ids.shape[0]
     pe = pe if pe is not None else ox.positional_encoding(max(max_len, src_ids.shape[1]) + 1)
-    memory = encode(w, ox.embed(src_ids, w["src_embed.0.lut.weight"], pe), src_mask, mode, n_layers)
+    memory = encode(w, ox.embed(src_ids, w["src_embed.0.lut.weight"], pe), src_mask, mode, n_layers, fault=fault)
     ckv = cross_kv(w, memory, mode, n_layers)
     ys = np.full((B, 1), start_symbol, dtype=np.int64)
     caches = [dict() for _ in range(n_layers)] if kv_cache else None
@@ -226,7 +250,8 @@ def greedy_decode(w, src_ids: np.ndarray, src_mask: np.ndarray, max_len: int = 7
     for i in range(max_len - 1):
         if kv_cache:
             emb = ox.embed(ys[:, i:i + 1], w["tgt_embed.0.lut.weight"], pe, pos0=i)
-            out = decode(w, emb, memory, src_mask, mode, n_layers, ckv, caches, pos0=i)
+            out = decode(w, emb, memory, src_mask, mode, n_layers, ckv, caches, pos0=i,
+                         fault=fault if (fault is not None and fault.get("step", 0) == i) else None)
         else:
             emb = ox.embed(ys, w["tgt_embed.0.lut.weight"], pe)
             out = decode(w, emb, memory, src_mask, mode, n_layers, ckv)

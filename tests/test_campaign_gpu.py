@@ -1,0 +1,69 @@
+"""Fault-injection campaign on the fused engine vs the oracle model, trial for trial (north star: "Fault-injection
+outcome classifications must match trial-for-trial"), on a small model so the oracle finishes in seconds."""
+import numpy as np
+import pytest
+import torch
+
+from onnx_transformer_b200 import campaign as C
+from onnx_transformer_b200 import weights as W
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+
+N_LAYERS, SRC_V, TGT_V, B, S, MAXLEN = 2, 97, 37, 4, 16, 10
+
+
+def _oracle_fault(tr: C.Trial, S_, T_):
+    operand = "input" if tr.inject_type.startswith("INPUT") else ("weight" if tr.inject_type.startswith("WEIGHT") else "output")
+    shape = C._tensor_shape(tr.module, tr.target, operand, S_, T_)
+    idx = tuple(int(i) for i in np.unravel_index(tr.flat_index, shape))
+    return dict(module=tr.module, layer=tr.layer, target=tr.target, type=tr.inject_type, bit=tr.bit, flat_index=tr.flat_index, index=idx,
+                window_start=tr.window_start, window_len=tr.window_len, value_bits=tr.value_bits, step=0)
+
+
+def test_trials_match_oracle_outcomes(tmp_path):
+    from onnx_transformer_b200.engine import QuantizedTransformer
+    fw = W.init_float_weights(21, SRC_V, TGT_V, N_LAYERS, randomize_norms=True)
+    # a random-init model rarely emits </s>: alias it to a frequently generated token so that all outcome classes occur
+    fw["generator.proj.weight"][W.EOS_ID] = fw["generator.proj.weight"][19]
+    fw["generator.proj.bias"][W.EOS_ID] = fw["generator.proj.bias"][19]
+    eng = QuantizedTransformer(fw, n_layers=N_LAYERS, max_len=MAXLEN)
+    wq = om.get_quantized(fw, None, N_LAYERS)
+    ids, mask = W.synthetic_tokens(21, B, S, SRC_V)
+    trials = C.make_trials(60, 0, B, S, n_layers=N_LAYERS)
+    csv = str(tmp_path / "results.csv")
+    res = C.run_trials(eng, ids, mask, trials, csv)
+    assert len(res) == len(trials)
+    rows = open(csv).read().strip().split("\n")
+    assert len(rows) == len(trials) and all(len(r.split(",")) == 5 for r in rows)
+    golden = {}
+    agree, confident, confident_agree = 0, 0, 0
+    for tr, r in zip(trials, res):
+        b = tr.sentence
+        if b not in golden:
+            golden[b] = om.greedy_decode(wq, ids[b:b + 1], mask[b:b + 1], MAXLEN, 0, "int-exact", N_LAYERS, return_margins=True)
+        g_ys, g_margins, _ = golden[b]
+        f_ys, f_margins, _ = om.greedy_decode(wq, ids[b:b + 1], mask[b:b + 1], MAXLEN, 0, "int-exact", N_LAYERS, return_margins=True,
+                                              fault=_oracle_fault(tr, S, 1))
+        ref = C.classify(g_ys[0], f_ys[0])
+        same = ref["outcome"] == r["outcome"] and ref["tokens_equal"] == r["tokens_equal"]
+        agree += same
+        # a trial is "confident" when neither oracle decode had a near-tie (float tolerance class cannot flip a token)
+        if min(g_margins.min(), f_margins.min()) > 0.05:
+            confident += 1
+            confident_agree += same
+    assert confident >= 10
+    assert confident_agree == confident, (confident_agree, confident)
+    assert agree >= 0.9 * len(trials)
+    # resume: a second run skips every trial id already in the CSV
+    assert C.run_trials(eng, ids, mask, trials, csv) == []
+
+
+def test_bleu_method4_and_classification():
+    g = [5, 6, 7, 8, 9, 10]
+    assert C.sentence_bleu_method4(g, g) == pytest.approx(1.0)
+    assert 0.0 < C.sentence_bleu_method4(g, [5, 6, 7, 30, 9, 10]) < 1.0
+    assert C.sentence_bleu_method4(g, [40, 41]) == 0.0
+    ys = np.array([0, 5, 6, 1, 9, 9]); ys2 = np.array([0, 5, 7, 1, 9, 9]); ys3 = np.array([0, 5, 6, 7, 8, 9])
+    assert C.classify(ys, ys)["outcome"] == "masked" and C.classify(ys, ys2)["outcome"] == "changed"
+    assert C.classify(ys, ys3)["outcome"] == "no-EOS"

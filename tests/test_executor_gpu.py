@@ -1,0 +1,120 @@
+"""GPU parity of the drop-in node-by-node executor (onnx_transformer_b200.executor: run_module / inference /
+execute_node with the reference's fault hooks) against the oracle's numpy restatement of the reference executor, on the
+same graph, inputs and explicit random draws."""
+import numpy as np
+import pytest
+import torch
+
+from onnx_transformer_b200 import faults
+from onnx_transformer_b200 import graph as G
+from onnx_transformer_b200 import weights as W
+from oracle import executor as oe
+from oracle import intexact as ox
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from onnx_transformer_b200 import executor as ex
+    fw = W.init_float_weights(5, 67, 59, 2, randomize_norms=True)
+    w = om.get_quantized(fw, None, 2)
+    enc, dec = G.build_encoder_graph(w, batch=2, n_layers=2), G.build_decoder_graph(w, batch=2, n_layers=2)
+    ids, mask = W.synthetic_tokens(11, 2, 5, 67, min_len=3)
+    x = ox.embed(ids, w["src_embed.0.lut.weight"], ox.positional_encoding(32))
+    return ex, w, enc, dec, x, mask
+
+
+def _int_tensor_mismatch(wd_gpu, wd_ref, names):
+    bad, tot = 0, 0
+    for n in names:
+        a, b = wd_gpu[n].cpu().numpy(), wd_ref[n]
+        assert a.shape == b.shape, n
+        assert np.max(np.abs(a - b)) <= 1, n
+        bad += int(np.count_nonzero(a != b)); tot += a.size
+    return bad / tot
+
+
+def test_encoder_walk_matches_oracle_executor(setup):
+    ex, w, enc, dec, x, mask = setup
+    ins = {"global_in": x, "global_in_1": mask}
+    wd, g = ex.prepare_inference(enc, ins)
+    out, wd = ex.run_module("Encoder", ins, None, wd, g, None)
+    assert list(out.keys()) == ["global_out"] and out["global_out"].is_cuda
+    rwd, rg = oe.prepare_inference(enc, ins)
+    rout, rwd = oe.run_module("Encoder", ins, None, rwd, rg, None, "int-exact")
+    np.testing.assert_allclose(out["global_out"].cpu().numpy(), rout["global_out"], rtol=1e-3, atol=2e-2)
+    # every intermediate retained under its ONNX name; integer (Round) tensors bit-exact up to boundary flips
+    names = [n.output[0] for n in enc.node]
+    assert all(n in wd for n in names)
+    rounds = [n.output[0] for n in enc.node if n.op_type == "Round"]
+    assert _int_tensor_mismatch(wd, rwd, rounds) < 2e-3
+    # first-layer tensors have seen no float reduction other than LayerNorm: essentially exact
+    assert _int_tensor_mismatch(wd, rwd, ["Round_0_out0", "Round_36_out0", "Round_37_out0"]) < 1e-4
+    mm = wd["MatMul_0_out0"].cpu().numpy()
+    np.testing.assert_allclose(mm, rwd["MatMul_0_out0"], rtol=1e-5, atol=1e-5)
+
+
+def test_decoder_walk_matches_oracle_executor(setup):
+    ex, w, enc, dec, x, mask = setup
+    memory = om.encode(w, x, mask, "int-exact", 2)
+    ys = np.array([[0, 7, 9], [0, 4, 33]])
+    temb = ox.embed(ys, w["tgt_embed.0.lut.weight"], ox.positional_encoding(32))
+    sub = (np.triu(np.ones((1, 3, 3)), k=1) == 0).astype(np.int64)
+    ins = {"global_in": temb, "global_in_1": memory, "global_in_2": mask, "global_in_3": sub}
+    wd, g = ex.prepare_inference(dec, ins)
+    out, wd = ex.run_module("Decoder", ins, None, wd, g, None)
+    rwd, rg = oe.prepare_inference(dec, ins)
+    rout, rwd = oe.run_module("Decoder", ins, None, rwd, rg, None, "int-exact")
+    np.testing.assert_allclose(out["global_out"].cpu().numpy(), rout["global_out"], rtol=1e-3, atol=3e-2)
+    assert _int_tensor_mismatch(wd, rwd, ["Round_60_out0", "Round_61_out0", "Round_73_out0"]) < 1e-4
+
+
+@pytest.mark.parametrize("target,fault_model,bit,draws", [
+    ("MatMul_6", "INPUT", 6, {"target_indices": [1, 2, 77]}),
+    ("MatMul_7", "WEIGHT", 7, {"target_indices": [300, 1999]}),
+    ("MatMul_3", "INPUT16", 5, {"target_indices": [0, 1, 100], "window_start": 0}),
+    ("MatMul_12", "WEIGHT16", 3, {"target_indices": [0, 3, 130], "window_start": 0, "window_len": 2}),
+    ("MatMul_4", "INPUT", 7, {"target_indices": [1, 2, 3, 1]}),
+    ("MatMul_3", "RANDOM_BITFLIP", None, {"target_indices": [1, 2, 3, 4], "flip_bit": 30}),
+    ("MatMul_7", "RANDOM", None, {"target_indices": [0, 1, 9], "random_bits": 0x41200000}),
+])
+def test_fault_hooks_match_oracle_trial_for_trial(setup, target, fault_model, bit, draws):
+    ex, w, enc, dec, x, mask = setup
+    ins = {"global_in": x, "global_in_1": mask}
+    t = [d for d in faults.targets_from_graph(enc, "Encoder") if d["target_layer"] == target][0]
+    p_gpu = faults.build_inject_parameters(enc, t, fault_model, bit, rng_draws=dict(draws))
+    p_ref = faults.build_inject_parameters(enc, t, fault_model, bit, rng_draws=dict(draws))
+    wd, g = ex.prepare_inference(enc, ins)
+    gold, wdg = ex.run_module("Encoder", ins, None, wd, g, None)
+    golden_mm = wdg[t["output_tensor"]].clone()
+    wd2, g = ex.prepare_inference(enc, ins)
+    out, wd2 = ex.run_module("Encoder", ins, None, wd2, g, p_gpu)
+    rwd, rg = oe.prepare_inference(enc, ins)
+    rgold, rwdg = oe.run_module("Encoder", ins, None, rwd, rg, None, "int-exact")
+    r_golden_mm = rwdg[t["output_tensor"]].copy()
+    rwd2, rg = oe.prepare_inference(enc, ins)
+    rout, rwd2 = oe.run_module("Encoder", ins, None, rwd2, rg, p_ref, "int-exact")
+    assert p_gpu["faulty_trace"] in ([], None) and p_gpu["rng_draws_used"] == p_ref["rng_draws_used"]
+    # the injected perturbation (faulty - golden) of the target MatMul output: same support, same values
+    d_gpu = (wd2[t["output_tensor"]] - golden_mm).cpu().numpy()
+    d_ref = rwd2[t["output_tensor"]] - r_golden_mm
+    assert np.array_equal(d_gpu != 0, d_ref != 0) or np.count_nonzero((d_gpu != 0) != (d_ref != 0)) <= 2
+    assert np.count_nonzero(d_ref) >= 1
+    np.testing.assert_allclose(d_gpu, d_ref, rtol=2e-3, atol=1e-4 * max(1.0, float(np.abs(d_ref).max())))
+    # and the fault propagates to the module output identically (within the float tolerance class)
+    np.testing.assert_allclose(out["global_out"].cpu().numpy(), rout["global_out"], rtol=1e-3, atol=5e-2)
+
+
+def test_graph_file_roundtrip_and_numpy_inputs(setup, tmp_path):
+    ex, w, enc, dec, x, mask = setup
+    path = str(tmp_path / "encoder_try_cleaned.otg")
+    ex.save_graph(enc, path)
+    wd, g = ex.prepare_inference(path, {"global_in": x, "global_in_1": mask})
+    assert [n.name for n in g.node] == [n.name for n in enc.node] and len(g.initializer) == len(enc.initializer)
+    out, _ = ex.run_module("Encoder", {"global_in": x, "global_in_1": mask}, path, wd, g)
+    wd2, g2 = ex.prepare_inference(enc, {"global_in": x, "global_in_1": mask})
+    out2, _ = ex.run_module("Encoder", {"global_in": torch.from_numpy(x), "global_in_1": torch.from_numpy(mask)}, None, wd2, g2)
+    assert torch.equal(out["global_out"], out2["global_out"])
+    assert isinstance(ex.to_numpy(out)["global_out"], np.ndarray)
