@@ -26,7 +26,7 @@ def test_trials_match_oracle_outcomes(tmp_path):
     fw = W.init_float_weights(21, SRC_V, TGT_V, N_LAYERS, randomize_norms=True)
     # a random-init model rarely emits </s>: alias it to a frequently generated token so that all outcome classes occur
     fw["generator.proj.weight"][W.EOS_ID] = fw["generator.proj.weight"][19]
-    fw["generator.proj.bias"][W.EOS_ID] = fw["generator.proj.bias"][19]
+    fw["generator.proj.bias"][W.EOS_ID] = fw["generator.proj.bias"][19] + 0.3
     eng = QuantizedTransformer(fw, n_layers=N_LAYERS, max_len=MAXLEN)
     wq = om.get_quantized(fw, None, N_LAYERS)
     ids, mask = W.synthetic_tokens(21, B, S, SRC_V)
