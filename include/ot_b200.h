@@ -87,6 +87,14 @@ int ot_linear_w4a8(const int8_t* A, int64_t lda, const uint8_t* W4, int64_t ldw,
                    int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group,
                    const OtFault* fault, void* stream);
 
+/* a6+a7+a8..a10 in one kernel: A = RowQuant(LayerNorm(x)) is produced in shared memory by the GEMM's own warps
+ * (layer_norm.py:12-15 + quant_linear.py:31-43, op for op as ot_layernorm_quant) and fed to the MMA without a round trip
+ * through HBM; the rest as ot_linear_w8a8 (no fault hook: a fault trial uses the two separate entry points).  K must be 512. */
+int ot_ln_linear_w8a8(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                      const int8_t* W, int64_t ldw, int M, int N, int K,
+                      const float* col_scale, const float* bias, const float* residual, int64_t ldr, int relu,
+                      int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group, void* stream);
+
 /* Standalone nibble unpack: W4 [rows, cols/2] -> int8 [rows, cols] (sign-extended). */
 int ot_unpack_int4(const uint8_t* W4, int8_t* W8, int64_t rows, int64_t cols, void* stream);
 

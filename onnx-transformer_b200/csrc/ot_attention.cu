@@ -300,6 +300,139 @@ __global__ void __launch_bounds__(256, 1) attention_q8_kernel(const AttnArgs a) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Decode specialisation (Tq = 1, Tk <= 96, no fault, no probability dump): one CTA per sentence, warp h = head h,
+// K/V rows are read straight from the (L2-resident) cache -- no shared-memory staging, no block barrier before the
+// head merge.  Same arithmetic, op for op, as attention_q8_kernel.
+constexpr int kDecKeysPerLane = 3;
+__global__ void __launch_bounds__(256) attention_decode_kernel(const AttnArgs a) {
+  __shared__ __align__(16) float Cs[kDm];
+  const int step = a.step_dev ? *a.step_dev : 0;
+  const int Tk = a.step_dev ? step + 1 : a.Tk;
+  const int q_pos0 = a.step_dev ? step : a.q_pos0;
+  const int b = blockIdx.x;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int new0 = (a.k_new != nullptr) ? Tk - 1 : Tk;
+
+  // append this step's K/V head slice (and, by head 0, the scales) to the cache
+  if (a.k_new != nullptr) {
+    const int64_t src = static_cast<int64_t>(b) * a.ld_new + h * kDk;
+    const int64_t dst = (static_cast<int64_t>(b) * a.Tk_cap + new0) * a.ldk + h * kDk;
+    if (lane < 4) *reinterpret_cast<uint4*>(a.k + dst + lane * 16) = *reinterpret_cast<const uint4*>(a.k_new + src + lane * 16);
+    else if (lane < 8) *reinterpret_cast<uint4*>(a.v + dst + (lane - 4) * 16) = *reinterpret_cast<const uint4*>(a.v_new + src + (lane - 4) * 16);
+    if (h == 0 && lane == 8) {
+      const int64_t sdst = (static_cast<int64_t>(b) * a.Tk_cap + new0) * a.skv_stride;
+      a.sk[sdst] = a.sk_new[static_cast<int64_t>(b) * a.snew_stride];
+      a.sv[sdst] = a.sv_new[static_cast<int64_t>(b) * a.snew_stride];
+    }
+  }
+
+  uint32_t qw[16];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(a.q + static_cast<int64_t>(b) * a.ldq + h * kDk);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint4 t = __ldg(qp + w);
+      qw[4 * w] = t.x; qw[4 * w + 1] = t.y; qw[4 * w + 2] = t.z; qw[4 * w + 3] = t.w;
+    }
+  }
+  const float sqi = a.sq[static_cast<int64_t>(b) * a.sq_stride];
+
+  float sc[kDecKeysPerLane], svl[kDecKeysPerLane];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
+    const int j = kk * 32 + lane;
+    sc[kk] = -INFINITY;
+    svl[kk] = 0.f;
+    if (j < Tk) {
+      const bool fresh = j >= new0;
+      const int8_t* kp = fresh ? a.k_new + static_cast<int64_t>(b) * a.ld_new + h * kDk
+                               : a.k + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk;
+      int dot = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint4 t = *reinterpret_cast<const uint4*>(kp + w * 16);
+        dot = __dp4a(static_cast<int>(qw[4 * w]), static_cast<int>(t.x), dot);
+        dot = __dp4a(static_cast<int>(qw[4 * w + 1]), static_cast<int>(t.y), dot);
+        dot = __dp4a(static_cast<int>(qw[4 * w + 2]), static_cast<int>(t.z), dot);
+        dot = __dp4a(static_cast<int>(qw[4 * w + 3]), static_cast<int>(t.w), dot);
+      }
+      const float skj = fresh ? a.sk_new[static_cast<int64_t>(b) * a.snew_stride] : a.sk[(static_cast<int64_t>(b) * a.Tk_cap + j) * a.skv_stride];
+      svl[kk] = fresh ? a.sv_new[static_cast<int64_t>(b) * a.snew_stride] : a.sv[(static_cast<int64_t>(b) * a.Tk_cap + j) * a.skv_stride];
+      float s = __fdiv_rn(__fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), skj), 8.0f);
+      const bool keep = (a.mask_kind != 1) || a.key_mask[static_cast<int64_t>(b) * a.mask_stride + j] != 0;
+      const bool visible = keep && (a.mask_kind != 2 || j <= q_pos0);
+      sc[kk] = visible ? s : -1e9f;
+      mx = fmaxf(mx, sc[kk]);
+    }
+  }
+  mx = warp_max_f(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
+    if (kk * 32 + lane < Tk) {
+      sc[kk] = expf(__fsub_rn(sc[kk], mx));
+      sum += sc[kk];
+    }
+  }
+  sum = warp_sum_f(sum);
+  float pq[kDecKeysPerLane];
+#pragma unroll
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk)
+    pq[kk] = (kk * 32 + lane < Tk) ? rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f)) : 0.f;
+
+  // context: lane owns features 2*lane, 2*lane+1; keys in order j = 0..Tk-1 (same order as the generic kernel)
+  float acc0 = 0.f, acc1 = 0.f;
+  const int d0 = 2 * lane;
+#pragma unroll
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
+    if (kk * 32 >= Tk) break;
+    const int jn = min(32, Tk - kk * 32);
+#pragma unroll 4
+    for (int jj = 0; jj < jn; ++jj) {
+      const float p = __shfl_sync(0xffffffffu, pq[kk], jj);
+      const float svj = __shfl_sync(0xffffffffu, svl[kk], jj);
+      if (p == 0.f) continue;
+      const int j = kk * 32 + jj;
+      const int8_t* vp = (j >= new0) ? a.v_new + static_cast<int64_t>(b) * a.ld_new + h * kDk
+                                     : a.v + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk;
+      const char2 vv = *reinterpret_cast<const char2*>(vp + d0);
+      const float ph = __fdiv_rn(p, 127.0f);
+      acc0 = fmaf(ph, __fmul_rn(__int2float_rn(vv.x), svj), acc0);
+      acc1 = fmaf(ph, __fmul_rn(__int2float_rn(vv.y), svj), acc1);
+    }
+  }
+  *reinterpret_cast<float2*>(Cs + h * kDk + d0) = make_float2(acc0, acc1);
+  __syncthreads();
+  if (h == 0) {
+    const int64_t row = b;
+    float4 v[4];
+    float amax = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      v[t] = *reinterpret_cast<const float4*>(Cs + (t * 32 + lane) * 4);
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[t].x), fabsf(v[t].y)), fmaxf(fabsf(v[t].z), fabsf(v[t].w))));
+    }
+    if (a.ctx) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) *reinterpret_cast<float4*>(a.ctx + row * a.ld_ctx + (t * 32 + lane) * 4) = v[t];
+    }
+    if (a.ctx_q) {
+      const float s = __fdiv_rn(fmaxf(warp_max_f(amax), 1e-5f), 127.0f);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int q0i = __float2int_rn(rintf(__fdiv_rn(v[t].x, s))), q1i = __float2int_rn(rintf(__fdiv_rn(v[t].y, s)));
+        const int q2i = __float2int_rn(rintf(__fdiv_rn(v[t].z, s))), q3i = __float2int_rn(rintf(__fdiv_rn(v[t].w, s)));
+        const uint32_t w = (static_cast<uint32_t>(q0i) & 0xFFu) | ((static_cast<uint32_t>(q1i) & 0xFFu) << 8) |
+                           ((static_cast<uint32_t>(q2i) & 0xFFu) << 16) | ((static_cast<uint32_t>(q3i) & 0xFFu) << 24);
+        *reinterpret_cast<uint32_t*>(a.ctx_q + row * kDm + (t * 32 + lane) * 4) = w;
+      }
+      if (lane == 0) a.ctx_s[row] = s;
+    }
+  }
+}
+
 template <int QT>
 static size_t attn_smem_bytes(int Tk) {
   const int Tk_pad = (Tk + 31) & ~31;
@@ -357,6 +490,12 @@ extern "C" int ot_attention_q8(const int8_t* q, int64_t ldq, const float* sq, in
   a.ctx = ctx; a.ld_ctx = ld_ctx; a.ctx_q = ctx_q; a.ctx_s = ctx_s; a.probs_q = probs_q;
   if (fault) a.fault = *fault; else a.fault.mode = OT_FAULT_NONE;
   cudaStream_t s = as_stream(stream);
+  if (Tq == 1 && tk_max <= 32 * kDecKeysPerLane && a.fault.mode == OT_FAULT_NONE && probs_q == nullptr) {
+    attention_decode_kernel<<<B, 256, 0, s>>>(a);
+    OT_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return OT_OK;
+  }
   if (Tq == 1) return launch_attention<1>(a, tk_max, s);
   if (Tq <= 16 || tk_max > 128) return launch_attention<16>(a, tk_max, s);
   return launch_attention<32>(a, tk_max, s);

@@ -29,7 +29,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 128;  // int8 elements == bytes: one 128-byte swizzle row
 constexpr int kUmmaK = 32;    // kind::i8 consumes 32 bytes of K per instruction
 constexpr int kGemmThreads = 192;
-constexpr int kMaxCluster = 8;
+constexpr int kMaxCluster = 16;  // > 8 is a non-portable cluster size (opt-in per kernel)
 
 struct GemmArgs {
   int M, N, K;
@@ -49,6 +49,12 @@ struct GemmArgs {
   float* out_scale;
   int cluster_n;  // CTAs per quant group (OT_OUT_Q8), else 1
   int w4;         // W is int4-packed: unpack in shared memory
+  // LayerNorm + RowQuant prologue (MODE 2): the A operand is produced in shared memory from fp32 rows
+  const float* ln_x;
+  int64_t ln_ldx;
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
   OtFault fault;
 };
 
@@ -62,7 +68,8 @@ struct GemmSmem {
   static constexpr int SLOT_OFF = BAR_OFF + (3 * STAGES + 1) * 8;  // TMEM base address slot
   static constexpr int ROWMAX_OFF = BAR_OFF + 256;                 // float [kMaxCluster][128]
   static constexpr int COLP_OFF = ROWMAX_OFF + kMaxCluster * kBlockM * 4;  // float col_scale[BLOCK_N], bias[BLOCK_N]
-  static constexpr int B4_OFF = COLP_OFF + 2 * 256 * 4;                    // 128-byte aligned (TMA destination)
+  static constexpr int ROWS_OFF = COLP_OFF + 2 * 256 * 4;                  // float row_scale[128] (LN prologue)
+  static constexpr int B4_OFF = ROWS_OFF + kBlockM * 4;                    // 128-byte aligned (TMA destination)
   static_assert((3 * STAGES + 1) * 8 + 16 <= 256, "barrier block overflows its 256-byte slot");
   static constexpr int TOTAL_W8 = B4_OFF + 1024;  // + slack for the 1024-byte alignment of the tile base
   static constexpr int TOTAL_W4 = B4_OFF + STAGES * B4_BYTES + 1024;
@@ -214,9 +221,13 @@ __device__ __forceinline__ int quant_exact(float y, float s, float r) {
   return __float2int_rn(n);
 }
 
-template <int BLOCK_N, int STAGES, bool W4>
+// MODE 0: int8 weights; 1: packed int4 weights unpacked in shared memory; 2: int8 weights, A = RowQuant(LayerNorm(x)) computed
+// by the epilogue warps straight into the swizzled operand tile (K = 512 = STAGES k-blocks, all resident).
+template <int BLOCK_N, int STAGES, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs g) {
+  constexpr bool W4 = (MODE == 1);
+  constexpr bool ALN = (MODE == 2);
   using L = GemmSmem<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -233,6 +244,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   float* rowmax_x = reinterpret_cast<float*>(smem + L::ROWMAX_OFF);
   float* s_cs = reinterpret_cast<float*>(smem + L::COLP_OFF);
   float* s_bias = s_cs + 256;
+  float* s_rows = reinterpret_cast<float*>(smem + L::ROWS_OFF);
   uint8_t* sB4 = smem + L::B4_OFF;
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) / 32, 0);
@@ -274,7 +286,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t phase = (kb / STAGES) & 1;
         mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1);
         const uint32_t fb = smem_u32(&full_bar[s]);
-        if (W4) {
+        if (ALN) {
+          mbar_arrive_expect_tx(fb, L::B_BYTES);
+          tma_load_2d(smem_u32(sB + s * L::B_BYTES), &tmap_b, fb, kb * kBlockK, n_blk * BLOCK_N);
+        } else if (W4) {
           mbar_arrive_expect_tx(fb, L::A_BYTES + L::B4_BYTES);
           tma_load_2d(smem_u32(sA + s * L::A_BYTES), &tmap_a, fb, kb * kBlockK, m_blk * kBlockM);
           tma_load_2d(smem_u32(sB4 + s * L::B4_BYTES), &tmap_b, fb, kb * (kBlockK / 2), n_blk * BLOCK_N);
@@ -290,6 +305,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_i8(kBlockM, BLOCK_N);
+      if (ALN) mbar_wait(smem_u32(&unpacked_bar[0]), 0);   // the LN prologue has written all of A
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         const int s = kb % STAGES;
         const uint32_t phase = (kb / STAGES) & 1;
@@ -355,6 +371,67 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
 
+    if (ALN) {
+      // A-operand producer: LayerNorm (layer_norm.py:12-15) + RowQuant (quant_linear.py:31-43) of this tile's rows, op for op
+      // as layernorm_quant_kernel<4>; one warp per row, 4 x float4 per lane; the int8 row goes into the 4 resident k-block
+      // tiles in the 128-byte-swizzled layout the MMA descriptors expect.
+      const int we = warp_idx - 2;
+      const float nf = 512.0f;
+      for (int r = we; r < kBlockM; r += 4) {
+        const int grow = m_blk * kBlockM + r;
+        if (grow >= g.M) break;
+        const float4* xr = reinterpret_cast<const float4*>(g.ln_x + static_cast<int64_t>(grow) * g.ln_ldx);
+        float4 v[4];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i] = __ldg(xr + i * 32 + lane);
+          sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mu = __fdiv_rn(sum, nf);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i].x = __fsub_rn(v[i].x, mu); v[i].y = __fsub_rn(v[i].y, mu);
+          v[i].z = __fsub_rn(v[i].z, mu); v[i].w = __fsub_rn(v[i].w, mu);
+          sq += (__fmul_rn(v[i].x, v[i].x) + __fmul_rn(v[i].y, v[i].y)) + (__fmul_rn(v[i].z, v[i].z) + __fmul_rn(v[i].w, v[i].w));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        float var = __fdiv_rn(sq, nf);
+        var = __fdiv_rn(__fmul_rn(var, nf), nf - 1.0f);
+        const float denom = __fadd_rn(__fsqrt_rn(var), g.ln_eps);
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 ga = __ldg(reinterpret_cast<const float4*>(g.ln_gamma) + i * 32 + lane);
+          const float4 be = __ldg(reinterpret_cast<const float4*>(g.ln_beta) + i * 32 + lane);
+          v[i].x = __fadd_rn(__fdiv_rn(__fmul_rn(ga.x, v[i].x), denom), be.x);
+          v[i].y = __fadd_rn(__fdiv_rn(__fmul_rn(ga.y, v[i].y), denom), be.y);
+          v[i].z = __fadd_rn(__fdiv_rn(__fmul_rn(ga.z, v[i].z), denom), be.z);
+          v[i].w = __fadd_rn(__fdiv_rn(__fmul_rn(ga.w, v[i].w), denom), be.w);
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const float sc = __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int q0 = __float2int_rn(rintf(__fdiv_rn(v[i].x, sc))), q1 = __float2int_rn(rintf(__fdiv_rn(v[i].y, sc)));
+          const int q2 = __float2int_rn(rintf(__fdiv_rn(v[i].z, sc))), q3 = __float2int_rn(rintf(__fdiv_rn(v[i].w, sc)));
+          const uint32_t w = (static_cast<uint32_t>(q0) & 0xFFu) | ((static_cast<uint32_t>(q1) & 0xFFu) << 8) |
+                             ((static_cast<uint32_t>(q2) & 0xFFu) << 16) | ((static_cast<uint32_t>(q3) & 0xFFu) << 24);
+          // k = i*128 + lane*4 -> k-block i, 16-byte chunk lane/4 (XOR-swizzled with row % 8), byte (lane%4)*4
+          *reinterpret_cast<uint32_t*>(sA + i * L::A_BYTES + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) = w;
+        }
+        if (lane == 0) s_rows[r] = sc;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&unpacked_bar[0]));
+    }
+
     // Stage the per-column epilogue parameters once per CTA (overlaps the main loop), then wait for the accumulator.
     {
       const int t = (warp_idx - 2) * 32 + lane;
@@ -366,7 +443,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     const FaultCtx f = resolve_fault(g);
     const EpiFlags e = {g.bias != nullptr, g.relu != 0, f.mode == OT_FAULT_RANDOM_BITFLIP || f.mode == OT_FAULT_RANDOM};
-    const float sx = (g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f;
+    const float sx = ALN ? (row_ok ? s_rows[row_in_tile] : 1.0f) : ((g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f);
     const int col_base = n_blk * BLOCK_N;
 
     mbar_wait(smem_u32(tmem_full_bar), 0);
@@ -435,7 +512,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       const FaultCtx f = resolve_fault(g);
       const EpiFlags e = {g.bias != nullptr, g.relu != 0, f.mode == OT_FAULT_RANDOM_BITFLIP || f.mode == OT_FAULT_RANDOM};
-      const float sx = (g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f;
+      const float sx = ALN ? (row_ok ? s_rows[row_in_tile] : 1.0f) : ((g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f);
       const int col_base = n_blk * BLOCK_N;
 
       float amax = 0.0f;
@@ -551,21 +628,25 @@ static int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint
   return OT_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool W4>
+template <int BLOCK_N, int STAGES, int MODE>
 static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
+  constexpr bool W4 = (MODE == 1);
   using L = GemmSmem<BLOCK_N, STAGES>;
   CUtensorMap ta, tb;
-  int rc = get_tensor_map(&ta, g.A, g.M, g.K, g.lda, kBlockM, kBlockK, true);
-  if (rc) return rc;
+  int rc = OT_OK;
   if (W4) rc = get_tensor_map(&tb, g.W, g.N, g.K / 2, g.ldw, BLOCK_N, kBlockK / 2, false);
   else rc = get_tensor_map(&tb, g.W, g.N, g.K, g.ldw, BLOCK_N, kBlockK, true);
   if (rc) return rc;
+  if (MODE == 2) ta = tb;   // A is produced in shared memory by the LN prologue
+  else rc = get_tensor_map(&ta, g.A, g.M, g.K, g.lda, kBlockM, kBlockK, true);
+  if (rc) return rc;
 
-  auto kernel = gemm_i8_kernel<BLOCK_N, STAGES, W4>;
+  auto kernel = gemm_i8_kernel<BLOCK_N, STAGES, MODE>;
   const int smem = W4 ? L::TOTAL_W4 : L::TOTAL_W8;
   static bool attr_set = false;
   if (!attr_set) {
     OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -585,7 +666,7 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   return OT_OK;
 }
 
-template <bool W4>
+template <int MODE>
 static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
   const int m_tiles = (g.M + kBlockM - 1) / kBlockM;
   int block_n;
@@ -596,7 +677,7 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
     // largest admissible BLOCK_N that still gives >= one CTA per SM; for tiny M the smallest admissible one
     int best = -1;
     for (int bn : {256, 128, 64, 32}) {
-      if (quant_group % bn != 0 || quant_group / bn > kMaxCluster) continue;
+      if (quant_group % bn != 0 || quant_group / bn > kMaxCluster || (MODE == 2 && bn > 128)) continue;
       best = bn;
       if (static_cast<int64_t>(m_tiles) * (g.N / bn) >= 148) break;
     }
@@ -606,7 +687,7 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
   } else {
     int best = 32;
     for (int bn : {256, 128, 64, 32}) {
-      if (g.N % bn != 0) continue;
+      if (g.N % bn != 0 || (MODE == 2 && bn > 128)) continue;
       best = bn;
       if (static_cast<int64_t>(m_tiles) * (g.N / bn) >= 148) break;
     }
@@ -616,16 +697,25 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
   if (const char* force = getenv("OT_GEMM_FORCE_BN")) {   // tuning / profiling aid only
     const int bn = atoi(force);
     if ((bn == 32 || bn == 64 || bn == 128 || bn == 256) && g.N % bn == 0 &&
-        (g.out_kind != OT_OUT_Q8 || (quant_group % bn == 0 && quant_group / bn <= kMaxCluster))) {
+        (g.out_kind != OT_OUT_Q8 || (quant_group % bn == 0 && quant_group / bn <= kMaxCluster)) && !(MODE == 2 && bn > 128)) {
       block_n = bn;
       g.cluster_n = g.out_kind == OT_OUT_Q8 ? quant_group / bn : 1;
     }
   }
+  if (MODE == 2) {
+    OT_REQUIRE(block_n <= 128, "LN prologue needs BLOCK_N <= 128 (4 resident k-blocks)");
+    switch (block_n) {
+      case 128: return launch_gemm<128, 4, 2>(g, stream);
+      case 64: return launch_gemm<64, 4, 2>(g, stream);
+      default: return launch_gemm<32, 4, 2>(g, stream);
+    }
+  }
+  constexpr int M01 = MODE == 1 ? 1 : 0;
   switch (block_n) {
-    case 256: return launch_gemm<256, 3, W4>(g, stream);
-    case 128: return launch_gemm<128, 4, W4>(g, stream);
-    case 64: return launch_gemm<64, 4, W4>(g, stream);
-    default: return launch_gemm<32, 4, W4>(g, stream);
+    case 256: return launch_gemm<256, 3, M01>(g, stream);
+    case 128: return launch_gemm<128, 4, M01>(g, stream);
+    case 64: return launch_gemm<64, 4, M01>(g, stream);
+    default: return launch_gemm<32, 4, M01>(g, stream);
   }
 }
 
@@ -667,7 +757,7 @@ static int linear_common(bool w4, const int8_t* A, int64_t lda, const void* W, i
     g.fault.mode = OT_FAULT_NONE;
   }
   cudaStream_t s = as_stream(stream);
-  return w4 ? dispatch_gemm<true>(g, quant_group, s) : dispatch_gemm<false>(g, quant_group, s);
+  return w4 ? dispatch_gemm<1>(g, quant_group, s) : dispatch_gemm<0>(g, quant_group, s);
 }
 
 }  // namespace ot
@@ -678,6 +768,33 @@ extern "C" int ot_linear_w8a8(const int8_t* A, int64_t lda, const int8_t* W, int
                               const OtFault* fault, void* stream) {
   return ot::linear_common(false, A, lda, W, ldw, M, N, K, row_scale, col_scale, bias, residual, ldr, relu, out_kind, out, ldo,
                            out_scale, quant_group, fault, stream);
+}
+
+extern "C" int ot_ln_linear_w8a8(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, const int8_t* W, int64_t ldw,
+                                 int M, int N, int K, const float* col_scale, const float* bias, const float* residual, int64_t ldr,
+                                 int relu, int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group, void* stream) {
+  using namespace ot;
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(x && gamma && beta && W && out, "null operand");
+  OT_REQUIRE(K == 512, "the LayerNorm prologue is specialised for d_model = 512 (4 resident k-blocks)");
+  OT_REQUIRE(M > 0 && N > 0 && N % 32 == 0 && ldx % 4 == 0 && ldw % 16 == 0, "bad shape");
+  OT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "operands must be 16-byte aligned");
+  OT_REQUIRE(out_kind >= OT_OUT_I32 && out_kind <= OT_OUT_Q8, "bad out_kind");
+  if (out_kind == OT_OUT_Q8) OT_REQUIRE(out_scale != nullptr && ldo % 16 == 0, "OT_OUT_Q8 needs out_scale and a 16-byte pitch");
+  else OT_REQUIRE(ldo % 4 == 0, "out pitch must be a multiple of 4 elements");
+  GemmArgs g = {};
+  g.M = M; g.N = N; g.K = K;
+  g.A = nullptr; g.lda = 0;
+  g.W = W; g.ldw = ldw;
+  g.row_scale = nullptr; g.col_scale = col_scale; g.bias = bias;
+  g.residual = residual; g.ldr = ldr;
+  g.relu = relu; g.out_kind = out_kind;
+  g.out = out; g.ldo = ldo; g.out_scale = out_scale;
+  g.cluster_n = 1; g.w4 = 0;
+  g.ln_x = x; g.ln_ldx = ldx; g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps;
+  g.fault.mode = OT_FAULT_NONE;
+  return dispatch_gemm<2>(g, quant_group, as_stream(stream));
 }
 
 extern "C" int ot_linear_w4a8(const int8_t* A, int64_t lda, const uint8_t* W4, int64_t ldw, int M, int N, int K,

@@ -138,6 +138,7 @@ class QuantizedTransformer:
         self.pe = self._positional_encoding(max(max_len, 512) + 1)
         self._enc_ws: Dict[int, dict] = {}
         self._dec_ws: Dict[tuple, dict] = {}
+        self.fused_ln = True     # decode: LayerNorm+RowQuant as the prologue of the following GEMM (M <= 128)
         self.graph_replays = 0   # CUDA-graph replays of the greedy step (each replays ws['graph_launches'] kernels)
         torch.cuda.synchronize(self.dev)
 
@@ -272,6 +273,7 @@ class QuantizedTransformer:
         """One greedy step for all sentences: embed ys[:, t] -> 6 decoder layers on ONE new row per sentence (KV cache) ->
         final norm -> generator -> arg-max -> ys[:, t+1]; t lives in device memory (ws['step'])."""
         step = ws["step"]
+        fused_ln = self.fused_ln and B <= 128
         x = ws["x"][0]
         K.embed_pe(ws["ys"], self.tgt_lut, self.pe, seq_len=1, pos_dev=step, ids_stride=ws["ys"].stride(0), rows=B, out=x)
         cur = 0
@@ -280,8 +282,13 @@ class QuantizedTransformer:
             f = (lambda tgt: fault.to_ot() if (fault is not None and fault.module == "Decoder" and fault.layer == l and fault.target == tgt) else None)  # noqa: E731
             # --- masked self-attention over the KV cache
             nxt = ws["x"][1 - cur]
-            K.layernorm_quant(x, L["ln1"][0], L["ln1"][1], want_q=True, q=ws["xq"], s=ws["sx"])
-            self._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], f)
+            if fused_ln and not (f("q") or f("k") or f("v")):
+                # LayerNorm + RowQuant run as the GEMM's prologue (one launch instead of two, no int8 round trip)
+                K.ln_linear_w8a8(x, L["ln1"][0], L["ln1"][1], L["qkv"].wq, col_scale=L["qkv"].sw, bias=L["qkv"].bias, out_kind=K.OUT_Q8,
+                                 quant_group=D, out=ws["qkv"], out_scale=ws["sqkv"])
+            else:
+                K.layernorm_quant(x, L["ln1"][0], L["ln1"][1], want_q=True, q=ws["xq"], s=ws["sx"])
+                self._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], f)
             K.attention_q8(ws["qkv"], ws["sqkv"], ws["kc"][l], ws["vc"][l], ws["skc"][l], ws["svc"][l], B=B, Tq=1, Tk=1, Tk_cap=self.max_len,
                            ldq=3 * D, sq_stride=3, ldk=D, skv_stride=1,
                            k_new=ws["qkv"][:, D:], v_new=ws["qkv"][:, 2 * D:], sk_new=ws["sqkv"][:, 1:], sv_new=ws["sqkv"][:, 2:],
@@ -292,9 +299,13 @@ class QuantizedTransformer:
             x, cur = nxt, 1 - cur
             # --- cross-attention over the cached memory projections
             nxt = ws["x"][1 - cur]
-            K.layernorm_quant(x, L["ln2"][0], L["ln2"][1], want_q=True, q=ws["xq"], s=ws["sx"])
-            K.linear_w8a8(ws["xq"], L["cq"].wq, row_scale=ws["sx"], col_scale=L["cq"].sw, bias=L["cq"].bias, out_kind=K.OUT_Q8,
-                          quant_group=D, out=ws["q2"], out_scale=ws["sq2"], fault=f("cq"))
+            if fused_ln and not f("cq"):
+                K.ln_linear_w8a8(x, L["ln2"][0], L["ln2"][1], L["cq"].wq, col_scale=L["cq"].sw, bias=L["cq"].bias, out_kind=K.OUT_Q8,
+                                 quant_group=D, out=ws["q2"], out_scale=ws["sq2"])
+            else:
+                K.layernorm_quant(x, L["ln2"][0], L["ln2"][1], want_q=True, q=ws["xq"], s=ws["sx"])
+                K.linear_w8a8(ws["xq"], L["cq"].wq, row_scale=ws["sx"], col_scale=L["cq"].sw, bias=L["cq"].bias, out_kind=K.OUT_Q8,
+                              quant_group=D, out=ws["q2"], out_scale=ws["sq2"], fault=f("cq"))
             K.attention_q8(ws["q2"], ws["sq2"], ws["ckv"][:, 2 * D * l:], ws["ckv"][:, 2 * D * l + D:], ws["sckv"][:, 2 * l:], ws["sckv"][:, 2 * l + 1:],
                            B=B, Tq=1, Tk=S, Tk_cap=S, ldq=D, sq_stride=1, ldk=2 * D * nl, skv_stride=2 * nl, mask_kind=1,
                            key_mask=ws["mask"], mask_stride=S, want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"],
@@ -304,9 +315,13 @@ class QuantizedTransformer:
             x, cur = nxt, 1 - cur
             # --- feed forward
             nxt = ws["x"][1 - cur]
-            K.layernorm_quant(x, L["ln3"][0], L["ln3"][1], want_q=True, q=ws["xq"], s=ws["sx"])
-            K.linear_w8a8(ws["xq"], L["w1"].wq, row_scale=ws["sx"], col_scale=L["w1"].sw, bias=L["w1"].bias, relu=True,
-                          out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"], fault=f("ffn1"))
+            if fused_ln and not f("ffn1"):
+                K.ln_linear_w8a8(x, L["ln3"][0], L["ln3"][1], L["w1"].wq, col_scale=L["w1"].sw, bias=L["w1"].bias, relu=True,
+                                 out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"])
+            else:
+                K.layernorm_quant(x, L["ln3"][0], L["ln3"][1], want_q=True, q=ws["xq"], s=ws["sx"])
+                K.linear_w8a8(ws["xq"], L["w1"].wq, row_scale=ws["sx"], col_scale=L["w1"].sw, bias=L["w1"].bias, relu=True,
+                              out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"], fault=f("ffn1"))
             K.linear_w8a8(ws["hq"], L["w2"].wq, row_scale=ws["sh"], col_scale=L["w2"].sw, bias=L["w2"].bias, residual=x,
                           out_kind=K.OUT_F32, out=nxt, fault=f("ffn2"))
             x, cur = nxt, 1 - cur

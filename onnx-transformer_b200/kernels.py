@@ -79,6 +79,26 @@ def linear_w8a8(a_q: torch.Tensor, w_q: torch.Tensor, *, row_scale=None, col_sca
     return (out, out_scale) if out_kind == OUT_Q8 else out
 
 
+def ln_linear_w8a8(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, w_q: torch.Tensor, *, eps: float = 1e-6, col_scale=None,
+                   bias=None, residual=None, relu=False, out_kind=OUT_F32, quant_group=0, out=None, out_scale=None):
+    """LayerNorm + RowQuant prologue fused into the int8 GEMM (x fp32 [M,512])."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(w_q, torch.int8, "w_q")
+    M, K = x.shape
+    N = w_q.shape[0]
+    if out is None:
+        dt = {OUT_I32: torch.int32, OUT_F32: torch.float32, OUT_Q8: torch.int8}[out_kind]
+        out = torch.empty((M, N), dtype=dt, device=x.device)
+    if out_kind == OUT_Q8 and out_scale is None:
+        out_scale = torch.empty((M, N // quant_group), dtype=torch.float32, device=x.device)
+    rc = lib.ot_ln_linear_w8a8(_ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), eps, _ptr(w_q), w_q.stride(0), M, N, K, _ptr(col_scale),
+                               _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, 1 if relu else 0, out_kind,
+                               _ptr(out), out.stride(0), _ptr(out_scale), int(quant_group), _stream())
+    _lib.check(rc, "ot_ln_linear_w8a8")
+    return (out, out_scale) if out_kind == OUT_Q8 else out
+
+
 def unpack_int4(w4: torch.Tensor) -> torch.Tensor:
     _req(w4, torch.uint8, "w4")
     rows, half = w4.shape

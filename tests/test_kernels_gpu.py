@@ -68,6 +68,30 @@ def test_gemm_fused_requant_bit_exact(K, M, N, K_, group, relu):
     assert np.array_equal(q.cpu().numpy(), qr)
 
 
+@pytest.mark.parametrize("M,N,group,relu", [(64, 1536, 512, False), (64, 512, 512, False), (64, 2048, 2048, True), (200, 1536, 512, False), (1, 512, 512, False)])
+def test_gemm_layernorm_prologue_equals_unfused(K, M, N, group, relu):
+    """ot_ln_linear_w8a8 == ot_layernorm_quant followed by ot_linear_w8a8, bit for bit (same op order), and vs the oracle."""
+    rng = np.random.default_rng(77 + M + N)
+    x = (rng.normal(size=(M, 512)) * 2 + 0.5).astype(np.float32)
+    ga = (1 + 0.1 * rng.normal(size=512)).astype(np.float32)
+    be = (0.1 * rng.normal(size=512)).astype(np.float32)
+    w = rand_i8(rng, (N, 512))
+    sw = rng.uniform(1e-4, 1e-2, size=N).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    xd, gd, bd, wd, swd, bbd = dev(x), dev(ga), dev(be), dev(w), dev(sw), dev(b)
+    q, s = K.ln_linear_w8a8(xd, gd, bd, wd, col_scale=swd, bias=bbd, relu=relu, out_kind=K.OUT_Q8, quant_group=group)
+    _, xq, sx = K.layernorm_quant(xd, gd, bd, want_q=True)
+    q2, s2 = K.linear_w8a8(xq, wd, row_scale=sx, col_scale=swd, bias=bbd, relu=relu, out_kind=K.OUT_Q8, quant_group=group)
+    assert torch.equal(q, q2) and torch.equal(s, s2)
+    f = K.ln_linear_w8a8(xd, gd, bd, wd, col_scale=swd, bias=bbd, residual=xd if N == 512 else None, out_kind=K.OUT_F32)
+    f2 = K.linear_w8a8(xq, wd, row_scale=sx, col_scale=swd, bias=bbd, residual=xd if N == 512 else None, out_kind=K.OUT_F32)
+    assert torch.equal(f, f2)
+    # and against the oracle, given the kernel's own LayerNorm rounding (float tolerance class): integer tensors from identical xq
+    y = ox.linear_w8a8(xq.cpu().numpy(), sx.cpu().numpy(), w, sw, b, relu)
+    qr, sr = ox.group_quant(y, group)
+    assert np.array_equal(q.cpu().numpy(), qr) and np.array_equal(s.cpu().numpy().view(np.uint32), sr.view(np.uint32))
+
+
 def test_gemm_w4_bit_exact(K):
     rng = np.random.default_rng(3)
     M, N, K_ = 192, 512, 512
