@@ -59,6 +59,13 @@ enum OtGemmOut {
 int ot_version(void);
 const char* ot_last_error(void);
 int ot_device_ok(void); /* 1 when the current device is sm_100 */
+/* Programmatic dependent launch: when enabled (default off) every kernel of this library is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and waits (griddepcontrol.wait) before touching upstream data, so its
+ * launch latency and prologue overlap the predecessor's tail.  Process-wide switch; CUDA-graph capturable. */
+int ot_set_pdl(int enable);
+/* Profiling aid: device timeline buffer (u64[1 + 4*capacity], zeroed by the caller; NULL disables).  Block 0 of every
+ * kernel appends {kernel id, t_start, t_after_dependency_wait, t_end} in %globaltimer nanoseconds. */
+int ot_set_timeline(unsigned long long* buf, unsigned int capacity);
 /* Number of kernels launched by this library in this process (bench.py's gpu_launches counter). */
 int64_t ot_launch_count(void);
 

@@ -45,6 +45,8 @@ SIGNATURES = {
     "ot_last_error": (C.c_char_p, []),
     "ot_device_ok": (_i, []),
     "ot_launch_count": (_l, []),
+    "ot_set_pdl": (_i, [_i]),
+    "ot_set_timeline": (_i, [_p, C.c_uint]),
     "ot_linear_w8a8": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, C.POINTER(OtFault), _p]),
     "ot_linear_w4a8": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, C.POINTER(OtFault), _p]),
     "ot_ln_linear_w8a8": (_i, [_p, _l, _p, _p, _f, _p, _l, _i, _i, _i, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, _p]),

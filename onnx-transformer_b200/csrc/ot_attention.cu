@@ -56,6 +56,10 @@ __device__ __forceinline__ float patch_f32(const OtFault& f, float v) {
 template <int QT>
 __global__ void __launch_bounds__(256, 1) attention_q8_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
+  const unsigned int tl = tl_begin(2);
+  pdl_wait();      // upstream results are complete and visible from here on
+  pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
+  tl_mark(tl, 2);
   const int step = a.step_dev ? *a.step_dev : 0;
   const int Tk = a.step_dev ? step + a.Tq : a.Tk;
   const int q_pos0 = a.step_dev ? step : a.q_pos0;
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(256, 1) attention_q8_kernel(const AttnArgs a) 
   // ---- fault context (App. D); operand selector in fault.reserved
   const OtFault& f = a.fault;
   const bool has_fault = f.mode != OT_FAULT_NONE;
-  int fb = -1, fh = -1, fi = -1, fj = -1, fd = -1, fdelta = 0, fw0 = 0, fw1 = 0;
+  int fb = -1, fh = -1, fi = -1, fj = -1, fd = -1, fw0 = 0, fw1 = 0;
   if (has_fault) {
     const int64_t idx = f.flat_index;
     const int wl = f.window_len;
@@ -306,7 +310,12 @@ __global__ void __launch_bounds__(256, 1) attention_q8_kernel(const AttnArgs a) 
 // head merge.  Same arithmetic, op for op, as attention_q8_kernel.
 constexpr int kDecKeysPerLane = 3;
 __global__ void __launch_bounds__(256) attention_decode_kernel(const AttnArgs a) {
-  __shared__ __align__(16) float Cs[kDm];
+  // per-head V slices (48 KB): low-latency P.V operands; a warp's finished context row (64 floats) overwrites the head of its own slice
+  __shared__ __align__(16) int8_t Vh[kHeads][32 * kDecKeysPerLane][kDk];
+  const unsigned int tl = tl_begin(3);
+  pdl_wait();      // upstream results are complete and visible from here on
+  pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
+  tl_mark(tl, 2);
   const int step = a.step_dev ? *a.step_dev : 0;
   const int Tk = a.step_dev ? step + 1 : a.Tk;
   const int q_pos0 = a.step_dev ? step : a.q_pos0;
@@ -382,6 +391,26 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(const AttnArgs a)
   for (int kk = 0; kk < kDecKeysPerLane; ++kk)
     pq[kk] = (kk * 32 + lane < Tk) ? rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f)) : 0.f;
 
+  // stage this head's V slice [Tk][64] into shared memory: 4 lanes x 16 B per row, 8 rows per instruction, all independent
+  {
+    uint4 vbuf[4 * kDecKeysPerLane];
+#pragma unroll
+    for (int it = 0; it < 4 * kDecKeysPerLane; ++it) {          // all loads are issued before the first store
+      const int j = it * 8 + (lane >> 2);
+      vbuf[it] = make_uint4(0, 0, 0, 0);
+      if (j < Tk) {
+        const int8_t* vp = (j >= new0) ? a.v_new + static_cast<int64_t>(b) * a.ld_new + h * kDk
+                                       : a.v + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk;
+        vbuf[it] = *reinterpret_cast<const uint4*>(vp + (lane & 3) * 16);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 4 * kDecKeysPerLane; ++it) {
+      const int j = it * 8 + (lane >> 2);
+      if (j < Tk) *reinterpret_cast<uint4*>(&Vh[h][j][(lane & 3) * 16]) = vbuf[it];
+    }
+  }
+  __syncwarp();
   // context: lane owns features 2*lane, 2*lane+1; keys in order j = 0..Tk-1 (same order as the generic kernel)
   float acc0 = 0.f, acc1 = 0.f;
   const int d0 = 2 * lane;
@@ -389,21 +418,18 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(const AttnArgs a)
   for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
     if (kk * 32 >= Tk) break;
     const int jn = min(32, Tk - kk * 32);
-#pragma unroll 4
     for (int jj = 0; jj < jn; ++jj) {
       const float p = __shfl_sync(0xffffffffu, pq[kk], jj);
       const float svj = __shfl_sync(0xffffffffu, svl[kk], jj);
       if (p == 0.f) continue;
-      const int j = kk * 32 + jj;
-      const int8_t* vp = (j >= new0) ? a.v_new + static_cast<int64_t>(b) * a.ld_new + h * kDk
-                                     : a.v + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk;
-      const char2 vv = *reinterpret_cast<const char2*>(vp + d0);
+      const char2 vv = *reinterpret_cast<const char2*>(&Vh[h][kk * 32 + jj][d0]);
       const float ph = __fdiv_rn(p, 127.0f);
       acc0 = fmaf(ph, __fmul_rn(__int2float_rn(vv.x), svj), acc0);
       acc1 = fmaf(ph, __fmul_rn(__int2float_rn(vv.y), svj), acc1);
     }
   }
-  *reinterpret_cast<float2*>(Cs + h * kDk + d0) = make_float2(acc0, acc1);
+  __syncwarp();
+  *reinterpret_cast<float2*>(reinterpret_cast<float*>(&Vh[h][0][0]) + d0) = make_float2(acc0, acc1);
   __syncthreads();
   if (h == 0) {
     const int64_t row = b;
@@ -411,7 +437,9 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(const AttnArgs a)
     float amax = 0.f;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      v[t] = *reinterpret_cast<const float4*>(Cs + (t * 32 + lane) * 4);
+      // feature f = (t*32+lane)*4 .. +3 lives in head f/64 at offset f%64
+      const int f0 = (t * 32 + lane) * 4;
+      v[t] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(&Vh[f0 >> 6][0][0]) + (f0 & 63));
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[t].x), fabsf(v[t].y)), fmaxf(fabsf(v[t].z), fabsf(v[t].w))));
     }
     if (a.ctx) {
@@ -431,6 +459,8 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(const AttnArgs a)
       if (lane == 0) a.ctx_s[row] = s;
     }
   }
+  __syncthreads();
+  tl_mark(tl, 3);
 }
 
 template <int QT>
@@ -451,11 +481,12 @@ static int launch_attention(const AttnArgs& a, int tk_max, cudaStream_t stream) 
     configured = smem;
   }
   dim3 grid((a.Tq + QT - 1) / QT, a.B, 1);
-  kernel<<<grid, 256, smem, stream>>>(a);
-  OT_CHECK_CUDA(cudaGetLastError());
+  OT_CHECK_CUDA(launch_kernel(kernel, grid, dim3(256), smem, stream, 1, a));
   count_launch();
   return OT_OK;
 }
+
+OT_DEFINE_TL_SETTER(tl_set_attention)
 
 }  // namespace ot
 
@@ -491,8 +522,7 @@ extern "C" int ot_attention_q8(const int8_t* q, int64_t ldq, const float* sq, in
   if (fault) a.fault = *fault; else a.fault.mode = OT_FAULT_NONE;
   cudaStream_t s = as_stream(stream);
   if (Tq == 1 && tk_max <= 32 * kDecKeysPerLane && a.fault.mode == OT_FAULT_NONE && probs_q == nullptr) {
-    attention_decode_kernel<<<B, 256, 0, s>>>(a);
-    OT_CHECK_CUDA(cudaGetLastError());
+    OT_CHECK_CUDA(launch_kernel(attention_decode_kernel, dim3(B), dim3(256), 0, s, 1, a));
     count_launch();
     return OT_OK;
   }

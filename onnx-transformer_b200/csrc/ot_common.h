@@ -11,6 +11,11 @@ namespace ot {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 bool device_is_sm100();
+void set_pdl(int on);
+void tl_set_gemm(unsigned long long*, unsigned int);
+void tl_set_attention(unsigned long long*, unsigned int);
+void tl_set_rowops(unsigned long long*, unsigned int);
+void tl_set_generator(unsigned long long*, unsigned int);
 
 #define OT_CHECK_CUDA(expr)                                                                  \
   do {                                                                                       \
@@ -36,6 +41,73 @@ bool device_is_sm100();
       return OT_ENODEV;                                              \
     }                                                                \
   } while (0)
+
+// Programmatic dependent launch (PDL): when enabled, a kernel is launched with programmaticStreamSerialization so that its
+// launch latency and prologue (barrier init, TMEM alloc, descriptor prefetch) overlap the tail of its predecessor; every
+// PDL-launched kernel executes pdl_wait() before it touches global memory produced upstream.
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Optional device-side timeline (profiling aid, ot_set_timeline): block 0 / thread 0 of every kernel records
+// {kernel id, t_start, t_after_pdl_wait, t_end} from %globaltimer.  Each translation unit holds its own copy of the pointer.
+static __device__ unsigned long long* tl_buf = nullptr;
+static __device__ unsigned int tl_cap = 0;
+struct TlMark {
+  unsigned int slot;
+};
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool tl_on() { return tl_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0; }
+__device__ __forceinline__ unsigned int tl_begin(int kernel_id) {
+  if (!tl_on()) return 0xffffffffu;
+  const unsigned int slot = static_cast<unsigned int>(atomicAdd(tl_buf, 1ull));
+  if (slot >= tl_cap) return 0xffffffffu;
+  tl_buf[1 + slot * 4] = static_cast<unsigned long long>(kernel_id);
+  tl_buf[2 + slot * 4] = tl_now();
+  return slot;
+}
+__device__ __forceinline__ void tl_mark(unsigned int slot, int which) {
+  if (slot != 0xffffffffu) tl_buf[1 + slot * 4 + which] = tl_now();
+}
+#define OT_DEFINE_TL_SETTER(name)                                                        \
+  void name(unsigned long long* buf, unsigned int cap) {                                 \
+    cudaMemcpyToSymbol(tl_buf, &buf, sizeof(buf));                                       \
+    cudaMemcpyToSymbol(tl_cap, &cap, sizeof(cap));                                       \
+  }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                        Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -28,7 +28,9 @@ namespace ot {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 128;  // int8 elements == bytes: one 128-byte swizzle row
 constexpr int kUmmaK = 32;    // kind::i8 consumes 32 bytes of K per instruction
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;     // two warps per TMEM lane quarter, each owning half of the tile's columns
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGemmThreads = 64 + kEpiThreads;
 constexpr int kMaxCluster = 16;  // > 8 is a non-portable cluster size (opt-in per kernel)
 
 struct GemmArgs {
@@ -55,6 +57,7 @@ struct GemmArgs {
   const float* ln_gamma;
   const float* ln_beta;
   float ln_eps;
+  unsigned long long* trace;  // optional per-CTA phase timestamps (profiling aid, OT_GEMM_TRACE)
   OtFault fault;
 };
 
@@ -67,7 +70,7 @@ struct GemmSmem {
   static constexpr int BAR_OFF = TILE_BYTES;                       // full[S], empty[S], tmem_full, unpacked[S]
   static constexpr int SLOT_OFF = BAR_OFF + (3 * STAGES + 1) * 8;  // TMEM base address slot
   static constexpr int ROWMAX_OFF = BAR_OFF + 256;                 // float [kMaxCluster][128]
-  static constexpr int COLP_OFF = ROWMAX_OFF + kMaxCluster * kBlockM * 4;  // float col_scale[BLOCK_N], bias[BLOCK_N]
+  static constexpr int COLP_OFF = ROWMAX_OFF + kMaxCluster * 2 * kBlockM * 4;  // float col_scale[BLOCK_N], bias[BLOCK_N]
   static constexpr int ROWS_OFF = COLP_OFF + 2 * 256 * 4;                  // float row_scale[128] (LN prologue)
   static constexpr int B4_OFF = ROWS_OFF + kBlockM * 4;                    // 128-byte aligned (TMA destination)
   static_assert((3 * STAGES + 1) * 8 + 16 <= 256, "barrier block overflows its 256-byte slot");
@@ -167,36 +170,41 @@ __device__ __forceinline__ float finish_one(const EpiFlags& e, float v, float bi
   return e.relu ? vr : v;
 }
 
-// One kCW-column chunk of one accumulator row: TMEM -> registers -> fp32 values y[kCW] (residual included).
-// The chunk is narrow and the chunk loops are NOT unrolled, keeping the executed instruction footprint of a launch small.
+// One kCW-column chunk of one accumulator row: registers (already loaded from TMEM) -> fp32 values y[kCW], residual included.
+// Chunks are narrow and the chunk loops are NOT unrolled, keeping the executed instruction footprint of a launch small.
 constexpr int kCW = 16;
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const FaultCtx& f, const EpiFlags& e, uint32_t taddr, int row,
-                                               bool row_ok, int col0, int c, const float* s_cs, const float* s_bias, float sx,
-                                               float (&y)[kCW]) {
-  float4 res[kCW / 4];
-  const bool has_res = g.residual != nullptr && row_ok;
+__device__ __forceinline__ void load_residual(const GemmArgs& g, bool has_res, int row, int col, float4 (&res)[kCW / 4]) {
   if (has_res) {
-    const float4* rp = reinterpret_cast<const float4*>(g.residual + static_cast<int64_t>(row) * g.ldr + col0 + c);
+    const float4* rp = reinterpret_cast<const float4*>(g.residual + static_cast<int64_t>(row) * g.ldr + col);
 #pragma unroll
     for (int j = 0; j < kCW / 4; ++j) res[j] = __ldg(rp + j);
   }
-  uint32_t r[kCW];
-  tmem_ld_32x16(taddr + c, r);
-  tmem_wait_ld();
+}
+__device__ __forceinline__ void chunk_values(const GemmArgs& g, const FaultCtx& f, const EpiFlags& e, const uint32_t (&r)[kCW],
+                                             const float4 (&res)[kCW / 4], bool has_res, int row, bool row_ok, int col0, int c,
+                                             const float* s_cs, const float* s_bias, float sx, float (&y)[kCW]) {
   int acc[kCW];
 #pragma unroll
   for (int j = 0; j < kCW; ++j) acc[j] = static_cast<int>(r[j]);
   if (f.mode != OT_FAULT_NONE && row_ok) patch_acc<kCW>(g, f, row, col0 + c, acc);
+  float cs[kCW], bs[kCW];
+#pragma unroll
+  for (int j = 0; j < kCW / 4; ++j) {   // 128-bit broadcast reads of the staged column parameters
+    const float4 a4 = *reinterpret_cast<const float4*>(s_cs + c + 4 * j);
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + 4 * j);
+    cs[4 * j] = a4.x; cs[4 * j + 1] = a4.y; cs[4 * j + 2] = a4.z; cs[4 * j + 3] = a4.w;
+    bs[4 * j] = b4.x; bs[4 * j + 1] = b4.y; bs[4 * j + 2] = b4.z; bs[4 * j + 3] = b4.w;
+  }
   float mm[kCW];
 #pragma unroll
-  for (int j = 0; j < kCW; ++j) mm[j] = __fmul_rn(__fmul_rn(__int2float_rn(acc[j]), sx), s_cs[c + j]);   // MatMul_k_out0
+  for (int j = 0; j < kCW; ++j) mm[j] = __fmul_rn(__fmul_rn(__int2float_rn(acc[j]), sx), cs[j]);   // MatMul_k_out0
   if (e.out_fault && row == f.row && f.col >= col0 + c && f.col < col0 + c + kCW) {
 #pragma unroll
     for (int j = 0; j < kCW; ++j)
       if (col0 + c + j == f.col) mm[j] = patch_out(g, f, row, f.col, mm[j]);
   }
 #pragma unroll
-  for (int j = 0; j < kCW; ++j) y[j] = finish_one(e, mm[j], s_bias[c + j]);
+  for (int j = 0; j < kCW; ++j) y[j] = finish_one(e, mm[j], bs[j]);
   if (has_res) {
 #pragma unroll
     for (int j = 0; j < kCW / 4; ++j) {
@@ -219,6 +227,80 @@ __device__ __forceinline__ int quant_exact(float y, float s, float r) {
   float n = rintf(q1);
   if (fabsf(fabsf(q1 - n) - 0.5f) < 1.52587890625e-05f) n = rintf(__fdiv_rn(y, s));
   return __float2int_rn(n);
+}
+
+// What a pass does with the fp32 values of a chunk.
+enum { PASS_STORE_F32 = 0, PASS_AMAX = 1, PASS_STORE_Q8 = 2 };
+struct PassState {
+  float amax;    // PASS_AMAX result
+  float s, s_rcp;  // PASS_STORE_Q8 scale and its reciprocal
+};
+template <int KIND>
+__device__ __forceinline__ void consume_chunk(const GemmArgs& g, PassState& st, const float (&y)[kCW], int row, bool row_ok, int col) {
+  if (KIND == PASS_AMAX) {
+#pragma unroll
+    for (int j = 0; j < kCW; ++j) st.amax = fmaxf(st.amax, fabsf(y[j]));
+  } else if (KIND == PASS_STORE_F32) {
+    if (row_ok) {
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<int64_t>(row) * g.ldo + col);
+#pragma unroll
+      for (int j = 0; j < kCW / 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+    }
+  } else {
+    if (row_ok) {
+      uint32_t packed[kCW / 4];
+#pragma unroll
+      for (int j = 0; j < kCW / 4; ++j) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) w |= (static_cast<uint32_t>(quant_exact(y[4 * j + b], st.s, st.s_rcp)) & 0xFFu) << (8 * b);
+        packed[j] = w;
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<int8_t*>(g.out) + static_cast<int64_t>(row) * g.ldo + col) =
+          make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+  }
+}
+
+// One pass over the BLOCK_N accumulator columns of this thread's row, software-pipelined: while chunk c is processed, the
+// tcgen05.ld of chunk c+1 (and its residual loads) are already in flight (two register sets, ping-pong; no latency hiding
+// comes from elsewhere: there is one epilogue warp per scheduler).
+template <int KIND>
+__device__ __forceinline__ void epilogue_pass(const GemmArgs& g, const FaultCtx& f, const EpiFlags& e, uint32_t taddr_row, int row, bool row_ok,
+                                              int col_base, int c0, int c1, const float* s_cs, const float* s_bias, float sx, PassState& st) {
+  const bool has_res = g.residual != nullptr && row_ok;
+  uint32_t ra[kCW], rb[kCW];
+  float4 resa[kCW / 4], resb[kCW / 4];
+  float y[kCW];
+  tmem_ld_32x16(taddr_row + c0, ra);
+  load_residual(g, has_res, row, col_base + c0, resa);
+#pragma unroll 1
+  for (int c = c0; c < c1; c += 2 * kCW) {
+    const bool has_b = c + kCW < c1;
+    tmem_wait_ld();
+    if (has_b) {
+      tmem_ld_32x16(taddr_row + c + kCW, rb);
+      load_residual(g, has_res, row, col_base + c + kCW, resb);
+    }
+    chunk_values(g, f, e, ra, resa, has_res, row, row_ok, col_base, c, s_cs, s_bias, sx, y);
+    consume_chunk<KIND>(g, st, y, row, row_ok, col_base + c);
+    if (!has_b) break;
+    tmem_wait_ld();
+    if (c + 2 * kCW < c1) {
+      tmem_ld_32x16(taddr_row + c + 2 * kCW, ra);
+      load_residual(g, has_res, row, col_base + c + 2 * kCW, resa);
+    }
+    chunk_values(g, f, e, rb, resb, has_res, row, row_ok, col_base, c + kCW, s_cs, s_bias, sx, y);
+    consume_chunk<KIND>(g, st, y, row, row_ok, col_base + c + kCW);
+  }
+}
+
+__device__ __forceinline__ void trace_mark(const GemmArgs& g, int slot) {
+  if (g.trace != nullptr && (threadIdx.x == 64)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+  }
 }
 
 // MODE 0: int8 weights; 1: packed int4 weights unpacked in shared memory; 2: int8 weights, A = RowQuant(LayerNorm(x)) computed
@@ -247,6 +329,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   float* s_rows = reinterpret_cast<float*>(smem + L::ROWS_OFF);
   uint8_t* sB4 = smem + L::B4_OFF;
 
+  const unsigned int tl = tl_begin(1);
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) / 32, 0);
   const int lane = threadIdx.x & 31;
   const int n_blk = blockIdx.x;
@@ -262,7 +345,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(smem_u32(&full_bar[s]), 1);
         mbar_init(smem_u32(&empty_bar[s]), 1);
-        mbar_init(smem_u32(&unpacked_bar[s]), 128);
+        mbar_init(smem_u32(&unpacked_bar[s]), kEpiThreads);
       }
       mbar_init(smem_u32(tmem_full_bar), 1);
       fence_mbar_init();
@@ -277,6 +360,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the predecessor's tail under PDL
+  pdl_wait();      // upstream results are complete and visible from here on
+  pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
+  tl_mark(tl, 2);
+  trace_mark(g, 0);
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
@@ -332,18 +420,20 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int row = m_blk * kBlockM + row_in_tile;
     const bool row_ok = row < g.M;
     const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int half = (warp_idx - 2) >> 2;               // which half of the tile's columns this warp owns
+    const int c_lo = half * (BLOCK_N / 2), c_hi = c_lo + BLOCK_N / 2;
 
     if (W4) {
       // Unpack packed int4 weights (low nibble = even k) to int8 directly into the swizzled MMA layout.
       // One epilogue thread handles 16 packed bytes (32 k-values) at a time = two 16-byte int8 chunks.
-      const int t = (warp_idx - 2) * 32 + lane;  // 0..127
+      const int t = (warp_idx - 2) * 32 + lane;  // 0..kEpiThreads-1
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         const int s = kb % STAGES;
         const uint32_t phase = (kb / STAGES) & 1;
         mbar_wait(smem_u32(&full_bar[s]), phase);
         const uint8_t* src = sB4 + s * L::B4_BYTES;  // [BLOCK_N][64] bytes, dense (no swizzle: 64-byte rows)
         uint8_t* dst = sB + s * L::B_BYTES;
-        for (int item = t; item < BLOCK_N * 4; item += 128) {
+        for (int item = t; item < BLOCK_N * 4; item += kEpiThreads) {
           const int n = item >> 2;        // weight row within the tile
           const int c = item & 3;         // 16-byte packed chunk -> int8 chunks 2c, 2c+1
           const uint4 p = *reinterpret_cast<const uint4*>(src + n * 64 + c * 16);
@@ -377,69 +467,105 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // tiles in the 128-byte-swizzled layout the MMA descriptors expect.
       const int we = warp_idx - 2;
       const float nf = 512.0f;
-      for (int r = we; r < kBlockM; r += 4) {
-        const int grow = m_blk * kBlockM + r;
-        if (grow >= g.M) break;
-        const float4* xr = reinterpret_cast<const float4*>(g.ln_x + static_cast<int64_t>(grow) * g.ln_ldx);
-        float4 v[4];
-        float sum = 0.f;
+      float4 ga[4], be[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          v[i] = __ldg(xr + i * 32 + lane);
-          sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      for (int i = 0; i < 4; ++i) {
+        ga[i] = __ldg(reinterpret_cast<const float4*>(g.ln_gamma) + i * 32 + lane);
+        be[i] = __ldg(reinterpret_cast<const float4*>(g.ln_beta) + i * 32 + lane);
+      }
+      // kLnRows rows per iteration: their loads and shuffle reductions are independent and interleave (a single row at a
+      // time is a serial chain of L2 latencies: measured 44 us per GEMM)
+      constexpr int kLnRows = 4;
+      const int rows_here = min(kBlockM, g.M - m_blk * kBlockM);
+      for (int r0 = we; r0 < rows_here; r0 += kEpiWarps * kLnRows) {
+        float4 v[kLnRows][4];
+        float red[kLnRows];
+#pragma unroll
+        for (int u = 0; u < kLnRows; ++u) {
+          const int r = min(r0 + kEpiWarps * u, rows_here - 1);    // clamp: surplus slots recompute the last row (not stored)
+          const float4* xr = reinterpret_cast<const float4*>(g.ln_x + static_cast<int64_t>(m_blk * kBlockM + r) * g.ln_ldx);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[u][i] = __ldg(xr + i * 32 + lane);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mu = __fdiv_rn(sum, nf);
-        float sq = 0.f;
+        for (int u = 0; u < kLnRows; ++u) {
+          float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          v[i].x = __fsub_rn(v[i].x, mu); v[i].y = __fsub_rn(v[i].y, mu);
-          v[i].z = __fsub_rn(v[i].z, mu); v[i].w = __fsub_rn(v[i].w, mu);
-          sq += (__fmul_rn(v[i].x, v[i].x) + __fmul_rn(v[i].y, v[i].y)) + (__fmul_rn(v[i].z, v[i].z) + __fmul_rn(v[i].w, v[i].w));
+          for (int i = 0; i < 4; ++i) sum += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+          red[u] = sum;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        float var = __fdiv_rn(sq, nf);
-        var = __fdiv_rn(__fmul_rn(var, nf), nf - 1.0f);
-        const float denom = __fadd_rn(__fsqrt_rn(var), g.ln_eps);
-        float amax = 0.f;
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 ga = __ldg(reinterpret_cast<const float4*>(g.ln_gamma) + i * 32 + lane);
-          const float4 be = __ldg(reinterpret_cast<const float4*>(g.ln_beta) + i * 32 + lane);
-          v[i].x = __fadd_rn(__fdiv_rn(__fmul_rn(ga.x, v[i].x), denom), be.x);
-          v[i].y = __fadd_rn(__fdiv_rn(__fmul_rn(ga.y, v[i].y), denom), be.y);
-          v[i].z = __fadd_rn(__fdiv_rn(__fmul_rn(ga.z, v[i].z), denom), be.z);
-          v[i].w = __fadd_rn(__fdiv_rn(__fmul_rn(ga.w, v[i].w), denom), be.w);
-          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+          for (int u = 0; u < kLnRows; ++u) red[u] += __shfl_xor_sync(0xffffffffu, red[u], o);
+#pragma unroll
+        for (int u = 0; u < kLnRows; ++u) {
+          const float mu = __fdiv_rn(red[u], nf);
+          float sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[u][i].x = __fsub_rn(v[u][i].x, mu); v[u][i].y = __fsub_rn(v[u][i].y, mu);
+            v[u][i].z = __fsub_rn(v[u][i].z, mu); v[u][i].w = __fsub_rn(v[u][i].w, mu);
+            sq += (__fmul_rn(v[u][i].x, v[u][i].x) + __fmul_rn(v[u][i].y, v[u][i].y)) +
+                  (__fmul_rn(v[u][i].z, v[u][i].z) + __fmul_rn(v[u][i].w, v[u][i].w));
+          }
+          red[u] = sq;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        const float sc = __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f);
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q0 = __float2int_rn(rintf(__fdiv_rn(v[i].x, sc))), q1 = __float2int_rn(rintf(__fdiv_rn(v[i].y, sc)));
-          const int q2 = __float2int_rn(rintf(__fdiv_rn(v[i].z, sc))), q3 = __float2int_rn(rintf(__fdiv_rn(v[i].w, sc)));
-          const uint32_t w = (static_cast<uint32_t>(q0) & 0xFFu) | ((static_cast<uint32_t>(q1) & 0xFFu) << 8) |
-                             ((static_cast<uint32_t>(q2) & 0xFFu) << 16) | ((static_cast<uint32_t>(q3) & 0xFFu) << 24);
-          // k = i*128 + lane*4 -> k-block i, 16-byte chunk lane/4 (XOR-swizzled with row % 8), byte (lane%4)*4
-          *reinterpret_cast<uint32_t*>(sA + i * L::A_BYTES + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) = w;
+          for (int u = 0; u < kLnRows; ++u) red[u] += __shfl_xor_sync(0xffffffffu, red[u], o);
+#pragma unroll
+        for (int u = 0; u < kLnRows; ++u) {
+          float var = __fdiv_rn(red[u], nf);
+          var = __fdiv_rn(__fmul_rn(var, nf), nf - 1.0f);
+          const float denom = __fadd_rn(__fsqrt_rn(var), g.ln_eps);
+          float amax = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[u][i].x = __fadd_rn(__fdiv_rn(__fmul_rn(ga[i].x, v[u][i].x), denom), be[i].x);
+            v[u][i].y = __fadd_rn(__fdiv_rn(__fmul_rn(ga[i].y, v[u][i].y), denom), be[i].y);
+            v[u][i].z = __fadd_rn(__fdiv_rn(__fmul_rn(ga[i].z, v[u][i].z), denom), be[i].z);
+            v[u][i].w = __fadd_rn(__fdiv_rn(__fmul_rn(ga[i].w, v[u][i].w), denom), be[i].w);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[u][i].x), fabsf(v[u][i].y)), fmaxf(fabsf(v[u][i].z), fabsf(v[u][i].w))));
+          }
+          red[u] = amax;
         }
-        if (lane == 0) s_rows[r] = sc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int u = 0; u < kLnRows; ++u) red[u] = fmaxf(red[u], __shfl_xor_sync(0xffffffffu, red[u], o));
+#pragma unroll
+        for (int u = 0; u < kLnRows; ++u) {
+          const int r = r0 + kEpiWarps * u;
+          const bool live = r < rows_here;
+          const float sc = __fdiv_rn(fmaxf(red[u], 1e-5f), 127.0f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!live) continue;
+            const int q0 = __float2int_rn(rintf(__fdiv_rn(v[u][i].x, sc))), q1 = __float2int_rn(rintf(__fdiv_rn(v[u][i].y, sc)));
+            const int q2 = __float2int_rn(rintf(__fdiv_rn(v[u][i].z, sc))), q3 = __float2int_rn(rintf(__fdiv_rn(v[u][i].w, sc)));
+            const uint32_t w = (static_cast<uint32_t>(q0) & 0xFFu) | ((static_cast<uint32_t>(q1) & 0xFFu) << 8) |
+                               ((static_cast<uint32_t>(q2) & 0xFFu) << 16) | ((static_cast<uint32_t>(q3) & 0xFFu) << 24);
+            // k = i*128 + lane*4 -> k-block i, 16-byte chunk lane/4 (XOR-swizzled with row % 8), byte (lane%4)*4
+            *reinterpret_cast<uint32_t*>(sA + i * L::A_BYTES + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) = w;
+          }
+          if (live && lane == 0) s_rows[r] = sc;
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&unpacked_bar[0]));
+      trace_mark(g, 1);
     }
 
     // Stage the per-column epilogue parameters once per CTA (overlaps the main loop), then wait for the accumulator.
     {
       const int t = (warp_idx - 2) * 32 + lane;
-      for (int c = t; c < BLOCK_N; c += 128) {
+      for (int c = t; c < BLOCK_N; c += kEpiThreads) {
         s_cs[c] = g.col_scale ? __ldg(g.col_scale + n_blk * BLOCK_N + c) : 1.0f;
         s_bias[c] = g.bias ? __ldg(g.bias + n_blk * BLOCK_N + c) : 0.0f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // epilogue warps only
     }
     const FaultCtx f = resolve_fault(g);
     const EpiFlags e = {g.bias != nullptr, g.relu != 0, f.mode == OT_FAULT_RANDOM_BITFLIP || f.mode == OT_FAULT_RANDOM};
@@ -448,11 +574,12 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     mbar_wait(smem_u32(tmem_full_bar), 0);
     tc_fence_after();
+    trace_mark(g, 2);
 
     if (g.out_kind == OT_OUT_I32) {
       int* out = reinterpret_cast<int*>(g.out);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += kCW) {
+      for (int c = c_lo; c < c_hi; c += kCW) {
         uint32_t r[kCW];
         tmem_ld_32x16(taddr_row + c, r);
         tmem_wait_ld();
@@ -467,42 +594,30 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     } else if (g.out_kind == OT_OUT_F32) {
-      float* out = reinterpret_cast<float*>(g.out);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += kCW) {
-        float y[kCW];
-        epilogue_chunk(g, f, e, taddr_row, row, row_ok, col_base, c, s_cs, s_bias, sx, y);
-        if (row_ok) {
-          float4* dst = reinterpret_cast<float4*>(out + static_cast<int64_t>(row) * g.ldo + col_base + c);
-#pragma unroll
-          for (int j = 0; j < kCW / 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        }
-      }
+      PassState st = {0.f, 1.f, 1.f};
+      epilogue_pass<PASS_STORE_F32>(g, f, e, taddr_row, row, row_ok, col_base, c_lo, c_hi, s_cs, s_bias, sx, st);
     } else {
       // OT_OUT_Q8, pass 1: per-row abs-max over this CTA's BLOCK_N columns, broadcast to the cluster.
-      float amax = 0.0f;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += kCW) {
-        float y[kCW];
-        epilogue_chunk(g, f, e, taddr_row, row, row_ok, col_base, c, s_cs, s_bias, sx, y);
-#pragma unroll
-        for (int j = 0; j < kCW; ++j) amax = fmaxf(amax, fabsf(y[j]));
-      }
+      PassState st = {0.f, 1.f, 1.f};
+      epilogue_pass<PASS_AMAX>(g, f, e, taddr_row, row, row_ok, col_base, c_lo, c_hi, s_cs, s_bias, sx, st);
+      float amax = st.amax;
       if (!row_ok) amax = 0.0f;
       const uint32_t my_rank = g.cluster_n > 1 ? cluster_ctarank() : 0u;
-      const uint32_t slot = smem_u32(rowmax_x + my_rank * kBlockM + row_in_tile);
+      const uint32_t slot = smem_u32(rowmax_x + (my_rank * 2 + half) * kBlockM + row_in_tile);
       if (g.cluster_n > 1) {
         for (int peer = 0; peer < g.cluster_n; ++peer) st_shared_cluster_f32(mapa_shared(slot, peer), amax);
       } else {
-        rowmax_x[row_in_tile] = amax;
+        rowmax_x[half * kBlockM + row_in_tile] = amax;
       }
     }
   }
 
+  trace_mark(g, 3);
   if (g.out_kind == OT_OUT_Q8) {
     // every thread of every CTA in the cluster: make the row maxima visible
     if (g.cluster_n > 1) cluster_sync_all();
     else __syncthreads();
+    trace_mark(g, 4);
 
     if (warp_idx >= 2) {
       const int quarter = warp_idx & 3;
@@ -510,45 +625,31 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row = m_blk * kBlockM + row_in_tile;
       const bool row_ok = row < g.M;
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int half = (warp_idx - 2) >> 2;
+      const int c_lo = half * (BLOCK_N / 2), c_hi = c_lo + BLOCK_N / 2;
       const FaultCtx f = resolve_fault(g);
       const EpiFlags e = {g.bias != nullptr, g.relu != 0, f.mode == OT_FAULT_RANDOM_BITFLIP || f.mode == OT_FAULT_RANDOM};
       const float sx = ALN ? (row_ok ? s_rows[row_in_tile] : 1.0f) : ((g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f);
       const int col_base = n_blk * BLOCK_N;
 
       float amax = 0.0f;
-      for (int p = 0; p < g.cluster_n; ++p) amax = fmaxf(amax, rowmax_x[p * kBlockM + row_in_tile]);
+      for (int p = 0; p < 2 * g.cluster_n; ++p) amax = fmaxf(amax, rowmax_x[p * kBlockM + row_in_tile]);
       // RowQuant (quant_linear.py:31-43): s = max(amax, 1e-5)/127 ; q = rint(y / s)
       const float s = __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f);
       const float s_rcp = __frcp_rn(s);
       const int group = n_blk / g.cluster_n;
       const int groups_per_row = (g.N / BLOCK_N) / g.cluster_n;
-      if (row_ok && (n_blk % g.cluster_n) == 0) g.out_scale[static_cast<int64_t>(row) * groups_per_row + group] = s;
+      if (row_ok && half == 0 && (n_blk % g.cluster_n) == 0) g.out_scale[static_cast<int64_t>(row) * groups_per_row + group] = s;
 
-      int8_t* out = reinterpret_cast<int8_t*>(g.out);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += kCW) {
-        float y[kCW];
-        epilogue_chunk(g, f, e, taddr_row, row, row_ok, col_base, c, s_cs, s_bias, sx, y);
-        if (row_ok) {
-          uint32_t packed[kCW / 4];
-#pragma unroll
-          for (int j = 0; j < kCW / 4; ++j) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int q = quant_exact(y[4 * j + b], s, s_rcp);
-              w |= (static_cast<uint32_t>(q) & 0xFFu) << (8 * b);
-            }
-            packed[j] = w;
-          }
-          *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * g.ldo + col_base + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        }
-      }
+      PassState st = {0.f, s, s_rcp};
+      epilogue_pass<PASS_STORE_Q8>(g, f, e, taddr_row, row, row_ok, col_base, c_lo, c_hi, s_cs, s_bias, sx, st);
     }
   }
 
+  trace_mark(g, 5);
   tc_fence_before();
   __syncthreads();
+  tl_mark(tl, 3);
   if (warp_idx == 1) tmem_dealloc(tmem_base, BLOCK_N);
 }
 
@@ -649,19 +750,8 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(g.N / BLOCK_N, (g.M + kBlockM - 1) / kBlockM, 1);
-  cfg.blockDim = dim3(kGemmThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = g.cluster_n;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  OT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, g));
+  OT_CHECK_CUDA(launch_kernel(kernel, dim3(g.N / BLOCK_N, (g.M + kBlockM - 1) / kBlockM, 1), dim3(kGemmThreads, 1, 1), smem, stream, g.cluster_n,
+                              ta, tb, g));
   count_launch();
   return OT_OK;
 }
@@ -694,6 +784,7 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
     block_n = best;
     g.cluster_n = 1;
   }
+  if (const char* tr = getenv("OT_GEMM_TRACE")) g.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16));
   if (const char* force = getenv("OT_GEMM_FORCE_BN")) {   // tuning / profiling aid only
     const int bn = atoi(force);
     if ((bn == 32 || bn == 64 || bn == 128 || bn == 256) && g.N % bn == 0 &&
@@ -759,6 +850,8 @@ static int linear_common(bool w4, const int8_t* A, int64_t lda, const void* W, i
   cudaStream_t s = as_stream(stream);
   return w4 ? dispatch_gemm<1>(g, quant_group, s) : dispatch_gemm<0>(g, quant_group, s);
 }
+
+OT_DEFINE_TL_SETTER(tl_set_gemm)
 
 }  // namespace ot
 

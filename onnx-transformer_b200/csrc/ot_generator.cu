@@ -16,6 +16,10 @@ __global__ void __launch_bounds__(256) generator_logits_kernel(const float* __re
                                                                float* __restrict__ logits) {
   __shared__ float hs[kGenRows][kGenKC + 1];
   __shared__ float ws[kGenVT][kGenKC + 1];
+  const unsigned int tl = tl_begin(7);
+  pdl_wait();      // upstream results are complete and visible from here on
+  pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
+  tl_mark(tl, 2);
   const int v0 = blockIdx.x * kGenVT;
   const int r0 = blockIdx.y * kGenRows;
   const int tid = threadIdx.x;
@@ -54,6 +58,7 @@ __global__ void __launch_bounds__(256) generator_logits_kernel(const float* __re
       if (r < rows) logits[static_cast<int64_t>(r) * vocab + v0 + vl] = __fadd_rn(acc[t], bv);
     }
   }
+  tl_mark(tl, 3);
 }
 
 // Per row: first arg-max, top1-top2 margin, optional log-softmax in place of the logits.
@@ -61,6 +66,10 @@ __global__ void __launch_bounds__(256) generator_reduce_kernel(float* __restrict
                                                                float* __restrict__ logp, float* __restrict__ margin) {
   __shared__ float s_val[8], s_second[8], s_sum[8];
   __shared__ int s_idx[8];
+  const unsigned int tl = tl_begin(8);
+  pdl_wait();      // upstream results are complete and visible from here on
+  pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
+  tl_mark(tl, 2);
   const int row = blockIdx.x;
   const float* x = logits + static_cast<int64_t>(row) * vocab;
   float best = -INFINITY, second = -INFINITY;
@@ -107,7 +116,10 @@ __global__ void __launch_bounds__(256) generator_reduce_kernel(float* __restrict
     float* out = logp + static_cast<int64_t>(row) * vocab;
     for (int v = threadIdx.x; v < vocab; v += blockDim.x) out[v] = x[v] - lse;
   }
+  tl_mark(tl, 3);
 }
+
+OT_DEFINE_TL_SETTER(tl_set_generator)
 
 }  // namespace ot
 
@@ -122,10 +134,8 @@ extern "C" int ot_generator_argmax(const float* h, int64_t ldh, const float* Wg,
   OT_REQUIRE(rows > 0 && d % 4 == 0 && ldh % 4 == 0 && vocab > 1, "bad generator shape");
   cudaStream_t s = as_stream(stream);
   dim3 grid((vocab + kGenVT - 1) / kGenVT, (rows + kGenRows - 1) / kGenRows, 1);
-  generator_logits_kernel<<<grid, 256, 0, s>>>(h, ldh, Wg, bg, rows, d, vocab, scratch_logits);
-  OT_CHECK_CUDA(cudaGetLastError());
-  generator_reduce_kernel<<<rows, 256, 0, s>>>(scratch_logits, vocab, next_ids, logp, margin);
-  OT_CHECK_CUDA(cudaGetLastError());
+  OT_CHECK_CUDA(launch_kernel(generator_logits_kernel, grid, dim3(256), 0, s, 1, h, ldh, Wg, bg, rows, d, vocab, scratch_logits));
+  OT_CHECK_CUDA(launch_kernel(generator_reduce_kernel, dim3(rows), dim3(256), 0, s, 1, scratch_logits, vocab, next_ids, logp, margin));
   count_launch(2);
   return OT_OK;
 }

@@ -33,6 +33,10 @@ __global__ void __launch_bounds__(256) layernorm_quant_kernel(const float* __res
                                                               const float* __restrict__ beta, int64_t rows, int n, float eps,
                                                               float* __restrict__ y_out, int8_t* __restrict__ q_out,
                                                               float* __restrict__ s_out) {
+  const unsigned int tl = tl_begin(4);
+  pdl_wait();      // upstream results are complete and visible from here on
+  pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
+  tl_mark(tl, 2);
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -84,6 +88,7 @@ __global__ void __launch_bounds__(256) layernorm_quant_kernel(const float* __res
       qr[i * 32 + lane] = pack4(quant_one(v[i].x, s), quant_one(v[i].y, s), quant_one(v[i].z, s), quant_one(v[i].w, s));
     if (lane == 0) s_out[row] = s;
   }
+  tl_mark(tl, 3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -91,6 +96,8 @@ __global__ void __launch_bounds__(256) layernorm_quant_kernel(const float* __res
 __global__ void __launch_bounds__(256) rowquant_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int n, int group,
                                                        int8_t* __restrict__ q, float* __restrict__ s_out,
                                                        float* __restrict__ xhat) {
+  pdl_wait();      // upstream results are complete and visible from here on
+  pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
   const int lane = threadIdx.x & 31;
   const int groups = n / group;
   const int64_t item = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -133,6 +140,10 @@ __global__ void __launch_bounds__(128) embed_pe_kernel(const int64_t* __restrict
                                                        const float* __restrict__ table, const float* __restrict__ pe,
                                                        int64_t rows, int seq_len, int d, int pos0,
                                                        const int32_t* __restrict__ pos_dev, float scale, float* __restrict__ out) {
+  const unsigned int tl = tl_begin(6);
+  pdl_wait();      // upstream results are complete and visible from here on
+  pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
+  tl_mark(tl, 2);
   const int64_t row = blockIdx.x;
   if (row >= rows) return;
   const int dyn = pos_dev ? *pos_dev : 0;
@@ -161,11 +172,18 @@ __global__ void __launch_bounds__(256) unpack_int4_kernel(const uint8_t* __restr
 // ys[b, step+1] = next[b]; step++  (greedy_decode: parallelized_inject_onnx_transformer.py:753-758)
 __global__ void append_token_kernel(int64_t* __restrict__ ys, int64_t ld, const int64_t* __restrict__ next, int B,
                                     int32_t* __restrict__ step_dev) {
+  const unsigned int tl = tl_begin(9);
+  pdl_wait();      // upstream results are complete and visible from here on
+  pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
+  tl_mark(tl, 2);
   const int step = *step_dev;
   for (int b = threadIdx.x; b < B; b += blockDim.x) ys[static_cast<int64_t>(b) * ld + step + 1] = next[b];
   __syncthreads();
   if (threadIdx.x == 0) *step_dev = step + 1;
+  tl_mark(tl, 3);
 }
+
+OT_DEFINE_TL_SETTER(tl_set_rowops)
 
 }  // namespace ot
 
@@ -183,7 +201,7 @@ extern "C" int ot_layernorm_quant(const float* x, const float* gamma, const floa
   cudaStream_t s = as_stream(stream);
 #define OT_LN_CASE(V)                                                                                            \
   case V:                                                                                                        \
-    layernorm_quant_kernel<V><<<grid, warps * 32, 0, s>>>(x, gamma, beta, rows, n, eps, y_out, q_out, s_out);    \
+    OT_CHECK_CUDA(launch_kernel(layernorm_quant_kernel<V>, dim3(grid), dim3(warps * 32), 0, s, 1, x, gamma, beta, rows, n, eps, y_out, q_out, s_out)); \
     break;
   switch (n / 128) {
     OT_LN_CASE(1) OT_LN_CASE(2) OT_LN_CASE(3) OT_LN_CASE(4) OT_LN_CASE(5) OT_LN_CASE(6) OT_LN_CASE(7) OT_LN_CASE(8)
@@ -204,9 +222,8 @@ extern "C" int ot_rowquant(const float* x, int64_t ldx, int64_t rows, int n, int
   if (rows == 0) return OT_OK;
   const int64_t items = rows * (n / group);
   const int warps = 8;
-  rowquant_kernel<<<static_cast<unsigned>((items + warps - 1) / warps), warps * 32, 0, as_stream(stream)>>>(x, ldx, rows, n, group,
-                                                                                                          q, s, xhat);
-  OT_CHECK_CUDA(cudaGetLastError());
+  OT_CHECK_CUDA(launch_kernel(rowquant_kernel, dim3(static_cast<unsigned>((items + warps - 1) / warps)), dim3(warps * 32), 0, as_stream(stream), 1,
+                              x, ldx, rows, n, group, q, s, xhat));
   count_launch();
   return OT_OK;
 }
@@ -229,9 +246,8 @@ extern "C" int ot_embed_pe(const int64_t* ids, int64_t ids_stride, const float* 
   OT_REQUIRE_DEVICE();
   OT_REQUIRE(ids && table && pe && out && rows >= 0 && seq_len > 0 && d % 4 == 0, "bad embed_pe arguments");
   if (rows == 0) return OT_OK;
-  embed_pe_kernel<<<static_cast<unsigned>(rows), 128, 0, as_stream(stream)>>>(ids, ids_stride, table, pe, rows, seq_len, d, pos0,
-                                                                             pos_dev, scale, out);
-  OT_CHECK_CUDA(cudaGetLastError());
+  OT_CHECK_CUDA(launch_kernel(embed_pe_kernel, dim3(static_cast<unsigned>(rows)), dim3(128), 0, as_stream(stream), 1, ids, ids_stride, table, pe,
+                              rows, seq_len, d, pos0, pos_dev, scale, out));
   count_launch();
   return OT_OK;
 }
@@ -251,8 +267,7 @@ extern "C" int ot_unpack_int4(const uint8_t* W4, int8_t* W8, int64_t rows, int64
 extern "C" int ot_append_token(int64_t* ys, int64_t ld_ys, const int64_t* next_ids, int B, int32_t* step_dev, void* stream) {
   OT_REQUIRE_DEVICE();
   OT_REQUIRE(ys && next_ids && step_dev && B > 0, "bad append_token arguments");
-  append_token_kernel<<<1, 256, 0, as_stream(stream)>>>(ys, ld_ys, next_ids, B, step_dev);
-  OT_CHECK_CUDA(cudaGetLastError());
+  OT_CHECK_CUDA(launch_kernel(append_token_kernel, dim3(1), dim3(256), 0, as_stream(stream), 1, ys, ld_ys, next_ids, B, step_dev));
   count_launch();
   return OT_OK;
 }

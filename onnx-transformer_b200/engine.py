@@ -91,10 +91,11 @@ class QuantizedTransformer:
     """Device-resident model + workspaces.  `float_weights`: reference state_dict names -> fp32 arrays (already
     smoothed if SmoothQuant is wanted: get_quantized_model.smooth_lm is an offline weight transform)."""
 
-    def __init__(self, float_weights: Dict[str, np.ndarray], n_layers: int = 6, device: Optional[torch.device] = None, max_len: int = W.MAX_LEN):
+    def __init__(self, float_weights: Dict[str, np.ndarray], n_layers: int = 6, device: Optional[torch.device] = None, max_len: int = W.MAX_LEN,
+                 pdl: bool = True, fused_ln: bool = False):
         if not torch.cuda.is_available():
             raise K.OtError("QuantizedTransformer needs a CUDA device: this package has no CPU fallback")
-        K._lib.load()
+        K._lib.load().ot_set_pdl(1 if pdl else 0)   # programmatic dependent launch for every kernel of the library
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.n_layers = n_layers
         self.max_len = max_len
@@ -138,7 +139,7 @@ class QuantizedTransformer:
         self.pe = self._positional_encoding(max(max_len, 512) + 1)
         self._enc_ws: Dict[int, dict] = {}
         self._dec_ws: Dict[tuple, dict] = {}
-        self.fused_ln = True     # decode: LayerNorm+RowQuant as the prologue of the following GEMM (M <= 128)
+        self.fused_ln = fused_ln  # decode: LayerNorm+RowQuant as the prologue of the following GEMM (M <= 128)
         self.graph_replays = 0   # CUDA-graph replays of the greedy step (each replays ws['graph_launches'] kernels)
         torch.cuda.synchronize(self.dev)
 

@@ -22,6 +22,9 @@ VARIANTS = {
     "big_ffn1_q8": (65536, 2048, 512, K.OUT_Q8, 2048, True, False),
     "big_ffn2_f32": (65536, 512, 2048, K.OUT_F32, 0, False, True),
     "big_i32": (65536, 2048, 512, K.OUT_I32, 0, False, False),
+    "ln_qkv_q8": (64, 1536, 512, K.OUT_Q8, 512, False, False),
+    "ln_cq_q8": (64, 512, 512, K.OUT_Q8, 512, False, False),
+    "ln_ffn1_q8": (64, 2048, 512, K.OUT_Q8, 2048, True, False),
 }
 
 
@@ -39,7 +42,16 @@ def main():
         out = torch.empty((M, N), dtype={K.OUT_I32: torch.int32, K.OUT_F32: torch.float32, K.OUT_Q8: torch.int8}[kind], device="cuda")
         osc = torch.empty((M, max(1, N // group if group else 1)), dtype=torch.float32, device="cuda")
 
+        xf = torch.randn(M, Kd, device="cuda")
+        ga = torch.rand(Kd, device="cuda") + 0.5
+        be = torch.randn(Kd, device="cuda") * 0.1
+
+        def run_ln():
+            K.ln_linear_w8a8(xf, ga, be, w, col_scale=sw, bias=b, relu=relu, out_kind=kind, quant_group=group, out=out, out_scale=osc)
+
         def run():
+            if name.startswith("ln_"):
+                return run_ln()
             K.linear_w8a8(a, w, row_scale=sx, col_scale=sw, bias=b, residual=r, relu=relu, out_kind=kind, quant_group=group, out=out,
                           out_scale=osc if kind == K.OUT_Q8 else None)
 
