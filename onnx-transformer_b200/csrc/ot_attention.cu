@@ -346,6 +346,19 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(const AttnArgs a)
     }
   }
   const float sqi = a.sq[static_cast<int64_t>(b) * a.sq_stride];
+  // this head's V slice [Tk][64]: 4 lanes x 16 B per row, 8 rows per instruction; issued now so that their L2 latency
+  // overlaps the K loads, the scores and the softmax (stored to shared memory just before the P.V loop)
+  uint4 vbuf[4 * kDecKeysPerLane];
+#pragma unroll
+  for (int it = 0; it < 4 * kDecKeysPerLane; ++it) {
+    const int j = it * 8 + (lane >> 2);
+    vbuf[it] = make_uint4(0, 0, 0, 0);
+    if (j < Tk) {
+      const int8_t* vp = (j >= new0) ? a.v_new + static_cast<int64_t>(b) * a.ld_new + h * kDk
+                                     : a.v + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk;
+      vbuf[it] = *reinterpret_cast<const uint4*>(vp + (lane & 3) * 16);
+    }
+  }
 
   float sc[kDecKeysPerLane], svl[kDecKeysPerLane];
   float mx = -INFINITY;
@@ -386,44 +399,31 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(const AttnArgs a)
     }
   }
   sum = warp_sum_f(sum);
-  float pq[kDecKeysPerLane];
+  float pq[kDecKeysPerLane];   // quantized probability already divided by 127 (Div(127) of attention.py:35), one division per key
 #pragma unroll
   for (int kk = 0; kk < kDecKeysPerLane; ++kk)
-    pq[kk] = (kk * 32 + lane < Tk) ? rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f)) : 0.f;
+    pq[kk] = (kk * 32 + lane < Tk) ? __fdiv_rn(rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f)), 127.0f) : 0.f;
 
   // stage this head's V slice [Tk][64] into shared memory: 4 lanes x 16 B per row, 8 rows per instruction, all independent
-  {
-    uint4 vbuf[4 * kDecKeysPerLane];
 #pragma unroll
-    for (int it = 0; it < 4 * kDecKeysPerLane; ++it) {          // all loads are issued before the first store
-      const int j = it * 8 + (lane >> 2);
-      vbuf[it] = make_uint4(0, 0, 0, 0);
-      if (j < Tk) {
-        const int8_t* vp = (j >= new0) ? a.v_new + static_cast<int64_t>(b) * a.ld_new + h * kDk
-                                       : a.v + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk;
-        vbuf[it] = *reinterpret_cast<const uint4*>(vp + (lane & 3) * 16);
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < 4 * kDecKeysPerLane; ++it) {
-      const int j = it * 8 + (lane >> 2);
-      if (j < Tk) *reinterpret_cast<uint4*>(&Vh[h][j][(lane & 3) * 16]) = vbuf[it];
-    }
+  for (int it = 0; it < 4 * kDecKeysPerLane; ++it) {
+    const int j = it * 8 + (lane >> 2);
+    *reinterpret_cast<uint4*>(&Vh[h][j][(lane & 3) * 16]) = vbuf[it];   // rows >= Tk are zero-filled
   }
   __syncwarp();
   // context: lane owns features 2*lane, 2*lane+1; keys in order j = 0..Tk-1 (same order as the generic kernel)
   float acc0 = 0.f, acc1 = 0.f;
   const int d0 = 2 * lane;
+  // Branch-free and unrolled: a key with p = 0 (masked, or beyond Tk where sv = 0) contributes exactly +0, so skipping it
+  // (as the generic kernel does) and adding it give the same sum; 8 independent shuffles / shared loads are in flight.
 #pragma unroll
   for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
     if (kk * 32 >= Tk) break;
-    const int jn = min(32, Tk - kk * 32);
-    for (int jj = 0; jj < jn; ++jj) {
-      const float p = __shfl_sync(0xffffffffu, pq[kk], jj);
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const float ph = __shfl_sync(0xffffffffu, pq[kk], jj);
       const float svj = __shfl_sync(0xffffffffu, svl[kk], jj);
-      if (p == 0.f) continue;
       const char2 vv = *reinterpret_cast<const char2*>(&Vh[h][kk * 32 + jj][d0]);
-      const float ph = __fdiv_rn(p, 127.0f);
       acc0 = fmaf(ph, __fmul_rn(__int2float_rn(vv.x), svj), acc0);
       acc1 = fmaf(ph, __fmul_rn(__int2float_rn(vv.y), svj), acc1);
     }

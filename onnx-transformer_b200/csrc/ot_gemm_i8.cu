@@ -137,17 +137,28 @@ __device__ __noinline__ int patch_acc_one(const GemmArgs& g, const FaultCtx& f, 
   return acc;
 }
 template <int CW>
-__device__ __forceinline__ void patch_acc(const GemmArgs& g, const FaultCtx& f, int row, int col0, int (&acc)[CW]) {
-  // only the affected row (INPUT / ACC) or the chunk holding the affected column (WEIGHT) does any work
-  const bool hit = (f.mode == OT_FAULT_WEIGHT) ? (f.col >= col0 && f.col < col0 + CW) : (row == f.row);
-  if (!hit) return;
-#pragma unroll
+__device__ __noinline__ void patch_acc_array(const GemmArgs& g, const FaultCtx& f, int row, int col0, int* acc) {
   for (int j = 0; j < CW; ++j) acc[j] = patch_acc_one(g, f, row, col0 + j, acc[j]);
 }
+template <int CW>
+__device__ __forceinline__ void patch_acc(const GemmArgs& g, const FaultCtx& f, int row, int col0, int (&acc)[CW]) {
+  // only the affected row (INPUT / ACC) or the chunk holding the affected column (WEIGHT) does any work; the values take
+  // a detour through local memory on that rare path only, so the fault-free epilogue carries one call site per chunk
+  const bool hit = (f.mode == OT_FAULT_WEIGHT) ? (f.col >= col0 && f.col < col0 + CW) : (row == f.row);
+  if (!hit) return;
+  int tmp[CW];
+#pragma unroll
+  for (int j = 0; j < CW; ++j) tmp[j] = acc[j];
+  patch_acc_array<CW>(g, f, row, col0, tmp);
+#pragma unroll
+  for (int j = 0; j < CW; ++j) acc[j] = tmp[j];
+}
 
-// fp32 output faults on the MatMul result (before the bias Add): inject_utils/layers.py:18-33.
-__device__ __noinline__ float patch_out(const GemmArgs& g, const FaultCtx& f, int row, int col, float v) {
-  if (row != f.row || col != f.col) return v;
+// fp32 output faults on the MatMul result (before the bias Add): inject_utils/layers.py:18-33.  `vals[idx]` is the golden value.
+__device__ __noinline__ float patch_out(const GemmArgs& g, const FaultCtx& f, int row, int col, float, const float* vals, int idx) {
+  float v = 0.f;
+  for (int j = 0; j < 16; ++j)
+    if (j == idx) v = vals[j];
   uint32_t bits = __float_as_uint(v);
   if (f.mode == OT_FAULT_RANDOM_BITFLIP) bits ^= (1u << g.fault.bit);
   else if (f.mode == OT_FAULT_RANDOM) bits = g.fault.value_bits;
@@ -199,9 +210,9 @@ __device__ __forceinline__ void chunk_values(const GemmArgs& g, const FaultCtx& 
 #pragma unroll
   for (int j = 0; j < kCW; ++j) mm[j] = __fmul_rn(__fmul_rn(__int2float_rn(acc[j]), sx), cs[j]);   // MatMul_k_out0
   if (e.out_fault && row == f.row && f.col >= col0 + c && f.col < col0 + c + kCW) {
+    const float patched = patch_out(g, f, row, f.col, 0.f, mm, f.col - (col0 + c));
 #pragma unroll
-    for (int j = 0; j < kCW; ++j)
-      if (col0 + c + j == f.col) mm[j] = patch_out(g, f, row, f.col, mm[j]);
+    for (int j = 0; j < kCW; ++j) mm[j] = (col0 + c + j == f.col) ? patched : mm[j];
   }
 #pragma unroll
   for (int j = 0; j < kCW; ++j) y[j] = finish_one(e, mm[j], bs[j]);
@@ -307,7 +318,7 @@ __device__ __forceinline__ void trace_mark(const GemmArgs& g, int slot) {
 // by the epilogue warps straight into the swizzled operand tile (K = 512 = STAGES k-blocks, all resident).
 template <int BLOCK_N, int STAGES, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs g) {
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GemmArgs g) {
   constexpr bool W4 = (MODE == 1);
   constexpr bool ALN = (MODE == 2);
   using L = GemmSmem<BLOCK_N, STAGES>;
@@ -779,7 +790,7 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
     for (int bn : {256, 128, 64, 32}) {
       if (g.N % bn != 0 || (MODE == 2 && bn > 128)) continue;
       best = bn;
-      if (static_cast<int64_t>(m_tiles) * (g.N / bn) >= 148) break;
+      if (static_cast<int64_t>(m_tiles) * (g.N / bn) >= 96) break;   // measured: 128 tiles of BN=128 beat 256 tiles of BN=64
     }
     block_n = best;
     g.cluster_n = 1;
