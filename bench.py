@@ -126,71 +126,102 @@ def run_reference_arm(args):
     return 0
 
 
-# ----------------------------------------------------------------------------------------------- kernel-family probe
-def probe_decode_families(eng, ws, B, S, reps=20):
-    """Average device time (CUDA events on the launching stream) and algorithmic bytes of each kernel family of ONE
-    greedy step at a mid-run prefix length, each family launched back to back in isolation."""
+# ----------------------------------------------------------------------------------------------- kernel-family timing
+FAMILY = {1: "gemm_i8", 2: "attention_q8", 3: "attention_q8", 4: "layernorm_quant", 5: "rowquant", 6: "embed_pe", 7: "generator", 8: "generator",
+          9: "append_token"}
+
+
+def decode_family_timeline(eng, ws, B, S, reps=8, step=35):
+    """In-situ kernel durations of the greedy step: the captured step graph is replayed `reps` times (at a mid-run prefix
+    length) with the library's device timeline on -- block 0 of every kernel stamps %globaltimer when its dependency wait
+    ends and when it finishes -- and bracketed by CUDA events on the launching stream.  Returns per family
+    {launches_per_step, us_per_launch, us_per_step} and the event-timed step duration."""
+    import ctypes as C
     import torch
-    from onnx_transformer_b200 import kernels as K
-    D, FF, nl = 512, 2048, eng.n_layers
-    T = 36
-    ws["step"].fill_(T - 1)
-    L = eng.dec[0]
-    x, nxt = ws["x"][0], ws["x"][1]
+    from onnx_transformer_b200 import _lib
+    lib = _lib.load()
+    cap = 128 * reps
+    buf = torch.zeros(1 + 4 * cap, dtype=torch.int64, device=eng.dev)
+    ws["step"].fill_(step)
+    ws["graph"].replay()
+    torch.cuda.synchronize()
+    ws["step"].fill_(step)
+    lib.ot_set_timeline(C.c_void_p(buf.data_ptr()), cap)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ws["graph"].replay()
+    e1.record()
+    torch.cuda.synchronize()
+    lib.ot_set_timeline(None, 0)
+    t = buf.cpu().numpy()
+    n = min(int(t[0]), cap)
+    rec = t[1:1 + 4 * n].reshape(n, 4)
     fam = {}
-
-    def timed(name, fn, launches, bytes_per_launch):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / (reps * launches)
-        fam[name] = {"us_per_launch": us, "launches_per_step": launches * (nl if name != "generator" else 1), "bytes_per_launch": bytes_per_launch}
-
-    def gemms():
-        eng._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], lambda t: None)
-        K.linear_w8a8(ws["cq"], L["o"].wq, row_scale=ws["cs"], col_scale=L["o"].sw, bias=L["o"].bias, residual=x, out_kind=K.OUT_F32, out=nxt)
-        K.linear_w8a8(ws["xq"], L["cq"].wq, row_scale=ws["sx"], col_scale=L["cq"].sw, bias=L["cq"].bias, out_kind=K.OUT_Q8, quant_group=D,
-                      out=ws["q2"], out_scale=ws["sq2"])
-        K.linear_w8a8(ws["cq"], L["co"].wq, row_scale=ws["cs"], col_scale=L["co"].sw, bias=L["co"].bias, residual=x, out_kind=K.OUT_F32, out=nxt)
-        K.linear_w8a8(ws["xq"], L["w1"].wq, row_scale=ws["sx"], col_scale=L["w1"].sw, bias=L["w1"].bias, relu=True, out_kind=K.OUT_Q8,
-                      quant_group=FF, out=ws["hq"], out_scale=ws["sh"])
-        K.linear_w8a8(ws["hq"], L["w2"].wq, row_scale=ws["sh"], col_scale=L["w2"].sw, bias=L["w2"].bias, residual=x, out_kind=K.OUT_F32, out=nxt)
-
-    # algorithmic bytes of the 6 GEMMs of one decoder layer-step: int8 weights (3,670,016 B, SURVEY 8d) + operands/results
-    w_bytes = 3 * D * D + 3 * D * D + 2 * D * FF
-    io_bytes = B * (D + 3 * D + 3 * 4) + 3 * B * (D + D * 4 + D * 4) - B * D * 4 + B * (D + D + 4) + B * (D + FF + 4) + B * (FF + 2 * D * 4)
-    timed("gemm_i8", gemms, 6, (w_bytes + io_bytes + 4 * (3 * D + 3 * D + FF + D) * 2) / 6.0)
-
-    def attn():
-        K.attention_q8(ws["qkv"], ws["sqkv"], ws["kc"][0], ws["vc"][0], ws["skc"][0], ws["svc"][0], B=B, Tq=1, Tk=1, Tk_cap=eng.max_len,
-                       ldq=3 * D, sq_stride=3, ldk=D, skv_stride=1, k_new=ws["qkv"][:, D:], v_new=ws["qkv"][:, 2 * D:],
-                       sk_new=ws["sqkv"][:, 1:], sv_new=ws["sqkv"][:, 2:], ld_new=3 * D, snew_stride=3, mask_kind=2, step_dev=ws["step"],
-                       want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"])
-        K.attention_q8(ws["q2"], ws["sq2"], ws["ckv"][:, 0:], ws["ckv"][:, D:], ws["sckv"][:, 0:], ws["sckv"][:, 1:], B=B, Tq=1, Tk=S, Tk_cap=S,
-                       ldq=D, sq_stride=1, ldk=2 * D * nl, skv_stride=2 * nl, mask_kind=1, key_mask=ws["mask"], mask_stride=S,
-                       want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"])
-
-    attn_bytes = B * (T * 2 * D + T * 8 + D + 2 * D + D + 4) + B * (S * 2 * D + S * 8 + S + D + D + 4)
-    timed("attention_q8", attn, 2, attn_bytes / 2.0)
-
-    def lns():
-        for key in ("ln1", "ln2", "ln3"):
-            K.layernorm_quant(x, L[key][0], L[key][1], want_q=True, q=ws["xq"], s=ws["sx"])
-
-    timed("layernorm_quant", lns, 3, B * (D * 4 + D + 4) + 2 * D * 4)
-
-    def gen():
-        K.generator_argmax(ws["hout"], eng.gen_w, eng.gen_b, next_ids=ws["next"], scratch=ws["logits"])
-
-    timed("generator", gen, 2, (eng.vocab * D * 4 + B * D * 4 + 2 * B * eng.vocab * 4) / 2.0)
+    for kid, _, ready, end in rec:
+        if end <= ready:      # a kernel whose block 0 does not stamp its end
+            continue
+        name = FAMILY.get(int(kid), "other")
+        f = fam.setdefault(name, [0, 0.0])
+        f[0] += 1
+        f[1] += (end - ready) / 1e3
+    out = {k: {"launches_per_step": c / reps, "us_per_launch": tot / c, "us_per_step": tot / reps} for k, (c, tot) in fam.items()}
     ws["step"].zero_()
-    return fam
+    return out, e0.elapsed_time(e1) * 1e3 / reps
+
+
+def decode_family_bytes(eng, B, S, T=36):
+    """Algorithmic bytes per launch of each family for one greedy step (DESIGN.md section 4 / SURVEY.md 8d)."""
+    D, FF, nl, V = 512, 2048, eng.n_layers, eng.vocab
+    w_bytes = 3 * D * D + 3 * D * D + 2 * D * FF                       # int8 weights of the 6 GEMMs of a decoder layer: 3,670,016 B
+    io = B * (D + 3 * D + 12) + 3 * B * (D + 4 + 2 * D * 4) + B * (D + D + 4) + B * (D + FF + 4) + B * (FF + 4 + 2 * D * 4)
+    par = 8 * (3 * D + 3 * D + FF + D)                                 # fp32 scale + bias per output column
+    gemm = (w_bytes + io + par) / 6.0
+    attn = (B * (T * (2 * D + 8) + 3 * D + D + 16) + B * (S * (2 * D + 8 + 1) + D + D + 8)) / 2.0
+    ln = B * (D * 4 + D + 4) + 2 * D * 4
+    gen = (V * D * 4 + B * D * 4 + 3 * B * V * 4) / 2.0
+    return {"gemm_i8": gemm, "attention_q8": attn, "layernorm_quant": ln, "generator": gen}
+
+
+def extra_measurements(eng, dev):
+    """Side measurements for the other BASELINE.json configs (not the headline): cfg3 encoder-only forward at B=512 x S=128 and
+    cfg5 fault-injection trials/s (golden decode cached, one faulty B=1 decode per trial)."""
+    import torch
+    from onnx_transformer_b200 import campaign as C
+    from onnx_transformer_b200 import weights as W
+    out = {}
+    ids_np, mask_np = W.synthetic_tokens(7, 512, 128)
+    ids, mask = torch.from_numpy(ids_np).to(dev), torch.from_numpy(mask_np).to(dev)
+    for _ in range(2):
+        eng.encode(ids, mask)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        eng.encode(ids, mask)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    tokens = 512 * 128
+    ops = tokens * 37.75e6 + 6 * 2 * (512 * 8 * 128 * 128 * 64)          # SURVEY.md 8d: linears + QK^T, 2 ops per MAC
+    out["cfg3_encoder_only"] = {"batch": 512, "src_len": 128, "ms": ms, "tokens_per_s": tokens / (ms * 1e-3),
+                                "int8_top_per_s": ops / (ms * 1e-3) / 1e12, "frac_of_4.5_POPS": ops / (ms * 1e-3) / 4.5e15}
+    del ids, mask
+    eng._enc_ws = {}
+    torch.cuda.empty_cache()
+    ids_np, mask_np = W.synthetic_tokens(11, 8, 64)
+    trials = C.make_trials(24, 0, 8, 64)
+    C.run_trials(eng, ids_np, mask_np, trials[:2])                         # warm-up (graph capture for B=1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = C.run_trials(eng, ids_np, mask_np, trials)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    from collections import Counter
+    out["cfg5_fault_injection"] = {"trials": len(trials), "trials_per_s": len(trials) / dt, "outcomes": dict(Counter(r["outcome"] for r in res)),
+                                   "note": "wall clock incl. one golden batch decode; one B=1 faulty greedy decode per trial"}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- main (GPU arm)
@@ -203,6 +234,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_DEFAULT)
     ap.add_argument("--src-len", type=int, default=S_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg3 encoder-only and cfg5 fault-injection side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -289,20 +321,25 @@ def main():
     e2e_value = tokens / (e2e_ms * 1e-3)
 
     if rank == 0:
-        fam = probe_decode_families(eng, ws, B, S)
+        fam, step_us = decode_family_timeline(eng, ws, B, S)
+        nbytes = decode_family_bytes(eng, B, S)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        share = {k: v["us_per_launch"] * v["launches_per_step"] for k, v in fam.items()}
-        dom = max(share, key=share.get)
-        achieved = fam[dom]["bytes_per_launch"] / (fam[dom]["us_per_launch"] * 1e-6) / 1e9
+        share = {k: round(v["us_per_step"], 1) for k, v in fam.items()}
+        dom = max((k for k in share if k in nbytes), key=lambda k: share[k])
+        achieved = nbytes[dom] / (fam[dom]["us_per_launch"] * 1e-6) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                    "us_per_launch": fam[dom]["us_per_launch"], "algorithmic_bytes_per_launch": fam[dom]["bytes_per_launch"],
-                    "families_us_per_step": share}
+                    "us_per_launch": fam[dom]["us_per_launch"], "launches_per_step": fam[dom]["launches_per_step"],
+                    "algorithmic_bytes_per_launch": nbytes[dom], "greedy_step_us": step_us, "families_us_per_greedy_step": share,
+                    "note": "M=64 decode GEMMs are latency-bound (weights L2-resident); see DESIGN.md 4/7"}
+        extra = {}
+        if not args.no_extra:
+            extra = extra_measurements(eng, dev)
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -319,7 +356,7 @@ def main():
                            "l2": "512 MB flush between timed iterations"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes + mask_np.nbytes), "d2h_bytes_per_step": int(B * MAX_LEN * 8)},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

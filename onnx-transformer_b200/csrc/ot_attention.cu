@@ -18,6 +18,7 @@ constexpr int kDm = kHeads * kDk;   // 512
 constexpr int kKPitch = kDm + 16;   // padded K row pitch: conflict-free 128-bit reads across keys
 constexpr int kMaxTk = 192;
 constexpr int kKeysPerLane = kMaxTk / 32;
+constexpr int kQG = 8;              // queries whose P.V products share one pass over the V rows (register tile 8 x 2 per lane)
 
 struct AttnArgs {
   const int8_t* q; int64_t ldq; const float* sq; int64_t sq_stride;
@@ -69,8 +70,8 @@ __global__ void __launch_bounds__(256, 1) attention_q8_kernel(const AttnArgs a) 
   int8_t* Vs = Ks + static_cast<size_t>(Tk_pad) * kKPitch;            // [Tk][512]
   int8_t* Qs = Vs + static_cast<size_t>(Tk_pad) * kDm;                // [QT][512]
   float* Cs = reinterpret_cast<float*>(Qs + QT * kDm);                // [QT][512] fp32 context tile
-  float* Pw = Cs + QT * kDm;                                          // [8][Tk_pad] quantized probabilities / 127
-  float* sks = Pw + kHeads * Tk_pad;                                  // [Tk_pad]
+  float* Pw = Cs + QT * kDm;                                          // [8 warps][Tk_pad][kQG] quantized probabilities
+  float* sks = Pw + kHeads * Tk_pad * kQG;                                  // [Tk_pad]
   float* svs = sks + Tk_pad;                                          // [Tk_pad]
   uint8_t* keep = reinterpret_cast<uint8_t*>(svs + Tk_pad);           // [Tk_pad] key-padding mask
 
@@ -173,7 +174,103 @@ __global__ void __launch_bounds__(256, 1) attention_q8_kernel(const AttnArgs a) 
 
   // ---- per head (warp) and query: scores -> softmax -> quantized P -> context
   const int h = warp;
-  float* P = Pw + h * Tk_pad;
+  float* P = Pw + h * Tk_pad * kQG;
+  if (!has_fault) {
+    // ---- fast path: groups of kQG queries.  Phase 1 computes each query's quantized probabilities into a transposed
+    // [key][kQG] tile; phase 2 walks the V rows ONCE for the whole group (v is converted and scaled once per key, the
+    // kQG probabilities arrive as two 128-bit broadcast loads), same summation order over keys as the per-query path.
+    const int d0 = 2 * lane;
+    for (int g0 = 0; g0 < nq; g0 += kQG) {
+      const int ng = min(kQG, nq - g0);
+#pragma unroll 1
+      for (int qq = 0; qq < kQG; ++qq) {
+        if (qq >= ng) {
+#pragma unroll
+          for (int kk = 0; kk < kKeysPerLane; ++kk)
+            if (kk * 32 < Tk_pad) P[(kk * 32 + lane) * kQG + qq] = 0.f;
+          continue;
+        }
+        const int iq = g0 + qq, i = q0 + iq;
+        const float sqi = a.sq[(static_cast<int64_t>(b) * a.Tq + i) * a.sq_stride];
+        uint32_t qw[16];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint4 t = *reinterpret_cast<const uint4*>(Qs + iq * kDm + h * kDk + w * 16);
+          qw[4 * w] = t.x; qw[4 * w + 1] = t.y; qw[4 * w + 2] = t.z; qw[4 * w + 3] = t.w;
+        }
+        float sc[kKeysPerLane];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int kk = 0; kk < kKeysPerLane; ++kk) {
+          const int j = kk * 32 + lane;
+          sc[kk] = -INFINITY;
+          if (kk * 32 < Tk && j < Tk) {
+            int dot = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const uint4 t = *reinterpret_cast<const uint4*>(Ks + j * kKPitch + h * kDk + w * 16);
+              dot = __dp4a(static_cast<int>(qw[4 * w]), static_cast<int>(t.x), dot);
+              dot = __dp4a(static_cast<int>(qw[4 * w + 1]), static_cast<int>(t.y), dot);
+              dot = __dp4a(static_cast<int>(qw[4 * w + 2]), static_cast<int>(t.z), dot);
+              dot = __dp4a(static_cast<int>(qw[4 * w + 3]), static_cast<int>(t.w), dot);
+            }
+            const float sv_ = __fdiv_rn(__fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), sks[j]), 8.0f);
+            const bool visible = keep[j] && (a.mask_kind != 2 || j <= q_pos0 + i);
+            sc[kk] = visible ? sv_ : -1e9f;
+            mx = fmaxf(mx, sc[kk]);
+          }
+        }
+        mx = warp_max_f(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < kKeysPerLane; ++kk) {
+          const int j = kk * 32 + lane;
+          if (kk * 32 < Tk && j < Tk) {
+            sc[kk] = expf(__fsub_rn(sc[kk], mx));
+            sum += sc[kk];
+          }
+        }
+        sum = warp_sum_f(sum);
+#pragma unroll
+        for (int kk = 0; kk < kKeysPerLane; ++kk) {
+          const int j = kk * 32 + lane;
+          if (kk * 32 < Tk_pad) {
+            float ph = 0.f;
+            if (j < Tk) {
+              const float pq = rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f));   // Round(Mul(p,127))
+              if (a.probs_q) a.probs_q[((static_cast<int64_t>(b) * kHeads + h) * a.Tq + i) * Tk + j] = static_cast<uint8_t>(pq);
+              ph = __fdiv_rn(pq, 127.0f);                                          // Div(127)
+            }
+            P[j * kQG + qq] = ph;
+          }
+        }
+      }
+      __syncwarp();
+      float acc[kQG][2];
+#pragma unroll
+      for (int qq = 0; qq < kQG; ++qq) acc[qq][0] = acc[qq][1] = 0.f;
+#pragma unroll 2
+      for (int j = 0; j < Tk; ++j) {
+        const char2 vv = *reinterpret_cast<const char2*>(Vs + j * kDm + h * kDk + d0);
+        const float svj = svs[j];
+        const float v0 = __fmul_rn(__int2float_rn(vv.x), svj), v1 = __fmul_rn(__int2float_rn(vv.y), svj);
+        const float4 pa = *reinterpret_cast<const float4*>(P + j * kQG);
+        const float4 pb = *reinterpret_cast<const float4*>(P + j * kQG + 4);
+        acc[0][0] = fmaf(pa.x, v0, acc[0][0]); acc[0][1] = fmaf(pa.x, v1, acc[0][1]);
+        acc[1][0] = fmaf(pa.y, v0, acc[1][0]); acc[1][1] = fmaf(pa.y, v1, acc[1][1]);
+        acc[2][0] = fmaf(pa.z, v0, acc[2][0]); acc[2][1] = fmaf(pa.z, v1, acc[2][1]);
+        acc[3][0] = fmaf(pa.w, v0, acc[3][0]); acc[3][1] = fmaf(pa.w, v1, acc[3][1]);
+        acc[4][0] = fmaf(pb.x, v0, acc[4][0]); acc[4][1] = fmaf(pb.x, v1, acc[4][1]);
+        acc[5][0] = fmaf(pb.y, v0, acc[5][0]); acc[5][1] = fmaf(pb.y, v1, acc[5][1]);
+        acc[6][0] = fmaf(pb.z, v0, acc[6][0]); acc[6][1] = fmaf(pb.z, v1, acc[6][1]);
+        acc[7][0] = fmaf(pb.w, v0, acc[7][0]); acc[7][1] = fmaf(pb.w, v1, acc[7][1]);
+      }
+#pragma unroll
+      for (int qq = 0; qq < kQG; ++qq)
+        if (qq < ng) *reinterpret_cast<float2*>(Cs + (g0 + qq) * kDm + h * kDk + d0) = make_float2(acc[qq][0], acc[qq][1]);
+      __syncwarp();
+    }
+  } else
   for (int iq = 0; iq < nq; ++iq) {
     const int i = q0 + iq;
     const float sqi = a.sq[(static_cast<int64_t>(b) * a.Tq + i) * a.sq_stride];
@@ -467,7 +564,7 @@ template <int QT>
 static size_t attn_smem_bytes(int Tk) {
   const int Tk_pad = (Tk + 31) & ~31;
   return static_cast<size_t>(Tk_pad) * kKPitch + static_cast<size_t>(Tk_pad) * kDm + QT * kDm + QT * kDm * 4 +
-         static_cast<size_t>(kHeads) * Tk_pad * 4 + 2 * Tk_pad * 4 + Tk_pad;
+         static_cast<size_t>(kHeads) * Tk_pad * kQG * 4 + 2 * Tk_pad * 4 + Tk_pad;
 }
 
 template <int QT>
@@ -527,6 +624,6 @@ extern "C" int ot_attention_q8(const int8_t* q, int64_t ldq, const float* sq, in
     return OT_OK;
   }
   if (Tq == 1) return launch_attention<1>(a, tk_max, s);
-  if (Tq <= 16 || tk_max > 128) return launch_attention<16>(a, tk_max, s);
+  if (Tq <= 16 || attn_smem_bytes<32>(tk_max) > 227 * 1024) return launch_attention<16>(a, tk_max, s);
   return launch_attention<32>(a, tk_max, s);
 }
