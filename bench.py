@@ -210,17 +210,17 @@ def extra_measurements(eng, dev):
     del ids, mask
     eng._enc_ws = {}
     torch.cuda.empty_cache()
-    ids_np, mask_np = W.synthetic_tokens(11, 8, 64)
-    trials = C.make_trials(24, 0, 8, 64)
-    C.run_trials(eng, ids_np, mask_np, trials[:2])                         # warm-up (graph capture for B=1)
+    ids_np, mask_np = W.synthetic_tokens(11, 64, 64)
+    trials = C.make_trials(256, 0, 64, 64)
+    C.run_trials_batched(eng, ids_np, mask_np, trials[:64], 64)            # warm-up
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = C.run_trials(eng, ids_np, mask_np, trials)
+    res = C.run_trials_batched(eng, ids_np, mask_np, trials, 64)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     from collections import Counter
     out["cfg5_fault_injection"] = {"trials": len(trials), "trials_per_s": len(trials) / dt, "outcomes": dict(Counter(r["outcome"] for r in res)),
-                                   "note": "wall clock incl. one golden batch decode; one B=1 faulty greedy decode per trial"}
+                                   "note": "wall clock incl. one golden batch decode; 64 trials per faulty greedy decode (one fault per batch row)"}
     return out
 
 

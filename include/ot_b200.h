@@ -86,6 +86,16 @@ int ot_linear_w8a8(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, i
                    int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group,
                    const OtFault* fault, void* stream);
 
+/* Batched fault trials (one fault per batch unit): unit u owns output rows [u*rows_per_unit, (u+1)*rows_per_unit);
+ * unit_fault_dev[u] (DEVICE int32) is the index of its fault in faults_dev (DEVICE array) or -1; every fault's flat_index /
+ * window is relative to its own unit, i.e. addresses the one-sentence tensors the reference's trials see
+ * (parallelized_inject_onnx_transformer.py runs batch 1).  A WEIGHT fault perturbs the rows of its unit only. */
+int ot_linear_w8a8_mf(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K,
+                      const float* row_scale, const float* col_scale, const float* bias,
+                      const float* residual, int64_t ldr, int relu,
+                      int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group,
+                      const OtFault* faults_dev, const int32_t* unit_fault_dev, int rows_per_unit, void* stream);
+
 /* Same contract, W holds int4 values packed two per byte (low nibble = even k), [N, K/2] bytes:
  * Brevitas 4-bit weights are unpacked to int8 in shared memory ahead of the MMA (config #4). */
 int ot_linear_w4a8(const int8_t* A, int64_t lda, const uint8_t* W4, int64_t ldw, int M, int N, int K,
@@ -155,6 +165,16 @@ int ot_attention_q8(const int8_t* q, int64_t ldq, const float* sq, int64_t sq_st
                     int64_t mask_stride, int q_pos0, const int32_t* step_dev,
                     float* ctx, int64_t ld_ctx, int8_t* ctx_q, float* ctx_s, uint8_t* probs_q,
                     const OtFault* fault, void* stream);
+
+/* ot_attention_q8 with batched fault trials: unit = sentence b; unit_fault_dev[b] / faults_dev as for ot_linear_w8a8_mf. */
+int ot_attention_q8_mf(const int8_t* q, int64_t ldq, const float* sq, int64_t sq_stride,
+                       int8_t* k, int8_t* v, int64_t ldk, float* sk, float* sv, int64_t skv_stride,
+                       const int8_t* k_new, const int8_t* v_new, int64_t ld_new, const float* sk_new,
+                       const float* sv_new, int64_t snew_stride,
+                       int B, int H, int Tq, int Tk, int Tk_cap, int mask_kind, const uint8_t* key_mask,
+                       int64_t mask_stride, int q_pos0, const int32_t* step_dev,
+                       float* ctx, int64_t ld_ctx, int8_t* ctx_q, float* ctx_s, uint8_t* probs_q,
+                       const OtFault* fault, const OtFault* faults_dev, const int32_t* unit_fault_dev, void* stream);
 
 /* ---- a21: generator Linear(512 -> vocab) + log_softmax + arg-max (generator.py:14-15) ---------------
  * h fp32 [rows, d] (ldh), Wg fp32 [vocab, d], bg [vocab].  next_ids int64 [rows] = first arg-max (torch.max);

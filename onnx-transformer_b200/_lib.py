@@ -48,6 +48,7 @@ SIGNATURES = {
     "ot_set_pdl": (_i, [_i]),
     "ot_set_timeline": (_i, [_p, C.c_uint]),
     "ot_linear_w8a8": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, C.POINTER(OtFault), _p]),
+    "ot_linear_w8a8_mf": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, _p, _p, _i, _p]),
     "ot_linear_w4a8": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, C.POINTER(OtFault), _p]),
     "ot_ln_linear_w8a8": (_i, [_p, _l, _p, _p, _f, _p, _l, _i, _i, _i, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, _p]),
     "ot_unpack_int4": (_i, [_p, _p, _l, _l, _p]),
@@ -57,6 +58,8 @@ SIGNATURES = {
     "ot_embed_pe": (_i, [_p, _l, _p, _p, _l, _i, _i, _i, _p, _f, _p, _p]),
     "ot_attention_q8": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _p, _p, _l, _p, _p, _l,
                                _i, _i, _i, _i, _i, _i, _p, _l, _i, _p, _p, _l, _p, _p, _p, C.POINTER(OtFault), _p]),
+    "ot_attention_q8_mf": (_i, [_p, _l, _p, _l, _p, _p, _l, _p, _p, _l, _p, _p, _l, _p, _p, _l,
+                                  _i, _i, _i, _i, _i, _i, _p, _l, _i, _p, _p, _l, _p, _p, _p, C.POINTER(OtFault), _p, _p, _p]),
     "ot_generator_argmax": (_i, [_p, _l, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ot_append_token": (_i, [_p, _l, _p, _i, _p, _p]),
     "ot_unary_f32": (_i, [_i, _p, _p, _l, _p]),

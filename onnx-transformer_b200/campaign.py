@@ -192,6 +192,39 @@ def run_trials(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials: List[T
     return out
 
 
+def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials: List[Trial], batch: int = 64,
+                       csv_path: Optional[str] = None, rank: int = 0, world: int = 1) -> List[Dict[str, object]]:
+    """Same outcomes as run_trials, `batch` trials per greedy decode: row b of a batch re-decodes trial b's sentence with
+    trial b's fault (one fault per batch unit: ot_linear_w8a8_mf / ot_attention_q8_mf).  The kernels are batch-invariant,
+    so every row equals the batch-1 decode the reference would run."""
+    import torch
+    from .engine import FaultSpec
+    dev = engine.dev
+    ids = torch.from_numpy(src_ids).to(dev)
+    mask = torch.from_numpy(src_mask).to(dev)
+    golden = engine.greedy_decode(ids, mask).cpu().numpy()
+    mine = trials[rank::world]
+    out = []
+    for c0 in range(0, len(mine), batch):
+        chunk = mine[c0:c0 + batch]
+        rows = torch.tensor([t.sentence for t in chunk], dtype=torch.int64, device=dev)
+        specs = [FaultSpec(t.module, t.layer, t.target, t.inject_type, t.bit, t.flat_index, t.window_start, t.window_len, t.value_bits, step=0)
+                 for t in chunk]
+        if len(chunk) < batch:                      # keep one workspace / CUDA graph shape: pad with fault-free rows
+            pad = batch - len(chunk)
+            rows = torch.cat([rows, rows.new_zeros(pad)])
+            specs = specs + [None] * pad
+        faulty = engine.greedy_decode(ids[rows].contiguous(), mask[rows].contiguous(), fault=specs).cpu().numpy()
+        for k, trial in enumerate(chunk):
+            res = classify(golden[trial.sentence], faulty[k])
+            res.update(asdict(trial))
+            out.append(res)
+            if csv_path:
+                with open(csv_path, "a") as f:
+                    f.write(csv_row(trial, res))
+    return out
+
+
 def main(argv=None):
     """Same three flags as the reference (parallelized_inject_onnx_transformer.py:47-52) plus --gpus/--batch/--seed/--trials."""
     ap = argparse.ArgumentParser()
@@ -215,7 +248,7 @@ def main(argv=None):
     trials = make_trials(args.trials, args.seed, args.batch, args.src_len, modules=(args.module,))
     os.makedirs(os.path.dirname(args.experiment_output_name) or ".", exist_ok=True)
     path = args.experiment_output_name if world == 1 else "%s.rank%d" % (args.experiment_output_name, rank)
-    res = run_trials(eng, ids, mask, trials, path, rank, world)
+    res = run_trials_batched(eng, ids, mask, trials, args.batch, path, rank, world)
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, [(r["trial_id"], r["outcome"]) for r in res])

@@ -32,6 +32,8 @@ struct AttnArgs {
   int8_t* ctx_q; float* ctx_s;
   uint8_t* probs_q;
   OtFault fault;
+  const OtFault* mf_faults;   // batched trials: mf_unit[b] = index of sentence b's fault or -1; indices relative to the sentence
+  const int32_t* mf_unit;
 };
 
 enum { OPERAND_Q = 0, OPERAND_K = 1, OPERAND_P = 2, OPERAND_V = 3, OPERAND_SCORES = 4, OPERAND_CTX = 5 };
@@ -136,7 +138,12 @@ __global__ void __launch_bounds__(256, 1) attention_q8_kernel(const AttnArgs a) 
   __syncthreads();
 
   // ---- fault context (App. D); operand selector in fault.reserved
-  const OtFault& f = a.fault;
+  OtFault f = a.fault;
+  if (a.mf_unit != nullptr) {
+    const int fi_ = a.mf_unit[b];
+    if (fi_ >= 0) f = a.mf_faults[fi_];
+    else f.mode = OT_FAULT_NONE;
+  }
   const bool has_fault = f.mode != OT_FAULT_NONE;
   int fb = -1, fh = -1, fi = -1, fj = -1, fd = -1, fw0 = 0, fw1 = 0;
   if (has_fault) {
@@ -170,6 +177,7 @@ __global__ void __launch_bounds__(256, 1) attention_q8_kernel(const AttnArgs a) 
       } break;
     }
   }
+  if (a.mf_unit != nullptr) fb = b;   // batched faults address the sentence's own tensors
   const bool fault_here = has_fault && fb == b && fh == warp;
 
   // ---- per head (warp) and query: scores -> softmax -> quantized P -> context
@@ -589,6 +597,13 @@ OT_DEFINE_TL_SETTER(tl_set_attention)
 
 using namespace ot;
 
+extern "C" int ot_attention_q8_mf(const int8_t* q, int64_t ldq, const float* sq, int64_t sq_stride, int8_t* k, int8_t* v, int64_t ldk, float* sk,
+                                  float* sv, int64_t skv_stride, const int8_t* k_new, const int8_t* v_new, int64_t ld_new, const float* sk_new,
+                                  const float* sv_new, int64_t snew_stride, int B, int H, int Tq, int Tk, int Tk_cap, int mask_kind,
+                                  const uint8_t* key_mask, int64_t mask_stride, int q_pos0, const int32_t* step_dev, float* ctx, int64_t ld_ctx,
+                                  int8_t* ctx_q, float* ctx_s, uint8_t* probs_q, const OtFault* fault, const OtFault* faults_dev,
+                                  const int32_t* unit_fault_dev, void* stream);
+
 extern "C" int ot_attention_q8(const int8_t* q, int64_t ldq, const float* sq, int64_t sq_stride,
                                int8_t* k, int8_t* v, int64_t ldk, float* sk, float* sv, int64_t skv_stride,
                                const int8_t* k_new, const int8_t* v_new, int64_t ld_new, const float* sk_new,
@@ -597,6 +612,19 @@ extern "C" int ot_attention_q8(const int8_t* q, int64_t ldq, const float* sq, in
                                int64_t mask_stride, int q_pos0, const int32_t* step_dev,
                                float* ctx, int64_t ld_ctx, int8_t* ctx_q, float* ctx_s, uint8_t* probs_q,
                                const OtFault* fault, void* stream) {
+  return ot_attention_q8_mf(q, ldq, sq, sq_stride, k, v, ldk, sk, sv, skv_stride, k_new, v_new, ld_new, sk_new, sv_new, snew_stride, B, H, Tq, Tk,
+                            Tk_cap, mask_kind, key_mask, mask_stride, q_pos0, step_dev, ctx, ld_ctx, ctx_q, ctx_s, probs_q, fault, nullptr, nullptr,
+                            stream);
+}
+
+extern "C" int ot_attention_q8_mf(const int8_t* q, int64_t ldq, const float* sq, int64_t sq_stride,
+                                  int8_t* k, int8_t* v, int64_t ldk, float* sk, float* sv, int64_t skv_stride,
+                                  const int8_t* k_new, const int8_t* v_new, int64_t ld_new, const float* sk_new,
+                                  const float* sv_new, int64_t snew_stride,
+                                  int B, int H, int Tq, int Tk, int Tk_cap, int mask_kind, const uint8_t* key_mask,
+                                  int64_t mask_stride, int q_pos0, const int32_t* step_dev,
+                                  float* ctx, int64_t ld_ctx, int8_t* ctx_q, float* ctx_s, uint8_t* probs_q,
+                                  const OtFault* fault, const OtFault* faults_dev, const int32_t* unit_fault_dev, void* stream) {
   OT_REQUIRE_DEVICE();
   OT_REQUIRE(q && sq && k && v && sk && sv, "null operand");
   OT_REQUIRE(H == kHeads, "this build is specialised for 8 heads of 64 features (model.py:15-16)");
@@ -617,8 +645,10 @@ extern "C" int ot_attention_q8(const int8_t* q, int64_t ldq, const float* sq, in
   a.key_mask = key_mask; a.mask_stride = mask_stride; a.q_pos0 = q_pos0; a.step_dev = step_dev;
   a.ctx = ctx; a.ld_ctx = ld_ctx; a.ctx_q = ctx_q; a.ctx_s = ctx_s; a.probs_q = probs_q;
   if (fault) a.fault = *fault; else a.fault.mode = OT_FAULT_NONE;
+  OT_REQUIRE((faults_dev == nullptr) == (unit_fault_dev == nullptr) && !(fault && unit_fault_dev), "bad batched-fault arguments");
+  a.mf_faults = faults_dev; a.mf_unit = unit_fault_dev;
   cudaStream_t s = as_stream(stream);
-  if (Tq == 1 && tk_max <= 32 * kDecKeysPerLane && a.fault.mode == OT_FAULT_NONE && probs_q == nullptr) {
+  if (Tq == 1 && tk_max <= 32 * kDecKeysPerLane && a.fault.mode == OT_FAULT_NONE && a.mf_unit == nullptr && probs_q == nullptr) {
     OT_CHECK_CUDA(launch_kernel(attention_decode_kernel, dim3(B), dim3(256), 0, s, 1, a));
     count_launch();
     return OT_OK;

@@ -58,7 +58,12 @@ struct GemmArgs {
   const float* ln_beta;
   float ln_eps;
   unsigned long long* trace;  // optional per-CTA phase timestamps (profiling aid, OT_GEMM_TRACE)
-  OtFault fault;
+  OtFault fault;              // single fault, absolute indices (mode NONE when unused)
+  // batched trials: unit u owns output rows [u*mf_rows, (u+1)*mf_rows); mf_unit[u] = index into mf_faults or -1; each
+  // fault's flat_index / windows are relative to its own unit (the reference's one-sentence tensors)
+  const OtFault* mf_faults;
+  const int32_t* mf_unit;
+  int mf_rows;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -86,6 +91,8 @@ struct FaultCtx {
   int k;      // contraction index of the flipped operand element
   int delta;  // q' - q
   int w0, w1; // affected window [w0, w1) along columns (INPUT) or rows (WEIGHT)
+  int bit;
+  uint32_t value_bits;
 };
 
 __device__ __forceinline__ int load_w_elem(const GemmArgs& g, int n, int k) {
@@ -95,31 +102,52 @@ __device__ __forceinline__ int load_w_elem(const GemmArgs& g, int n, int k) {
   return (nib ^ 8) - 8;
 }
 
-__device__ __noinline__ FaultCtx resolve_fault(const GemmArgs& g) {
+// `ft` addresses a tensor whose first row is global row `row0` and which spans `nrows` rows (the whole problem for a single
+// fault; one batch unit for batched trials).
+__device__ __noinline__ FaultCtx resolve_fault_at(const GemmArgs& g, const OtFault& ft, int row0, int nrows) {
   FaultCtx f;
-  f.mode = g.fault.mode;
+  f.mode = ft.mode;
   f.row = f.col = f.k = -1;
   f.delta = 0;
   f.w0 = 0;
   f.w1 = 0;
+  f.bit = ft.bit;
+  f.value_bits = ft.value_bits;
   if (f.mode == OT_FAULT_INPUT) {
-    f.row = static_cast<int>(g.fault.flat_index / g.K);
-    f.k = static_cast<int>(g.fault.flat_index % g.K);
+    f.row = row0 + static_cast<int>(ft.flat_index / g.K);
+    f.k = static_cast<int>(ft.flat_index % g.K);
     int q = g.A[static_cast<int64_t>(f.row) * g.lda + f.k];
-    f.delta = flip_int8_bit(q, g.fault.bit) - q;
-    f.w0 = g.fault.window_len > 0 ? g.fault.window_start : 0;
-    f.w1 = g.fault.window_len > 0 ? min(g.N, g.fault.window_start + g.fault.window_len) : g.N;
+    f.delta = flip_int8_bit(q, ft.bit) - q;
+    f.w0 = ft.window_len > 0 ? ft.window_start : 0;
+    f.w1 = ft.window_len > 0 ? min(g.N, ft.window_start + ft.window_len) : g.N;
   } else if (f.mode == OT_FAULT_WEIGHT) {
-    f.col = static_cast<int>(g.fault.flat_index / g.K);
-    f.k = static_cast<int>(g.fault.flat_index % g.K);
+    f.col = static_cast<int>(ft.flat_index / g.K);
+    f.k = static_cast<int>(ft.flat_index % g.K);
     int q = load_w_elem(g, f.col, f.k);
-    f.delta = flip_int8_bit(q, g.fault.bit) - q;
-    f.w0 = g.fault.window_len > 0 ? g.fault.window_start : 0;
-    f.w1 = g.fault.window_len > 0 ? min(g.M, g.fault.window_start + g.fault.window_len) : g.M;
+    f.delta = flip_int8_bit(q, ft.bit) - q;
+    f.w0 = row0 + (ft.window_len > 0 ? ft.window_start : 0);
+    f.w1 = row0 + (ft.window_len > 0 ? min(nrows, ft.window_start + ft.window_len) : nrows);
   } else if (f.mode != OT_FAULT_NONE) {
-    f.row = static_cast<int>(g.fault.flat_index / g.N);
-    f.col = static_cast<int>(g.fault.flat_index % g.N);
+    f.row = row0 + static_cast<int>(ft.flat_index / g.N);
+    f.col = static_cast<int>(ft.flat_index % g.N);
   }
+  return f;
+}
+// The fault (if any) that applies to output row `row`.
+__device__ __forceinline__ FaultCtx resolve_fault(const GemmArgs& g, int row, bool row_ok) {
+  if (g.mf_unit != nullptr) {
+    if (row_ok) {
+      const int u = row / g.mf_rows;
+      const int fi = g.mf_unit[u];
+      if (fi >= 0) return resolve_fault_at(g, g.mf_faults[fi], u * g.mf_rows, g.mf_rows);
+    }
+  } else if (g.fault.mode != OT_FAULT_NONE) {
+    return resolve_fault_at(g, g.fault, 0, g.M);
+  }
+  FaultCtx f;
+  f.mode = OT_FAULT_NONE;
+  f.row = f.col = f.k = -1;
+  f.delta = 0; f.w0 = f.w1 = 0; f.bit = 0; f.value_bits = 0;
   return f;
 }
 
@@ -132,7 +160,7 @@ __device__ __noinline__ int patch_acc_one(const GemmArgs& g, const FaultCtx& f, 
   } else if (f.mode == OT_FAULT_WEIGHT) {
     if (col == f.col && row >= f.w0 && row < f.w1) acc += static_cast<int>(g.A[static_cast<int64_t>(row) * g.lda + f.k]) * f.delta;
   } else if (f.mode == OT_FAULT_ACC_BITFLIP) {
-    if (row == f.row && col == f.col) acc ^= (1 << g.fault.bit);
+    if (row == f.row && col == f.col) acc ^= (1 << f.bit);
   }
   return acc;
 }
@@ -160,8 +188,8 @@ __device__ __noinline__ float patch_out(const GemmArgs& g, const FaultCtx& f, in
   for (int j = 0; j < 16; ++j)
     if (j == idx) v = vals[j];
   uint32_t bits = __float_as_uint(v);
-  if (f.mode == OT_FAULT_RANDOM_BITFLIP) bits ^= (1u << g.fault.bit);
-  else if (f.mode == OT_FAULT_RANDOM) bits = g.fault.value_bits;
+  if (f.mode == OT_FAULT_RANDOM_BITFLIP) bits ^= (1u << f.bit);
+  else if (f.mode == OT_FAULT_RANDOM) bits = f.value_bits;
   else return v;
   float r = __uint_as_float(bits);
   return (r != r) ? 0.0f : r;  // NaN -> 0 (bin2fp32)
@@ -578,7 +606,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // epilogue warps only
     }
-    const FaultCtx f = resolve_fault(g);
+    const FaultCtx f = resolve_fault(g, row, row_ok);
     const EpiFlags e = {g.bias != nullptr, g.relu != 0, f.mode == OT_FAULT_RANDOM_BITFLIP || f.mode == OT_FAULT_RANDOM};
     const float sx = ALN ? (row_ok ? s_rows[row_in_tile] : 1.0f) : ((g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f);
     const int col_base = n_blk * BLOCK_N;
@@ -638,7 +666,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       const int half = (warp_idx - 2) >> 2;
       const int c_lo = half * (BLOCK_N / 2), c_hi = c_lo + BLOCK_N / 2;
-      const FaultCtx f = resolve_fault(g);
+      const FaultCtx f = resolve_fault(g, row, row_ok);
       const EpiFlags e = {g.bias != nullptr, g.relu != 0, f.mode == OT_FAULT_RANDOM_BITFLIP || f.mode == OT_FAULT_RANDOM};
       const float sx = ALN ? (row_ok ? s_rows[row_in_tile] : 1.0f) : ((g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f);
       const int col_base = n_blk * BLOCK_N;
@@ -824,7 +852,7 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
 static int linear_common(bool w4, const int8_t* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                          const float* row_scale, const float* col_scale, const float* bias, const float* residual, int64_t ldr,
                          int relu, int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group, const OtFault* fault,
-                         void* stream) {
+                         void* stream, const OtFault* mf_faults = nullptr, const int32_t* mf_unit = nullptr, int mf_rows = 0) {
   OT_REQUIRE_DEVICE();
   OT_REQUIRE(A && W && out, "null operand");
   OT_REQUIRE(M > 0 && N > 0 && K > 0, "empty problem");
@@ -858,6 +886,10 @@ static int linear_common(bool w4, const int8_t* A, int64_t lda, const void* W, i
   } else {
     g.fault.mode = OT_FAULT_NONE;
   }
+  if (mf_unit != nullptr) {
+    OT_REQUIRE(mf_faults != nullptr && mf_rows > 0 && M % mf_rows == 0 && fault == nullptr, "bad batched-fault arguments");
+    g.mf_faults = mf_faults; g.mf_unit = mf_unit; g.mf_rows = mf_rows;
+  }
   cudaStream_t s = as_stream(stream);
   return w4 ? dispatch_gemm<1>(g, quant_group, s) : dispatch_gemm<0>(g, quant_group, s);
 }
@@ -872,6 +904,14 @@ extern "C" int ot_linear_w8a8(const int8_t* A, int64_t lda, const int8_t* W, int
                               const OtFault* fault, void* stream) {
   return ot::linear_common(false, A, lda, W, ldw, M, N, K, row_scale, col_scale, bias, residual, ldr, relu, out_kind, out, ldo,
                            out_scale, quant_group, fault, stream);
+}
+
+extern "C" int ot_linear_w8a8_mf(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K,
+                                 const float* row_scale, const float* col_scale, const float* bias, const float* residual,
+                                 int64_t ldr, int relu, int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group,
+                                 const OtFault* faults_dev, const int32_t* unit_fault_dev, int rows_per_unit, void* stream) {
+  return ot::linear_common(false, A, lda, W, ldw, M, N, K, row_scale, col_scale, bias, residual, ldr, relu, out_kind, out, ldo,
+                           out_scale, quant_group, nullptr, stream, faults_dev, unit_fault_dev, rows_per_unit);
 }
 
 extern "C" int ot_ln_linear_w8a8(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, const int8_t* W, int64_t ldw,

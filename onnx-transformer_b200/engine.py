@@ -143,6 +143,52 @@ class QuantizedTransformer:
         self.graph_replays = 0   # CUDA-graph replays of the greedy step (each replays ws['graph_launches'] kernels)
         torch.cuda.synchronize(self.dev)
 
+    # ------------------------------------------------------------------------------------------ fault plumbing
+    def _fk(self, fault, module: str, layer: int, targets, rows_per_unit: int, adjust=None) -> dict:
+        """Keyword arguments (`fault=` or `mf=`) for the kernel wrapper at launch site (module, layer, targets).
+        `fault` is None, one FaultSpec (indices absolute over the whole batch) or a list with one Optional[FaultSpec] per
+        sentence (batched trials; indices relative to the sentence, as in the reference's batch-1 trials)."""
+        if fault is None:
+            return {}
+        if isinstance(fault, FaultSpec):
+            if fault.module == module and fault.layer == layer and fault.target in targets:
+                fo = fault.to_ot()
+                if adjust is not None:
+                    adjust(fo, fault.target)
+                return {"fault": fo}
+            return {}
+        entries, unit = [], []
+        for sp in fault:
+            if sp is not None and sp.module == module and sp.layer == layer and sp.target in targets:
+                fo = sp.to_ot()
+                if adjust is not None:
+                    adjust(fo, sp.target)
+                unit.append(len(entries))
+                entries.append(fo)
+            else:
+                unit.append(-1)
+        if not entries:
+            return {}
+        return {"mf": (K.pack_faults(entries, self.dev), torch.tensor(unit, dtype=torch.int32, device=self.dev), rows_per_unit)}
+
+    @staticmethod
+    def _block_adjust(names, width_n: int):
+        """Re-index a fault aimed at one projection of a fused GEMM (q|k|v, or the 12 cross K/V blocks) into the fused
+        [*, width_n] output / concatenated weight."""
+        def adjust(fo, tgt):
+            i = names.index(tgt)
+            if fo.mode == K.FAULT_WEIGHT:
+                fo.flat_index += i * D * D                       # row block i of the concatenated weight
+            elif fo.mode in (K.FAULT_RANDOM, K.FAULT_RANDOM_BITFLIP):
+                r, c = divmod(fo.flat_index, D)
+                fo.flat_index = r * width_n + i * D + c
+            elif fo.mode == K.FAULT_INPUT:
+                # the shared input feeds every projection; the reference perturbs only the targeted MatMul
+                w0 = fo.window_start if fo.window_len > 0 else 0
+                wl = fo.window_len if fo.window_len > 0 else D
+                fo.window_start, fo.window_len = i * D + w0, wl
+        return adjust
+
     # ------------------------------------------------------------------------------------------ setup helpers
     def _positional_encoding(self, n: int) -> torch.Tensor:
         """positional_encodings.py:14-21 -- a constant table (buffer `pe` of the reference module), built with the
@@ -184,22 +230,22 @@ class QuantizedTransformer:
             K.embed_pe(src_ids.reshape(-1).contiguous(), self.src_lut, self.pe, seq_len=S, out=x)
         cur = 0
         for l, L in enumerate(self.enc):
-            f = (lambda tgt: fault.to_ot() if (fault is not None and fault.module == "Encoder" and fault.layer == l and fault.target == tgt) else None)  # noqa: E731
+            fk = (lambda *tgt, _l=l, **kw: self._fk(fault, "Encoder", _l, tgt, S, **kw))  # noqa: E731
             nxt = ws["x"][1 - cur]
             K.layernorm_quant(x, L["ln1"][0], L["ln1"][1], want_q=True, q=ws["xq"], s=ws["sx"])
-            self._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], f)
+            self._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], fk)
             K.attention_q8(ws["qkv"], ws["sqkv"], ws["qkv"][:, D:], ws["qkv"][:, 2 * D:], ws["sqkv"][:, 1:], ws["sqkv"][:, 2:],
                            B=B, Tq=S, Tk=S, ldq=3 * D, sq_stride=3, ldk=3 * D, skv_stride=3, mask_kind=1, key_mask=mask, mask_stride=S,
-                           want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], fault=f("qk") or f("pv"))
+                           want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], **fk("qk", "pv"))
             K.linear_w8a8(ws["cq"], L["o"].wq, row_scale=ws["cs"], col_scale=L["o"].sw, bias=L["o"].bias, residual=x,
-                          out_kind=K.OUT_F32, out=nxt, fault=f("o"))
+                          out_kind=K.OUT_F32, out=nxt, **fk("o"))
             x, cur = nxt, 1 - cur
             nxt = ws["x"][1 - cur]
             K.layernorm_quant(x, L["ln2"][0], L["ln2"][1], want_q=True, q=ws["xq"], s=ws["sx"])
             K.linear_w8a8(ws["xq"], L["w1"].wq, row_scale=ws["sx"], col_scale=L["w1"].sw, bias=L["w1"].bias, relu=True,
-                          out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"], fault=f("ffn1"))
+                          out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"], **fk("ffn1"))
             K.linear_w8a8(ws["hq"], L["w2"].wq, row_scale=ws["sh"], col_scale=L["w2"].sw, bias=L["w2"].bias, residual=x,
-                          out_kind=K.OUT_F32, out=nxt, fault=f("ffn2"))
+                          out_kind=K.OUT_F32, out=nxt, **fk("ffn2"))
             x, cur = nxt, 1 - cur
             if capture is not None:
                 capture["enc%d.out" % l] = x.clone()
@@ -208,29 +254,12 @@ class QuantizedTransformer:
         K.layernorm_quant(x, self.enc_norm[0], self.enc_norm[1], want_y=True, want_q=False, y=memory)
         return memory
 
-    def _qkv(self, lin: _Linear, xq, sx, out, out_scale, f):
+    def _qkv(self, lin: _Linear, xq, sx, out, out_scale, fk):
         """Q, K, V projections as ONE GEMM (they share Round_{36+8l}); a fault aimed at one of them is re-indexed into
         the fused [M,1536] output / [1536,512] weight."""
-        fault = None
-        for i, tgt in enumerate(("q", "k", "v")):
-            fo = f(tgt)
-            if fo is None:
-                continue
-            M = xq.shape[0]
-            if fo.mode == K.FAULT_WEIGHT:
-                fo.flat_index += i * D * D                     # row block i of the concatenated weight
-            elif fo.mode in (K.FAULT_RANDOM, K.FAULT_RANDOM_BITFLIP):
-                r, c = divmod(fo.flat_index, D)
-                fo.flat_index = r * 3 * D + i * D + c
-            elif fo.mode == K.FAULT_INPUT:
-                # the shared input feeds all three projections, the reference perturbs only the targeted MatMul:
-                # restrict the affected output columns to that projection's block
-                w0 = fo.window_start if fo.window_len > 0 else 0
-                wl = fo.window_len if fo.window_len > 0 else D
-                fo.window_start, fo.window_len = i * D + w0, wl
-            fault = fo
+        kw = fk("q", "k", "v", adjust=self._block_adjust(("q", "k", "v"), 3 * D))
         K.linear_w8a8(xq, lin.wq, row_scale=sx, col_scale=lin.sw, bias=lin.bias, out_kind=K.OUT_Q8, quant_group=D, out=out,
-                      out_scale=out_scale, fault=fault)
+                      out_scale=out_scale, **kw)
 
     # ------------------------------------------------------------------------------------------ decoder
     def _dec_workspace(self, B: int, S: int) -> dict:
@@ -255,20 +284,30 @@ class QuantizedTransformer:
     def _prepare_cross_kv(self, ws: dict, memory: torch.Tensor, fault: Optional[FaultSpec]):
         """Round_60 + MatMul_0..11 + Round_61..72: once per sentence batch (the reference recomputes them every step)."""
         K.rowquant(memory.reshape(-1, D), q=ws["mq"], s=ws["sm"])
-        fo = None
-        if fault is not None and fault.module == "Decoder" and fault.target in ("ck", "cv"):
-            fo = fault.to_ot()
-            blk = 2 * fault.layer + (0 if fault.target == "ck" else 1)
-            if fo.mode == K.FAULT_WEIGHT:
-                fo.flat_index += blk * D * D
-            elif fo.mode == K.FAULT_INPUT:
-                w0 = fo.window_start if fo.window_len > 0 else 0
-                fo.window_start, fo.window_len = blk * D + w0, (fo.window_len if fo.window_len > 0 else D)
-            else:
-                r, c = divmod(fo.flat_index, D)
-                fo.flat_index = r * self.ckv.N + blk * D + c
+        S = memory.shape[1]
+        names = tuple(x for l in range(self.n_layers) for x in (("ck", l), ("cv", l)))
+        kw = {}
+        if fault is not None:
+            # the fused GEMM spans all layers: the block index is (target, layer)
+            specs = [fault] if isinstance(fault, FaultSpec) else list(fault)
+            hit = [sp for sp in specs if sp is not None and sp.module == "Decoder" and sp.target in ("ck", "cv")]
+            if hit:
+                def mk(sp):
+                    fo = sp.to_ot()
+                    self._block_adjust(names, self.ckv.N)(fo, (sp.target, sp.layer))
+                    return fo
+                if isinstance(fault, FaultSpec):
+                    kw = {"fault": mk(fault)}
+                else:
+                    entries, unit = [], []
+                    for sp in specs:
+                        if sp is not None and sp.module == "Decoder" and sp.target in ("ck", "cv"):
+                            unit.append(len(entries)); entries.append(mk(sp))
+                        else:
+                            unit.append(-1)
+                    kw = {"mf": (K.pack_faults(entries, self.dev), torch.tensor(unit, dtype=torch.int32, device=self.dev), S)}
         K.linear_w8a8(ws["mq"], self.ckv.wq, row_scale=ws["sm"], col_scale=self.ckv.sw, bias=self.ckv.bias, out_kind=K.OUT_Q8,
-                      quant_group=D, out=ws["ckv"], out_scale=ws["sckv"], fault=fo)
+                      quant_group=D, out=ws["ckv"], out_scale=ws["sckv"], **kw)
 
     def _decode_step(self, ws: dict, B: int, S: int, fault: Optional[FaultSpec] = None, want_margin: bool = False):
         """One greedy step for all sentences: embed ys[:, t] -> 6 decoder layers on ONE new row per sentence (KV cache) ->
@@ -280,51 +319,51 @@ class QuantizedTransformer:
         cur = 0
         nl = self.n_layers
         for l, L in enumerate(self.dec):
-            f = (lambda tgt: fault.to_ot() if (fault is not None and fault.module == "Decoder" and fault.layer == l and fault.target == tgt) else None)  # noqa: E731
+            fk = (lambda *tgt, _l=l, **kw: self._fk(fault, "Decoder", _l, tgt, 1, **kw))  # noqa: E731
             # --- masked self-attention over the KV cache
             nxt = ws["x"][1 - cur]
-            if fused_ln and not (f("q") or f("k") or f("v")):
+            if fused_ln and not fk("q", "k", "v"):
                 # LayerNorm + RowQuant run as the GEMM's prologue (one launch instead of two, no int8 round trip)
                 K.ln_linear_w8a8(x, L["ln1"][0], L["ln1"][1], L["qkv"].wq, col_scale=L["qkv"].sw, bias=L["qkv"].bias, out_kind=K.OUT_Q8,
                                  quant_group=D, out=ws["qkv"], out_scale=ws["sqkv"])
             else:
                 K.layernorm_quant(x, L["ln1"][0], L["ln1"][1], want_q=True, q=ws["xq"], s=ws["sx"])
-                self._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], f)
+                self._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], fk)
             K.attention_q8(ws["qkv"], ws["sqkv"], ws["kc"][l], ws["vc"][l], ws["skc"][l], ws["svc"][l], B=B, Tq=1, Tk=1, Tk_cap=self.max_len,
                            ldq=3 * D, sq_stride=3, ldk=D, skv_stride=1,
                            k_new=ws["qkv"][:, D:], v_new=ws["qkv"][:, 2 * D:], sk_new=ws["sqkv"][:, 1:], sv_new=ws["sqkv"][:, 2:],
                            ld_new=3 * D, snew_stride=3, mask_kind=2, step_dev=step,
-                           want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], fault=f("qk") or f("pv"))
+                           want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], **fk("qk", "pv"))
             K.linear_w8a8(ws["cq"], L["o"].wq, row_scale=ws["cs"], col_scale=L["o"].sw, bias=L["o"].bias, residual=x,
-                          out_kind=K.OUT_F32, out=nxt, fault=f("o"))
+                          out_kind=K.OUT_F32, out=nxt, **fk("o"))
             x, cur = nxt, 1 - cur
             # --- cross-attention over the cached memory projections
             nxt = ws["x"][1 - cur]
-            if fused_ln and not f("cq"):
+            if fused_ln and not fk("cq"):
                 K.ln_linear_w8a8(x, L["ln2"][0], L["ln2"][1], L["cq"].wq, col_scale=L["cq"].sw, bias=L["cq"].bias, out_kind=K.OUT_Q8,
                                  quant_group=D, out=ws["q2"], out_scale=ws["sq2"])
             else:
                 K.layernorm_quant(x, L["ln2"][0], L["ln2"][1], want_q=True, q=ws["xq"], s=ws["sx"])
                 K.linear_w8a8(ws["xq"], L["cq"].wq, row_scale=ws["sx"], col_scale=L["cq"].sw, bias=L["cq"].bias, out_kind=K.OUT_Q8,
-                              quant_group=D, out=ws["q2"], out_scale=ws["sq2"], fault=f("cq"))
+                              quant_group=D, out=ws["q2"], out_scale=ws["sq2"], **fk("cq"))
             K.attention_q8(ws["q2"], ws["sq2"], ws["ckv"][:, 2 * D * l:], ws["ckv"][:, 2 * D * l + D:], ws["sckv"][:, 2 * l:], ws["sckv"][:, 2 * l + 1:],
                            B=B, Tq=1, Tk=S, Tk_cap=S, ldq=D, sq_stride=1, ldk=2 * D * nl, skv_stride=2 * nl, mask_kind=1,
                            key_mask=ws["mask"], mask_stride=S, want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"],
-                           fault=f("cqk") or f("cpv"))
+                           **fk("cqk", "cpv"))
             K.linear_w8a8(ws["cq"], L["co"].wq, row_scale=ws["cs"], col_scale=L["co"].sw, bias=L["co"].bias, residual=x,
-                          out_kind=K.OUT_F32, out=nxt, fault=f("co"))
+                          out_kind=K.OUT_F32, out=nxt, **fk("co"))
             x, cur = nxt, 1 - cur
             # --- feed forward
             nxt = ws["x"][1 - cur]
-            if fused_ln and not f("ffn1"):
+            if fused_ln and not fk("ffn1"):
                 K.ln_linear_w8a8(x, L["ln3"][0], L["ln3"][1], L["w1"].wq, col_scale=L["w1"].sw, bias=L["w1"].bias, relu=True,
                                  out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"])
             else:
                 K.layernorm_quant(x, L["ln3"][0], L["ln3"][1], want_q=True, q=ws["xq"], s=ws["sx"])
                 K.linear_w8a8(ws["xq"], L["w1"].wq, row_scale=ws["sx"], col_scale=L["w1"].sw, bias=L["w1"].bias, relu=True,
-                              out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"], fault=f("ffn1"))
+                              out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"], **fk("ffn1"))
             K.linear_w8a8(ws["hq"], L["w2"].wq, row_scale=ws["sh"], col_scale=L["w2"].sw, bias=L["w2"].bias, residual=x,
-                          out_kind=K.OUT_F32, out=nxt, fault=f("ffn2"))
+                          out_kind=K.OUT_F32, out=nxt, **fk("ffn2"))
             x, cur = nxt, 1 - cur
         K.layernorm_quant(x, self.dec_norm[0], self.dec_norm[1], want_y=True, want_q=False, y=ws["hout"])
         K.generator_argmax(ws["hout"], self.gen_w, self.gen_b, next_ids=ws["next"], scratch=ws["logits"],
@@ -347,7 +386,10 @@ class QuantizedTransformer:
         ws["ys"].zero_()
         ws["ys"][:, 0] = start_symbol
         ws["step"].zero_()
-        fault_step = fault.step if (fault is not None and fault.module == "Decoder" and fault.target not in ("ck", "cv")) else -1
+        specs = [] if fault is None else ([fault] if isinstance(fault, FaultSpec) else [sp for sp in fault if sp is not None])
+        steps = {sp.step for sp in specs if sp.module == "Decoder" and sp.target not in ("ck", "cv")}
+        assert len(steps) <= 1, "all Decoder-target faults of a batch must share one injection step"
+        fault_step = steps.pop() if steps else -1
         want_m = return_margins
         if use_graph and ws["graph"] is None and not want_m:
             # warm-up (sets function attributes, fills the TMA descriptor cache), then capture one step

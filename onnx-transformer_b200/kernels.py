@@ -48,10 +48,27 @@ def _fault_ref(fault: Optional[OtFault]):
     return C.byref(fault) if fault is not None else None
 
 
+_FAULT_DTYPE = None
+
+
+def pack_faults(faults, device) -> torch.Tensor:
+    """A list of OtFault -> device byte tensor holding the C array (32 bytes per entry)."""
+    import numpy as np
+    global _FAULT_DTYPE
+    if _FAULT_DTYPE is None:
+        _FAULT_DTYPE = np.dtype([("mode", "<i4"), ("bit", "<i4"), ("flat_index", "<i8"), ("window_start", "<i4"), ("window_len", "<i4"),
+                                 ("value_bits", "<u4"), ("reserved", "<i4")])
+        assert _FAULT_DTYPE.itemsize == C.sizeof(OtFault)
+    arr = np.zeros(len(faults), dtype=_FAULT_DTYPE)
+    for i, f in enumerate(faults):
+        arr[i] = (f.mode, f.bit, f.flat_index, f.window_start, f.window_len, f.value_bits, f.reserved)
+    return torch.from_numpy(arr.view(np.uint8)).to(device)
+
+
 # ------------------------------------------------------------------------------------------------ GEMM
 def linear_w8a8(a_q: torch.Tensor, w_q: torch.Tensor, *, row_scale=None, col_scale=None, bias=None, residual=None,
                 relu=False, out_kind=OUT_F32, quant_group=0, fault: Optional[OtFault] = None, out=None, out_scale=None,
-                w4=False):
+                w4=False, mf=None):
     """a_q int8 [M,K] (row stride multiple of 16), w_q int8 [N,K] (or uint8 [N,K/2] packed int4 when w4).
     Returns out (int32 / fp32 / int8 [M,N]) and, for OUT_Q8, (out, out_scale [M, N/quant_group])."""
     lib = _lib.load()
@@ -71,6 +88,14 @@ def linear_w8a8(a_q: torch.Tensor, w_q: torch.Tensor, *, row_scale=None, col_sca
         out = torch.empty((M, N), dtype=dt, device=dev)
     if out_kind == OUT_Q8 and out_scale is None:
         out_scale = torch.empty((M, N // quant_group), dtype=torch.float32, device=dev)
+    if mf is not None:
+        faults_dev, unit_dev, rows_per_unit = mf
+        assert not w4 and fault is None
+        rc = lib.ot_linear_w8a8_mf(_ptr(a_q), a_q.stride(0), _ptr(w_q), w_q.stride(0), M, N, K, _ptr(row_scale), _ptr(col_scale), _ptr(bias),
+                                   _ptr(residual), residual.stride(0) if residual is not None else 0, 1 if relu else 0, out_kind, _ptr(out),
+                                   out.stride(0), _ptr(out_scale), int(quant_group), _ptr(faults_dev), _ptr(unit_dev), int(rows_per_unit), _stream())
+        _lib.check(rc, "ot_linear_w8a8_mf")
+        return (out, out_scale) if out_kind == OUT_Q8 else out
     fn = lib.ot_linear_w4a8 if w4 else lib.ot_linear_w8a8
     rc = fn(_ptr(a_q), a_q.stride(0), _ptr(w_q), w_q.stride(0), M, N, K,
             _ptr(row_scale), _ptr(col_scale), _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0,
@@ -173,7 +198,7 @@ def attention_q8(q, sq, k, v, sk, sv, *, B, Tq, Tk, Tk_cap=None, ldq=None, sq_st
                  k_new=None, v_new=None, sk_new=None, sv_new=None, ld_new=0, snew_stride=1,
                  mask_kind=0, key_mask=None, mask_stride=0, q_pos0=0, step_dev=None,
                  want_ctx=True, want_q=False, want_probs=False, fault: Optional[OtFault] = None,
-                 ctx=None, ctx_q=None, ctx_s=None):
+                 ctx=None, ctx_q=None, ctx_s=None, mf=None):
     """Pointer-level wrapper; q/k/v may be views into fused QKV buffers (give ldq/ldk/strides explicitly)."""
     Tk_cap = Tk_cap or Tk
     ldq = ldq if ldq is not None else q.stride(-2)
@@ -187,11 +212,12 @@ def attention_q8(q, sq, k, v, sk, sv, *, B, Tq, Tk, Tk_cap=None, ldq=None, sq_st
     probs = torch.empty((B, 8, Tq, Tk), dtype=torch.uint8, device=dev) if want_probs else None
     if key_mask is not None and mask_stride == 0:
         mask_stride = key_mask.stride(0)
-    rc = _lib.load().ot_attention_q8(
+    rc = _lib.load().ot_attention_q8_mf(
         _ptr(q), ldq, _ptr(sq), sq_stride, _ptr(k), _ptr(v), ldk, _ptr(sk), _ptr(sv), skv_stride,
         _ptr(k_new), _ptr(v_new), ld_new, _ptr(sk_new), _ptr(sv_new), snew_stride,
         B, 8, Tq, Tk, Tk_cap, mask_kind, _ptr(key_mask), mask_stride, q_pos0, _ptr(step_dev),
-        _ptr(ctx), ctx.stride(0) if ctx is not None else 0, _ptr(ctx_q), _ptr(ctx_s), _ptr(probs), _fault_ref(fault), _stream())
+        _ptr(ctx), ctx.stride(0) if ctx is not None else 0, _ptr(ctx_q), _ptr(ctx_s), _ptr(probs), _fault_ref(fault),
+        _ptr(mf[0]) if mf is not None else None, _ptr(mf[1]) if mf is not None else None, _stream())
     _lib.check(rc, "ot_attention_q8")
     return ctx, ctx_q, ctx_s, probs
 

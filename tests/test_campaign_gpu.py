@@ -59,6 +59,21 @@ def test_trials_match_oracle_outcomes(tmp_path):
     assert C.run_trials(eng, ids, mask, trials, csv) == []
 
 
+def test_batched_trials_equal_one_by_one():
+    """One fault per batch row (ot_*_mf entry points) == the batch-1 decode per trial, token for token."""
+    from onnx_transformer_b200.engine import QuantizedTransformer
+    fw = W.init_float_weights(21, SRC_V, TGT_V, N_LAYERS, randomize_norms=True)
+    eng = QuantizedTransformer(fw, n_layers=N_LAYERS, max_len=MAXLEN)
+    ids, mask = W.synthetic_tokens(21, B, S, SRC_V)
+    trials = C.make_trials(48, 3, B, S, n_layers=N_LAYERS)
+    one = C.run_trials(eng, ids, mask, trials)
+    many = C.run_trials_batched(eng, ids, mask, trials, batch=16)
+    assert len(one) == len(many) == len(trials)
+    for a, b in zip(one, many):
+        assert a["trial_id"] == b["trial_id"]
+        assert (a["outcome"], a["tokens_equal"], a["faulty_bleu"]) == (b["outcome"], b["tokens_equal"], b["faulty_bleu"]), a
+
+
 def test_bleu_method4_and_classification():
     g = [5, 6, 7, 8, 9, 10]
     assert C.sentence_bleu_method4(g, g) == pytest.approx(1.0)
