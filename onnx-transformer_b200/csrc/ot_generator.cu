@@ -72,11 +72,14 @@ __global__ void __launch_bounds__(256) generator_reduce_kernel(float* __restrict
   tl_mark(tl, 2);
   const int row = blockIdx.x;
   const float* x = logits + static_cast<int64_t>(row) * vocab;
+  // torch.max / np.argmax semantics: a NaN logit (a fault can produce one) ranks above every number, the first one wins;
+  // NaNs are mapped to +inf for the comparison so the returned index is always a valid token id.
   float best = -INFINITY, second = -INFINITY;
   int bidx = 0x7fffffff;
   for (int v = threadIdx.x; v < vocab; v += blockDim.x) {
-    const float t = x[v];
-    if (t > best) { second = best; best = t; bidx = v; }
+    float t = x[v];
+    if (t != t) t = INFINITY;
+    if (t > best || (t == best && v < bidx)) { second = best; best = t; bidx = v; }
     else if (t > second) second = t;
   }
   // warp then block reduction of (best, first index, second)
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(256) generator_reduce_kernel(float* __restrict
       else s2 = fmaxf(s2, ob);
     }
     s_val[0] = b; s_idx[0] = bi; s_second[0] = s2;
-    next_ids[row] = bi;
+    next_ids[row] = (bi >= 0 && bi < vocab) ? bi : 0;
     if (margin) margin[row] = b - s2;
   }
   __syncthreads();
