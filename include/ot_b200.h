@@ -115,6 +115,9 @@ int ot_ln_linear_w8a8(const float* x, int64_t ldx, const float* gamma, const flo
 /* Standalone nibble unpack: W4 [rows, cols/2] -> int8 [rows, cols] (sign-extended). */
 int ot_unpack_int4(const uint8_t* W4, int8_t* W8, int64_t rows, int64_t cols, void* stream);
 
+/* Inverse of ot_unpack_int4: int8 values in [-8, 7] -> packed nibbles (low nibble = even k). */
+int ot_pack_int4(const int8_t* W8, uint8_t* W4, int64_t rows, int64_t cols, void* stream);
+
 /* ---- a6+a7: LayerNorm (+ per-token quant) ---------------------------------------------------------
  * layer_norm.py:12-15: a*(x-mean)/(sqrt(sum((x-mean)^2)/(n-1)) + eps) + b, then the RowQuant of
  * quant_linear.py:31-43 when q_out != NULL.  x fp32 [rows, n]; y_out (fp32, optional) [rows,n];

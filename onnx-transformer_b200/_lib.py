@@ -52,6 +52,7 @@ SIGNATURES = {
     "ot_linear_w4a8": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, C.POINTER(OtFault), _p]),
     "ot_ln_linear_w8a8": (_i, [_p, _l, _p, _p, _f, _p, _l, _i, _i, _i, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, _p]),
     "ot_unpack_int4": (_i, [_p, _p, _l, _l, _p]),
+    "ot_pack_int4": (_i, [_p, _p, _l, _l, _p]),
     "ot_layernorm_quant": (_i, [_p, _p, _p, _l, _i, _f, _p, _p, _p, _p]),
     "ot_rowquant": (_i, [_p, _l, _l, _i, _i, _p, _p, _p, _p]),
     "ot_residual_add": (_i, [_p, _p, _p, _l, _p]),

@@ -169,6 +169,14 @@ __global__ void __launch_bounds__(256) unpack_int4_kernel(const uint8_t* __restr
   }
 }
 
+__global__ void __launch_bounds__(256) pack_int4_kernel(const int8_t* __restrict__ w8, uint8_t* __restrict__ w4, int64_t nbytes) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nbytes;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint16_t pair = reinterpret_cast<const uint16_t*>(w8)[i];       // even k in the low byte
+    w4[i] = static_cast<uint8_t>((pair & 0xF) | (((pair >> 8) & 0xF) << 4));
+  }
+}
+
 // ys[b, step+1] = next[b]; step++  (greedy_decode: parallelized_inject_onnx_transformer.py:753-758)
 __global__ void append_token_kernel(int64_t* __restrict__ ys, int64_t ld, const int64_t* __restrict__ next, int B,
                                     int32_t* __restrict__ step_dev) {
@@ -259,6 +267,18 @@ extern "C" int ot_unpack_int4(const uint8_t* W4, int8_t* W8, int64_t rows, int64
   if (nbytes == 0) return OT_OK;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>((nbytes + 255) / 256, 148 * 16));
   unpack_int4_kernel<<<grid, 256, 0, as_stream(stream)>>>(W4, W8, nbytes);
+  OT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OT_OK;
+}
+
+extern "C" int ot_pack_int4(const int8_t* W8, uint8_t* W4, int64_t rows, int64_t cols, void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(W4 && W8 && rows >= 0 && cols % 2 == 0, "cols must be even");
+  const int64_t nbytes = rows * cols / 2;
+  if (nbytes == 0) return OT_OK;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>((nbytes + 255) / 256, 148 * 16));
+  pack_int4_kernel<<<grid, 256, 0, as_stream(stream)>>>(W8, W4, nbytes);
   OT_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OT_OK;

@@ -72,7 +72,7 @@ class FaultSpec:
 class _Linear:
     """Device-resident quantized linear: int8 weight [N,K], per-output-channel scale, fp32 bias."""
 
-    def __init__(self, w_float: List[torch.Tensor], biases: List[torch.Tensor]):
+    def __init__(self, w_float: List[torch.Tensor], biases: List[torch.Tensor], bits: int = 8):
         # W8A8Linear.from_float (quant_linear.py:122-147): stored weight = round(W/s)*s ; forward re-quantizes it
         # (quant_linear.py:114-116).  Both steps run on the GPU through the RowQuant kernel.
         qs, ss = [], []
@@ -85,6 +85,24 @@ class _Linear:
         self.sw = torch.cat(ss, 0).contiguous()
         self.bias = torch.cat([b.reshape(-1) for b in biases], 0).contiguous()
         self.N, self.K = self.wq.shape
+        self.w4 = False
+        if bits == 4:
+            # config #4 (dialect B style 4-bit weights): signed non-narrow range [-8, 7], per-channel scale
+            # amax / 8, packed two per byte; unpacked to int8 in shared memory by the GEMM (ot_linear_w4a8)
+            w = torch.cat([x.contiguous() for x in w_float], 0)
+            amax = K.reduce_last("ReduceMax", K.unary("Abs", w))
+            s4 = K.binary("Div", K.clip(amax, 1e-5, 3.4e38), torch.full((1,), 8.0, device=w.device))
+            q4 = K.cast(K.clip(K.unary("Round", K.binary("Div", w, s4)), -8.0, 7.0), torch.int8)
+            self.wq8 = q4                                   # unpacked copy (tests / fault bookkeeping)
+            self.wq = K.pack_int4(q4)
+            self.sw = s4.reshape(-1).contiguous()
+            self.w4 = True
+
+    def gemm(self, a_q, row_scale, **kw):
+        """a_q @ W^T through the tcgen05 GEMM with this layer's scales and bias (w8 or packed-w4 weights)."""
+        if self.w4 and (kw.get("fault") is not None or kw.get("mf") is not None):
+            raise K.OtError("fault hooks are implemented for the int8-weight engine (dialect A)")
+        return K.linear_w8a8(a_q, self.wq, row_scale=row_scale, col_scale=self.sw, bias=self.bias, w4=self.w4, **kw)
 
 
 class QuantizedTransformer:
@@ -92,7 +110,7 @@ class QuantizedTransformer:
     smoothed if SmoothQuant is wanted: get_quantized_model.smooth_lm is an offline weight transform)."""
 
     def __init__(self, float_weights: Dict[str, np.ndarray], n_layers: int = 6, device: Optional[torch.device] = None, max_len: int = W.MAX_LEN,
-                 pdl: bool = True, fused_ln: bool = False):
+                 pdl: bool = True, fused_ln: bool = False, weight_bits: int = 8):
         if not torch.cuda.is_available():
             raise K.OtError("QuantizedTransformer needs a CUDA device: this package has no CPU fallback")
         K._lib.load().ot_set_pdl(1 if pdl else 0)   # programmatic dependent launch for every kernel of the library
@@ -100,6 +118,8 @@ class QuantizedTransformer:
         self.n_layers = n_layers
         self.max_len = max_len
         t = lambda name: torch.from_numpy(np.ascontiguousarray(float_weights[name], dtype=np.float32)).to(self.dev)  # noqa: E731
+        self.weight_bits = weight_bits
+        _L = lambda ws_, bs_: _Linear(ws_, bs_, bits=weight_bits)  # noqa: E731
         self.enc, self.dec = [], []
         for l in range(n_layers):
             p = "encoder.layers.%d." % l
@@ -107,10 +127,10 @@ class QuantizedTransformer:
             self.enc.append(dict(
                 ln1=(t(p + "sublayer.0.norm.a_2"), t(p + "sublayer.0.norm.b_2")),
                 ln2=(t(p + "sublayer.1.norm.a_2"), t(p + "sublayer.1.norm.b_2")),
-                qkv=_Linear([t((a % i) + ".weight") for i in range(3)], [t((a % i) + ".bias") for i in range(3)]),
-                o=_Linear([t((a % 3) + ".weight")], [t((a % 3) + ".bias")]),
-                w1=_Linear([t(p + "feed_forward.w_1.weight")], [t(p + "feed_forward.w_1.bias")]),
-                w2=_Linear([t(p + "feed_forward.w_2.weight")], [t(p + "feed_forward.w_2.bias")])))
+                qkv=_L([t((a % i) + ".weight") for i in range(3)], [t((a % i) + ".bias") for i in range(3)]),
+                o=_L([t((a % 3) + ".weight")], [t((a % 3) + ".bias")]),
+                w1=_L([t(p + "feed_forward.w_1.weight")], [t(p + "feed_forward.w_1.bias")]),
+                w2=_L([t(p + "feed_forward.w_2.weight")], [t(p + "feed_forward.w_2.bias")])))
         ckv_w, ckv_b = [], []
         for l in range(n_layers):
             p = "decoder.layers.%d." % l
@@ -119,16 +139,16 @@ class QuantizedTransformer:
                 ln1=(t(p + "sublayer.0.norm.a_2"), t(p + "sublayer.0.norm.b_2")),
                 ln2=(t(p + "sublayer.1.norm.a_2"), t(p + "sublayer.1.norm.b_2")),
                 ln3=(t(p + "sublayer.2.norm.a_2"), t(p + "sublayer.2.norm.b_2")),
-                qkv=_Linear([t((a % i) + ".weight") for i in range(3)], [t((a % i) + ".bias") for i in range(3)]),
-                o=_Linear([t((a % 3) + ".weight")], [t((a % 3) + ".bias")]),
-                cq=_Linear([t((c % 0) + ".weight")], [t((c % 0) + ".bias")]),
-                co=_Linear([t((c % 3) + ".weight")], [t((c % 3) + ".bias")]),
-                w1=_Linear([t(p + "feed_forward.w_1.weight")], [t(p + "feed_forward.w_1.bias")]),
-                w2=_Linear([t(p + "feed_forward.w_2.weight")], [t(p + "feed_forward.w_2.bias")])))
+                qkv=_L([t((a % i) + ".weight") for i in range(3)], [t((a % i) + ".bias") for i in range(3)]),
+                o=_L([t((a % 3) + ".weight")], [t((a % 3) + ".bias")]),
+                cq=_L([t((c % 0) + ".weight")], [t((c % 0) + ".bias")]),
+                co=_L([t((c % 3) + ".weight")], [t((c % 3) + ".bias")]),
+                w1=_L([t(p + "feed_forward.w_1.weight")], [t(p + "feed_forward.w_1.bias")]),
+                w2=_L([t(p + "feed_forward.w_2.weight")], [t(p + "feed_forward.w_2.bias")])))
             ckv_w += [t((c % 1) + ".weight"), t((c % 2) + ".weight")]
             ckv_b += [t((c % 1) + ".bias"), t((c % 2) + ".bias")]
         # all 12 cross-attention K/V projections (MatMul_0..11) as one [12*512, 512] GEMM sharing Round_60
-        self.ckv = _Linear(ckv_w, ckv_b)
+        self.ckv = _L(ckv_w, ckv_b)
         self.enc_norm = (t("encoder.norm.a_2"), t("encoder.norm.b_2"))
         self.dec_norm = (t("decoder.norm.a_2"), t("decoder.norm.b_2"))
         self.src_lut = t("src_embed.0.lut.weight")
@@ -237,14 +257,14 @@ class QuantizedTransformer:
             K.attention_q8(ws["qkv"], ws["sqkv"], ws["qkv"][:, D:], ws["qkv"][:, 2 * D:], ws["sqkv"][:, 1:], ws["sqkv"][:, 2:],
                            B=B, Tq=S, Tk=S, ldq=3 * D, sq_stride=3, ldk=3 * D, skv_stride=3, mask_kind=1, key_mask=mask, mask_stride=S,
                            want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], **fk("qk", "pv"))
-            K.linear_w8a8(ws["cq"], L["o"].wq, row_scale=ws["cs"], col_scale=L["o"].sw, bias=L["o"].bias, residual=x,
+            L["o"].gemm(ws["cq"], ws["cs"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("o"))
             x, cur = nxt, 1 - cur
             nxt = ws["x"][1 - cur]
             K.layernorm_quant(x, L["ln2"][0], L["ln2"][1], want_q=True, q=ws["xq"], s=ws["sx"])
-            K.linear_w8a8(ws["xq"], L["w1"].wq, row_scale=ws["sx"], col_scale=L["w1"].sw, bias=L["w1"].bias, relu=True,
+            L["w1"].gemm(ws["xq"], ws["sx"], relu=True,
                           out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"], **fk("ffn1"))
-            K.linear_w8a8(ws["hq"], L["w2"].wq, row_scale=ws["sh"], col_scale=L["w2"].sw, bias=L["w2"].bias, residual=x,
+            L["w2"].gemm(ws["hq"], ws["sh"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("ffn2"))
             x, cur = nxt, 1 - cur
             if capture is not None:
@@ -258,7 +278,7 @@ class QuantizedTransformer:
         """Q, K, V projections as ONE GEMM (they share Round_{36+8l}); a fault aimed at one of them is re-indexed into
         the fused [M,1536] output / [1536,512] weight."""
         kw = fk("q", "k", "v", adjust=self._block_adjust(("q", "k", "v"), 3 * D))
-        K.linear_w8a8(xq, lin.wq, row_scale=sx, col_scale=lin.sw, bias=lin.bias, out_kind=K.OUT_Q8, quant_group=D, out=out,
+        lin.gemm(xq, sx, out_kind=K.OUT_Q8, quant_group=D, out=out,
                       out_scale=out_scale, **kw)
 
     # ------------------------------------------------------------------------------------------ decoder
@@ -306,14 +326,14 @@ class QuantizedTransformer:
                         else:
                             unit.append(-1)
                     kw = {"mf": (K.pack_faults(entries, self.dev), torch.tensor(unit, dtype=torch.int32, device=self.dev), S)}
-        K.linear_w8a8(ws["mq"], self.ckv.wq, row_scale=ws["sm"], col_scale=self.ckv.sw, bias=self.ckv.bias, out_kind=K.OUT_Q8,
+        self.ckv.gemm(ws["mq"], ws["sm"], out_kind=K.OUT_Q8,
                       quant_group=D, out=ws["ckv"], out_scale=ws["sckv"], **kw)
 
     def _decode_step(self, ws: dict, B: int, S: int, fault: Optional[FaultSpec] = None, want_margin: bool = False):
         """One greedy step for all sentences: embed ys[:, t] -> 6 decoder layers on ONE new row per sentence (KV cache) ->
         final norm -> generator -> arg-max -> ys[:, t+1]; t lives in device memory (ws['step'])."""
         step = ws["step"]
-        fused_ln = self.fused_ln and B <= 128
+        fused_ln = self.fused_ln and B <= 128 and self.weight_bits == 8
         x = ws["x"][0]
         K.embed_pe(ws["ys"], self.tgt_lut, self.pe, seq_len=1, pos_dev=step, ids_stride=ws["ys"].stride(0), rows=B, out=x)
         cur = 0
@@ -334,7 +354,7 @@ class QuantizedTransformer:
                            k_new=ws["qkv"][:, D:], v_new=ws["qkv"][:, 2 * D:], sk_new=ws["sqkv"][:, 1:], sv_new=ws["sqkv"][:, 2:],
                            ld_new=3 * D, snew_stride=3, mask_kind=2, step_dev=step,
                            want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], **fk("qk", "pv"))
-            K.linear_w8a8(ws["cq"], L["o"].wq, row_scale=ws["cs"], col_scale=L["o"].sw, bias=L["o"].bias, residual=x,
+            L["o"].gemm(ws["cq"], ws["cs"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("o"))
             x, cur = nxt, 1 - cur
             # --- cross-attention over the cached memory projections
@@ -344,13 +364,13 @@ class QuantizedTransformer:
                                  quant_group=D, out=ws["q2"], out_scale=ws["sq2"])
             else:
                 K.layernorm_quant(x, L["ln2"][0], L["ln2"][1], want_q=True, q=ws["xq"], s=ws["sx"])
-                K.linear_w8a8(ws["xq"], L["cq"].wq, row_scale=ws["sx"], col_scale=L["cq"].sw, bias=L["cq"].bias, out_kind=K.OUT_Q8,
+                L["cq"].gemm(ws["xq"], ws["sx"], out_kind=K.OUT_Q8,
                               quant_group=D, out=ws["q2"], out_scale=ws["sq2"], **fk("cq"))
             K.attention_q8(ws["q2"], ws["sq2"], ws["ckv"][:, 2 * D * l:], ws["ckv"][:, 2 * D * l + D:], ws["sckv"][:, 2 * l:], ws["sckv"][:, 2 * l + 1:],
                            B=B, Tq=1, Tk=S, Tk_cap=S, ldq=D, sq_stride=1, ldk=2 * D * nl, skv_stride=2 * nl, mask_kind=1,
                            key_mask=ws["mask"], mask_stride=S, want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"],
                            **fk("cqk", "cpv"))
-            K.linear_w8a8(ws["cq"], L["co"].wq, row_scale=ws["cs"], col_scale=L["co"].sw, bias=L["co"].bias, residual=x,
+            L["co"].gemm(ws["cq"], ws["cs"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("co"))
             x, cur = nxt, 1 - cur
             # --- feed forward
@@ -360,9 +380,9 @@ class QuantizedTransformer:
                                  out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"])
             else:
                 K.layernorm_quant(x, L["ln3"][0], L["ln3"][1], want_q=True, q=ws["xq"], s=ws["sx"])
-                K.linear_w8a8(ws["xq"], L["w1"].wq, row_scale=ws["sx"], col_scale=L["w1"].sw, bias=L["w1"].bias, relu=True,
+                L["w1"].gemm(ws["xq"], ws["sx"], relu=True,
                               out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"], **fk("ffn1"))
-            K.linear_w8a8(ws["hq"], L["w2"].wq, row_scale=ws["sh"], col_scale=L["w2"].sw, bias=L["w2"].bias, residual=x,
+            L["w2"].gemm(ws["hq"], ws["sh"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("ffn2"))
             x, cur = nxt, 1 - cur
         K.layernorm_quant(x, self.dec_norm[0], self.dec_norm[1], want_y=True, want_q=False, y=ws["hout"])

@@ -132,6 +132,14 @@ def unpack_int4(w4: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pack_int4(w8: torch.Tensor) -> torch.Tensor:
+    _req(w8, torch.int8, "w8")
+    rows, cols = w8.shape
+    out = torch.empty((rows, cols // 2), dtype=torch.uint8, device=w8.device)
+    _lib.check(_lib.load().ot_pack_int4(_ptr(w8.contiguous()), _ptr(out), rows, cols, _stream()), "ot_pack_int4")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ row ops
 def layernorm_quant(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6, want_y=False, want_q=True,
                     y=None, q=None, s=None):

@@ -66,6 +66,21 @@ def fake_quantize_weights(w: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     return out
 
 
+def quantize_weights_int4(w: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """Config #4 (dialect B style, SURVEY.md App. C -- Brevitas semantics from its documentation, parity unpinned): every
+    attention / FFN linear weight on the signed 4-bit grid [-8, 7] with per-output-channel scale amax/8.  The result is
+    stored de-quantized, with "<name>.int4_scale" beside it so the executor can recover (q, s) exactly."""
+    out = dict(w)
+    for k, v in w.items():
+        if k.endswith(".weight") and v.ndim == 2 and (".linears." in k or ".feed_forward." in k):
+            amax = np.max(np.abs(v), axis=-1, keepdims=True).astype(F32)
+            s = (np.maximum(amax, F32(1e-5)) / F32(8.0)).astype(F32)
+            q = np.clip(np.rint((v / s).astype(F32)), -8, 7).astype(np.int8)
+            out[k] = q                       # int8 values in [-8,7]
+            out[k[:-7] + ".int4_scale"] = s
+    return out
+
+
 def get_quantized(float_weights: Dict[str, np.ndarray], scales: Optional[Dict[str, np.ndarray]] = None, n_layers: int = 6):
     """get_quantized_model.py:174-178: smooth_lm (when scales are given) then quantize_transformer."""
     w = {k: np.array(v, dtype=F32, copy=True) for k, v in float_weights.items()}
@@ -85,7 +100,10 @@ def _linear(w, prefix: str, x: np.ndarray, mode: str, relu=False, residual=None,
     shape = x.shape
     x2 = x.reshape(-1, shape[-1])
     xq, sx = xq_sx if xq_sx is not None else ox.row_quant(x2)
-    wq, sw = ox.row_quant(w[prefix + ".weight"])
+    if prefix + ".int4_scale" in w:          # config #4: static 4-bit weights
+        wq, sw = w[prefix + ".weight"], w[prefix + ".int4_scale"]
+    else:
+        wq, sw = ox.row_quant(w[prefix + ".weight"])
     bias = w[prefix + ".bias"]
     if mode == "int-exact":
         acc = ox.int_matmul(xq, wq)

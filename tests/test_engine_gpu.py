@@ -77,3 +77,27 @@ def test_full_size_model_decode_runs_and_matches_oracle_prefix():
     # decoding is deterministic and batch-invariant: sentence 0 alone gives the same tokens
     ys0 = eng.greedy_decode(idt[:1], mt[:1]).cpu().numpy()
     assert np.array_equal(ys0[0], ys[0])
+
+
+def test_int4_weight_engine_matches_oracle():
+    """BASELINE config #4: packed int4 weights (unpacked to int8 in shared memory by the GEMM), int8 activations."""
+    from onnx_transformer_b200.engine import QuantizedTransformer
+    fw = W.init_float_weights(9, 101, 89, 2, randomize_norms=True)
+    eng = QuantizedTransformer(fw, n_layers=2, max_len=9, weight_bits=4)
+    w4 = om.quantize_weights_int4({k: np.array(v) for k, v in fw.items()})
+    assert np.array_equal(eng.enc[0]["w1"].wq8.cpu().numpy(), w4["encoder.layers.0.feed_forward.w_1.weight"])
+    assert np.array_equal(eng.enc[0]["w1"].sw.cpu().numpy().view(np.uint32), w4["encoder.layers.0.feed_forward.w_1.int4_scale"].reshape(-1).view(np.uint32))
+    ids, mask = W.synthetic_tokens(9, 3, 12, 101, min_len=6)
+    idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    mem = eng.encode(idt, mt).cpu().numpy()
+    pe = ox.positional_encoding(80)
+    ref = om.encode(w4, ox.embed(ids, w4["src_embed.0.lut.weight"], pe), mask, "int-exact", 2)
+    err = np.abs(mem - ref)
+    assert err.mean() < 2e-2 and err.max() < 0.3
+    ys = eng.greedy_decode(idt, mt, 9).cpu().numpy()
+    ref_ys, margins, _ = om.greedy_decode(w4, ids, mask, 9, 0, "int-exact", 2, return_margins=True)
+    for b in range(3):
+        for t in range(8):
+            if ys[b, t + 1] != ref_ys[b, t + 1]:
+                assert margins[b, t] < 0.1, (b, t, margins[b, t])
+                break
