@@ -456,43 +456,53 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(const AttnArgs a)
   uint4 vbuf[4 * kDecKeysPerLane];
 #pragma unroll
   for (int it = 0; it < 4 * kDecKeysPerLane; ++it) {
-    const int j = it * 8 + (lane >> 2);
-    vbuf[it] = make_uint4(0, 0, 0, 0);
-    if (j < Tk) {
-      const int8_t* vp = (j >= new0) ? a.v_new + static_cast<int64_t>(b) * a.ld_new + h * kDk
-                                     : a.v + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk;
-      vbuf[it] = *reinterpret_cast<const uint4*>(vp + (lane & 3) * 16);
-    }
+    const int jr = it * 8 + (lane >> 2);
+    const int j = min(jr, Tk - 1);
+    const int8_t* vp = (j >= new0) ? a.v_new + static_cast<int64_t>(b) * a.ld_new + h * kDk
+                                   : a.v + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk;
+    const uint4 t = *reinterpret_cast<const uint4*>(vp + (lane & 3) * 16);
+    vbuf[it] = (jr < Tk) ? t : make_uint4(0, 0, 0, 0);
   }
 
+  // K rows, scales and mask of this lane's keys: branch-free (indices clamped, results masked) so that all loads of all
+  // three key rounds are in flight together instead of one L2 round trip per round
   float sc[kDecKeysPerLane], svl[kDecKeysPerLane];
+  uint4 kreg[kDecKeysPerLane][4];
+  float skl[kDecKeysPerLane];
+  uint8_t keepl[kDecKeysPerLane];
+#pragma unroll
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
+    const int j = min(kk * 32 + lane, Tk - 1);
+    const bool fresh = j >= new0;
+    const int8_t* kp = fresh ? a.k_new + static_cast<int64_t>(b) * a.ld_new + h * kDk
+                             : a.k + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) kreg[kk][w] = *reinterpret_cast<const uint4*>(kp + w * 16);
+    const float* skp = fresh ? a.sk_new + static_cast<int64_t>(b) * a.snew_stride : a.sk + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.skv_stride;
+    const float* svp = fresh ? a.sv_new + static_cast<int64_t>(b) * a.snew_stride : a.sv + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.skv_stride;
+    skl[kk] = *skp;
+    svl[kk] = *svp;
+    keepl[kk] = (a.mask_kind == 1) ? a.key_mask[static_cast<int64_t>(b) * a.mask_stride + j] : 1;
+  }
   float mx = -INFINITY;
 #pragma unroll
   for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
     const int j = kk * 32 + lane;
-    sc[kk] = -INFINITY;
-    svl[kk] = 0.f;
-    if (j < Tk) {
-      const bool fresh = j >= new0;
-      const int8_t* kp = fresh ? a.k_new + static_cast<int64_t>(b) * a.ld_new + h * kDk
-                               : a.k + (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk;
-      int dot = 0;
+    int dot = 0;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const uint4 t = *reinterpret_cast<const uint4*>(kp + w * 16);
-        dot = __dp4a(static_cast<int>(qw[4 * w]), static_cast<int>(t.x), dot);
-        dot = __dp4a(static_cast<int>(qw[4 * w + 1]), static_cast<int>(t.y), dot);
-        dot = __dp4a(static_cast<int>(qw[4 * w + 2]), static_cast<int>(t.z), dot);
-        dot = __dp4a(static_cast<int>(qw[4 * w + 3]), static_cast<int>(t.w), dot);
-      }
-      const float skj = fresh ? a.sk_new[static_cast<int64_t>(b) * a.snew_stride] : a.sk[(static_cast<int64_t>(b) * a.Tk_cap + j) * a.skv_stride];
-      svl[kk] = fresh ? a.sv_new[static_cast<int64_t>(b) * a.snew_stride] : a.sv[(static_cast<int64_t>(b) * a.Tk_cap + j) * a.skv_stride];
-      float s = __fdiv_rn(__fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), skj), 8.0f);
-      const bool keep = (a.mask_kind != 1) || a.key_mask[static_cast<int64_t>(b) * a.mask_stride + j] != 0;
-      const bool visible = keep && (a.mask_kind != 2 || j <= q_pos0);
-      sc[kk] = visible ? s : -1e9f;
-      mx = fmaxf(mx, sc[kk]);
+    for (int w = 0; w < 4; ++w) {
+      const uint4 t = kreg[kk][w];
+      dot = __dp4a(static_cast<int>(qw[4 * w]), static_cast<int>(t.x), dot);
+      dot = __dp4a(static_cast<int>(qw[4 * w + 1]), static_cast<int>(t.y), dot);
+      dot = __dp4a(static_cast<int>(qw[4 * w + 2]), static_cast<int>(t.z), dot);
+      dot = __dp4a(static_cast<int>(qw[4 * w + 3]), static_cast<int>(t.w), dot);
     }
+    const float s = __fdiv_rn(__fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), skl[kk]), 8.0f);
+    const bool visible = keepl[kk] != 0 && (a.mask_kind != 2 || j <= q_pos0);
+    const bool live = j < Tk;
+    sc[kk] = live ? (visible ? s : -1e9f) : -INFINITY;
+    svl[kk] = live ? svl[kk] : 0.f;
+    mx = live ? fmaxf(mx, sc[kk]) : mx;
   }
   mx = warp_max_f(mx);
   float sum = 0.f;

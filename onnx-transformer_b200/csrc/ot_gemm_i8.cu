@@ -256,16 +256,21 @@ __device__ __forceinline__ void chunk_values(const GemmArgs& g, const FaultCtx& 
 }
 
 // rint(y / s) with the quotient rounded exactly like IEEE division, without the per-element div.rn expansion (whose
-// special-case path is taken for every zero dividend -- half of a ReLU output).  q1 = y*r corrected by one FMA residual
-// step (r = RN(1/s)) is within 1 ulp of RN(y/s); the integer result can only differ when q1 sits within 2^-16 of a
-// half-integer, and exactly then the true IEEE division decides.  |y/s| <= 127 by construction of s.
-__device__ __forceinline__ int quant_exact(float y, float s, float r) {
+// special-case path is taken for every zero dividend -- half of a ReLU output -- and whose branch serialises the chunk).
+// q1 = y*r corrected by one FMA residual step (r = RN(1/s)) is within 1 ulp of RN(y/s); the integer result can only differ
+// when q1 sits within 2^-16 of a half-integer, and exactly then the true IEEE division decides.  The 16 elements of a chunk
+// are evaluated branch-free; the (rare) exact fallback is taken once per chunk, out of line.  |y/s| <= 127 by construction.
+__device__ __forceinline__ float quant_fast(float y, float s, float r, bool& near_half) {
   const float q0 = __fmul_rn(y, r);
   const float rem = __fmaf_rn(-q0, s, y);
   const float q1 = __fmaf_rn(rem, r, q0);
-  float n = rintf(q1);
-  if (fabsf(fabsf(q1 - n) - 0.5f) < 1.52587890625e-05f) n = rintf(__fdiv_rn(y, s));
-  return __float2int_rn(n);
+  const float n = rintf(q1);
+  near_half = near_half || (fabsf(fabsf(q1 - n) - 0.5f) < 1.52587890625e-05f);
+  return n;
+}
+template <int CW>
+__device__ __noinline__ void quant_exact_array(const float* y, float s, float* n) {
+  for (int j = 0; j < CW; ++j) n[j] = rintf(__fdiv_rn(y[j], s));
 }
 
 // What a pass does with the fp32 values of a chunk.
@@ -287,12 +292,24 @@ __device__ __forceinline__ void consume_chunk(const GemmArgs& g, PassState& st, 
     }
   } else {
     if (row_ok) {
+      float n[kCW];
+      bool near_half = false;
+#pragma unroll
+      for (int j = 0; j < kCW; ++j) n[j] = quant_fast(y[j], st.s, st.s_rcp, near_half);
+      if (near_half) {                       // ~2^-13 of the chunks: redo the chunk with true IEEE division
+        float yy[kCW], nn[kCW];
+#pragma unroll
+        for (int j = 0; j < kCW; ++j) yy[j] = y[j];
+        quant_exact_array<kCW>(yy, st.s, nn);
+#pragma unroll
+        for (int j = 0; j < kCW; ++j) n[j] = nn[j];
+      }
       uint32_t packed[kCW / 4];
 #pragma unroll
       for (int j = 0; j < kCW / 4; ++j) {
         uint32_t w = 0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) w |= (static_cast<uint32_t>(quant_exact(y[4 * j + b], st.s, st.s_rcp)) & 0xFFu) << (8 * b);
+        for (int b = 0; b < 4; ++b) w |= (static_cast<uint32_t>(__float2int_rn(n[4 * j + b])) & 0xFFu) << (8 * b);
         packed[j] = w;
       }
       *reinterpret_cast<uint4*>(reinterpret_cast<int8_t*>(g.out) + static_cast<int64_t>(row) * g.ldo + col) =
@@ -335,7 +352,7 @@ __device__ __forceinline__ void epilogue_pass(const GemmArgs& g, const FaultCtx&
 }
 
 __device__ __forceinline__ void trace_mark(const GemmArgs& g, int slot) {
-  if (g.trace != nullptr && (threadIdx.x == 64)) {
+  if (g.trace != nullptr && (threadIdx.x == 128)) {   // warp 4 = TMEM lane quarter 0: rows 0-31 of the tile, always valid
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
@@ -823,7 +840,10 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
     block_n = best;
     g.cluster_n = 1;
   }
-  if (const char* tr = getenv("OT_GEMM_TRACE")) g.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16));
+  if (const char* tr = getenv("OT_GEMM_TRACE")) {   // profiling aid: phase timestamps of launches with N == OT_GEMM_TRACE_N (all if unset)
+    const char* trn = getenv("OT_GEMM_TRACE_N");
+    if (!trn || atoi(trn) == g.N) g.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16));
+  }
   if (const char* force = getenv("OT_GEMM_FORCE_BN")) {   // tuning / profiling aid only
     const int bn = atoi(force);
     if ((bn == 32 || bn == 64 || bn == 128 || bn == 256) && g.N % bn == 0 &&

@@ -6,16 +6,22 @@
 
 namespace ot {
 
-constexpr int kGenVT = 16;    // vocab rows per CTA
-constexpr int kGenKC = 128;   // K chunk
+constexpr int kGenVT = 32;    // vocab entries per CTA
+constexpr int kGenKC = 64;    // K chunk (one chunk of FMAs ~ one L2 round trip: the register prefetch of the next chunk is hidden)
 constexpr int kGenRows = 64;  // h rows per CTA pass
+constexpr int kGenPH = kGenRows + 4;   // shared pitches (floats): rows of 16-byte aligned float4, conflict-free broadcasts
+constexpr int kGenPW = kGenVT + 4;
 
-// logits[r, v] = bias[v] + sum_k h[r,k] * W[v,k];  CTA: 64 rows x 16 vocab entries, 256 threads, 4 outputs each.
-__global__ void __launch_bounds__(256) generator_logits_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ W,
+// logits[r, v] = bias[v] + sum_k h[r,k] * W[v,k]  (k ascending, fmaf: same order as a plain sequential dot product).
+// CTA: 64 rows x 32 vocab entries, 128 threads, 4x4 register tile per thread; the operand chunks are stored k-major in
+// shared memory so that a thread's 4 rows / 4 vocab entries are one 128-bit load and a warp touches 64 B + 128 B per k
+// (the previous 1x4 tiling was shared-memory-bandwidth bound: 25 us); the next chunk's global loads are prefetched into
+// registers while the current one is multiplied.
+__global__ void __launch_bounds__(128) generator_logits_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ W,
                                                                const float* __restrict__ bias, int rows, int d, int vocab,
                                                                float* __restrict__ logits) {
-  __shared__ float hs[kGenRows][kGenKC + 1];
-  __shared__ float ws[kGenVT][kGenKC + 1];
+  __shared__ __align__(16) float hs[kGenKC][kGenPH];
+  __shared__ __align__(16) float ws[kGenKC][kGenPW];
   const unsigned int tl = tl_begin(7);
   pdl_wait();      // upstream results are complete and visible from here on
   pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
@@ -23,39 +29,70 @@ __global__ void __launch_bounds__(256) generator_logits_kernel(const float* __re
   const int v0 = blockIdx.x * kGenVT;
   const int r0 = blockIdx.y * kGenRows;
   const int tid = threadIdx.x;
-  const int vl = tid & 15;        // vocab entry within tile
-  const int rl = tid >> 4;        // 0..15 -> rows rl, rl+16, rl+32, rl+48
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int tx = tid & 7;         // vocab group: entries 4*tx .. 4*tx+3
+  const int ty = tid >> 3;        // row group:   rows    4*ty .. 4*ty+3
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // global -> register staging: h chunk = 64 rows x 16 float4 (8 per thread), W chunk = 32 rows x 16 float4 (4 per thread)
+  float4 hreg[8], wreg[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 128, r = idx >> 4, c = idx & 15;
+      hreg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < rows && k0 + c * 4 < d) hreg[i] = __ldg(reinterpret_cast<const float4*>(h + static_cast<int64_t>(r0 + r) * ldh + k0) + c);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 128, r = idx >> 4, c = idx & 15;
+      wreg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v0 + r < vocab && k0 + c * 4 < d) wreg[i] = __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(v0 + r) * d + k0) + c);
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 128, r = idx >> 4, c = idx & 15;
+      hs[c * 4][r] = hreg[i].x; hs[c * 4 + 1][r] = hreg[i].y; hs[c * 4 + 2][r] = hreg[i].z; hs[c * 4 + 3][r] = hreg[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 128, r = idx >> 4, c = idx & 15;
+      ws[c * 4][r] = wreg[i].x; ws[c * 4 + 1][r] = wreg[i].y; ws[c * 4 + 2][r] = wreg[i].z; ws[c * 4 + 3][r] = wreg[i].w;
+    }
+  };
+  fetch(0);
   for (int k0 = 0; k0 < d; k0 += kGenKC) {
-    for (int idx = tid; idx < kGenRows * (kGenKC / 4); idx += 256) {
-      const int r = idx / (kGenKC / 4), c = idx % (kGenKC / 4);
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r0 + r < rows && k0 + c * 4 < d) t = __ldg(reinterpret_cast<const float4*>(h + static_cast<int64_t>(r0 + r) * ldh + k0) + c);
-      hs[r][c * 4] = t.x; hs[r][c * 4 + 1] = t.y; hs[r][c * 4 + 2] = t.z; hs[r][c * 4 + 3] = t.w;
-    }
-    for (int idx = tid; idx < kGenVT * (kGenKC / 4); idx += 256) {
-      const int r = idx / (kGenKC / 4), c = idx % (kGenKC / 4);
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (v0 + r < vocab && k0 + c * 4 < d) t = __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(v0 + r) * d + k0) + c);
-      ws[r][c * 4] = t.x; ws[r][c * 4 + 1] = t.y; ws[r][c * 4 + 2] = t.z; ws[r][c * 4 + 3] = t.w;
-    }
+    __syncthreads();            // previous chunk fully consumed
+    stash();
     __syncthreads();
+    if (k0 + kGenKC < d) fetch(k0 + kGenKC);
 #pragma unroll 8
     for (int k = 0; k < kGenKC; ++k) {
-      const float w = ws[vl][k];
-      acc[0] = fmaf(hs[rl][k], w, acc[0]);
-      acc[1] = fmaf(hs[rl + 16][k], w, acc[1]);
-      acc[2] = fmaf(hs[rl + 32][k], w, acc[2]);
-      acc[3] = fmaf(hs[rl + 48][k], w, acc[3]);
-    }
-    __syncthreads();
-  }
-  if (v0 + vl < vocab) {
-    const float bv = bias ? __ldg(bias + v0 + vl) : 0.f;
+      const float4 hv = *reinterpret_cast<const float4*>(&hs[k][ty * 4]);
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[k][tx * 4]);
+      const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+      const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int r = r0 + rl + 16 * t;
-      if (r < rows) logits[static_cast<int64_t>(r) * vocab + v0 + vl] = __fadd_rn(acc[t], bv);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(hh[i], ww[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = v0 + tx * 4 + j;
+    if (v < vocab) {
+      const float bv = bias ? __ldg(bias + v) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty * 4 + i;
+        if (r < rows) logits[static_cast<int64_t>(r) * vocab + v] = __fadd_rn(acc[i][j], bv);
+      }
     }
   }
   tl_mark(tl, 3);
@@ -137,7 +174,7 @@ extern "C" int ot_generator_argmax(const float* h, int64_t ldh, const float* Wg,
   OT_REQUIRE(rows > 0 && d % 4 == 0 && ldh % 4 == 0 && vocab > 1, "bad generator shape");
   cudaStream_t s = as_stream(stream);
   dim3 grid((vocab + kGenVT - 1) / kGenVT, (rows + kGenRows - 1) / kGenRows, 1);
-  OT_CHECK_CUDA(launch_kernel(generator_logits_kernel, grid, dim3(256), 0, s, 1, h, ldh, Wg, bg, rows, d, vocab, scratch_logits));
+  OT_CHECK_CUDA(launch_kernel(generator_logits_kernel, grid, dim3(128), 0, s, 1, h, ldh, Wg, bg, rows, d, vocab, scratch_logits));
   OT_CHECK_CUDA(launch_kernel(generator_reduce_kernel, dim3(rows), dim3(256), 0, s, 1, scratch_logits, vocab, next_ids, logp, margin));
   count_launch(2);
   return OT_OK;

@@ -10,6 +10,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from onnx_transformer_b200 import _lib, weights as W  # noqa: E402
 from onnx_transformer_b200.engine import QuantizedTransformer  # noqa: E402
 
+trace_n = None
+for a in sys.argv:
+    if a.startswith("--trace-n="):
+        trace_n = int(a.split("=")[1])
+tbuf = torch.zeros(4096 * 8, dtype=torch.int64, device="cuda")
+if trace_n is not None:      # per-CTA phase stamps of the GEMMs with N == trace_n (the last such launch of the step wins)
+    os.environ["OT_GEMM_TRACE"] = hex(tbuf.data_ptr())
+    os.environ["OT_GEMM_TRACE_N"] = str(trace_n)
 pdl = "--no-pdl" not in sys.argv
 fused = "--fused-ln" in sys.argv
 eng = QuantizedTransformer(W.init_float_weights(0), pdl=pdl, fused_ln=fused)
@@ -51,3 +59,11 @@ for r in rec:
 print("family      n   body_us  idle_before_us")
 for k, (c, b, g) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print("%-10s %3d %9.1f %9.1f" % (k, c, b, g))
+
+if trace_n is not None:
+    tt = tbuf.cpu().numpy().reshape(-1, 8)
+    tt = tt[tt[:, 0] > 0]
+    t0 = tt[:, 0].min()
+    print("GEMM N=%d phase stamps per CTA (us): setup ln_done acc_ready pass1 clsync end" % trace_n)
+    for i, r in enumerate(tt[:20]):
+        print(i, " ".join("%7.2f" % ((v - t0) / 1e3) if v > 0 else "      -" for v in r[:6]))
