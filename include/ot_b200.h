@@ -191,6 +191,25 @@ int ot_generator_argmax(const float* h, int64_t ldh, const float* Wg, const floa
  * ys[b, *step + 1] = next_ids[b]; (*step)++ -- device-side so that one CUDA graph replays every step. */
 int ot_append_token(int64_t* ys, int64_t ld_ys, const int64_t* next_ids, int B, int32_t* step_dev, void* stream);
 
+/* ---- persistent greedy decoder: the fault-free greedy loop of parallelized_inject_onnx_transformer.py:616-758
+ * (batched as batch_output.py:659-672) as ONE kernel launch for any number of steps.  One CTA per SM stays resident;
+ * the ~70 dependent ops of a step are phases separated by a grid-wide barrier (see csrc/ot_decoder.cu).  The plan is an
+ * opaque device-resident block (ot_decoder_plan_size bytes, 256-byte aligned) holding the TMA descriptors and every
+ * pointer of the decoder; it is built once per (model, workspace) by ot_decoder_plan_build:
+ *   layer_ptrs: n_layers x 28 device pointers, per layer
+ *       ln1_g ln1_b ln2_g ln2_b ln3_g ln3_b | qkv_w qkv_sw qkv_b | o_w o_sw o_b | cq_w cq_sw cq_b | co_w co_sw co_b |
+ *       w1_w w1_sw w1_b | w2_w w2_sw w2_b | kc vc skc svc          (int8 weights [N,K], fp32 scales/biases, KV cache)
+ *   ws_ptrs: 24 device pointers
+ *       x xq sx acc cq cs hq sh rowmax ckv sckv mask fin_g fin_b hout gen_w gen_b gen_pv gen_pi tgt_lut pe ys bar trace
+ *       (acc: int32 [4*64*2048]; rowmax: u32 [n_layers*64]; gen_pv/gen_pi: [ceil(vocab/32)*64]; trace: u64 [128] or NULL)
+ * B <= 64 sentences, S <= 96 source tokens, cap <= 96 cache positions.  ot_decoder_run executes greedy steps
+ * t0 .. t0+n_steps-1: reads ys[:, t0], writes ys[:, t0+1 .. t0+n_steps] and KV-cache positions t0 .. t0+n_steps-1.
+ * Results are bit-identical to stepping with the per-op entry points above. */
+int ot_decoder_plan_size(void);
+int ot_decoder_plan_build(void* plan_dev, int n_layers, int B, int S, int cap, int vocab, int64_t ys_ld,
+                          const void* const* layer_ptrs, const void* const* ws_ptrs);
+int ot_decoder_run(const void* plan_dev, unsigned int* bar_dev, int t0, int n_steps, void* stream);
+
 /* ---- elementwise / shape op family: one CUDA handler per remaining ONNX op name of SURVEY.md 8a -----
  * Unary  (op: 0 Abs 1 Relu 2 Sqrt 3 Round 4 Neg 5 Exp 6 Identity), fp32, n elements. */
 int ot_unary_f32(int op, const float* x, float* y, int64_t n, void* stream);

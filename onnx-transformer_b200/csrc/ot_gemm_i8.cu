@@ -749,7 +749,7 @@ struct MapKeyHash {
 };
 
 // 2-D byte tensor [rows, cols] with row pitch ld; box = [box_rows, box_cols]; cached per (ptr, shape).
-static int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                           uint32_t box_cols, bool swizzle128) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;

@@ -3,31 +3,12 @@
 // fp32 op order follows SURVEY.md App. A (the order of the ops the reference exports); compiled with
 // -fmad=false, explicit *_rn intrinsics where the order matters for bit-exact integer results.
 #include "ot_common.h"
+#include "ot_rowmath.cuh"
 
 namespace ot {
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
-// RowQuant of quant_linear.py:31-43: s = max(amax, 1e-5) / 127 ; q = rint(x / s).
-__device__ __forceinline__ float quant_scale(float amax) { return __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f); }
-__device__ __forceinline__ int quant_one(float x, float s) { return __float2int_rn(rintf(__fdiv_rn(x, s))); }
-__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
-  return (static_cast<uint32_t>(a) & 0xFFu) | ((static_cast<uint32_t>(b) & 0xFFu) << 8) |
-         ((static_cast<uint32_t>(c) & 0xFFu) << 16) | ((static_cast<uint32_t>(d) & 0xFFu) << 24);
-}
-
 // ------------------------------------------------------------------------------------------------
-// LayerNorm (layer_norm.py:12-15 as exported): mu = mean(x); d = x-mu; v = mean(d*d)*n/(n-1);
-// y = (a*d)/(sqrt(v)+eps) + b ; optional RowQuant of y.   VEC = n / 128 float4 per lane.
+// LayerNorm (+ optional RowQuant of y); the row math lives in ot_rowmath.cuh.   VEC = n / 128 float4 per lane.
 template <int VEC>
 __global__ void __launch_bounds__(256) layernorm_quant_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int64_t rows, int n, float eps,
@@ -42,39 +23,9 @@ __global__ void __launch_bounds__(256) layernorm_quant_kernel(const float* __res
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + row * n);
   float4 v[VEC];
-  float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    v[i] = __ldg(xr + i * 32 + lane);
-    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float nf = static_cast<float>(n);
-  const float mu = __fdiv_rn(warp_sum(sum), nf);
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    v[i].x = __fsub_rn(v[i].x, mu);
-    v[i].y = __fsub_rn(v[i].y, mu);
-    v[i].z = __fsub_rn(v[i].z, mu);
-    v[i].w = __fsub_rn(v[i].w, mu);
-    sq += (__fmul_rn(v[i].x, v[i].x) + __fmul_rn(v[i].y, v[i].y)) + (__fmul_rn(v[i].z, v[i].z) + __fmul_rn(v[i].w, v[i].w));
-  }
-  float var = __fdiv_rn(warp_sum(sq), nf);                    // ReduceMean(d*d)
-  var = __fdiv_rn(__fmul_rn(var, nf), nf - 1.0f);            // * N / (N-1)
-  const float denom = __fadd_rn(__fsqrt_rn(var), eps);       // sqrt + eps (eps added to std)
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
-  float amax = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const float4 g = __ldg(g4 + i * 32 + lane);
-    const float4 b = __ldg(b4 + i * 32 + lane);
-    v[i].x = __fadd_rn(__fdiv_rn(__fmul_rn(g.x, v[i].x), denom), b.x);
-    v[i].y = __fadd_rn(__fdiv_rn(__fmul_rn(g.y, v[i].y), denom), b.y);
-    v[i].z = __fadd_rn(__fdiv_rn(__fmul_rn(g.z, v[i].z), denom), b.z);
-    v[i].w = __fadd_rn(__fdiv_rn(__fmul_rn(g.w, v[i].w), denom), b.w);
-    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-  }
+  for (int i = 0; i < VEC; ++i) v[i] = __ldg(xr + i * 32 + lane);
+  const float amax = layernorm_row<VEC>(v, lane, n, gamma, beta, eps);
   if (y_out) {
     float4* yr = reinterpret_cast<float4*>(y_out + row * n);
 #pragma unroll

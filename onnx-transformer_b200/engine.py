@@ -110,7 +110,7 @@ class QuantizedTransformer:
     smoothed if SmoothQuant is wanted: get_quantized_model.smooth_lm is an offline weight transform)."""
 
     def __init__(self, float_weights: Dict[str, np.ndarray], n_layers: int = 6, device: Optional[torch.device] = None, max_len: int = W.MAX_LEN,
-                 pdl: bool = True, fused_ln: bool = False, weight_bits: int = 8):
+                 pdl: bool = True, fused_ln: bool = False, weight_bits: int = 8, persistent: bool = True):
         if not torch.cuda.is_available():
             raise K.OtError("QuantizedTransformer needs a CUDA device: this package has no CPU fallback")
         K._lib.load().ot_set_pdl(1 if pdl else 0)   # programmatic dependent launch for every kernel of the library
@@ -161,6 +161,10 @@ class QuantizedTransformer:
         self._dec_ws: Dict[tuple, dict] = {}
         self.fused_ln = fused_ln  # decode: LayerNorm+RowQuant as the prologue of the following GEMM (M <= 128)
         self.graph_replays = 0   # CUDA-graph replays of the greedy step (each replays ws['graph_launches'] kernels)
+        # fault-free greedy steps run inside ONE persistent kernel (csrc/ot_decoder.cu) when the shapes allow it
+        # (B <= 64, S <= 96, int8 weights); otherwise, and for the step a fault is injected in, the per-op kernels are used
+        self.persistent = persistent
+        self.persistent_steps = 0
         torch.cuda.synchronize(self.dev)
 
     # ------------------------------------------------------------------------------------------ fault plumbing
@@ -301,6 +305,31 @@ class QuantizedTransformer:
             self._dec_ws = {key: ws}
         return ws
 
+    def _decoder_plan(self, ws: dict, B: int, S: int, trace: bool = False):
+        """The persistent decoder's plan for this workspace (built once), or None when the shapes / weights rule it out."""
+        if not self.persistent or self.weight_bits != 8 or B > 64 or S > 96 or self.max_len > 96 or self.n_layers > 8:
+            return None
+        plan = ws.get("plan")
+        if plan is None or (trace and plan.trace is None):
+            e = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=self.dev)  # noqa: E731
+            layers = []
+            for l, L in enumerate(self.dec):
+                row = [L["ln1"][0], L["ln1"][1], L["ln2"][0], L["ln2"][1], L["ln3"][0], L["ln3"][1]]
+                for name in ("qkv", "o", "cq", "co", "w1", "w2"):
+                    row += [L[name].wq, L[name].sw, L[name].bias]
+                row += [ws["kc"][l], ws["vc"][l], ws["skc"][l], ws["svc"][l]]
+                layers.append(row)
+            n_tiles = (self.vocab + 31) // 32
+            extra = dict(acc=torch.zeros(4 * 64 * FF, dtype=torch.int32, device=self.dev),
+                         rowmax=torch.zeros(self.n_layers * 64, dtype=torch.int32, device=self.dev),
+                         gen_pv=e(n_tiles * 64), gen_pi=torch.zeros(n_tiles * 64, dtype=torch.int32, device=self.dev))
+            wst = [ws["x"][0], ws["xq"], ws["sx"], extra["acc"], ws["cq"], ws["cs"], ws["hq"], ws["sh"], extra["rowmax"], ws["ckv"], ws["sckv"],
+                   ws["mask"], self.dec_norm[0], self.dec_norm[1], ws["hout"], self.gen_w, self.gen_b, extra["gen_pv"], extra["gen_pi"],
+                   self.tgt_lut, self.pe]
+            plan = K.DecoderPlan(layers, wst, n_layers=self.n_layers, B=B, S=S, cap=self.max_len, vocab=self.vocab, ys=ws["ys"], trace=trace)
+            ws["plan"] = plan
+        return plan
+
     def _prepare_cross_kv(self, ws: dict, memory: torch.Tensor, fault: Optional[FaultSpec]):
         """Round_60 + MatMul_0..11 + Round_61..72: once per sentence batch (the reference recomputes them every step)."""
         K.rowquant(memory.reshape(-1, D), q=ws["mq"], s=ws["sm"])
@@ -411,6 +440,19 @@ class QuantizedTransformer:
         assert len(steps) <= 1, "all Decoder-target faults of a batch must share one injection step"
         fault_step = steps.pop() if steps else -1
         want_m = return_margins
+        plan = self._decoder_plan(ws, B, S) if (use_graph and not want_m) else None
+        if plan is not None:
+            # fault-free steps inside the persistent kernel; the injected step (if any) through the per-op kernels
+            n = max_len - 1
+            if 0 <= fault_step < n:
+                plan.run(0, fault_step)
+                ws["step"].fill_(fault_step)
+                self._decode_step(ws, B, S, fault=fault)
+                plan.run(fault_step + 1, n - fault_step - 1)
+            else:
+                plan.run(0, n)
+            self.persistent_steps += n
+            return ws["ys"][:, :max_len].clone()
         if use_graph and ws["graph"] is None and not want_m:
             # warm-up (sets function attributes, fills the TMA descriptor cache), then capture one step
             self._decode_step(ws, B, S)

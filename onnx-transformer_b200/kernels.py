@@ -257,6 +257,36 @@ def append_token(ys: torch.Tensor, next_ids: torch.Tensor, step_dev: torch.Tenso
     _lib.check(rc, "ot_append_token")
 
 
+# ------------------------------------------------------------------------------------------------ persistent decoder
+class DecoderPlan:
+    """Device-resident plan of the persistent greedy decoder (ot_decoder_plan_build).  Keeps every tensor it points to alive."""
+
+    def __init__(self, layers, ws_tensors, *, n_layers: int, B: int, S: int, cap: int, vocab: int, ys: torch.Tensor, trace: bool = False):
+        lib = _lib.load()
+        dev = ys.device
+        self.keep = (layers, ws_tensors)
+        self.buf = torch.zeros(lib.ot_decoder_plan_size() + 256, dtype=torch.uint8, device=dev)
+        self.bar = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.trace = torch.zeros(128, dtype=torch.int64, device=dev) if trace else None
+        flat_l = [t for layer in layers for t in layer]
+        assert len(flat_l) == 28 * n_layers
+        ws_all = list(ws_tensors) + [ys, self.bar, self.trace]
+        assert len(ws_all) == 24
+        for t in flat_l + ws_all[:-1]:
+            if t is not None and not t.is_contiguous() and t.dim() > 1 and t.stride(-1) != 1:
+                raise OtError("decoder plan tensors must be row-major")
+        lp = (C.c_void_p * len(flat_l))(*[t.data_ptr() for t in flat_l])
+        wp = (C.c_void_p * 24)(*[(t.data_ptr() if t is not None else None) for t in ws_all])
+        base = (self.buf.data_ptr() + 255) & ~255
+        self.ptr = C.c_void_p(base)
+        rc = lib.ot_decoder_plan_build(self.ptr, n_layers, B, S, cap, vocab, ys.stride(0), lp, wp)
+        _lib.check(rc, "ot_decoder_plan_build")
+
+    def run(self, t0: int, n_steps: int):
+        rc = _lib.load().ot_decoder_run(self.ptr, _ptr(self.bar), int(t0), int(n_steps), _stream())
+        _lib.check(rc, "ot_decoder_run")
+
+
 # ------------------------------------------------------------------------------------------------ elementwise family
 def _shape4(shape):
     shape = tuple(int(x) for x in shape)

@@ -1,0 +1,64 @@
+"""Persistent decoder: decode time (persistent vs per-op graph path) and the per-phase timeline of one greedy step
+(%globaltimer of CTA 0 after every grid barrier)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from onnx_transformer_b200 import weights as W  # noqa: E402
+from onnx_transformer_b200.engine import QuantizedTransformer  # noqa: E402
+
+B, S = 64, 64
+fw = W.init_float_weights(0)
+ids, mask = W.synthetic_tokens(1000, B, S)
+ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+
+
+def timeit(eng, reps=5):
+    for _ in range(2):
+        ys = eng.greedy_decode(ids, mask)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ys = eng.greedy_decode(ids, mask)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, ys
+
+
+ep = QuantizedTransformer(fw, persistent=True)
+ms_p, ys_p = timeit(ep)
+print("persistent: %.2f ms/decode  %.0f tok/s" % (ms_p, B * 71 / ms_p * 1e3), flush=True)
+if "--no-graph" not in sys.argv:
+    eg = QuantizedTransformer(fw, persistent=False)
+    ms_g, ys_g = timeit(eg)
+    print("per-op graph: %.2f ms/decode  %.0f tok/s   identical=%s" % (ms_g, B * 71 / ms_g * 1e3, bool(torch.equal(ys_p, ys_g))), flush=True)
+
+ws = ep._dec_workspace(B, S)
+plan = ep._decoder_plan(ws, B, S, trace=True)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+plan.run(35, 1)
+torch.cuda.synchronize()
+e0.record()
+plan.run(30, 10)
+e1.record()
+torch.cuda.synchronize()
+print("10 steps in one launch: %.1f us/step" % (e0.elapsed_time(e1) * 100))
+t = plan.trace.cpu().numpy()
+names = []
+for l in range(6):
+    names += ["ln1", "qkv", "sattn", "o", "ln2", "cq", "cattn", "co", "ln3", "ffn1a", "ffn1b", "ffn2"]
+names += ["lnf", "gen", "red"]
+prev = t[127]
+tot = {}
+for i, n in enumerate(names):
+    d = (t[i] - prev) / 1e3
+    prev = t[i]
+    tot.setdefault(n, []).append(d)
+print("phase   mean_us  (per layer / step)   sum_us")
+for n, v in tot.items():
+    print("%-6s %7.2f   x%d   %7.1f   %s" % (n, np.mean(v), len(v), np.sum(v), " ".join("%.2f" % x for x in v)))
+print("step total %.1f us" % ((t[len(names) - 1] - t[127]) / 1e3))
