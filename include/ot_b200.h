@@ -200,8 +200,9 @@ int ot_append_token(int64_t* ys, int64_t ld_ys, const int64_t* next_ids, int B, 
  *       ln1_g ln1_b ln2_g ln2_b ln3_g ln3_b | qkv_w qkv_sw qkv_b | o_w o_sw o_b | cq_w cq_sw cq_b | co_w co_sw co_b |
  *       w1_w w1_sw w1_b | w2_w w2_sw w2_b | kc vc skc svc          (int8 weights [N,K], fp32 scales/biases, KV cache)
  *   ws_ptrs: 24 device pointers
- *       x xq sx acc cq cs hq sh rowmax ckv sckv mask fin_g fin_b hout gen_w gen_b gen_pv gen_pi tgt_lut pe ys bar trace
- *       (acc: int32 [4*64*2048]; rowmax: u32 [n_layers*64]; gen_pv/gen_pi: [ceil(vocab/32)*64]; trace: u64 [128] or NULL)
+ *       x xq sx acc cq cs hq sh rowmax ckv sckv mask fin_g fin_b houtT gen_wt gen_b gen_pv gen_pi tgt_lut pe ys bar trace
+ *       (acc: int32 [4*64*2048]; rowmax: u32 [n_layers*64]; houtT: fp32 [512*64]; gen_wt: the generator weight re-laid out
+ *        as [ceil(vocab/32)][512][32]; gen_pv/gen_pi: [ceil(vocab/32)*64]; trace: u64 [256] or NULL)
  * B <= 64 sentences, S <= 96 source tokens, cap <= 96 cache positions.  ot_decoder_run executes greedy steps
  * t0 .. t0+n_steps-1: reads ys[:, t0], writes ys[:, t0+1 .. t0+n_steps] and KV-cache positions t0 .. t0+n_steps-1.
  * Results are bit-identical to stepping with the per-op entry points above. */

@@ -52,8 +52,8 @@ __device__ __forceinline__ float layernorm_row(float4 (&v)[VEC], int lane, int n
   float amax = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const float4 g = __ldg(g4 + i * 32 + lane);
-    const float4 b = __ldg(b4 + i * 32 + lane);
+    const float4 g = g4[i * 32 + lane];   // plain loads: gamma/beta may be staged in shared memory
+    const float4 b = b4[i * 32 + lane];
     v[i].x = __fadd_rn(__fdiv_rn(__fmul_rn(g.x, v[i].x), denom), b.x);
     v[i].y = __fadd_rn(__fdiv_rn(__fmul_rn(g.y, v[i].y), denom), b.y);
     v[i].z = __fadd_rn(__fdiv_rn(__fmul_rn(g.z, v[i].z), denom), b.z);

@@ -320,11 +320,18 @@ class QuantizedTransformer:
                 row += [ws["kc"][l], ws["vc"][l], ws["skc"][l], ws["svc"][l]]
                 layers.append(row)
             n_tiles = (self.vocab + 31) // 32
-            extra = dict(acc=torch.zeros(4 * 64 * FF, dtype=torch.int32, device=self.dev),
+            if n_tiles > 148:
+                return None
+            if getattr(self, "_gen_wt", None) is None:
+                # generator weight re-laid out once, tile-major / k-major: [tile][k][32 vocab entries] (zero rows past the vocabulary)
+                wpad = torch.zeros((n_tiles * 32, D), dtype=torch.float32, device=self.dev)
+                wpad[: self.vocab] = self.gen_w
+                self._gen_wt = wpad.reshape(n_tiles, 32, D).permute(0, 2, 1).contiguous()
+            extra = dict(acc=torch.zeros(4 * 64 * FF, dtype=torch.int32, device=self.dev), houtT=torch.zeros(D * 64, dtype=torch.float32, device=self.dev),
                          rowmax=torch.zeros(self.n_layers * 64, dtype=torch.int32, device=self.dev),
                          gen_pv=e(n_tiles * 64), gen_pi=torch.zeros(n_tiles * 64, dtype=torch.int32, device=self.dev))
             wst = [ws["x"][0], ws["xq"], ws["sx"], extra["acc"], ws["cq"], ws["cs"], ws["hq"], ws["sh"], extra["rowmax"], ws["ckv"], ws["sckv"],
-                   ws["mask"], self.dec_norm[0], self.dec_norm[1], ws["hout"], self.gen_w, self.gen_b, extra["gen_pv"], extra["gen_pi"],
+                   ws["mask"], self.dec_norm[0], self.dec_norm[1], extra["houtT"], self._gen_wt, self.gen_b, extra["gen_pv"], extra["gen_pi"],
                    self.tgt_lut, self.pe]
             plan = K.DecoderPlan(layers, wst, n_layers=self.n_layers, B=B, S=S, cap=self.max_len, vocab=self.vocab, ys=ws["ys"], trace=trace)
             ws["plan"] = plan

@@ -267,7 +267,7 @@ class DecoderPlan:
         self.keep = (layers, ws_tensors)
         self.buf = torch.zeros(lib.ot_decoder_plan_size() + 256, dtype=torch.uint8, device=dev)
         self.bar = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.trace = torch.zeros(128, dtype=torch.int64, device=dev) if trace else None
+        self.trace = torch.zeros(256, dtype=torch.int64, device=dev) if trace else None
         flat_l = [t for layer in layers for t in layer]
         assert len(flat_l) == 28 * n_layers
         ws_all = list(ws_tensors) + [ys, self.bar, self.trace]

@@ -51,14 +51,14 @@ t = plan.trace.cpu().numpy()
 names = []
 for l in range(6):
     names += ["ln1", "qkv", "sattn", "o", "ln2", "cq", "cattn", "co", "ln3", "ffn1a", "ffn1b", "ffn2"]
-names += ["lnf", "gen", "red"]
-prev = t[127]
-tot = {}
+names += ["lnf", "gen"]
+prev = t[255]
+work, wait = {}, {}
 for i, n in enumerate(names):
-    d = (t[i] - prev) / 1e3
-    prev = t[i]
-    tot.setdefault(n, []).append(d)
-print("phase   mean_us  (per layer / step)   sum_us")
-for n, v in tot.items():
-    print("%-6s %7.2f   x%d   %7.1f   %s" % (n, np.mean(v), len(v), np.sum(v), " ".join("%.2f" % x for x in v)))
-print("step total %.1f us" % ((t[len(names) - 1] - t[127]) / 1e3))
+    work.setdefault(n, []).append((t[2 * i] - prev) / 1e3)          # CTA 0: phase start -> its arrival at the barrier
+    wait.setdefault(n, []).append((t[2 * i + 1] - t[2 * i]) / 1e3)  # CTA 0: arrival -> release
+    prev = t[2 * i + 1]
+print("phase   n   work_us(CTA0)  barrier_wait_us   sum_us")
+for n in work:
+    print("%-6s x%d   %7.2f   %7.2f   %7.1f" % (n, len(work[n]), np.mean(work[n]), np.mean(wait[n]), np.sum(work[n]) + np.sum(wait[n])))
+print("step total %.1f us" % ((t[2 * len(names) - 1] - t[255]) / 1e3))
