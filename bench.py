@@ -171,7 +171,7 @@ def decode_family_timeline(eng, ws, B, S, reps=8, step=35):
 
 
 def decode_family_bytes(eng, B, S, T=36):
-    """Algorithmic bytes per launch of each family for one greedy step (DESIGN.md section 4 / SURVEY.md 8d)."""
+    """Algorithmic bytes per launch of each family for one greedy step of the per-op path (DESIGN.md section 4 / SURVEY.md 8d)."""
     D, FF, nl, V = 512, 2048, eng.n_layers, eng.vocab
     w_bytes = 3 * D * D + 3 * D * D + 2 * D * FF                       # int8 weights of the 6 GEMMs of a decoder layer: 3,670,016 B
     io = B * (D + 3 * D + 12) + 3 * B * (D + 4 + 2 * D * 4) + B * (D + D + 4) + B * (D + FF + 4) + B * (FF + 4 + 2 * D * 4)
@@ -181,6 +181,45 @@ def decode_family_bytes(eng, B, S, T=36):
     ln = B * (D * 4 + D + 4) + 2 * D * 4
     gen = (V * D * 4 + B * D * 4 + 3 * B * V * 4) / 2.0
     return {"gemm_i8": gemm, "attention_q8": attn, "layernorm_quant": ln, "generator": gen}
+
+
+def persistent_decoder_bytes(eng, B, S, n_steps):
+    """Algorithmic bytes of ONE launch of decoder_steps_kernel (all `n_steps` greedy steps): only what any decoder must move per
+    step -- every weight once (int8 GEMM weights + fp32 scales/biases/LayerNorm, fp32 generator), the self-attention KV cache
+    prefix read + one appended row, the cached cross-attention K/V + scales + mask, the embedding rows and the token ids.  The
+    int32 accumulator planes / activations exchanged between phases through L2 are NOT counted."""
+    D, FF, nl, V = 512, 2048, eng.n_layers, eng.vocab
+    w_int8 = nl * (3 * D * D + 3 * D * D + 2 * D * FF)               # 6 x 3,670,016 B
+    w_par = nl * (8 * (3 * D + 3 * D + FF + D) + 6 * D * 4)          # per-column scale + bias, LayerNorm gamma/beta
+    gen = V * D * 4 + V * 4 + 2 * D * 4                              # generator weight + bias, final norm
+    cross = nl * B * S * (2 * D + 8) + B * S
+    per_step_const = w_int8 + w_par + gen + cross + B * (D * 4 + 8) + D * 4
+    total = 0
+    for t in range(n_steps):
+        total += per_step_const + nl * B * (t * (2 * D + 8) + (2 * D + 8))
+    return total, {"int8_weights": w_int8, "scales_bias_ln": w_par, "generator_fp32": gen, "cross_kv": cross,
+                   "self_kv_read_mean": nl * B * ((n_steps - 1) / 2.0) * (2 * D + 8)}
+
+
+PHASES = ["ln1", "qkv", "self_attn", "o", "ln2", "cq", "cross_attn", "co", "ln3", "ffn1_mma", "ffn1_quant", "ffn2"]
+
+
+def persistent_phase_trace(eng, ws, B, S, t_mid=35):
+    """Per-phase timeline of one greedy step inside the persistent kernel: CTA 0 stamps %globaltimer on entering / leaving
+    every grid barrier (ot_decoder.cu grid_sync).  Returns {phase: us per greedy step (work + barrier wait)} and the step total."""
+    plan = eng._decoder_plan(ws, B, S, trace=True)
+    plan.run(t_mid, 2)
+    import torch
+    torch.cuda.synchronize()
+    t = plan.trace.cpu().numpy()
+    names = PHASES * eng.n_layers + ["final_norm", "generator"]
+    out, prev = {}, t[255]
+    for i, n in enumerate(names):
+        out[n] = out.get(n, 0.0) + (t[2 * i + 1] - prev) / 1e3
+        prev = t[2 * i + 1]
+    total = (t[2 * len(names) - 1] - t[255]) / 1e3
+    ws.pop("plan", None)      # drop the tracing plan: the next decode rebuilds the plain one
+    return {k: round(float(v), 2) for k, v in out.items()}, float(total)
 
 
 def extra_measurements(eng, dev):
@@ -301,6 +340,8 @@ def main():
         one_step()
     sync_all()
     ws = eng._dec_workspace(B, S)
+    persistent = ws.get("plan") is not None
+    eng.decoder_events = [] if persistent else None     # CUDA events around every decoder_steps_kernel launch of the timed region
     launches_per_graph = ws.get("graph_launches", 0)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -310,6 +351,7 @@ def main():
     sync_all()
     launches = (K._lib.launch_count() - l0) + (eng.graph_replays - r0) * launches_per_graph
     clocks = sampler.stop()
+    dec_events, eng.decoder_events = eng.decoder_events, None
     e2e_ms = timed_loop(one_step_e2e, args.steps)
     sync_all()
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -321,22 +363,44 @@ def main():
     e2e_value = tokens / (e2e_ms * 1e-3)
 
     if rank == 0:
-        fam, step_us = decode_family_timeline(eng, ws, B, S)
-        nbytes = decode_family_bytes(eng, B, S)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        share = {k: round(v["us_per_step"], 1) for k, v in fam.items()}
-        dom = max((k for k in share if k in nbytes), key=lambda k: share[k])
-        achieved = nbytes[dom] / (fam[dom]["us_per_launch"] * 1e-6) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                    "us_per_launch": fam[dom]["us_per_launch"], "launches_per_step": fam[dom]["launches_per_step"],
-                    "algorithmic_bytes_per_launch": nbytes[dom], "greedy_step_us": step_us, "families_us_per_greedy_step": share,
-                    "note": "M=64 decode GEMMs are latency-bound (weights L2-resident); see DESIGN.md 4/7"}
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"
+        n_dec = MAX_LEN - 1
+        if persistent:
+            # dominant kernel: decoder_steps_kernel, ONE launch per batch decode (all 71 greedy steps); its duration is the mean of
+            # the CUDA-event pairs recorded around each launch INSIDE the timed region, on the launching stream
+            kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in dec_events]))
+            nbytes, parts = persistent_decoder_bytes(eng, B, S, n_dec)
+            achieved = nbytes / (kernel_ms * 1e-3) / 1e9
+            phases, step_us = persistent_phase_trace(eng, ws, B, S)
+            traffic = None
+            try:     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "decoder_traffic.json")))["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            roofline = {"kernel": "decoder_steps_kernel (persistent greedy decoder, %d steps per launch)" % n_dec, "bound": "hbm",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "us_per_launch": kernel_ms * 1e3, "launches_per_step": 1, "algorithmic_bytes_per_launch": nbytes,
+                        "algorithmic_bytes_per_greedy_step": parts, "share_of_step": kernel_ms / (total_ms / args.steps),
+                        "greedy_step_us": kernel_ms * 1e3 / n_dec, "traced_greedy_step_us": step_us, "phase_us_per_greedy_step": phases,
+                        "note": "working set (weights 31 MB + K/V caches 54 MB) is L2-resident; a greedy step at batch 64 is a chain of "
+                                "~74 dependent phases, each bound by grid-barrier + L2 round-trip latency, not by bandwidth (DESIGN.md 4/7)"}
+        else:
+            fam, step_us = decode_family_timeline(eng, ws, B, S)
+            nbytes = decode_family_bytes(eng, B, S)
+            share = {k: round(v["us_per_step"], 1) for k, v in fam.items()}
+            dom = max((k for k in share if k in nbytes), key=lambda k: share[k])
+            achieved = nbytes[dom] / (fam[dom]["us_per_launch"] * 1e-6) / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "peak_source": peak_src,
+                        "us_per_launch": fam[dom]["us_per_launch"], "launches_per_step": fam[dom]["launches_per_step"],
+                        "algorithmic_bytes_per_launch": nbytes[dom], "greedy_step_us": step_us, "families_us_per_greedy_step": share,
+                        "note": "M=64 decode GEMMs are latency-bound (weights L2-resident); see DESIGN.md 4/7"}
         extra = {}
         if not args.no_extra:
             extra = extra_measurements(eng, dev)

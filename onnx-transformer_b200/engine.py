@@ -165,6 +165,9 @@ class QuantizedTransformer:
         # (B <= 64, S <= 96, int8 weights); otherwise, and for the step a fault is injected in, the per-op kernels are used
         self.persistent = persistent
         self.persistent_steps = 0
+        # measurement hook (bench.py): when a list, greedy_decode appends a (start, end) CUDA-event pair around every
+        # persistent-decoder launch, recorded on the launching stream
+        self.decoder_events = None
         torch.cuda.synchronize(self.dev)
 
     # ------------------------------------------------------------------------------------------ fault plumbing
@@ -456,6 +459,12 @@ class QuantizedTransformer:
                 ws["step"].fill_(fault_step)
                 self._decode_step(ws, B, S, fault=fault)
                 plan.run(fault_step + 1, n - fault_step - 1)
+            elif self.decoder_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                plan.run(0, n)
+                e1.record()
+                self.decoder_events.append((e0, e1))
             else:
                 plan.run(0, n)
             self.persistent_steps += n
