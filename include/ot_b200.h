@@ -211,6 +211,21 @@ int ot_decoder_plan_build(void* plan_dev, int n_layers, int B, int S, int cap, i
                           const void* const* layer_ptrs, const void* const* ws_ptrs);
 int ot_decoder_run(const void* plan_dev, unsigned int* bar_dev, int t0, int n_steps, void* stream);
 
+/* ---- cluster-resident greedy decoder (csrc/ot_cdecoder.cu): the same fault-free greedy loop, same results bit for bit, but
+ * the batch is cut into groups of `spc` <= 8 sentences and every group is decoded by ONE thread-block cluster of 8 CTAs that
+ * exchanges rows <-> column slices through distributed shared memory (st.shared::cluster + barrier.cluster) instead of L2 +
+ * grid barriers.  Clusters are independent: any B, no co-residency requirement.  The plan is an opaque device-resident block
+ * (ot_cdecoder_plan_size bytes, 256-byte aligned):
+ *   layer_ptrs: n_layers x 28 device pointers, per layer, in the order of ot_decoder_plan_build
+ *   ws_ptrs: 12 device pointers: ckv sckv mask fin_g fin_b gen_w4 gen_b tgt_lut pe ys trace(u64[256] or NULL) reserved(NULL)
+ *       (gen_w4: the generator weight re-laid out as [ceil(vocab/32)][128][32][4] = tile / k-quad / entry / k, zero padded)
+ * S <= 96 source tokens, cap <= 96 cache positions, vocab <= 6144.  ot_cdecoder_run executes greedy steps t0 .. t0+n_steps-1:
+ * reads ys[:, t0], writes ys[:, t0+1 .. t0+n_steps] and the self-attention KV-cache positions t0 .. t0+n_steps-1. */
+int ot_cdecoder_plan_size(void);
+int ot_cdecoder_plan_build(void* plan_dev, int n_layers, int B, int S, int cap, int vocab, int spc, int64_t ys_ld,
+                           const void* const* layer_ptrs, const void* const* ws_ptrs);
+int ot_cdecoder_run(const void* plan_dev, int B, int spc, int t0, int n_steps, void* stream);
+
 /* ---- elementwise / shape op family: one CUDA handler per remaining ONNX op name of SURVEY.md 8a -----
  * Unary  (op: 0 Abs 1 Relu 2 Sqrt 3 Round 4 Neg 5 Exp 6 Identity), fp32, n elements. */
 int ot_unary_f32(int op, const float* x, float* y, int64_t n, void* stream);

@@ -1,0 +1,902 @@
+// ot_cdecoder_run: the KV-cached greedy decoder as a CLUSTER-RESIDENT persistent kernel (fault-free fast path of
+// greedy_decode, parallelized_inject_onnx_transformer.py:616-758 / batch_output.py:659-672).
+//
+// A greedy step at batch 64 is a chain of ~74 dependent operations of a few hundred KB each.  It is bound by the latency of
+// the all-to-all exchange between "column owners" (GEMM tiles need every sentence row) and "row owners" (LayerNorm, RowQuant,
+// softmax need every feature of a sentence), not by bandwidth or by the tensor cores.  ot_decoder.cu does that exchange through
+// L2 with a grid-wide barrier (~1.3 us + L2 round trips per link).  Here the exchange never leaves the SM-to-SM network:
+//
+//   * sentences are independent, so the batch is cut into groups of <= 8 sentences and every group is decoded by ONE thread-block
+//     cluster of 8 CTAs; clusters never talk to each other (no grid barrier, no co-residency requirement);
+//   * CTA r of a cluster OWNS sentence r of the group: its residual row x, its attention (warp = head), its LayerNorm / RowQuant;
+//   * every CTA also owns a fixed 1/8 slice of the output features of each of the 6 GEMMs of a layer.  The weight slice streams
+//     through a 6 x 16 KB TMA ring (128-byte swizzle) that runs ahead of the dependency chain (weights are constants); the
+//     activations of all 8 sentences are the small operand: tcgen05.mma kind::i8, M = 128 weight rows, N = 16 (8 sentences used),
+//     int32 accumulators in TMEM, so a thread of the epilogue owns ONE output feature (its scale and bias are two registers);
+//   * GEMM epilogue -> SCATTER: y[s][f] = fl(fl(float(acc)*sx[s])*sw[f]) + b[f] is stored straight into the recv buffer of the
+//     CTA that owns sentence s (st.shared::cluster); row phase -> ALL-GATHER: the owner writes its quantized int8 row + scale
+//     into the swizzled operand buffer of every CTA of the cluster.  One barrier.cluster (release/acquire) per exchange.
+//
+// Arithmetic is instruction-for-instruction that of the stand-alone kernels (ot_rowmath.cuh, ot_attention_decode.cuh,
+// ot_generator.cu), so tokens and KV caches are bit-identical to the per-op engine path (tests/test_decoder_gpu.py).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ot_attention_decode.cuh"
+#include "ot_common.h"
+#include "ot_ptx.cuh"
+#include "ot_rowmath.cuh"
+
+namespace ot {
+
+int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
+                   bool swizzle128);
+
+namespace cd {
+
+constexpr int kD = 512;
+constexpr int kFF = 2048;
+constexpr int kCS = 8;              // CTAs per cluster = max sentences per cluster
+constexpr int kThreads = 256;
+constexpr int kIssuer = 224;        // warp 7, lane 0: MMA issuer
+constexpr int kLoader = 192;        // warp 6, lane 0: TMA producer of the weight ring.  NOT in the issuer's warp: a blocked
+                                    // mbarrier.try_wait of one lane stalls the divergent lanes of its warp (measured: 0.5 us per chunk)
+constexpr int kSlots = 6;
+constexpr int kSlotBytes = 16384;   // 128 weight rows x 128 B (one k-block)
+constexpr int kChunks = 44;         // weight chunks per layer per CTA
+constexpr int kMaxLayers = 8;
+constexpr int kKsPitch = kD + 16;
+constexpr int kMaxKeys = 32 * kDecKeysPerLane;   // 96
+constexpr int kGenVT = 32;          // vocabulary entries per generator tile
+
+// shared-memory map (dynamic, base aligned to 1024)
+constexpr int kSmRing = 0;                                  // weight ring
+constexpr int kSmBx = kSmRing + kSlots * kSlotBytes;        // 98304: activation operand, K = 512: [4 k-blocks][16 rows][128 B]
+constexpr int kSmKs = kSmBx + 4 * 2048;                     // 106496: attention K rows [96][528]; aliased by the K = 2048 operand (32 KB)
+constexpr int kSmBh = kSmKs;
+constexpr int kSmVh = kSmKs + 51200;                        // 157696: attention V slices [8][96][64]; aliased by the generator input [8][512] fp32
+constexpr int kSmHb = kSmVh;
+constexpr int kSmRecv = kSmVh + kHeads * kMaxKeys * kDk;    // 206848: fp32 row scattered by the GEMM epilogues (<= 2048 floats)
+constexpr int kSmX = kSmRecv + 8192;                        // 215040: residual row x of my sentence (512 floats)
+constexpr int kSmRow = kSmX + 2048;                         // 217088: int8 staging: q|k|v (1536 B) + ctx (512 B), or h (2048 B)
+constexpr int kSmCtx = kSmRow + 2048;                       // 219136: merged context row / final-norm row, 512 floats
+constexpr int kSmMisc = kSmCtx + 2048;                      // 221184: scales, reduction scratch, generator partials (1536 B)
+constexpr int kSmHot = kSmMisc + 1536;                      // 222720: CdHot copy (<= 1920 B) + 128 B of barriers
+constexpr int kSmTotal = kSmHot + 2048;                     // 224768
+static_assert(kMaxKeys * kKsPitch <= 51200 && 16 * 2048 <= 51200, "K region");
+static_assert(kSmTotal + 1024 <= 232448, "shared memory budget");
+
+// misc region (floats unless noted)
+constexpr int kMiSB = 0;        // [8] scale of each sentence's current operand row
+constexpr int kMiRed = 16;      // [64] reduction scratch
+constexpr int kMiGenV = 80;     // [8 ranks][8 sentences]: best logit of rank's vocabulary slice  (written by peers)
+constexpr int kMiGenI = 144;    // [8][8] int: its index
+constexpr int kMiPartV = 208;   // [8 warps][8 sentences] per-warp partials (local)
+constexpr int kMiPartI = 272;   // [8][8] int -> 336 floats = 1344 B
+static_assert((kMiPartI + 64) * 4 <= 1536, "misc region");
+constexpr int kSmBars = kSmHot + 1920;   // 12 ring barriers + accfull (104 B) + TMEM slot at +120
+
+struct CdLayer {
+  const float *ln_g[3], *ln_b[3];     // ln1, ln2, ln3
+  const float *sw[6], *bias[6];       // qkv, o, cq, co, w1, w2
+  int8_t *kc, *vc;                    // self-attention KV cache [B, cap, 512]
+  float *skc, *svc;                   // [B, cap]
+};
+
+struct alignas(16) CdHot {
+  CdLayer layer[kMaxLayers];
+  int n_layers, B, S, cap, vocab, n_gen_tiles, spc, pad0;
+  float emb_scale;
+  int pad1;
+  const int8_t* ckv; const float* sckv;       // cross K/V projections [B*S, 2*512*n_layers], scales [B*S, 2*n_layers]
+  const uint8_t* mask;                        // [B, S]
+  const float *fin_g, *fin_b;
+  const float *gen_w4, *gen_b;                // generator weight [n_gen_tiles][128][32][4] (tile / k4 / vocab entry / k), bias
+  const float *tgt_lut, *pe;
+  int64_t* ys; int64_t ys_ld;
+  unsigned long long* trace;                  // optional [256]
+};
+static_assert(sizeof(CdHot) % 16 == 0 && sizeof(CdHot) <= 1920, "CdHot is copied to shared memory in 16-byte pieces");
+
+struct CdPlan {
+  CUtensorMap map_w[kMaxLayers][6];           // qkv, o, cq, co, w1, w2: box = 64 rows x 128 B
+  CdHot hot;
+};
+
+struct Ctx {
+  const CdHot* P;
+  const CdPlan* G;
+  uint8_t* smem;
+  uint64_t* bars;        // full[kSlots], empty[kSlots], accfull
+  uint32_t tmem;
+  int rank, n_own, b;    // cluster rank, sentences of this cluster, my sentence (or -1)
+  uint32_t pn, cn, total;   // weight chunks issued / consumed / to do (issuer thread only)
+  uint32_t acc_parity;
+  int trace_slot;
+  bool trace_on;
+  bool fine;                       // intra-phase marks of one layer (profiling aid, trace slots 150..249)
+  int mark_slot;
+  unsigned long long t_step;
+};
+constexpr int kBarEmpty = kSlots, kBarAcc = 2 * kSlots;
+
+// profiling aid: (id << 32 | ns since the step began) into trace[150 + n]
+__device__ __forceinline__ void mark(Ctx& c, int id) {
+  if (c.fine && threadIdx.x == 0 && c.mark_slot < 100) {
+    c.P->trace[150 + c.mark_slot] = (static_cast<unsigned long long>(id) << 32) | ((tl_now() - c.t_step) & 0xffffffffull);
+    ++c.mark_slot;
+  }
+}
+__device__ __forceinline__ float* misc(Ctx& c) { return reinterpret_cast<float*>(c.smem + kSmMisc); }
+
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_b32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// One exchange: everything this CTA stored (local or remote shared memory, generic proxy) before the barrier is visible to every
+// thread of the cluster after it, also through the async proxy (tcgen05.mma operand reads).
+__device__ __forceinline__ void csync(Ctx& c) {
+  mark(c, 1);
+  if (c.trace_on && threadIdx.x == 0) c.P->trace[2 * c.trace_slot] = tl_now();
+  __syncwarp();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  tc_fence_before();
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  tc_fence_after();
+  if (c.trace_on && threadIdx.x == 0) c.P->trace[2 * c.trace_slot + 1] = tl_now();
+  __syncwarp();
+  ++c.trace_slot;
+  mark(c, 2);
+}
+
+// ------------------------------------------------------------------------------------------------ weight ring
+struct Chunk { int g, row0, rows, kb; };
+__device__ __forceinline__ Chunk chunk_of(int j) {
+  Chunk k;
+  if (j < 8) { k.g = 0; k.row0 = (j < 4) ? 0 : 128; k.rows = (j < 4) ? 128 : 64; k.kb = j & 3; }
+  else if (j < 20) { k.g = 1 + ((j - 8) >> 2); k.row0 = 0; k.rows = 64; k.kb = j & 3; }
+  else if (j < 28) { k.g = 4; k.row0 = (j < 24) ? 0 : 128; k.rows = 128; k.kb = j & 3; }
+  else { k.g = 5; k.row0 = 0; k.rows = 64; k.kb = j - 28; }
+  return k;
+}
+__device__ __forceinline__ int slice_rows(int g) { return g == 0 ? 192 : (g == 4 ? 256 : 64); }
+
+// issuer thread: load weight chunk c.pn into its ring slot (the slot must be free)
+__device__ __forceinline__ void issue_chunk(Ctx& c) {
+  const uint32_t n = c.pn;
+  const int slot = n % kSlots;
+  const int l = (n / kChunks) % c.P->n_layers;
+  const Chunk k = chunk_of(n % kChunks);
+  const CUtensorMap* map = &c.G->map_w[l][k.g];
+  const uint32_t fb = smem_u32(&c.bars[slot]);
+  const uint32_t dst = smem_u32(c.smem + kSmRing + slot * kSlotBytes);
+  const int r0 = slice_rows(k.g) * c.rank + k.row0;
+  mbar_arrive_expect_tx(fb, k.rows * 128);
+  tma_load_2d(dst, map, fb, k.kb * 128, r0);
+  if (k.rows == 128) tma_load_2d(dst + 8192, map, fb, k.kb * 128, r0 + 64);
+  ++c.pn;
+}
+// loader thread: issue every chunk below `upto` (blocking on the ring slot of each: chunk n reuses the slot of chunk n - kSlots,
+// free once that chunk's MMAs have completed)
+__device__ __forceinline__ void fill_until(Ctx& c, uint32_t upto) {
+  upto = min(upto, c.total);
+  while (c.pn < upto) {
+    const uint32_t round = c.pn / kSlots;
+    if (round > 0) mbar_wait(smem_u32(&c.bars[kBarEmpty + c.pn % kSlots]), (round - 1) & 1);
+    issue_chunk(c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM phase
+// g: 0 qkv, 1 o, 2 cq, 3 co, 4 w1 (ReLU), 5 w2.  D[f][s] = sum_k W[f][k] * a[s][k]; then scatter y[s][f] to the owner of s.
+__device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) {
+  const CdHot& P = *c.P;
+  const CdLayer& L = P.layer[l];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rows = slice_rows(g);
+  const int nkb = (g == 5) ? 16 : 4;
+  const int tile = warp >> 2;
+  const int fl = 128 * tile + 32 * (warp & 3) + lane;
+  const bool act = (128 * tile + 32 * (warp & 3)) < rows;     // warp-uniform
+  const int f = rows * c.rank + fl;
+  float sw = 0.f, bb = 0.f;
+  mark(c, 10 + g);
+  if (act) { sw = __ldg(L.sw[g] + f); bb = __ldg(L.bias[g] + f); }
+  if (tid == kIssuer) {
+    const uint32_t bbase = smem_u32(c.smem + (g == 5 ? kSmBh : kSmBx));
+    constexpr uint32_t idesc = make_idesc_i8(128, 16);
+    const int ntile = (rows + 127) >> 7;
+    for (int t = 0; t < ntile; ++t) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int slot = c.cn % kSlots;
+        mbar_wait(smem_u32(&c.bars[slot]), (c.cn / kSlots) & 1);
+        tc_fence_after();
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(c.smem + kSmRing + slot * kSlotBytes));
+        const uint64_t b_desc = make_smem_desc_sw128(bbase + kb * 2048);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_i8_ss(c.tmem + 16 * t, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+        mma_commit(smem_u32(&c.bars[kBarEmpty + slot]));
+        ++c.cn;
+      }
+    }
+    mma_commit(smem_u32(&c.bars[kBarAcc]));
+  } else if (tid == kLoader) {
+    // keep the ring full while this GEMM drains it: by the time its last MMA has completed the next kSlots chunks (the start of
+    // the next GEMM) are in flight, so the ring runs ahead of the dependency chain
+    fill_until(c, gend + kSlots);
+  }
+  __syncwarp();
+  if (act) {
+    mbar_wait(smem_u32(&c.bars[kBarAcc]), c.acc_parity);
+    tc_fence_after();
+    mark(c, 20 + g);
+    uint32_t r[8];
+    tmem_ld_32x8(c.tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + 16 * tile, r);
+    tmem_wait_ld();
+    const float* sB = misc(c) + kMiSB;
+    const uint32_t recv = smem_u32(c.smem + kSmRecv) + 4u * static_cast<uint32_t>(f);
+#pragma unroll
+    for (int s = 0; s < kCS; ++s) {
+      if (s < c.n_own) {
+        float y = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[s])), sB[s]), sw), bb);
+        if (g == 4) y = fmaxf(y, 0.0f);
+        st_cluster_b32(mapa_shared(recv, s), __float_as_uint(y));
+      }
+    }
+  }
+  mark(c, 30 + g);
+  c.acc_parity ^= 1u;
+}
+
+// ------------------------------------------------------------------------------------------------ all-gather helpers
+// Push the int8 row staged at `src` (K bytes, K = 512 or 2048) into row `rank` of every CTA's operand buffer (128-byte swizzle:
+// 16-byte chunk c of a row lands at chunk c ^ (row & 7) of its 128-byte line), plus its scale.
+__device__ __forceinline__ void push_row_q8(Ctx& c, const uint8_t* src, int K, int dst_off, float scale) {
+  const int tid = threadIdx.x;
+  const int chunks = K >> 4;                       // 32 or 128
+  const int per_peer_shift = (K == 512) ? 5 : 7;
+  for (int idx = tid; idx < chunks * kCS; idx += kThreads) {
+    const int peer = idx >> per_peer_shift, ch = idx & (chunks - 1);
+    const uint4 v = *reinterpret_cast<const uint4*>(src + ch * 16);
+    const int kb = ch >> 3, cc = ch & 7;
+    const uint32_t local = smem_u32(c.smem + dst_off + kb * 2048 + c.rank * 128 + ((cc ^ (c.rank & 7)) << 4));
+    st_cluster_v4(mapa_shared(local, peer), v);
+  }
+  if (tid < kCS) st_cluster_b32(mapa_shared(smem_u32(misc(c) + kMiSB + c.rank), tid), __float_as_uint(scale));
+}
+
+// ------------------------------------------------------------------------------------------------ row phases (owner CTA)
+// LayerNorm of my sentence.  SRC 0: x = embedding(token)*sqrt(d) + pe[t]; SRC 1: x = x + recv (the scattered O / CO / FFN2 row).
+// quant: RowQuant -> all-gather into Bx; else (final norm) the fp32 row goes to every CTA's generator input.
+__device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, const float* gamma, const float* beta, bool quant) {
+  const CdHot& P = *c.P;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* xr = reinterpret_cast<float*>(c.smem + kSmX);
+  uint8_t* rowq = c.smem + kSmRow;
+  float* yrow = reinterpret_cast<float*>(c.smem + kSmCtx);
+  float* red = misc(c) + kMiRed;
+  mark(c, 40);
+  if (c.b >= 0 && warp == 0) {
+    float4 v[4];
+    if (SRC == 0) {
+      const float4* e4 = reinterpret_cast<const float4*>(P.tgt_lut + token * kD);
+      const float4* p4 = reinterpret_cast<const float4*>(P.pe + static_cast<int64_t>(t) * kD);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 e = __ldg(e4 + i * 32 + lane), q = __ldg(p4 + i * 32 + lane);
+        v[i] = make_float4(__fadd_rn(__fmul_rn(e.x, P.emb_scale), q.x), __fadd_rn(__fmul_rn(e.y, P.emb_scale), q.y),
+                           __fadd_rn(__fmul_rn(e.z, P.emb_scale), q.z), __fadd_rn(__fmul_rn(e.w, P.emb_scale), q.w));
+      }
+    } else {
+      const float4* y4 = reinterpret_cast<const float4*>(c.smem + kSmRecv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 res = reinterpret_cast<const float4*>(xr)[i * 32 + lane], y = y4[i * 32 + lane];
+        v[i] = make_float4(__fadd_rn(res.x, y.x), __fadd_rn(res.y, y.y), __fadd_rn(res.z, y.z), __fadd_rn(res.w, y.w));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(xr)[i * 32 + lane] = v[i];
+    mark(c, 41);
+    const float amax = layernorm_row<4>(v, lane, kD, gamma, beta, 1e-6f);
+    mark(c, 42);
+    if (quant) {
+      const float s = quant_scale(warp_max(amax));
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint32_t*>(rowq)[i * 32 + lane] = pack4(quant_one(v[i].x, s), quant_one(v[i].y, s), quant_one(v[i].z, s), quant_one(v[i].w, s));
+      if (lane == 0) red[0] = s;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(yrow)[i * 32 + lane] = v[i];
+    }
+  }
+  mark(c, 43);
+  __syncthreads();
+  mark(c, 44);
+  if (c.b >= 0) {
+    if (quant) {
+      push_row_q8(c, rowq, kD, kSmBx, red[0]);
+    } else {
+      for (int idx = tid; idx < 128 * kCS; idx += kThreads) {
+        const int peer = idx >> 7, ch = idx & 127;
+        const uint4 v = *reinterpret_cast<const uint4*>(yrow + ch * 4);
+        st_cluster_v4(mapa_shared(smem_u32(c.smem + kSmHb + (c.rank * kD + ch * 4) * 4), peer), v);
+      }
+    }
+  }
+  mark(c, 45);
+}
+
+// FFN1 row (bias + ReLU applied by the GEMM epilogue): RowQuant over 2048 features -> all-gather into Bh.
+__device__ __forceinline__ void phase_ffnq(Ctx& c) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* red = misc(c) + kMiRed;
+  uint8_t* rowq = c.smem + kSmRow;
+  mark(c, 60);
+  if (c.b >= 0) {
+    const float4* y4 = reinterpret_cast<const float4*>(c.smem + kSmRecv);
+    const float4 a = y4[2 * tid], b = y4[2 * tid + 1];
+    float am = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+    am = warp_max(am);
+    if (lane == 0) red[warp] = am;
+    __syncthreads();
+    const float s = quant_scale(fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]))));
+    uint2 w;
+    w.x = pack4(quant_one(a.x, s), quant_one(a.y, s), quant_one(a.z, s), quant_one(a.w, s));
+    w.y = pack4(quant_one(b.x, s), quant_one(b.y, s), quant_one(b.z, s), quant_one(b.w, s));
+    reinterpret_cast<uint2*>(rowq)[tid] = w;
+    __syncthreads();
+    mark(c, 61);
+    push_row_q8(c, rowq, kFF, kSmBh, s);
+  }
+  mark(c, 62);
+}
+
+// ------------------------------------------------------------------------------------------------ attention (owner CTA)
+struct AttnPre {
+  float skl[kDecKeysPerLane], svl[kDecKeysPerLane];
+  uint8_t keepl[kDecKeysPerLane];
+};
+// Issued during the preceding GEMM phase: the old K/V rows of my sentence into shared memory (cp.async) and, per lane, the
+// scales / mask of its keys j = 32*kk + lane.
+__device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* k, const int8_t* v, int64_t ldk, int64_t row0, const float* sk,
+                                              const float* sv, int64_t sstride, const uint8_t* key_mask, int mask_stride, AttnPre& pre) {
+  int8_t* Ks = reinterpret_cast<int8_t*>(c.smem + kSmKs);
+  int8_t* Vh = reinterpret_cast<int8_t*>(c.smem + kSmVh);
+  if (threadIdx.x < 192) {      // warps 6 / 7 go straight to the weight ring / the MMAs
+    for (int idx = threadIdx.x; idx < n_old * 32; idx += 192) {
+      const int j = idx >> 5, ch = idx & 31;
+      const int64_t src = (row0 + j) * ldk + ch * 16;
+      cp_async16(smem_u32(Ks + j * kKsPitch + ch * 16), k + src);
+      cp_async16(smem_u32(Vh + ((ch >> 2) * kMaxKeys + j) * kDk + (ch & 3) * 16), v + src);
+    }
+  }
+  cp_async_commit();
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
+    const int j = kk * 32 + lane;
+    const bool old = j < n_old;
+    const int jc = old ? j : 0;
+    pre.skl[kk] = (n_old > 0) ? __ldcg(sk + (row0 + jc) * sstride) : 0.f;
+    pre.svl[kk] = (n_old > 0) ? __ldcg(sv + (row0 + jc) * sstride) : 0.f;
+    pre.keepl[kk] = (key_mask != nullptr && old) ? key_mask[static_cast<int64_t>(c.b) * mask_stride + j] : 1;
+  }
+}
+
+// RowQuant (groups of 512 features) of my projection row in recv: NG = 3: q | k | v, NG = 1: cross-attention q.
+__device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale)[3]) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* rowbuf = c.smem + kSmRow;
+  float* red = misc(c) + kMiRed;
+  const float4* y4 = reinterpret_cast<const float4*>(c.smem + kSmRecv);
+  const int N = NG * kD;
+  float4 y[2];
+  float am[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = tid + 256 * j;
+    y[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < N / 4) {
+      y[j] = y4[i];
+      am[j] = fmaxf(fmaxf(fabsf(y[j].x), fabsf(y[j].y)), fmaxf(fabsf(y[j].z), fabsf(y[j].w)));
+    }
+  }
+  am[0] = warp_max(am[0]);
+  am[1] = warp_max(am[1]);
+  if (lane == 0) { red[warp] = am[0]; red[8 + warp] = am[1]; }
+  __syncthreads();
+  scale[0] = quant_scale(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])));
+  scale[1] = scale[2] = 0.f;
+  if (NG == 3) {
+    scale[1] = quant_scale(fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
+    scale[2] = quant_scale(fmaxf(fmaxf(red[8], red[9]), fmaxf(red[10], red[11])));
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = tid + 256 * j;
+    if (i < N / 4) {
+      const float s = scale[i >> 7];
+      reinterpret_cast<uint32_t*>(rowbuf)[i] = pack4(quant_one(y[j].x, s), quant_one(y[j].y, s), quant_one(y[j].z, s), quant_one(y[j].w, s));
+    }
+  }
+  __syncthreads();
+}
+
+// Decode attention of my sentence with K rows in Ks and V slices in Vh: the arithmetic of attention_decode_body
+// (ot_attention_decode.cuh), instruction for instruction.  warp h = head h.  Leaves the quantized context row at rowbuf + 1536
+// and its scale in red[16].
+__device__ __forceinline__ void attention_smem(Ctx& c, int Tk, int q_pos0, int mask_kind, float sqi, const AttnPre& pre) {
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int8_t* rowbuf = reinterpret_cast<const int8_t*>(c.smem + kSmRow);
+  const int8_t* Ks = reinterpret_cast<const int8_t*>(c.smem + kSmKs);
+  AttnDecVh Vh = reinterpret_cast<AttnDecVh>(c.smem + kSmVh);
+  float* ctx = reinterpret_cast<float*>(c.smem + kSmCtx);
+  float* red = misc(c) + kMiRed;
+  uint32_t qw[16];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(rowbuf + h * kDk);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint4 t = qp[w];
+      qw[4 * w] = t.x; qw[4 * w + 1] = t.y; qw[4 * w + 2] = t.z; qw[4 * w + 3] = t.w;
+    }
+  }
+  float sc[kDecKeysPerLane], svl[kDecKeysPerLane];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
+    const int j = kk * 32 + lane;
+    const int jc = min(j, Tk - 1);
+    const uint4* kp = reinterpret_cast<const uint4*>(Ks + jc * kKsPitch + h * kDk);
+    int dot = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint4 t = kp[w];
+      dot = __dp4a(static_cast<int>(qw[4 * w]), static_cast<int>(t.x), dot);
+      dot = __dp4a(static_cast<int>(qw[4 * w + 1]), static_cast<int>(t.y), dot);
+      dot = __dp4a(static_cast<int>(qw[4 * w + 2]), static_cast<int>(t.z), dot);
+      dot = __dp4a(static_cast<int>(qw[4 * w + 3]), static_cast<int>(t.w), dot);
+    }
+    const float s = __fdiv_rn(__fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), pre.skl[kk]), 8.0f);
+    const bool visible = pre.keepl[kk] != 0 && (mask_kind != 2 || j <= q_pos0);
+    const bool live = j < Tk;
+    sc[kk] = live ? (visible ? s : -1e9f) : -INFINITY;
+    svl[kk] = live ? pre.svl[kk] : 0.f;
+    mx = live ? fmaxf(mx, sc[kk]) : mx;
+  }
+  mark(c, 54);
+  mx = warp_max_f(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
+    if (kk * 32 + lane < Tk) {
+      sc[kk] = expf(__fsub_rn(sc[kk], mx));
+      sum += sc[kk];
+    }
+  }
+  sum = warp_sum_f(sum);
+  float pq[kDecKeysPerLane];
+#pragma unroll
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk)
+    pq[kk] = (kk * 32 + lane < Tk) ? __fdiv_rn(rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f)), 127.0f) : 0.f;
+  mark(c, 55);
+  float acc0 = 0.f, acc1 = 0.f;
+  const int d0 = 2 * lane;
+  // keys in order j = 0..; a key with p = 0 (masked, or beyond Tk where sv = 0 and the V bytes are stale but finite)
+  // contributes exactly +-0, as in attention_decode_body
+#pragma unroll
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
+    if (kk * 32 >= Tk) break;
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const float ph = __shfl_sync(0xffffffffu, pq[kk], jj);
+      const float svj = __shfl_sync(0xffffffffu, svl[kk], jj);
+      const char2 vv = *reinterpret_cast<const char2*>(&Vh[h][kk * 32 + jj][d0]);
+      acc0 = fmaf(ph, __fmul_rn(__int2float_rn(vv.x), svj), acc0);
+      acc1 = fmaf(ph, __fmul_rn(__int2float_rn(vv.y), svj), acc1);
+    }
+  }
+  mark(c, 56);
+  *reinterpret_cast<float2*>(ctx + h * kDk + d0) = make_float2(acc0, acc1);
+  __syncthreads();
+  mark(c, 57);
+  if (h == 0) {
+    float4 v[4];
+    float amax = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      v[t] = *reinterpret_cast<const float4*>(ctx + (t * 32 + lane) * 4);
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[t].x), fabsf(v[t].y)), fmaxf(fabsf(v[t].z), fabsf(v[t].w))));
+    }
+    const float s = __fdiv_rn(fmaxf(warp_max_f(amax), 1e-5f), 127.0f);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int q0i = __float2int_rn(rintf(__fdiv_rn(v[t].x, s))), q1i = __float2int_rn(rintf(__fdiv_rn(v[t].y, s)));
+      const int q2i = __float2int_rn(rintf(__fdiv_rn(v[t].z, s))), q3i = __float2int_rn(rintf(__fdiv_rn(v[t].w, s)));
+      const uint32_t w = (static_cast<uint32_t>(q0i) & 0xFFu) | ((static_cast<uint32_t>(q1i) & 0xFFu) << 8) |
+                         ((static_cast<uint32_t>(q2i) & 0xFFu) << 16) | ((static_cast<uint32_t>(q3i) & 0xFFu) << 24);
+      *reinterpret_cast<uint32_t*>(c.smem + kSmRow + 1536 + (t * 32 + lane) * 4) = w;
+    }
+    if (lane == 0) red[16] = s;
+  }
+  __syncthreads();
+}
+
+// self: RowQuant of q | k | v, KV-cache append, causal attention over t+1 keys; cross: RowQuant of q, attention over the S cached
+// memory keys with the key-padding mask.  Ends with the all-gather of the quantized context row.
+__device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l, AttnPre& pre) {
+  const CdHot& P = *c.P;
+  const CdLayer& L = P.layer[l];
+  if (c.b < 0) return;
+  mark(c, 50);
+  cp_async_wait_all();
+  float sc[3];
+  mark(c, 51);
+  quant_groups(c, self ? 3 : 1, sc);
+  mark(c, 52);       // (its barriers also publish the prefetched K/V rows)
+  if (self) {
+    const int tid = threadIdx.x;
+    const int8_t* rowbuf = reinterpret_cast<const int8_t*>(c.smem + kSmRow);
+    int8_t* Ks = reinterpret_cast<int8_t*>(c.smem + kSmKs);
+    int8_t* Vh = reinterpret_cast<int8_t*>(c.smem + kSmVh);
+    const int64_t dst = (static_cast<int64_t>(c.b) * P.cap + t) * kD;
+    if (tid < 32) {
+      const uint4 kk = *reinterpret_cast<const uint4*>(rowbuf + kD + tid * 16);
+      *reinterpret_cast<uint4*>(Ks + t * kKsPitch + tid * 16) = kk;
+      *reinterpret_cast<uint4*>(L.kc + dst + tid * 16) = kk;
+    } else if (tid < 64) {
+      const int ch = tid - 32;
+      const uint4 vv = *reinterpret_cast<const uint4*>(rowbuf + 2 * kD + ch * 16);
+      *reinterpret_cast<uint4*>(Vh + ((ch >> 2) * kMaxKeys + t) * kDk + (ch & 3) * 16) = vv;
+      *reinterpret_cast<uint4*>(L.vc + dst + ch * 16) = vv;
+    } else if (tid == 64) {
+      L.skc[static_cast<int64_t>(c.b) * P.cap + t] = sc[1];
+      L.svc[static_cast<int64_t>(c.b) * P.cap + t] = sc[2];
+    }
+    const int lane = tid & 31;
+#pragma unroll
+    for (int kk = 0; kk < kDecKeysPerLane; ++kk)
+      if (kk * 32 + lane == t) { pre.skl[kk] = sc[1]; pre.svl[kk] = sc[2]; }
+    __syncthreads();
+  }
+  mark(c, 53);
+  attention_smem(c, self ? t + 1 : P.S, self ? t : 0, self ? 2 : 1, sc[0], pre);
+  mark(c, 58);
+  push_row_q8(c, c.smem + kSmRow + 1536, kD, kSmBx, (misc(c) + kMiRed)[16]);
+  mark(c, 59);
+}
+
+// ------------------------------------------------------------------------------------------------ generator
+// logits[s, v] = bias[v] + sum_k h[s,k] * W[v,k]  (k ascending, fmaf: the order of generator_logits_kernel).  The vocabulary is cut
+// into tiles of 32 entries; tile j belongs to CTA j % 8 of every cluster, and inside the CTA to warp (j / 8) % 8.  A lane owns one
+// entry of each of its warp's (up to NT) tiles for all 8 sentences; weights arrive as one coalesced 16-byte load per lane per 4 k.
+template <int NT>
+__device__ __forceinline__ void generator_warp(const CdHot& P, const float* hb, int rank, int warp, int lane, float (&best)[kCS], int (&bidx)[kCS]) {
+  float acc[NT][kCS];
+  const float4* wp[NT];
+  int v[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int tile = rank + kCS * (warp + 8 * i);
+    wp[i] = reinterpret_cast<const float4*>(P.gen_w4) + static_cast<int64_t>(tile) * 128 * 32 + lane;
+    v[i] = tile * kGenVT + lane;
+#pragma unroll
+    for (int s = 0; s < kCS; ++s) acc[i][s] = 0.f;
+  }
+  const float4* h4 = reinterpret_cast<const float4*>(hb);
+  constexpr int G = 4;                     // k-quads per register group: the next group's weights are in flight during this group's FMAs
+  float4 wn[G][NT];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int i = 0; i < NT; ++i) wn[g][i] = __ldg(wp[i] + g * 32);
+#pragma unroll 1
+  for (int k0 = 0; k0 < 128; k0 += G) {
+    float4 w[G][NT];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        w[g][i] = wn[g][i];
+        if (k0 + G < 128) wn[g][i] = __ldg(wp[i] + (k0 + G + g) * 32);
+      }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int s = 0; s < kCS; ++s) {
+        const float4 h = h4[s * 128 + k0 + g];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          acc[i][s] = fmaf(h.x, w[g][i].x, acc[i][s]);
+          acc[i][s] = fmaf(h.y, w[g][i].y, acc[i][s]);
+          acc[i][s] = fmaf(h.z, w[g][i].z, acc[i][s]);
+          acc[i][s] = fmaf(h.w, w[g][i].w, acc[i][s]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const bool ok = v[i] < P.vocab;
+    const float bv = (ok && P.gen_b) ? __ldg(P.gen_b + v[i]) : 0.f;
+#pragma unroll
+    for (int s = 0; s < kCS; ++s) {
+      float lg = __fadd_rn(acc[i][s], bv);
+      if (lg != lg) lg = INFINITY;               // torch.max / np.argmax: a NaN logit ranks above every number
+      if (ok && (lg > best[s] || (lg == best[s] && v[i] < bidx[s]))) { best[s] = lg; bidx[s] = v[i]; }
+    }
+  }
+}
+
+__device__ __forceinline__ void phase_generator(Ctx& c) {
+  const CdHot& P = *c.P;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* hb = reinterpret_cast<const float*>(c.smem + kSmHb);
+  float best[kCS];
+  int bidx[kCS];
+#pragma unroll
+  for (int s = 0; s < kCS; ++s) { best[s] = -INFINITY; bidx[s] = 0x7fffffff; }
+  // tiles of this warp: rank + 8*(warp + 8*i) < n_gen_tiles
+  int nt = 0;
+  while (nt < 3 && c.rank + kCS * (warp + 8 * nt) < P.n_gen_tiles) ++nt;
+  if (nt == 3) generator_warp<3>(P, hb, c.rank, warp, lane, best, bidx);
+  else if (nt == 2) generator_warp<2>(P, hb, c.rank, warp, lane, best, bidx);
+  else if (nt == 1) generator_warp<1>(P, hb, c.rank, warp, lane, best, bidx);
+  float* pv = misc(c) + kMiPartV;
+  int* pi = reinterpret_cast<int*>(misc(c) + kMiPartI);
+#pragma unroll
+  for (int s = 0; s < kCS; ++s) {
+    float bv = best[s];
+    int bi = bidx[s];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > bv || (ob == bv && oi < bi)) { bv = ob; bi = oi; }
+    }
+    if (lane == 0) { pv[warp * kCS + s] = bv; pi[warp * kCS + s] = bi; }
+  }
+  __syncthreads();
+  if (tid < c.n_own) {                 // sentence tid: combine the 8 warps, send to its owner
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float ob = pv[w * kCS + tid];
+      const int oi = pi[w * kCS + tid];
+      if (ob > bv || (ob == bv && oi < bi)) { bv = ob; bi = oi; }
+    }
+    st_cluster_b32(mapa_shared(smem_u32(misc(c) + kMiGenV + c.rank), tid), __float_as_uint(bv));
+    st_cluster_b32(mapa_shared(smem_u32(misc(c) + kMiGenI + c.rank), tid), static_cast<uint32_t>(bi));
+  }
+}
+// owner, warp 0: first arg-max over the 8 vocabulary slices
+__device__ __forceinline__ int generator_pick(Ctx& c, int lane) {
+  const float* gv = misc(c) + kMiGenV;
+  const int* gi = reinterpret_cast<const int*>(misc(c) + kMiGenI);
+  float bv = (lane < kCS) ? gv[lane] : -INFINITY;
+  int bi = (lane < kCS) ? gi[lane] : 0x7fffffff;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > bv || (ob == bv && oi < bi)) { bv = ob; bi = oi; }
+  }
+  bi = __shfl_sync(0xffffffffu, bi, 0);
+  return (bi >= 0 && bi < c.P->vocab) ? bi : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __restrict__ plan, int t0, int n_steps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  Ctx c;
+  c.G = plan;
+  c.smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);    // same offset in every CTA of the cluster
+  c.P = reinterpret_cast<const CdHot*>(c.smem + kSmHot);
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(CdHot) / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(c.smem + kSmHot)[i] = reinterpret_cast<const uint4*>(&plan->hot)[i];
+  c.bars = reinterpret_cast<uint64_t*>(c.smem + kSmBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.smem + kSmBars + 120);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 7) {
+    if (lane == 0) {
+      for (int i = 0; i <= kBarAcc; ++i) mbar_init(smem_u32(&c.bars[i]), 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 32);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem = *tmem_slot;
+  const CdHot& P = *c.P;
+  const int nl = P.n_layers;
+  c.rank = static_cast<int>(cluster_ctarank());
+  const int cluster_id = blockIdx.x / kCS;
+  c.n_own = min(P.spc, P.B - cluster_id * P.spc);
+  c.b = (c.rank < c.n_own) ? cluster_id * P.spc + c.rank : -1;
+  c.pn = c.cn = 0;
+  c.total = static_cast<uint32_t>(n_steps) * nl * kChunks;
+  c.acc_parity = 0;
+  c.trace_slot = 0;
+  c.trace_on = false;
+  c.fine = false;
+  c.mark_slot = 0;
+  c.t_step = 0;
+  if (tid == kLoader) fill_until(c, kSlots);
+  __syncwarp();
+  csync(c);          // every CTA of the cluster is running (its shared memory may be written) and has its barriers initialised
+
+  const int t_last = t0 + n_steps - 1;
+  AttnPre pre;
+#pragma unroll 1
+  for (int t = t0; t <= t_last; ++t) {
+    c.trace_slot = 0;
+    c.trace_on = P.trace != nullptr && blockIdx.x == 0 && t == t_last;
+    if (c.trace_on && tid == 0) { c.t_step = tl_now(); P.trace[255] = c.t_step; }
+    // ---- token -> embedding + positional encoding -> LayerNorm 1 of layer 0 -> all-gather
+    {
+      int64_t token = 0;
+      if (c.b >= 0 && warp == 0) {
+        if (t > t0) {
+          token = generator_pick(c, lane);
+          if (lane == 0) P.ys[static_cast<int64_t>(c.b) * P.ys_ld + t] = token;
+        } else {
+          token = __ldcg(P.ys + static_cast<int64_t>(c.b) * P.ys_ld + t);
+        }
+      }
+      phase_ln(c, 0, token, t, P.layer[0].ln_g[0], P.layer[0].ln_b[0], true);
+      csync(c);
+    }
+#pragma unroll 1
+    for (int l = 0; l < nl; ++l) {
+      const CdLayer& L = P.layer[l];
+      c.fine = c.trace_on && l == min(2, nl - 1);
+#pragma unroll 1
+      for (int q = 0; q < 11; ++q) {
+        if (q == 0 || q == 2 || q == 4 || q == 6 || q == 8 || q == 10) {
+          // ---- GEMM phases; the attention operands of my sentence are prefetched alongside
+          if ((q == 0 || q == 4) && c.b >= 0) {
+            const bool self = q == 0;
+            attn_prefetch(c, self ? t : P.S, self ? L.kc : P.ckv + 2 * kD * l, self ? L.vc : P.ckv + 2 * kD * l + kD,
+                          self ? kD : 2 * kD * nl, static_cast<int64_t>(c.b) * (self ? P.cap : P.S), self ? L.skc : P.sckv + 2 * l,
+                          self ? L.svc : P.sckv + 2 * l + 1, self ? 1 : 2 * nl, self ? nullptr : P.mask, P.S, pre);
+          }
+          // index one past this GEMM's last weight chunk in the launch-wide chunk sequence
+          const int g = q >> 1;
+          const uint32_t gend = (static_cast<uint32_t>(t - t0) * nl + l) * kChunks + (g == 0 ? 8 : g == 1 ? 12 : g == 2 ? 16 : g == 3 ? 20 : g == 4 ? 28 : 44);
+          phase_gemm(c, l, g, gend);
+        } else if (q == 1 || q == 5) {
+          phase_attention(c, q == 1, t, l, pre);
+        } else if (q == 3 || q == 7) {
+          phase_ln(c, 1, 0, t, L.ln_g[q == 3 ? 1 : 2], L.ln_b[q == 3 ? 1 : 2], true);
+        } else {
+          phase_ffnq(c);
+        }
+        csync(c);
+      }
+      // ---- residual + LayerNorm 1 of the next layer, or the final norm (fp32 row to every CTA's generator input)
+      if (l + 1 < nl) phase_ln(c, 1, 0, t, P.layer[l + 1].ln_g[0], P.layer[l + 1].ln_b[0], true);
+      else phase_ln(c, 1, 0, t, P.fin_g, P.fin_b, false);
+      csync(c);
+    }
+    c.fine = false;
+    phase_generator(c);
+    csync(c);
+  }
+  // the last step's token
+  if (c.b >= 0 && warp == 0) {
+    const int id = generator_pick(c, lane);
+    if (lane == 0) P.ys[static_cast<int64_t>(c.b) * P.ys_ld + t_last + 1] = id;
+  }
+  cp_async_wait_all();
+  tc_fence_before();
+  csync(c);          // no CTA exits while a peer may still address its shared memory
+  if (warp == 7) tmem_dealloc(c.tmem, 32);
+}
+
+}  // namespace cd
+}  // namespace ot
+
+using namespace ot;
+using namespace ot::cd;
+
+extern "C" int ot_cdecoder_plan_size(void) { return static_cast<int>(sizeof(CdPlan)); }
+
+// layer_ptrs: n_layers x 28 device pointers in the order
+//   ln1_g ln1_b ln2_g ln2_b ln3_g ln3_b | qkv_w qkv_sw qkv_b | o_w o_sw o_b | cq_w cq_sw cq_b | co_w co_sw co_b |
+//   w1_w w1_sw w1_b | w2_w w2_sw w2_b | kc vc skc svc
+// ws_ptrs (12): ckv sckv mask fin_g fin_b gen_w4 gen_b tgt_lut pe ys trace(optional) reserved
+extern "C" int ot_cdecoder_plan_build(void* plan_dev, int n_layers, int B, int S, int cap, int vocab, int spc, int64_t ys_ld,
+                                      const void* const* layer_ptrs, const void* const* ws_ptrs) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(plan_dev && layer_ptrs && ws_ptrs, "null argument");
+  OT_REQUIRE(n_layers >= 1 && n_layers <= kMaxLayers, "1..8 decoder layers");
+  OT_REQUIRE(B >= 1 && spc >= 1 && spc <= kCS, "1..8 sentences per cluster");
+  OT_REQUIRE(S >= 1 && S <= kMaxKeys && cap >= 2 && cap <= kMaxKeys, "source length and cache capacity must be <= 96");
+  OT_REQUIRE(vocab > 1 && (vocab + kGenVT - 1) / kGenVT <= kCS * 8 * 3, "at most 192 generator tiles of 32 vocabulary entries");
+  CdPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  CdHot& h = plan.hot;
+  h.n_layers = n_layers; h.B = B; h.S = S; h.cap = cap; h.vocab = vocab; h.spc = spc;
+  h.n_gen_tiles = (vocab + kGenVT - 1) / kGenVT;
+  h.emb_scale = sqrtf(static_cast<float>(kD));
+  for (int k = 0; k < 10; ++k) OT_REQUIRE(ws_ptrs[k] != nullptr || k == 6, "null workspace pointer");
+  h.ckv = static_cast<const int8_t*>(ws_ptrs[0]); h.sckv = static_cast<const float*>(ws_ptrs[1]);
+  h.mask = static_cast<const uint8_t*>(ws_ptrs[2]);
+  h.fin_g = static_cast<const float*>(ws_ptrs[3]); h.fin_b = static_cast<const float*>(ws_ptrs[4]);
+  h.gen_w4 = static_cast<const float*>(ws_ptrs[5]); h.gen_b = static_cast<const float*>(ws_ptrs[6]);
+  h.tgt_lut = static_cast<const float*>(ws_ptrs[7]); h.pe = static_cast<const float*>(ws_ptrs[8]);
+  h.ys = static_cast<int64_t*>(const_cast<void*>(ws_ptrs[9]));
+  h.trace = static_cast<unsigned long long*>(const_cast<void*>(ws_ptrs[10]));
+  h.ys_ld = ys_ld;
+  int rc;
+  for (int l = 0; l < n_layers; ++l) {
+    const void* const* p = layer_ptrs + l * 28;
+    for (int k = 0; k < 28; ++k) OT_REQUIRE(p[k] != nullptr, "null layer pointer");
+    CdLayer& L = h.layer[l];
+    auto f = [&](int k) { return static_cast<const float*>(p[k]); };
+    for (int i = 0; i < 3; ++i) { L.ln_g[i] = f(2 * i); L.ln_b[i] = f(2 * i + 1); }
+    for (int w = 0; w < 6; ++w) { L.sw[w] = f(7 + 3 * w); L.bias[w] = f(8 + 3 * w); }
+    L.kc = static_cast<int8_t*>(const_cast<void*>(p[24])); L.vc = static_cast<int8_t*>(const_cast<void*>(p[25]));
+    L.skc = static_cast<float*>(const_cast<void*>(p[26])); L.svc = static_cast<float*>(const_cast<void*>(p[27]));
+    const int wn[6] = {3 * kD, kD, kD, kD, kFF, kD};
+    const int wk[6] = {kD, kD, kD, kD, kD, kFF};
+    for (int w = 0; w < 6; ++w)
+      if ((rc = get_tensor_map(&plan.map_w[l][w], p[6 + 3 * w], wn[w], wk[w], wk[w], 64, 128, true))) return rc;
+  }
+  OT_CHECK_CUDA(cudaMemcpy(plan_dev, &plan, sizeof(plan), cudaMemcpyHostToDevice));
+  return OT_OK;
+}
+
+// Runs greedy steps t0 .. t0+n_steps-1 for B sentences (ys[:, t0] must hold the current tokens; caches hold positions < t0).
+extern "C" int ot_cdecoder_run(const void* plan_dev, int B, int spc, int t0, int n_steps, void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(plan_dev && B >= 1 && spc >= 1 && spc <= kCS && t0 >= 0 && n_steps >= 0, "bad arguments");
+  if (n_steps == 0) return OT_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OT_CHECK_CUDA(cudaFuncSetAttribute(cdecoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal + 1024));
+    attr_set = true;
+  }
+  const int n_clusters = (B + spc - 1) / spc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_clusters * kCS);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmTotal + 1024;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const CdPlan* plan = static_cast<const CdPlan*>(plan_dev);
+  OT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cdecoder_kernel, plan, t0, n_steps));
+  count_launch();
+  return OT_OK;
+}

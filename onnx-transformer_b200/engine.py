@@ -110,7 +110,8 @@ class QuantizedTransformer:
     smoothed if SmoothQuant is wanted: get_quantized_model.smooth_lm is an offline weight transform)."""
 
     def __init__(self, float_weights: Dict[str, np.ndarray], n_layers: int = 6, device: Optional[torch.device] = None, max_len: int = W.MAX_LEN,
-                 pdl: bool = True, fused_ln: bool = False, weight_bits: int = 8, persistent: bool = True):
+                 pdl: bool = True, fused_ln: bool = False, weight_bits: int = 8, persistent: bool = True, decoder: str = "cluster",
+                 sentences_per_cluster: int = 8):
         if not torch.cuda.is_available():
             raise K.OtError("QuantizedTransformer needs a CUDA device: this package has no CPU fallback")
         K._lib.load().ot_set_pdl(1 if pdl else 0)   # programmatic dependent launch for every kernel of the library
@@ -163,7 +164,10 @@ class QuantizedTransformer:
         self.graph_replays = 0   # CUDA-graph replays of the greedy step (each replays ws['graph_launches'] kernels)
         # fault-free greedy steps run inside ONE persistent kernel (csrc/ot_decoder.cu) when the shapes allow it
         # (B <= 64, S <= 96, int8 weights); otherwise, and for the step a fault is injected in, the per-op kernels are used
+        # decoder: "cluster" = csrc/ot_cdecoder.cu (8-CTA clusters, DSMEM exchanges; any B), "grid" = csrc/ot_decoder.cu (grid barriers, B <= 64)
         self.persistent = persistent
+        self.decoder = decoder
+        self.sentences_per_cluster = sentences_per_cluster
         self.persistent_steps = 0
         # measurement hook (bench.py): when a list, greedy_decode appends a (start, end) CUDA-event pair around every
         # persistent-decoder launch, recorded on the launching stream
@@ -310,7 +314,11 @@ class QuantizedTransformer:
 
     def _decoder_plan(self, ws: dict, B: int, S: int, trace: bool = False):
         """The persistent decoder's plan for this workspace (built once), or None when the shapes / weights rule it out."""
-        if not self.persistent or self.weight_bits != 8 or B > 64 or S > 96 or self.max_len > 96 or self.n_layers > 8:
+        if not self.persistent or self.weight_bits != 8 or S > 96 or self.max_len > 96 or self.n_layers > 8:
+            return None
+        if self.decoder == "cluster":
+            return self._cluster_plan(ws, B, S, trace)
+        if B > 64:
             return None
         plan = ws.get("plan")
         if plan is None or (trace and plan.trace is None):
@@ -337,6 +345,31 @@ class QuantizedTransformer:
                    ws["mask"], self.dec_norm[0], self.dec_norm[1], extra["houtT"], self._gen_wt, self.gen_b, extra["gen_pv"], extra["gen_pi"],
                    self.tgt_lut, self.pe]
             plan = K.DecoderPlan(layers, wst, n_layers=self.n_layers, B=B, S=S, cap=self.max_len, vocab=self.vocab, ys=ws["ys"], trace=trace)
+            ws["plan"] = plan
+        return plan
+
+    def _cluster_plan(self, ws: dict, B: int, S: int, trace: bool = False):
+        """Plan of the cluster-resident decoder (csrc/ot_cdecoder.cu) for this workspace."""
+        n_tiles = (self.vocab + 31) // 32
+        if n_tiles > 192:
+            return None
+        plan = ws.get("plan")
+        if plan is None or (trace and plan.trace is None):
+            layers = []
+            for l, L in enumerate(self.dec):
+                row = [L["ln1"][0], L["ln1"][1], L["ln2"][0], L["ln2"][1], L["ln3"][0], L["ln3"][1]]
+                for name in ("qkv", "o", "cq", "co", "w1", "w2"):
+                    row += [L[name].wq, L[name].sw, L[name].bias]
+                row += [ws["kc"][l], ws["vc"][l], ws["skc"][l], ws["svc"][l]]
+                layers.append(row)
+            if getattr(self, "_gen_w4", None) is None:
+                # generator weight re-laid out once: [tile of 32 entries][k / 4][entry][4 consecutive k] (zero rows past the vocabulary)
+                wpad = torch.zeros((n_tiles * 32, D), dtype=torch.float32, device=self.dev)
+                wpad[: self.vocab] = self.gen_w
+                self._gen_w4 = wpad.reshape(n_tiles, 32, D // 4, 4).permute(0, 2, 1, 3).contiguous()
+            wst = [ws["ckv"], ws["sckv"], ws["mask"], self.dec_norm[0], self.dec_norm[1], self._gen_w4, self.gen_b, self.tgt_lut, self.pe]
+            plan = K.ClusterDecoderPlan(layers, wst, n_layers=self.n_layers, B=B, S=S, cap=self.max_len, vocab=self.vocab, ys=ws["ys"],
+                                        spc=self.sentences_per_cluster, trace=trace)
             ws["plan"] = plan
         return plan
 

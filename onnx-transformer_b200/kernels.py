@@ -287,6 +287,47 @@ class DecoderPlan:
         _lib.check(rc, "ot_decoder_run")
 
 
+class ClusterDecoderPlan:
+    """Device-resident plan of the cluster-resident greedy decoder (ot_cdecoder_plan_build): groups of `spc` sentences, one
+    8-CTA cluster each.  Keeps every tensor it points to alive."""
+
+    PHASES = ["qkv", "self_attn", "o", "ln2", "cq", "cross_attn", "co", "ln3", "ffn1", "ffn1_quant", "ffn2", "ln1"]
+
+    def __init__(self, layers, ws_tensors, *, n_layers: int, B: int, S: int, cap: int, vocab: int, ys: torch.Tensor, spc: int = 8,
+                 trace: bool = False):
+        lib = _lib.load()
+        dev = ys.device
+        self.keep = (layers, ws_tensors)
+        self.B, self.spc, self.n_layers = B, spc, n_layers
+        self.buf = torch.zeros(lib.ot_cdecoder_plan_size() + 256, dtype=torch.uint8, device=dev)
+        self.trace = torch.zeros(256, dtype=torch.int64, device=dev) if trace else None
+        flat_l = [t for layer in layers for t in layer]
+        assert len(flat_l) == 28 * n_layers
+        ws_all = list(ws_tensors) + [ys, self.trace, None]
+        assert len(ws_all) == 12
+        for t in flat_l + ws_all:
+            if t is not None and not t.is_contiguous() and t.dim() > 1 and t.stride(-1) != 1:
+                raise OtError("decoder plan tensors must be row-major")
+        lp = (C.c_void_p * len(flat_l))(*[t.data_ptr() for t in flat_l])
+        wp = (C.c_void_p * 12)(*[(t.data_ptr() if t is not None else None) for t in ws_all])
+        base = (self.buf.data_ptr() + 255) & ~255
+        self.ptr = C.c_void_p(base)
+        rc = lib.ot_cdecoder_plan_build(self.ptr, n_layers, B, S, cap, vocab, spc, ys.stride(0), lp, wp)
+        _lib.check(rc, "ot_cdecoder_plan_build")
+
+    def run(self, t0: int, n_steps: int):
+        rc = _lib.load().ot_cdecoder_run(self.ptr, self.B, self.spc, int(t0), int(n_steps), _stream())
+        _lib.check(rc, "ot_cdecoder_run")
+
+    def phase_names(self):
+        """Names of the barrier.cluster intervals of one greedy step, in trace order."""
+        names = ["ln1"]                     # embedding + positional encoding + LayerNorm 1 of layer 0
+        for _ in range(self.n_layers):
+            names += self.PHASES          # ... the last one is LayerNorm 1 of the NEXT layer
+        names[-1] = "final_norm"
+        return names + ["generator"]
+
+
 # ------------------------------------------------------------------------------------------------ elementwise family
 def _shape4(shape):
     shape = tuple(int(x) for x in shape)

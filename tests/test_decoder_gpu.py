@@ -1,4 +1,5 @@
-"""The persistent greedy decoder (csrc/ot_decoder.cu: all steps in ONE kernel, phases separated by grid barriers) against
+"""The persistent greedy decoders -- csrc/ot_cdecoder.cu ("cluster": 8-CTA clusters exchanging rows / column slices through
+distributed shared memory) and csrc/ot_decoder.cu ("grid": phases separated by grid barriers), all steps in ONE kernel -- against
 the per-op kernel path (CUDA-graph replay / eager) of the same engine and against the numpy oracle.  The two device paths
 execute the same arithmetic instruction for instruction, so tokens AND KV caches must be bit-identical; against the oracle
 tokens are identical wherever the top-2 logit margin allows (tolerance class of the float reductions)."""
@@ -12,10 +13,13 @@ from oracle import model as om
 pytestmark = pytest.mark.gpu
 
 
-def _engines(seed, n_layers, src_vocab, tgt_vocab, max_len):
+DECODERS = ["cluster", "grid"]
+
+
+def _engines(seed, n_layers, src_vocab, tgt_vocab, max_len, decoder="cluster", spc=8):
     from onnx_transformer_b200.engine import QuantizedTransformer
     fw = W.init_float_weights(seed, src_vocab, tgt_vocab, n_layers, randomize_norms=True)
-    return fw, QuantizedTransformer(fw, n_layers=n_layers, max_len=max_len, persistent=True), \
+    return fw, QuantizedTransformer(fw, n_layers=n_layers, max_len=max_len, persistent=True, decoder=decoder, sentences_per_cluster=spc), \
         QuantizedTransformer(fw, n_layers=n_layers, max_len=max_len, persistent=False)
 
 
@@ -34,9 +38,10 @@ def _assert_same_state(ep, eg, ys_p, ys_g, B, S, steps):
             assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("decoder", DECODERS)
 @pytest.mark.parametrize("B,S,min_len", [(3, 11, 5), (1, 4, 0), (7, 33, 9)])
-def test_persistent_decoder_bit_identical_to_per_op_path_small(B, S, min_len):
-    fw, ep, eg = _engines(1, 2, 211, 197, 9)
+def test_persistent_decoder_bit_identical_to_per_op_path_small(B, S, min_len, decoder):
+    fw, ep, eg = _engines(1, 2, 211, 197, 9, decoder)
     ids, mask = W.synthetic_tokens(B + S, B, S, 211, min_len=min_len)
     idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
     ys_p = ep.greedy_decode(idt, mt, 9)
@@ -56,9 +61,22 @@ def test_persistent_decoder_bit_identical_to_per_op_path_small(B, S, min_len):
                 break
 
 
-def test_persistent_decoder_full_size_batch64():
+@pytest.mark.parametrize("B,spc", [(13, 5), (9, 8), (20, 3)])
+def test_cluster_decoder_sentence_groups(B, spc):
+    """Several clusters, a ragged last group, fewer than 8 sentences per cluster."""
+    fw, ep, eg = _engines(2, 2, 211, 197, 10, "cluster", spc)
+    ids, mask = W.synthetic_tokens(B, B, 17, 211, min_len=3)
+    idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    ys_p = ep.greedy_decode(idt, mt, 10)
+    ys_g = eg.greedy_decode(idt, mt, 10)
+    assert ep.persistent_steps == 9
+    _assert_same_state(ep, eg, ys_p, ys_g, B, 17, 9)
+
+
+@pytest.mark.parametrize("decoder", DECODERS)
+def test_persistent_decoder_full_size_batch64(decoder):
     """BASELINE config #2 shape: Transformer-base, 64 sentences x 64 source tokens, 71 greedy steps."""
-    fw, ep, eg = _engines(0, 6, W.SRC_VOCAB, W.TGT_VOCAB, W.MAX_LEN)
+    fw, ep, eg = _engines(0, 6, W.SRC_VOCAB, W.TGT_VOCAB, W.MAX_LEN, decoder)
     ids, mask = W.synthetic_tokens(1000, 64, 64)
     idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
     ys_p = ep.greedy_decode(idt, mt)
@@ -72,10 +90,11 @@ def test_persistent_decoder_full_size_batch64():
     assert torch.equal(ep.greedy_decode(i2, m2), eg.greedy_decode(i2, m2))
 
 
-def test_persistent_decoder_with_an_injected_step():
+@pytest.mark.parametrize("decoder", DECODERS)
+def test_persistent_decoder_with_an_injected_step(decoder):
     """A fault step runs through the per-op kernels between two persistent launches: same result as the all-per-op run."""
     from onnx_transformer_b200.engine import FaultSpec
-    fw, ep, eg = _engines(3, 2, 211, 197, 12)
+    fw, ep, eg = _engines(3, 2, 211, 197, 12, decoder)
     ids, mask = W.synthetic_tokens(3, 4, 10, 211, min_len=4)
     idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
     golden = ep.greedy_decode(idt, mt, 12)

@@ -29,7 +29,9 @@ def timeit(eng, reps=5):
     return e0.elapsed_time(e1) / reps, ys
 
 
-ep = QuantizedTransformer(fw, persistent=True)
+DEC = "grid" if "--grid" in sys.argv else "cluster"
+SPC = int(os.environ.get("OT_SPC", "8"))
+ep = QuantizedTransformer(fw, persistent=True, decoder=DEC, sentences_per_cluster=SPC)
 ms_p, ys_p = timeit(ep)
 print("persistent: %.2f ms/decode  %.0f tok/s" % (ms_p, B * 71 / ms_p * 1e3), flush=True)
 if "--no-graph" not in sys.argv:
@@ -48,10 +50,13 @@ e1.record()
 torch.cuda.synchronize()
 print("10 steps in one launch: %.1f us/step" % (e0.elapsed_time(e1) * 100))
 t = plan.trace.cpu().numpy()
-names = []
-for l in range(6):
-    names += ["ln1", "qkv", "sattn", "o", "ln2", "cq", "cattn", "co", "ln3", "ffn1a", "ffn1b", "ffn2"]
-names += ["lnf", "gen"]
+if DEC == "cluster":
+    names = plan.phase_names()
+else:
+    names = []
+    for l in range(6):
+        names += ["ln1", "qkv", "sattn", "o", "ln2", "cq", "cattn", "co", "ln3", "ffn1a", "ffn1b", "ffn2"]
+    names += ["lnf", "gen"]
 prev = t[255]
 work, wait = {}, {}
 for i, n in enumerate(names):
@@ -62,3 +67,13 @@ print("phase   n   work_us(CTA0)  barrier_wait_us   sum_us")
 for n in work:
     print("%-6s x%d   %7.2f   %7.2f   %7.1f" % (n, len(work[n]), np.mean(work[n]), np.mean(wait[n]), np.sum(work[n]) + np.sum(wait[n])))
 print("step total %.1f us" % ((t[2 * len(names) - 1] - t[255]) / 1e3))
+if DEC == "cluster":
+    print("fine marks of layer 2 (id: us since step start, delta):")
+    prev = None
+    for i in range(150, 250):
+        v = int(t[i])
+        if v == 0:
+            break
+        mid, ns = v >> 32, v & 0xffffffff
+        print("  %3d  %9.2f  %+7.2f" % (mid, ns / 1e3, 0.0 if prev is None else (ns - prev) / 1e3))
+        prev = ns
