@@ -44,20 +44,21 @@ constexpr int kThreads = 256;
 constexpr int kIssuer = 224;        // warp 7, lane 0: MMA issuer
 constexpr int kLoader = 192;        // warp 6, lane 0: TMA producer of the weight ring.  NOT in the issuer's warp: a blocked
                                     // mbarrier.try_wait of one lane stalls the divergent lanes of its warp (measured: 0.5 us per chunk)
-constexpr int kSlots = 6;
-constexpr int kSlotBytes = 16384;   // 128 weight rows x 128 B (one k-block)
-constexpr int kChunks = 44;         // weight chunks per layer per CTA
+constexpr int kSlots = 3;
+constexpr int kSlotBytes = 32768;   // up to 256 weight rows x 128 B (one k-block), or 64 rows x 4 k-blocks
+constexpr int kChunks = 15;         // weight chunks per layer per CTA
 constexpr int kMaxLayers = 8;
 constexpr int kKsPitch = kD + 16;
 constexpr int kMaxKeys = 32 * kDecKeysPerLane;   // 96
 constexpr int kGenVT = 32;          // vocabulary entries per generator tile
+constexpr int kTmemCols = 256;      // accumulator: lanes 0..7 = sentences, columns = the CTA's output features of the GEMM (<= 256)
 
 // shared-memory map (dynamic, base aligned to 1024)
 constexpr int kSmRing = 0;                                  // weight ring
 constexpr int kSmBx = kSmRing + kSlots * kSlotBytes;        // 98304: activation operand, K = 512: [4 k-blocks][16 rows][128 B]
 constexpr int kSmKs = kSmBx + 4 * 2048;                     // 106496: attention K rows [96][528]; aliased by the K = 2048 operand (32 KB)
 constexpr int kSmBh = kSmKs;
-constexpr int kSmVh = kSmKs + 51200;                        // 157696: attention V slices [8][96][64]; aliased by the generator input [8][512] fp32
+constexpr int kSmVh = kSmKs + 51200;                        // 157696: attention V rows [96][512]; aliased by the generator input [8][512] fp32
 constexpr int kSmHb = kSmVh;
 constexpr int kSmRecv = kSmVh + kHeads * kMaxKeys * kDk;    // 206848: fp32 row scattered by the GEMM epilogues (<= 2048 floats)
 constexpr int kSmX = kSmRecv + 8192;                        // 215040: residual row x of my sentence (512 floats)
@@ -71,6 +72,7 @@ static_assert(kSmTotal + 1024 <= 232448, "shared memory budget");
 
 // misc region (floats unless noted)
 constexpr int kMiSB = 0;        // [8] scale of each sentence's current operand row
+constexpr int kMiTok = 12;      // int: the token my sentence feeds this step
 constexpr int kMiRed = 16;      // [64] reduction scratch
 constexpr int kMiGenV = 80;     // [8 ranks][8 sentences]: best logit of rank's vocabulary slice  (written by peers)
 constexpr int kMiGenI = 144;    // [8][8] int: its index
@@ -114,14 +116,14 @@ struct Ctx {
   uint32_t tmem;
   int rank, n_own, b;    // cluster rank, sentences of this cluster, my sentence (or -1)
   uint32_t pn, cn, total;   // weight chunks issued / consumed / to do (issuer thread only)
-  uint32_t acc_parity;
+  uint32_t acc_parity, kv_parity;
   int trace_slot;
   bool trace_on;
   bool fine;                       // intra-phase marks of one layer (profiling aid, trace slots 150..249)
   int mark_slot;
   unsigned long long t_step;
 };
-constexpr int kBarEmpty = kSlots, kBarAcc = 2 * kSlots;
+constexpr int kBarEmpty = kSlots, kBarAcc = 2 * kSlots, kBarKv = 2 * kSlots + 1;
 
 // profiling aid: (id << 32 | ns since the step began) into trace[150 + n]
 __device__ __forceinline__ void mark(Ctx& c, int id) {
@@ -140,6 +142,11 @@ __device__ __forceinline__ void st_cluster_b32(uint32_t addr, uint32_t v) {
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit (async proxy), completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -169,18 +176,23 @@ __device__ __forceinline__ void csync(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------------ weight ring
-struct Chunk { int g, row0, rows, kb; };
+// A measured property of tcgen05.mma shapes this layout is built on: an instruction costs about as long as its M-side operand
+// takes to read (~1 cycle per row) however small N is, so the many weight rows go on the N side (up to 256 per instruction)
+// and the 8 sentences on the M side (M = 64, the smallest).  Chunk = what one ring slot holds:
+//   qkv  (192 rows / CTA): 4 chunks = k-blocks, 3 boxes of 64 rows        o, cq, co (64 rows): 1 chunk = 4 k-blocks (4 boxes)
+//   ffn1 (256 rows / CTA): 4 chunks = k-blocks, 4 boxes of 64 rows        ffn2 (64 rows, K = 2048): 4 chunks of 4 k-blocks
+struct Chunk { int g, kb0, boxes; bool by_rows; };
 __device__ __forceinline__ Chunk chunk_of(int j) {
   Chunk k;
-  if (j < 8) { k.g = 0; k.row0 = (j < 4) ? 0 : 128; k.rows = (j < 4) ? 128 : 64; k.kb = j & 3; }
-  else if (j < 20) { k.g = 1 + ((j - 8) >> 2); k.row0 = 0; k.rows = 64; k.kb = j & 3; }
-  else if (j < 28) { k.g = 4; k.row0 = (j < 24) ? 0 : 128; k.rows = 128; k.kb = j & 3; }
-  else { k.g = 5; k.row0 = 0; k.rows = 64; k.kb = j - 28; }
+  if (j < 4) { k.g = 0; k.kb0 = j; k.boxes = 3; k.by_rows = true; }
+  else if (j < 7) { k.g = j - 3; k.kb0 = 0; k.boxes = 4; k.by_rows = false; }
+  else if (j < 11) { k.g = 4; k.kb0 = j - 7; k.boxes = 4; k.by_rows = true; }
+  else { k.g = 5; k.kb0 = 4 * (j - 11); k.boxes = 4; k.by_rows = false; }
   return k;
 }
 __device__ __forceinline__ int slice_rows(int g) { return g == 0 ? 192 : (g == 4 ? 256 : 64); }
 
-// issuer thread: load weight chunk c.pn into its ring slot (the slot must be free)
+// loader thread: load weight chunk c.pn into its ring slot (the slot must be free)
 __device__ __forceinline__ void issue_chunk(Ctx& c) {
   const uint32_t n = c.pn;
   const int slot = n % kSlots;
@@ -189,10 +201,10 @@ __device__ __forceinline__ void issue_chunk(Ctx& c) {
   const CUtensorMap* map = &c.G->map_w[l][k.g];
   const uint32_t fb = smem_u32(&c.bars[slot]);
   const uint32_t dst = smem_u32(c.smem + kSmRing + slot * kSlotBytes);
-  const int r0 = slice_rows(k.g) * c.rank + k.row0;
-  mbar_arrive_expect_tx(fb, k.rows * 128);
-  tma_load_2d(dst, map, fb, k.kb * 128, r0);
-  if (k.rows == 128) tma_load_2d(dst + 8192, map, fb, k.kb * 128, r0 + 64);
+  const int r0 = slice_rows(k.g) * c.rank;
+  mbar_arrive_expect_tx(fb, k.boxes * 8192);
+  for (int i = 0; i < k.boxes; ++i)
+    tma_load_2d(dst + i * 8192, map, fb, (k.by_rows ? k.kb0 : k.kb0 + i) * 128, k.by_rows ? r0 + 64 * i : r0);
   ++c.pn;
 }
 // loader thread: issue every chunk below `upto` (blocking on the ring slot of each: chunk n reuses the slot of chunk n - kSlots,
@@ -207,60 +219,98 @@ __device__ __forceinline__ void fill_until(Ctx& c, uint32_t upto) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM phase
-// g: 0 qkv, 1 o, 2 cq, 3 co, 4 w1 (ReLU), 5 w2.  D[f][s] = sum_k W[f][k] * a[s][k]; then scatter y[s][f] to the owner of s.
+// g: 0 qkv, 1 o, 2 cq, 3 co, 4 w1 (ReLU), 5 w2.  D[s][f] = sum_k a[s][k] * W[f][k] (rows s >= 8 of the M = 64 tile are whatever
+// follows the 8 operand rows in shared memory: never read back); then scatter y[s][f] to the owner of sentence s.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+
 __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) {
   const CdHot& P = *c.P;
   const CdLayer& L = P.layer[l];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = slice_rows(g);
-  const int nkb = (g == 5) ? 16 : 4;
-  const int tile = warp >> 2;
-  const int fl = 128 * tile + 32 * (warp & 3) + lane;
-  const bool act = (128 * tile + 32 * (warp & 3)) < rows;     // warp-uniform
-  const int f = rows * c.rank + fl;
-  float sw = 0.f, bb = 0.f;
   mark(c, 10 + g);
-  if (act) { sw = __ldg(L.sw[g] + f); bb = __ldg(L.bias[g] + f); }
+  // epilogue threads: warps 0 and 4 (the two that may read TMEM lanes 0..31), each half of the columns in groups of 32;
+  // 16x256b fragment: thread t holds sentence t/4, features 8*i + 2*(t%4) + {0,1} of every 8-column block i
+  const bool epi = (warp & 3) == 0;
+  const int half = rows >> 1;                       // 96 / 32 / 128 columns per warp
+  const int col0 = (warp >> 2) * half;
+  const int ngroups = half >> 5;                    // 3 / 1 / 4
+  const int srow = lane >> 2;
+  float2 sw[16], bb[16];
+  if (epi) {
+    const float* swp = L.sw[g] + rows * c.rank + col0 + 2 * (lane & 3);
+    const float* bp = L.bias[g] + rows * c.rank + col0 + 2 * (lane & 3);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < 4 * ngroups) {
+        sw[i] = __ldg(reinterpret_cast<const float2*>(swp + 8 * i));
+        bb[i] = __ldg(reinterpret_cast<const float2*>(bp + 8 * i));
+      }
+    }
+  }
   if (tid == kIssuer) {
-    const uint32_t bbase = smem_u32(c.smem + (g == 5 ? kSmBh : kSmBx));
-    constexpr uint32_t idesc = make_idesc_i8(128, 16);
-    const int ntile = (rows + 127) >> 7;
-    for (int t = 0; t < ntile; ++t) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int slot = c.cn % kSlots;
-        mbar_wait(smem_u32(&c.bars[slot]), (c.cn / kSlots) & 1);
-        tc_fence_after();
-        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(c.smem + kSmRing + slot * kSlotBytes));
-        const uint64_t b_desc = make_smem_desc_sw128(bbase + kb * 2048);
+    const uint32_t abase = smem_u32(c.smem + (g == 5 ? kSmBh : kSmBx));
+    const uint32_t idesc = make_idesc_i8(64, rows);
+    const bool by_rows = (g == 0 || g == 4);
+    const int nchunks = (g >= 1 && g <= 3) ? 1 : 4;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int slot = c.cn % kSlots;
+      mbar_wait(smem_u32(&c.bars[slot]), (c.cn / kSlots) & 1);
+      tc_fence_after();
+      const uint32_t sbase = smem_u32(c.smem + kSmRing + slot * kSlotBytes);
+      const int nkb = by_rows ? 1 : 4;              // k-blocks held by this chunk
+#pragma unroll 1
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = by_rows ? ch : 4 * ch + i;
+        const uint64_t a_desc = make_smem_desc_sw128(abase + kb * 2048);
+        const uint64_t b_desc = make_smem_desc_sw128(sbase + i * 8192);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          mma_i8_ss(c.tmem + 16 * t, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-        mma_commit(smem_u32(&c.bars[kBarEmpty + slot]));
-        ++c.cn;
+          mma_i8_ss(c.tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
       }
+      mma_commit(smem_u32(&c.bars[kBarEmpty + slot]));
+      ++c.cn;
     }
     mma_commit(smem_u32(&c.bars[kBarAcc]));
   } else if (tid == kLoader) {
     // keep the ring full while this GEMM drains it: by the time its last MMA has completed the next kSlots chunks (the start of
-    // the next GEMM) are in flight, so the ring runs ahead of the dependency chain
+    // the next GEMMs) are in flight, so the ring runs ahead of the dependency chain
     fill_until(c, gend + kSlots);
   }
   __syncwarp();
-  if (act) {
+  if (epi) {
     mbar_wait(smem_u32(&c.bars[kBarAcc]), c.acc_parity);
     tc_fence_after();
     mark(c, 20 + g);
-    uint32_t r[8];
-    tmem_ld_32x8(c.tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + 16 * tile, r);
-    tmem_wait_ld();
-    const float* sB = misc(c) + kMiSB;
-    const uint32_t recv = smem_u32(c.smem + kSmRecv) + 4u * static_cast<uint32_t>(f);
+    const float sx = (misc(c) + kMiSB)[srow];
+    const uint32_t recv = mapa_shared(smem_u32(c.smem + kSmRecv) + 4u * static_cast<uint32_t>(rows * c.rank + col0 + 2 * (lane & 3)), srow);
 #pragma unroll
-    for (int s = 0; s < kCS; ++s) {
-      if (s < c.n_own) {
-        float y = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[s])), sB[s]), sw), bb);
-        if (g == 4) y = fmaxf(y, 0.0f);
-        st_cluster_b32(mapa_shared(recv, s), __float_as_uint(y));
+    for (int gq = 0; gq < 4; ++gq) {
+      if (gq < ngroups) {
+        uint32_t r[16];
+        tmem_ld_16x256b_x4(c.tmem + col0 + 32 * gq, r);
+        tmem_wait_ld();
+        if (srow < c.n_own) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 w2 = sw[4 * gq + i], b2 = bb[4 * gq + i];
+            float y0 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i])), sx), w2.x), b2.x);
+            float y1 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i + 1])), sx), w2.y), b2.y);
+            if (g == 4) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
+            st_cluster_v2(recv + 4u * static_cast<uint32_t>(32 * gq + 8 * i), y0, y1);
+          }
+        }
       }
     }
   }
@@ -288,6 +338,12 @@ __device__ __forceinline__ void push_row_q8(Ctx& c, const uint8_t* src, int K, i
 // ------------------------------------------------------------------------------------------------ row phases (owner CTA)
 // LayerNorm of my sentence.  SRC 0: x = embedding(token)*sqrt(d) + pe[t]; SRC 1: x = x + recv (the scattered O / CO / FFN2 row).
 // quant: RowQuant -> all-gather into Bx; else (final norm) the fp32 row goes to every CTA's generator input.
+__device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// The row is spread over 4 warps -- warp i holds float4 i*32+lane, exactly the element layernorm_row<4> gives lane `lane` in its
+// i-th register -- and every reduction is evaluated in layernorm_row's order: per lane ((p0 + p1) + p2) + p3 over the four
+// registers, then the xor-shuffle tree over lanes.  Same instructions on the same operands => bit-identical results, at a quarter
+// of the dependent-division chain (a single warp spends 2.2 us per row in IEEE divisions).
 __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, const float* gamma, const float* beta, bool quant) {
   const CdHot& P = *c.P;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -295,40 +351,54 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
   uint8_t* rowq = c.smem + kSmRow;
   float* yrow = reinterpret_cast<float*>(c.smem + kSmCtx);
   float* red = misc(c) + kMiRed;
+  float* part = reinterpret_cast<float*>(c.smem + kSmRow + 1024);    // [2][4][32] partial sums (the staging row only uses its first 512 B here)
   mark(c, 40);
-  if (c.b >= 0 && warp == 0) {
-    float4 v[4];
+  if (c.b >= 0 && warp < 4) {
+    const int i4 = warp * 32 + lane;
+    float4 v;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i4);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + i4);
     if (SRC == 0) {
-      const float4* e4 = reinterpret_cast<const float4*>(P.tgt_lut + token * kD);
-      const float4* p4 = reinterpret_cast<const float4*>(P.pe + static_cast<int64_t>(t) * kD);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 e = __ldg(e4 + i * 32 + lane), q = __ldg(p4 + i * 32 + lane);
-        v[i] = make_float4(__fadd_rn(__fmul_rn(e.x, P.emb_scale), q.x), __fadd_rn(__fmul_rn(e.y, P.emb_scale), q.y),
-                           __fadd_rn(__fmul_rn(e.z, P.emb_scale), q.z), __fadd_rn(__fmul_rn(e.w, P.emb_scale), q.w));
-      }
+      const float4 e = __ldg(reinterpret_cast<const float4*>(P.tgt_lut + token * kD) + i4);
+      const float4 q = __ldg(reinterpret_cast<const float4*>(P.pe + static_cast<int64_t>(t) * kD) + i4);
+      v = make_float4(__fadd_rn(__fmul_rn(e.x, P.emb_scale), q.x), __fadd_rn(__fmul_rn(e.y, P.emb_scale), q.y),
+                      __fadd_rn(__fmul_rn(e.z, P.emb_scale), q.z), __fadd_rn(__fmul_rn(e.w, P.emb_scale), q.w));
     } else {
-      const float4* y4 = reinterpret_cast<const float4*>(c.smem + kSmRecv);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 res = reinterpret_cast<const float4*>(xr)[i * 32 + lane], y = y4[i * 32 + lane];
-        v[i] = make_float4(__fadd_rn(res.x, y.x), __fadd_rn(res.y, y.y), __fadd_rn(res.z, y.z), __fadd_rn(res.w, y.w));
-      }
+      const float4 res = reinterpret_cast<const float4*>(xr)[i4], y = reinterpret_cast<const float4*>(c.smem + kSmRecv)[i4];
+      v = make_float4(__fadd_rn(res.x, y.x), __fadd_rn(res.y, y.y), __fadd_rn(res.z, y.z), __fadd_rn(res.w, y.w));
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(xr)[i * 32 + lane] = v[i];
+    reinterpret_cast<float4*>(xr)[i4] = v;
     mark(c, 41);
-    const float amax = layernorm_row<4>(v, lane, kD, gamma, beta, 1e-6f);
+    const float nf = static_cast<float>(kD);
+    part[warp * 32 + lane] = (v.x + v.y) + (v.z + v.w);
+    bar_sync_128();
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sum += part[i * 32 + lane];
+    const float mu = __fdiv_rn(warp_sum(sum), nf);
+    v.x = __fsub_rn(v.x, mu); v.y = __fsub_rn(v.y, mu); v.z = __fsub_rn(v.z, mu); v.w = __fsub_rn(v.w, mu);
+    part[128 + warp * 32 + lane] = (__fmul_rn(v.x, v.x) + __fmul_rn(v.y, v.y)) + (__fmul_rn(v.z, v.z) + __fmul_rn(v.w, v.w));
+    bar_sync_128();
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sq += part[128 + i * 32 + lane];
+    float var = __fdiv_rn(warp_sum(sq), nf);
+    var = __fdiv_rn(__fmul_rn(var, nf), nf - 1.0f);
+    const float denom = __fadd_rn(__fsqrt_rn(var), 1e-6f);
+    v.x = __fadd_rn(__fdiv_rn(__fmul_rn(g.x, v.x), denom), be.x);
+    v.y = __fadd_rn(__fdiv_rn(__fmul_rn(g.y, v.y), denom), be.y);
+    v.z = __fadd_rn(__fdiv_rn(__fmul_rn(g.z, v.z), denom), be.z);
+    v.w = __fadd_rn(__fdiv_rn(__fmul_rn(g.w, v.w), denom), be.w);
     mark(c, 42);
     if (quant) {
-      const float s = quant_scale(warp_max(amax));
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        reinterpret_cast<uint32_t*>(rowq)[i * 32 + lane] = pack4(quant_one(v[i].x, s), quant_one(v[i].y, s), quant_one(v[i].z, s), quant_one(v[i].w, s));
-      if (lane == 0) red[0] = s;
+      const float am = warp_max(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      if (lane == 0) red[32 + warp] = am;
+      bar_sync_128();
+      const float s = quant_scale(fmaxf(fmaxf(red[32], red[33]), fmaxf(red[34], red[35])));
+      reinterpret_cast<uint32_t*>(rowq)[i4] = pack4(quant_one(v.x, s), quant_one(v.y, s), quant_one(v.z, s), quant_one(v.w, s));
+      if (tid == 0) red[0] = s;
     } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(yrow)[i * 32 + lane] = v[i];
+      reinterpret_cast<float4*>(yrow)[i4] = v;
     }
   }
   mark(c, 43);
@@ -378,21 +448,20 @@ struct AttnPre {
   float skl[kDecKeysPerLane], svl[kDecKeysPerLane];
   uint8_t keepl[kDecKeysPerLane];
 };
-// Issued during the preceding GEMM phase: the old K/V rows of my sentence into shared memory (cp.async) and, per lane, the
+// Issued during the preceding GEMM phase: the old K/V rows of my sentence into shared memory (bulk copies) and, per lane, the
 // scales / mask of its keys j = 32*kk + lane.
 __device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* k, const int8_t* v, int64_t ldk, int64_t row0, const float* sk,
                                               const float* sv, int64_t sstride, const uint8_t* key_mask, int mask_stride, AttnPre& pre) {
-  int8_t* Ks = reinterpret_cast<int8_t*>(c.smem + kSmKs);
-  int8_t* Vh = reinterpret_cast<int8_t*>(c.smem + kSmVh);
-  if (threadIdx.x < 192) {      // warps 6 / 7 go straight to the weight ring / the MMAs
-    for (int idx = threadIdx.x; idx < n_old * 32; idx += 192) {
-      const int j = idx >> 5, ch = idx & 31;
-      const int64_t src = (row0 + j) * ldk + ch * 16;
-      cp_async16(smem_u32(Ks + j * kKsPitch + ch * 16), k + src);
-      cp_async16(smem_u32(Vh + ((ch >> 2) * kMaxKeys + j) * kDk + (ch & 3) * 16), v + src);
-    }
+  // one 512-byte bulk copy per K row and per V row: the copies run in the TMA unit, so neither the issuing threads nor the
+  // release fence of the next barrier.cluster wait for them (cp.async copies did: +0.7 us on every GEMM-phase barrier)
+  const uint32_t bar = smem_u32(&c.bars[kBarKv]);
+  if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(n_old) * 2u * kD);
+  if (static_cast<int>(threadIdx.x) < 2 * n_old) {
+    const int j = threadIdx.x >> 1;
+    const int64_t src = (row0 + j) * ldk;
+    if (threadIdx.x & 1) bulk_load(smem_u32(c.smem + kSmVh + j * kD), v + src, kD, bar);
+    else bulk_load(smem_u32(c.smem + kSmKs + j * kKsPitch), k + src, kD, bar);
   }
-  cp_async_commit();
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
@@ -451,8 +520,7 @@ __device__ __forceinline__ void attention_smem(Ctx& c, int Tk, int q_pos0, int m
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int8_t* rowbuf = reinterpret_cast<const int8_t*>(c.smem + kSmRow);
   const int8_t* Ks = reinterpret_cast<const int8_t*>(c.smem + kSmKs);
-  AttnDecVh Vh = reinterpret_cast<AttnDecVh>(c.smem + kSmVh);
-  float* ctx = reinterpret_cast<float*>(c.smem + kSmCtx);
+  const int8_t* Vs = reinterpret_cast<const int8_t*>(c.smem + kSmVh);      // [key][512]
   float* red = misc(c) + kMiRed;
   uint32_t qw[16];
   {
@@ -513,34 +581,24 @@ __device__ __forceinline__ void attention_smem(Ctx& c, int Tk, int q_pos0, int m
     for (int jj = 0; jj < 32; ++jj) {
       const float ph = __shfl_sync(0xffffffffu, pq[kk], jj);
       const float svj = __shfl_sync(0xffffffffu, svl[kk], jj);
-      const char2 vv = *reinterpret_cast<const char2*>(&Vh[h][kk * 32 + jj][d0]);
+      const char2 vv = *reinterpret_cast<const char2*>(Vs + (kk * 32 + jj) * kD + h * kDk + d0);
       acc0 = fmaf(ph, __fmul_rn(__int2float_rn(vv.x), svj), acc0);
       acc1 = fmaf(ph, __fmul_rn(__int2float_rn(vv.y), svj), acc1);
     }
   }
   mark(c, 56);
-  *reinterpret_cast<float2*>(ctx + h * kDk + d0) = make_float2(acc0, acc1);
+  // RowQuant of the merged context row (all 8 heads): the row abs-max is a max (exact in any order), every lane quantizes its own
+  // two features with the instructions of attention_decode_body
+  const float am = warp_max_f(fmaxf(fabsf(acc0), fabsf(acc1)));
+  if (lane == 0) red[24 + h] = am;
   __syncthreads();
   mark(c, 57);
-  if (h == 0) {
-    float4 v[4];
-    float amax = 0.f;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      v[t] = *reinterpret_cast<const float4*>(ctx + (t * 32 + lane) * 4);
-      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[t].x), fabsf(v[t].y)), fmaxf(fabsf(v[t].z), fabsf(v[t].w))));
-    }
-    const float s = __fdiv_rn(fmaxf(warp_max_f(amax), 1e-5f), 127.0f);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int q0i = __float2int_rn(rintf(__fdiv_rn(v[t].x, s))), q1i = __float2int_rn(rintf(__fdiv_rn(v[t].y, s)));
-      const int q2i = __float2int_rn(rintf(__fdiv_rn(v[t].z, s))), q3i = __float2int_rn(rintf(__fdiv_rn(v[t].w, s)));
-      const uint32_t w = (static_cast<uint32_t>(q0i) & 0xFFu) | ((static_cast<uint32_t>(q1i) & 0xFFu) << 8) |
-                         ((static_cast<uint32_t>(q2i) & 0xFFu) << 16) | ((static_cast<uint32_t>(q3i) & 0xFFu) << 24);
-      *reinterpret_cast<uint32_t*>(c.smem + kSmRow + 1536 + (t * 32 + lane) * 4) = w;
-    }
-    if (lane == 0) red[16] = s;
-  }
+  const float amax = fmaxf(fmaxf(fmaxf(red[24], red[25]), fmaxf(red[26], red[27])), fmaxf(fmaxf(red[28], red[29]), fmaxf(red[30], red[31])));
+  const float s = __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f);
+  const int q0i = __float2int_rn(rintf(__fdiv_rn(acc0, s))), q1i = __float2int_rn(rintf(__fdiv_rn(acc1, s)));
+  *reinterpret_cast<uint16_t*>(c.smem + kSmRow + 1536 + h * kDk + d0) =
+      static_cast<uint16_t>((static_cast<uint32_t>(q0i) & 0xFFu) | ((static_cast<uint32_t>(q1i) & 0xFFu) << 8));
+  if (threadIdx.x == 0) red[16] = s;
   __syncthreads();
 }
 
@@ -551,11 +609,12 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
   const CdLayer& L = P.layer[l];
   if (c.b < 0) return;
   mark(c, 50);
-  cp_async_wait_all();
+  mbar_wait(smem_u32(&c.bars[kBarKv]), c.kv_parity);
+  c.kv_parity ^= 1u;
   float sc[3];
   mark(c, 51);
   quant_groups(c, self ? 3 : 1, sc);
-  mark(c, 52);       // (its barriers also publish the prefetched K/V rows)
+  mark(c, 52);       // 
   if (self) {
     const int tid = threadIdx.x;
     const int8_t* rowbuf = reinterpret_cast<const int8_t*>(c.smem + kSmRow);
@@ -569,7 +628,7 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
     } else if (tid < 64) {
       const int ch = tid - 32;
       const uint4 vv = *reinterpret_cast<const uint4*>(rowbuf + 2 * kD + ch * 16);
-      *reinterpret_cast<uint4*>(Vh + ((ch >> 2) * kMaxKeys + t) * kDk + (ch & 3) * 16) = vv;
+      *reinterpret_cast<uint4*>(Vh + t * kD + ch * 16) = vv;
       *reinterpret_cast<uint4*>(L.vc + dst + ch * 16) = vv;
     } else if (tid == 64) {
       L.skc[static_cast<int64_t>(c.b) * P.cap + t] = sc[1];
@@ -723,11 +782,11 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 7) {
     if (lane == 0) {
-      for (int i = 0; i <= kBarAcc; ++i) mbar_init(smem_u32(&c.bars[i]), 1);
+      for (int i = 0; i <= kBarKv; ++i) mbar_init(smem_u32(&c.bars[i]), 1);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(tmem_slot), 32);
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -743,6 +802,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   c.pn = c.cn = 0;
   c.total = static_cast<uint32_t>(n_steps) * nl * kChunks;
   c.acc_parity = 0;
+  c.kv_parity = 0;
   c.trace_slot = 0;
   c.trace_on = false;
   c.fine = false;
@@ -761,15 +821,19 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
     if (c.trace_on && tid == 0) { c.t_step = tl_now(); P.trace[255] = c.t_step; }
     // ---- token -> embedding + positional encoding -> LayerNorm 1 of layer 0 -> all-gather
     {
-      int64_t token = 0;
+      int* tok = reinterpret_cast<int*>(misc(c) + kMiTok);
       if (c.b >= 0 && warp == 0) {
+        int64_t token;
         if (t > t0) {
           token = generator_pick(c, lane);
           if (lane == 0) P.ys[static_cast<int64_t>(c.b) * P.ys_ld + t] = token;
         } else {
           token = __ldcg(P.ys + static_cast<int64_t>(c.b) * P.ys_ld + t);
         }
+        if (lane == 0) *tok = static_cast<int>(token);
       }
+      __syncthreads();
+      const int64_t token = *tok;
       phase_ln(c, 0, token, t, P.layer[0].ln_g[0], P.layer[0].ln_b[0], true);
       csync(c);
     }
@@ -789,7 +853,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
           }
           // index one past this GEMM's last weight chunk in the launch-wide chunk sequence
           const int g = q >> 1;
-          const uint32_t gend = (static_cast<uint32_t>(t - t0) * nl + l) * kChunks + (g == 0 ? 8 : g == 1 ? 12 : g == 2 ? 16 : g == 3 ? 20 : g == 4 ? 28 : 44);
+          const uint32_t gend = (static_cast<uint32_t>(t - t0) * nl + l) * kChunks + (g == 0 ? 4 : g == 1 ? 5 : g == 2 ? 6 : g == 3 ? 7 : g == 4 ? 11 : 15);
           phase_gemm(c, l, g, gend);
         } else if (q == 1 || q == 5) {
           phase_attention(c, q == 1, t, l, pre);
@@ -817,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   cp_async_wait_all();
   tc_fence_before();
   csync(c);          // no CTA exits while a peer may still address its shared memory
-  if (warp == 7) tmem_dealloc(c.tmem, 32);
+  if (warp == 7) tmem_dealloc(c.tmem, kTmemCols);
 }
 
 }  // namespace cd
