@@ -294,23 +294,34 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
     tc_fence_after();
     mark(c, 20 + g);
     const float sx = (misc(c) + kMiSB)[srow];
-    const uint32_t recv = mapa_shared(smem_u32(c.smem + kSmRecv) + 4u * static_cast<uint32_t>(rows * c.rank + col0 + 2 * (lane & 3)), srow);
+    // y of one 32-column group is staged per warp as [sentence][32 features] (1 KB) and leaves as 16-byte chunks, 128 contiguous
+    // bytes per destination CTA and instruction: 4x fewer DSMEM packets than storing the fragment's float2 pairs directly
+    float* stage = reinterpret_cast<float*>(c.smem + kSmCtx) + (warp >> 2) * 256;
+    const uint32_t recv0 = smem_u32(c.smem + kSmRecv) + 4u * static_cast<uint32_t>(rows * c.rank + col0);
 #pragma unroll
     for (int gq = 0; gq < 4; ++gq) {
       if (gq < ngroups) {
         uint32_t r[16];
         tmem_ld_16x256b_x4(c.tmem + col0 + 32 * gq, r);
         tmem_wait_ld();
-        if (srow < c.n_own) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 w2 = sw[4 * gq + i], b2 = bb[4 * gq + i];
-            float y0 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i])), sx), w2.x), b2.x);
-            float y1 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i + 1])), sx), w2.y), b2.y);
-            if (g == 4) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
-            st_cluster_v2(recv + 4u * static_cast<uint32_t>(32 * gq + 8 * i), y0, y1);
+        for (int i = 0; i < 4; ++i) {
+          const float2 w2 = sw[4 * gq + i], b2 = bb[4 * gq + i];
+          float y0 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i])), sx), w2.x), b2.x);
+          float y1 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i + 1])), sx), w2.y), b2.y);
+          if (g == 4) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
+          *reinterpret_cast<float2*>(stage + srow * 32 + 8 * i + 2 * (lane & 3)) = make_float2(y0, y1);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int id = lane + 32 * j, s = id >> 3, ch = id & 7;     // sentence, 16-byte chunk of its 32 features
+          if (s < c.n_own) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stage + s * 32 + ch * 4);
+            st_cluster_v4(mapa_shared(recv0 + 4u * static_cast<uint32_t>(32 * gq + 4 * ch), s), v);
           }
         }
+        __syncwarp();
       }
     }
   }
@@ -395,7 +406,7 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
       if (lane == 0) red[32 + warp] = am;
       bar_sync_128();
       const float s = quant_scale(fmaxf(fmaxf(red[32], red[33]), fmaxf(red[34], red[35])));
-      reinterpret_cast<uint32_t*>(rowq)[i4] = pack4(quant_one(v.x, s), quant_one(v.y, s), quant_one(v.z, s), quant_one(v.w, s));
+      reinterpret_cast<uint32_t*>(rowq)[i4] = quant4_pack(v, s, __frcp_rn(s));
       if (tid == 0) red[0] = s;
     } else {
       reinterpret_cast<float4*>(yrow)[i4] = v;
@@ -432,9 +443,10 @@ __device__ __forceinline__ void phase_ffnq(Ctx& c) {
     if (lane == 0) red[warp] = am;
     __syncthreads();
     const float s = quant_scale(fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]))));
+    const float r = __frcp_rn(s);
     uint2 w;
-    w.x = pack4(quant_one(a.x, s), quant_one(a.y, s), quant_one(a.z, s), quant_one(a.w, s));
-    w.y = pack4(quant_one(b.x, s), quant_one(b.y, s), quant_one(b.z, s), quant_one(b.w, s));
+    w.x = quant4_pack(a, s, r);
+    w.y = quant4_pack(b, s, r);
     reinterpret_cast<uint2*>(rowq)[tid] = w;
     __syncthreads();
     mark(c, 61);
@@ -454,13 +466,18 @@ __device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* k
                                               const float* sv, int64_t sstride, const uint8_t* key_mask, int mask_stride, AttnPre& pre) {
   // one 512-byte bulk copy per K row and per V row: the copies run in the TMA unit, so neither the issuing threads nor the
   // release fence of the next barrier.cluster wait for them (cp.async copies did: +0.7 us on every GEMM-phase barrier)
+  // Issued by warps 1, 2, 3 and 5: idle during a GEMM phase (0 / 4: epilogue, 6: weight ring, 7: MMA issuer); a warp needs
+  // ~20 ns per bulk-copy instruction, which must not sit in front of the MMAs or the epilogue.
   const uint32_t bar = smem_u32(&c.bars[kBarKv]);
-  if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(n_old) * 2u * kD);
-  if (static_cast<int>(threadIdx.x) < 2 * n_old) {
-    const int j = threadIdx.x >> 1;
-    const int64_t src = (row0 + j) * ldk;
-    if (threadIdx.x & 1) bulk_load(smem_u32(c.smem + kSmVh + j * kD), v + src, kD, bar);
-    else bulk_load(smem_u32(c.smem + kSmKs + j * kKsPitch), k + src, kD, bar);
+  const int w = threadIdx.x >> 5;
+  if (threadIdx.x == 32) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(n_old) * 2u * kD);
+  if (w == 1 || w == 2 || w == 3 || w == 5) {
+    for (int idx = (w == 5 ? 96 : (w - 1) * 32) + (threadIdx.x & 31); idx < 2 * n_old; idx += 128) {
+      const int j = idx >> 1;
+      const int64_t src = (row0 + j) * ldk;
+      if (idx & 1) bulk_load(smem_u32(c.smem + kSmVh + j * kD), v + src, kD, bar);
+      else bulk_load(smem_u32(c.smem + kSmKs + j * kKsPitch), k + src, kD, bar);
+    }
   }
   const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -507,7 +524,7 @@ __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale
     const int i = tid + 256 * j;
     if (i < N / 4) {
       const float s = scale[i >> 7];
-      reinterpret_cast<uint32_t*>(rowbuf)[i] = pack4(quant_one(y[j].x, s), quant_one(y[j].y, s), quant_one(y[j].z, s), quant_one(y[j].w, s));
+      reinterpret_cast<uint32_t*>(rowbuf)[i] = quant4_pack(y[j], s, __frcp_rn(s));
     }
   }
   __syncthreads();
@@ -595,7 +612,8 @@ __device__ __forceinline__ void attention_smem(Ctx& c, int Tk, int q_pos0, int m
   mark(c, 57);
   const float amax = fmaxf(fmaxf(fmaxf(red[24], red[25]), fmaxf(red[26], red[27])), fmaxf(fmaxf(red[28], red[29]), fmaxf(red[30], red[31])));
   const float s = __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f);
-  const int q0i = __float2int_rn(rintf(__fdiv_rn(acc0, s))), q1i = __float2int_rn(rintf(__fdiv_rn(acc1, s)));
+  const uint32_t q01 = quant4_pack(make_float4(acc0, acc1, 0.f, 0.f), s, __frcp_rn(s));
+  const int q0i = static_cast<int>(q01 & 0xFFu), q1i = static_cast<int>((q01 >> 8) & 0xFFu);
   *reinterpret_cast<uint16_t*>(c.smem + kSmRow + 1536 + h * kDk + d0) =
       static_cast<uint16_t>((static_cast<uint32_t>(q0i) & 0xFFu) | ((static_cast<uint32_t>(q1i) & 0xFFu) << 8));
   if (threadIdx.x == 0) red[16] = s;

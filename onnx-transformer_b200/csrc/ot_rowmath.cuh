@@ -19,6 +19,27 @@ __device__ __forceinline__ float warp_max(float v) {
 // RowQuant of quant_linear.py:31-43: s = max(amax, 1e-5) / 127 ; q = rint(x / s).
 __device__ __forceinline__ float quant_scale(float amax) { return __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f); }
 __device__ __forceinline__ int quant_one(float x, float s) { return __float2int_rn(rintf(__fdiv_rn(x, s))); }
+// rint(y / s) with the quotient rounded exactly like IEEE division, without the div.rn expansion (whose special-case path is taken
+// for every zero dividend -- half of a ReLU output -- and whose branch serialises independent elements).  q1 = y*r corrected by
+// one FMA residual step (r = RN(1/s)) is within 1 ulp of RN(y/s); the integer can only differ when q1 sits within 2^-16 of a
+// half-integer (|y/s| <= 127, so 1 ulp <= 2^-17), and exactly then the true division decides (flagged, redone by the caller).
+__device__ __forceinline__ float quant_fast_n(float y, float s, float r, bool& near_half) {
+  const float q0 = __fmul_rn(y, r);
+  const float rem = __fmaf_rn(-q0, s, y);
+  const float q1 = __fmaf_rn(rem, r, q0);
+  const float n = rintf(q1);
+  near_half = near_half || (fabsf(fabsf(q1 - n) - 0.5f) < 1.52587890625e-05f);
+  return n;
+}
+// pack4(quant_one(v.x, s), ...) of four values, same bits as the division form
+__device__ __forceinline__ uint32_t quant4_pack(float4 v, float s, float r) {
+  bool nh = false;
+  int a = __float2int_rn(quant_fast_n(v.x, s, r, nh)), b = __float2int_rn(quant_fast_n(v.y, s, r, nh));
+  int c = __float2int_rn(quant_fast_n(v.z, s, r, nh)), d = __float2int_rn(quant_fast_n(v.w, s, r, nh));
+  if (nh) { a = quant_one(v.x, s); b = quant_one(v.y, s); c = quant_one(v.z, s); d = quant_one(v.w, s); }
+  return (static_cast<uint32_t>(a) & 0xFFu) | ((static_cast<uint32_t>(b) & 0xFFu) << 8) | ((static_cast<uint32_t>(c) & 0xFFu) << 16) |
+         ((static_cast<uint32_t>(d) & 0xFFu) << 24);
+}
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
   return (static_cast<uint32_t>(a) & 0xFFu) | ((static_cast<uint32_t>(b) & 0xFFu) << 8) |
          ((static_cast<uint32_t>(c) & 0xFFu) << 16) | ((static_cast<uint32_t>(d) & 0xFFu) << 24);
