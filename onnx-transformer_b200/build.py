@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     # bit-exact fp32 epilogues: no FMA contraction, IEEE div/sqrt (defaults, stated explicitly), no fast math
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", *os.environ.get("OT_NVCC_EXTRA", "").split(),
     "-Xcompiler", "-fPIC",
 ]
 

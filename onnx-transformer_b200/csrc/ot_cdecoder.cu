@@ -10,12 +10,15 @@
 //     cluster of 8 CTAs; clusters never talk to each other (no grid barrier, no co-residency requirement);
 //   * CTA r of a cluster OWNS sentence r of the group: its residual row x, its attention (warp = head), its LayerNorm / RowQuant;
 //   * every CTA also owns a fixed 1/8 slice of the output features of each of the 6 GEMMs of a layer.  The weight slice streams
-//     through a 6 x 16 KB TMA ring (128-byte swizzle) that runs ahead of the dependency chain (weights are constants); the
-//     activations of all 8 sentences are the small operand: tcgen05.mma kind::i8, M = 128 weight rows, N = 16 (8 sentences used),
-//     int32 accumulators in TMEM, so a thread of the epilogue owns ONE output feature (its scale and bias are two registers);
-//   * GEMM epilogue -> SCATTER: y[s][f] = fl(fl(float(acc)*sx[s])*sw[f]) + b[f] is stored straight into the recv buffer of the
-//     CTA that owns sentence s (st.shared::cluster); row phase -> ALL-GATHER: the owner writes its quantized int8 row + scale
-//     into the swizzled operand buffer of every CTA of the cluster.  One barrier.cluster (release/acquire) per exchange.
+//     through a 4 x 32 KB TMA ring (128-byte swizzle) that is refilled right after every GEMM, so each GEMM finds all of its
+//     weights resident (weights are constants: the ring runs ahead of the dependency chain).  tcgen05.mma kind::i8 with the 8
+//     sentences on the M side (M = 64) and the weight rows on the N side (64..256 per instruction), int32 accumulators in TMEM;
+//   * GEMM epilogue -> SCATTER: y[s][f] = fl(fl(float(acc)*sx[s])*sw[f]) + b[f] goes straight into the recv buffer of the CTA
+//     that owns sentence s; row phase -> ALL-GATHER: the owner writes its quantized int8 row + scale into the swizzled operand
+//     buffer of every CTA of the cluster;
+//   * both exchanges are DATA-FLOW synchronised: every remote store is a st.async that also signals complete_tx on an mbarrier
+//     of the destination CTA, and a consumer waits only for the bytes it is about to read.  There is no barrier.cluster in the
+//     steady state (it cost 0.7 us per exchange, 74 exchanges per greedy step).
 //
 // Arithmetic is instruction-for-instruction that of the stand-alone kernels (ot_rowmath.cuh, ot_attention_decode.cuh,
 // ot_generator.cu), so tokens and KV caches are bit-identical to the per-op engine path (tests/test_decoder_gpu.py).
@@ -32,8 +35,7 @@
 
 namespace ot {
 
-int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
-                   bool swizzle128);
+int get_tensor_map_kblocks(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows, uint32_t box_kb);
 
 namespace cd {
 
@@ -44,31 +46,31 @@ constexpr int kThreads = 256;
 constexpr int kIssuer = 224;        // warp 7, lane 0: MMA issuer
 constexpr int kLoader = 192;        // warp 6, lane 0: TMA producer of the weight ring.  NOT in the issuer's warp: a blocked
                                     // mbarrier.try_wait of one lane stalls the divergent lanes of its warp (measured: 0.5 us per chunk)
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 constexpr int kSlotBytes = 32768;   // up to 256 weight rows x 128 B (one k-block), or 64 rows x 4 k-blocks
 constexpr int kChunks = 15;         // weight chunks per layer per CTA
 constexpr int kMaxLayers = 8;
-constexpr int kKsPitch = kD + 16;
 constexpr int kMaxKeys = 32 * kDecKeysPerLane;   // 96
 constexpr int kGenVT = 32;          // vocabulary entries per generator tile
 constexpr int kTmemCols = 256;      // accumulator: lanes 0..7 = sentences, columns = the CTA's output features of the GEMM (<= 256)
 
 // shared-memory map (dynamic, base aligned to 1024)
 constexpr int kSmRing = 0;                                  // weight ring
-constexpr int kSmBx = kSmRing + kSlots * kSlotBytes;        // 98304: activation operand, K = 512: [4 k-blocks][16 rows][128 B]
-constexpr int kSmKs = kSmBx + 4 * 2048;                     // 106496: attention K rows [96][528]; aliased by the K = 2048 operand (32 KB)
-constexpr int kSmBh = kSmKs;
-constexpr int kSmVh = kSmKs + 51200;                        // 157696: attention V rows [96][512]; aliased by the generator input [8][512] fp32
-constexpr int kSmHb = kSmVh;
-constexpr int kSmRecv = kSmVh + kHeads * kMaxKeys * kDk;    // 206848: fp32 row scattered by the GEMM epilogues (<= 2048 floats)
-constexpr int kSmX = kSmRecv + 8192;                        // 215040: residual row x of my sentence (512 floats)
-constexpr int kSmRow = kSmX + 2048;                         // 217088: int8 staging: q|k|v (1536 B) + ctx (512 B), or h (2048 B)
-constexpr int kSmCtx = kSmRow + 2048;                       // 219136: merged context row / final-norm row, 512 floats
-constexpr int kSmMisc = kSmCtx + 2048;                      // 221184: scales, reduction scratch, generator partials (1536 B)
-constexpr int kSmHot = kSmMisc + 1536;                      // 222720: CdHot copy (<= 1920 B) + 128 B of barriers
-constexpr int kSmTotal = kSmHot + 2048;                     // 224768
-static_assert(kMaxKeys * kKsPitch <= 51200 && 16 * 2048 <= 51200, "K region");
+constexpr int kSmBx = kSmRing + kSlots * kSlotBytes;        // 131072: activation operand, K = 512: [4 k-blocks][8 rows][128 B]
+constexpr int kSmBh = kSmBx + 4 * 1024;                     // 135168: activation operand, K = 2048: [16 k-blocks][8 rows][128 B]
+constexpr int kSmVs = kSmBh + 16 * 1024;                    // 151552: attention V rows [96][512]; aliased by the generator input [8][512] fp32
+constexpr int kSmHb = kSmVs;
+constexpr int kSmRecv = kSmVs + kMaxKeys * kD;              // 200704: fp32 row scattered by the GEMM epilogues (<= 2048 floats)
+constexpr int kSmX = kSmRecv + 8192;                        // 208896: residual row x of my sentence (512 floats)
+constexpr int kSmRow = kSmX + 2048;                         // 210944: int8 staging: q|k|v (1536 B) + ctx (512 B), or h (2048 B)
+constexpr int kSmCtx = kSmRow + 2048;                       // 212992: epilogue staging (2 x 1 KB) / final-norm row (512 floats)
+constexpr int kSmMisc = kSmCtx + 2048;                      // 215040: scales, reduction scratch, generator partials (1536 B)
+constexpr int kSmHot = kSmMisc + 1536;                      // 216576: CdHot copy (<= 1920 B) + 128 B of barriers
+constexpr int kSmTotal = kSmHot + 2048;                     // 218624
 static_assert(kSmTotal + 1024 <= 232448, "shared memory budget");
+// The M = 64 MMA reads 8 row groups (8 KB) from each operand k-block although only the first group (8 sentences) is real:
+// the over-read past Bh must stay inside the CTA's allocation.
+static_assert(kSmBh + 16 * 1024 + 7 * 1024 <= kSmTotal, "operand over-read");
 
 // misc region (floats unless noted)
 constexpr int kMiSB = 0;        // [8] scale of each sentence's current operand row
@@ -79,7 +81,7 @@ constexpr int kMiGenI = 144;    // [8][8] int: its index
 constexpr int kMiPartV = 208;   // [8 warps][8 sentences] per-warp partials (local)
 constexpr int kMiPartI = 272;   // [8][8] int -> 336 floats = 1344 B
 static_assert((kMiPartI + 64) * 4 <= 1536, "misc region");
-constexpr int kSmBars = kSmHot + 1920;   // 12 ring barriers + accfull (104 B) + TMEM slot at +120
+constexpr int kSmBars = kSmHot + 1920;   // 12 mbarriers (96 B) + TMEM slot at +120
 
 struct CdLayer {
   const float *ln_g[3], *ln_b[3];     // ln1, ln2, ln3
@@ -104,26 +106,29 @@ struct alignas(16) CdHot {
 static_assert(sizeof(CdHot) % 16 == 0 && sizeof(CdHot) <= 1920, "CdHot is copied to shared memory in 16-byte pieces");
 
 struct CdPlan {
-  CUtensorMap map_w[kMaxLayers][6];           // qkv, o, cq, co, w1, w2: box = 64 rows x 128 B
+  CUtensorMap map_w[kMaxLayers][6];           // qkv, o, cq, co, w1, w2: (128 B, row, k-block) views, box = one ring chunk
   CdHot hot;
 };
+
+// mbarriers: full[kSlots], empty[kSlots] (weight ring), accfull (MMAs of a GEMM done), kvfull (V rows prefetched),
+// gather (operand rows + scales from every owner), scatter (my sentence's row from every CTA)
+constexpr int kBarEmpty = kSlots, kBarAcc = 2 * kSlots, kBarKv = 2 * kSlots + 1, kBarG = 2 * kSlots + 2, kBarS = 2 * kSlots + 3;
 
 struct Ctx {
   const CdHot* P;
   const CdPlan* G;
   uint8_t* smem;
-  uint64_t* bars;        // full[kSlots], empty[kSlots], accfull
+  uint64_t* bars;
   uint32_t tmem;
   int rank, n_own, b;    // cluster rank, sentences of this cluster, my sentence (or -1)
-  uint32_t pn, cn, total;   // weight chunks issued / consumed / to do (issuer thread only)
-  uint32_t acc_parity, kv_parity;
+  uint32_t pn, cn, total;   // weight chunks issued (loader thread) / consumed (issuer thread) / to do
+  uint32_t acc_parity, kv_parity, g_parity, s_parity;
   int trace_slot;
   bool trace_on;
   bool fine;                       // intra-phase marks of one layer (profiling aid, trace slots 150..249)
   int mark_slot;
   unsigned long long t_step;
 };
-constexpr int kBarEmpty = kSlots, kBarAcc = 2 * kSlots, kBarKv = 2 * kSlots + 1;
 
 // profiling aid: (id << 32 | ns since the step began) into trace[150 + n]
 __device__ __forceinline__ void mark(Ctx& c, int id) {
@@ -134,41 +139,43 @@ __device__ __forceinline__ void mark(Ctx& c, int id) {
 }
 __device__ __forceinline__ float* misc(Ctx& c) { return reinterpret_cast<float*>(c.smem + kSmMisc); }
 
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+// remote (or local) shared-memory stores that also signal complete_tx(bytes) on an mbarrier of the destination CTA
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar) : "memory");
 }
-__device__ __forceinline__ void st_cluster_b32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void st_async_b32(uint32_t addr, uint32_t v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(v), "r"(mbar) : "memory");
 }
 // 1-D bulk copy global -> shared through the TMA unit (async proxy), completion signalled on an mbarrier
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 
-// One exchange: everything this CTA stored (local or remote shared memory, generic proxy) before the barrier is visible to every
-// thread of the cluster after it, also through the async proxy (tcgen05.mma operand reads).
-__device__ __forceinline__ void csync(Ctx& c) {
+// Start of a phase: wait until the `bytes` this phase consumes have landed in this CTA (bar = kBarG: operand rows + scales of an
+// all-gather, kBarS: my sentence's row of a scatter).  Thread 0 arms the mbarrier phase (one arrival + the expected byte count;
+// bytes that arrived before the arming are accounted for by the signed tx-count).  Buffers are reused every second exchange; that
+// is safe because a CTA sends its contribution to exchange k+1 only after it has consumed exchange k, and every exchange gathers
+// from all 8 CTAs.  Also the profiling hook: CTA 0 stamps the begin / end of every wait.
+__device__ __forceinline__ void xwait(Ctx& c, int bar, uint32_t bytes, uint32_t& parity, bool waits) {
   mark(c, 1);
   if (c.trace_on && threadIdx.x == 0) c.P->trace[2 * c.trace_slot] = tl_now();
-  __syncwarp();
-  asm volatile("fence.proxy.async;" ::: "memory");
-  tc_fence_before();
-  cluster_arrive_release();
-  cluster_wait_acquire();
-  asm volatile("fence.proxy.async;" ::: "memory");
-  tc_fence_after();
+  if (waits) {
+    const uint32_t b = smem_u32(&c.bars[bar]);
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(b, bytes);
+    mbar_wait(b, parity);
+    parity ^= 1u;
+  }
   if (c.trace_on && threadIdx.x == 0) c.P->trace[2 * c.trace_slot + 1] = tl_now();
   __syncwarp();
   ++c.trace_slot;
@@ -181,13 +188,15 @@ __device__ __forceinline__ void csync(Ctx& c) {
 // and the 8 sentences on the M side (M = 64, the smallest).  Chunk = what one ring slot holds:
 //   qkv  (192 rows / CTA): 4 chunks = k-blocks, 3 boxes of 64 rows        o, cq, co (64 rows): 1 chunk = 4 k-blocks (4 boxes)
 //   ffn1 (256 rows / CTA): 4 chunks = k-blocks, 4 boxes of 64 rows        ffn2 (64 rows, K = 2048): 4 chunks of 4 k-blocks
-struct Chunk { int g, kb0, boxes; bool by_rows; };
+// Every chunk is ONE TMA instruction (a 3-D box over the (128 B, row, k-block) view of the weight): a warp needs ~0.1 us per TMA
+// instruction, and the loader's warp is also a worker of the row phase that follows.
+struct Chunk { int g, kb0, bytes; };
 __device__ __forceinline__ Chunk chunk_of(int j) {
   Chunk k;
-  if (j < 4) { k.g = 0; k.kb0 = j; k.boxes = 3; k.by_rows = true; }
-  else if (j < 7) { k.g = j - 3; k.kb0 = 0; k.boxes = 4; k.by_rows = false; }
-  else if (j < 11) { k.g = 4; k.kb0 = j - 7; k.boxes = 4; k.by_rows = true; }
-  else { k.g = 5; k.kb0 = 4 * (j - 11); k.boxes = 4; k.by_rows = false; }
+  if (j < 4) { k.g = 0; k.kb0 = j; k.bytes = 192 * 128; }
+  else if (j < 7) { k.g = j - 3; k.kb0 = 0; k.bytes = 4 * 64 * 128; }
+  else if (j < 11) { k.g = 4; k.kb0 = j - 7; k.bytes = 256 * 128; }
+  else { k.g = 5; k.kb0 = 4 * (j - 11); k.bytes = 4 * 64 * 128; }
   return k;
 }
 __device__ __forceinline__ int slice_rows(int g) { return g == 0 ? 192 : (g == 4 ? 256 : 64); }
@@ -201,14 +210,13 @@ __device__ __forceinline__ void issue_chunk(Ctx& c) {
   const CUtensorMap* map = &c.G->map_w[l][k.g];
   const uint32_t fb = smem_u32(&c.bars[slot]);
   const uint32_t dst = smem_u32(c.smem + kSmRing + slot * kSlotBytes);
-  const int r0 = slice_rows(k.g) * c.rank;
-  mbar_arrive_expect_tx(fb, k.boxes * 8192);
-  for (int i = 0; i < k.boxes; ++i)
-    tma_load_2d(dst + i * 8192, map, fb, (k.by_rows ? k.kb0 : k.kb0 + i) * 128, k.by_rows ? r0 + 64 * i : r0);
+  mbar_arrive_expect_tx(fb, k.bytes);
+  tma_load_3d(dst, map, fb, 0, slice_rows(k.g) * c.rank, k.kb0);
   ++c.pn;
 }
-// loader thread: issue every chunk below `upto` (blocking on the ring slot of each: chunk n reuses the slot of chunk n - kSlots,
-// free once that chunk's MMAs have completed)
+// loader thread: issue every chunk below `upto` (chunk n reuses the slot of chunk n - kSlots, free once that chunk's MMAs have
+// completed).  Called right after a GEMM's last MMA: no GEMM has more than kSlots chunks, so every GEMM starts with all of its
+// weights in flight or resident.
 __device__ __forceinline__ void fill_until(Ctx& c, uint32_t upto) {
   upto = min(upto, c.total);
   while (c.pn < upto) {
@@ -221,25 +229,11 @@ __device__ __forceinline__ void fill_until(Ctx& c, uint32_t upto) {
 // ------------------------------------------------------------------------------------------------ GEMM phase
 // g: 0 qkv, 1 o, 2 cq, 3 co, 4 w1 (ReLU), 5 w2.  D[s][f] = sum_k a[s][k] * W[f][k] (rows s >= 8 of the M = 64 tile are whatever
 // follows the 8 operand rows in shared memory: never read back); then scatter y[s][f] to the owner of sentence s.
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void st_cluster_v2(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
-}
-
 __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) {
   const CdHot& P = *c.P;
   const CdLayer& L = P.layer[l];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = slice_rows(g);
-  mark(c, 10 + g);
   // epilogue threads: warps 0 and 4 (the two that may read TMEM lanes 0..31), each half of the columns in groups of 32;
   // 16x256b fragment: thread t holds sentence t/4, features 8*i + 2*(t%4) + {0,1} of every 8-column block i
   const bool epi = (warp & 3) == 0;
@@ -248,7 +242,7 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
   const int ngroups = half >> 5;                    // 3 / 1 / 4
   const int srow = lane >> 2;
   float2 sw[16], bb[16];
-  if (epi) {
+  if (epi) {        // per-feature constants: in flight while the operand rows arrive
     const float* swp = L.sw[g] + rows * c.rank + col0 + 2 * (lane & 3);
     const float* bp = L.bias[g] + rows * c.rank + col0 + 2 * (lane & 3);
 #pragma unroll
@@ -259,7 +253,9 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
       }
     }
   }
+  xwait(c, kBarG, static_cast<uint32_t>(c.n_own) * (g == 5 ? kFF + 4 : kD + 4), c.g_parity, true);
   if (tid == kIssuer) {
+    asm volatile("fence.proxy.async;" ::: "memory");      // operand rows were written through the generic proxy
     const uint32_t abase = smem_u32(c.smem + (g == 5 ? kSmBh : kSmBx));
     const uint32_t idesc = make_idesc_i8(64, rows);
     const bool by_rows = (g == 0 || g == 4);
@@ -273,7 +269,7 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
 #pragma unroll 1
       for (int i = 0; i < nkb; ++i) {
         const int kb = by_rows ? ch : 4 * ch + i;
-        const uint64_t a_desc = make_smem_desc_sw128(abase + kb * 2048);
+        const uint64_t a_desc = make_smem_desc_sw128(abase + kb * 1024);
         const uint64_t b_desc = make_smem_desc_sw128(sbase + i * 8192);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -284,8 +280,7 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
     }
     mma_commit(smem_u32(&c.bars[kBarAcc]));
   } else if (tid == kLoader) {
-    // keep the ring full while this GEMM drains it: by the time its last MMA has completed the next kSlots chunks (the start of
-    // the next GEMMs) are in flight, so the ring runs ahead of the dependency chain
+    mbar_wait(smem_u32(&c.bars[kBarAcc]), c.acc_parity);     // every slot this GEMM used is free: refill the ring
     fill_until(c, gend + kSlots);
   }
   __syncwarp();
@@ -295,9 +290,10 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
     mark(c, 20 + g);
     const float sx = (misc(c) + kMiSB)[srow];
     // y of one 32-column group is staged per warp as [sentence][32 features] (1 KB) and leaves as 16-byte chunks, 128 contiguous
-    // bytes per destination CTA and instruction: 4x fewer DSMEM packets than storing the fragment's float2 pairs directly
+    // bytes per destination CTA and instruction
     float* stage = reinterpret_cast<float*>(c.smem + kSmCtx) + (warp >> 2) * 256;
     const uint32_t recv0 = smem_u32(c.smem + kSmRecv) + 4u * static_cast<uint32_t>(rows * c.rank + col0);
+    const uint32_t sbar = smem_u32(&c.bars[kBarS]);
 #pragma unroll
     for (int gq = 0; gq < 4; ++gq) {
       if (gq < ngroups) {
@@ -318,12 +314,13 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
           const int id = lane + 32 * j, s = id >> 3, ch = id & 7;     // sentence, 16-byte chunk of its 32 features
           if (s < c.n_own) {
             const uint4 v = *reinterpret_cast<const uint4*>(stage + s * 32 + ch * 4);
-            st_cluster_v4(mapa_shared(recv0 + 4u * static_cast<uint32_t>(32 * gq + 4 * ch), s), v);
+            st_async_v4(mapa_shared(recv0 + 4u * static_cast<uint32_t>(32 * gq + 4 * ch), s), v, mapa_shared(sbar, s));
           }
         }
         __syncwarp();
       }
     }
+    tc_fence_before();
   }
   mark(c, 30 + g);
   c.acc_parity ^= 1u;
@@ -331,26 +328,27 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
 
 // ------------------------------------------------------------------------------------------------ all-gather helpers
 // Push the int8 row staged at `src` (K bytes, K = 512 or 2048) into row `rank` of every CTA's operand buffer (128-byte swizzle:
-// 16-byte chunk c of a row lands at chunk c ^ (row & 7) of its 128-byte line), plus its scale.
+// 16-byte chunk c of a row lands at chunk c ^ (row & 7) of its 128-byte line; k-blocks 1 KB apart), plus its scale.
 __device__ __forceinline__ void push_row_q8(Ctx& c, const uint8_t* src, int K, int dst_off, float scale) {
   const int tid = threadIdx.x;
   const int chunks = K >> 4;                       // 32 or 128
   const int per_peer_shift = (K == 512) ? 5 : 7;
+  const uint32_t gbar = smem_u32(&c.bars[kBarG]);
   for (int idx = tid; idx < chunks * kCS; idx += kThreads) {
     const int peer = idx >> per_peer_shift, ch = idx & (chunks - 1);
     const uint4 v = *reinterpret_cast<const uint4*>(src + ch * 16);
     const int kb = ch >> 3, cc = ch & 7;
-    const uint32_t local = smem_u32(c.smem + dst_off + kb * 2048 + c.rank * 128 + ((cc ^ (c.rank & 7)) << 4));
-    st_cluster_v4(mapa_shared(local, peer), v);
+    const uint32_t local = smem_u32(c.smem + dst_off + kb * 1024 + c.rank * 128 + ((cc ^ (c.rank & 7)) << 4));
+    st_async_v4(mapa_shared(local, peer), v, mapa_shared(gbar, peer));
   }
-  if (tid < kCS) st_cluster_b32(mapa_shared(smem_u32(misc(c) + kMiSB + c.rank), tid), __float_as_uint(scale));
+  if (tid < kCS) st_async_b32(mapa_shared(smem_u32(misc(c) + kMiSB + c.rank), tid), __float_as_uint(scale), mapa_shared(gbar, tid));
 }
 
 // ------------------------------------------------------------------------------------------------ row phases (owner CTA)
-// LayerNorm of my sentence.  SRC 0: x = embedding(token)*sqrt(d) + pe[t]; SRC 1: x = x + recv (the scattered O / CO / FFN2 row).
-// quant: RowQuant -> all-gather into Bx; else (final norm) the fp32 row goes to every CTA's generator input.
 __device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// LayerNorm of my sentence.  SRC 0: x = embedding(token)*sqrt(d) + pe[t]; SRC 1: x = x + recv (the scattered O / CO / FFN2 row).
+// quant: RowQuant -> all-gather into Bx; else (final norm) the fp32 row goes to every CTA's generator input.
 // The row is spread over 4 warps -- warp i holds float4 i*32+lane, exactly the element layernorm_row<4> gives lane `lane` in its
 // i-th register -- and every reduction is evaluated in layernorm_row's order: per lane ((p0 + p1) + p2) + p3 over the four
 // registers, then the xor-shuffle tree over lanes.  Same instructions on the same operands => bit-identical results, at a quarter
@@ -363,7 +361,6 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
   float* yrow = reinterpret_cast<float*>(c.smem + kSmCtx);
   float* red = misc(c) + kMiRed;
   float* part = reinterpret_cast<float*>(c.smem + kSmRow + 1024);    // [2][4][32] partial sums (the staging row only uses its first 512 B here)
-  mark(c, 40);
   if (c.b >= 0 && warp < 4) {
     const int i4 = warp * 32 + lane;
     float4 v;
@@ -419,10 +416,11 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
     if (quant) {
       push_row_q8(c, rowq, kD, kSmBx, red[0]);
     } else {
+      const uint32_t gbar = smem_u32(&c.bars[kBarG]);
       for (int idx = tid; idx < 128 * kCS; idx += kThreads) {
         const int peer = idx >> 7, ch = idx & 127;
         const uint4 v = *reinterpret_cast<const uint4*>(yrow + ch * 4);
-        st_cluster_v4(mapa_shared(smem_u32(c.smem + kSmHb + (c.rank * kD + ch * 4) * 4), peer), v);
+        st_async_v4(mapa_shared(smem_u32(c.smem + kSmHb + (c.rank * kD + ch * 4) * 4), peer), v, mapa_shared(gbar, peer));
       }
     }
   }
@@ -434,7 +432,6 @@ __device__ __forceinline__ void phase_ffnq(Ctx& c) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* red = misc(c) + kMiRed;
   uint8_t* rowq = c.smem + kSmRow;
-  mark(c, 60);
   if (c.b >= 0) {
     const float4* y4 = reinterpret_cast<const float4*>(c.smem + kSmRecv);
     const float4 a = y4[2 * tid], b = y4[2 * tid + 1];
@@ -460,24 +457,21 @@ struct AttnPre {
   float skl[kDecKeysPerLane], svl[kDecKeysPerLane];
   uint8_t keepl[kDecKeysPerLane];
 };
-// Issued during the preceding GEMM phase: the old K/V rows of my sentence into shared memory (bulk copies) and, per lane, the
-// scales / mask of its keys j = 32*kk + lane.
-__device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* k, const int8_t* v, int64_t ldk, int64_t row0, const float* sk,
-                                              const float* sv, int64_t sstride, const uint8_t* key_mask, int mask_stride, AttnPre& pre) {
-  // one 512-byte bulk copy per K row and per V row: the copies run in the TMA unit, so neither the issuing threads nor the
-  // release fence of the next barrier.cluster wait for them (cp.async copies did: +0.7 us on every GEMM-phase barrier)
-  // Issued by warps 1, 2, 3 and 5: idle during a GEMM phase (0 / 4: epilogue, 6: weight ring, 7: MMA issuer); a warp needs
-  // ~20 ns per bulk-copy instruction, which must not sit in front of the MMAs or the epilogue.
+// Issued during the preceding GEMM phase: the old V rows of my sentence into shared memory (one 512-byte bulk copy per row; the
+// copies run in the TMA unit) and, per lane, the scales / mask of its keys j = 32*kk + lane.  Issued by warps 1, 2, 3 and 5: idle
+// during a GEMM phase (0 / 4: epilogue, 6: weight ring, 7: MMA issuer); a warp needs ~20 ns per bulk-copy instruction.
+__device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* v, int64_t ldk, int64_t row0, const float* sk, const float* sv,
+                                              int64_t sstride, const uint8_t* key_mask, int mask_stride, AttnPre& pre) {
   const uint32_t bar = smem_u32(&c.bars[kBarKv]);
   const int w = threadIdx.x >> 5;
-  if (threadIdx.x == 32) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(n_old) * 2u * kD);
+  if (threadIdx.x == 32) {
+    asm volatile("fence.proxy.async;" ::: "memory");     // the V region was last touched through the generic proxy
+    mbar_arrive_expect_tx(bar, static_cast<uint32_t>(n_old) * kD);
+  }
+  __syncwarp();
   if (w == 1 || w == 2 || w == 3 || w == 5) {
-    for (int idx = (w == 5 ? 96 : (w - 1) * 32) + (threadIdx.x & 31); idx < 2 * n_old; idx += 128) {
-      const int j = idx >> 1;
-      const int64_t src = (row0 + j) * ldk;
-      if (idx & 1) bulk_load(smem_u32(c.smem + kSmVh + j * kD), v + src, kD, bar);
-      else bulk_load(smem_u32(c.smem + kSmKs + j * kKsPitch), k + src, kD, bar);
-    }
+    for (int j = (w == 5 ? 96 : (w - 1) * 32) + (threadIdx.x & 31); j < n_old; j += 128)
+      bulk_load(smem_u32(c.smem + kSmVs + j * kD), v + (row0 + j) * ldk, kD, bar);
   }
   const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -530,22 +524,90 @@ __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale
   __syncthreads();
 }
 
-// Decode attention of my sentence with K rows in Ks and V slices in Vh: the arithmetic of attention_decode_body
-// (ot_attention_decode.cuh), instruction for instruction.  warp h = head h.  Leaves the quantized context row at rowbuf + 1536
-// and its scale in red[16].
-__device__ __forceinline__ void attention_smem(Ctx& c, int Tk, int q_pos0, int mask_kind, float sqi, const AttnPre& pre) {
-  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// self: RowQuant of q | k | v, KV-cache append, causal attention over t+1 keys; cross: RowQuant of q, attention over the S cached
+// memory keys with the key-padding mask.  warp h = head h; the arithmetic of attention_decode_body (ot_attention_decode.cuh),
+// instruction for instruction: K rows straight from the (L2-resident) cache into registers -- issued before the RowQuant, which
+// hides their latency --, V rows from the prefetched shared-memory copy.  Ends with the all-gather of the quantized context row.
+__device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l, AttnPre& pre) {
+  const CdHot& P = *c.P;
+  const CdLayer& L = P.layer[l];
+  if (c.b < 0) return;
+  const int tid = threadIdx.x, h = tid >> 5, lane = tid & 31;
   const int8_t* rowbuf = reinterpret_cast<const int8_t*>(c.smem + kSmRow);
-  const int8_t* Ks = reinterpret_cast<const int8_t*>(c.smem + kSmKs);
-  const int8_t* Vs = reinterpret_cast<const int8_t*>(c.smem + kSmVh);      // [key][512]
+  int8_t* Vs = reinterpret_cast<int8_t*>(c.smem + kSmVs);      // [key][512]
   float* red = misc(c) + kMiRed;
-  uint32_t qw[16];
+  const int Tk = self ? t + 1 : P.S;
+  const int n_old = self ? t : P.S;
+  // K: instruction i reads the head slices of keys 8i .. 8i+7, four lanes per key and 16 bytes per lane (64 contiguous bytes per
+  // row: coalesced, unlike one key per lane), straight from the (L2-resident) cache; issued before the RowQuant, which hides the
+  // latency.  Indices are clamped, never predicated on the loaded value.
+  const int m8 = lane >> 2, ch = lane & 3;
+  uint4 kq[4 * kDecKeysPerLane];
   {
-    const uint4* qp = reinterpret_cast<const uint4*>(rowbuf + h * kDk);
+    const int8_t* kbase = self ? L.kc + static_cast<int64_t>(c.b) * P.cap * kD : P.ckv + static_cast<int64_t>(c.b) * P.S * (2 * kD * P.n_layers) + 2 * kD * l;
+    const int64_t ldk = self ? kD : 2 * kD * P.n_layers;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const uint4 t = qp[w];
-      qw[4 * w] = t.x; qw[4 * w + 1] = t.y; qw[4 * w + 2] = t.z; qw[4 * w + 3] = t.w;
+    for (int i = 0; i < 4 * kDecKeysPerLane; ++i) {
+      kq[i] = make_uint4(0, 0, 0, 0);
+      if (8 * i < n_old) {
+        const int j = min(8 * i + m8, n_old - 1);
+        kq[i] = __ldcg(reinterpret_cast<const uint4*>(kbase + j * ldk + h * kDk) + ch);
+      }
+    }
+  }
+  float sc3[3];
+  mark(c, 50);
+  quant_groups(c, self ? 3 : 1, sc3);
+  mark(c, 51);
+  mbar_wait(smem_u32(&c.bars[kBarKv]), c.kv_parity);
+  c.kv_parity ^= 1u;
+  mark(c, 52);
+  if (self) {
+    // this step's K / V row: into the cache (global), V also next to the prefetched rows, K into the registers of its 4 lanes
+    const int64_t dst = (static_cast<int64_t>(c.b) * P.cap + t) * kD;
+    if (tid < 32) {
+      *reinterpret_cast<uint4*>(L.kc + dst + tid * 16) = *reinterpret_cast<const uint4*>(rowbuf + kD + tid * 16);
+    } else if (tid < 64) {
+      const int c16 = tid - 32;
+      const uint4 vv = *reinterpret_cast<const uint4*>(rowbuf + 2 * kD + c16 * 16);
+      *reinterpret_cast<uint4*>(Vs + t * kD + c16 * 16) = vv;
+      *reinterpret_cast<uint4*>(L.vc + dst + c16 * 16) = vv;
+    } else if (tid == 64) {
+      L.skc[static_cast<int64_t>(c.b) * P.cap + t] = sc3[1];
+      L.svc[static_cast<int64_t>(c.b) * P.cap + t] = sc3[2];
+    }
+    if (tid < 64) asm volatile("fence.proxy.async;" ::: "memory");   // later steps read these rows through bulk copies (async proxy)
+#pragma unroll
+    for (int kk = 0; kk < kDecKeysPerLane; ++kk)
+      if (kk * 32 + lane == t) { pre.skl[kk] = sc3[1]; pre.svl[kk] = sc3[2]; }
+#pragma unroll
+    for (int i = 0; i < 4 * kDecKeysPerLane; ++i)
+      if (8 * i + m8 == t) kq[i] = *reinterpret_cast<const uint4*>(rowbuf + kD + h * kDk + ch * 16);
+    __syncthreads();
+  }
+  const int q_pos0 = self ? t : 0, mask_kind = self ? 2 : 1;
+  const float sqi = sc3[0];
+  mark(c, 53);
+  // int8 dot products: 4 dp4a per lane on its 16 bytes, summed over the key's 4 lanes (integer: exact in any order), then handed
+  // to the lane that owns the key in the softmax (key 32*kk + lane)
+  int dotl[kDecKeysPerLane];
+  {
+    const uint4 qv = *reinterpret_cast<const uint4*>(rowbuf + h * kDk + ch * 16);
+#pragma unroll
+    for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
+      dotl[kk] = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 tk = kq[4 * kk + q];
+        int d = __dp4a(static_cast<int>(qv.x), static_cast<int>(tk.x), 0);
+        d = __dp4a(static_cast<int>(qv.y), static_cast<int>(tk.y), d);
+        d = __dp4a(static_cast<int>(qv.z), static_cast<int>(tk.z), d);
+        d = __dp4a(static_cast<int>(qv.w), static_cast<int>(tk.w), d);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        const int got = __shfl_sync(0xffffffffu, d, 4 * (lane & 7));     // key 8*(4kk+q) + (lane & 7)
+        if ((lane >> 3) == q) dotl[kk] = got;
+      }
     }
   }
   float sc[kDecKeysPerLane], svl[kDecKeysPerLane];
@@ -553,18 +615,7 @@ __device__ __forceinline__ void attention_smem(Ctx& c, int Tk, int q_pos0, int m
 #pragma unroll
   for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
     const int j = kk * 32 + lane;
-    const int jc = min(j, Tk - 1);
-    const uint4* kp = reinterpret_cast<const uint4*>(Ks + jc * kKsPitch + h * kDk);
-    int dot = 0;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const uint4 t = kp[w];
-      dot = __dp4a(static_cast<int>(qw[4 * w]), static_cast<int>(t.x), dot);
-      dot = __dp4a(static_cast<int>(qw[4 * w + 1]), static_cast<int>(t.y), dot);
-      dot = __dp4a(static_cast<int>(qw[4 * w + 2]), static_cast<int>(t.z), dot);
-      dot = __dp4a(static_cast<int>(qw[4 * w + 3]), static_cast<int>(t.w), dot);
-    }
-    const float s = __fdiv_rn(__fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), pre.skl[kk]), 8.0f);
+    const float s = __fdiv_rn(__fmul_rn(__fmul_rn(__int2float_rn(dotl[kk]), sqi), pre.skl[kk]), 8.0f);
     const bool visible = pre.keepl[kk] != 0 && (mask_kind != 2 || j <= q_pos0);
     const bool live = j < Tk;
     sc[kk] = live ? (visible ? s : -1e9f) : -INFINITY;
@@ -582,10 +633,15 @@ __device__ __forceinline__ void attention_smem(Ctx& c, int Tk, int q_pos0, int m
     }
   }
   sum = warp_sum_f(sum);
-  float pq[kDecKeysPerLane];
+  // quantized probability (already divided by 127, attention.py:35) and V scale of every key, staged for broadcast reads: the
+  // P.V loop is bound by the shared-memory / shuffle pipe, and one 16-byte broadcast load per TWO keys replaces four shuffles
+  float2* pv = reinterpret_cast<float2*>(c.smem + kSmRecv) + h * kMaxKeys;     // (the scattered q|k|v row has been consumed)
 #pragma unroll
-  for (int kk = 0; kk < kDecKeysPerLane; ++kk)
-    pq[kk] = (kk * 32 + lane < Tk) ? __fdiv_rn(rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f)), 127.0f) : 0.f;
+  for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
+    const float pqk = (kk * 32 + lane < Tk) ? __fdiv_rn(rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f)), 127.0f) : 0.f;
+    pv[kk * 32 + lane] = make_float2(pqk, svl[kk]);
+  }
+  __syncwarp();
   mark(c, 55);
   float acc0 = 0.f, acc1 = 0.f;
   const int d0 = 2 * lane;
@@ -594,74 +650,30 @@ __device__ __forceinline__ void attention_smem(Ctx& c, int Tk, int q_pos0, int m
 #pragma unroll
   for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
     if (kk * 32 >= Tk) break;
-#pragma unroll 8
-    for (int jj = 0; jj < 32; ++jj) {
-      const float ph = __shfl_sync(0xffffffffu, pq[kk], jj);
-      const float svj = __shfl_sync(0xffffffffu, svl[kk], jj);
-      const char2 vv = *reinterpret_cast<const char2*>(Vs + (kk * 32 + jj) * kD + h * kDk + d0);
-      acc0 = fmaf(ph, __fmul_rn(__int2float_rn(vv.x), svj), acc0);
-      acc1 = fmaf(ph, __fmul_rn(__int2float_rn(vv.y), svj), acc1);
+#pragma unroll 4
+    for (int jj = 0; jj < 32; jj += 2) {
+      const float4 ps = *reinterpret_cast<const float4*>(pv + kk * 32 + jj);      // p, sv of keys jj and jj+1
+      const char2 va = *reinterpret_cast<const char2*>(Vs + (kk * 32 + jj) * kD + h * kDk + d0);
+      const char2 vb = *reinterpret_cast<const char2*>(Vs + (kk * 32 + jj + 1) * kD + h * kDk + d0);
+      acc0 = fmaf(ps.x, __fmul_rn(__int2float_rn(va.x), ps.y), acc0);
+      acc1 = fmaf(ps.x, __fmul_rn(__int2float_rn(va.y), ps.y), acc1);
+      acc0 = fmaf(ps.z, __fmul_rn(__int2float_rn(vb.x), ps.w), acc0);
+      acc1 = fmaf(ps.z, __fmul_rn(__int2float_rn(vb.y), ps.w), acc1);
     }
   }
-  mark(c, 56);
   // RowQuant of the merged context row (all 8 heads): the row abs-max is a max (exact in any order), every lane quantizes its own
   // two features with the instructions of attention_decode_body
+  mark(c, 56);
   const float am = warp_max_f(fmaxf(fabsf(acc0), fabsf(acc1)));
   if (lane == 0) red[24 + h] = am;
   __syncthreads();
-  mark(c, 57);
   const float amax = fmaxf(fmaxf(fmaxf(red[24], red[25]), fmaxf(red[26], red[27])), fmaxf(fmaxf(red[28], red[29]), fmaxf(red[30], red[31])));
   const float s = __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f);
   const uint32_t q01 = quant4_pack(make_float4(acc0, acc1, 0.f, 0.f), s, __frcp_rn(s));
-  const int q0i = static_cast<int>(q01 & 0xFFu), q1i = static_cast<int>((q01 >> 8) & 0xFFu);
-  *reinterpret_cast<uint16_t*>(c.smem + kSmRow + 1536 + h * kDk + d0) =
-      static_cast<uint16_t>((static_cast<uint32_t>(q0i) & 0xFFu) | ((static_cast<uint32_t>(q1i) & 0xFFu) << 8));
-  if (threadIdx.x == 0) red[16] = s;
+  *reinterpret_cast<uint16_t*>(c.smem + kSmRow + 1536 + h * kDk + d0) = static_cast<uint16_t>(q01 & 0xFFFFu);
   __syncthreads();
-}
-
-// self: RowQuant of q | k | v, KV-cache append, causal attention over t+1 keys; cross: RowQuant of q, attention over the S cached
-// memory keys with the key-padding mask.  Ends with the all-gather of the quantized context row.
-__device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l, AttnPre& pre) {
-  const CdHot& P = *c.P;
-  const CdLayer& L = P.layer[l];
-  if (c.b < 0) return;
-  mark(c, 50);
-  mbar_wait(smem_u32(&c.bars[kBarKv]), c.kv_parity);
-  c.kv_parity ^= 1u;
-  float sc[3];
-  mark(c, 51);
-  quant_groups(c, self ? 3 : 1, sc);
-  mark(c, 52);       // 
-  if (self) {
-    const int tid = threadIdx.x;
-    const int8_t* rowbuf = reinterpret_cast<const int8_t*>(c.smem + kSmRow);
-    int8_t* Ks = reinterpret_cast<int8_t*>(c.smem + kSmKs);
-    int8_t* Vh = reinterpret_cast<int8_t*>(c.smem + kSmVh);
-    const int64_t dst = (static_cast<int64_t>(c.b) * P.cap + t) * kD;
-    if (tid < 32) {
-      const uint4 kk = *reinterpret_cast<const uint4*>(rowbuf + kD + tid * 16);
-      *reinterpret_cast<uint4*>(Ks + t * kKsPitch + tid * 16) = kk;
-      *reinterpret_cast<uint4*>(L.kc + dst + tid * 16) = kk;
-    } else if (tid < 64) {
-      const int ch = tid - 32;
-      const uint4 vv = *reinterpret_cast<const uint4*>(rowbuf + 2 * kD + ch * 16);
-      *reinterpret_cast<uint4*>(Vh + t * kD + ch * 16) = vv;
-      *reinterpret_cast<uint4*>(L.vc + dst + ch * 16) = vv;
-    } else if (tid == 64) {
-      L.skc[static_cast<int64_t>(c.b) * P.cap + t] = sc[1];
-      L.svc[static_cast<int64_t>(c.b) * P.cap + t] = sc[2];
-    }
-    const int lane = tid & 31;
-#pragma unroll
-    for (int kk = 0; kk < kDecKeysPerLane; ++kk)
-      if (kk * 32 + lane == t) { pre.skl[kk] = sc[1]; pre.svl[kk] = sc[2]; }
-    __syncthreads();
-  }
-  mark(c, 53);
-  attention_smem(c, self ? t + 1 : P.S, self ? t : 0, self ? 2 : 1, sc[0], pre);
   mark(c, 58);
-  push_row_q8(c, c.smem + kSmRow + 1536, kD, kSmBx, (misc(c) + kMiRed)[16]);
+  push_row_q8(c, c.smem + kSmRow + 1536, kD, kSmBx, s);
   mark(c, 59);
 }
 
@@ -765,8 +777,9 @@ __device__ __forceinline__ void phase_generator(Ctx& c) {
       const int oi = pi[w * kCS + tid];
       if (ob > bv || (ob == bv && oi < bi)) { bv = ob; bi = oi; }
     }
-    st_cluster_b32(mapa_shared(smem_u32(misc(c) + kMiGenV + c.rank), tid), __float_as_uint(bv));
-    st_cluster_b32(mapa_shared(smem_u32(misc(c) + kMiGenI + c.rank), tid), static_cast<uint32_t>(bi));
+    const uint32_t sbar = mapa_shared(smem_u32(&c.bars[kBarS]), tid);
+    st_async_b32(mapa_shared(smem_u32(misc(c) + kMiGenV + c.rank), tid), __float_as_uint(bv), sbar);
+    st_async_b32(mapa_shared(smem_u32(misc(c) + kMiGenI + c.rank), tid), static_cast<uint32_t>(bi), sbar);
   }
 }
 // owner, warp 0: first arg-max over the 8 vocabulary slices
@@ -800,7 +813,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 7) {
     if (lane == 0) {
-      for (int i = 0; i <= kBarKv; ++i) mbar_init(smem_u32(&c.bars[i]), 1);
+      for (int i = 0; i <= kBarS; ++i) mbar_init(smem_u32(&c.bars[i]), 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -819,8 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   c.b = (c.rank < c.n_own) ? cluster_id * P.spc + c.rank : -1;
   c.pn = c.cn = 0;
   c.total = static_cast<uint32_t>(n_steps) * nl * kChunks;
-  c.acc_parity = 0;
-  c.kv_parity = 0;
+  c.acc_parity = c.kv_parity = c.g_parity = c.s_parity = 0;
   c.trace_slot = 0;
   c.trace_on = false;
   c.fine = false;
@@ -828,19 +840,24 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   c.t_step = 0;
   if (tid == kLoader) fill_until(c, kSlots);
   __syncwarp();
-  csync(c);          // every CTA of the cluster is running (its shared memory may be written) and has its barriers initialised
+  // every CTA of the cluster is running (its shared memory may be written) and has its barriers initialised
+  cluster_arrive_release();
+  cluster_wait_acquire();
 
   const int t_last = t0 + n_steps - 1;
+  const bool own = c.b >= 0;
   AttnPre pre;
 #pragma unroll 1
   for (int t = t0; t <= t_last; ++t) {
     c.trace_slot = 0;
     c.trace_on = P.trace != nullptr && blockIdx.x == 0 && t == t_last;
     if (c.trace_on && tid == 0) { c.t_step = tl_now(); P.trace[255] = c.t_step; }
-    // ---- token -> embedding + positional encoding -> LayerNorm 1 of layer 0 -> all-gather
+    // ---- token (arg-max over the 8 vocabulary slices of the previous step) -> embedding + positional encoding -> LayerNorm 1
+    //      of layer 0 -> all-gather
     {
+      xwait(c, kBarS, 64, c.s_parity, own && t > t0);
       int* tok = reinterpret_cast<int*>(misc(c) + kMiTok);
-      if (c.b >= 0 && warp == 0) {
+      if (own && warp == 0) {
         int64_t token;
         if (t > t0) {
           token = generator_pick(c, lane);
@@ -851,9 +868,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
         if (lane == 0) *tok = static_cast<int>(token);
       }
       __syncthreads();
-      const int64_t token = *tok;
-      phase_ln(c, 0, token, t, P.layer[0].ln_g[0], P.layer[0].ln_b[0], true);
-      csync(c);
+      phase_ln(c, 0, *tok, t, P.layer[0].ln_g[0], P.layer[0].ln_b[0], true);
     }
 #pragma unroll 1
     for (int l = 0; l < nl; ++l) {
@@ -861,44 +876,47 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
       c.fine = c.trace_on && l == min(2, nl - 1);
 #pragma unroll 1
       for (int q = 0; q < 11; ++q) {
-        if (q == 0 || q == 2 || q == 4 || q == 6 || q == 8 || q == 10) {
+        if ((q & 1) == 0) {
           // ---- GEMM phases; the attention operands of my sentence are prefetched alongside
-          if ((q == 0 || q == 4) && c.b >= 0) {
+          if ((q == 0 || q == 4) && own) {
             const bool self = q == 0;
-            attn_prefetch(c, self ? t : P.S, self ? L.kc : P.ckv + 2 * kD * l, self ? L.vc : P.ckv + 2 * kD * l + kD,
-                          self ? kD : 2 * kD * nl, static_cast<int64_t>(c.b) * (self ? P.cap : P.S), self ? L.skc : P.sckv + 2 * l,
-                          self ? L.svc : P.sckv + 2 * l + 1, self ? 1 : 2 * nl, self ? nullptr : P.mask, P.S, pre);
+            attn_prefetch(c, self ? t : P.S, self ? L.vc : P.ckv + 2 * kD * l + kD, self ? kD : 2 * kD * nl,
+                          static_cast<int64_t>(c.b) * (self ? P.cap : P.S), self ? L.skc : P.sckv + 2 * l, self ? L.svc : P.sckv + 2 * l + 1,
+                          self ? 1 : 2 * nl, self ? nullptr : P.mask, P.S, pre);
           }
           // index one past this GEMM's last weight chunk in the launch-wide chunk sequence
           const int g = q >> 1;
           const uint32_t gend = (static_cast<uint32_t>(t - t0) * nl + l) * kChunks + (g == 0 ? 4 : g == 1 ? 5 : g == 2 ? 6 : g == 3 ? 7 : g == 4 ? 11 : 15);
           phase_gemm(c, l, g, gend);
-        } else if (q == 1 || q == 5) {
-          phase_attention(c, q == 1, t, l, pre);
-        } else if (q == 3 || q == 7) {
-          phase_ln(c, 1, 0, t, L.ln_g[q == 3 ? 1 : 2], L.ln_b[q == 3 ? 1 : 2], true);
         } else {
-          phase_ffnq(c);
+          // ---- row phases: my sentence's row has arrived from the 8 column owners
+          xwait(c, kBarS, (q == 1 ? 3 * kD : q == 9 ? kFF : kD) * 4, c.s_parity, own);
+          if (q == 1 || q == 5) phase_attention(c, q == 1, t, l, pre);
+          else if (q == 3 || q == 7) phase_ln(c, 1, 0, t, L.ln_g[q == 3 ? 1 : 2], L.ln_b[q == 3 ? 1 : 2], true);
+          else phase_ffnq(c);
         }
-        csync(c);
       }
       // ---- residual + LayerNorm 1 of the next layer, or the final norm (fp32 row to every CTA's generator input)
+      xwait(c, kBarS, kD * 4, c.s_parity, own);
       if (l + 1 < nl) phase_ln(c, 1, 0, t, P.layer[l + 1].ln_g[0], P.layer[l + 1].ln_b[0], true);
       else phase_ln(c, 1, 0, t, P.fin_g, P.fin_b, false);
-      csync(c);
     }
     c.fine = false;
+    xwait(c, kBarG, static_cast<uint32_t>(c.n_own) * kD * 4, c.g_parity, true);
     phase_generator(c);
-    csync(c);
+    if (c.trace_on && tid == 0) P.trace[254] = tl_now();
   }
   // the last step's token
-  if (c.b >= 0 && warp == 0) {
+  xwait(c, kBarS, 64, c.s_parity, own);
+  if (own && warp == 0) {
     const int id = generator_pick(c, lane);
     if (lane == 0) P.ys[static_cast<int64_t>(c.b) * P.ys_ld + t_last + 1] = id;
   }
-  cp_async_wait_all();
   tc_fence_before();
-  csync(c);          // no CTA exits while a peer may still address its shared memory
+  __syncthreads();
+  // no CTA exits while a peer may still address its shared memory
+  cluster_arrive_release();
+  cluster_wait_acquire();
   if (warp == 7) tmem_dealloc(c.tmem, kTmemCols);
 }
 
@@ -949,8 +967,10 @@ extern "C" int ot_cdecoder_plan_build(void* plan_dev, int n_layers, int B, int S
     L.skc = static_cast<float*>(const_cast<void*>(p[26])); L.svc = static_cast<float*>(const_cast<void*>(p[27]));
     const int wn[6] = {3 * kD, kD, kD, kD, kFF, kD};
     const int wk[6] = {kD, kD, kD, kD, kD, kFF};
+    const int box_rows[6] = {192, 64, 64, 64, 256, 64};      // the CTA's slice of the output features
+    const int box_kb[6] = {1, 4, 4, 4, 1, 4};                // k-blocks per ring chunk
     for (int w = 0; w < 6; ++w)
-      if ((rc = get_tensor_map(&plan.map_w[l][w], p[6 + 3 * w], wn[w], wk[w], wk[w], 64, 128, true))) return rc;
+      if ((rc = get_tensor_map_kblocks(&plan.map_w[l][w], p[6 + 3 * w], wn[w], wk[w], wk[w], box_rows[w], box_kb[w]))) return rc;
   }
   OT_CHECK_CUDA(cudaMemcpy(plan_dev, &plan, sizeof(plan), cudaMemcpyHostToDevice));
   return OT_OK;

@@ -785,6 +785,28 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
   return OT_OK;
 }
 
+// 3-D view of a K-major int8 matrix [rows, K] (row pitch ld) as (128 bytes of a k-block, row, k-block): one TMA instruction
+// fetches box_rows x box_kb k-block tiles, each landing as [box_rows][128 B] with the 128-byte swizzle, k-blocks back to back.
+int get_tensor_map_kblocks(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows, uint32_t box_kb) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return OT_ECUDA;
+  }
+  cuuint64_t gdim[3] = {128, rows, K / 128};
+  cuuint64_t gstride[2] = {ld, 128};
+  cuuint32_t box[3] = {128, box_rows, box_kb};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (k-block view) failed with CUresult %d (rows %llu K %llu box %u x %u)", (int)r, (unsigned long long)rows,
+              (unsigned long long)K, box_rows, box_kb);
+    return OT_ECUDA;
+  }
+  return OT_OK;
+}
+
 template <int BLOCK_N, int STAGES, int MODE>
 static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   constexpr bool W4 = (MODE == 1);

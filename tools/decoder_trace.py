@@ -57,17 +57,28 @@ else:
     for l in range(6):
         names += ["ln1", "qkv", "sattn", "o", "ln2", "cq", "cattn", "co", "ln3", "ffn1a", "ffn1b", "ffn2"]
     names += ["lnf", "gen"]
-prev = t[255]
 work, wait = {}, {}
-for i, n in enumerate(names):
-    work.setdefault(n, []).append((t[2 * i] - prev) / 1e3)          # CTA 0: phase start -> its arrival at the barrier
-    wait.setdefault(n, []).append((t[2 * i + 1] - t[2 * i]) / 1e3)  # CTA 0: arrival -> release
-    prev = t[2 * i + 1]
-print("phase   n   work_us(CTA0)  barrier_wait_us   sum_us")
-for n in work:
-    print("%-6s x%d   %7.2f   %7.2f   %7.1f" % (n, len(work[n]), np.mean(work[n]), np.mean(wait[n]), np.sum(work[n]) + np.sum(wait[n])))
-print("step total %.1f us" % ((t[2 * len(names) - 1] - t[255]) / 1e3))
 if DEC == "cluster":
+    # cluster decoder: t[2i] = phase i begins waiting for its input bytes, t[2i+1] = they have all arrived; t[254] = step end
+    for i, n in enumerate(names):
+        end = t[2 * (i + 1)] if i + 1 < len(names) else t[254]
+        wait.setdefault(n, []).append((t[2 * i + 1] - t[2 * i]) / 1e3)
+        work.setdefault(n, []).append((end - t[2 * i + 1]) / 1e3)
+    print("phase   n   input_wait_us  work_us(CTA0)   sum_us")
+    for n in work:
+        print("%-10s x%d   %7.2f   %7.2f   %7.1f" % (n, len(work[n]), np.mean(wait[n]), np.mean(work[n]), np.sum(work[n]) + np.sum(wait[n])))
+    print("step total %.1f us" % ((t[254] - t[255]) / 1e3))
+else:
+    prev = t[255]
+    for i, n in enumerate(names):
+        work.setdefault(n, []).append((t[2 * i] - prev) / 1e3)          # CTA 0: phase start -> its arrival at the barrier
+        wait.setdefault(n, []).append((t[2 * i + 1] - t[2 * i]) / 1e3)  # CTA 0: arrival -> release
+        prev = t[2 * i + 1]
+    print("phase   n   work_us(CTA0)  barrier_wait_us   sum_us")
+    for n in work:
+        print("%-6s x%d   %7.2f   %7.2f   %7.1f" % (n, len(work[n]), np.mean(work[n]), np.mean(wait[n]), np.sum(work[n]) + np.sum(wait[n])))
+    print("step total %.1f us" % ((t[2 * len(names) - 1] - t[255]) / 1e3))
+if DEC == "cluster" and "--marks" in sys.argv:
     print("fine marks of layer 2 (id: us since step start, delta):")
     prev = None
     for i in range(150, 250):
