@@ -201,23 +201,32 @@ def persistent_decoder_bytes(eng, B, S, n_steps):
                    "self_kv_read_mean": nl * B * ((n_steps - 1) / 2.0) * (2 * D + 8)}
 
 
-PHASES = ["ln1", "qkv", "self_attn", "o", "ln2", "cq", "cross_attn", "co", "ln3", "ffn1_mma", "ffn1_quant", "ffn2"]
-
-
 def persistent_phase_trace(eng, ws, B, S, t_mid=35):
-    """Per-phase timeline of one greedy step inside the persistent kernel: CTA 0 stamps %globaltimer on entering / leaving
-    every grid barrier (ot_decoder.cu grid_sync).  Returns {phase: us per greedy step (work + barrier wait)} and the step total."""
+    """Per-phase timeline of one greedy step inside the persistent decoder kernel, stamped by CTA 0 with %globaltimer.
+    cluster decoder (ot_cdecoder.cu xwait): t[2i] = phase i starts waiting for its input bytes, t[2i+1] = they have arrived,
+    t[254] = step end; grid decoder (ot_decoder.cu grid_sync): t[2i] / t[2i+1] = arrival at / release from barrier i.
+    Returns {phase: us per greedy step} and the step total."""
+    import torch
+    from onnx_transformer_b200 import kernels as K
     plan = eng._decoder_plan(ws, B, S, trace=True)
     plan.run(t_mid, 2)
-    import torch
     torch.cuda.synchronize()
     t = plan.trace.cpu().numpy()
-    names = PHASES * eng.n_layers + ["final_norm", "generator"]
-    out, prev = {}, t[255]
-    for i, n in enumerate(names):
-        out[n] = out.get(n, 0.0) + (t[2 * i + 1] - prev) / 1e3
-        prev = t[2 * i + 1]
-    total = (t[2 * len(names) - 1] - t[255]) / 1e3
+    out = {}
+    if isinstance(plan, K.ClusterDecoderPlan):
+        names = plan.phase_names()
+        for i, n in enumerate(names):
+            end = t[2 * (i + 1)] if i + 1 < len(names) else t[254]
+            out[n] = out.get(n, 0.0) + (end - t[2 * i]) / 1e3
+        total = (t[254] - t[255]) / 1e3
+    else:
+        names = ["ln1", "qkv", "self_attn", "o", "ln2", "cq", "cross_attn", "co", "ln3", "ffn1_mma", "ffn1_quant", "ffn2"] * eng.n_layers
+        names += ["final_norm", "generator"]
+        prev = t[255]
+        for i, n in enumerate(names):
+            out[n] = out.get(n, 0.0) + (t[2 * i + 1] - prev) / 1e3
+            prev = t[2 * i + 1]
+        total = (t[2 * len(names) - 1] - t[255]) / 1e3
     ws.pop("plan", None)      # drop the tracing plan: the next decode rebuilds the plain one
     return {k: round(float(v), 2) for k, v in out.items()}, float(total)
 
@@ -372,7 +381,7 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"
         n_dec = MAX_LEN - 1
         if persistent:
-            # dominant kernel: decoder_steps_kernel, ONE launch per batch decode (all 71 greedy steps); its duration is the mean of
+            # dominant kernel: the persistent decoder, ONE launch per batch decode (all 71 greedy steps); its duration is the mean of
             # the CUDA-event pairs recorded around each launch INSIDE the timed region, on the launching stream
             kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in dec_events]))
             nbytes, parts = persistent_decoder_bytes(eng, B, S, n_dec)
@@ -383,13 +392,14 @@ def main():
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "decoder_traffic.json")))["dram_bytes_per_launch"]
             except Exception:
                 pass
-            roofline = {"kernel": "decoder_steps_kernel (persistent greedy decoder, %d steps per launch)" % n_dec, "bound": "hbm",
+            kname = "cdecoder_kernel (cluster-resident greedy decoder" if eng.decoder == "cluster" else "decoder_steps_kernel (grid-barrier greedy decoder"
+            roofline = {"kernel": "%s, %d steps per launch)" % (kname, n_dec), "bound": "hbm",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "us_per_launch": kernel_ms * 1e3, "launches_per_step": 1, "algorithmic_bytes_per_launch": nbytes,
                         "algorithmic_bytes_per_greedy_step": parts, "share_of_step": kernel_ms / (total_ms / args.steps),
                         "greedy_step_us": kernel_ms * 1e3 / n_dec, "traced_greedy_step_us": step_us, "phase_us_per_greedy_step": phases,
                         "note": "working set (weights 31 MB + K/V caches 54 MB) is L2-resident; a greedy step at batch 64 is a chain of "
-                                "~74 dependent phases, each bound by grid-barrier + L2 round-trip latency, not by bandwidth (DESIGN.md 4/7)"}
+                                "~74 dependent phases, each bound by exchange + instruction latency, not by bandwidth (DESIGN.md 4/7)"}
         else:
             fam, step_us = decode_family_timeline(eng, ws, B, S)
             nbytes = decode_family_bytes(eng, B, S)

@@ -130,8 +130,13 @@ struct Ctx {
   unsigned long long t_step;
 };
 
-// profiling aid: (id << 32 | ns since the step began) into trace[150 + n]
+// profiling aid, compiled in with -DOT_CD_MARKS (tools/decoder_trace.py --marks): (id << 32 | ns since the step began) into
+// trace[150 + n] at points inside the phases of one layer
 __device__ __forceinline__ void mark(Ctx& c, int id) {
+#ifndef OT_CD_MARKS
+  (void)c; (void)id;
+  return;
+#endif
   if (c.fine && threadIdx.x == 0 && c.mark_slot < 100) {
     c.P->trace[150 + c.mark_slot] = (static_cast<unsigned long long>(id) << 32) | ((tl_now() - c.t_step) & 0xffffffffull);
     ++c.mark_slot;
