@@ -48,7 +48,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -287,6 +287,10 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    # rank 0 must print ONE JSON line on stdout: library chatter (the NCCL version banner ...) goes to stderr until then
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from onnx_transformer_b200 import kernels as K
@@ -431,7 +435,10 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes + mask_np.nbytes), "d2h_bytes_per_step": int(B * MAX_LEN * 8)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
