@@ -75,6 +75,7 @@ static_assert(kSmBh + 16 * 1024 + 7 * 1024 <= kSmTotal, "operand over-read");
 // misc region (floats unless noted)
 constexpr int kMiSB = 0;        // [8] scale of each sentence's current operand row
 constexpr int kMiTok = 12;      // int: the token my sentence feeds this step
+constexpr int kMiSh = 13;       // scale of my sentence's quantized FFN hidden row
 constexpr int kMiRed = 16;      // [64] reduction scratch
 constexpr int kMiGenV = 80;     // [8 ranks][8 sentences]: best logit of rank's vocabulary slice  (written by peers)
 constexpr int kMiGenI = 144;    // [8][8] int: its index
@@ -192,7 +193,9 @@ __device__ __forceinline__ void xwait(Ctx& c, int bar, uint32_t bytes, uint32_t&
 // takes to read (~1 cycle per row) however small N is, so the many weight rows go on the N side (up to 256 per instruction)
 // and the 8 sentences on the M side (M = 64, the smallest).  Chunk = what one ring slot holds:
 //   qkv  (192 rows / CTA): 4 chunks = k-blocks, 3 boxes of 64 rows        o, cq, co (64 rows): 1 chunk = 4 k-blocks (4 boxes)
-//   ffn1 (256 rows / CTA): 4 chunks = k-blocks, 4 boxes of 64 rows        ffn2 (64 rows, K = 2048): 4 chunks of 4 k-blocks
+//   ffn1 (256 rows / CTA): 4 chunks = k-blocks                            ffn2: SPLIT-K -- CTA r takes output rows 256*(r&1)..+256
+//   and k-blocks 4*(r>>1)..+4 (4 chunks): 16 MMAs of N = 256 instead of 64 of N = 64 (an M = 64 MMA costs ~86 cycles whatever N);
+//   the 4 int32 partial planes are summed by the row owner (exact), which also applies the fp32 epilogue
 // Every chunk is ONE TMA instruction (a 3-D box over the (128 B, row, k-block) view of the weight): a warp needs ~0.1 us per TMA
 // instruction, and the loader's warp is also a worker of the row phase that follows.
 struct Chunk { int g, kb0, bytes; };
@@ -201,10 +204,10 @@ __device__ __forceinline__ Chunk chunk_of(int j) {
   if (j < 4) { k.g = 0; k.kb0 = j; k.bytes = 192 * 128; }
   else if (j < 7) { k.g = j - 3; k.kb0 = 0; k.bytes = 4 * 64 * 128; }
   else if (j < 11) { k.g = 4; k.kb0 = j - 7; k.bytes = 256 * 128; }
-  else { k.g = 5; k.kb0 = 4 * (j - 11); k.bytes = 4 * 64 * 128; }
+  else { k.g = 5; k.kb0 = j - 11; k.bytes = 256 * 128; }
   return k;
 }
-__device__ __forceinline__ int slice_rows(int g) { return g == 0 ? 192 : (g == 4 ? 256 : 64); }
+__device__ __forceinline__ int slice_rows(int g) { return g == 0 ? 192 : (g >= 4 ? 256 : 64); }
 
 // loader thread: load weight chunk c.pn into its ring slot (the slot must be free)
 __device__ __forceinline__ void issue_chunk(Ctx& c) {
@@ -216,7 +219,8 @@ __device__ __forceinline__ void issue_chunk(Ctx& c) {
   const uint32_t fb = smem_u32(&c.bars[slot]);
   const uint32_t dst = smem_u32(c.smem + kSmRing + slot * kSlotBytes);
   mbar_arrive_expect_tx(fb, k.bytes);
-  tma_load_3d(dst, map, fb, 0, slice_rows(k.g) * c.rank, k.kb0);
+  if (k.g == 5) tma_load_3d(dst, map, fb, 0, 256 * (c.rank & 1), 4 * (c.rank >> 1) + k.kb0);
+  else tma_load_3d(dst, map, fb, 0, slice_rows(k.g) * c.rank, k.kb0);
   ++c.pn;
 }
 // loader thread: issue every chunk below `upto` (chunk n reuses the slot of chunk n - kSlots, free once that chunk's MMAs have
@@ -247,7 +251,7 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
   const int ngroups = half >> 5;                    // 3 / 1 / 4
   const int srow = lane >> 2;
   float2 sw[16], bb[16];
-  if (epi) {        // per-feature constants: in flight while the operand rows arrive
+  if (epi && g != 5) {        // per-feature constants: in flight while the operand rows arrive
     const float* swp = L.sw[g] + rows * c.rank + col0 + 2 * (lane & 3);
     const float* bp = L.bias[g] + rows * c.rank + col0 + 2 * (lane & 3);
 #pragma unroll
@@ -263,8 +267,9 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
     asm volatile("fence.proxy.async;" ::: "memory");      // operand rows were written through the generic proxy
     const uint32_t abase = smem_u32(c.smem + (g == 5 ? kSmBh : kSmBx));
     const uint32_t idesc = make_idesc_i8(64, rows);
-    const bool by_rows = (g == 0 || g == 4);
+    const bool by_rows = (g == 0 || g >= 4);
     const int nchunks = (g >= 1 && g <= 3) ? 1 : 4;
+    const int kb_base = (g == 5) ? 4 * (c.rank >> 1) : 0;
     for (int ch = 0; ch < nchunks; ++ch) {
       const int slot = c.cn % kSlots;
       mbar_wait(smem_u32(&c.bars[slot]), (c.cn / kSlots) & 1);
@@ -274,7 +279,7 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
 #pragma unroll 1
       for (int i = 0; i < nkb; ++i) {
         const int kb = by_rows ? ch : 4 * ch + i;
-        const uint64_t a_desc = make_smem_desc_sw128(abase + kb * 1024);
+        const uint64_t a_desc = make_smem_desc_sw128(abase + (kb_base + kb) * 1024);
         const uint64_t b_desc = make_smem_desc_sw128(sbase + i * 8192);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -307,11 +312,15 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 w2 = sw[4 * gq + i], b2 = bb[4 * gq + i];
-          float y0 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i])), sx), w2.x), b2.x);
-          float y1 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i + 1])), sx), w2.y), b2.y);
-          if (g == 4) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
-          *reinterpret_cast<float2*>(stage + srow * 32 + 8 * i + 2 * (lane & 3)) = make_float2(y0, y1);
+          if (g == 5) {      // split-K partial: raw int32, the owner sums the 4 planes and applies the epilogue
+            *reinterpret_cast<uint2*>(stage + srow * 32 + 8 * i + 2 * (lane & 3)) = make_uint2(r[4 * i], r[4 * i + 1]);
+          } else {
+            const float2 w2 = sw[4 * gq + i], b2 = bb[4 * gq + i];
+            float y0 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i])), sx), w2.x), b2.x);
+            float y1 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i + 1])), sx), w2.y), b2.y);
+            if (g == 4) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
+            *reinterpret_cast<float2*>(stage + srow * 32 + 8 * i + 2 * (lane & 3)) = make_float2(y0, y1);
+          }
         }
         __syncwarp();
 #pragma unroll
@@ -352,13 +361,15 @@ __device__ __forceinline__ void push_row_q8(Ctx& c, const uint8_t* src, int K, i
 // ------------------------------------------------------------------------------------------------ row phases (owner CTA)
 __device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// LayerNorm of my sentence.  SRC 0: x = embedding(token)*sqrt(d) + pe[t]; SRC 1: x = x + recv (the scattered O / CO / FFN2 row).
+// LayerNorm of my sentence.  SRC 0: x = embedding(token)*sqrt(d) + pe[t]; SRC 1: x = x + recv (the scattered O / CO row);
+// SRC 2: x = x + (fl(fl(float(p0+p1+p2+p3)*s_h)*s_w[f]) + b[f]) with the 4 split-K int32 planes of FFN2 in recv (sw2 / b2 given).
 // quant: RowQuant -> all-gather into Bx; else (final norm) the fp32 row goes to every CTA's generator input.
 // The row is spread over 4 warps -- warp i holds float4 i*32+lane, exactly the element layernorm_row<4> gives lane `lane` in its
 // i-th register -- and every reduction is evaluated in layernorm_row's order: per lane ((p0 + p1) + p2) + p3 over the four
 // registers, then the xor-shuffle tree over lanes.  Same instructions on the same operands => bit-identical results, at a quarter
 // of the dependent-division chain (a single warp spends 2.2 us per row in IEEE divisions).
-__device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, const float* gamma, const float* beta, bool quant) {
+__device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, const float* gamma, const float* beta, bool quant,
+                                         const float* sw2 = nullptr, const float* b2 = nullptr) {
   const CdHot& P = *c.P;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* xr = reinterpret_cast<float*>(c.smem + kSmX);
@@ -376,9 +387,19 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
       const float4 q = __ldg(reinterpret_cast<const float4*>(P.pe + static_cast<int64_t>(t) * kD) + i4);
       v = make_float4(__fadd_rn(__fmul_rn(e.x, P.emb_scale), q.x), __fadd_rn(__fmul_rn(e.y, P.emb_scale), q.y),
                       __fadd_rn(__fmul_rn(e.z, P.emb_scale), q.z), __fadd_rn(__fmul_rn(e.w, P.emb_scale), q.w));
-    } else {
+    } else if (SRC == 1) {
       const float4 res = reinterpret_cast<const float4*>(xr)[i4], y = reinterpret_cast<const float4*>(c.smem + kSmRecv)[i4];
       v = make_float4(__fadd_rn(res.x, y.x), __fadd_rn(res.y, y.y), __fadd_rn(res.z, y.z), __fadd_rn(res.w, y.w));
+    } else {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(sw2) + i4), b4 = __ldg(reinterpret_cast<const float4*>(b2) + i4);
+      const int4* pl = reinterpret_cast<const int4*>(c.smem + kSmRecv);
+      const int4 p0 = pl[i4], p1 = pl[128 + i4], p2 = pl[256 + i4], p3 = pl[384 + i4];
+      const float sh = (misc(c) + kMiSh)[0];
+      const float4 res = reinterpret_cast<const float4*>(xr)[i4];
+      v.x = __fadd_rn(res.x, __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn((p0.x + p1.x) + (p2.x + p3.x)), sh), w4.x), b4.x));
+      v.y = __fadd_rn(res.y, __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn((p0.y + p1.y) + (p2.y + p3.y)), sh), w4.y), b4.y));
+      v.z = __fadd_rn(res.z, __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn((p0.z + p1.z) + (p2.z + p3.z)), sh), w4.z), b4.z));
+      v.w = __fadd_rn(res.w, __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn((p0.w + p1.w) + (p2.w + p3.w)), sh), w4.w), b4.w));
     }
     reinterpret_cast<float4*>(xr)[i4] = v;
     mark(c, 41);
@@ -450,6 +471,7 @@ __device__ __forceinline__ void phase_ffnq(Ctx& c) {
     w.x = quant4_pack(a, s, r);
     w.y = quant4_pack(b, s, r);
     reinterpret_cast<uint2*>(rowq)[tid] = w;
+    if (tid == 0) (misc(c) + kMiSh)[0] = s;
     __syncthreads();
     mark(c, 61);
     push_row_q8(c, rowq, kFF, kSmBh, s);
@@ -902,9 +924,9 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
         }
       }
       // ---- residual + LayerNorm 1 of the next layer, or the final norm (fp32 row to every CTA's generator input)
-      xwait(c, kBarS, kD * 4, c.s_parity, own);
-      if (l + 1 < nl) phase_ln(c, 1, 0, t, P.layer[l + 1].ln_g[0], P.layer[l + 1].ln_b[0], true);
-      else phase_ln(c, 1, 0, t, P.fin_g, P.fin_b, false);
+      xwait(c, kBarS, 4 * kD * 4, c.s_parity, own);      // 4 split-K planes of int32 partials
+      if (l + 1 < nl) phase_ln(c, 2, 0, t, P.layer[l + 1].ln_g[0], P.layer[l + 1].ln_b[0], true, L.sw[5], L.bias[5]);
+      else phase_ln(c, 2, 0, t, P.fin_g, P.fin_b, false, L.sw[5], L.bias[5]);
     }
     c.fine = false;
     xwait(c, kBarG, static_cast<uint32_t>(c.n_own) * kD * 4, c.g_parity, true);
@@ -972,8 +994,8 @@ extern "C" int ot_cdecoder_plan_build(void* plan_dev, int n_layers, int B, int S
     L.skc = static_cast<float*>(const_cast<void*>(p[26])); L.svc = static_cast<float*>(const_cast<void*>(p[27]));
     const int wn[6] = {3 * kD, kD, kD, kD, kFF, kD};
     const int wk[6] = {kD, kD, kD, kD, kD, kFF};
-    const int box_rows[6] = {192, 64, 64, 64, 256, 64};      // the CTA's slice of the output features
-    const int box_kb[6] = {1, 4, 4, 4, 1, 4};                // k-blocks per ring chunk
+    const int box_rows[6] = {192, 64, 64, 64, 256, 256};     // weight rows of a ring chunk
+    const int box_kb[6] = {1, 4, 4, 4, 1, 1};                // k-blocks of a ring chunk
     for (int w = 0; w < 6; ++w)
       if ((rc = get_tensor_map_kblocks(&plan.map_w[l][w], p[6 + 3 * w], wn[w], wk[w], wk[w], box_rows[w], box_kb[w]))) return rc;
   }
