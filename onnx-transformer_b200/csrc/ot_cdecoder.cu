@@ -708,9 +708,19 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
 // logits[s, v] = bias[v] + sum_k h[s,k] * W[v,k]  (k ascending, fmaf: the order of generator_logits_kernel).  The vocabulary is cut
 // into tiles of 32 entries; tile j belongs to CTA j % 8 of every cluster, and inside the CTA to warp (j / 8) % 8.  A lane owns one
 // entry of each of its warp's (up to NT) tiles for all 8 sentences; weights arrive as one coalesced 16-byte load per lane per 4 k.
+// acc = a * (w, w) + acc on both halves: one FFMA2 (fma.rn.f32x2, sm_100) = two IEEE fp32 FMAs, half the issue slots
+__device__ __forceinline__ void fma2(float2& acc, const float2 a, const float w) {
+  uint64_t ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rb) : "f"(w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(acc.x), "f"(acc.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(rc));
+}
+
 template <int NT>
-__device__ __forceinline__ void generator_warp(const CdHot& P, const float* hb, int rank, int warp, int lane, float (&best)[kCS], int (&bidx)[kCS]) {
-  float acc[NT][kCS];
+__device__ __forceinline__ void generator_warp(const CdHot& P, const float* hT, int rank, int warp, int lane, float (&best)[kCS], int (&bidx)[kCS]) {
+  float2 acc[NT][kCS / 2];            // [tile][sentence pair]
   const float4* wp[NT];
   int v[NT];
 #pragma unroll
@@ -719,9 +729,9 @@ __device__ __forceinline__ void generator_warp(const CdHot& P, const float* hb, 
     wp[i] = reinterpret_cast<const float4*>(P.gen_w4) + static_cast<int64_t>(tile) * 128 * 32 + lane;
     v[i] = tile * kGenVT + lane;
 #pragma unroll
-    for (int s = 0; s < kCS; ++s) acc[i][s] = 0.f;
+    for (int s = 0; s < kCS / 2; ++s) acc[i][s] = make_float2(0.f, 0.f);
   }
-  const float4* h4 = reinterpret_cast<const float4*>(hb);
+  const float4* h4 = reinterpret_cast<const float4*>(hT);      // k-major: h4[2k], h4[2k+1] = sentences 0..3, 4..7 of feature k
   constexpr int G = 4;                     // k-quads per register group: the next group's weights are in flight during this group's FMAs
   float4 wn[G][NT];
 #pragma unroll
@@ -741,14 +751,15 @@ __device__ __forceinline__ void generator_warp(const CdHot& P, const float* hb, 
 #pragma unroll
     for (int g = 0; g < G; ++g) {
 #pragma unroll
-      for (int s = 0; s < kCS; ++s) {
-        const float4 h = h4[s * 128 + k0 + g];
+      for (int kk = 0; kk < 4; ++kk) {      // k = 4*(k0+g) + kk, ascending: the fmaf chain of generator_logits_kernel per (sentence, entry)
+        const float4 ha = h4[2 * (4 * (k0 + g) + kk)], hb = h4[2 * (4 * (k0 + g) + kk) + 1];
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-          acc[i][s] = fmaf(h.x, w[g][i].x, acc[i][s]);
-          acc[i][s] = fmaf(h.y, w[g][i].y, acc[i][s]);
-          acc[i][s] = fmaf(h.z, w[g][i].z, acc[i][s]);
-          acc[i][s] = fmaf(h.w, w[g][i].w, acc[i][s]);
+          const float wk = kk == 0 ? w[g][i].x : (kk == 1 ? w[g][i].y : (kk == 2 ? w[g][i].z : w[g][i].w));
+          fma2(acc[i][0], make_float2(ha.x, ha.y), wk);
+          fma2(acc[i][1], make_float2(ha.z, ha.w), wk);
+          fma2(acc[i][2], make_float2(hb.x, hb.y), wk);
+          fma2(acc[i][3], make_float2(hb.z, hb.w), wk);
         }
       }
     }
@@ -759,7 +770,7 @@ __device__ __forceinline__ void generator_warp(const CdHot& P, const float* hb, 
     const float bv = (ok && P.gen_b) ? __ldg(P.gen_b + v[i]) : 0.f;
 #pragma unroll
     for (int s = 0; s < kCS; ++s) {
-      float lg = __fadd_rn(acc[i][s], bv);
+      float lg = __fadd_rn((s & 1) ? acc[i][s >> 1].y : acc[i][s >> 1].x, bv);
       if (lg != lg) lg = INFINITY;               // torch.max / np.argmax: a NaN logit ranks above every number
       if (ok && (lg > best[s] || (lg == best[s] && v[i] < bidx[s]))) { best[s] = lg; bidx[s] = v[i]; }
     }
@@ -769,7 +780,20 @@ __device__ __forceinline__ void generator_warp(const CdHot& P, const float* hb, 
 __device__ __forceinline__ void phase_generator(Ctx& c) {
   const CdHot& P = *c.P;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the gathered rows [sentence][512] -> k-major [512][8 sentences] (second 16 KB of the V region): a sentence PAIR of one
+  // feature is then one 64-bit operand of an FFMA2
   const float* hb = reinterpret_cast<const float*>(c.smem + kSmHb);
+  float* hT = reinterpret_cast<float*>(c.smem + kSmHb + kCS * kD * 4);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int k = tid + 256 * j;
+    float hv[kCS];
+#pragma unroll
+    for (int s = 0; s < kCS; ++s) hv[s] = hb[s * kD + k];
+    reinterpret_cast<float4*>(hT)[2 * k] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    reinterpret_cast<float4*>(hT)[2 * k + 1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+  }
+  __syncthreads();
   float best[kCS];
   int bidx[kCS];
 #pragma unroll
@@ -777,9 +801,9 @@ __device__ __forceinline__ void phase_generator(Ctx& c) {
   // tiles of this warp: rank + 8*(warp + 8*i) < n_gen_tiles
   int nt = 0;
   while (nt < 3 && c.rank + kCS * (warp + 8 * nt) < P.n_gen_tiles) ++nt;
-  if (nt == 3) generator_warp<3>(P, hb, c.rank, warp, lane, best, bidx);
-  else if (nt == 2) generator_warp<2>(P, hb, c.rank, warp, lane, best, bidx);
-  else if (nt == 1) generator_warp<1>(P, hb, c.rank, warp, lane, best, bidx);
+  if (nt == 3) generator_warp<3>(P, hT, c.rank, warp, lane, best, bidx);
+  else if (nt == 2) generator_warp<2>(P, hT, c.rank, warp, lane, best, bidx);
+  else if (nt == 1) generator_warp<1>(P, hT, c.rank, warp, lane, best, bidx);
   float* pv = misc(c) + kMiPartV;
   int* pi = reinterpret_cast<int*>(misc(c) + kMiPartI);
 #pragma unroll
