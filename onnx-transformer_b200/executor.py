@@ -63,7 +63,12 @@ def load_graph(path: str) -> Graph:
 
 
 def _as_graph(module_path_or_graph) -> Graph:
+    """A graph object, an `.otg` archive (save_graph) or a real `.onnx` / `.onnx.gz` file (onnx_reader: protobuf wire reader +
+    the Constant-folding / node-naming part of qonnx's cleanup)."""
     if isinstance(module_path_or_graph, str):
+        if module_path_or_graph.endswith((".onnx", ".onnx.gz")):
+            from . import onnx_reader
+            return onnx_reader.load_onnx(module_path_or_graph)
         return load_graph(module_path_or_graph)
     return module_path_or_graph
 
@@ -267,6 +272,7 @@ HANDLERS = {
     "Unsqueeze": _h_unsqueeze, "MatMul": _h_matmul, "MatMulInteger": _h_matmul_integer,
     "QuantizeLinear": _h_quantize_linear, "DequantizeLinear": _h_dequantize_linear,
     "Shape": _h_shape, "Gather": _h_gather, "ReduceProd": _h_reduce_prod,
+    "Identity": lambda node, ins, wd: ins[0],          # raw exports alias shared initializers (deduplicated biases) this way
 }
 
 

@@ -101,3 +101,49 @@ def synthetic_tokens(seed: int, batch: int, src_len: int, src_vocab: int = SRC_V
             ids[b, lens[b]:] = PAD_ID
     mask = (ids != PAD_ID)[:, None, :]
     return ids, mask
+
+
+# ------------------------------------------------------------------------------------------------ SmoothQuant pre-pass
+def smoothing_plan(n_layers: int = 6) -> List[Tuple[str, List[str], str]]:
+    """(LayerNorm, linears fed by it, key of the activation-scale vector) for every smoothing step of
+    get_quantized_model.smooth_lm (:46-148).  Encoder layer: norm0 -> self-attn q,k,v; norm1 -> w_1.  Decoder layer: norm0 ->
+    self-attn q,k,v; norm1 -> src-attn q AND k,v (the reference scales the k/v projections of `memory` too, :123-131: kept);
+    norm2 -> w_1.  The scale vector of a q/k/v group is the one recorded for its first linear."""
+    plan = []
+    for side, attn_groups in (("encoder", [(0, "self_attn")]), ("decoder", [(0, "self_attn"), (1, "src_attn")])):
+        for l in range(n_layers):
+            p = "%s.layers.%d" % (side, l)
+            for sub, attn in attn_groups:
+                fcs = ["%s.%s.linears.%d" % (p, attn, i) for i in range(3)]
+                plan.append(("%s.sublayer.%d.norm" % (p, sub), fcs, fcs[0]))
+            ffn_sub = len(attn_groups)
+            plan.append(("%s.sublayer.%d.norm" % (p, ffn_sub), [p + ".feed_forward.w_1"], p + ".feed_forward.w_1"))
+    return plan
+
+
+def smooth_lm(float_weights: Dict[str, np.ndarray], act_scales: Dict[str, np.ndarray], n_layers: int = 6, alpha: float = 0.5) -> Dict[str, np.ndarray]:
+    """SmoothQuant as the reference applies it before quantisation (get_quantized_model.py:10-36 smooth_ln_fcs, :46-148 smooth_lm):
+    an OFFLINE transform of the fp32 state_dict -- per input channel j of a LayerNorm -> linear(s) pair,
+        s_j = clamp(act_j^alpha / clamp(max_rows |W[:, j]|, 1e-5)^(1-alpha), 1e-5);  a_2, b_2 /= s;  W[:, j] *= s_j
+    -- so it stays on the host, like in the reference (torch CPU there, numpy fp32 here; same op order).  Returns a new dict; the
+    result feeds QuantizedTransformer / graph.build_*_graph."""
+    w = dict(float_weights)
+    f32 = np.float32
+    for ln, fcs, key in smoothing_plan(n_layers):
+        act = np.asarray(act_scales[key], dtype=f32)
+        col_max = np.max(np.stack([np.max(np.abs(w[fc + ".weight"]), axis=0) for fc in fcs]), axis=0).astype(f32)
+        col_max = np.maximum(col_max, f32(1e-5))
+        s = np.maximum((np.power(act, f32(alpha)) / np.power(col_max, f32(1.0 - alpha))).astype(f32), f32(1e-5))
+        assert s.shape == w[ln + ".a_2"].shape
+        w[ln + ".a_2"] = (w[ln + ".a_2"] / s).astype(f32)
+        w[ln + ".b_2"] = (w[ln + ".b_2"] / s).astype(f32)
+        for fc in fcs:
+            w[fc + ".weight"] = (w[fc + ".weight"] * s[None, :]).astype(f32)
+    return w
+
+
+def load_act_scales(path: str) -> Dict[str, np.ndarray]:
+    """scales/transformer_scales.pt of the reference (get_quantized_scales.py:125): {linear name: abs-max per input channel}."""
+    import torch
+    blob = torch.load(path, map_location="cpu")
+    return {k: np.asarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32) for k, v in blob.items()}

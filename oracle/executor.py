@@ -121,10 +121,21 @@ def run_node(node, ins: List[Optional[np.ndarray]], prov: Optional[dict] = None,
             prov[node.output[0]] = src
         return out
     if op == "Unsqueeze":
+        axes = _attr(node, "axes")
+        if axes is None:                       # opset 13: axes is the second input
+            axes = [int(a) for a in np.asarray(ins[1]).reshape(-1)]
         out = x
-        for ax in sorted(int(a) for a in _attr(node, "axes")):
+        for ax in sorted(int(a) for a in axes):
             out = np.expand_dims(out, ax)
         return out
+    if op == "Identity":
+        return x
+    if op == "Shape":                          # the raw (un-cleaned) export computes N and N-1 of every LayerNorm on the fly
+        return np.asarray(x.shape, dtype=np.int64)
+    if op == "Gather":
+        return np.take(x, np.asarray(ins[1], dtype=np.int64), axis=int(_attr(node, "axis", 0)))
+    if op == "ReduceProd":
+        return np.prod(x, axis=None if _attr(node, "axes") is None else tuple(_attr(node, "axes")), keepdims=bool(_attr(node, "keepdims", 1)))
     if op == "MatMul":
         a, b = ins[0], ins[1]
         pa, pb = prov.get(node.input[0]), prov.get(node.input[1])

@@ -1,0 +1,85 @@
+"""Real ONNX import: tests/golden/ref_encoder_tiny.onnx.gz is a genuine opset-13 file written by torch's ONNX
+exporter from the REFERENCE's own modules (model.make_model + get_quantized_model.quantize_transformer, 1 encoder layer, d_model
+128; tests/golden/make_onnx_fixture.py), with the torch model's input / output beside it.  The protobuf wire reader must recover
+the graph the survey describes, the oracle executor must reproduce the reference model's output on it (this pins the oracle's
+node-by-node restatement against a reference artefact), and on the GPU the product executor must agree with both."""
+import os
+
+import numpy as np
+import pytest
+
+from onnx_transformer_b200 import onnx_reader as R
+from oracle import executor as oex
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ONNX = os.path.join(HERE, "golden", "ref_encoder_tiny.onnx.gz")
+IO = os.path.join(HERE, "golden", "ref_encoder_tiny_io.npz")
+
+# non-constant nodes of one exported encoder layer and of the final norm
+LAYER = {"Div": 32, "Mul": 20, "Round": 14, "Abs": 13, "ReduceMax": 13, "Clip": 13, "Add": 12, "Transpose": 10, "MatMul": 8, "ReduceMean": 6,
+         "Sub": 6, "Cast": 5, "Reshape": 4, "Shape": 2, "Gather": 2, "ReduceProd": 2, "Sqrt": 2, "Softmax": 1, "Where": 1, "Equal": 1, "Relu": 1,
+         "Unsqueeze": 1}
+FINAL_NORM = {"ReduceMean": 3, "Sub": 3, "Mul": 3, "Div": 2, "Add": 2, "Cast": 1, "Shape": 1, "Gather": 1, "ReduceProd": 1, "Sqrt": 1}
+
+
+def test_wire_reader_recovers_the_exported_graph():
+    g = R.load_onnx(ONNX)
+    hist = g.op_histogram()
+    identity = hist.pop("Identity", 0)          # the exporter aliases equal (deduplicated) biases through Identity nodes
+    assert identity == 3
+    want = dict(LAYER)
+    for k, v in FINAL_NORM.items():
+        want[k] = want.get(k, 0) + v
+    assert hist == want, {k: (hist.get(k), want.get(k)) for k in set(hist) | set(want) if hist.get(k) != want.get(k)}
+    assert sum(LAYER.values()) == 169 and len(g.node) == 169 + sum(FINAL_NORM.values()) + 3
+    assert [(v.name, tuple(v.shape), v.dtype) for v in g.input] == [("global_in", (2, 5, 128), "float32"), ("global_in_1", (2, 1, 5), "bool")]
+    assert [v.name for v in g.output] == ["global_out"]
+    inits = {i.name: i.array for i in g.initializer}
+    assert inits["layers.0.self_attn.linears.1.weight"].shape == (128, 128) and inits["layers.0.feed_forward.w_1.bias"].dtype == np.float32
+    names = [n.name for n in g.node]
+    assert len(set(names)) == len(names) and "MatMul_7" in names and "Round_13" in names       # unique <OpType>_<k> names
+    clip = g.node_by_name("Clip_0")
+    assert clip.input[2] == ""                   # the empty third Clip input the reference patches around (onnx_optimized_inference.py:29-31)
+    assert all(n.op_type != "Constant" for n in g.node)
+    tr = [n for n in g.node if n.op_type == "Transpose"][0]
+    assert tr.attr("perm") in ([1, 0], [0, 2, 1, 3], [0, 2, 3, 1])
+
+
+def test_reader_rejects_garbage():
+    with pytest.raises(R.OnnxFormatError):
+        R.read_model(b"\x0a\xff\xff\xff\xff\x0f")          # a length-delimited field longer than the buffer
+    with pytest.raises(R.OnnxFormatError):
+        R.read_model(b"\x08\x01")                           # a ModelProto without a graph
+
+
+@pytest.mark.parametrize("mode", ["ref-float", "int-exact"])
+def test_oracle_executor_reproduces_the_reference_model_on_its_own_export(mode):
+    g = R.load_onnx(ONNX)
+    io = np.load(IO)
+    feeds = {"global_in": io["x"], "global_in_1": io["mask"]}
+    wd, graph = oex.prepare_inference(g, feeds)
+    out, wd = oex.run_module("Encoder", feeds, None, wd, graph, mode=mode)
+    y = out["global_out"]
+    assert y.shape == io["y"].shape
+    np.testing.assert_allclose(y, io["y"], rtol=0, atol=5e-6)      # |y| <= 3.3: float reductions only
+    assert "/layers.0/sublayer.0/self_attn/Softmax_output_0" in wd    # every intermediate is retained under its ONNX tensor name
+
+
+@pytest.mark.gpu
+def test_product_executor_runs_the_real_onnx_file():
+    from onnx_transformer_b200 import executor as ex
+    io = np.load(IO)
+    feeds = {"global_in": io["x"], "global_in_1": io["mask"]}
+    wd, graph = ex.prepare_inference(ONNX, feeds)
+    out, wd = ex.run_module("Encoder", feeds, ONNX, wd, graph)
+    y = ex.to_numpy(out)["global_out"]
+    np.testing.assert_allclose(y, io["y"], rtol=0, atol=3e-3 * float(np.abs(io["y"]).max()))   # 1e-3 relative class
+    # integer tensors against the oracle walk of the same graph: every Round output, bit for bit up to rounding-boundary flips
+    wd_o, graph_o = oex.prepare_inference(R.load_onnx(ONNX), feeds)
+    _, wd_o = oex.run_module("Encoder", feeds, None, wd_o, graph_o, mode="int-exact")
+    rounds = [n.output[0] for n in graph_o.node if n.op_type == "Round"]
+    assert len(rounds) == 14
+    for name in rounds:
+        got, want = ex.to_numpy({name: wd[name]})[name], wd_o[name]
+        assert got.shape == want.shape
+        assert np.mean(got != want) < 2e-3 and np.max(np.abs(got - want)) <= 1.0, name
