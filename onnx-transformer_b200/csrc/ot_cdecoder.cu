@@ -677,8 +677,9 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
 #pragma unroll
   for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
     if (kk * 32 >= Tk) break;
-#pragma unroll 4
-    for (int jj = 0; jj < 32; jj += 2) {
+    const int jend = min(32, Tk - kk * 32);        // keys past Tk have p = 0: adding +0 to a sum that is never -0 changes nothing
+#pragma unroll 8
+    for (int jj = 0; jj < jend; jj += 2) {
       const float4 ps = *reinterpret_cast<const float4*>(pv + kk * 32 + jj);      // p, sv of keys jj and jj+1
       const char2 va = *reinterpret_cast<const char2*>(Vs + (kk * 32 + jj) * kD + h * kDk + d0);
       const char2 vb = *reinterpret_cast<const char2*>(Vs + (kk * 32 + jj + 1) * kD + h * kDk + d0);
