@@ -101,3 +101,31 @@ def test_int4_weight_engine_matches_oracle():
             if ys[b, t + 1] != ref_ys[b, t + 1]:
                 assert margins[b, t] < 0.1, (b, t, margins[b, t])
                 break
+
+
+def test_cfg3_full_size_encoder_is_sentence_shardable():
+    """BASELINE config #3 (encoder only, 512 sentences x 128 source tokens): the size-independent property the multi-GPU partition
+    rests on -- a sentence's memory rows do not depend on which other sentences share its batch, bit for bit (no cross-sentence op)."""
+    from onnx_transformer_b200.engine import QuantizedTransformer
+    fw = W.init_float_weights(0)
+    eng = QuantizedTransformer(fw)
+    ids, mask = W.synthetic_tokens(7, 512, 128, min_len=40)
+    idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    full = eng.encode(idt, mt).clone()
+    assert full.shape == (512, 128, 512) and bool(torch.isfinite(full).all())
+    for lo, hi in ((0, 8), (250, 314), (505, 512)):          # shards of 8 / 64 / 7 sentences, as rank r of N would see them
+        part = eng.encode(idt[lo:hi].contiguous(), mt[lo:hi].contiguous())
+        assert torch.equal(part.view(torch.int32), full[lo:hi].view(torch.int32)), (lo, hi)
+
+
+def test_cluster_decoder_any_batch_size():
+    """The cluster-resident decoder has no co-residency requirement: 80 sentences = 10 independent clusters, same tokens as the
+    per-op path."""
+    from onnx_transformer_b200.engine import QuantizedTransformer
+    fw = W.init_float_weights(5, 211, 197, 2, randomize_norms=True)
+    ep = QuantizedTransformer(fw, n_layers=2, max_len=12, decoder="cluster")
+    eg = QuantizedTransformer(fw, n_layers=2, max_len=12, persistent=False)
+    ids, mask = W.synthetic_tokens(9, 80, 23, 211, min_len=6)
+    idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    assert torch.equal(ep.greedy_decode(idt, mt, 12), eg.greedy_decode(idt, mt, 12))
+    assert ep.persistent_steps == 11
