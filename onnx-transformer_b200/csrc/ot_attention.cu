@@ -22,7 +22,7 @@ __device__ __forceinline__ float patch_f32(const OtFault& f, float v) {
 }
 
 template <int QT>
-__global__ void __launch_bounds__(256, 1) attention_q8_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(256, QT <= 8 ? 2 : 1) attention_q8_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const unsigned int tl = tl_begin(2);
   pdl_wait();      // upstream results are complete and visible from here on
@@ -490,6 +490,10 @@ extern "C" int ot_attention_q8_mf(const int8_t* q, int64_t ldq, const float* sq,
     return OT_OK;
   }
   if (Tq == 1) return launch_attention<1>(a, tk_max, s);
+  // short sequences: tiles of 8 queries keep the CTA under half of the shared memory, so two CTAs (16 warps) share an SM -- the
+  // kernel is latency-bound at 8 warps per SM -- and the grid has 4x more CTAs to fill the 148 SMs with
+  if (Tq > 1 && attn_smem_bytes<8>(tk_max) <= 113 * 1024 && static_cast<int64_t>(B) * ((Tq + 31) / 32) < 4 * 148)
+    return launch_attention<8>(a, tk_max, s);
   if (Tq <= 16 || attn_smem_bytes<32>(tk_max) > 227 * 1024) return launch_attention<16>(a, tk_max, s);
   return launch_attention<32>(a, tk_max, s);
 }
