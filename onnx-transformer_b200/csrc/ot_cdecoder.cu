@@ -262,7 +262,7 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
       }
     }
   }
-  xwait(c, kBarG, static_cast<uint32_t>(c.n_own) * (g == 5 ? kFF + 4 : kD + 4), c.g_parity, true);
+  xwait(c, kBarG, static_cast<uint32_t>(c.n_own) * (kD + 4), c.g_parity, true);      // 512 operand bytes + the scale per sentence
   if (tid == kIssuer) {
     asm volatile("fence.proxy.async;" ::: "memory");      // operand rows were written through the generic proxy
     const uint32_t abase = smem_u32(c.smem + (g == 5 ? kSmBh : kSmBx));
@@ -341,15 +341,16 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
 }
 
 // ------------------------------------------------------------------------------------------------ all-gather helpers
-// Push the int8 row staged at `src` (K bytes, K = 512 or 2048) into row `rank` of every CTA's operand buffer (128-byte swizzle:
-// 16-byte chunk c of a row lands at chunk c ^ (row & 7) of its 128-byte line; k-blocks 1 KB apart), plus its scale.
+// Push the int8 row staged at `src` into row `rank` of every CTA's operand buffer (128-byte swizzle: 16-byte chunk c of a row lands
+// at chunk c ^ (row & 7) of its 128-byte line; k-blocks 1 KB apart), plus its scale.  K = 512: the whole row to every peer.
+// K = 2048 (the FFN hidden row): FFN2 is split-K, peer p only consumes k-blocks 4*(p>>1)..+4, so it is only sent those 512 bytes
+// (a quarter of the DSMEM traffic of a full all-gather).  Either way a peer receives 512 + 4 bytes per sentence.
 __device__ __forceinline__ void push_row_q8(Ctx& c, const uint8_t* src, int K, int dst_off, float scale) {
   const int tid = threadIdx.x;
-  const int chunks = K >> 4;                       // 32 or 128
-  const int per_peer_shift = (K == 512) ? 5 : 7;
   const uint32_t gbar = smem_u32(&c.bars[kBarG]);
-  for (int idx = tid; idx < chunks * kCS; idx += kThreads) {
-    const int peer = idx >> per_peer_shift, ch = idx & (chunks - 1);
+  {
+    const int peer = tid >> 5;                                    // 256 threads = 8 peers x 32 chunks of 16 bytes
+    const int ch = (K == kD ? 0 : 32 * (peer >> 1)) + (tid & 31);
     const uint4 v = *reinterpret_cast<const uint4*>(src + ch * 16);
     const int kb = ch >> 3, cc = ch & 7;
     const uint32_t local = smem_u32(c.smem + dst_off + kb * 1024 + c.rank * 128 + ((cc ^ (c.rank & 7)) << 4));
