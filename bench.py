@@ -106,7 +106,7 @@ def run_reference_arm(args):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b, sample_steps = 16, 8
+    sample_b, sample_steps = 16, 16          # ~3 s of CPU work per timed step on 16 cores
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_sample(2, args.src_len, 2)
     vals, secs = [], []
@@ -422,9 +422,9 @@ def main():
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            v, dt = cpu_reference_sample(16, S, 8)
+            v, dt = cpu_reference_sample(16, S, 32)            # ~10-15 s of CPU work
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "oracle port (numpy ref-float, full-prefix recompute, %d BLAS threads): 16 sentences x %d src tokens, first 8 of 71 "
+                   "sample": "oracle port (numpy ref-float, full-prefix recompute, %d BLAS threads): 16 sentences x %d src tokens, first 32 of 71 "
                              "greedy steps, %.1f s" % (cores, S, dt)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
