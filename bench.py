@@ -54,9 +54,13 @@ class ClockSampler:
             return
         def reader():
             for line in self.proc.stdout:
-                self.samples.append(line.strip())
+                self.samples.append((time.time(), line.strip()))
         self.thread = threading.Thread(target=reader, daemon=True)
         self.thread.start()
+
+    def mark_begin(self):
+        """Samples from here on belong to the timed region (nvidia-smi itself is started earlier: it needs ~100 ms to come up)."""
+        self.t_begin = time.time()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -68,7 +72,20 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.samples:
+        t_begin = getattr(self, "t_begin", 0.0)
+        timed = [line for (t, line) in self.samples if t >= t_begin]
+        window = "timed region"
+        if len(timed) < 2:            # a very short timed region: fall back to the samples taken under the same load just before it
+            timed = [line for (_, line) in self.samples][-5:]
+            window = "warm-up + timed region"
+        if not timed:                 # nothing at all: one synchronous query, flagged as such
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
+                timed, window = out[:1], "single query after the timed region"
+            except Exception:
+                pass
+        for line in timed:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -80,7 +97,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm (oracle port)
@@ -349,6 +366,8 @@ def main():
             total_ms += e0.elapsed_time(e1)
         return total_ms
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                      # before the warm-up: nvidia-smi needs ~100 ms to deliver its first sample
     for _ in range(args.warmup):
         one_step()
     sync_all()
@@ -356,10 +375,9 @@ def main():
     persistent = ws.get("plan") is not None
     eng.decoder_events = [] if persistent else None     # CUDA events around every decoder_steps_kernel launch of the timed region
     launches_per_graph = ws.get("graph_launches", 0)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     l0, r0 = K._lib.launch_count(), eng.graph_replays
     sync_all()
+    sampler.mark_begin()
     total_ms = timed_loop(one_step, args.steps)
     sync_all()
     launches = (K._lib.launch_count() - l0) + (eng.graph_replays - r0) * launches_per_graph
