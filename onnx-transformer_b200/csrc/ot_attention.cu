@@ -375,6 +375,152 @@ __global__ void __launch_bounds__(256, QT <= 8 ? 2 : 1) attention_q8_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Encoder-size specialisation (Tq >= 32, fault-free, fp32 context requested): one CTA per (sentence, HEAD).  The kernel above
+// stages all 8 heads' K / V of a sentence (132 KB at Tk = 128: one CTA of 8 warps per SM) and is latency-bound at 0.25 IPC; a
+// head's K / V slice is 18 KB, so three of these CTAs (24 warps) share an SM and a sentence's K / V bytes are read once instead of
+// once per query tile.  Same arithmetic, op for op, as the fast path of attention_q8_kernel (groups of kQG queries; P.V walks the
+// keys in order for the whole group).  The per-token RowQuant of the merged context needs all 8 heads of a row, i.e. 8 CTAs:
+// ot_attention_q8 runs rowquant_kernel on the fp32 context afterwards (same quant_scale / quant_one instructions).
+constexpr int kKhPitch = kDk + 16;     // 80-byte K rows: conflict-free 128-bit reads with lane = key
+
+__global__ void __launch_bounds__(256) attention_heads_kernel(const AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  pdl_wait();
+  pdl_trigger();
+  const int Tk = a.Tk, Tq = a.Tq;
+  const int Tk_pad = (Tk + 31) & ~31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  int8_t* Kh = reinterpret_cast<int8_t*>(smem);                              // [Tk_pad][80]
+  int8_t* Vh = Kh + static_cast<size_t>(Tk_pad) * kKhPitch;                  // [Tk_pad][64]
+  int8_t* Qh = Vh + static_cast<size_t>(Tk_pad) * kDk;                       // [Tq][64]
+  float* Pw = reinterpret_cast<float*>(Qh + ((static_cast<size_t>(Tq) * kDk + 15) & ~static_cast<size_t>(15)));   // [8 warps][Tk_pad][kQG]
+  float* sks = Pw + static_cast<size_t>(8) * Tk_pad * kQG;                   // [Tk_pad]
+  float* svs = sks + Tk_pad;
+  uint8_t* keep = reinterpret_cast<uint8_t*>(svs + Tk_pad);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int idx = tid; idx < Tk * 4; idx += 256) {
+    const int j = idx >> 2, c = idx & 3;
+    const int64_t src = (static_cast<int64_t>(b) * a.Tk_cap + j) * a.ldk + h * kDk + c * 16;
+    *reinterpret_cast<uint4*>(Kh + j * kKhPitch + c * 16) = *reinterpret_cast<const uint4*>(a.k + src);
+    *reinterpret_cast<uint4*>(Vh + j * kDk + c * 16) = *reinterpret_cast<const uint4*>(a.v + src);
+  }
+  for (int idx = tid; idx < Tq * 4; idx += 256) {
+    const int i = idx >> 2, c = idx & 3;
+    *reinterpret_cast<uint4*>(Qh + i * kDk + c * 16) =
+        *reinterpret_cast<const uint4*>(a.q + (static_cast<int64_t>(b) * Tq + i) * a.ldq + h * kDk + c * 16);
+  }
+  for (int j = tid; j < Tk_pad; j += 256) {
+    float s1 = 0.f, s2 = 0.f;
+    uint8_t kp = 0;
+    if (j < Tk) {
+      const int64_t src = (static_cast<int64_t>(b) * a.Tk_cap + j) * a.skv_stride;
+      s1 = a.sk[src];
+      s2 = a.sv[src];
+      kp = (a.mask_kind == 1) ? a.key_mask[static_cast<int64_t>(b) * a.mask_stride + j] : 1;
+    }
+    sks[j] = s1; svs[j] = s2; keep[j] = kp;
+  }
+  __syncthreads();
+
+  float* P = Pw + static_cast<size_t>(warp) * Tk_pad * kQG;
+  const int d0 = 2 * lane;
+  for (int g0 = warp * kQG; g0 < Tq; g0 += 8 * kQG) {
+    const int ng = min(kQG, Tq - g0);
+#pragma unroll 1
+    for (int qq = 0; qq < kQG; ++qq) {
+      if (qq >= ng) {
+#pragma unroll
+        for (int kk = 0; kk < kKeysPerLane; ++kk)
+          if (kk * 32 < Tk_pad) P[(kk * 32 + lane) * kQG + qq] = 0.f;
+        continue;
+      }
+      const int i = g0 + qq;
+      const float sqi = a.sq[(static_cast<int64_t>(b) * Tq + i) * a.sq_stride];
+      uint32_t qw[16];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint4 t = *reinterpret_cast<const uint4*>(Qh + i * kDk + w * 16);
+        qw[4 * w] = t.x; qw[4 * w + 1] = t.y; qw[4 * w + 2] = t.z; qw[4 * w + 3] = t.w;
+      }
+      float sc[kKeysPerLane];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int kk = 0; kk < kKeysPerLane; ++kk) {
+        const int j = kk * 32 + lane;
+        sc[kk] = -INFINITY;
+        if (kk * 32 < Tk && j < Tk) {
+          int dot = 0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint4 t = *reinterpret_cast<const uint4*>(Kh + j * kKhPitch + w * 16);
+            dot = __dp4a(static_cast<int>(qw[4 * w]), static_cast<int>(t.x), dot);
+            dot = __dp4a(static_cast<int>(qw[4 * w + 1]), static_cast<int>(t.y), dot);
+            dot = __dp4a(static_cast<int>(qw[4 * w + 2]), static_cast<int>(t.z), dot);
+            dot = __dp4a(static_cast<int>(qw[4 * w + 3]), static_cast<int>(t.w), dot);
+          }
+          const float sv_ = __fdiv_rn(__fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), sks[j]), 8.0f);
+          const bool visible = keep[j] && (a.mask_kind != 2 || j <= a.q_pos0 + i);
+          sc[kk] = visible ? sv_ : -1e9f;
+          mx = fmaxf(mx, sc[kk]);
+        }
+      }
+      mx = warp_max_f(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < kKeysPerLane; ++kk) {
+        const int j = kk * 32 + lane;
+        if (kk * 32 < Tk && j < Tk) {
+          sc[kk] = expf(__fsub_rn(sc[kk], mx));
+          sum += sc[kk];
+        }
+      }
+      sum = warp_sum_f(sum);
+#pragma unroll
+      for (int kk = 0; kk < kKeysPerLane; ++kk) {
+        const int j = kk * 32 + lane;
+        if (kk * 32 < Tk_pad) {
+          float ph = 0.f;
+          if (j < Tk) ph = __fdiv_rn(rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f)), 127.0f);   // Round(Mul(p,127)) then Div(127)
+          P[j * kQG + qq] = ph;
+        }
+      }
+    }
+    __syncwarp();
+    float acc[kQG][2];
+#pragma unroll
+    for (int qq = 0; qq < kQG; ++qq) acc[qq][0] = acc[qq][1] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < Tk; ++j) {
+      const char2 vv = *reinterpret_cast<const char2*>(Vh + j * kDk + d0);
+      const float svj = svs[j];
+      const float v0 = __fmul_rn(__int2float_rn(vv.x), svj), v1 = __fmul_rn(__int2float_rn(vv.y), svj);
+      const float4 pa = *reinterpret_cast<const float4*>(P + j * kQG);
+      const float4 pb = *reinterpret_cast<const float4*>(P + j * kQG + 4);
+      acc[0][0] = fmaf(pa.x, v0, acc[0][0]); acc[0][1] = fmaf(pa.x, v1, acc[0][1]);
+      acc[1][0] = fmaf(pa.y, v0, acc[1][0]); acc[1][1] = fmaf(pa.y, v1, acc[1][1]);
+      acc[2][0] = fmaf(pa.z, v0, acc[2][0]); acc[2][1] = fmaf(pa.z, v1, acc[2][1]);
+      acc[3][0] = fmaf(pa.w, v0, acc[3][0]); acc[3][1] = fmaf(pa.w, v1, acc[3][1]);
+      acc[4][0] = fmaf(pb.x, v0, acc[4][0]); acc[4][1] = fmaf(pb.x, v1, acc[4][1]);
+      acc[5][0] = fmaf(pb.y, v0, acc[5][0]); acc[5][1] = fmaf(pb.y, v1, acc[5][1]);
+      acc[6][0] = fmaf(pb.z, v0, acc[6][0]); acc[6][1] = fmaf(pb.z, v1, acc[6][1]);
+      acc[7][0] = fmaf(pb.w, v0, acc[7][0]); acc[7][1] = fmaf(pb.w, v1, acc[7][1]);
+    }
+#pragma unroll
+    for (int qq = 0; qq < kQG; ++qq)
+      if (qq < ng)
+        *reinterpret_cast<float2*>(a.ctx + (static_cast<int64_t>(b) * Tq + g0 + qq) * a.ld_ctx + h * kDk + d0) = make_float2(acc[qq][0], acc[qq][1]);
+    __syncwarp();
+  }
+}
+
+static size_t attn_heads_smem_bytes(int Tq, int Tk) {
+  const size_t Tk_pad = (Tk + 31) & ~31;
+  return Tk_pad * kKhPitch + Tk_pad * kDk + ((static_cast<size_t>(Tq) * kDk + 15) & ~static_cast<size_t>(15)) + 8 * Tk_pad * kQG * 4 + 2 * Tk_pad * 4 +
+         Tk_pad + 16;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Decode specialisation (Tq = 1, Tk <= 96, no fault, no probability dump): one CTA per sentence, warp h = head h,
 // K/V rows are read straight from the (L2-resident) cache -- no shared-memory staging, no block barrier before the
 // head merge.  Same arithmetic, op for op, as attention_q8_kernel; the body lives in ot_attention_decode.cuh.
@@ -487,6 +633,20 @@ extern "C" int ot_attention_q8_mf(const int8_t* q, int64_t ldq, const float* sq,
   if (Tq == 1 && tk_max <= 32 * kDecKeysPerLane && a.fault.mode == OT_FAULT_NONE && a.mf_unit == nullptr && probs_q == nullptr) {
     OT_CHECK_CUDA(launch_kernel(attention_decode_kernel, dim3(B), dim3(256), 0, s, 1, a));
     count_launch();
+    return OT_OK;
+  }
+  if (Tq >= 32 && ctx != nullptr && a.fault.mode == OT_FAULT_NONE && a.mf_unit == nullptr && probs_q == nullptr && k_new == nullptr &&
+      step_dev == nullptr && attn_heads_smem_bytes(Tq, Tk) <= 100 * 1024) {
+    const size_t smem = attn_heads_smem_bytes(Tq, Tk);
+    static size_t configured = 0;
+    if (smem > configured) {
+      OT_CHECK_CUDA(cudaFuncSetAttribute(attention_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      configured = smem;
+    }
+    OT_CHECK_CUDA(launch_kernel(attention_heads_kernel, dim3(kHeads, B), dim3(256), smem, s, 1, a));
+    count_launch();
+    if (ctx_q != nullptr)     // the merged rows are complete only across the 8 head CTAs: RowQuant as a second launch
+      return ot_rowquant(ctx, ld_ctx, static_cast<int64_t>(B) * Tq, kDm, kDm, ctx_q, ctx_s, nullptr, stream);
     return OT_OK;
   }
   if (Tq == 1) return launch_attention<1>(a, tk_max, s);

@@ -237,7 +237,8 @@ class QuantizedTransformer:
         if ws is None:
             e = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=self.dev)  # noqa: E731
             ws = dict(x=[e(M, D), e(M, D)], xq=e(M, D, dt=torch.int8), sx=e(M), qkv=e(M, 3 * D, dt=torch.int8), sqkv=e(M, 3),
-                      cq=e(M, D, dt=torch.int8), cs=e(M), hq=e(M, FF, dt=torch.int8), sh=e(M, 1))
+                      cq=e(M, D, dt=torch.int8), cs=e(M), hq=e(M, FF, dt=torch.int8), sh=e(M, 1),
+                      ctx=e(M, D))     # fp32 context: the per-(sentence, head) attention kernel quantizes it in a second launch
             self._enc_ws = {M: ws}   # keep only the latest shape resident
         return ws
 
@@ -267,7 +268,7 @@ class QuantizedTransformer:
             self._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], fk)
             K.attention_q8(ws["qkv"], ws["sqkv"], ws["qkv"][:, D:], ws["qkv"][:, 2 * D:], ws["sqkv"][:, 1:], ws["sqkv"][:, 2:],
                            B=B, Tq=S, Tk=S, ldq=3 * D, sq_stride=3, ldk=3 * D, skv_stride=3, mask_kind=1, key_mask=mask, mask_stride=S,
-                           want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], **fk("qk", "pv"))
+                           want_ctx=True, ctx=ws["ctx"], want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], **fk("qk", "pv"))
             L["o"].gemm(ws["cq"], ws["cs"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("o"))
             x, cur = nxt, 1 - cur
