@@ -264,7 +264,7 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
   }
   xwait(c, kBarG, static_cast<uint32_t>(c.n_own) * (kD + 4), c.g_parity, true);      // 512 operand bytes + the scale per sentence
   if (tid == kIssuer) {
-    asm volatile("fence.proxy.async;" ::: "memory");      // operand rows were written through the generic proxy
+    fence_proxy_async_smem();      // operand rows were written through the generic proxy (shared memory only: the narrow fence)
     const uint32_t abase = smem_u32(c.smem + (g == 5 ? kSmBh : kSmBx));
     const uint32_t idesc = make_idesc_i8(64, rows);
     const bool by_rows = (g == 0 || g >= 4);
@@ -493,7 +493,7 @@ __device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* v
   const uint32_t bar = smem_u32(&c.bars[kBarKv]);
   const int w = threadIdx.x >> 5;
   if (threadIdx.x == 32) {
-    asm volatile("fence.proxy.async;" ::: "memory");     // the V region was last touched through the generic proxy
+    fence_proxy_async_smem();     // the V region was last touched through the generic proxy
     mbar_arrive_expect_tx(bar, static_cast<uint32_t>(n_old) * kD);
   }
   __syncwarp();
