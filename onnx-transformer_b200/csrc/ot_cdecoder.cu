@@ -604,7 +604,7 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
       L.skc[static_cast<int64_t>(c.b) * P.cap + t] = sc3[1];
       L.svc[static_cast<int64_t>(c.b) * P.cap + t] = sc3[2];
     }
-    if (tid < 64) asm volatile("fence.proxy.async;" ::: "memory");   // later steps read these rows through bulk copies (async proxy)
+    if (tid < 64) asm volatile("fence.proxy.async.global;" ::: "memory");   // later steps read these rows through bulk copies (async proxy)
 #pragma unroll
     for (int kk = 0; kk < kDecKeysPerLane; ++kk)
       if (kk * 32 + lane == t) { pre.skl[kk] = sc3[1]; pre.svl[kk] = sc3[2]; }
