@@ -488,7 +488,7 @@ struct AttnPre {
 // Issued during the preceding GEMM phase: the old V rows of my sentence into shared memory (one 512-byte bulk copy per row; the
 // copies run in the TMA unit) and, per lane, the scales / mask of its keys j = 32*kk + lane.  Issued by warps 1, 2, 3 and 5: idle
 // during a GEMM phase (0 / 4: epilogue, 6: weight ring, 7: MMA issuer); a warp needs ~20 ns per bulk-copy instruction.
-__device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* v, int64_t ldk, int64_t row0, const float* sk, const float* sv,
+__device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* k, const int8_t* v, int64_t ldk, int64_t row0, const float* sk, const float* sv,
                                               int64_t sstride, const uint8_t* key_mask, int mask_stride, AttnPre& pre) {
   const uint32_t bar = smem_u32(&c.bars[kBarKv]);
   const int w = threadIdx.x >> 5;
@@ -498,8 +498,13 @@ __device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* v
   }
   __syncwarp();
   if (w == 1 || w == 2 || w == 3 || w == 5) {
-    for (int j = (w == 5 ? 96 : (w - 1) * 32) + (threadIdx.x & 31); j < n_old; j += 128)
+    for (int j = (w == 5 ? 96 : (w - 1) * 32) + (threadIdx.x & 31); j < n_old; j += 128) {
       bulk_load(smem_u32(c.smem + kSmVs + j * kD), v + (row0 + j) * ldk, kD, bar);
+      // the K row of the same key: towards L1 (the attention phase reads the head slices with ld.global.ca)
+      const int8_t* kr = k + (row0 + j) * ldk;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) asm volatile("prefetch.global.L1 [%0];" ::"l"(kr + q * 128));
+    }
   }
   const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -579,7 +584,7 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
       kq[i] = make_uint4(0, 0, 0, 0);
       if (8 * i < n_old) {
         const int j = min(8 * i + m8, n_old - 1);
-        kq[i] = __ldcg(reinterpret_cast<const uint4*>(kbase + j * ldk + h * kDk) + ch);
+        kq[i] = __ldca(reinterpret_cast<const uint4*>(kbase + j * ldk + h * kDk) + ch);
       }
     }
   }
@@ -933,7 +938,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
           // ---- GEMM phases; the attention operands of my sentence are prefetched alongside
           if ((q == 0 || q == 4) && own) {
             const bool self = q == 0;
-            attn_prefetch(c, self ? t : P.S, self ? L.vc : P.ckv + 2 * kD * l + kD, self ? kD : 2 * kD * nl,
+            attn_prefetch(c, self ? t : P.S, self ? L.kc : P.ckv + 2 * kD * l, self ? L.vc : P.ckv + 2 * kD * l + kD, self ? kD : 2 * kD * nl,
                           static_cast<int64_t>(c.b) * (self ? P.cap : P.S), self ? L.skc : P.sckv + 2 * l, self ? L.svc : P.sckv + 2 * l + 1,
                           self ? 1 : 2 * nl, self ? nullptr : P.mask, P.S, pre);
           }
