@@ -426,7 +426,7 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
     v.w = __fadd_rn(__fdiv_rn(__fmul_rn(g.w, v.w), denom), be.w);
     mark(c, 42);
     if (quant) {
-      const float am = warp_max(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      const float am = warp_max_nonneg(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
       if (lane == 0) red[32 + warp] = am;
       bar_sync_128();
       const float s = quant_scale(fmaxf(fmaxf(red[32], red[33]), fmaxf(red[34], red[35])));
@@ -463,7 +463,7 @@ __device__ __forceinline__ void phase_ffnq(Ctx& c) {
     const float4* y4 = reinterpret_cast<const float4*>(c.smem + kSmRecv);
     const float4 a = y4[2 * tid], b = y4[2 * tid + 1];
     float am = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
-    am = warp_max(am);
+    am = warp_max_nonneg(am);
     if (lane == 0) red[warp] = am;
     __syncthreads();
     const float s = quant_scale(fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]))));
@@ -536,8 +536,8 @@ __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale
       am[j] = fmaxf(fmaxf(fabsf(y[j].x), fabsf(y[j].y)), fmaxf(fabsf(y[j].z), fabsf(y[j].w)));
     }
   }
-  am[0] = warp_max(am[0]);
-  am[1] = warp_max(am[1]);
+  am[0] = warp_max_nonneg(am[0]);
+  am[1] = warp_max_nonneg(am[1]);
   if (lane == 0) { red[warp] = am[0]; red[8 + warp] = am[1]; }
   __syncthreads();
   scale[0] = quant_scale(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])));
@@ -698,7 +698,7 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
   // RowQuant of the merged context row (all 8 heads): the row abs-max is a max (exact in any order), every lane quantizes its own
   // two features with the instructions of attention_decode_body
   mark(c, 56);
-  const float am = warp_max_f(fmaxf(fabsf(acc0), fabsf(acc1)));
+  const float am = warp_max_nonneg(fmaxf(fabsf(acc0), fabsf(acc1)));
   if (lane == 0) red[24 + h] = am;
   __syncthreads();
   const float amax = fmaxf(fmaxf(fmaxf(red[24], red[25]), fmaxf(red[26], red[27])), fmaxf(fmaxf(red[28], red[29]), fmaxf(red[30], red[31])));

@@ -16,6 +16,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Max of a NON-NEGATIVE quantity over the warp as one redux.sync: IEEE floats >= 0 order like their bit patterns.  A NaN lane
+// counts as 0 -- fmaxf ignores NaN operands the same way, and every user clamps the result with fmaxf(., 1e-5f), so the all-NaN
+// corner gives the same scale as the shuffle tree of warp_max.
+__device__ __forceinline__ float warp_max_nonneg(float v) {
+  return __uint_as_float(__reduce_max_sync(0xffffffffu, (v == v) ? __float_as_uint(v) : 0u));
+}
+
 // RowQuant of quant_linear.py:31-43: s = max(amax, 1e-5) / 127 ; q = rint(x / s).
 __device__ __forceinline__ float quant_scale(float amax) { return __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f); }
 __device__ __forceinline__ int quant_one(float x, float s) { return __float2int_rn(rintf(__fdiv_rn(x, s))); }
