@@ -656,7 +656,7 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
     mx = live ? fmaxf(mx, sc[kk]) : mx;
   }
   mark(c, 54);
-  mx = warp_max_f(mx);
+  mx = warp_max_any(mx);
   float sum = 0.f;
 #pragma unroll
   for (int kk = 0; kk < kDecKeysPerLane; ++kk) {

@@ -23,6 +23,16 @@ __device__ __forceinline__ float warp_max_nonneg(float v) {
   return __uint_as_float(__reduce_max_sync(0xffffffffu, (v == v) ? __float_as_uint(v) : 0u));
 }
 
+// Max of ANY floats over the warp as one redux.sync through the order-preserving map float -> uint (flip all bits of negatives,
+// the sign bit of non-negatives).  NaN lanes count as -inf, as fmaxf ignores them.
+__device__ __forceinline__ float warp_max_any(float v) {
+  uint32_t u = (v == v) ? __float_as_uint(v) : 0xff800000u;
+  u ^= (u & 0x80000000u) ? 0xffffffffu : 0x80000000u;
+  u = __reduce_max_sync(0xffffffffu, u);
+  u ^= (u & 0x80000000u) ? 0x80000000u : 0xffffffffu;
+  return __uint_as_float(u);
+}
+
 // RowQuant of quant_linear.py:31-43: s = max(amax, 1e-5) / 127 ; q = rint(x / s).
 __device__ __forceinline__ float quant_scale(float amax) { return __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f); }
 __device__ __forceinline__ int quant_one(float x, float s) { return __float2int_rn(rintf(__fdiv_rn(x, s))); }
