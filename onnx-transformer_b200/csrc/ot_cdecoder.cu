@@ -715,19 +715,25 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
 // logits[s, v] = bias[v] + sum_k h[s,k] * W[v,k]  (k ascending, fmaf: the order of generator_logits_kernel).  The vocabulary is cut
 // into tiles of 32 entries; tile j belongs to CTA j % 8 of every cluster, and inside the CTA to warp (j / 8) % 8.  A lane owns one
 // entry of each of its warp's (up to NT) tiles for all 8 sentences; weights arrive as one coalesced 16-byte load per lane per 4 k.
-// acc = a * (w, w) + acc on both halves: one FFMA2 (fma.rn.f32x2, sm_100) = two IEEE fp32 FMAs, half the issue slots
-__device__ __forceinline__ void fma2(float2& acc, const float2 a, const float w) {
-  uint64_t ra, rb, rc;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(rb) : "f"(w));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(acc.x), "f"(acc.y));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(rc));
+// Packed fp32 pairs stay in 64-bit registers for the whole loop: one FFMA2 (fma.rn.f32x2, sm_100) = two IEEE fp32 FMAs for one
+// issue slot.  (Packing / unpacking around every FMA cost four extra moves each: the first version of this loop was 50 % MOV / IMAD.)
+__device__ __forceinline__ void fma2(unsigned long long& acc, const unsigned long long a, const unsigned long long ww) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(ww));
+}
+__device__ __forceinline__ unsigned long long dup2(const float w) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(w));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(const unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
 }
 
 template <int NT>
 __device__ __forceinline__ void generator_warp(const CdHot& P, const float* hT, int rank, int warp, int lane, float (&best)[kCS], int (&bidx)[kCS]) {
-  float2 acc[NT][kCS / 2];            // [tile][sentence pair]
+  unsigned long long acc[NT][kCS / 2];            // [tile][sentence pair], packed (lo = even sentence)
   const float4* wp[NT];
   int v[NT];
 #pragma unroll
@@ -736,9 +742,9 @@ __device__ __forceinline__ void generator_warp(const CdHot& P, const float* hT, 
     wp[i] = reinterpret_cast<const float4*>(P.gen_w4) + static_cast<int64_t>(tile) * 128 * 32 + lane;
     v[i] = tile * kGenVT + lane;
 #pragma unroll
-    for (int s = 0; s < kCS / 2; ++s) acc[i][s] = make_float2(0.f, 0.f);
+    for (int s = 0; s < kCS / 2; ++s) acc[i][s] = 0ull;
   }
-  const float4* h4 = reinterpret_cast<const float4*>(hT);      // k-major: h4[2k], h4[2k+1] = sentences 0..3, 4..7 of feature k
+  const ulonglong2* h2 = reinterpret_cast<const ulonglong2*>(hT);      // k-major: h2[2k] = sentence pairs (0,1),(2,3); h2[2k+1] = (4,5),(6,7)
   constexpr int G = 4;                     // k-quads per register group: the next group's weights are in flight during this group's FMAs
   float4 wn[G][NT];
 #pragma unroll
@@ -759,14 +765,14 @@ __device__ __forceinline__ void generator_warp(const CdHot& P, const float* hT, 
     for (int g = 0; g < G; ++g) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {      // k = 4*(k0+g) + kk, ascending: the fmaf chain of generator_logits_kernel per (sentence, entry)
-        const float4 ha = h4[2 * (4 * (k0 + g) + kk)], hb = h4[2 * (4 * (k0 + g) + kk) + 1];
+        const ulonglong2 ha = h2[2 * (4 * (k0 + g) + kk)], hb = h2[2 * (4 * (k0 + g) + kk) + 1];
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-          const float wk = kk == 0 ? w[g][i].x : (kk == 1 ? w[g][i].y : (kk == 2 ? w[g][i].z : w[g][i].w));
-          fma2(acc[i][0], make_float2(ha.x, ha.y), wk);
-          fma2(acc[i][1], make_float2(ha.z, ha.w), wk);
-          fma2(acc[i][2], make_float2(hb.x, hb.y), wk);
-          fma2(acc[i][3], make_float2(hb.z, hb.w), wk);
+          const unsigned long long ww = dup2(kk == 0 ? w[g][i].x : (kk == 1 ? w[g][i].y : (kk == 2 ? w[g][i].z : w[g][i].w)));
+          fma2(acc[i][0], ha.x, ww);
+          fma2(acc[i][1], ha.y, ww);
+          fma2(acc[i][2], hb.x, ww);
+          fma2(acc[i][3], hb.y, ww);
         }
       }
     }
@@ -776,10 +782,15 @@ __device__ __forceinline__ void generator_warp(const CdHot& P, const float* hT, 
     const bool ok = v[i] < P.vocab;
     const float bv = (ok && P.gen_b) ? __ldg(P.gen_b + v[i]) : 0.f;
 #pragma unroll
-    for (int s = 0; s < kCS; ++s) {
-      float lg = __fadd_rn((s & 1) ? acc[i][s >> 1].y : acc[i][s >> 1].x, bv);
-      if (lg != lg) lg = INFINITY;               // torch.max / np.argmax: a NaN logit ranks above every number
-      if (ok && (lg > best[s] || (lg == best[s] && v[i] < bidx[s]))) { best[s] = lg; bidx[s] = v[i]; }
+    for (int s2 = 0; s2 < kCS / 2; ++s2) {
+      const float2 pr = unpack2(acc[i][s2]);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int s = 2 * s2 + e;
+        float lg = __fadd_rn(e ? pr.y : pr.x, bv);
+        if (lg != lg) lg = INFINITY;               // torch.max / np.argmax: a NaN logit ranks above every number
+        if (ok && (lg > best[s] || (lg == best[s] && v[i] < bidx[s]))) { best[s] = lg; bidx[s] = v[i]; }
+      }
     }
   }
 }
