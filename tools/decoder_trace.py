@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from onnx_transformer_b200 import weights as W  # noqa: E402
 from onnx_transformer_b200.engine import QuantizedTransformer  # noqa: E402
 
-B, S = 64, 64
+B, S = int(os.environ.get("OT_B", "64")), 64
 fw = W.init_float_weights(0)
 ids, mask = W.synthetic_tokens(1000, B, S)
 ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
