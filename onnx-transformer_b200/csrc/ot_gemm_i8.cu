@@ -75,7 +75,9 @@ struct GemmSmem {
   static constexpr int BAR_OFF = TILE_BYTES;                       // full[S], empty[S], tmem_full, unpacked[S]
   static constexpr int SLOT_OFF = BAR_OFF + (3 * STAGES + 1) * 8;  // TMEM base address slot
   static constexpr int ROWMAX_OFF = BAR_OFF + 256;                 // float [kMaxCluster][128]
-  static constexpr int COLP_OFF = ROWMAX_OFF + kMaxCluster * 2 * kBlockM * 4;  // float col_scale[BLOCK_N], bias[BLOCK_N]
+  // a quant group is at most 2048 columns: at most 2048 / BLOCK_N CTAs exchange row maxima
+  static constexpr int MAX_CL = (2048 / BLOCK_N) < kMaxCluster ? (2048 / BLOCK_N) : kMaxCluster;
+  static constexpr int COLP_OFF = ROWMAX_OFF + MAX_CL * 2 * kBlockM * 4;  // float col_scale[BLOCK_N], bias[BLOCK_N]
   static constexpr int ROWS_OFF = COLP_OFF + 2 * 256 * 4;                  // float row_scale[128] (LN prologue)
   static constexpr int B4_OFF = ROWS_OFF + kBlockM * 4;                    // 128-byte aligned (TMA destination)
   static_assert((3 * STAGES + 1) * 8 + 16 <= 256, "barrier block overflows its 256-byte slot");
@@ -361,8 +363,10 @@ __device__ __forceinline__ void trace_mark(const GemmArgs& g, int slot) {
 
 // MODE 0: int8 weights; 1: packed int4 weights unpacked in shared memory; 2: int8 weights, A = RowQuant(LayerNorm(x)) computed
 // by the epilogue warps straight into the swizzled operand tile (K = 512 = STAGES k-blocks, all resident).
+// STAGES == 2 is the large-M requant variant: half the operand ring (K = 512 is 4 k-blocks) so that TWO CTAs share an SM and one
+// CTA's epilogue (the long part: 0.3 issue slots per cycle at 8 epilogue warps) overlaps the other's TMA / MMA main loop.
 template <int BLOCK_N, int STAGES, int MODE>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, STAGES == 2 ? 2 : 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GemmArgs g) {
   constexpr bool W4 = (MODE == 1);
   constexpr bool ALN = (MODE == 2);
@@ -883,6 +887,8 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
     }
   }
   constexpr int M01 = MODE == 1 ? 1 : 0;
+  if (MODE == 0 && block_n == 256 && g.out_kind == OT_OUT_Q8 && static_cast<int64_t>(m_tiles) * (g.N / 256) >= 2 * 148 && !getenv("OT_GEMM_ONE_CTA"))
+    return launch_gemm<256, 2, 0>(g, stream);
   switch (block_n) {
     case 256: return launch_gemm<256, 3, M01>(g, stream);
     case 128: return launch_gemm<128, 4, M01>(g, stream);
