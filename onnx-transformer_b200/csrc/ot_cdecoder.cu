@@ -410,14 +410,14 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) sum += part[i * 32 + lane];
-    const float mu = __fdiv_rn(warp_sum(sum), nf);
+    const float mu = __fmul_rn(warp_sum(sum), 1.0f / kD);       // division by 512 = multiplication by 2^-9, bit for bit (also for subnormals)
     v.x = __fsub_rn(v.x, mu); v.y = __fsub_rn(v.y, mu); v.z = __fsub_rn(v.z, mu); v.w = __fsub_rn(v.w, mu);
     part[128 + warp * 32 + lane] = (__fmul_rn(v.x, v.x) + __fmul_rn(v.y, v.y)) + (__fmul_rn(v.z, v.z) + __fmul_rn(v.w, v.w));
     bar_sync_128();
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) sq += part[128 + i * 32 + lane];
-    float var = __fdiv_rn(warp_sum(sq), nf);
+    float var = __fmul_rn(warp_sum(sq), 1.0f / kD);
     var = __fdiv_rn(__fmul_rn(var, nf), nf - 1.0f);
     const float denom = __fadd_rn(__fsqrt_rn(var), 1e-6f);
     v.x = __fadd_rn(__fdiv_rn(__fmul_rn(g.x, v.x), denom), be.x);
@@ -648,7 +648,7 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
 #pragma unroll
   for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
     const int j = kk * 32 + lane;
-    const float s = __fdiv_rn(__fmul_rn(__fmul_rn(__int2float_rn(dotl[kk]), sqi), pre.skl[kk]), 8.0f);
+    const float s = __fmul_rn(__fmul_rn(__fmul_rn(__int2float_rn(dotl[kk]), sqi), pre.skl[kk]), 0.125f);      // / sqrt(d_k) = / 8: exact scaling
     const bool visible = pre.keepl[kk] != 0 && (mask_kind != 2 || j <= q_pos0);
     const bool live = j < Tk;
     sc[kk] = live ? (visible ? s : -1e9f) : -INFINITY;
