@@ -429,7 +429,7 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
       const float am = warp_max_nonneg(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
       if (lane == 0) red[32 + warp] = am;
       bar_sync_128();
-      const float s = quant_scale(fmaxf(fmaxf(red[32], red[33]), fmaxf(red[34], red[35])));
+      const float s = quant_scale_x(fmaxf(fmaxf(red[32], red[33]), fmaxf(red[34], red[35])));
       reinterpret_cast<uint32_t*>(rowq)[i4] = quant4_pack(v, s, __frcp_rn(s));
       if (tid == 0) red[0] = s;
     } else {
@@ -466,7 +466,7 @@ __device__ __forceinline__ void phase_ffnq(Ctx& c) {
     am = warp_max_nonneg(am);
     if (lane == 0) red[warp] = am;
     __syncthreads();
-    const float s = quant_scale(fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]))));
+    const float s = quant_scale_x(fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]))));
     const float r = __frcp_rn(s);
     uint2 w;
     w.x = quant4_pack(a, s, r);
@@ -540,11 +540,11 @@ __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale
   am[1] = warp_max_nonneg(am[1]);
   if (lane == 0) { red[warp] = am[0]; red[8 + warp] = am[1]; }
   __syncthreads();
-  scale[0] = quant_scale(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])));
+  scale[0] = quant_scale_x(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])));
   scale[1] = scale[2] = 0.f;
   if (NG == 3) {
-    scale[1] = quant_scale(fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
-    scale[2] = quant_scale(fmaxf(fmaxf(red[8], red[9]), fmaxf(red[10], red[11])));
+    scale[1] = quant_scale_x(fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
+    scale[2] = quant_scale_x(fmaxf(fmaxf(red[8], red[9]), fmaxf(red[10], red[11])));
   }
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
@@ -671,7 +671,7 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
   float2* pv = reinterpret_cast<float2*>(c.smem + kSmRecv) + h * kMaxKeys;     // (the scattered q|k|v row has been consumed)
 #pragma unroll
   for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
-    const float pqk = (kk * 32 + lane < Tk) ? __fdiv_rn(rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f)), 127.0f) : 0.f;
+    const float pqk = (kk * 32 + lane < Tk) ? div127_exact(rintf(__fmul_rn(__fdiv_rn(sc[kk], sum), 127.0f))) : 0.f;
     pv[kk * 32 + lane] = make_float2(pqk, svl[kk]);
   }
   __syncwarp();
@@ -702,7 +702,7 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
   if (lane == 0) red[24 + h] = am;
   __syncthreads();
   const float amax = fmaxf(fmaxf(fmaxf(red[24], red[25]), fmaxf(red[26], red[27])), fmaxf(fmaxf(red[28], red[29]), fmaxf(red[30], red[31])));
-  const float s = __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f);
+  const float s = quant_scale_x(amax);
   const uint32_t q01 = quant4_pack(make_float4(acc0, acc1, 0.f, 0.f), s, __frcp_rn(s));
   *reinterpret_cast<uint16_t*>(c.smem + kSmRow + 1536 + h * kDk + d0) = static_cast<uint16_t>(q01 & 0xFFFFu);
   __syncthreads();

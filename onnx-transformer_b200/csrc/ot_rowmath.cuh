@@ -33,6 +33,19 @@ __device__ __forceinline__ float warp_max_any(float v) {
   return __uint_as_float(u);
 }
 
+// x / 127 rounded exactly like IEEE division, for 0 or 1e-5 <= x <= 1e30, without the div.rn expansion (range check + branch to a
+// subroutine): r = RN(1/127) refined by one Newton step, quotient corrected by one exact FMA residual.  tools/check_div127.c
+// compares the sequence with x / 127.0f for EVERY float in [1e-5, 1e30] (975,318,303 values): 0 mismatches.  Outside that range the
+// true division is used.
+__device__ __forceinline__ float div127_exact(float x) {
+  const float r = 0.007874015718698502f;                 // RN(1/127)
+  const float r2 = __fmaf_rn(__fmaf_rn(-127.0f, r, 1.0f), r, r);
+  const float q0 = __fmul_rn(x, r2);
+  const float q1 = __fmaf_rn(__fmaf_rn(-127.0f, q0, x), r2, q0);
+  return (x == 0.0f || (x >= 1e-5f && x <= 1e30f)) ? q1 : __fdiv_rn(x, 127.0f);
+}
+__device__ __forceinline__ float quant_scale_x(float amax) { return div127_exact(fmaxf(amax, 1e-5f)); }
+
 // RowQuant of quant_linear.py:31-43: s = max(amax, 1e-5) / 127 ; q = rint(x / s).
 __device__ __forceinline__ float quant_scale(float amax) { return __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f); }
 __device__ __forceinline__ int quant_one(float x, float s) { return __float2int_rn(rintf(__fdiv_rn(x, s))); }
