@@ -418,7 +418,7 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
 #pragma unroll
     for (int i = 0; i < 4; ++i) sq += part[128 + i * 32 + lane];
     float var = __fmul_rn(warp_sum(sq), 1.0f / kD);
-    var = __fdiv_rn(__fmul_rn(var, nf), nf - 1.0f);
+    var = div511_exact(__fmul_rn(var, nf));                     // * N / (N-1)
     const float denom = __fadd_rn(__fsqrt_rn(var), 1e-6f);
     v.x = __fadd_rn(__fdiv_rn(__fmul_rn(g.x, v.x), denom), be.x);
     v.y = __fadd_rn(__fdiv_rn(__fmul_rn(g.y, v.y), denom), be.y);

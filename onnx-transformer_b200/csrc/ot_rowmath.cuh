@@ -45,6 +45,14 @@ __device__ __forceinline__ float div127_exact(float x) {
   return (x == 0.0f || (x >= 1e-5f && x <= 1e30f)) ? q1 : __fdiv_rn(x, 127.0f);
 }
 __device__ __forceinline__ float quant_scale_x(float amax) { return div127_exact(fmaxf(amax, 1e-5f)); }
+// x / 511 (the N-1 of the 512-feature LayerNorm), same construction, checked for every float in [1e-37, 1e37] (2,062,065,881 values).
+__device__ __forceinline__ float div511_exact(float x) {
+  const float r = 1.0f / 511.0f;                         // RN(1/511), folded at compile time
+  const float r2 = __fmaf_rn(__fmaf_rn(-511.0f, r, 1.0f), r, r);
+  const float q0 = __fmul_rn(x, r2);
+  const float q1 = __fmaf_rn(__fmaf_rn(-511.0f, q0, x), r2, q0);
+  return (x == 0.0f || (x >= 1e-37f && x <= 1e37f)) ? q1 : __fdiv_rn(x, 511.0f);
+}
 
 // RowQuant of quant_linear.py:31-43: s = max(amax, 1e-5) / 127 ; q = rint(x / s).
 __device__ __forceinline__ float quant_scale(float amax) { return __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f); }
