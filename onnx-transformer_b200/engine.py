@@ -315,7 +315,9 @@ class QuantizedTransformer:
 
     def _decoder_plan(self, ws: dict, B: int, S: int, trace: bool = False):
         """The persistent decoder's plan for this workspace (built once), or None when the shapes / weights rule it out."""
-        if not self.persistent or self.weight_bits != 8 or S > 96 or self.max_len > 96 or self.n_layers > 8:
+        if not self.persistent or S > 96 or self.max_len > 96 or self.n_layers > 8:
+            return None
+        if self.weight_bits != 8 and self.decoder != "cluster":
             return None
         if self.decoder == "cluster":
             return self._cluster_plan(ws, B, S, trace)
@@ -360,7 +362,9 @@ class QuantizedTransformer:
             for l, L in enumerate(self.dec):
                 row = [L["ln1"][0], L["ln1"][1], L["ln2"][0], L["ln2"][1], L["ln3"][0], L["ln3"][1]]
                 for name in ("qkv", "o", "cq", "co", "w1", "w2"):
-                    row += [L[name].wq, L[name].sw, L[name].bias]
+                    # 4-bit weights (cfg4): the decoder's working set is L2-resident either way, so it reads the int8 copy of the
+                    # [-8, 7] values the packed GEMM would unpack in shared memory -- same int32 accumulators, same scales
+                    row += [L[name].wq8 if L[name].w4 else L[name].wq, L[name].sw, L[name].bias]
                 row += [ws["kc"][l], ws["vc"][l], ws["skc"][l], ws["svc"][l]]
                 layers.append(row)
             if getattr(self, "_gen_w4", None) is None:

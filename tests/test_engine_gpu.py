@@ -94,7 +94,11 @@ def test_int4_weight_engine_matches_oracle():
     ref = om.encode(w4, ox.embed(ids, w4["src_embed.0.lut.weight"], pe), mask, "int-exact", 2)
     err = np.abs(mem - ref)
     assert err.mean() < 2e-2 and err.max() < 0.3
-    ys = eng.greedy_decode(idt, mt, 9).cpu().numpy()
+    ys_t = eng.greedy_decode(idt, mt, 9)
+    assert eng.persistent_steps == 8          # the cluster decoder runs cfg4 too (on the int8 copy of the 4-bit values)
+    eng_g = QuantizedTransformer(fw, n_layers=2, max_len=9, weight_bits=4, persistent=False)     # packed-int4 GEMMs, per-op path
+    assert torch.equal(ys_t, eng_g.greedy_decode(idt, mt, 9))
+    ys = ys_t.cpu().numpy()
     ref_ys, margins, _ = om.greedy_decode(w4, ids, mask, 9, 0, "int-exact", 2, return_margins=True)
     for b in range(3):
         for t in range(8):
