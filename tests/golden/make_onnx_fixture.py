@@ -68,6 +68,23 @@ def main():
     np.savez_compressed(os.path.join(out_dir, "ref_encoder_tiny_io.npz"), x=x.numpy(), mask=mask.numpy(), y=y.numpy())
     print("wrote", path + ".gz", len(raw), "bytes raw")
 
+    # ---- the decoder of the same model (1 layer): inputs as onnx_optimized_custom_inference.py:646-651 feeds them
+    T = 4
+    xt = torch.randn(B, T, 128)
+    tgt_mask = torch.tril(torch.ones(1, T, T, dtype=torch.int64))          # subsequent_mask(T)
+    with torch.no_grad():
+        yd = model.decoder(xt, y, mask, tgt_mask)
+    path = os.path.join(out_dir, "ref_decoder_tiny.onnx")
+    torch.onnx.export(model.decoder, (xt, y, mask, tgt_mask), path, opset_version=13, dynamo=False,
+                      input_names=["global_in", "global_in_1", "global_in_2", "global_in_3"], output_names=["global_out"])
+    raw = open(path, "rb").read()
+    with gzip.open(path + ".gz", "wb", compresslevel=9) as f:
+        f.write(raw)
+    os.remove(path)
+    np.savez_compressed(os.path.join(out_dir, "ref_decoder_tiny_io.npz"), x=xt.numpy(), memory=y.numpy(), src_mask=mask.numpy(),
+                        tgt_mask=tgt_mask.numpy(), y=yd.numpy())
+    print("wrote", path + ".gz", len(raw), "bytes raw")
+
 
 if __name__ == "__main__":
     main()

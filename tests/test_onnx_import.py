@@ -65,6 +65,50 @@ def test_oracle_executor_reproduces_the_reference_model_on_its_own_export(mode):
     assert "/layers.0/sublayer.0/self_attn/Softmax_output_0" in wd    # every intermediate is retained under its ONNX tensor name
 
 
+DEC_ONNX = os.path.join(HERE, "golden", "ref_decoder_tiny.onnx.gz")
+DEC_IO = os.path.join(HERE, "golden", "ref_decoder_tiny_io.npz")
+# non-constant nodes of one exported decoder layer
+DEC_LAYER = {"Div": 56, "Mul": 34, "Round": 25, "Abs": 23, "ReduceMax": 23, "Clip": 23, "Add": 19, "Transpose": 18, "MatMul": 14, "ReduceMean": 9,
+             "Sub": 9, "Cast": 9, "Reshape": 8, "Shape": 3, "Gather": 3, "ReduceProd": 3, "Sqrt": 3, "Softmax": 2, "Where": 2, "Equal": 2,
+             "Unsqueeze": 2, "Relu": 1}
+
+
+def _decoder_feeds():
+    io = np.load(DEC_IO)
+    return io, {"global_in": io["x"], "global_in_1": io["memory"], "global_in_2": io["src_mask"], "global_in_3": io["tgt_mask"]}
+
+
+def test_decoder_export_matches_the_survey_and_the_reference_model():
+    """The decoder of the same reference model (1 layer; inputs as onnx_optimized_custom_inference.py:646-651 feeds them: embedded
+    prefix, memory, source key mask, causal mask): op histogram of SURVEY App. B (291 nodes per layer) and the torch output."""
+    g = R.load_onnx(DEC_ONNX)
+    hist = g.op_histogram()
+    hist.pop("Identity", None)
+    want = dict(DEC_LAYER)
+    for k, v in FINAL_NORM.items():
+        want[k] = want.get(k, 0) + v
+    assert sum(DEC_LAYER.values()) == 291
+    assert hist.get("Cast") in (9, 10)       # this torch version shares one mask Cast between the two attention blocks
+    want["Cast"] = hist["Cast"]
+    assert hist == want, {k: (hist.get(k), want.get(k)) for k in set(hist) | set(want) if hist.get(k) != want.get(k)}
+    assert [(v.name, v.dtype) for v in g.input] == [("global_in", "float32"), ("global_in_1", "float32"), ("global_in_2", "bool"), ("global_in_3", "int64")]
+    io, feeds = _decoder_feeds()
+    for mode in ("ref-float", "int-exact"):
+        wd, graph = oex.prepare_inference(R.load_onnx(DEC_ONNX), feeds)
+        out, wd = oex.run_module("Decoder", feeds, None, wd, graph, mode=mode)
+        np.testing.assert_allclose(out["global_out"], io["y"], rtol=0, atol=5e-6)
+
+
+@pytest.mark.gpu
+def test_product_executor_runs_the_real_decoder_onnx_file():
+    from onnx_transformer_b200 import executor as ex
+    io, feeds = _decoder_feeds()
+    wd, graph = ex.prepare_inference(DEC_ONNX, feeds)
+    out, wd = ex.run_module("Decoder", feeds, DEC_ONNX, wd, graph)
+    y = ex.to_numpy(out)["global_out"]
+    np.testing.assert_allclose(y, io["y"], rtol=0, atol=3e-3 * float(np.abs(io["y"]).max()))
+
+
 @pytest.mark.gpu
 def test_product_executor_runs_the_real_onnx_file():
     from onnx_transformer_b200 import executor as ex
