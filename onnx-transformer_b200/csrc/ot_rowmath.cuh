@@ -93,7 +93,11 @@ __device__ __forceinline__ float layernorm_row(float4 (&v)[VEC], int lane, int n
 #pragma unroll
   for (int i = 0; i < VEC; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float nf = static_cast<float>(n);
-  const float mu = __fdiv_rn(warp_sum(sum), nf);
+  // n = 512 (every LayerNorm of this model): the divisions by N and N-1 as exact equivalents (a power-of-two scaling; the FMA
+  // sequence of div511_exact, verified for every float) -- same bits, no div.rn expansion; any other n takes the IEEE divisions
+  const bool n512 = (n == 512);
+  const float tot = warp_sum(sum);
+  const float mu = n512 ? __fmul_rn(tot, 0.001953125f) : __fdiv_rn(tot, nf);
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -103,8 +107,9 @@ __device__ __forceinline__ float layernorm_row(float4 (&v)[VEC], int lane, int n
     v[i].w = __fsub_rn(v[i].w, mu);
     sq += (__fmul_rn(v[i].x, v[i].x) + __fmul_rn(v[i].y, v[i].y)) + (__fmul_rn(v[i].z, v[i].z) + __fmul_rn(v[i].w, v[i].w));
   }
-  float var = __fdiv_rn(warp_sum(sq), nf);                    // ReduceMean(d*d)
-  var = __fdiv_rn(__fmul_rn(var, nf), nf - 1.0f);            // * N / (N-1)
+  const float tsq = warp_sum(sq);
+  float var = n512 ? __fmul_rn(tsq, 0.001953125f) : __fdiv_rn(tsq, nf);            // ReduceMean(d*d)
+  var = n512 ? div511_exact(__fmul_rn(var, nf)) : __fdiv_rn(__fmul_rn(var, nf), nf - 1.0f);            // * N / (N-1)
   const float denom = __fadd_rn(__fsqrt_rn(var), eps);       // sqrt + eps (eps added to std)
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);

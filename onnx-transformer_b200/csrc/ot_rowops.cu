@@ -32,11 +32,12 @@ __global__ void __launch_bounds__(256) layernorm_quant_kernel(const float* __res
     for (int i = 0; i < VEC; ++i) yr[i * 32 + lane] = v[i];
   }
   if (q_out) {
-    const float s = quant_scale(warp_max(amax));
+    const float s = quant_scale_x(warp_max_nonneg(amax));      // exact equivalents of the division / shuffle-tree forms (ot_rowmath.cuh)
+    const float s_rcp = __frcp_rn(s);
     uint32_t* qr = reinterpret_cast<uint32_t*>(q_out + row * n);
 #pragma unroll
     for (int i = 0; i < VEC; ++i)
-      qr[i * 32 + lane] = pack4(quant_one(v[i].x, s), quant_one(v[i].y, s), quant_one(v[i].z, s), quant_one(v[i].w, s));
+      qr[i * 32 + lane] = quant4_pack(v[i], s, s_rcp);
     if (lane == 0) s_out[row] = s;
   }
   tl_mark(tl, 3);
@@ -62,13 +63,16 @@ __global__ void __launch_bounds__(256) rowquant_kernel(const float* __restrict__
     const float4 v = __ldg(xr + i);
     amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
   }
-  const float s = quant_scale(warp_max(amax));
+  const float s = quant_scale_x(warp_max_nonneg(amax));
+  const float s_rcp = __frcp_rn(s);
   uint32_t* qr = reinterpret_cast<uint32_t*>(q + row * n + static_cast<int64_t>(gidx) * group);
   float4* hr = xhat ? reinterpret_cast<float4*>(xhat + row * n + static_cast<int64_t>(gidx) * group) : nullptr;
   for (int i = lane; i < nvec; i += 32) {
     const float4 v = __ldg(xr + i);
-    const int a = quant_one(v.x, s), b = quant_one(v.y, s), c = quant_one(v.z, s), d = quant_one(v.w, s);
-    qr[i] = pack4(a, b, c, d);
+    const uint32_t packed = quant4_pack(v, s, s_rcp);
+    const int a = static_cast<int8_t>(packed & 0xFF), b = static_cast<int8_t>((packed >> 8) & 0xFF);
+    const int c = static_cast<int8_t>((packed >> 16) & 0xFF), d = static_cast<int8_t>(packed >> 24);
+    qr[i] = packed;
     if (hr) hr[i] = make_float4(__fmul_rn(__int2float_rn(a), s), __fmul_rn(__int2float_rn(b), s),
                                 __fmul_rn(__int2float_rn(c), s), __fmul_rn(__int2float_rn(d), s));
   }
