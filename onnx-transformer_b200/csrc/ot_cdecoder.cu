@@ -518,6 +518,13 @@ __device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* k
   }
 }
 
+// float(int8) of byte B of w, where w holds the int8 bytes XOR 0x80 (i.e. v + 128 in [0, 255]): the float with bits 0x4B000000 | u
+// is 2^23 + u exactly, and subtracting 2^23 + 128 is exact -- the value I2F.S8 gives, without the conversion pipe.
+template <int B>
+__device__ __forceinline__ float s8_as_float(uint32_t w) {
+  return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + B)), 8388736.0f);
+}
+
 // RowQuant (groups of 512 features) of my projection row in recv: NG = 3: q | k | v, NG = 1: cross-attention q.
 __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale)[3]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -539,7 +546,9 @@ __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale
   am[0] = warp_max_nonneg(am[0]);
   am[1] = warp_max_nonneg(am[1]);
   if (lane == 0) { red[warp] = am[0]; red[8 + warp] = am[1]; }
+  mark(c, 60);
   __syncthreads();
+  mark(c, 61);
   scale[0] = quant_scale_x(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])));
   scale[1] = scale[2] = 0.f;
   if (NG == 3) {
@@ -554,6 +563,7 @@ __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale
       reinterpret_cast<uint32_t*>(rowbuf)[i] = quant4_pack(y[j], s, __frcp_rn(s));
     }
   }
+  mark(c, 62);
   __syncthreads();
 }
 
@@ -678,21 +688,22 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
   mark(c, 55);
   float acc0 = 0.f, acc1 = 0.f;
   const int d0 = 2 * lane;
-  // keys in order j = 0..; a key with p = 0 (masked, or beyond Tk where sv = 0 and the V bytes are stale but finite)
-  // contributes exactly +-0, as in attention_decode_body
-#pragma unroll
-  for (int kk = 0; kk < kDecKeysPerLane; ++kk) {
-    if (kk * 32 >= Tk) break;
-    const int jend = min(32, Tk - kk * 32);        // keys past Tk have p = 0: adding +0 to a sum that is never -0 changes nothing
+  // keys in order j = 0..; a key with p = 0 (masked, or the odd one at Tk where sv = 0 and the V bytes are stale but finite)
+  // contributes exactly +-0, as in attention_decode_body: adding +0 to a sum that is never -0 changes nothing.  The int8 -> fp32
+  // conversions are exact bit constructions (s8_as_float) on the integer / FMA pipes: I2F shares the MIO queue with the
+  // shared-memory loads of this loop and was its bound (profiles/r1_ncu_cdecoder_v4_final.txt: stall_mio on the I2F lines).
+  {
+    const float4* pv4 = reinterpret_cast<const float4*>(pv);
+    const uint8_t* vcol = reinterpret_cast<const uint8_t*>(Vs) + h * kDk + d0;
 #pragma unroll 8
-    for (int jj = 0; jj < jend; jj += 2) {
-      const float4 ps = *reinterpret_cast<const float4*>(pv + kk * 32 + jj);      // p, sv of keys jj and jj+1
-      const char2 va = *reinterpret_cast<const char2*>(Vs + (kk * 32 + jj) * kD + h * kDk + d0);
-      const char2 vb = *reinterpret_cast<const char2*>(Vs + (kk * 32 + jj + 1) * kD + h * kDk + d0);
-      acc0 = fmaf(ps.x, __fmul_rn(__int2float_rn(va.x), ps.y), acc0);
-      acc1 = fmaf(ps.x, __fmul_rn(__int2float_rn(va.y), ps.y), acc1);
-      acc0 = fmaf(ps.z, __fmul_rn(__int2float_rn(vb.x), ps.w), acc0);
-      acc1 = fmaf(ps.z, __fmul_rn(__int2float_rn(vb.y), ps.w), acc1);
+    for (int j = 0; j < Tk; j += 2) {
+      const float4 ps = pv4[j >> 1];                                             // p, sv of keys j and j+1
+      const uint32_t wa = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(vcol + j * kD)) ^ 0x8080u;
+      const uint32_t wb = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(vcol + (j + 1) * kD)) ^ 0x8080u;
+      acc0 = fmaf(ps.x, __fmul_rn(s8_as_float<0>(wa), ps.y), acc0);
+      acc1 = fmaf(ps.x, __fmul_rn(s8_as_float<1>(wa), ps.y), acc1);
+      acc0 = fmaf(ps.z, __fmul_rn(s8_as_float<0>(wb), ps.w), acc0);
+      acc1 = fmaf(ps.z, __fmul_rn(s8_as_float<1>(wb), ps.w), acc1);
     }
   }
   // RowQuant of the merged context row (all 8 heads): the row abs-max is a max (exact in any order), every lane quantizes its own
