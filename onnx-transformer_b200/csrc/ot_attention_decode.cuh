@@ -54,6 +54,13 @@ struct AttnDecRow {
   float sk_new, sv_new;
 };
 
+// float(int8) of byte B of w, where w holds the int8 bytes XOR 0x80 (i.e. v + 128 in [0, 255]): the float with bits 0x4B000000 | u
+// is 2^23 + u exactly, and subtracting 2^23 + 128 is exact -- the value I2F.S8 gives, without the conversion pipe.
+template <int B>
+__device__ __forceinline__ float s8_as_float(uint32_t w) {
+  return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + B)), 8388736.0f);
+}
+
 typedef int8_t (*AttnDecVh)[32 * kDecKeysPerLane][kDk];   // [kHeads][96][64] shared-memory V slices, 16-byte aligned
 
 // Decode attention of sentence b (Tq = 1, Tk <= 96, no fault): 256 threads, warp h = head h; K/V rows are read straight from
@@ -170,9 +177,9 @@ __device__ __forceinline__ void attention_decode_body(const AttnArgs& a, const A
     for (int jj = 0; jj < 32; ++jj) {
       const float ph = __shfl_sync(0xffffffffu, pq[kk], jj);
       const float svj = __shfl_sync(0xffffffffu, svl[kk], jj);
-      const char2 vv = *reinterpret_cast<const char2*>(&Vh[h][kk * 32 + jj][d0]);
-      acc0 = fmaf(ph, __fmul_rn(__int2float_rn(vv.x), svj), acc0);
-      acc1 = fmaf(ph, __fmul_rn(__int2float_rn(vv.y), svj), acc1);
+      const uint32_t vv = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&Vh[h][kk * 32 + jj][d0])) ^ 0x8080u;
+      acc0 = fmaf(ph, __fmul_rn(s8_as_float<0>(vv), svj), acc0);
+      acc1 = fmaf(ph, __fmul_rn(s8_as_float<1>(vv), svj), acc1);
     }
   }
   __syncwarp();

@@ -62,11 +62,11 @@ constexpr int kSmVs = kSmBh + 16 * 1024;                    // 151552: attention
 constexpr int kSmHb = kSmVs;
 constexpr int kSmRecv = kSmVs + kMaxKeys * kD;              // 200704: fp32 row scattered by the GEMM epilogues (<= 2048 floats)
 constexpr int kSmX = kSmRecv + 8192;                        // 208896: residual row x of my sentence (512 floats)
-constexpr int kSmRow = kSmX + 2048;                         // 210944: int8 staging: q|k|v (1536 B) + ctx (512 B), or h (2048 B)
+constexpr int kSmRow = kSmX + 2048;                         // 210944: int8 staging: q|k|v (1536 B) + ctx (512 B), or my 2 k-blocks of the FFN hidden operand
 constexpr int kSmCtx = kSmRow + 2048;                       // 212992: epilogue staging (2 x 1 KB) / final-norm row (512 floats)
-constexpr int kSmMisc = kSmCtx + 2048;                      // 215040: scales, reduction scratch, generator partials (1536 B)
-constexpr int kSmHot = kSmMisc + 1536;                      // 216576: CdHot copy (<= 1920 B) + 128 B of barriers
-constexpr int kSmTotal = kSmHot + 2048;                     // 218624
+constexpr int kSmMisc = kSmCtx + 2048;                      // 215040: scales, reduction scratch, generator partials, hidden-row maxima (2 KB)
+constexpr int kSmHot = kSmMisc + 2048;                      // 217088: CdHot copy (<= 1920 B) + 128 B of barriers
+constexpr int kSmTotal = kSmHot + 2048;                     // 219136
 static_assert(kSmTotal + 1024 <= 232448, "shared memory budget");
 // The M = 64 MMA reads 8 row groups (8 KB) from each operand k-block although only the first group (8 sentences) is real:
 // the over-read past Bh must stay inside the CTA's allocation.
@@ -75,14 +75,14 @@ static_assert(kSmBh + 16 * 1024 + 7 * 1024 <= kSmTotal, "operand over-read");
 // misc region (floats unless noted)
 constexpr int kMiSB = 0;        // [8] scale of each sentence's current operand row
 constexpr int kMiTok = 12;      // int: the token my sentence feeds this step
-constexpr int kMiSh = 13;       // scale of my sentence's quantized FFN hidden row
 constexpr int kMiRed = 16;      // [64] reduction scratch
 constexpr int kMiGenV = 80;     // [8 ranks][8 sentences]: best logit of rank's vocabulary slice  (written by peers)
 constexpr int kMiGenI = 144;    // [8][8] int: its index
 constexpr int kMiPartV = 208;   // [8 warps][8 sentences] per-warp partials (local)
 constexpr int kMiPartI = 272;   // [8][8] int -> 336 floats = 1344 B
-static_assert((kMiPartI + 64) * 4 <= 1536, "misc region");
-constexpr int kSmBars = kSmHot + 1920;   // 12 mbarriers (96 B) + TMEM slot at +120
+constexpr int kMiMax = 384;     // [8 sentences][16]: abs-max of the FFN hidden row over each (CTA, epilogue warp)'s 128 columns (written by peers)
+static_assert((kMiPartI + 64) <= kMiMax && (kMiMax + 128) * 4 <= 2048, "misc region");
+constexpr int kSmBars = kSmHot + 1920;   // 13 mbarriers (104 B) + TMEM slot at +120
 
 struct CdLayer {
   const float *ln_g[3], *ln_b[3];     // ln1, ln2, ln3
@@ -112,8 +112,10 @@ struct CdPlan {
 };
 
 // mbarriers: full[kSlots], empty[kSlots] (weight ring), accfull (MMAs of a GEMM done), kvfull (V rows prefetched),
-// gather (operand rows + scales from every owner), scatter (my sentence's row from every CTA)
-constexpr int kBarEmpty = kSlots, kBarAcc = 2 * kSlots, kBarKv = 2 * kSlots + 1, kBarG = 2 * kSlots + 2, kBarS = 2 * kSlots + 3;
+// gather (operand rows + scales from every owner), scatter (my sentence's row from every CTA), maxima (the 16 partial abs-maxima
+// of every sentence's FFN hidden row)
+constexpr int kBarEmpty = kSlots, kBarAcc = 2 * kSlots, kBarKv = 2 * kSlots + 1, kBarG = 2 * kSlots + 2, kBarS = 2 * kSlots + 3,
+              kBarM = 2 * kSlots + 4;
 
 struct Ctx {
   const CdHot* P;
@@ -123,7 +125,7 @@ struct Ctx {
   uint32_t tmem;
   int rank, n_own, b;    // cluster rank, sentences of this cluster, my sentence (or -1)
   uint32_t pn, cn, total;   // weight chunks issued (loader thread) / consumed (issuer thread) / to do
-  uint32_t acc_parity, kv_parity, g_parity, s_parity;
+  uint32_t acc_parity, kv_parity, g_parity, s_parity, m_parity;
   int trace_slot;
   bool trace_on;
   bool fine;                       // intra-phase marks of one layer (profiling aid, trace slots 150..249)
@@ -262,7 +264,8 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
       }
     }
   }
-  xwait(c, kBarG, static_cast<uint32_t>(c.n_own) * (kD + 4), c.g_parity, true);      // 512 operand bytes + the scale per sentence
+  // 512 operand bytes + the scale per sentence; FFN2: 8 rows x 256 hidden bytes from me and from my split-K partner
+  xwait(c, kBarG, g == 5 ? 2u * kCS * 256u : static_cast<uint32_t>(c.n_own) * (kD + 4), c.g_parity, true);
   if (tid == kIssuer) {
     fence_proxy_async_smem();      // operand rows were written through the generic proxy (shared memory only: the narrow fence)
     const uint32_t abase = smem_u32(c.smem + (g == 5 ? kSmBh : kSmBx));
@@ -304,6 +307,43 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
     float* stage = reinterpret_cast<float*>(c.smem + kSmCtx) + (warp >> 2) * 256;
     const uint32_t recv0 = smem_u32(c.smem + kSmRecv) + 4u * static_cast<uint32_t>(rows * c.rank + col0);
     const uint32_t sbar = smem_u32(&c.bars[kBarS]);
+    if (g == 4) {
+      // FFN1: bias + ReLU, then the RowQuant of the hidden rows right here.  Every (CTA, epilogue warp) sends the abs-max of its 128
+      // columns of each sentence to all 8 CTAs (512 bytes per CTA in total); with the 16 partials of a sentence every CTA derives
+      // the same scale, quantizes its own columns and writes them -- already in the swizzled operand layout -- into the FFN2
+      // operand buffers of the two CTAs whose split-K slice covers them: itself and rank ^ 1.  (Before: fp32 scatter to the
+      // sentence's owner, a RowQuant phase there, and an all-gather: one more exchange per layer.)
+      // Here: y -> shared memory [sentence][256 columns] (8-float groups XOR-swizzled by the sentence against bank conflicts).
+      float* ybuf = reinterpret_cast<float*>(c.smem + kSmRecv) + srow * 256;
+      float am = 0.f;
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        uint32_t r[16];
+        tmem_ld_16x256b_x4(c.tmem + col0 + 32 * gq, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 w2 = sw[4 * gq + i], b2 = bb[4 * gq + i];
+          const float y0 = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i])), sx), w2.x), b2.x), 0.0f);
+          const float y1 = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i + 1])), sx), w2.y), b2.y), 0.0f);
+          const int col = col0 + 32 * gq + 8 * i;
+          *reinterpret_cast<float2*>(ybuf + (col ^ (srow << 3)) + 2 * (lane & 3)) = make_float2(y0, y1);
+          am = fmaxf(am, fmaxf(y0, y1));          // y >= 0 (fmaxf(NaN, 0) = 0): the abs-max is the max
+        }
+      }
+      tc_fence_before();
+      am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+      am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+      const uint32_t mbar = smem_u32(&c.bars[kBarM]);
+      const uint32_t slot = smem_u32(misc(c) + kMiMax + srow * 16 + 2 * c.rank + (warp >> 2));
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int peer = 2 * (lane & 3) + j;
+        st_async_b32(mapa_shared(slot, peer), __float_as_uint(am), mapa_shared(mbar, peer));
+      }
+      if (tid == 0) mbar_arrive_expect_tx(mbar, kCS * 16 * 4);
+      mark(c, 70);
+    } else {
 #pragma unroll
     for (int gq = 0; gq < 4; ++gq) {
       if (gq < ngroups) {
@@ -318,7 +358,6 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
             const float2 w2 = sw[4 * gq + i], b2 = bb[4 * gq + i];
             float y0 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i])), sx), w2.x), b2.x);
             float y1 = __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * i + 1])), sx), w2.y), b2.y);
-            if (g == 4) { y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); }
             *reinterpret_cast<float2*>(stage + srow * 32 + 8 * i + 2 * (lane & 3)) = make_float2(y0, y1);
           }
         }
@@ -335,25 +374,51 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
       }
     }
     tc_fence_before();
+    }
+  }
+  if (g == 4) {
+    // all 256 threads: 8 columns of one sentence each
+    mbar_wait(smem_u32(&c.bars[kBarM]), c.m_parity);
+    c.m_parity ^= 1u;
+    __syncthreads();                 // y of the two epilogue warps is in shared memory
+    mark(c, 71);
+    const float4* m4 = reinterpret_cast<const float4*>(misc(c) + kMiMax + warp * 16);
+    const float4 ma = m4[0], mb = m4[1], mc = m4[2], md = m4[3];
+    const float amax = fmaxf(fmaxf(fmaxf(fmaxf(ma.x, ma.y), fmaxf(ma.z, ma.w)), fmaxf(fmaxf(mb.x, mb.y), fmaxf(mb.z, mb.w))),
+                             fmaxf(fmaxf(fmaxf(mc.x, mc.y), fmaxf(mc.z, mc.w)), fmaxf(fmaxf(md.x, md.y), fmaxf(md.z, md.w))));
+    const float s = quant_scale_x(amax);
+    const float rinv = __frcp_rn(s);
+    const float4* y4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(c.smem + kSmRecv) + warp * 256 + ((8 * lane) ^ (warp << 3)));
+    uint2 w;
+    w.x = quant4_pack(y4[0], s, rinv);
+    w.y = quant4_pack(y4[1], s, rinv);
+    // columns 8*lane .. +7 of sentence `warp`: k-block lane >> 4, 16-byte chunk (lane >> 1) & 7 (swizzled by the row), half lane & 1
+    *reinterpret_cast<uint2*>(c.smem + kSmRow + (lane >> 4) * 1024 + warp * 128 + ((((lane >> 1) & 7) ^ warp) << 4) + 8 * (lane & 1)) = w;
+    __syncthreads();
+    mark(c, 72);
+    {
+      const int ch = tid & 127, dest = (tid >> 7) ? (c.rank ^ 1) : c.rank;       // 2 KB = 128 chunks, to me and to my split-K partner
+      const uint4 v = *reinterpret_cast<const uint4*>(c.smem + kSmRow + ch * 16);
+      const uint32_t dst = smem_u32(c.smem + kSmBh + 2 * c.rank * 1024 + ch * 16);
+      st_async_v4(mapa_shared(dst, dest), v, mapa_shared(smem_u32(&c.bars[kBarG]), dest));
+    }
   }
   mark(c, 30 + g);
   c.acc_parity ^= 1u;
 }
 
 // ------------------------------------------------------------------------------------------------ all-gather helpers
-// Push the int8 row staged at `src` into row `rank` of every CTA's operand buffer (128-byte swizzle: 16-byte chunk c of a row lands
-// at chunk c ^ (row & 7) of its 128-byte line; k-blocks 1 KB apart), plus its scale.  K = 512: the whole row to every peer.
-// K = 2048 (the FFN hidden row): FFN2 is split-K, peer p only consumes k-blocks 4*(p>>1)..+4, so it is only sent those 512 bytes
-// (a quarter of the DSMEM traffic of a full all-gather).  Either way a peer receives 512 + 4 bytes per sentence.
-__device__ __forceinline__ void push_row_q8(Ctx& c, const uint8_t* src, int K, int dst_off, float scale) {
+// Push the 512-byte int8 row staged at `src` into row `rank` of every CTA's operand buffer (128-byte swizzle: 16-byte chunk c of a
+// row lands at chunk c ^ (row & 7) of its 128-byte line; k-blocks 1 KB apart), plus its scale: a peer receives 512 + 4 bytes per
+// sentence.
+__device__ __forceinline__ void push_row_q8(Ctx& c, const uint8_t* src, float scale) {
   const int tid = threadIdx.x;
   const uint32_t gbar = smem_u32(&c.bars[kBarG]);
   {
-    const int peer = tid >> 5;                                    // 256 threads = 8 peers x 32 chunks of 16 bytes
-    const int ch = (K == kD ? 0 : 32 * (peer >> 1)) + (tid & 31);
+    const int peer = tid >> 5, ch = tid & 31;                     // 256 threads = 8 peers x 32 chunks of 16 bytes
     const uint4 v = *reinterpret_cast<const uint4*>(src + ch * 16);
     const int kb = ch >> 3, cc = ch & 7;
-    const uint32_t local = smem_u32(c.smem + dst_off + kb * 1024 + c.rank * 128 + ((cc ^ (c.rank & 7)) << 4));
+    const uint32_t local = smem_u32(c.smem + kSmBx + kb * 1024 + c.rank * 128 + ((cc ^ (c.rank & 7)) << 4));
     st_async_v4(mapa_shared(local, peer), v, mapa_shared(gbar, peer));
   }
   if (tid < kCS) st_async_b32(mapa_shared(smem_u32(misc(c) + kMiSB + c.rank), tid), __float_as_uint(scale), mapa_shared(gbar, tid));
@@ -395,7 +460,12 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
       const float4 w4 = __ldg(reinterpret_cast<const float4*>(sw2) + i4), b4 = __ldg(reinterpret_cast<const float4*>(b2) + i4);
       const int4* pl = reinterpret_cast<const int4*>(c.smem + kSmRecv);
       const int4 p0 = pl[i4], p1 = pl[128 + i4], p2 = pl[256 + i4], p3 = pl[384 + i4];
-      const float sh = (misc(c) + kMiSh)[0];
+      // scale of my sentence's quantized hidden row: from its 16 partial maxima (exchanged during FFN1; every CTA derives the same value)
+      mbar_wait(smem_u32(&c.bars[kBarM]), c.m_parity ^ 1u);
+      const float4* m4 = reinterpret_cast<const float4*>(misc(c) + kMiMax + c.rank * 16);
+      const float4 ma = m4[0], mb = m4[1], mc = m4[2], md = m4[3];
+      const float sh = quant_scale_x(fmaxf(fmaxf(fmaxf(fmaxf(ma.x, ma.y), fmaxf(ma.z, ma.w)), fmaxf(fmaxf(mb.x, mb.y), fmaxf(mb.z, mb.w))),
+                                            fmaxf(fmaxf(fmaxf(mc.x, mc.y), fmaxf(mc.z, mc.w)), fmaxf(fmaxf(md.x, md.y), fmaxf(md.z, md.w)))));
       const float4 res = reinterpret_cast<const float4*>(xr)[i4];
       v.x = __fadd_rn(res.x, __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn((p0.x + p1.x) + (p2.x + p3.x)), sh), w4.x), b4.x));
       v.y = __fadd_rn(res.y, __fadd_rn(__fmul_rn(__fmul_rn(__int2float_rn((p0.y + p1.y) + (p2.y + p3.y)), sh), w4.y), b4.y));
@@ -441,7 +511,7 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
   mark(c, 44);
   if (c.b >= 0) {
     if (quant) {
-      push_row_q8(c, rowq, kD, kSmBx, red[0]);
+      push_row_q8(c, rowq, red[0]);
     } else {
       const uint32_t gbar = smem_u32(&c.bars[kBarG]);
       for (int idx = tid; idx < 128 * kCS; idx += kThreads) {
@@ -452,32 +522,6 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
     }
   }
   mark(c, 45);
-}
-
-// FFN1 row (bias + ReLU applied by the GEMM epilogue): RowQuant over 2048 features -> all-gather into Bh.
-__device__ __forceinline__ void phase_ffnq(Ctx& c) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* red = misc(c) + kMiRed;
-  uint8_t* rowq = c.smem + kSmRow;
-  if (c.b >= 0) {
-    const float4* y4 = reinterpret_cast<const float4*>(c.smem + kSmRecv);
-    const float4 a = y4[2 * tid], b = y4[2 * tid + 1];
-    float am = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
-    am = warp_max_nonneg(am);
-    if (lane == 0) red[warp] = am;
-    __syncthreads();
-    const float s = quant_scale_x(fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]))));
-    const float r = __frcp_rn(s);
-    uint2 w;
-    w.x = quant4_pack(a, s, r);
-    w.y = quant4_pack(b, s, r);
-    reinterpret_cast<uint2*>(rowq)[tid] = w;
-    if (tid == 0) (misc(c) + kMiSh)[0] = s;
-    __syncthreads();
-    mark(c, 61);
-    push_row_q8(c, rowq, kFF, kSmBh, s);
-  }
-  mark(c, 62);
 }
 
 // ------------------------------------------------------------------------------------------------ attention (owner CTA)
@@ -518,13 +562,6 @@ __device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* k
   }
 }
 
-// float(int8) of byte B of w, where w holds the int8 bytes XOR 0x80 (i.e. v + 128 in [0, 255]): the float with bits 0x4B000000 | u
-// is 2^23 + u exactly, and subtracting 2^23 + 128 is exact -- the value I2F.S8 gives, without the conversion pipe.
-template <int B>
-__device__ __forceinline__ float s8_as_float(uint32_t w) {
-  return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + B)), 8388736.0f);
-}
-
 // RowQuant (groups of 512 features) of my projection row in recv: NG = 3: q | k | v, NG = 1: cross-attention q.
 __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale)[3]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -546,9 +583,7 @@ __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale
   am[0] = warp_max_nonneg(am[0]);
   am[1] = warp_max_nonneg(am[1]);
   if (lane == 0) { red[warp] = am[0]; red[8 + warp] = am[1]; }
-  mark(c, 60);
   __syncthreads();
-  mark(c, 61);
   scale[0] = quant_scale_x(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])));
   scale[1] = scale[2] = 0.f;
   if (NG == 3) {
@@ -563,7 +598,6 @@ __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale
       reinterpret_cast<uint32_t*>(rowbuf)[i] = quant4_pack(y[j], s, __frcp_rn(s));
     }
   }
-  mark(c, 62);
   __syncthreads();
 }
 
@@ -718,7 +752,7 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
   *reinterpret_cast<uint16_t*>(c.smem + kSmRow + 1536 + h * kDk + d0) = static_cast<uint16_t>(q01 & 0xFFFFu);
   __syncthreads();
   mark(c, 58);
-  push_row_q8(c, c.smem + kSmRow + 1536, kD, kSmBx, s);
+  push_row_q8(c, c.smem + kSmRow + 1536, s);
   mark(c, 59);
 }
 
@@ -893,7 +927,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 7) {
     if (lane == 0) {
-      for (int i = 0; i <= kBarS; ++i) mbar_init(smem_u32(&c.bars[i]), 1);
+      for (int i = 0; i <= kBarM; ++i) mbar_init(smem_u32(&c.bars[i]), 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -912,7 +946,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   c.b = (c.rank < c.n_own) ? cluster_id * P.spc + c.rank : -1;
   c.pn = c.cn = 0;
   c.total = static_cast<uint32_t>(n_steps) * nl * kChunks;
-  c.acc_parity = c.kv_parity = c.g_parity = c.s_parity = 0;
+  c.acc_parity = c.kv_parity = c.g_parity = c.s_parity = c.m_parity = 0;
   c.trace_slot = 0;
   c.trace_on = false;
   c.fine = false;
@@ -956,6 +990,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
       c.fine = c.trace_on && l == min(2, nl - 1);
 #pragma unroll 1
       for (int q = 0; q < 11; ++q) {
+        if (q == 9) continue;      // the FFN hidden rows are quantized and exchanged by the FFN1 epilogue itself
         if ((q & 1) == 0) {
           // ---- GEMM phases; the attention operands of my sentence are prefetched alongside
           if ((q == 0 || q == 4) && own) {
@@ -970,10 +1005,9 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
           phase_gemm(c, l, g, gend);
         } else {
           // ---- row phases: my sentence's row has arrived from the 8 column owners
-          xwait(c, kBarS, (q == 1 ? 3 * kD : q == 9 ? kFF : kD) * 4, c.s_parity, own);
+          xwait(c, kBarS, (q == 1 ? 3 * kD : kD) * 4, c.s_parity, own);
           if (q == 1 || q == 5) phase_attention(c, q == 1, t, l, pre);
-          else if (q == 3 || q == 7) phase_ln(c, 1, 0, t, L.ln_g[q == 3 ? 1 : 2], L.ln_b[q == 3 ? 1 : 2], true);
-          else phase_ffnq(c);
+          else phase_ln(c, 1, 0, t, L.ln_g[q == 3 ? 1 : 2], L.ln_b[q == 3 ? 1 : 2], true);
         }
       }
       // ---- residual + LayerNorm 1 of the next layer, or the final norm (fp32 row to every CTA's generator input)

@@ -22,6 +22,7 @@
 
 #include "ot_common.h"
 #include "ot_ptx.cuh"
+#include "ot_rowmath.cuh"
 
 namespace ot {
 
@@ -257,19 +258,8 @@ __device__ __forceinline__ void chunk_values(const GemmArgs& g, const FaultCtx& 
   }
 }
 
-// rint(y / s) with the quotient rounded exactly like IEEE division, without the per-element div.rn expansion (whose
-// special-case path is taken for every zero dividend -- half of a ReLU output -- and whose branch serialises the chunk).
-// q1 = y*r corrected by one FMA residual step (r = RN(1/s)) is within 1 ulp of RN(y/s); the integer result can only differ
-// when q1 sits within 2^-16 of a half-integer, and exactly then the true IEEE division decides.  The 16 elements of a chunk
-// are evaluated branch-free; the (rare) exact fallback is taken once per chunk, out of line.  |y/s| <= 127 by construction.
-__device__ __forceinline__ float quant_fast(float y, float s, float r, bool& near_half) {
-  const float q0 = __fmul_rn(y, r);
-  const float rem = __fmaf_rn(-q0, s, y);
-  const float q1 = __fmaf_rn(rem, r, q0);
-  const float n = rintf(q1);
-  near_half = near_half || (fabsf(fabsf(q1 - n) - 0.5f) < 1.52587890625e-05f);
-  return n;
-}
+// RowQuant of a chunk: quant_fast_bits (ot_rowmath.cuh) on the 16 elements, branch-free; the (rare) exact fallback is taken once per
+// chunk, out of line.
 template <int CW>
 __device__ __noinline__ void quant_exact_array(const float* y, float s, float* n) {
   for (int j = 0; j < CW; ++j) n[j] = rintf(__fdiv_rn(y[j], s));
@@ -294,25 +284,26 @@ __device__ __forceinline__ void consume_chunk(const GemmArgs& g, PassState& st, 
     }
   } else {
     if (row_ok) {
-      float n[kCW];
-      bool near_half = false;
+      uint32_t tb[kCW];
+      bool slow = false;
 #pragma unroll
-      for (int j = 0; j < kCW; ++j) n[j] = quant_fast(y[j], st.s, st.s_rcp, near_half);
-      if (near_half) {                       // ~2^-13 of the chunks: redo the chunk with true IEEE division
+      for (int j = 0; j < kCW; ++j) tb[j] = quant_fast_bits(y[j], st.s, st.s_rcp, slow);
+      uint32_t packed[kCW / 4];
+#pragma unroll
+      for (int j = 0; j < kCW / 4; ++j)
+        packed[j] = __byte_perm(__byte_perm(tb[4 * j], tb[4 * j + 1], 0x0040), __byte_perm(tb[4 * j + 2], tb[4 * j + 3], 0x0040), 0x5410);
+      if (slow) {                            // ~2^-13 of the chunks: redo the chunk with true IEEE division
         float yy[kCW], nn[kCW];
 #pragma unroll
         for (int j = 0; j < kCW; ++j) yy[j] = y[j];
         quant_exact_array<kCW>(yy, st.s, nn);
 #pragma unroll
-        for (int j = 0; j < kCW; ++j) n[j] = nn[j];
-      }
-      uint32_t packed[kCW / 4];
+        for (int j = 0; j < kCW / 4; ++j) {
+          uint32_t w = 0;
 #pragma unroll
-      for (int j = 0; j < kCW / 4; ++j) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) w |= (static_cast<uint32_t>(__float2int_rn(n[4 * j + b])) & 0xFFu) << (8 * b);
-        packed[j] = w;
+          for (int b = 0; b < 4; ++b) w |= (static_cast<uint32_t>(__float2int_rn(nn[4 * j + b])) & 0xFFu) << (8 * b);
+          packed[j] = w;
+        }
       }
       *reinterpret_cast<uint4*>(reinterpret_cast<int8_t*>(g.out) + static_cast<int64_t>(row) * g.ldo + col) =
           make_uint4(packed[0], packed[1], packed[2], packed[3]);

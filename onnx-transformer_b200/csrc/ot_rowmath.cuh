@@ -58,25 +58,34 @@ __device__ __forceinline__ float div511_exact(float x) {
 __device__ __forceinline__ float quant_scale(float amax) { return __fdiv_rn(fmaxf(amax, 1e-5f), 127.0f); }
 __device__ __forceinline__ int quant_one(float x, float s) { return __float2int_rn(rintf(__fdiv_rn(x, s))); }
 // rint(y / s) with the quotient rounded exactly like IEEE division, without the div.rn expansion (whose special-case path is taken
-// for every zero dividend -- half of a ReLU output -- and whose branch serialises independent elements).  q1 = y*r corrected by
-// one FMA residual step (r = RN(1/s)) is within 1 ulp of RN(y/s); the integer can only differ when q1 sits within 2^-16 of a
-// half-integer (|y/s| <= 127, so 1 ulp <= 2^-17), and exactly then the true division decides (flagged, redone by the caller).
-__device__ __forceinline__ float quant_fast_n(float y, float s, float r, bool& near_half) {
+// for every zero dividend -- half of a ReLU output -- and whose branch serialises independent elements) and without the conversion
+// pipe (FRND / F2I are quarter rate and share the MIO queue with the shared-memory instructions around them):
+//   q1 = y*r corrected by one FMA residual step (r = RN(1/s)) is within 1 ulp of RN(y/s);
+//   t = q1 + 1.5*2^23 rounds q1 to an integer, ties to even, exactly as rintf does (|q1| < 2^22): n = t - 1.5*2^23, and the low byte
+//   of t's bit pattern is n mod 256 -- the int8 two's-complement byte;
+//   rint(q1) can only differ from rint(RN(y/s)) when q1 sits within 2^-16 of a half-integer (|y/s| <= 127, so 1 ulp <= 2^-17):
+//   exactly then -- or when q1 is not a small finite number -- the true division decides (flagged, redone by the caller).
+__device__ __forceinline__ uint32_t quant_fast_bits(float y, float s, float r, bool& slow) {
   const float q0 = __fmul_rn(y, r);
   const float rem = __fmaf_rn(-q0, s, y);
   const float q1 = __fmaf_rn(rem, r, q0);
-  const float n = rintf(q1);
-  near_half = near_half || (fabsf(fabsf(q1 - n) - 0.5f) < 1.52587890625e-05f);
-  return n;
+  const float t = __fadd_rn(q1, 12582912.0f);
+  const float n = __fsub_rn(t, 12582912.0f);
+  slow = slow || (fabsf(fabsf(q1 - n) - 0.5f) < 1.52587890625e-05f) || !(fabsf(q1) < 1024.0f);
+  return __float_as_uint(t);
 }
 // pack4(quant_one(v.x, s), ...) of four values, same bits as the division form
 __device__ __forceinline__ uint32_t quant4_pack(float4 v, float s, float r) {
-  bool nh = false;
-  int a = __float2int_rn(quant_fast_n(v.x, s, r, nh)), b = __float2int_rn(quant_fast_n(v.y, s, r, nh));
-  int c = __float2int_rn(quant_fast_n(v.z, s, r, nh)), d = __float2int_rn(quant_fast_n(v.w, s, r, nh));
-  if (nh) { a = quant_one(v.x, s); b = quant_one(v.y, s); c = quant_one(v.z, s); d = quant_one(v.w, s); }
-  return (static_cast<uint32_t>(a) & 0xFFu) | ((static_cast<uint32_t>(b) & 0xFFu) << 8) | ((static_cast<uint32_t>(c) & 0xFFu) << 16) |
-         ((static_cast<uint32_t>(d) & 0xFFu) << 24);
+  bool slow = false;
+  const uint32_t a = quant_fast_bits(v.x, s, r, slow), b = quant_fast_bits(v.y, s, r, slow);
+  const uint32_t c = quant_fast_bits(v.z, s, r, slow), d = quant_fast_bits(v.w, s, r, slow);
+  uint32_t w = __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+  if (slow) {
+    const int ia = quant_one(v.x, s), ib = quant_one(v.y, s), ic = quant_one(v.z, s), id = quant_one(v.w, s);
+    w = (static_cast<uint32_t>(ia) & 0xFFu) | ((static_cast<uint32_t>(ib) & 0xFFu) << 8) | ((static_cast<uint32_t>(ic) & 0xFFu) << 16) |
+        ((static_cast<uint32_t>(id) & 0xFFu) << 24);
+  }
+  return w;
 }
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
   return (static_cast<uint32_t>(a) & 0xFFu) | ((static_cast<uint32_t>(b) & 0xFFu) << 8) |

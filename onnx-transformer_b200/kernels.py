@@ -291,7 +291,7 @@ class ClusterDecoderPlan:
     """Device-resident plan of the cluster-resident greedy decoder (ot_cdecoder_plan_build): groups of `spc` sentences, one
     8-CTA cluster each.  Keeps every tensor it points to alive."""
 
-    PHASES = ["qkv", "self_attn", "o", "ln2", "cq", "cross_attn", "co", "ln3", "ffn1", "ffn1_quant", "ffn2", "ln1"]
+    PHASES = ["qkv", "self_attn", "o", "ln2", "cq", "cross_attn", "co", "ln3", "ffn1", "ffn2", "ln1"]      # ffn1 includes the RowQuant of the hidden rows
 
     def __init__(self, layers, ws_tensors, *, n_layers: int, B: int, S: int, cap: int, vocab: int, ys: torch.Tensor, spc: int = 8,
                  trace: bool = False):
