@@ -562,43 +562,49 @@ __device__ __forceinline__ void attn_prefetch(Ctx& c, int n_old, const int8_t* k
   }
 }
 
-// RowQuant (groups of 512 features) of my projection row in recv: NG = 3: q | k | v, NG = 1: cross-attention q.
+// RowQuant (groups of 512 features) of my projection row in recv: NG = 3: q | k | v, NG = 1: cross-attention q.  Warp h handles the
+// slices of head h -- lanes 0..15 its 64 q features (and, second register, its 64 v features), lanes 16..31 its 64 k features --
+// which are exactly the bytes warp h consumes afterwards: one block barrier (the row maxima), then only the warp's own lanes.
 __device__ __forceinline__ void quant_groups(Ctx& c, const int NG, float (&scale)[3]) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* rowbuf = c.smem + kSmRow;
+  const int tid = threadIdx.x, h = tid >> 5, lane = tid & 31, l16 = lane & 15, hi = lane >> 4;
+  uint32_t* rowbuf = reinterpret_cast<uint32_t*>(c.smem + kSmRow);
   float* red = misc(c) + kMiRed;
   const float4* y4 = reinterpret_cast<const float4*>(c.smem + kSmRecv);
-  const int N = NG * kD;
-  float4 y[2];
-  float am[2] = {0.f, 0.f};
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool has0 = hi == 0 || NG == 3, has1 = hi == 0 && NG == 3;
+  const float4 y0 = has0 ? y4[hi * 128 + h * 16 + l16] : zero;           // q (lanes 0..15) or k (lanes 16..31) slice of head h
+  const float4 y1 = has1 ? y4[256 + h * 16 + l16] : zero;                // v slice of head h
+  const float a0 = fmaxf(fmaxf(fabsf(y0.x), fabsf(y0.y)), fmaxf(fabsf(y0.z), fabsf(y0.w)));
+  const float a1 = fmaxf(fmaxf(fabsf(y1.x), fabsf(y1.y)), fmaxf(fabsf(y1.z), fabsf(y1.w)));
+  // maxima over each 16-lane half (non-negative floats order like their bit patterns; NaN counts as 0, as in warp_max_nonneg)
+  uint32_t u0 = (a0 == a0) ? __float_as_uint(a0) : 0u, u1 = (a1 == a1) ? __float_as_uint(a1) : 0u;
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int i = tid + 256 * j;
-    y[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < N / 4) {
-      y[j] = y4[i];
-      am[j] = fmaxf(fmaxf(fabsf(y[j].x), fabsf(y[j].y)), fmaxf(fabsf(y[j].z), fabsf(y[j].w)));
-    }
+  for (int o = 8; o > 0; o >>= 1) {
+    u0 = max(u0, __shfl_xor_sync(0xffffffffu, u0, o));
+    u1 = max(u1, __shfl_xor_sync(0xffffffffu, u1, o));
   }
-  am[0] = warp_max_nonneg(am[0]);
-  am[1] = warp_max_nonneg(am[1]);
-  if (lane == 0) { red[warp] = am[0]; red[8 + warp] = am[1]; }
+  if (l16 == 0) {
+    red[hi * 8 + h] = __uint_as_float(u0);
+    if (hi == 0) red[16 + h] = __uint_as_float(u1);
+  }
   __syncthreads();
-  scale[0] = quant_scale_x(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])));
+  const float4* r4 = reinterpret_cast<const float4*>(red);
+  {
+    const float4 a = r4[0], b = r4[1];
+    scale[0] = quant_scale_x(fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+  }
   scale[1] = scale[2] = 0.f;
   if (NG == 3) {
-    scale[1] = quant_scale_x(fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
-    scale[2] = quant_scale_x(fmaxf(fmaxf(red[8], red[9]), fmaxf(red[10], red[11])));
+    const float4 a = r4[2], b = r4[3], cc = r4[4], d = r4[5];
+    scale[1] = quant_scale_x(fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+    scale[2] = quant_scale_x(fmaxf(fmaxf(fmaxf(cc.x, cc.y), fmaxf(cc.z, cc.w)), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w))));
   }
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int i = tid + 256 * j;
-    if (i < N / 4) {
-      const float s = scale[i >> 7];
-      reinterpret_cast<uint32_t*>(rowbuf)[i] = quant4_pack(y[j], s, __frcp_rn(s));
-    }
+  if (has0) {
+    const float s = hi ? scale[1] : scale[0];
+    rowbuf[hi * 128 + h * 16 + l16] = quant4_pack(y0, s, __frcp_rn(s));
   }
-  __syncthreads();
+  if (has1) rowbuf[256 + h * 16 + l16] = quant4_pack(y1, scale[2], __frcp_rn(scale[2]));
+  __syncwarp();
 }
 
 // self: RowQuant of q | k | v, KV-cache append, causal attention over t+1 keys; cross: RowQuant of q, attention over the S cached
@@ -640,27 +646,28 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
   c.kv_parity ^= 1u;
   mark(c, 52);
   if (self) {
-    // this step's K / V row: into the cache (global), V also next to the prefetched rows, K into the registers of its 4 lanes
-    const int64_t dst = (static_cast<int64_t>(c.b) * P.cap + t) * kD;
-    if (tid < 32) {
-      *reinterpret_cast<uint4*>(L.kc + dst + tid * 16) = *reinterpret_cast<const uint4*>(rowbuf + kD + tid * 16);
-    } else if (tid < 64) {
-      const int c16 = tid - 32;
-      const uint4 vv = *reinterpret_cast<const uint4*>(rowbuf + 2 * kD + c16 * 16);
-      *reinterpret_cast<uint4*>(Vs + t * kD + c16 * 16) = vv;
+    // this step's K / V row: into the cache (global), V also next to the prefetched rows, K into the registers of its 4 lanes.
+    // Every warp moves the 64 bytes of its own head (lanes 0..3: k, lanes 4..7: v): no block barrier.
+    const int64_t dst = (static_cast<int64_t>(c.b) * P.cap + t) * kD + h * kDk;
+    if (lane < 4) {
+      *reinterpret_cast<uint4*>(L.kc + dst + lane * 16) = *reinterpret_cast<const uint4*>(rowbuf + kD + h * kDk + lane * 16);
+    } else if (lane < 8) {
+      const int c16 = lane - 4;
+      const uint4 vv = *reinterpret_cast<const uint4*>(rowbuf + 2 * kD + h * kDk + c16 * 16);
+      *reinterpret_cast<uint4*>(Vs + t * kD + h * kDk + c16 * 16) = vv;
       *reinterpret_cast<uint4*>(L.vc + dst + c16 * 16) = vv;
-    } else if (tid == 64) {
+    } else if (tid == 8) {
       L.skc[static_cast<int64_t>(c.b) * P.cap + t] = sc3[1];
       L.svc[static_cast<int64_t>(c.b) * P.cap + t] = sc3[2];
     }
-    if (tid < 64) asm volatile("fence.proxy.async.global;" ::: "memory");   // later steps read these rows through bulk copies (async proxy)
+    if (lane < 8) asm volatile("fence.proxy.async.global;" ::: "memory");   // later steps read these rows through bulk copies (async proxy)
 #pragma unroll
     for (int kk = 0; kk < kDecKeysPerLane; ++kk)
       if (kk * 32 + lane == t) { pre.skl[kk] = sc3[1]; pre.svl[kk] = sc3[2]; }
 #pragma unroll
     for (int i = 0; i < 4 * kDecKeysPerLane; ++i)
       if (8 * i + m8 == t) kq[i] = *reinterpret_cast<const uint4*>(rowbuf + kD + h * kDk + ch * 16);
-    __syncthreads();
+    __syncwarp();
   }
   const int q_pos0 = self ? t : 0, mask_kind = self ? 2 : 1;
   const float sqi = sc3[0];
@@ -750,9 +757,18 @@ __device__ __forceinline__ void phase_attention(Ctx& c, bool self, int t, int l,
   const float s = quant_scale_x(amax);
   const uint32_t q01 = quant4_pack(make_float4(acc0, acc1, 0.f, 0.f), s, __frcp_rn(s));
   *reinterpret_cast<uint16_t*>(c.smem + kSmRow + 1536 + h * kDk + d0) = static_cast<uint16_t>(q01 & 0xFFFFu);
-  __syncthreads();
+  __syncwarp();
   mark(c, 58);
-  push_row_q8(c, c.smem + kSmRow + 1536, s);
+  // all-gather: warp h sends the 64 bytes of head h (4 chunks of 16) to the 8 CTAs -- lane = (peer, chunk) -- in push_row_q8's layout
+  {
+    const uint32_t gbar = smem_u32(&c.bars[kBarG]);
+    const int peer = lane >> 2, ch = h * 4 + (lane & 3);
+    const uint4 v = *reinterpret_cast<const uint4*>(c.smem + kSmRow + 1536 + ch * 16);
+    const int kb = ch >> 3, cc = ch & 7;
+    const uint32_t local = smem_u32(c.smem + kSmBx + kb * 1024 + c.rank * 128 + ((cc ^ (c.rank & 7)) << 4));
+    st_async_v4(mapa_shared(local, peer), v, mapa_shared(gbar, peer));
+    if (tid < kCS) st_async_b32(mapa_shared(smem_u32(misc(c) + kMiSB + c.rank), tid), __float_as_uint(s), mapa_shared(gbar, tid));
+  }
   mark(c, 59);
 }
 
