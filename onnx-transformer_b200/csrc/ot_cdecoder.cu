@@ -170,19 +170,23 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
-// Start of a phase: wait until the `bytes` this phase consumes have landed in this CTA (bar = kBarG: operand rows + scales of an
-// all-gather, kBarS: my sentence's row of a scatter).  Thread 0 arms the mbarrier phase (one arrival + the expected byte count;
-// bytes that arrived before the arming are accounted for by the signed tx-count).  Buffers are reused every second exchange; that
-// is safe because a CTA sends its contribution to exchange k+1 only after it has consumed exchange k, and every exchange gathers
-// from all 8 CTAs.  Also the profiling hook: CTA 0 stamps the begin / end of every wait.
-__device__ __forceinline__ void xwait(Ctx& c, int bar, uint32_t bytes, uint32_t& parity, bool waits) {
+// Start of a phase: wait until the bytes this phase consumes have landed in this CTA (bar = kBarG: operand rows + scales of an
+// all-gather, kBarS: my sentence's row of a scatter).  A phase of the mbarrier = one arrival (thread 0) + the expected byte count.
+// Thread 0 arms the NEXT use of the barrier (`next_bytes`, 0 = none) the moment this one completes -- bytes that arrive before the
+// arming are accounted for by the signed tx-count, and the wait then ends when the last byte lands, not when thread 0 gets there
+// (it reaches the next wait 0.3-0.6 us after the row phase it also works in).  The first use is armed at kernel start.
+// A CTA cannot run two phases ahead of its own threads: between a wait and this CTA's contribution to the next exchange on the
+// same barrier lies a block barrier of the phase in between.  Buffers are reused every second exchange; that is safe because a CTA
+// sends its contribution to exchange k+1 only after it has consumed exchange k.  Also the profiling hook: CTA 0
+// stamps the begin / end of every wait.
+__device__ __forceinline__ void xwait(Ctx& c, int bar, uint32_t next_bytes, uint32_t& parity, bool waits) {
   mark(c, 1);
   if (c.trace_on && threadIdx.x == 0) c.P->trace[2 * c.trace_slot] = tl_now();
   if (waits) {
     const uint32_t b = smem_u32(&c.bars[bar]);
-    if (threadIdx.x == 0) mbar_arrive_expect_tx(b, bytes);
     mbar_wait(b, parity);
     parity ^= 1u;
+    if (threadIdx.x == 0 && next_bytes != 0) mbar_arrive_expect_tx(b, next_bytes);
   }
   if (c.trace_on && threadIdx.x == 0) c.P->trace[2 * c.trace_slot + 1] = tl_now();
   __syncwarp();
@@ -240,7 +244,7 @@ __device__ __forceinline__ void fill_until(Ctx& c, uint32_t upto) {
 // ------------------------------------------------------------------------------------------------ GEMM phase
 // g: 0 qkv, 1 o, 2 cq, 3 co, 4 w1 (ReLU), 5 w2.  D[s][f] = sum_k a[s][k] * W[f][k] (rows s >= 8 of the M = 64 tile are whatever
 // follows the 8 operand rows in shared memory: never read back); then scatter y[s][f] to the owner of sentence s.
-__device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) {
+__device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend, uint32_t next_gather_bytes) {
   const CdHot& P = *c.P;
   const CdLayer& L = P.layer[l];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -264,8 +268,8 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend) 
       }
     }
   }
-  // 512 operand bytes + the scale per sentence; FFN2: 8 rows x 256 hidden bytes from me and from my split-K partner
-  xwait(c, kBarG, g == 5 ? 2u * kCS * 256u : static_cast<uint32_t>(c.n_own) * (kD + 4), c.g_parity, true);
+  // consumes 512 operand bytes + the scale per sentence; FFN2: 8 rows x 256 hidden bytes from me and from my split-K partner
+  xwait(c, kBarG, next_gather_bytes, c.g_parity, true);
   if (tid == kIssuer) {
     fence_proxy_async_smem();      // operand rows were written through the generic proxy (shared memory only: the narrow fence)
     const uint32_t abase = smem_u32(c.smem + (g == 5 ? kSmBh : kSmBx));
@@ -969,6 +973,10 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   c.mark_slot = 0;
   c.t_step = 0;
   if (tid == kLoader) fill_until(c, kSlots);
+  if (tid == 0 && n_steps > 0) {       // first use of the gather / scatter barriers (the first step reads its token from ys: no token exchange)
+    mbar_arrive_expect_tx(smem_u32(&c.bars[kBarG]), static_cast<uint32_t>(c.n_own) * (kD + 4));
+    if (c.b >= 0) mbar_arrive_expect_tx(smem_u32(&c.bars[kBarS]), 3 * kD * 4);
+  }
   __syncwarp();
   // every CTA of the cluster is running (its shared memory may be written) and has its barriers initialised
   cluster_arrive_release();
@@ -985,7 +993,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
     // ---- token (arg-max over the 8 vocabulary slices of the previous step) -> embedding + positional encoding -> LayerNorm 1
     //      of layer 0 -> all-gather
     {
-      xwait(c, kBarS, 64, c.s_parity, own && t > t0);
+      xwait(c, kBarS, 3 * kD * 4, c.s_parity, own && t > t0);            // 64 bytes: the 8 slices' best (logit, index); next: q|k|v
       int* tok = reinterpret_cast<int*>(misc(c) + kMiTok);
       if (own && warp == 0) {
         int64_t token;
@@ -1018,26 +1026,29 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
           // index one past this GEMM's last weight chunk in the launch-wide chunk sequence
           const int g = q >> 1;
           const uint32_t gend = (static_cast<uint32_t>(t - t0) * nl + l) * kChunks + (g == 0 ? 4 : g == 1 ? 5 : g == 2 ? 6 : g == 3 ? 7 : g == 4 ? 11 : 15);
-          phase_gemm(c, l, g, gend);
+          // bytes of the gather that follows this one: operand rows + scales; FFN2's two 2 KB halves; the generator's fp32 rows
+          const uint32_t row_bytes = static_cast<uint32_t>(c.n_own) * (kD + 4);
+          const uint32_t next_gather = g < 4 ? row_bytes : g == 4 ? 2u * kCS * 256u : (l + 1 < nl ? row_bytes : static_cast<uint32_t>(c.n_own) * kD * 4);
+          phase_gemm(c, l, g, gend, next_gather);
         } else {
           // ---- row phases: my sentence's row has arrived from the 8 column owners
-          xwait(c, kBarS, (q == 1 ? 3 * kD : kD) * 4, c.s_parity, own);
+          xwait(c, kBarS, (q == 7 ? 4 * kD : kD) * 4, c.s_parity, own);     // next scatter: a 512-float row, or FFN2's 4 split-K planes
           if (q == 1 || q == 5) phase_attention(c, q == 1, t, l, pre);
           else phase_ln(c, 1, 0, t, L.ln_g[q == 3 ? 1 : 2], L.ln_b[q == 3 ? 1 : 2], true);
         }
       }
       // ---- residual + LayerNorm 1 of the next layer, or the final norm (fp32 row to every CTA's generator input)
-      xwait(c, kBarS, 4 * kD * 4, c.s_parity, own);      // 4 split-K planes of int32 partials
+      xwait(c, kBarS, l + 1 < nl ? 3 * kD * 4 : 64, c.s_parity, own);      // 4 split-K planes of int32 partials; next: q|k|v or the token
       if (l + 1 < nl) phase_ln(c, 2, 0, t, P.layer[l + 1].ln_g[0], P.layer[l + 1].ln_b[0], true, L.sw[5], L.bias[5]);
       else phase_ln(c, 2, 0, t, P.fin_g, P.fin_b, false, L.sw[5], L.bias[5]);
     }
     c.fine = false;
-    xwait(c, kBarG, static_cast<uint32_t>(c.n_own) * kD * 4, c.g_parity, true);
+    xwait(c, kBarG, t < t_last ? static_cast<uint32_t>(c.n_own) * (kD + 4) : 0u, c.g_parity, true);
     phase_generator(c);
     if (c.trace_on && tid == 0) P.trace[254] = tl_now();
   }
   // the last step's token
-  xwait(c, kBarS, 64, c.s_parity, own);
+  xwait(c, kBarS, 0, c.s_parity, own);
   if (own && warp == 0) {
     const int id = generator_pick(c, lane);
     if (lane == 0) P.ys[static_cast<int64_t>(c.b) * P.ys_ld + t_last + 1] = id;
