@@ -42,7 +42,8 @@ __device__ __forceinline__ float div127_exact(float x) {
   const float r2 = __fmaf_rn(__fmaf_rn(-127.0f, r, 1.0f), r, r);
   const float q0 = __fmul_rn(x, r2);
   const float q1 = __fmaf_rn(__fmaf_rn(-127.0f, q0, x), r2, q0);
-  return (x == 0.0f || (x >= 1e-5f && x <= 1e30f)) ? q1 : __fdiv_rn(x, 127.0f);
+  if (__builtin_expect(!(x == 0.0f || (x >= 1e-5f && x <= 1e30f)), 0)) return __fdiv_rn(x, 127.0f);
+  return q1;
 }
 __device__ __forceinline__ float quant_scale_x(float amax) { return div127_exact(fmaxf(amax, 1e-5f)); }
 // x / 511 (the N-1 of the 512-feature LayerNorm), same construction, checked for every float in [1e-37, 1e37] (2,062,065,881 values).
@@ -51,7 +52,8 @@ __device__ __forceinline__ float div511_exact(float x) {
   const float r2 = __fmaf_rn(__fmaf_rn(-511.0f, r, 1.0f), r, r);
   const float q0 = __fmul_rn(x, r2);
   const float q1 = __fmaf_rn(__fmaf_rn(-511.0f, q0, x), r2, q0);
-  return (x == 0.0f || (x >= 1e-37f && x <= 1e37f)) ? q1 : __fdiv_rn(x, 511.0f);
+  if (__builtin_expect(!(x == 0.0f || (x >= 1e-37f && x <= 1e37f)), 0)) return __fdiv_rn(x, 511.0f);
+  return q1;
 }
 
 // RowQuant of quant_linear.py:31-43: s = max(amax, 1e-5) / 127 ; q = rint(x / s).
@@ -80,7 +82,7 @@ __device__ __forceinline__ uint32_t quant4_pack(float4 v, float s, float r) {
   const uint32_t a = quant_fast_bits(v.x, s, r, slow), b = quant_fast_bits(v.y, s, r, slow);
   const uint32_t c = quant_fast_bits(v.z, s, r, slow), d = quant_fast_bits(v.w, s, r, slow);
   uint32_t w = __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
-  if (slow) {
+  if (__builtin_expect(slow, 0)) {
     const int ia = quant_one(v.x, s), ib = quant_one(v.y, s), ic = quant_one(v.z, s), id = quant_one(v.w, s);
     w = (static_cast<uint32_t>(ia) & 0xFFu) | ((static_cast<uint32_t>(ib) & 0xFFu) << 8) | ((static_cast<uint32_t>(ic) & 0xFFu) << 16) |
         ((static_cast<uint32_t>(id) & 0xFFu) << 24);
