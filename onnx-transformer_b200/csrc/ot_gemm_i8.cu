@@ -878,7 +878,8 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
     }
   }
   constexpr int M01 = MODE == 1 ? 1 : 0;
-  if (MODE == 0 && block_n == 256 && g.out_kind == OT_OUT_Q8 && static_cast<int64_t>(m_tiles) * (g.N / 256) >= 2 * 148 && !getenv("OT_GEMM_ONE_CTA"))
+  static const int two_cta_min = getenv("OT_GEMM_TWO_CTA_MIN") ? atoi(getenv("OT_GEMM_TWO_CTA_MIN")) : 2 * 148;
+  if (MODE == 0 && block_n == 256 && g.out_kind == OT_OUT_Q8 && static_cast<int64_t>(m_tiles) * (g.N / 256) >= two_cta_min && !getenv("OT_GEMM_ONE_CTA"))
     return launch_gemm<256, 2, 0>(g, stream);
   switch (block_n) {
     case 256: return launch_gemm<256, 3, M01>(g, stream);
