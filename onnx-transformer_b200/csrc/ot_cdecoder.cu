@@ -1,7 +1,7 @@
 // ot_cdecoder_run: the KV-cached greedy decoder as a CLUSTER-RESIDENT persistent kernel (fault-free fast path of
 // greedy_decode, parallelized_inject_onnx_transformer.py:616-758 / batch_output.py:659-672).
 //
-// A greedy step at batch 64 is a chain of ~74 dependent operations of a few hundred KB each.  It is bound by the latency of
+// A greedy step at batch 64 is a chain of ~68 dependent operations of a few hundred KB each.  It is bound by the latency of
 // the all-to-all exchange between "column owners" (GEMM tiles need every sentence row) and "row owners" (LayerNorm, RowQuant,
 // softmax need every feature of a sentence), not by bandwidth or by the tensor cores.  ot_decoder.cu does that exchange through
 // L2 with a grid-wide barrier (~1.3 us + L2 round trips per link).  Here the exchange never leaves the SM-to-SM network:
@@ -18,7 +18,7 @@
 //     buffer of every CTA of the cluster;
 //   * both exchanges are DATA-FLOW synchronised: every remote store is a st.async that also signals complete_tx on an mbarrier
 //     of the destination CTA, and a consumer waits only for the bytes it is about to read.  There is no barrier.cluster in the
-//     steady state (it cost 0.7 us per exchange, 74 exchanges per greedy step).
+//     steady state (it cost 0.7 us per exchange, 68 exchanges per greedy step).
 //
 // Arithmetic is instruction-for-instruction that of the stand-alone kernels (ot_rowmath.cuh, ot_attention_decode.cuh,
 // ot_generator.cu), so tokens and KV caches are bit-identical to the per-op engine path (tests/test_decoder_gpu.py).
@@ -66,7 +66,8 @@ constexpr int kSmRow = kSmX + 2048;                         // 210944: int8 stag
 constexpr int kSmCtx = kSmRow + 2048;                       // 212992: epilogue staging (2 x 1 KB) / final-norm row (512 floats)
 constexpr int kSmMisc = kSmCtx + 2048;                      // 215040: scales, reduction scratch, generator partials, hidden-row maxima (2 KB)
 constexpr int kSmHot = kSmMisc + 2048;                      // 217088: CdHot copy (<= 1920 B) + 128 B of barriers
-constexpr int kSmTotal = kSmHot + 2048;                     // 219136
+constexpr int kSmW2 = kSmHot + 2048;                        // 219136: FFN2 column scales + bias (2 x 512 floats), prefetched for the LayerNorm after it
+constexpr int kSmTotal = kSmW2 + 4096;                      // 223232
 static_assert(kSmTotal + 1024 <= 232448, "shared memory budget");
 // The M = 64 MMA reads 8 row groups (8 KB) from each operand k-block although only the first group (8 sentences) is real:
 // the over-read past Bh must stay inside the CTA's allocation.
@@ -156,6 +157,9 @@ __device__ __forceinline__ void st_async_b32(uint32_t addr, uint32_t v, uint32_t
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(v), "r"(mbar) : "memory");
 }
 // 1-D bulk copy global -> shared through the TMA unit (async proxy), completion signalled on an mbarrier
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -432,14 +436,13 @@ __device__ __forceinline__ void push_row_q8(Ctx& c, const uint8_t* src, float sc
 __device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // LayerNorm of my sentence.  SRC 0: x = embedding(token)*sqrt(d) + pe[t]; SRC 1: x = x + recv (the scattered O / CO row);
-// SRC 2: x = x + (fl(fl(float(p0+p1+p2+p3)*s_h)*s_w[f]) + b[f]) with the 4 split-K int32 planes of FFN2 in recv (sw2 / b2 given).
+// SRC 2: x = x + (fl(fl(float(p0+p1+p2+p3)*s_h)*s_w[f]) + b[f]) with the 4 split-K int32 planes of FFN2 in recv (s_w / b staged in kSmW2).
 // quant: RowQuant -> all-gather into Bx; else (final norm) the fp32 row goes to every CTA's generator input.
 // The row is spread over 4 warps -- warp i holds float4 i*32+lane, exactly the element layernorm_row<4> gives lane `lane` in its
 // i-th register -- and every reduction is evaluated in layernorm_row's order: per lane ((p0 + p1) + p2) + p3 over the four
 // registers, then the xor-shuffle tree over lanes.  Same instructions on the same operands => bit-identical results, at a quarter
 // of the dependent-division chain (a single warp spends 2.2 us per row in IEEE divisions).
-__device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, const float* gamma, const float* beta, bool quant,
-                                         const float* sw2 = nullptr, const float* b2 = nullptr) {
+__device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, const float* gamma, const float* beta, bool quant) {
   const CdHot& P = *c.P;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* xr = reinterpret_cast<float*>(c.smem + kSmX);
@@ -461,7 +464,10 @@ __device__ __forceinline__ void phase_ln(Ctx& c, int SRC, int64_t token, int t, 
       const float4 res = reinterpret_cast<const float4*>(xr)[i4], y = reinterpret_cast<const float4*>(c.smem + kSmRecv)[i4];
       v = make_float4(__fadd_rn(res.x, y.x), __fadd_rn(res.y, y.y), __fadd_rn(res.z, y.z), __fadd_rn(res.w, y.w));
     } else {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(sw2) + i4), b4 = __ldg(reinterpret_cast<const float4*>(b2) + i4);
+      // FFN2's column scales / bias: copied to shared memory by this very thread during the FFN2 GEMM phase (an L2 round trip
+      // -- 0.35 us -- would otherwise sit in front of the first reduction)
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      const float4 w4 = reinterpret_cast<const float4*>(c.smem + kSmW2)[i4], b4 = reinterpret_cast<const float4*>(c.smem + kSmW2)[128 + i4];
       const int4* pl = reinterpret_cast<const int4*>(c.smem + kSmRecv);
       const int4 p0 = pl[i4], p1 = pl[128 + i4], p2 = pl[256 + i4], p3 = pl[384 + i4];
       // scale of my sentence's quantized hidden row: from its 16 partial maxima (exchanged during FFN1; every CTA derives the same value)
@@ -1029,6 +1035,12 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
           // bytes of the gather that follows this one: operand rows + scales; FFN2's two 2 KB halves; the generator's fp32 rows
           const uint32_t row_bytes = static_cast<uint32_t>(c.n_own) * (kD + 4);
           const uint32_t next_gather = g < 4 ? row_bytes : g == 4 ? 2u * kCS * 256u : (l + 1 < nl ? row_bytes : static_cast<uint32_t>(c.n_own) * kD * 4);
+          if (g == 5 && own && warp < 4) {      // thread i of the LayerNorm that follows: its own 16 bytes of FFN2's scales and bias
+            const int i4 = warp * 32 + lane;
+            cp_async16(smem_u32(c.smem + kSmW2) + 16u * i4, reinterpret_cast<const float4*>(L.sw[5]) + i4);
+            cp_async16(smem_u32(c.smem + kSmW2) + 2048u + 16u * i4, reinterpret_cast<const float4*>(L.bias[5]) + i4);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+          }
           phase_gemm(c, l, g, gend, next_gather);
         } else {
           // ---- row phases: my sentence's row has arrived from the 8 column owners
@@ -1039,8 +1051,8 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
       }
       // ---- residual + LayerNorm 1 of the next layer, or the final norm (fp32 row to every CTA's generator input)
       xwait(c, kBarS, l + 1 < nl ? 3 * kD * 4 : 64, c.s_parity, own);      // 4 split-K planes of int32 partials; next: q|k|v or the token
-      if (l + 1 < nl) phase_ln(c, 2, 0, t, P.layer[l + 1].ln_g[0], P.layer[l + 1].ln_b[0], true, L.sw[5], L.bias[5]);
-      else phase_ln(c, 2, 0, t, P.fin_g, P.fin_b, false, L.sw[5], L.bias[5]);
+      if (l + 1 < nl) phase_ln(c, 2, 0, t, P.layer[l + 1].ln_g[0], P.layer[l + 1].ln_b[0], true);
+      else phase_ln(c, 2, 0, t, P.fin_g, P.fin_b, false);
     }
     c.fine = false;
     xwait(c, kBarG, t < t_last ? static_cast<uint32_t>(c.n_own) * (kD + 4) : 0u, c.g_parity, true);
