@@ -234,8 +234,8 @@ __device__ __forceinline__ void issue_chunk(Ctx& c) {
   ++c.pn;
 }
 // loader thread: issue every chunk below `upto` (chunk n reuses the slot of chunk n - kSlots, free once that chunk's MMAs have
-// completed).  Called right after a GEMM's last MMA: no GEMM has more than kSlots chunks, so every GEMM starts with all of its
-// weights in flight or resident.
+// completed: the wait below).  Called at the start of every GEMM phase with upto = kSlots chunks past the GEMM's last one: no GEMM
+// has more than kSlots chunks, so every GEMM starts with all of its weights in flight or resident.
 __device__ __forceinline__ void fill_until(Ctx& c, uint32_t upto) {
   upto = min(upto, c.total);
   while (c.pn < upto) {
@@ -301,7 +301,10 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend, 
     }
     mma_commit(smem_u32(&c.bars[kBarAcc]));
   } else if (tid == kLoader) {
-    mbar_wait(smem_u32(&c.bars[kBarAcc]), c.acc_parity);     // every slot this GEMM used is free: refill the ring
+    // Refill the ring WHILE this GEMM's MMAs run: a slot is reloaded as soon as the MMAs that read it have completed (its `empty`
+    // barrier), so all but the last chunk of the refill streams in during the MMA window.  Measured: a 128 KB TMA burst issued
+    // after the last MMA stalls every shared-memory load of the SM for ~0.9 us -- exactly when the epilogue and the next row
+    // phase need them -- while loads that land during the MMAs cost nothing (the MMA time is unchanged).
     fill_until(c, gend + kSlots);
   }
   __syncwarp();
