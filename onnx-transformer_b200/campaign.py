@@ -205,16 +205,16 @@ def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials
     golden = engine.greedy_decode(ids, mask).cpu().numpy()
     mine = trials[rank::world]
     out = []
-    for c0 in range(0, len(mine), batch):
-        chunk = mine[c0:c0 + batch]
-        rows = torch.tensor([t.sentence for t in chunk], dtype=torch.int64, device=dev)
-        specs = [FaultSpec(t.module, t.layer, t.target, t.inject_type, t.bit, t.flat_index, t.window_start, t.window_len, t.value_bits, step=0)
-                 for t in chunk]
-        if len(chunk) < batch:                      # keep one workspace / CUDA graph shape: pad with fault-free rows
-            pad = batch - len(chunk)
-            rows = torch.cat([rows, rows.new_zeros(pad)])
-            specs = specs + [None] * pad
-        faulty = engine.greedy_decode(ids[rows].contiguous(), mask[rows].contiguous(), fault=specs).cpu().numpy()
+    # Two batches in flight: while the GPU decodes batch i (one long persistent-decoder launch), the host classifies batch i-1 and
+    # launches the encoder / fault step of batch i+1.  Nothing in the loop synchronises the stream: index and result buffers are
+    # pinned, copies are asynchronous, a batch's tokens are read after its own event.
+    rows_pin = [torch.zeros(batch, dtype=torch.int64).pin_memory() for _ in range(2)]
+    ys_pin = [torch.zeros((batch, engine.max_len), dtype=torch.int64).pin_memory() for _ in range(2)]
+
+    def finish(item):
+        chunk, buf, ev = item
+        ev.synchronize()
+        faulty = buf.numpy()
         for k, trial in enumerate(chunk):
             res = classify(golden[trial.sentence], faulty[k])
             res.update(asdict(trial))
@@ -222,6 +222,27 @@ def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials
             if csv_path:
                 with open(csv_path, "a") as f:
                     f.write(csv_row(trial, res))
+
+    pending = None
+    for i, c0 in enumerate(range(0, len(mine), batch)):
+        chunk = mine[c0:c0 + batch]
+        specs = [FaultSpec(t.module, t.layer, t.target, t.inject_type, t.bit, t.flat_index, t.window_start, t.window_len, t.value_bits, step=0)
+                 for t in chunk]
+        rp = rows_pin[i % 2]
+        rp.zero_()                                  # keep one workspace / CUDA graph shape: pad with fault-free rows of sentence 0
+        rp[:len(chunk)] = torch.tensor([t.sentence for t in chunk], dtype=torch.int64)
+        specs = specs + [None] * (batch - len(chunk))
+        rows = rp.to(dev, non_blocking=True)
+        ys = engine.greedy_decode(ids[rows].contiguous(), mask[rows].contiguous(), fault=specs)
+        buf = ys_pin[i % 2]
+        buf[:, :ys.shape[1]].copy_(ys, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        if pending is not None:
+            finish(pending)
+        pending = (chunk, buf, ev)
+    if pending is not None:
+        finish(pending)
     return out
 
 

@@ -325,7 +325,9 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend, 
       // operand buffers of the two CTAs whose split-K slice covers them: itself and rank ^ 1.  (Before: fp32 scatter to the
       // sentence's owner, a RowQuant phase there, and an all-gather: one more exchange per layer.)
       // Here: y -> shared memory [sentence][256 columns] (8-float groups XOR-swizzled by the sentence against bank conflicts).
-      float* ybuf = reinterpret_cast<float*>(c.smem + kSmRecv) + srow * 256;
+      // (in the V region, idle between the attention phases: NOT in recv -- FFN2's split-K planes are scattered into recv by CTAs
+      // that depend only on their own pair's hidden bytes and may get there while this CTA still reads y)
+      float* ybuf = reinterpret_cast<float*>(c.smem + kSmVs) + srow * 256;
       float am = 0.f;
 #pragma unroll
       for (int gq = 0; gq < 4; ++gq) {
@@ -399,7 +401,7 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend, 
                              fmaxf(fmaxf(fmaxf(mc.x, mc.y), fmaxf(mc.z, mc.w)), fmaxf(fmaxf(md.x, md.y), fmaxf(md.z, md.w))));
     const float s = quant_scale_x(amax);
     const float rinv = __frcp_rn(s);
-    const float4* y4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(c.smem + kSmRecv) + warp * 256 + ((8 * lane) ^ (warp << 3)));
+    const float4* y4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(c.smem + kSmVs) + warp * 256 + ((8 * lane) ^ (warp << 3)));
     uint2 w;
     w.x = quant4_pack(y4[0], s, rinv);
     w.y = quant4_pack(y4[1], s, rinv);

@@ -51,8 +51,8 @@ def _fault_ref(fault: Optional[OtFault]):
 _FAULT_DTYPE = None
 
 
-def pack_faults(faults, device) -> torch.Tensor:
-    """A list of OtFault -> device byte tensor holding the C array (32 bytes per entry)."""
+def faults_to_numpy(faults):
+    """A list of OtFault -> numpy uint8 array holding the C array (32 bytes per entry)."""
     import numpy as np
     global _FAULT_DTYPE
     if _FAULT_DTYPE is None:
@@ -62,7 +62,12 @@ def pack_faults(faults, device) -> torch.Tensor:
     arr = np.zeros(len(faults), dtype=_FAULT_DTYPE)
     for i, f in enumerate(faults):
         arr[i] = (f.mode, f.bit, f.flat_index, f.window_start, f.window_len, f.value_bits, f.reserved)
-    return torch.from_numpy(arr.view(np.uint8)).to(device)
+    return arr.view(np.uint8)
+
+
+def pack_faults(faults, device) -> torch.Tensor:
+    """A list of OtFault -> device byte tensor holding the C array (32 bytes per entry)."""
+    return torch.from_numpy(faults_to_numpy(faults)).to(device)
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
