@@ -82,3 +82,36 @@ def test_bleu_method4_and_classification():
     ys = np.array([0, 5, 6, 1, 9, 9]); ys2 = np.array([0, 5, 7, 1, 9, 9]); ys3 = np.array([0, 5, 6, 7, 8, 9])
     assert C.classify(ys, ys)["outcome"] == "masked" and C.classify(ys, ys2)["outcome"] == "changed"
     assert C.classify(ys, ys3)["outcome"] == "no-EOS"
+
+
+def test_pipelined_batched_trials_are_deterministic_and_path_independent():
+    """Full-size model, 64 trials per batched decode, two batches in flight: the same tokens trial for trial (a) on a second run and
+    (b) with the 70 fault-free steps on the per-op kernel path instead of the cluster-resident decoder.  (The 100,000-trial version is
+    tools/campaign_consistency.py; it found a shared-memory reuse race that changed 3 of 100,000 trials.)"""
+    import hashlib
+    from onnx_transformer_b200.engine import QuantizedTransformer
+    fw = W.init_float_weights(0)
+    ids, mask = W.synthetic_tokens(11, 64, 64)
+    trials = C.make_trials(1280, 0, 64, 64)
+
+    def run(eng):
+        orig, hashes = C.classify, {}
+
+        def spy(golden, faulty):
+            r = orig(golden, faulty)
+            r["hash"] = hashlib.md5(np.ascontiguousarray(faulty).tobytes()).hexdigest()
+            return r
+        C.classify = spy
+        try:
+            for r in C.run_trials_batched(eng, ids, mask, trials, 64):
+                hashes[r["trial_id"]] = r["hash"]
+        finally:
+            C.classify = orig
+        return hashes
+
+    ep = QuantizedTransformer(fw, persistent=True)
+    a, b = run(ep), run(ep)
+    assert len(a) == len(trials) and a == b
+    assert ep.persistent_steps > 0
+    g = run(QuantizedTransformer(fw, persistent=False))
+    assert [k for k in a if a[k] != g[k]] == []
