@@ -181,7 +181,9 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)
 // (it reaches the next wait 0.3-0.6 us after the row phase it also works in).  The first use is armed at kernel start.
 // A CTA cannot run two phases ahead of its own threads: between a wait and this CTA's contribution to the next exchange on the
 // same barrier lies a block barrier of the phase in between.  Buffers are reused every second exchange; that is safe because a CTA
-// sends its contribution to exchange k+1 only after it has consumed exchange k.  Also the profiling hook: CTA 0
+// sends its contribution to exchange k+1 only after it has consumed exchange k AND every exchange is an all-to-all -- except the
+// FFN1 -> FFN2 hand-off (pair-wise): a pair may be one GEMM phase ahead of the rest of the cluster, so nothing a CTA still uses in
+// its FFN1 tail may live in a buffer that FFN2's epilogue writes remotely (recv).  Also the profiling hook: CTA 0
 // stamps the begin / end of every wait.
 __device__ __forceinline__ void xwait(Ctx& c, int bar, uint32_t next_bytes, uint32_t& parity, bool waits) {
   mark(c, 1);
