@@ -276,7 +276,7 @@ def extra_measurements(eng, dev):
     eng._enc_ws = {}
     torch.cuda.empty_cache()
     ids_np, mask_np = W.synthetic_tokens(11, 64, 64)
-    trials = C.make_trials(256, 0, 64, 64)
+    trials = C.make_trials(2048, 0, 64, 64)
     C.run_trials_batched(eng, ids_np, mask_np, trials[:64], 64)            # warm-up
     torch.cuda.synchronize()
     t0 = time.perf_counter()
