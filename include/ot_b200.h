@@ -36,12 +36,15 @@ enum OtFaultMode {
   OT_FAULT_WEIGHT = 2,         /* WEIGHT / WEIGHT16: bit flip in the int8 B operand                   */
   OT_FAULT_RANDOM_BITFLIP = 3, /* flip bit `bit` (0 = LSB .. 31) of one fp32 output element, NaN -> 0 */
   OT_FAULT_RANDOM = 4,         /* replace one fp32 output element by `value_bits`, NaN -> 0           */
-  OT_FAULT_ACC_BITFLIP = 5     /* flip bit `bit` of one int32 accumulator (north-star epilogue hook)  */
+  OT_FAULT_ACC_BITFLIP = 5,    /* flip bit `bit` of one int32 accumulator (north-star epilogue hook)  */
+  OT_FAULT_OUT_Q8_BITFLIP = 6  /* flip bit `bit` (0..7, wrap as flip_int8_bit, inject_utils/layers.py:61-68) of one
+                                  requantized int8 output element (OT_OUT_Q8 only; north-star epilogue hook) */
 };
 
 typedef struct OtFault {
   int32_t mode;         /* enum OtFaultMode */
-  int32_t bit;          /* 0..7 for operand faults, 0..31 for output / accumulator faults */
+  int32_t bit;          /* 0..7 for operand faults (0..3 for packed int4 weights: flip_int4_bit, layers.py:48-59),
+                           0..31 for output / accumulator faults */
   int64_t flat_index;   /* row-major flat index into the faulty tensor: A [M,K], B [N,K] or out [M,N] */
   int32_t window_start; /* INPUT16: first affected output column; WEIGHT16: first affected output row */
   int32_t window_len;   /* number of affected columns / rows; <= 0 means the whole row / column      */
@@ -52,7 +55,9 @@ typedef struct OtFault {
 enum OtGemmOut {
   OT_OUT_I32 = 0, /* raw int32 accumulators (ONNX MatMulInteger)                                        */
   OT_OUT_F32 = 1, /* fp32: fl(fl(float(acc)*row_scale[m])*col_scale[n]) + bias[n], ReLU, + residual      */
-  OT_OUT_Q8 = 2   /* OT_OUT_F32 followed by the per-row abs-max requant over groups of `quant_group` cols */
+  OT_OUT_Q8 = 2,  /* OT_OUT_F32 followed by the per-row abs-max requant over groups of `quant_group` cols */
+  OT_OUT_QLINEAR = 3 /* ONNX QLinearMatMul: int8 saturate(rint(fl(fl(float(acc')*a_scale)*b_scale) / y_scale) + y_zp)
+                        (internal to ot_qlinear_matmul) */
 };
 
 /* ---- library / device ---------------------------------------------------------------------------- */
@@ -103,6 +108,35 @@ int ot_linear_w4a8(const int8_t* A, int64_t lda, const uint8_t* W4, int64_t ldw,
                    const float* residual, int64_t ldr, int relu,
                    int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group,
                    const OtFault* fault, void* stream);
+
+/* ot_linear_w8a8_mf for packed int4 weights (cfg4 fault trials; WEIGHT faults flip one of the 4 bits: flip_int4_bit,
+ * inject_utils/layers.py:48-59). */
+int ot_linear_w4a8_mf(const int8_t* A, int64_t lda, const uint8_t* W4, int64_t ldw, int M, int N, int K,
+                      const float* row_scale, const float* col_scale, const float* bias,
+                      const float* residual, int64_t ldr, int relu,
+                      int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group,
+                      const OtFault* faults_dev, const int32_t* unit_fault_dev, int rows_per_unit, void* stream);
+
+/* ONNX-spec MatMulInteger (the dialect-B / QCDQ graphs of inject_operations.py):
+ *   out[m,n] = sum_k (A[m,k] - a_zp[m]) * (W[n,k] - b_zp[n])          int32, wrap-around
+ * computed as the int8 tensor-core GEMM with the zero-point correction applied to the accumulator in the epilogue:
+ *   acc - a_zp[m]*b_colsum[n] - b_zp[n]*a_rowsum[m] + K*a_zp[m]*b_zp[n].
+ * W is K-major [N,K] (the transposed ONNX B operand).  a_zp [M] / b_zp [N] are int32 DEVICE arrays or NULL (= 0);
+ * a_rowsum [M] (required with b_zp) and b_colsum [N] (required with a_zp) come from ot_rowsum_i8.  uint8 operands are passed as
+ * int8 (x ^ 0x80) with their zero point lowered by 128.  Parity: ONNX operator spec only (no reference artefact). */
+int ot_matmul_integer(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K,
+                      const int32_t* a_zp, const int32_t* b_zp, const int32_t* a_rowsum, const int32_t* b_colsum,
+                      int32_t* out, int64_t ldo, const OtFault* fault, void* stream);
+
+/* ONNX-spec QLinearMatMul: out int8 [M,N] = saturate(rint(fl(fl(float(acc') * a_scale[m]) * b_scale[n]) / y_scale) + y_zp), acc' as in
+ * ot_matmul_integer; a_scale [M] / b_scale [N] fp32 DEVICE arrays (NULL = 1). */
+int ot_qlinear_matmul(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K,
+                      const float* a_scale, const float* b_scale, const int32_t* a_zp, const int32_t* b_zp,
+                      const int32_t* a_rowsum, const int32_t* b_colsum, float y_scale, int y_zp,
+                      int8_t* out, int64_t ldo, void* stream);
+
+/* Row sums of an int8 matrix [rows, cols] (pitch ld) -> int32 [rows]: the operand sums of the zero-point correction. */
+int ot_rowsum_i8(const int8_t* X, int64_t ld, int64_t rows, int cols, int32_t* out, void* stream);
 
 /* a6+a7+a8..a10 in one kernel: A = RowQuant(LayerNorm(x)) is produced in shared memory by the GEMM's own warps
  * (layer_norm.py:12-15 + quant_linear.py:31-43, op for op as ot_layernorm_quant) and fed to the MMA without a round trip
@@ -244,7 +278,7 @@ int ot_where_f32(const uint8_t* cond, const int64_t c_shape[4], float a_scalar, 
                  float* out, const int64_t out_shape[4], void* stream);
 /* Equal(x, scalar) on int64 -> u8. */
 int ot_equal_i64(const int64_t* x, int64_t scalar, uint8_t* out, int64_t n, void* stream);
-/* Cast between element kinds (0 f32, 1 i64, 2 u8/bool, 3 i8, 4 i32). */
+/* Cast between element kinds (0 f32, 1 i64, 2 u8 read numerically / written as bool 0|1, 3 i8, 4 i32; destination only: 5 = numeric u8). */
 int ot_cast(int src_kind, const void* src, int dst_kind, void* dst, int64_t n, void* stream);
 /* 4-D permutation copy of 4-byte elements (Transpose). */
 int ot_transpose4_b32(const void* x, const int64_t shape[4], const int perm[4], void* y, void* stream);

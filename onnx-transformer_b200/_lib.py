@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(HERE, "libot_b200.so")
 
 OT_OK, OT_EINVAL, OT_ECUDA, OT_ENODEV = 0, -1, -2, -3
 
-FAULT_NONE, FAULT_INPUT, FAULT_WEIGHT, FAULT_RANDOM_BITFLIP, FAULT_RANDOM, FAULT_ACC_BITFLIP = range(6)
-OUT_I32, OUT_F32, OUT_Q8 = 0, 1, 2
+FAULT_NONE, FAULT_INPUT, FAULT_WEIGHT, FAULT_RANDOM_BITFLIP, FAULT_RANDOM, FAULT_ACC_BITFLIP, FAULT_OUT_Q8_BITFLIP = range(7)
+OUT_I32, OUT_F32, OUT_Q8, OUT_QLINEAR = 0, 1, 2, 3
 
 
 class OtFault(C.Structure):
@@ -50,6 +50,10 @@ SIGNATURES = {
     "ot_linear_w8a8": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, C.POINTER(OtFault), _p]),
     "ot_linear_w8a8_mf": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, _p, _p, _i, _p]),
     "ot_linear_w4a8": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, C.POINTER(OtFault), _p]),
+    "ot_linear_w4a8_mf": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, _p, _p, _i, _p]),
+    "ot_matmul_integer": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _l, C.POINTER(OtFault), _p]),
+    "ot_qlinear_matmul": (_i, [_p, _l, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _i, _p, _l, _p]),
+    "ot_rowsum_i8": (_i, [_p, _l, _l, _i, _p, _p]),
     "ot_ln_linear_w8a8": (_i, [_p, _l, _p, _p, _f, _p, _l, _i, _i, _i, _p, _p, _p, _l, _i, _i, _p, _l, _p, _i, _p]),
     "ot_unpack_int4": (_i, [_p, _p, _l, _l, _p]),
     "ot_pack_int4": (_i, [_p, _p, _l, _l, _p]),

@@ -67,7 +67,8 @@ def _tensor_shape(module: str, target: str, operand: str, S: int, T: int):
     raise ValueError(target)
 
 
-def make_trials(n: int, seed: int, n_sentences: int, src_len: int, modules: Sequence[str] = ("Encoder", "Decoder"), n_layers: int = 6) -> List[Trial]:
+def make_trials(n: int, seed: int, n_sentences: int, src_len: int, modules: Sequence[str] = ("Encoder", "Decoder"), n_layers: int = 6,
+                weight_bits: int = 8) -> List[Trial]:
     """cfg5: trials = (sentence id, target, inject_type, bit, element index, window) from default_rng(seed).
     Decoder trials inject at greedy step 0 (target_inference_number = 1, :832), i.e. with T = 1."""
     from .graph import decoder_matmul_name, encoder_matmul_name
@@ -87,6 +88,8 @@ def make_trials(n: int, seed: int, n_sentences: int, src_len: int, modules: Sequ
         flat = int(np.ravel_multi_index(idx, shape))
         out_shape = _tensor_shape(module, target, "output", src_len, 1)
         bit = int(rng.integers(0, 32)) if ftype == "RANDOM_BITFLIP" else int(rng.integers(0, 8))
+        if weight_bits == 4 and ftype.startswith("WEIGHT") and target in ("ffn1", "ffn2"):
+            bit &= 3                    # cfg4: the linear weights are 4-bit (inject_main.py:410 `range(4)`, flip_int4_bit)
         ws, wl = 0, 0
         if ftype == "INPUT16":
             blocks = out_shape[3] // 16
@@ -104,7 +107,9 @@ def make_trials(n: int, seed: int, n_sentences: int, src_len: int, modules: Sequ
 def sentence_bleu_method4(reference: Sequence[int], hypothesis: Sequence[int]) -> float:
     """nltk.translate.bleu_score.sentence_bleu([reference], hypothesis, smoothing_function=SmoothingFunction().method4)
     (the call at parallelized_inject_onnx_transformer.py:393-397) on token sequences: uniform 4-gram weights, brevity
-    penalty, method4 smoothing (zero n-gram matches are replaced by 1 / (2^k * K / ln(len(hyp)))), K = 5."""
+    penalty, method4 smoothing (zero n-gram matches are replaced by 1 / (2^k * K / ln(len(hyp)))), K = 5.  Restated from nltk 3.8's
+    corpus_bleu / modified_precision / brevity_penalty / SmoothingFunction.method4 (nltk is not installable here: the pins are the
+    hand-evaluated closed forms of tests/test_bleu_cpu.py)."""
     hyp_len, ref_len = len(hypothesis), len(reference)
     if hyp_len == 0:
         return 0.0
@@ -126,9 +131,9 @@ def sentence_bleu_method4(reference: Sequence[int], hypothesis: Sequence[int]) -
             incvnt += 1
         else:
             p.append(num / den)
-    if min(p) <= 0:
-        return 0.0
-    return bp * math.exp(sum(0.25 * math.log(x) for x in p))
+    # nltk sums w_i * log(p_i) over the p_i > 0 only (corpus_bleu): a 1-token hypothesis (method4 does not smooth when
+    # len(hyp) == 1) scores bp * p_1 ** 0.25, not 0
+    return bp * math.exp(math.fsum(0.25 * math.log(x) for x in p if x > 0))
 
 
 def _sentence(ys: np.ndarray) -> Optional[List[int]]:
@@ -193,7 +198,7 @@ def run_trials(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials: List[T
 
 
 def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials: List[Trial], batch: int = 64,
-                       csv_path: Optional[str] = None, rank: int = 0, world: int = 1) -> List[Dict[str, object]]:
+                       csv_path: Optional[str] = None, rank: int = 0, world: int = 1, return_tokens: bool = False) -> List[Dict[str, object]]:
     """Same outcomes as run_trials, `batch` trials per greedy decode: row b of a batch re-decodes trial b's sentence with
     trial b's fault (one fault per batch unit: ot_linear_w8a8_mf / ot_attention_q8_mf).  The kernels are batch-invariant,
     so every row equals the batch-1 decode the reference would run."""
@@ -218,6 +223,8 @@ def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials
         for k, trial in enumerate(chunk):
             res = classify(golden[trial.sentence], faulty[k])
             res.update(asdict(trial))
+            if return_tokens:
+                res["golden_ys"], res["faulty_ys"] = golden[trial.sentence].copy(), faulty[k].copy()
             out.append(res)
             if csv_path:
                 with open(csv_path, "a") as f:

@@ -119,4 +119,12 @@ __host__ __device__ inline int flip_int8_bit(int value, int bit) {
   return flipped;
 }
 
+// 4-bit two's-complement bit flip with wrap to [-8, 7], as inject_utils/layers.py:48-59 (flip_int4_bit).
+__host__ __device__ inline int flip_int4_bit(int value, int bit) {
+  int flipped = value ^ (1 << bit);
+  if (flipped > 7) flipped -= 16;
+  if (flipped < -8) flipped += 16;
+  return flipped;
+}
+
 }  // namespace ot

@@ -119,6 +119,7 @@ __device__ __forceinline__ void store_as(int kind, void* dst, int64_t i, S v) {
     case 1: reinterpret_cast<int64_t*>(dst)[i] = static_cast<int64_t>(v); break;
     case 2: reinterpret_cast<uint8_t*>(dst)[i] = (v != S(0)) ? 1 : 0; break;   // Cast to bool
     case 3: reinterpret_cast<int8_t*>(dst)[i] = static_cast<int8_t>(v); break;
+    case 5: reinterpret_cast<uint8_t*>(dst)[i] = static_cast<uint8_t>(v); break;   // numeric uint8 (QuantizeLinear results)
     default: reinterpret_cast<int32_t*>(dst)[i] = static_cast<int32_t>(v); break;
   }
 }
@@ -297,7 +298,7 @@ extern "C" int ot_equal_i64(const int64_t* x, int64_t scalar, uint8_t* out, int6
 
 extern "C" int ot_cast(int src_kind, const void* src, int dst_kind, void* dst, int64_t n, void* stream) {
   OT_REQUIRE_DEVICE();
-  OT_REQUIRE(src && dst && n >= 0 && src_kind >= 0 && src_kind <= 4 && dst_kind >= 0 && dst_kind <= 4, "bad cast arguments");
+  OT_REQUIRE(src && dst && n >= 0 && src_kind >= 0 && src_kind <= 4 && dst_kind >= 0 && dst_kind <= 5, "bad cast arguments");
   if (n == 0) return OT_OK;
   cast_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(src_kind, src, dst_kind, dst, n);
   OT_CHECK_CUDA(cudaGetLastError());

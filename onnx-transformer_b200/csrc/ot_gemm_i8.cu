@@ -65,6 +65,13 @@ struct GemmArgs {
   const OtFault* mf_faults;
   const int32_t* mf_unit;
   int mf_rows;
+  // ONNX MatMulInteger / QLinearMatMul zero points: acc' = acc - a_zp[m]*colsum(W)[n] - b_zp[n]*rowsum(A)[m] + K*a_zp[m]*b_zp[n]
+  const int32_t* a_zp;      // [M] or NULL (0)
+  const int32_t* b_zp;      // [N] or NULL (0)
+  const int32_t* a_rowsum;  // [M]: sum_k A[m,k]   (needed when b_zp != NULL)
+  const int32_t* b_colsum;  // [N]: sum_k W[n,k]   (needed when a_zp != NULL)
+  float y_scale;            // OT_OUT_QLINEAR: q = saturate(rint(y / y_scale) + y_zp)
+  int y_zp;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -127,7 +134,7 @@ __device__ __noinline__ FaultCtx resolve_fault_at(const GemmArgs& g, const OtFau
     f.col = static_cast<int>(ft.flat_index / g.K);
     f.k = static_cast<int>(ft.flat_index % g.K);
     int q = load_w_elem(g, f.col, f.k);
-    f.delta = flip_int8_bit(q, ft.bit) - q;
+    f.delta = (g.w4 ? flip_int4_bit(q, ft.bit) : flip_int8_bit(q, ft.bit)) - q;   // inject_utils/layers.py:48-68
     f.w0 = row0 + (ft.window_len > 0 ? ft.window_start : 0);
     f.w1 = row0 + (ft.window_len > 0 ? min(nrows, ft.window_start + ft.window_len) : nrows);
   } else if (f.mode != OT_FAULT_NONE) {
@@ -185,6 +192,27 @@ __device__ __forceinline__ void patch_acc(const GemmArgs& g, const FaultCtx& f, 
   for (int j = 0; j < CW; ++j) acc[j] = tmp[j];
 }
 
+// Zero-point correction of ONNX MatMulInteger / QLinearMatMul, exact in int32 (wrap-around like the operator's int32 accumulator).
+template <int CW>
+__device__ __noinline__ void zp_correct_array(const GemmArgs& g, int row, int col0, int* acc) {
+  const int azp = g.a_zp ? g.a_zp[row] : 0;
+  const int rs = g.b_zp ? g.a_rowsum[row] : 0;
+  for (int j = 0; j < CW; ++j) {
+    const int bzp = g.b_zp ? g.b_zp[col0 + j] : 0;
+    const int cs = g.a_zp ? g.b_colsum[col0 + j] : 0;
+    acc[j] = acc[j] - azp * cs - bzp * rs + g.K * azp * bzp;
+  }
+}
+template <int CW>
+__device__ __forceinline__ void zp_correct(const GemmArgs& g, int row, int col0, int (&acc)[CW]) {
+  int tmp[CW];
+#pragma unroll
+  for (int j = 0; j < CW; ++j) tmp[j] = acc[j];
+  zp_correct_array<CW>(g, row, col0, tmp);
+#pragma unroll
+  for (int j = 0; j < CW; ++j) acc[j] = tmp[j];
+}
+
 // fp32 output faults on the MatMul result (before the bias Add): inject_utils/layers.py:18-33.  `vals[idx]` is the golden value.
 __device__ __noinline__ float patch_out(const GemmArgs& g, const FaultCtx& f, int row, int col, float, const float* vals, int idx) {
   float v = 0.f;
@@ -229,6 +257,7 @@ __device__ __forceinline__ void chunk_values(const GemmArgs& g, const FaultCtx& 
 #pragma unroll
   for (int j = 0; j < kCW; ++j) acc[j] = static_cast<int>(r[j]);
   if (f.mode != OT_FAULT_NONE && row_ok) patch_acc<kCW>(g, f, row, col0 + c, acc);
+  if ((g.a_zp != nullptr || g.b_zp != nullptr) && row_ok) zp_correct<kCW>(g, row, col0 + c, acc);
   float cs[kCW], bs[kCW];
 #pragma unroll
   for (int j = 0; j < kCW / 4; ++j) {   // 128-bit broadcast reads of the staged column parameters
@@ -266,14 +295,39 @@ __device__ __noinline__ void quant_exact_array(const float* y, float s, float* n
 }
 
 // What a pass does with the fp32 values of a chunk.
-enum { PASS_STORE_F32 = 0, PASS_AMAX = 1, PASS_STORE_Q8 = 2 };
+enum { PASS_STORE_F32 = 0, PASS_AMAX = 1, PASS_STORE_Q8 = 2, PASS_STORE_QLINEAR = 3 };
 struct PassState {
   float amax;    // PASS_AMAX result
   float s, s_rcp;  // PASS_STORE_Q8 scale and its reciprocal
 };
+// int8-output bit flip (north star: "applied to the int32 accumulator or int8 output inside the epilogue"): flip_int8_bit
+// (inject_utils/layers.py:61-68) on one element of the requantized tensor, out of line.
+__device__ __noinline__ uint32_t flip_packed_q8(uint32_t word, int byte, int bit) {
+  const int q = static_cast<int8_t>((word >> (8 * byte)) & 0xFFu);
+  const uint32_t nb = static_cast<uint32_t>(flip_int8_bit(q, bit)) & 0xFFu;
+  return (word & ~(0xFFu << (8 * byte))) | (nb << (8 * byte));
+}
+
 template <int KIND>
-__device__ __forceinline__ void consume_chunk(const GemmArgs& g, PassState& st, const float (&y)[kCW], int row, bool row_ok, int col) {
-  if (KIND == PASS_AMAX) {
+__device__ __forceinline__ void consume_chunk(const GemmArgs& g, const FaultCtx& f, PassState& st, const float (&y)[kCW], int row, bool row_ok, int col) {
+  if (KIND == PASS_STORE_QLINEAR) {
+    // ONNX QLinearMatMul: saturate(rint(y / y_scale) + y_zp), y = fl(fl(float(acc') * a_scale) * b_scale)
+    if (row_ok) {
+      uint32_t packed[kCW / 4];
+#pragma unroll
+      for (int j = 0; j < kCW / 4; ++j) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float qf = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(y[4 * j + b], g.y_scale)), static_cast<float>(g.y_zp)), -128.0f), 127.0f);
+          w |= (static_cast<uint32_t>(__float2int_rn(qf)) & 0xFFu) << (8 * b);
+        }
+        packed[j] = w;
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<int8_t*>(g.out) + static_cast<int64_t>(row) * g.ldo + col) =
+          make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+  } else if (KIND == PASS_AMAX) {
 #pragma unroll
     for (int j = 0; j < kCW; ++j) st.amax = fmaxf(st.amax, fabsf(y[j]));
   } else if (KIND == PASS_STORE_F32) {
@@ -305,6 +359,12 @@ __device__ __forceinline__ void consume_chunk(const GemmArgs& g, PassState& st, 
           packed[j] = w;
         }
       }
+      if (f.mode == OT_FAULT_OUT_Q8_BITFLIP && row == f.row && f.col >= col && f.col < col + kCW) {
+        const int e = f.col - col;
+#pragma unroll
+        for (int j = 0; j < kCW / 4; ++j)
+          if (j == (e >> 2)) packed[j] = flip_packed_q8(packed[j], e & 3, f.bit);
+      }
       *reinterpret_cast<uint4*>(reinterpret_cast<int8_t*>(g.out) + static_cast<int64_t>(row) * g.ldo + col) =
           make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
@@ -332,7 +392,7 @@ __device__ __forceinline__ void epilogue_pass(const GemmArgs& g, const FaultCtx&
       load_residual(g, has_res, row, col_base + c + kCW, resb);
     }
     chunk_values(g, f, e, ra, resa, has_res, row, row_ok, col_base, c, s_cs, s_bias, sx, y);
-    consume_chunk<KIND>(g, st, y, row, row_ok, col_base + c);
+    consume_chunk<KIND>(g, f, st, y, row, row_ok, col_base + c);
     if (!has_b) break;
     tmem_wait_ld();
     if (c + 2 * kCW < c1) {
@@ -340,7 +400,7 @@ __device__ __forceinline__ void epilogue_pass(const GemmArgs& g, const FaultCtx&
       load_residual(g, has_res, row, col_base + c + 2 * kCW, resa);
     }
     chunk_values(g, f, e, rb, resb, has_res, row, row_ok, col_base, c + kCW, s_cs, s_bias, sx, y);
-    consume_chunk<KIND>(g, st, y, row, row_ok, col_base + c + kCW);
+    consume_chunk<KIND>(g, f, st, y, row, row_ok, col_base + c + kCW);
   }
 }
 
@@ -638,6 +698,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < kCW; ++j) acc[j] = static_cast<int>(r[j]);
         if (f.mode != OT_FAULT_NONE && row_ok) patch_acc<kCW>(g, f, row, col_base + c, acc);
+        if ((g.a_zp != nullptr || g.b_zp != nullptr) && row_ok) zp_correct<kCW>(g, row, col_base + c, acc);
         if (row_ok) {
           int4* dst = reinterpret_cast<int4*>(out + static_cast<int64_t>(row) * g.ldo + col_base + c);
 #pragma unroll
@@ -647,6 +708,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else if (g.out_kind == OT_OUT_F32) {
       PassState st = {0.f, 1.f, 1.f};
       epilogue_pass<PASS_STORE_F32>(g, f, e, taddr_row, row, row_ok, col_base, c_lo, c_hi, s_cs, s_bias, sx, st);
+    } else if (g.out_kind == OT_OUT_QLINEAR) {
+      PassState st = {0.f, 1.f, 1.f};
+      epilogue_pass<PASS_STORE_QLINEAR>(g, f, e, taddr_row, row, row_ok, col_base, c_lo, c_hi, s_cs, s_bias, sx, st);
     } else {
       // OT_OUT_Q8, pass 1: per-row abs-max over this CTA's BLOCK_N columns, broadcast to the cluster.
       PassState st = {0.f, 1.f, 1.f};
@@ -889,20 +953,33 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
   }
 }
 
+struct ZpArgs {
+  const int32_t* a_zp = nullptr;
+  const int32_t* b_zp = nullptr;
+  const int32_t* a_rowsum = nullptr;
+  const int32_t* b_colsum = nullptr;
+  float y_scale = 1.0f;
+  int y_zp = 0;
+};
+
 static int linear_common(bool w4, const int8_t* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                          const float* row_scale, const float* col_scale, const float* bias, const float* residual, int64_t ldr,
                          int relu, int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group, const OtFault* fault,
-                         void* stream, const OtFault* mf_faults = nullptr, const int32_t* mf_unit = nullptr, int mf_rows = 0) {
+                         void* stream, const OtFault* mf_faults = nullptr, const int32_t* mf_unit = nullptr, int mf_rows = 0,
+                         const ZpArgs* zp = nullptr) {
   OT_REQUIRE_DEVICE();
   OT_REQUIRE(A && W && out, "null operand");
   OT_REQUIRE(M > 0 && N > 0 && K > 0, "empty problem");
   OT_REQUIRE(N % 32 == 0, "N must be a multiple of 32");
   OT_REQUIRE(K % 16 == 0 && lda % 16 == 0 && ldw % 16 == 0, "K and row pitches must be multiples of 16 bytes (TMA)");
   OT_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "operands must be 16-byte aligned");
-  OT_REQUIRE(out_kind >= OT_OUT_I32 && out_kind <= OT_OUT_Q8, "bad out_kind");
+  OT_REQUIRE(out_kind >= OT_OUT_I32 && out_kind <= OT_OUT_QLINEAR, "bad out_kind");
   OT_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
   if (out_kind == OT_OUT_Q8) {
     OT_REQUIRE(out_scale != nullptr, "OT_OUT_Q8 needs out_scale");
+    OT_REQUIRE(ldo % 16 == 0, "int8 out pitch must be a multiple of 16");
+  } else if (out_kind == OT_OUT_QLINEAR) {
+    OT_REQUIRE(zp != nullptr && zp->y_scale > 0.0f, "OT_OUT_QLINEAR needs a positive y_scale");
     OT_REQUIRE(ldo % 16 == 0, "int8 out pitch must be a multiple of 16");
   } else {
     OT_REQUIRE(ldo % 4 == 0, "out pitch must be a multiple of 4 elements");
@@ -918,11 +995,20 @@ static int linear_common(bool w4, const int8_t* A, int64_t lda, const void* W, i
   g.out = out; g.ldo = ldo; g.out_scale = out_scale;
   g.cluster_n = 1;
   g.w4 = w4 ? 1 : 0;
+  if (zp != nullptr) {
+    OT_REQUIRE(zp->a_zp == nullptr || zp->b_colsum != nullptr, "a_zp needs the column sums of W");
+    OT_REQUIRE(zp->b_zp == nullptr || zp->a_rowsum != nullptr, "b_zp needs the row sums of A");
+    g.a_zp = zp->a_zp; g.b_zp = zp->b_zp; g.a_rowsum = zp->a_rowsum; g.b_colsum = zp->b_colsum;
+    g.y_scale = zp->y_scale; g.y_zp = zp->y_zp;
+  }
   if (fault) {
     g.fault = *fault;
+    OT_REQUIRE(fault->mode >= OT_FAULT_NONE && fault->mode <= OT_FAULT_OUT_Q8_BITFLIP, "unknown fault mode");
     if (fault->mode == OT_FAULT_INPUT) OT_REQUIRE(fault->flat_index >= 0 && fault->flat_index < (int64_t)M * K && fault->bit >= 0 && fault->bit < 8, "INPUT fault out of range");
-    if (fault->mode == OT_FAULT_WEIGHT) OT_REQUIRE(fault->flat_index >= 0 && fault->flat_index < (int64_t)N * K && fault->bit >= 0 && fault->bit < 8, "WEIGHT fault out of range");
+    if (fault->mode == OT_FAULT_WEIGHT)
+      OT_REQUIRE(fault->flat_index >= 0 && fault->flat_index < (int64_t)N * K && fault->bit >= 0 && fault->bit < (w4 ? 4 : 8), "WEIGHT fault out of range");
     if (fault->mode >= OT_FAULT_RANDOM_BITFLIP) OT_REQUIRE(fault->flat_index >= 0 && fault->flat_index < (int64_t)M * N && fault->bit >= 0 && fault->bit < 32, "output fault out of range");
+    if (fault->mode == OT_FAULT_OUT_Q8_BITFLIP) OT_REQUIRE(out_kind == OT_OUT_Q8 && fault->bit < 8, "OT_FAULT_OUT_Q8_BITFLIP needs OT_OUT_Q8 and bit < 8");
   } else {
     g.fault.mode = OT_FAULT_NONE;
   }
@@ -952,6 +1038,32 @@ extern "C" int ot_linear_w8a8_mf(const int8_t* A, int64_t lda, const int8_t* W, 
                                  const OtFault* faults_dev, const int32_t* unit_fault_dev, int rows_per_unit, void* stream) {
   return ot::linear_common(false, A, lda, W, ldw, M, N, K, row_scale, col_scale, bias, residual, ldr, relu, out_kind, out, ldo,
                            out_scale, quant_group, nullptr, stream, faults_dev, unit_fault_dev, rows_per_unit);
+}
+
+extern "C" int ot_linear_w4a8_mf(const int8_t* A, int64_t lda, const uint8_t* W4, int64_t ldw, int M, int N, int K,
+                                 const float* row_scale, const float* col_scale, const float* bias, const float* residual,
+                                 int64_t ldr, int relu, int out_kind, void* out, int64_t ldo, float* out_scale, int quant_group,
+                                 const OtFault* faults_dev, const int32_t* unit_fault_dev, int rows_per_unit, void* stream) {
+  return ot::linear_common(true, A, lda, W4, ldw, M, N, K, row_scale, col_scale, bias, residual, ldr, relu, out_kind, out, ldo,
+                           out_scale, quant_group, nullptr, stream, faults_dev, unit_fault_dev, rows_per_unit);
+}
+
+extern "C" int ot_matmul_integer(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K, const int32_t* a_zp,
+                                 const int32_t* b_zp, const int32_t* a_rowsum, const int32_t* b_colsum, int32_t* out, int64_t ldo,
+                                 const OtFault* fault, void* stream) {
+  ot::ZpArgs zp;
+  zp.a_zp = a_zp; zp.b_zp = b_zp; zp.a_rowsum = a_rowsum; zp.b_colsum = b_colsum;
+  return ot::linear_common(false, A, lda, W, ldw, M, N, K, nullptr, nullptr, nullptr, nullptr, 0, 0, OT_OUT_I32, out, ldo, nullptr, 0, fault,
+                           stream, nullptr, nullptr, 0, &zp);
+}
+
+extern "C" int ot_qlinear_matmul(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K, const float* a_scale,
+                                 const float* b_scale, const int32_t* a_zp, const int32_t* b_zp, const int32_t* a_rowsum,
+                                 const int32_t* b_colsum, float y_scale, int y_zp, int8_t* out, int64_t ldo, void* stream) {
+  ot::ZpArgs zp;
+  zp.a_zp = a_zp; zp.b_zp = b_zp; zp.a_rowsum = a_rowsum; zp.b_colsum = b_colsum; zp.y_scale = y_scale; zp.y_zp = y_zp;
+  return ot::linear_common(false, A, lda, W, ldw, M, N, K, a_scale, b_scale, nullptr, nullptr, 0, 0, OT_OUT_QLINEAR, out, ldo, nullptr, 0,
+                           nullptr, stream, nullptr, nullptr, 0, &zp);
 }
 
 extern "C" int ot_ln_linear_w8a8(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, const int8_t* W, int64_t ldw,

@@ -132,6 +132,31 @@ __global__ void __launch_bounds__(256) pack_int4_kernel(const int8_t* __restrict
   }
 }
 
+// Row sums of an int8 matrix (zero-point correction terms of ONNX MatMulInteger / QLinearMatMul): warp per row, 16-byte loads where
+// the row allows, dp4a against 0x01010101.
+__global__ void __launch_bounds__(256) rowsum_i8_kernel(const int8_t* __restrict__ x, int64_t ld, int64_t rows, int cols, int32_t* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int8_t* r = x + row * ld;
+  int acc = 0;
+  const bool vec = ((reinterpret_cast<uintptr_t>(r) & 15) == 0);
+  const int nv = vec ? (cols >> 4) : 0;
+  for (int i = lane; i < nv; i += 32) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(r) + i);
+    acc = __dp4a(static_cast<int>(v.x), 0x01010101, acc);
+    acc = __dp4a(static_cast<int>(v.y), 0x01010101, acc);
+    acc = __dp4a(static_cast<int>(v.z), 0x01010101, acc);
+    acc = __dp4a(static_cast<int>(v.w), 0x01010101, acc);
+  }
+  for (int i = nv * 16 + lane; i < cols; i += 32) acc += r[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = acc;
+}
+
 // ys[b, step+1] = next[b]; step++  (greedy_decode: parallelized_inject_onnx_transformer.py:753-758)
 __global__ void append_token_kernel(int64_t* __restrict__ ys, int64_t ld, const int64_t* __restrict__ next, int B,
                                     int32_t* __restrict__ step_dev) {
@@ -187,6 +212,15 @@ extern "C" int ot_rowquant(const float* x, int64_t ldx, int64_t rows, int n, int
   const int warps = 8;
   OT_CHECK_CUDA(launch_kernel(rowquant_kernel, dim3(static_cast<unsigned>((items + warps - 1) / warps)), dim3(warps * 32), 0, as_stream(stream), 1,
                               x, ldx, rows, n, group, q, s, xhat));
+  count_launch();
+  return OT_OK;
+}
+
+extern "C" int ot_rowsum_i8(const int8_t* X, int64_t ld, int64_t rows, int cols, int32_t* out, void* stream) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(X && out && rows >= 0 && cols > 0 && ld >= cols, "bad rowsum arguments");
+  if (rows == 0) return OT_OK;
+  OT_CHECK_CUDA(launch_kernel(rowsum_i8_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, as_stream(stream), 1, X, ld, rows, cols, out));
   count_launch();
   return OT_OK;
 }

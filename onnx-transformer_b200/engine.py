@@ -59,6 +59,10 @@ class FaultSpec:
             mode = K.FAULT_RANDOM_BITFLIP
         elif t == "RANDOM":
             mode = K.FAULT_RANDOM
+        elif t == "ACC_BITFLIP":          # north-star epilogue hooks on the linear GEMMs: one int32 accumulator bit ...
+            mode = K.FAULT_ACC_BITFLIP
+        elif t == "OUT_Q8_BITFLIP":       # ... or one bit of a requantized int8 output element (q|k|v, ffn1, cross k|v)
+            mode = K.FAULT_OUT_Q8_BITFLIP
         else:
             raise ValueError("unknown inject_type %r" % t)
         operand = 0
@@ -99,9 +103,8 @@ class _Linear:
             self.w4 = True
 
     def gemm(self, a_q, row_scale, **kw):
-        """a_q @ W^T through the tcgen05 GEMM with this layer's scales and bias (w8 or packed-w4 weights)."""
-        if self.w4 and (kw.get("fault") is not None or kw.get("mf") is not None):
-            raise K.OtError("fault hooks are implemented for the int8-weight engine (dialect A)")
+        """a_q @ W^T through the tcgen05 GEMM with this layer's scales and bias (w8 or packed-w4 weights; a WEIGHT fault on packed
+        int4 weights flips one of 4 bits: flip_int4_bit, inject_utils/layers.py:48-59)."""
         return K.linear_w8a8(a_q, self.wq, row_scale=row_scale, col_scale=self.sw, bias=self.bias, w4=self.w4, **kw)
 
 
@@ -194,7 +197,15 @@ class QuantizedTransformer:
         # measurement hook (bench.py): when a list, greedy_decode appends a (start, end) CUDA-event pair around every
         # persistent-decoder launch, recorded on the launching stream
         self.decoder_events = None
+        # parity hook (tests/test_fullsize_parity_gpu.py): when a dict, encode() / the per-op greedy step store a clone of the operands and
+        # results of every launch site under "<module><layer>.<name>" so each MatMul can be re-checked on the model's own operands
+        self.capture: Optional[dict] = None
         torch.cuda.synchronize(self.dev)
+
+    def _cap(self, prefix: str, **tensors):
+        if self.capture is not None:
+            for k, v in tensors.items():
+                self.capture[prefix + "." + k] = v.clone()
 
     # ------------------------------------------------------------------------------------------ fault plumbing
     def _fk(self, fault, module: str, layer: int, targets, rows_per_unit: int, adjust=None) -> dict:
@@ -251,7 +262,7 @@ class QuantizedTransformer:
             i = names.index(tgt)
             if fo.mode == K.FAULT_WEIGHT:
                 fo.flat_index += i * D * D                       # row block i of the concatenated weight
-            elif fo.mode in (K.FAULT_RANDOM, K.FAULT_RANDOM_BITFLIP):
+            elif fo.mode in (K.FAULT_RANDOM, K.FAULT_RANDOM_BITFLIP, K.FAULT_ACC_BITFLIP, K.FAULT_OUT_Q8_BITFLIP):
                 r, c = divmod(fo.flat_index, D)
                 fo.flat_index = r * width_n + i * D + c
             elif fo.mode == K.FAULT_INPUT:
@@ -307,26 +318,32 @@ class QuantizedTransformer:
         for l, L in enumerate(self.enc):
             fk = (lambda *tgt, _l=l, **kw: self._fk(fault, "Encoder", _l, tgt, S, **kw))  # noqa: E731
             nxt = ws["x"][1 - cur]
+            cp = "enc%d" % l
             K.layernorm_quant(x, L["ln1"][0], L["ln1"][1], want_q=True, q=ws["xq"], s=ws["sx"])
+            self._cap(cp, x0=x, xq1=ws["xq"], sx1=ws["sx"])
             self._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], fk)
             K.attention_q8(ws["qkv"], ws["sqkv"], ws["qkv"][:, D:], ws["qkv"][:, 2 * D:], ws["sqkv"][:, 1:], ws["sqkv"][:, 2:],
                            B=B, Tq=S, Tk=S, ldq=3 * D, sq_stride=3, ldk=3 * D, skv_stride=3, mask_kind=1, key_mask=mask, mask_stride=S,
                            want_ctx=True, ctx=ws["ctx"], want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], **fk("qk", "pv"))
+            self._cap(cp, qkv=ws["qkv"], sqkv=ws["sqkv"], ctx=ws["ctx"], cq=ws["cq"], cs=ws["cs"])
             L["o"].gemm(ws["cq"], ws["cs"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("o"))
             x, cur = nxt, 1 - cur
             nxt = ws["x"][1 - cur]
             K.layernorm_quant(x, L["ln2"][0], L["ln2"][1], want_q=True, q=ws["xq"], s=ws["sx"])
+            self._cap(cp, x1=x, xq2=ws["xq"], sx2=ws["sx"])
             L["w1"].gemm(ws["xq"], ws["sx"], relu=True,
                           out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"], **fk("ffn1"))
             L["w2"].gemm(ws["hq"], ws["sh"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("ffn2"))
+            self._cap(cp, hq=ws["hq"], sh=ws["sh"], x2=nxt)
             x, cur = nxt, 1 - cur
             if capture is not None:
                 capture["enc%d.out" % l] = x.clone()
                 capture["enc%d.qkv" % l] = ws["qkv"].clone()
         memory = torch.empty((B, S, D), dtype=torch.float32, device=self.dev)
         K.layernorm_quant(x, self.enc_norm[0], self.enc_norm[1], want_y=True, want_q=False, y=memory)
+        self._cap("enc", x_final=x, memory=memory)
         return memory
 
     def _qkv(self, lin: _Linear, xq, sx, out, out_scale, fk):
@@ -448,6 +465,7 @@ class QuantizedTransformer:
                     kw = {"mf": self._mf_tensors(entries, unit) + (S,)}
         self.ckv.gemm(ws["mq"], ws["sm"], out_kind=K.OUT_Q8,
                       quant_group=D, out=ws["ckv"], out_scale=ws["sckv"], **kw)
+        self._cap("dec", mq=ws["mq"], sm=ws["sm"], ckv=ws["ckv"], sckv=ws["sckv"])
 
     def _decode_step(self, ws: dict, B: int, S: int, fault: Optional[FaultSpec] = None, want_margin: bool = False):
         """One greedy step for all sentences: embed ys[:, t] -> 6 decoder layers on ONE new row per sentence (KV cache) ->
@@ -474,6 +492,10 @@ class QuantizedTransformer:
                            k_new=ws["qkv"][:, D:], v_new=ws["qkv"][:, 2 * D:], sk_new=ws["sqkv"][:, 1:], sv_new=ws["sqkv"][:, 2:],
                            ld_new=3 * D, snew_stride=3, mask_kind=2, step_dev=step,
                            want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], **fk("qk", "pv"))
+            if self.capture is not None:
+                cp = "dec%d" % l
+                self._cap(cp, x0=x, xq1=ws["xq"], sx1=ws["sx"], qkv=ws["qkv"], sqkv=ws["sqkv"], cq=ws["cq"], cs=ws["cs"],
+                          kc=ws["kc"][l], vc=ws["vc"][l], skc=ws["skc"][l], svc=ws["svc"][l])
             L["o"].gemm(ws["cq"], ws["cs"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("o"))
             x, cur = nxt, 1 - cur
@@ -490,6 +512,8 @@ class QuantizedTransformer:
                            B=B, Tq=1, Tk=S, Tk_cap=S, ldq=D, sq_stride=1, ldk=2 * D * nl, skv_stride=2 * nl, mask_kind=1,
                            key_mask=ws["mask"], mask_stride=S, want_ctx=False, want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"],
                            **fk("cqk", "cpv"))
+            if self.capture is not None:
+                self._cap("dec%d" % l, x1=x, xq2=ws["xq"], sx2=ws["sx"], q2=ws["q2"], sq2=ws["sq2"], ccq=ws["cq"], ccs=ws["cs"])
             L["co"].gemm(ws["cq"], ws["cs"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("co"))
             x, cur = nxt, 1 - cur
@@ -504,15 +528,18 @@ class QuantizedTransformer:
                               out_kind=K.OUT_Q8, quant_group=FF, out=ws["hq"], out_scale=ws["sh"], **fk("ffn1"))
             L["w2"].gemm(ws["hq"], ws["sh"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("ffn2"))
+            if self.capture is not None:
+                self._cap("dec%d" % l, x2=x, xq3=ws["xq"], sx3=ws["sx"], hq=ws["hq"], sh=ws["sh"], x3=nxt)
             x, cur = nxt, 1 - cur
         K.layernorm_quant(x, self.dec_norm[0], self.dec_norm[1], want_y=True, want_q=False, y=ws["hout"])
         K.generator_argmax(ws["hout"], self.gen_w, self.gen_b, next_ids=ws["next"], scratch=ws["logits"],
                            want_margin=want_margin, margin=ws["margin"] if want_margin else None)
+        self._cap("dec", x_final=x, hout=ws["hout"], logits=ws["logits"], next=ws["next"])
         K.append_token(ws["ys"], ws["next"], step)
 
     def greedy_decode(self, src_ids: torch.Tensor, src_mask: torch.Tensor, max_len: Optional[int] = None, start_symbol: int = W.BOS_ID,
                       fault: Optional[FaultSpec] = None, use_graph: bool = True, memory: Optional[torch.Tensor] = None,
-                      return_margins: bool = False):
+                      return_margins: bool = False, per_op_step: Optional[int] = None):
         """Batched greedy decoding (batch_output.py:659-672 semantics: 71 steps, no early stop).
         src_ids int64 [B,S] on the device, src_mask bool [B,1,S].  Returns ys int64 [B,max_len] (device tensor)."""
         max_len = max_len or self.max_len
@@ -531,7 +558,8 @@ class QuantizedTransformer:
         specs = [] if fault is None else ([fault] if isinstance(fault, FaultSpec) else [sp for sp in fault if sp is not None])
         steps = {sp.step for sp in specs if sp.module == "Decoder" and sp.target not in ("ck", "cv")}
         assert len(steps) <= 1, "all Decoder-target faults of a batch must share one injection step"
-        fault_step = steps.pop() if steps else -1
+        # per_op_step: run that (fault-free) greedy step through the per-op kernels too -- the step self.capture records
+        fault_step = steps.pop() if steps else (per_op_step if per_op_step is not None else -1)
         want_m = return_margins
         plan = self._decoder_plan(ws, B, S) if (use_graph and not want_m) else None
         if plan is not None:

@@ -2,7 +2,9 @@
 
 Same entry points, argument meaning and hook behaviour as onnx_optimized_inference.py:
     run_module:297  inference:214  execute_node:18  expand_node_inputs_outputs:236  get_weight_dict:273  prepare_inference:282
-(and the `inject_operations.py` variants through `inject_input=` aliases at the bottom).
+The `inject_operations.py` variant of the same API (dialect B / QCDQ graphs: 4-tuple `execute_node`, `inject_input`, the
+DequantizeLinear-keyed operand hook, `perturb_matmul`) lives in onnx-transformer_b200/inject_operations.py and is served by the
+handler table below.
 
 Differences, all forced by the B200 design:
   * `weight_dict` values are torch CUDA tensors (numpy inputs are uploaded on entry); every intermediate is still kept
@@ -31,6 +33,8 @@ from . import kernels as K
 from .graph import Attribute, Graph, Initializer, Node, ValueInfo
 
 META_KEY = "__ot_int8__"   # side table: tensor name -> int8 provenance (never an ONNX tensor name)
+HOST_KEY = "__ot_host__"   # side table: small initializers (shapes, Clip bounds, scalars, zero points) kept on the host as numpy, filled by
+                           # get_weight_dict, so the walk does not synchronise the stream to read them (.item() / .tolist())
 FLOAT_MAX = 3.4e38          # onnx_optimized_inference.py:252
 
 
@@ -91,6 +95,16 @@ def _scalar(t: torch.Tensor):
     return t.numel() == 1
 
 
+def _host(node, pos: int, ins, wd) -> np.ndarray:
+    """Host copy of operand `pos` of `node`: from the side table of small initializers when the operand is one (no device
+    synchronisation), else read back from the device (a shape computed at run time by a raw, un-cleaned export)."""
+    name = node.input[pos] if pos < len(node.input) else ""
+    cached = wd.get(HOST_KEY, {}).get(name)
+    if cached is not None:
+        return cached
+    return ins[pos].detach().cpu().numpy()
+
+
 def _h_unary(op):
     def run(node, ins, wd):
         return K.unary(op, ins[0])
@@ -122,9 +136,17 @@ def _h_round(node, ins, wd):
 
 
 def _h_clip(node, ins, wd):
-    lo = float(ins[1].item()) if len(ins) > 1 and ins[1] is not None else -FLOAT_MAX
-    hi = float(ins[2].item()) if len(ins) > 2 and ins[2] is not None else FLOAT_MAX
-    return K.clip(ins[0], lo, hi)
+    x = ins[0]
+    if x.dtype in (torch.int8, torch.uint8):
+        # dialect B: QuantizeLinear -> Clip(-2^(b-1), 2^(b-1)-1) on the integer tensor when bit_width < 8
+        lo = int(_host(node, 1, ins, wd).reshape(-1)[0]) if len(ins) > 1 and ins[1] is not None else (-128 if x.dtype == torch.int8 else 0)
+        hi = int(_host(node, 2, ins, wd).reshape(-1)[0]) if len(ins) > 2 and ins[2] is not None else (127 if x.dtype == torch.int8 else 255)
+        out = K.cast(K.clip(K.cast(x, torch.float32, numeric_u8=True), float(lo), float(hi)), x.dtype, numeric_u8=True)
+        _meta(wd)[node.output[0]] = ("q", out)
+        return out
+    lo = float(_host(node, 1, ins, wd).reshape(-1)[0]) if len(ins) > 1 and ins[1] is not None else -FLOAT_MAX
+    hi = float(_host(node, 2, ins, wd).reshape(-1)[0]) if len(ins) > 2 and ins[2] is not None else FLOAT_MAX
+    return K.clip(x, lo, hi)
 
 
 def _h_reduce(op):
@@ -147,14 +169,14 @@ def _h_where(node, ins, wd):
     cond, a, x = ins
     if not _scalar(a):
         raise K.OtError("%s: Where with a tensor `X` operand has no CUDA handler" % node.name)
-    return K.where_scalar(cond, float(a.item()), x)
+    return K.where_scalar(cond, float(_host(node, 1, ins, wd).reshape(-1)[0]), x)
 
 
 def _h_equal(node, ins, wd):
     x, c = ins
     if x.dtype != torch.int64 or not _scalar(c):
         raise K.OtError("%s: Equal is implemented for int64 tensor == scalar" % node.name)
-    return K.equal_scalar_i64(x, int(c.item()))
+    return K.equal_scalar_i64(x, int(_host(node, 1, ins, wd).reshape(-1)[0]))
 
 
 _ONNX_DTYPE = {1: torch.float32, 7: torch.int64, 9: torch.bool, 3: torch.int8, 6: torch.int32, 2: torch.uint8}
@@ -179,13 +201,19 @@ def _h_transpose(node, ins, wd):
     src = m.get(node.input[0])
     if src is not None and src[0] == "qs" and perm == [1, 0] and x.dim() == 2:
         m[node.output[0]] = ("qsT", src[1], src[2])       # weight: keep the K-major int8 tensor, no data movement needed
-    if x.dtype == torch.bool:
-        return K.transpose(x.view(torch.uint8).to(torch.int32), perm).to(torch.bool)
+    if x.dtype in (torch.bool, torch.int8, torch.uint8):        # the transpose kernel moves 4-byte elements: widen, move, narrow (all CUDA handlers)
+        wide = K.cast(x.view(torch.uint8) if x.dtype == torch.bool else x, torch.int32, numeric_u8=True)
+        out = K.cast(K.transpose(wide, perm), torch.uint8 if x.dtype == torch.bool else x.dtype, numeric_u8=True)
+        if x.dtype == torch.bool:
+            return out.view(torch.bool)
+        if src is not None and src[0] == "q":
+            m[node.output[0]] = ("q", out)
+        return out
     return K.transpose(x, perm)
 
 
 def _h_reshape(node, ins, wd):
-    shape = [int(v) for v in ins[1].tolist()]
+    shape = [int(v) for v in _host(node, 1, ins, wd).reshape(-1)]
     x = ins[0]
     shape = [x.shape[i] if s == 0 else s for i, s in enumerate(shape)]
     out = x.reshape(shape)
@@ -199,7 +227,7 @@ def _h_reshape(node, ins, wd):
 def _h_unsqueeze(node, ins, wd):
     axes = node.attr("axes")
     if axes is None and len(ins) > 1:
-        axes = [int(v) for v in ins[1].tolist()]
+        axes = [int(v) for v in _host(node, 1, ins, wd).reshape(-1)]
     out = ins[0]
     for ax in sorted(int(a) for a in axes):
         out = out.unsqueeze(ax)
@@ -215,38 +243,149 @@ def _h_matmul(node, ins, wd):
         wq, sw = mb[1], mb[2]
         out = K.linear_w8a8(aq.contiguous(), wq.contiguous(), row_scale=sa, col_scale=sw, out_kind=K.OUT_F32)
         return out.reshape(tuple(a.shape[:-1]) + (wq.shape[0],))
+    if ma is not None and mb is not None and ma[0] == "dq" and mb[0] == "dq" and b.dim() == 2:
+        # dialect B: DequantizeLinear(A, per-row scale) x DequantizeLinear(W [K,N], per-column scale), zero points 0 -> the same
+        # int-exact factorisation; the K-major copy of the (static) weight is made once per weight tensor
+        if ma[3] in ("row", "scalar") and mb[3] in ("col", "scalar") and ma[1].dtype == torch.int8 and mb[1].dtype == torch.int8:
+            aq = ma[1].reshape(-1, ma[1].shape[-1]).contiguous()
+            if aq.shape[1] % 16 == 0 and mb[1].shape[1] % 32 == 0:
+                wt = _kmajor_weight(wd, node.input[1], mb[1])
+                sw = mb[2].reshape(-1)
+                sw = sw.expand(wt.shape[0]).contiguous() if sw.numel() == 1 else sw.contiguous()
+                sa = ma[2].reshape(-1)
+                sa = sa.expand(aq.shape[0]).contiguous() if sa.numel() == 1 else sa.contiguous()
+                out = K.linear_w8a8(aq, wt, row_scale=sa, col_scale=sw, out_kind=K.OUT_F32)
+                return out.reshape(tuple(a.shape[:-1]) + (wt.shape[0],))
     return K.matmul_f32(a, b)
 
 
+def _kmajor_weight(wd, name: str, w_kn: torch.Tensor) -> torch.Tensor:
+    """int8 [K,N] -> [N,K] (the tensor-core GEMM takes both operands K-major), cached per tensor name and storage."""
+    cache = _meta(wd).setdefault("__kmajor__", {})
+    hit = cache.get(name)
+    if hit is not None and hit[0] == w_kn.data_ptr():
+        return hit[1]
+    wt = K.cast(K.transpose(K.cast(w_kn, torch.int32), [1, 0]), torch.int8)
+    cache[name] = (w_kn.data_ptr(), wt)
+    return wt
+
+
+def _zero_point(node, pos, ins, wd):
+    """(device tensor or None, host numpy or None) of an optional zero-point operand; None when absent or identically zero."""
+    if pos >= len(ins) or ins[pos] is None:
+        return None, None
+    host = _host(node, pos, ins, wd)
+    if not np.any(host):
+        return None, None
+    return ins[pos], host
+
+
+def _as_s8(q: torch.Tensor, zp_dev, zp_host):
+    """uint8 operand -> the int8 tensor x ^ 0x80 (= x - 128) with its zero point lowered by 128 (the tensor cores take signed bytes)."""
+    if q.dtype == torch.int8:
+        return q, zp_dev
+    if q.dtype != torch.uint8:
+        raise K.OtError("integer MatMul operands must be int8 or uint8, got %s" % q.dtype)
+    shifted = K.cast(K.binary("Sub", K.cast(q, torch.float32, numeric_u8=True), torch.full((1,), 128.0, device=q.device)), torch.int8)
+    host = (zp_host.astype(np.int64) if zp_host is not None else np.zeros(1, np.int64)) - 128
+    return shifted, torch.from_numpy(host.astype(np.int32)).to(q.device)
+
+
 def _h_matmul_integer(node, ins, wd):
-    """ONNX MatMulInteger(A int8 [M,K], B int8 [K,N], a_zero_point, b_zero_point) -> int32, zero points folded on the
-    host side only when they are zero (dialect B uses zero_point = 0)."""
+    """ONNX MatMulInteger(A [.., K], B [K, N], a_zero_point, b_zero_point) -> int32: the int8 tensor-core GEMM with the zero-point
+    correction  - a_zp[m]*colsum(B)[n] - b_zp[n]*rowsum(A)[m] + K*a_zp[m]*b_zp[n]  applied to the accumulator in the epilogue
+    (ot_matmul_integer).  Spec-level parity only."""
     a, b = ins[0], ins[1]
-    for zp in ins[2:]:
-        if zp is not None and int(zp.abs().max().item()) != 0:
-            raise K.OtError("%s: non-zero zero points are not used by either dialect" % node.name)
-    bt = K.transpose(b.to(torch.int32), [1, 0]).to(torch.int8) if b.dim() == 2 else None
-    if bt is None or a.dtype != torch.int8:
-        raise K.OtError("%s: MatMulInteger expects int8 [.., K] x int8 [K, N]" % node.name)
-    out = K.linear_w8a8(a.reshape(-1, a.shape[-1]).contiguous(), bt.contiguous(), out_kind=K.OUT_I32)
-    return out.reshape(tuple(a.shape[:-1]) + (bt.shape[0],))
+    if b.dim() != 2:
+        raise K.OtError("%s: MatMulInteger expects B of rank 2" % node.name)
+    azd, azh = _zero_point(node, 2, ins, wd)
+    bzd, bzh = _zero_point(node, 3, ins, wd)
+    a8, azd = _as_s8(a, azd, azh)
+    b8, bzd = _as_s8(b, bzd, bzh)
+    wt = _kmajor_weight(wd, node.input[1], b8) if b.dtype == torch.int8 else K.cast(K.transpose(K.cast(b8, torch.int32), [1, 0]), torch.int8)
+    a2 = a8.reshape(-1, a8.shape[-1]).contiguous()
+    if azd is not None and azd.numel() not in (1, a2.shape[0]):
+        raise K.OtError("%s: a_zero_point must be a scalar or one value per row" % node.name)
+    out = K.matmul_integer(a2, wt, a_zp=azd, b_zp=bzd)
+    return out.reshape(tuple(a.shape[:-1]) + (wt.shape[0],))
+
+
+def _h_qlinear_matmul(node, ins, wd):
+    """ONNX QLinearMatMul(a, a_scale, a_zp, b, b_scale, b_zp, y_scale, y_zp) -> int8:
+    saturate(rint(fl(fl(float(acc') * a_scale) * b_scale) / y_scale) + y_zp), acc' as in MatMulInteger (ot_qlinear_matmul)."""
+    a, a_scale, b, b_scale = ins[0], ins[1], ins[3], ins[4]
+    if b.dim() != 2:
+        raise K.OtError("%s: QLinearMatMul expects b of rank 2" % node.name)
+    azd, azh = _zero_point(node, 2, ins, wd)
+    bzd, bzh = _zero_point(node, 5, ins, wd)
+    y_scale = float(_host(node, 6, ins, wd).reshape(-1)[0])
+    yzh = _host(node, 7, ins, wd) if len(ins) > 7 and ins[7] is not None else np.zeros(1, np.int8)
+    if yzh.dtype != np.int8:
+        raise K.OtError("%s: only int8 outputs (y_zero_point int8) have a CUDA handler" % node.name)
+    a8, azd = _as_s8(a, azd, azh)
+    b8, bzd = _as_s8(b, bzd, bzh)
+    wt = _kmajor_weight(wd, node.input[3], b8) if b.dtype == torch.int8 else K.cast(K.transpose(K.cast(b8, torch.int32), [1, 0]), torch.int8)
+    a2 = a8.reshape(-1, a8.shape[-1]).contiguous()
+    out = K.qlinear_matmul(a2, a_scale, azd, wt, b_scale, bzd, y_scale, int(yzh.reshape(-1)[0]))
+    _meta(wd)[node.output[0]] = ("q", out)
+    return out.reshape(tuple(a.shape[:-1]) + (wt.shape[0],))
+
+
+def _axis_view(t: torch.Tensor, rank: int, axis: int) -> torch.Tensor:
+    """A per-axis 1-D scale / zero point as a broadcastable tensor of `rank` dims (ONNX QuantizeLinear `axis`)."""
+    if t.numel() == 1 or t.dim() != 1:
+        return t
+    shape = [1] * rank
+    shape[axis if axis >= 0 else rank + axis] = t.numel()
+    return t.reshape(shape)
+
+
+def _scale_kind(s: torch.Tensor, x: torch.Tensor) -> str:
+    """How a broadcastable scale varies over x: 'scalar', 'row' (one value per row of the last axis) or 'col' (along the last axis)."""
+    if s.numel() == 1:
+        return "scalar"
+    if s.dim() == x.dim() and s.shape[-1] == 1 and s.numel() == x.numel() // x.shape[-1]:
+        return "row"
+    if s.dim() == x.dim() and s.numel() == x.shape[-1] and s.shape[-1] == x.shape[-1]:
+        return "col"
+    if s.dim() == x.dim() and s.shape[-1] == 1:
+        return "rowb"        # per row of one inner axis, broadcast over the others (e.g. (1,T,1) on [B,T,d])
+    return "other"
 
 
 def _h_quantize_linear(node, ins, wd):
-    """ONNX QuantizeLinear(x, scale, zero_point=0): saturate(round(x / scale)) -> int8 (dialect B)."""
-    x, s = ins[0], ins[1]
-    q = K.clip(K.unary("Round", K.binary("Div", x, s)), -128.0, 127.0)
-    out = K.cast(q, torch.int8)
+    """ONNX QuantizeLinear(x, y_scale, y_zero_point, axis=1): saturate(rint(x / y_scale) + y_zero_point); the result type is the zero
+    point's (uint8 when it is omitted).  Dialect B: Brevitas QuantIdentity exports, SURVEY.md App. C."""
+    x, s = ins[0], _axis_view(ins[1], ins[0].dim(), int(node.attr("axis", 1)))
+    zpd, zph = _zero_point(node, 2, ins, wd)
+    unsigned = (len(ins) < 3 or ins[2] is None) or ins[2].dtype == torch.uint8
+    q = K.unary("Round", K.binary("Div", x, s))
+    if zpd is not None:
+        q = K.binary("Add", q, K.cast(_axis_view(zpd, x.dim(), int(node.attr("axis", 1))), torch.float32, numeric_u8=True))
+    lo, hi = (0.0, 255.0) if unsigned else (-128.0, 127.0)
+    out = K.cast(K.clip(q, lo, hi), torch.uint8 if unsigned else torch.int8, numeric_u8=True)
     _meta(wd)[node.output[0]] = ("q", out)
     return out
 
 
 def _h_dequantize_linear(node, ins, wd):
-    x, s = ins[0], ins[1]
-    xf = K.cast(x, torch.float32) if x.dtype != torch.float32 else x
+    """ONNX DequantizeLinear(x, x_scale, x_zero_point, axis=1): (x - x_zero_point) * x_scale in fp32."""
+    x = ins[0]
+    axis = int(node.attr("axis", 1))
+    s = _axis_view(ins[1], x.dim(), axis)
+    zpd, zph = _zero_point(node, 2, ins, wd)
+    xf = K.cast(x, torch.float32, numeric_u8=True) if x.dtype != torch.float32 else x
+    if zpd is not None:
+        xf = K.binary("Sub", xf, K.cast(_axis_view(zpd, x.dim(), axis), torch.float32, numeric_u8=True))
     out = K.binary("Mul", xf, s)
-    if x.dtype == torch.int8 and s.dim() >= 1 and s.shape[-1] == 1 and s.numel() == x.numel() // x.shape[-1]:
-        _meta(wd)[node.output[0]] = ("qs", x, s.reshape(-1).contiguous())
+    if x.dtype == torch.int8 and zpd is None and x.dim() >= 2:
+        # int8 provenance for the tensor-core MatMul: ("dq", integer tensor, scale, how the scale varies).  A per-tensor scale serves
+        # as a per-row scale of an activation or a per-column scale of a weight.
+        kind = _scale_kind(s, x)
+        if kind == "rowb":       # e.g. (1,T,1) on [B,T,d]: materialise one scale per row
+            s, kind = s.expand(tuple(x.shape[:-1]) + (1,)), "row"
+        if kind in ("scalar", "row", "col"):
+            _meta(wd)[node.output[0]] = ("dq", x, s.reshape(-1).contiguous(), kind)
     return out
 
 
@@ -269,7 +408,7 @@ HANDLERS = {
     "Add": _h_binary("Add"), "Sub": _h_binary("Sub"), "Mul": _h_binary("Mul"), "Div": _h_binary("Div"),
     "Clip": _h_clip, "ReduceMax": _h_reduce("ReduceMax"), "ReduceMean": _h_reduce("ReduceMean"), "Softmax": _h_softmax,
     "Where": _h_where, "Equal": _h_equal, "Cast": _h_cast, "Transpose": _h_transpose, "Reshape": _h_reshape,
-    "Unsqueeze": _h_unsqueeze, "MatMul": _h_matmul, "MatMulInteger": _h_matmul_integer,
+    "Unsqueeze": _h_unsqueeze, "MatMul": _h_matmul, "MatMulInteger": _h_matmul_integer, "QLinearMatMul": _h_qlinear_matmul,
     "QuantizeLinear": _h_quantize_linear, "DequantizeLinear": _h_dequantize_linear,
     "Shape": _h_shape, "Gather": _h_gather, "ReduceProd": _h_reduce_prod,
     "Identity": lambda node, ins, wd: ins[0],          # raw exports alias shared initializers (deduplicated biases) this way
@@ -436,7 +575,11 @@ def inference(main_graph, weight_dict, module, inject_parameters=None):
 def get_weight_dict(module_path):
     """onnx_optimized_inference.py:273-280: (graph, {initializer name: tensor})."""
     graph = _as_graph(module_path)
-    return graph, {i.name: _to_device(i.array) for i in graph.initializer}
+    weight_dict = {i.name: _to_device(i.array) for i in graph.initializer}
+    # small initializers (Reshape shapes, Clip bounds, Where / Equal scalars, zero points, y_scale ...) also stay on the host: the
+    # handlers read them from this side table instead of synchronising the stream once per node
+    weight_dict[HOST_KEY] = {i.name: np.array(i.array) for i in graph.initializer if np.asarray(i.array).size <= 64}
+    return graph, weight_dict
 
 
 def prepare_inference(module_path, module_input_values):
@@ -446,6 +589,7 @@ def prepare_inference(module_path, module_input_values):
     for v in graph.input:
         if v.name not in init_names:
             weight_dict[v.name] = _to_device(module_input_values[v.name])
+            weight_dict[HOST_KEY].pop(v.name, None)
     return weight_dict, graph
 
 
@@ -453,10 +597,11 @@ def run_module(module, input_values, module_filepath, module_weight_dict, module
     """onnx_optimized_inference.py:297-304."""
     for input_name in list(input_values.keys()):
         module_weight_dict[input_name] = _to_device(input_values[input_name])
+        module_weight_dict.get(HOST_KEY, {}).pop(input_name, None)     # an overwritten initializer is no longer a known constant
     module_weight_dict.pop(META_KEY, None)
     return inference(module_graph, module_weight_dict, module, inject_parameters)
 
 
 def to_numpy(tensors: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
     """Convenience for callers that index the reference's numpy outputs."""
-    return {k: v.detach().cpu().numpy() for k, v in tensors.items() if isinstance(v, torch.Tensor)}
+    return {k: v.detach().cpu().numpy() for k, v in tensors.items() if isinstance(v, torch.Tensor) and k not in (META_KEY, HOST_KEY)}

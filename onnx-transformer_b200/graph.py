@@ -376,3 +376,63 @@ def _rename_output(g: Graph, old: str, new: str) -> None:
         n.output = [new if o == old else o for o in n.output]
         n.input = [new if i == old else i for i in n.input]
     g.value_info = [v for v in g.value_info if v.name != old]
+
+
+# ---------------------------------------------------------------------------------------------- dialect B (Brevitas QCDQ)
+def build_qcdq_block_graph(w1: np.ndarray, w2: np.ndarray, wk: np.ndarray, n_tokens: int, bit_width: int = 8, seed: int = 0) -> Graph:
+    """A dialect-B ("Brevitas QCDQ") block in the shape `export_onnx_qcdq` gives the reference's
+    quantized_position_feed_forward.py:23-41 and the score product of quantized_attention.py:52-58: every matmul operand --
+    weights included -- passes `QuantizeLinear(x, scale, zp=0:int8, axis) -> Clip(-2^(b-1), 2^(b-1)-1) [b < 8] -> DequantizeLinear`
+    and the product is a float `MatMul`:
+
+        x [1,T,d] --qcdq(per token)--> MatMul_0( . , qcdq(W1 [d,f], per column)) -> Relu -> qcdq(per token)
+                  --> MatMul_1( . , qcdq(W2 [f,d], per column)) = y [1,T,d]
+        q = qcdq(y, per token) ; k = Transpose(qcdq(MatMul_2(qcdq(x), qcdq(Wk)), per token), (0,2,1)) ; MatMul_3(q, k) = scores [1,T,T]
+
+    Weights are bias-free `nn.Parameter(d_in, d_out)` used as `x @ W` (quantized_attention.py:27-30); scales are static (learned in
+    the reference; here abs-max statistics of seeded activations) with the per-token shape (1,T,1) / per-channel shape (1,d_out) of
+    quantized_attention.py:32-45.  The Transpose sits between K's de-quantizer and the score MatMul, which is the case the
+    reference's `transposed_axes` handles (inject_utils/layers.py:176-181).  Node / tensor names follow the cleanup convention
+    (`<OpType>_<k>`, `<node>_out0`, `global_in`, `global_out`)."""
+    d, f = w1.shape
+    assert w2.shape == (f, d) and wk.shape == (d, d)
+    b = _Builder("qcdq_block", "encoder")
+    g = b.g
+    g.input = [ValueInfo("global_in", (1, n_tokens, d), "float32")]
+    qmax = float(2 ** (bit_width - 1))
+    rng = np.random.default_rng(seed)
+    zp = np.zeros((), dtype=np.int8)
+
+    def qcdq(x: str, scale: np.ndarray, axis: int) -> str:
+        ql = b.op("QuantizeLinear", [x], [Attribute("axis", i=axis)], consts={1: scale.astype(np.float32), 2: zp})
+        if bit_width < 8:
+            ql = b.op("Clip", [ql], consts={1: np.array(-2 ** (bit_width - 1), dtype=np.int8), 2: np.array(2 ** (bit_width - 1) - 1, dtype=np.int8)})
+        return b.op("DequantizeLinear", [ql], [Attribute("axis", i=axis)], consts={1: scale.astype(np.float32), 2: zp})
+
+    def act_scale(cal: np.ndarray) -> np.ndarray:
+        # static per-token scale = threshold / 2^(b-1); the threshold comes from abs-max statistics of a seeded calibration pass
+        # (Brevitas learns it from percentile statistics), jittered so that some run-time values saturate
+        return (np.maximum(np.abs(cal).reshape(n_tokens, -1).max(axis=1), 1e-5) * rng.uniform(0.7, 1.1, size=n_tokens) / qmax).astype(np.float32)
+
+    def weight_q(w: np.ndarray, name: str) -> str:
+        wname = b.init(name, w.astype(np.float32))
+        s = (np.maximum(np.abs(w).max(axis=0), 1e-5) / qmax).astype(np.float32)          # per output channel (column of [d_in, d_out])
+        return qcdq(wname, s, 1)
+
+    x_cal = rng.normal(size=(1, n_tokens, d)).astype(np.float32)
+    h_cal = np.maximum(x_cal @ w1, 0)
+    y_cal = h_cal @ w2
+    k_cal = x_cal @ wk
+    xq = qcdq("global_in", act_scale(x_cal), 1)
+    h = b.op("MatMul", [xq, weight_q(w1, "weights_1")], role={"kind": "matmul", "role": "ffn1"})
+    h = b.op("Relu", [h])
+    hq = qcdq(h, act_scale(h_cal), 1)
+    y = b.op("MatMul", [hq, weight_q(w2, "weights_2")], role={"kind": "matmul", "role": "ffn2"})
+    yq = qcdq(y, act_scale(y_cal), 1)
+    kx = b.op("MatMul", [xq, weight_q(wk, "weights_key")], role={"kind": "matmul", "role": "k"})
+    kq = qcdq(kx, act_scale(k_cal), 1)
+    kt = b.op("Transpose", [kq], [Attribute("perm", ints=[0, 2, 1])])
+    out = b.op("MatMul", [yq, kt], role={"kind": "matmul", "role": "qk"})
+    _rename_output(g, out, "global_out")
+    g.output = [ValueInfo("global_out", (1, n_tokens, n_tokens), "float32")]
+    return g

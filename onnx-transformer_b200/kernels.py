@@ -11,8 +11,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (FAULT_ACC_BITFLIP, FAULT_INPUT, FAULT_NONE, FAULT_RANDOM, FAULT_RANDOM_BITFLIP, FAULT_WEIGHT,  # noqa: F401
-                   OUT_F32, OUT_I32, OUT_Q8, OtError, OtFault)
+from ._lib import (FAULT_ACC_BITFLIP, FAULT_INPUT, FAULT_NONE, FAULT_OUT_Q8_BITFLIP, FAULT_RANDOM, FAULT_RANDOM_BITFLIP,  # noqa: F401
+                   FAULT_WEIGHT, OUT_F32, OUT_I32, OUT_Q8, OtError, OtFault)
 
 OPERAND_Q, OPERAND_K, OPERAND_P, OPERAND_V, OPERAND_SCORES, OPERAND_CTX = range(6)
 UNARY = {"Abs": 0, "Relu": 1, "Sqrt": 2, "Round": 3, "Neg": 4, "Exp": 5, "Identity": 6}
@@ -95,8 +95,9 @@ def linear_w8a8(a_q: torch.Tensor, w_q: torch.Tensor, *, row_scale=None, col_sca
         out_scale = torch.empty((M, N // quant_group), dtype=torch.float32, device=dev)
     if mf is not None:
         faults_dev, unit_dev, rows_per_unit = mf
-        assert not w4 and fault is None
-        rc = lib.ot_linear_w8a8_mf(_ptr(a_q), a_q.stride(0), _ptr(w_q), w_q.stride(0), M, N, K, _ptr(row_scale), _ptr(col_scale), _ptr(bias),
+        assert fault is None
+        fn_mf = lib.ot_linear_w4a8_mf if w4 else lib.ot_linear_w8a8_mf
+        rc = fn_mf(_ptr(a_q), a_q.stride(0), _ptr(w_q), w_q.stride(0), M, N, K, _ptr(row_scale), _ptr(col_scale), _ptr(bias),
                                    _ptr(residual), residual.stride(0) if residual is not None else 0, 1 if relu else 0, out_kind, _ptr(out),
                                    out.stride(0), _ptr(out_scale), int(quant_group), _ptr(faults_dev), _ptr(unit_dev), int(rows_per_unit), _stream())
         _lib.check(rc, "ot_linear_w8a8_mf")
@@ -107,6 +108,67 @@ def linear_w8a8(a_q: torch.Tensor, w_q: torch.Tensor, *, row_scale=None, col_sca
             1 if relu else 0, out_kind, _ptr(out), out.stride(0), _ptr(out_scale), int(quant_group), _fault_ref(fault), _stream())
     _lib.check(rc, "ot_linear_w4a8" if w4 else "ot_linear_w8a8")
     return (out, out_scale) if out_kind == OUT_Q8 else out
+
+
+def rowsum_i8(x: torch.Tensor) -> torch.Tensor:
+    """sum over the last axis of an int8 matrix -> int32 [rows] (operand sums of the zero-point correction)."""
+    _req(x, torch.int8, "x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty((x.shape[0],), dtype=torch.int32, device=x.device)
+    _lib.check(_lib.load().ot_rowsum_i8(_ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(out), _stream()), "ot_rowsum_i8")
+    return out
+
+
+def _zp_vec(zp, n: int, device) -> Optional[torch.Tensor]:
+    """Zero point (None, scalar or [n] tensor of any integer type) -> int32 [n] on the device, or None when identically zero is
+    KNOWN without a device read (None)."""
+    if zp is None:
+        return None
+    z = zp.to(device=device, dtype=torch.int32).reshape(-1)
+    return z.expand(n).contiguous() if z.numel() == 1 else z.contiguous()
+
+
+def matmul_integer(a_q: torch.Tensor, w_q: torch.Tensor, a_zp=None, b_zp=None, fault: Optional[OtFault] = None, out=None):
+    """ONNX MatMulInteger on K-major operands: a_q int8 [M,K], w_q int8 [N,K] (= B transposed); a_zp per row / scalar, b_zp per
+    column / scalar (int tensors, None = 0).  The zero-point correction runs in the GEMM epilogue (ot_matmul_integer)."""
+    lib = _lib.load()
+    _req(a_q, torch.int8, "a_q")
+    _req(w_q, torch.int8, "w_q")
+    M, K = a_q.shape
+    N = w_q.shape[0]
+    assert w_q.shape[1] == K and a_q.stride(1) == 1 and w_q.stride(1) == 1
+    az, bz = _zp_vec(a_zp, M, a_q.device), _zp_vec(b_zp, N, a_q.device)
+    rs = rowsum_i8(a_q) if bz is not None else None
+    cs = rowsum_i8(w_q) if az is not None else None
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.int32, device=a_q.device)
+    rc = lib.ot_matmul_integer(_ptr(a_q), a_q.stride(0), _ptr(w_q), w_q.stride(0), M, N, K, _ptr(az), _ptr(bz), _ptr(rs), _ptr(cs), _ptr(out),
+                               out.stride(0), _fault_ref(fault), _stream())
+    _lib.check(rc, "ot_matmul_integer")
+    return out
+
+
+def qlinear_matmul(a_q, a_scale, a_zp, w_q, b_scale, b_zp, y_scale: float, y_zp: int, out=None):
+    """ONNX QLinearMatMul on K-major operands (w_q = B transposed, [N,K]); a_scale fp32 scalar / [M], b_scale scalar / [N]."""
+    lib = _lib.load()
+    _req(a_q, torch.int8, "a_q")
+    _req(w_q, torch.int8, "w_q")
+    M, K = a_q.shape
+    N = w_q.shape[0]
+    dev = a_q.device
+    sa = a_scale.to(device=dev, dtype=torch.float32).reshape(-1)
+    sa = sa.expand(M).contiguous() if sa.numel() == 1 else sa.contiguous()
+    sb = b_scale.to(device=dev, dtype=torch.float32).reshape(-1)
+    sb = sb.expand(N).contiguous() if sb.numel() == 1 else sb.contiguous()
+    az, bz = _zp_vec(a_zp, M, dev), _zp_vec(b_zp, N, dev)
+    rs = rowsum_i8(a_q) if bz is not None else None
+    cs = rowsum_i8(w_q) if az is not None else None
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.int8, device=dev)
+    rc = lib.ot_qlinear_matmul(_ptr(a_q), a_q.stride(0), _ptr(w_q), w_q.stride(0), M, N, K, _ptr(sa), _ptr(sb), _ptr(az), _ptr(bz), _ptr(rs), _ptr(cs),
+                               float(y_scale), int(y_zp), _ptr(out), out.stride(0), _stream())
+    _lib.check(rc, "ot_qlinear_matmul")
+    return out
 
 
 def ln_linear_w8a8(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, w_q: torch.Tensor, *, eps: float = 1e-6, col_scale=None,
@@ -418,10 +480,12 @@ def equal_scalar_i64(x: torch.Tensor, scalar: int):
     return out
 
 
-def cast(x: torch.Tensor, dtype: torch.dtype):
+def cast(x: torch.Tensor, dtype: torch.dtype, numeric_u8: bool = False):
+    """ONNX Cast.  torch.uint8 as a destination means `bool` (0/1) unless numeric_u8 (QuantizeLinear's uint8 tensors)."""
     x = x.contiguous()
     out = torch.empty(x.shape, dtype=dtype, device=x.device)
-    rc = _lib.load().ot_cast(CAST_KIND[x.dtype], _ptr(x), CAST_KIND[dtype], _ptr(out), x.numel(), _stream())
+    dk = 5 if (numeric_u8 and dtype == torch.uint8) else CAST_KIND[dtype]
+    rc = _lib.load().ot_cast(CAST_KIND[x.dtype], _ptr(x), dk, _ptr(out), x.numel(), _stream())
     _lib.check(rc, "ot_cast")
     return out
 

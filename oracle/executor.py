@@ -9,6 +9,10 @@ run_module) and inject_utils/layers.py:70-142 (int_bit_flip, perturb_quantizer).
 versions unpinned: SURVEY.md 8c) is restated per op from the ONNX opset-13 operator specification: fp32 IEEE
 arithmetic, Round = half-to-even, Softmax over `axis`, MatMul = fp32 matrix product.
 
+Dialect B (Brevitas QCDQ; inject_operations.py) adds the ONNX-spec operators QuantizeLinear, DequantizeLinear, Clip on integer
+tensors, MatMulInteger and QLinearMatMul -- restated from the ONNX operator specification only: no reference artefact exists for
+them: PARITY UNPINNED for these five handlers.
+
 mode = "ref-float": every MatMul is an fp32 product of the de-quantized operands (the reference as is).
 mode = "int-exact": a MatMul whose operands are Round -> Mul(scale) [-> Transpose] chains is evaluated as the exact
 integer contraction followed by fl(fl(float(acc)*s_row)*s_col) (the factorisation the CUDA GEMM implements).
@@ -59,6 +63,27 @@ def _attr(node, name, default=None):
     return default
 
 
+def _axis_view(t: np.ndarray, rank: int, axis: int) -> np.ndarray:
+    """A per-axis 1-D scale / zero point broadcast along `axis` (ONNX QuantizeLinear / DequantizeLinear)."""
+    if t.size == 1 or t.ndim != 1:
+        return t
+    shape = [1] * rank
+    shape[axis if axis >= 0 else rank + axis] = t.size
+    return t.reshape(shape)
+
+
+def _scale_kind(s: np.ndarray, x: np.ndarray) -> str:
+    if s.size == 1:
+        return "scalar"
+    if s.ndim == x.ndim and s.shape[-1] == 1 and s.size == x.size // x.shape[-1]:
+        return "row"
+    if s.ndim == x.ndim and s.size == x.shape[-1] and s.shape[-1] == x.shape[-1]:
+        return "col"
+    if s.ndim == x.ndim and s.shape[-1] == 1:
+        return "rowb"
+    return "other"
+
+
 def run_node(node, ins: List[Optional[np.ndarray]], prov: Optional[dict] = None, mode: str = "ref-float") -> np.ndarray:
     """ONNX opset-13 semantics of one node on numpy arrays.  `prov` tracks int8 provenance for int-exact MatMuls."""
     op = node.op_type
@@ -82,6 +107,13 @@ def run_node(node, ins: List[Optional[np.ndarray]], prov: Optional[dict] = None,
                 src = prov.get(qn)
                 if src is not None and src[0] == "q" and s.ndim >= 1 and s.shape[-1] == 1 and s.size == src[1].size // src[1].shape[-1]:
                     prov[node.output[0]] = ("qs", src[1], s.reshape(-1))
+        return out
+    if op == "Clip" and x.dtype in (np.int8, np.uint8):          # dialect B: Clip on the integer tensor (bit_width < 8)
+        info = np.iinfo(x.dtype)
+        lo = int(ins[1]) if len(ins) > 1 and ins[1] is not None else info.min
+        hi = int(ins[2]) if len(ins) > 2 and ins[2] is not None else info.max
+        out = np.clip(x.astype(np.int32), lo, hi).astype(x.dtype)
+        prov[node.output[0]] = ("q", out)
         return out
     if op == "Clip":
         lo = F32(ins[1]) if len(ins) > 1 and ins[1] is not None else F32(-FLOAT_MAX)
@@ -136,9 +168,68 @@ def run_node(node, ins: List[Optional[np.ndarray]], prov: Optional[dict] = None,
         return np.take(x, np.asarray(ins[1], dtype=np.int64), axis=int(_attr(node, "axis", 0)))
     if op == "ReduceProd":
         return np.prod(x, axis=None if _attr(node, "axes") is None else tuple(_attr(node, "axes")), keepdims=bool(_attr(node, "keepdims", 1)))
+    if op == "QuantizeLinear":
+        # ONNX opset 13: saturate(round_half_even(x / y_scale) + y_zero_point); output type = zero point's (uint8 if omitted)
+        axis = int(_attr(node, "axis", 1))
+        s = _axis_view(np.asarray(ins[1], dtype=F32), x.ndim, axis)
+        zp = ins[2] if len(ins) > 2 and ins[2] is not None else None
+        dt = zp.dtype if zp is not None else np.dtype(np.uint8)
+        q = np.rint((x / s).astype(F32)).astype(F32)
+        if zp is not None and np.any(zp):
+            q = (q + _axis_view(np.asarray(zp), x.ndim, axis).astype(F32)).astype(F32)
+        info = np.iinfo(dt)
+        out = np.clip(q, info.min, info.max).astype(dt)
+        prov[node.output[0]] = ("q", out)
+        return out
+    if op == "DequantizeLinear":
+        # (x - x_zero_point) * x_scale
+        axis = int(_attr(node, "axis", 1))
+        s = _axis_view(np.asarray(ins[1], dtype=F32), x.ndim, axis)
+        zp = ins[2] if len(ins) > 2 and ins[2] is not None else None
+        xf = x.astype(F32)
+        has_zp = zp is not None and np.any(zp)
+        if has_zp:
+            xf = (xf - _axis_view(np.asarray(zp), x.ndim, axis).astype(F32)).astype(F32)
+        out = (xf * s).astype(F32)
+        if x.dtype == np.int8 and not has_zp and x.ndim >= 2:
+            kind = _scale_kind(s, x)
+            if kind == "rowb":
+                s, kind = np.broadcast_to(s, x.shape[:-1] + (1,)), "row"
+            if kind in ("scalar", "row", "col"):
+                prov[node.output[0]] = ("dq", x, np.ascontiguousarray(s).reshape(-1), kind)
+        return out
+    if op == "MatMulInteger":
+        # sum_k (A - a_zp)(B - b_zp) in int32 (wrap-around); a_zp scalar or per row, b_zp scalar or per column
+        a, b = ins[0].astype(np.int64), ins[1].astype(np.int64)
+        if len(ins) > 2 and ins[2] is not None:
+            az = np.asarray(ins[2]).astype(np.int64)
+            a = a - (az.reshape(-1, 1) if az.size > 1 else az)
+        if len(ins) > 3 and ins[3] is not None:
+            bz = np.asarray(ins[3]).astype(np.int64)
+            b = b - (bz.reshape(1, -1) if bz.size > 1 else bz)
+        return np.matmul(a, b).astype(np.int32)
+    if op == "QLinearMatMul":
+        a, a_s, a_z, b, b_s, b_z, y_s, y_z = (list(ins) + [None] * 8)[:8]
+        ai = a.astype(np.int64) - (0 if a_z is None else (np.asarray(a_z).astype(np.int64).reshape(-1, 1) if np.asarray(a_z).size > 1 else np.asarray(a_z).astype(np.int64)))
+        bi = b.astype(np.int64) - (0 if b_z is None else (np.asarray(b_z).astype(np.int64).reshape(1, -1) if np.asarray(b_z).size > 1 else np.asarray(b_z).astype(np.int64)))
+        acc = np.matmul(ai, bi).astype(np.int32)
+        sa = np.asarray(a_s, dtype=F32).reshape(-1, 1) if np.asarray(a_s).size > 1 else F32(a_s)
+        sb = np.asarray(b_s, dtype=F32).reshape(1, -1) if np.asarray(b_s).size > 1 else F32(b_s)
+        y = ((acc.astype(F32) * sa).astype(F32) * sb).astype(F32)
+        yz = np.zeros((), np.int8) if y_z is None else np.asarray(y_z)
+        q = (np.rint((y / F32(y_s)).astype(F32)) + yz.astype(F32)).astype(F32)
+        info = np.iinfo(yz.dtype)
+        return np.clip(q, info.min, info.max).astype(yz.dtype)
     if op == "MatMul":
         a, b = ins[0], ins[1]
         pa, pb = prov.get(node.input[0]), prov.get(node.input[1])
+        if mode == "int-exact" and pa is not None and pb is not None and pa[0] == "dq" and pb[0] == "dq" and b.ndim == 2 and \
+                pa[3] in ("row", "scalar") and pb[3] in ("col", "scalar") and pa[1].shape[-1] % 16 == 0 and pb[1].shape[1] % 32 == 0:
+            aq = pa[1].reshape(-1, pa[1].shape[-1])
+            acc = ox.int_matmul(aq, np.ascontiguousarray(pb[1].T))
+            sa = np.broadcast_to(pa[2], (aq.shape[0],)) if pa[2].size == 1 else pa[2]
+            sw = np.broadcast_to(pb[2], (pb[1].shape[1],)) if pb[2].size == 1 else pb[2]
+            return ox.linear_epilogue(acc, sa, sw).reshape(a.shape[:-1] + (pb[1].shape[1],))
         if mode == "int-exact" and pa is not None and pb is not None and pa[0] == "qs" and pb[0] == "qsT" and b.ndim == 2:
             aq = pa[1].reshape(-1, pa[1].shape[-1]).astype(np.int8)
             acc = ox.int_matmul(aq, pb[1].astype(np.int8))
