@@ -287,13 +287,8 @@ __device__ __forceinline__ void chunk_values(const GemmArgs& g, const FaultCtx& 
   }
 }
 
-// RowQuant of a chunk: quant_fast_bits (ot_rowmath.cuh) on the 16 elements, branch-free; the (rare) exact fallback is taken once per
-// chunk, out of line.
-template <int CW>
-__device__ __noinline__ void quant_exact_array(const float* y, float s, float* n) {
-  for (int j = 0; j < CW; ++j) n[j] = rintf(__fdiv_rn(y[j], s));
-}
-
+// RowQuant of a chunk: quant_fast_bits (ot_rowmath.cuh) on the 16 elements, branch-free; the (rare) exact redo touches only the
+// elements that need the IEEE division (quant_redo_chunk).
 // What a pass does with the fp32 values of a chunk.
 enum { PASS_STORE_F32 = 0, PASS_AMAX = 1, PASS_STORE_Q8 = 2, PASS_STORE_QLINEAR = 3 };
 struct PassState {
@@ -342,23 +337,11 @@ __device__ __forceinline__ void consume_chunk(const GemmArgs& g, const FaultCtx&
       bool slow = false;
 #pragma unroll
       for (int j = 0; j < kCW; ++j) tb[j] = quant_fast_bits(y[j], st.s, st.s_rcp, slow);
+      if (slow) quant_redo_chunk<kCW>(y, st.s, st.s_rcp, false, tb);   // rare: only the flagged elements take the true IEEE division
       uint32_t packed[kCW / 4];
 #pragma unroll
       for (int j = 0; j < kCW / 4; ++j)
         packed[j] = __byte_perm(__byte_perm(tb[4 * j], tb[4 * j + 1], 0x0040), __byte_perm(tb[4 * j + 2], tb[4 * j + 3], 0x0040), 0x5410);
-      if (slow) {                            // ~2^-13 of the chunks: redo the chunk with true IEEE division
-        float yy[kCW], nn[kCW];
-#pragma unroll
-        for (int j = 0; j < kCW; ++j) yy[j] = y[j];
-        quant_exact_array<kCW>(yy, st.s, nn);
-#pragma unroll
-        for (int j = 0; j < kCW / 4; ++j) {
-          uint32_t w = 0;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) w |= (static_cast<uint32_t>(__float2int_rn(nn[4 * j + b])) & 0xFFu) << (8 * b);
-          packed[j] = w;
-        }
-      }
       if (f.mode == OT_FAULT_OUT_Q8_BITFLIP && row == f.row && f.col >= col && f.col < col + kCW) {
         const int e = f.col - col;
 #pragma unroll
@@ -953,6 +936,10 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
   }
 }
 
+int launch_gemm_stream(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K, const float* row_scale,
+                       const float* col_scale, const float* bias, const float* residual, int64_t ldr, int relu, int out_kind, void* out,
+                       int64_t ldo, float* out_scale, int quant_group, cudaStream_t stream);
+
 struct ZpArgs {
   const int32_t* a_zp = nullptr;
   const int32_t* b_zp = nullptr;
@@ -1017,6 +1004,14 @@ static int linear_common(bool w4, const int8_t* A, int64_t lda, const void* W, i
     g.mf_faults = mf_faults; g.mf_unit = mf_unit; g.mf_rows = mf_rows;
   }
   cudaStream_t s = as_stream(stream);
+  // encoder-size, fault-free problems: the persistent double-accumulator kernel (ot_gemm_stream.cu); same results bit for bit
+  const char* stream_env = getenv("OT_GEMM_STREAM");      // "0" routes everything through gemm_i8_kernel (A/B comparisons in the tests)
+  const bool stream_on = !(stream_env && atoi(stream_env) == 0);
+  if (stream_on && !w4 && fault == nullptr && mf_unit == nullptr && zp == nullptr && !getenv("OT_GEMM_TRACE")) {
+    const int rc = launch_gemm_stream(A, lda, reinterpret_cast<const int8_t*>(W), ldw, M, N, K, row_scale, col_scale, bias, residual, ldr, relu, out_kind,
+                                      out, ldo, out_scale, quant_group, s);
+    if (rc <= 0) return rc;
+  }
   return w4 ? dispatch_gemm<1>(g, quant_group, s) : dispatch_gemm<0>(g, quant_group, s);
 }
 

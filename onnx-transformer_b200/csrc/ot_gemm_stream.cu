@@ -1,0 +1,443 @@
+// Encoder-size int8 GEMM (M >= 2048 rows, fault-free): the PERSISTENT, warp-specialised variant of ot_gemm_i8.cu.
+//
+// Why a second kernel.  At M = 65,536 (cfg3) the one-tile-per-CTA kernel spends almost all of its time in the epilogue: K = 512 is
+// 16 MMAs (~1.4 us) per 128 x 256 tile while the requant epilogue is ~16 fp32 instructions per element (~2.2 us at full issue
+// rate), the tile's TMA loads, MMAs and epilogue run back to back, and the accumulator is read from TMEM twice around a
+// barrier.cluster (profiles/r1_ncu_gemm_enc_ffn1_q8_v3.txt: tensor pipe 5.5 % active).  Here
+//   * one CTA per SM loops over its share of the tiles; warp 0 = TMA producer (3-stage ring of A 128x128 B + W 256x128 B k-blocks),
+//     warp 1 = tcgen05.mma issuer, warps 2..17 = epilogue (4 per scheduler: one row x 64 columns per thread);
+//   * TWO accumulators (2 x 256 TMEM columns = the whole TMEM): the MMAs of tile i+1 run under the epilogue of tile i;
+//   * the requant epilogue computes y = fl(fl(float(acc)*sx)*sw)+b (ReLU) ONCE, writes it back over its accumulator columns with
+//     tcgen05.st (TMEM as the per-thread stash: 128 values per thread do not fit in registers without unrolling 4k instructions),
+//     and after the row maxima are known quantizes from that stash: no recomputation;
+//   * the CTAs that share a quant group (N/256 tiles of the same 128 rows: 2 for q|k|v groups of 512, 8 for the FFN hidden layer)
+//     form a cluster and exchange row maxima by st.async + mbarrier complete_tx (0.15 us vs 0.65 us for barrier.cluster, measured
+//     in ot_cdecoder.cu); nobody waits at a cluster barrier in the steady state.
+// Results are bit-identical to ot_gemm_i8.cu: same fp32 finish order; the quantization is rint(RN(y/s)) in both (a one-multiply fast
+// pass + the true division for the elements within 2^-15 of a rounding boundary here, see quant_fast2_bits).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include "ot_common.h"
+#include "ot_ptx.cuh"
+#include "ot_rowmath.cuh"
+
+namespace ot {
+
+int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, bool swizzle128);
+
+constexpr int kSBM = 128, kSBN = 256, kSBK = 128, kSStages = 3;
+constexpr int kSEpiWarps = 16, kSEpiThreads = kSEpiWarps * 32, kSThreads = 64 + kSEpiThreads;
+constexpr int kSColsPerWarp = kSBN / (kSEpiWarps / 4);           // 64 columns per epilogue thread
+constexpr int kSA = kSBM * kSBK, kSB = kSBN * kSBK;             // bytes per stage
+constexpr int kSMaxCl = 8;
+constexpr int kSBarOff = kSStages * (kSA + kSB);                 // full[4] empty[4] tfull[2] tempty[2] xbar[2] + tmem slot
+constexpr int kSColOff = kSBarOff + 256;                         // float [16 warps][2 buffers][cs 64 | bias 64]
+constexpr int kSRowmaxOff = kSColOff + kSEpiWarps * 2 * 2 * kSColsPerWarp * 4;   // float rowmax[2][4*kSMaxCl][128]
+constexpr int kSSmem = kSRowmaxOff + 2 * 4 * kSMaxCl * 128 * 4 + 1024;
+
+struct StreamArgs {
+  int M, N, K;
+  const float* row_scale;
+  const float* col_scale;
+  const float* bias;
+  const float* residual;
+  int64_t ldr;
+  int relu;
+  void* out;
+  int64_t ldo;
+  float* out_scale;
+  int cluster_n;   // CTAs per quant group (Q8), 1 for fp32 output
+  unsigned long long* trace;   // profiling aid (OT_GEMM_STREAM_TRACE): CTA 0 stamps %globaltimer per tile and role
+};
+
+// trace layout: [tile li < 32][slot]: 0 epi tile start, 1 accumulator ready, 2 pass 1 done, 3 exchange done, 4 pass 2 done (epilogue warp 0);
+// 8 MMA: accumulator free, 9 MMA: all MMAs issued; 12 TMA: first k-block requested, 13 TMA: last k-block requested
+__device__ __forceinline__ void wtrace(const StreamArgs& g, uint32_t li, int e, int slot) {   // every epilogue warp of CTA 0, first 8 tiles
+  if (g.trace != nullptr && blockIdx.x == 0 && li < 8 && (threadIdx.x & 31) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.trace[512 + (li * 16 + e) * 8 + slot] = t;
+  }
+}
+__device__ __forceinline__ void strace(const StreamArgs& g, uint32_t li, int slot) {
+  if (g.trace != nullptr && blockIdx.x == 0 && li < 32) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.trace[li * 16 + slot] = t;
+  }
+}
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_async_f32(uint32_t addr, float v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)), "r"(mbar) : "memory");
+}
+
+template <bool Q8>
+__global__ void __launch_bounds__(kSThreads, 1)
+gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ StreamArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kSStages * kSA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSBarOff);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kSStages;
+  uint64_t* tfull_bar = bars + 2 * kSStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* xbar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
+  float* s_col = reinterpret_cast<float*>(smem + kSColOff);       // per-warp column parameters
+  float* rowmax = reinterpret_cast<float*>(smem + kSRowmaxOff);   // [xb][4*kSMaxCl][128]
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) / 32, 0);
+  const int lane = threadIdx.x & 31;
+  const int cn = g.cluster_n;
+  const uint32_t rank = cn > 1 ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / cn, n_clusters = gridDim.x / cn;
+  const int m_tiles = (g.M + kSBM - 1) / kSBM;
+  const int groups = (g.N / kSBN) / cn;
+  const int total = m_tiles * groups;
+  const int nkb = g.K / kSBK;
+
+  if (warp_idx == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp_idx == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < kSStages; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(smem_u32(&tfull_bar[b]), 1);
+        mbar_init(smem_u32(&tempty_bar[b]), kSEpiWarps);
+        mbar_init(smem_u32(&xbar[b]), 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  if (cn > 1) cluster_sync_all();   // every CTA of the cluster has initialised its barriers before anyone stores into it
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t cnt = 0, li = 0;
+      for (int it = cluster_id; it < total; it += n_clusters, ++li) {
+        const int m_tile = it / groups, n_tile = (it % groups) * cn + static_cast<int>(rank);
+        for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+          const uint32_t s = cnt % kSStages, ph = (cnt / kSStages) & 1u;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_arrive_expect_tx(fb, kSA + kSB);
+          tma_load_2d(smem_u32(sA + s * kSA), &tmap_a, fb, kb * kSBK, m_tile * kSBM);
+          tma_load_2d(smem_u32(sB + s * kSB), &tmap_b, fb, kb * kSBK, n_tile * kSBN);
+          if (kb == 0) strace(g, li, 12);
+        }
+        strace(g, li, 13);
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_i8(kSBM, kSBN);
+      uint32_t cnt = 0, li = 0;
+      for (int it = cluster_id; it < total; it += n_clusters, ++li) {
+        const uint32_t buf = li & 1u;
+        mbar_wait(smem_u32(&tempty_bar[buf]), ((li >> 1) & 1u) ^ 1u);     // the epilogue has drained this accumulator
+        tc_fence_after();
+        strace(g, li, 8);
+        const uint32_t d_tmem = tmem_base + buf * kSBN;
+        for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+          const uint32_t s = cnt % kSStages, ph = (cnt / kSStages) & 1u;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + s * kSA));
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sB + s * kSB));
+#pragma unroll
+          for (int k = 0; k < kSBK / 32; ++k)
+            mma_i8_ss(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          mma_commit(smem_u32(&empty_bar[s]));
+        }
+        mma_commit(smem_u32(&tfull_bar[buf]));
+        strace(g, li, 9);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    // 16 warps: warp e owns TMEM lanes [32*(warp_idx%4), +32) (hardware rule) = 32 rows, and column quarter cq = e/4 = 64 columns,
+    // as 4 chunks of 16.  Four warps per scheduler hide the TMEM / shared-memory latencies of each other; nothing in a tile needs a
+    // block barrier: the column parameters are staged per warp, the accumulator is handed back per warp.
+    const int e = warp_idx - 2;
+    const int quarter = warp_idx & 3;
+    const int cq = e >> 2;
+    const int row_in_tile = quarter * 32 + lane;
+    const bool has_bias = g.bias != nullptr, relu = g.relu != 0;
+    float* wcol = s_col + e * (2 * 2 * kSColsPerWarp);               // [buf][cs 64 | bias 64], private to this warp
+    uint32_t li = 0;
+    for (int it = cluster_id; it < total; it += n_clusters, ++li) {
+      const uint32_t buf = li & 1u, par = (li >> 1) & 1u;
+      const int m_tile = it / groups, grp = it % groups, n_tile = grp * cn + static_cast<int>(rank);
+      const int row = m_tile * kSBM + row_in_tile;
+      const bool row_ok = row < g.M;
+      const int col0 = n_tile * kSBN + cq * kSColsPerWarp;           // first of this warp's 64 columns
+      float* cs = wcol + buf * (2 * kSColsPerWarp);
+      float* bs = cs + kSColsPerWarp;
+      bool cols_bad;
+      {
+        const float c0 = g.col_scale ? __ldg(g.col_scale + col0 + lane) : 1.0f, c1 = g.col_scale ? __ldg(g.col_scale + col0 + 32 + lane) : 1.0f;
+        const float b0 = g.bias ? __ldg(g.bias + col0 + lane) : 0.0f, b1 = g.bias ? __ldg(g.bias + col0 + 32 + lane) : 0.0f;
+        cs[lane] = c0; cs[32 + lane] = c1; bs[lane] = b0; bs[32 + lane] = b1;
+        cols_bad = __any_sync(0xffffffffu, !(fabsf(c0) < 3.0e38f) || !(fabsf(c1) < 3.0e38f) || !(fabsf(b0) < 3.0e38f) || !(fabsf(b1) < 3.0e38f));
+        if (Q8 && cn > 1 && e == 0 && lane == 0) mbar_arrive_expect_tx(smem_u32(&xbar[buf]), static_cast<uint32_t>(cn) * 4u * 128u * 4u);
+        __syncwarp();
+      }
+      const float sx = (g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSBN + cq * kSColsPerWarp;
+
+      if (!Q8) {
+        // ---- fp32 output.  These GEMMs are HBM-bound on the fp32 residual + output: the residual of two 16-column chunks (128 B per
+        // thread, 64 KB per SM) is always in flight, requested before the accumulator is waited for.
+        const bool has_res = g.residual != nullptr && row_ok;
+        float* orow = reinterpret_cast<float*>(g.out) + static_cast<int64_t>(row) * g.ldo + col0;
+        const float4* rrow = reinterpret_cast<const float4*>(g.residual + static_cast<int64_t>(has_res ? row : 0) * g.ldr + col0);
+        float4 res[4][4];
+        uint32_t r[4][16];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[c][j] = __ldg(rrow + 4 * c + j);
+          }
+        mbar_wait(smem_u32(&tfull_bar[buf]), par);
+        tc_fence_after();
+        tmem_ld_32x16(taddr, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_wait_ld();
+          if (c + 1 < 4) tmem_ld_32x16(taddr + 16 * (c + 1), r[c + 1]);
+          if (c == 3) {
+            // the whole accumulator slice is in registers: the MMAs of the tile after next may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+          }
+          float y[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cs + 16 * c + 4 * j);
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + 16 * c + 4 * j);
+            const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float rv[4] = {res[c][j].x, res[c][j].y, res[c][j].z, res[c][j].w};
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              float v = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[c][4 * j + b])), sx), cv[b]);
+              const float vb = __fadd_rn(v, bv[b]);
+              v = has_bias ? vb : v;
+              const float vr = fmaxf(v, 0.0f);
+              v = relu ? vr : v;
+              y[4 * j + b] = has_res ? __fadd_rn(rv[b], v) : v;
+            }
+          }
+          if (c + 2 < 4 && has_res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[c + 2][j] = __ldg(rrow + 4 * (c + 2) + j);
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(orow + 16 * c)[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          }
+        }
+      } else {
+        if (e == 0 && lane == 0) strace(g, li, 0);
+        wtrace(g, li, e, 0);
+        mbar_wait(smem_u32(&tfull_bar[buf]), par);
+        tc_fence_after();
+        if (e == 0 && lane == 0) strace(g, li, 1);
+        wtrace(g, li, e, 1);
+        // ---- pass 1: y once, stashed over its own accumulator columns; row abs-max of this thread's 64 columns
+        float amax = 0.f;
+        {
+          uint32_t r[4][16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld_32x16(taddr + 16 * c, r[c]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 c4 = *reinterpret_cast<const float4*>(cs + 16 * c + 4 * j);
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + 16 * c + 4 * j);
+              const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                float v = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[c][4 * j + b])), sx), cv[b]);
+                const float vb = __fadd_rn(v, bv[b]);
+                v = has_bias ? vb : v;
+                const float vr = fmaxf(v, 0.0f);
+                v = relu ? vr : v;
+                amax = fmaxf(amax, fabsf(v));
+                r[c][4 * j + b] = __float_as_uint(v);
+              }
+            }
+            tmem_st_32x16(taddr + 16 * c, r[c]);
+          }
+        }
+        if (!row_ok) amax = 0.f;
+        if (e == 0 && lane == 0) strace(g, li, 2);
+        wtrace(g, li, e, 2);
+        // ---- exchange: this (CTA, column quarter)'s row maximum to every CTA of the quant group, data-flow synchronised
+        float* xrow = rowmax + (buf * 4 * kSMaxCl) * 128 + row_in_tile;
+        {
+          const uint32_t slot = smem_u32(xrow + (rank * 4 + cq) * 128);
+          const uint32_t xb = smem_u32(&xbar[buf]);
+          if (cn > 1) {
+            for (int peer = 0; peer < cn; ++peer) st_async_f32(mapa_shared(slot, peer), amax, mapa_shared(xb, peer));
+            mbar_wait(xb, par);
+          } else {
+            xrow[cq * 128] = amax;                   // a quant group of one tile: the four column quarters meet at a block barrier
+            asm volatile("bar.sync 1, %0;" ::"n"(kSEpiThreads) : "memory");
+          }
+        }
+        if (e == 0 && lane == 0) strace(g, li, 3);
+        wtrace(g, li, e, 3);
+        float rmax = 0.f;
+        for (int p = 0; p < 4 * cn; ++p) rmax = fmaxf(rmax, xrow[p * 128]);
+        const float s = __fdiv_rn(fmaxf(rmax, 1e-5f), 127.0f);
+        const float s_rcp = __frcp_rn(s);
+        if (row_ok && cq == 0 && rank == 0) g.out_scale[static_cast<int64_t>(row) * groups + grp] = s;
+        // rows whose inputs are not plain finite numbers take the exact division for every element (same results as ot_gemm_i8.cu)
+        const bool row_slow = !(rmax < 3.0e38f) || !(fabsf(sx) < 3.0e38f) || cols_bad;
+        // ---- pass 2: quantize from the stash
+        int8_t* orow = reinterpret_cast<int8_t*>(g.out) + static_cast<int64_t>(row) * g.ldo + col0;
+        {
+          tmem_wait_st();
+          uint32_t r[4][16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld_32x16(taddr + 16 * c, r[c]);
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));     // the stash is in registers: hand the accumulator back
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t tb[16];
+            float yv[16];
+            bool slow = row_slow;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              yv[j] = __uint_as_float(r[c][j]);
+              tb[j] = quant_fast2_bits(yv[j], s_rcp, slow);
+            }
+            if (slow) quant_redo_chunk2<16>(yv, s, s_rcp, row_slow, tb);    // rare: only the flagged elements take the division
+            uint32_t packed[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              packed[j] = __byte_perm(__byte_perm(tb[4 * j], tb[4 * j + 1], 0x0040), __byte_perm(tb[4 * j + 2], tb[4 * j + 3], 0x0040), 0x5410);
+            if (row_ok) *reinterpret_cast<uint4*>(orow + 16 * c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+        }
+        if (e == 0 && lane == 0) strace(g, li, 4);
+        wtrace(g, li, e, 4);
+        if (cn == 1) asm volatile("bar.sync 1, %0;" ::"n"(kSEpiThreads) : "memory");   // the rowmax slots are rewritten two tiles later, but the
+                                                                                          // block barrier above must not be overtaken by a fast warp
+      }
+    }
+  }
+
+  tc_fence_before();
+  if (cn > 1) cluster_sync_all();
+  else __syncthreads();
+  if (warp_idx == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Launch when the problem qualifies; returns 1 if it does not (caller falls back to gemm_i8_kernel), 0 on success, < 0 on error.
+int launch_gemm_stream(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K, const float* row_scale,
+                       const float* col_scale, const float* bias, const float* residual, int64_t ldr, int relu, int out_kind, void* out,
+                       int64_t ldo, float* out_scale, int quant_group, cudaStream_t stream) {
+  static const int min_m = getenv("OT_GEMM_STREAM_MIN_M") ? atoi(getenv("OT_GEMM_STREAM_MIN_M")) : 2048;
+  if (M < min_m || N % kSBN != 0 || K % kSBK != 0 || K < kSBK) return 1;
+  if (out_kind != OT_OUT_F32 && out_kind != OT_OUT_Q8) return 1;
+  int cn = 1;
+  if (out_kind == OT_OUT_Q8) {
+    if (residual != nullptr || quant_group % kSBN != 0 || quant_group / kSBN > kSMaxCl || N % quant_group != 0) return 1;
+    cn = quant_group / kSBN;
+    if ((cn & (cn - 1)) != 0) return 1;
+  }
+  CUtensorMap ta, tb;
+  int rc = get_tensor_map(&tb, W, N, K, ldw, kSBN, kSBK, true);
+  if (rc) return rc;
+  rc = get_tensor_map(&ta, A, M, K, lda, kSBM, kSBK, true);
+  if (rc) return rc;
+  StreamArgs g = {};
+  g.M = M; g.N = N; g.K = K;
+  g.row_scale = row_scale; g.col_scale = col_scale; g.bias = bias; g.residual = residual; g.ldr = ldr;
+  g.relu = relu; g.out = out; g.ldo = ldo; g.out_scale = out_scale; g.cluster_n = cn;
+  if (const char* tr = getenv("OT_GEMM_STREAM_TRACE")) g.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16));
+  auto kernel = out_kind == OT_OUT_Q8 ? gemm_stream_kernel<true> : gemm_stream_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  static int max_clusters[2][kSMaxCl + 1] = {};
+  const int ki = out_kind == OT_OUT_Q8 ? 1 : 0;
+  if (!attr_set[ki]) {
+    OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmem));
+    attr_set[ki] = true;
+  }
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int n_cl;
+  if (cn == 1) {
+    n_cl = sms;
+  } else {
+    if (max_clusters[ki][cn] == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>(sms / cn * cn));
+      cfg.blockDim = dim3(kSThreads);
+      cfg.dynamicSmemBytes = kSSmem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cn; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = sms / cn / 2 > 0 ? sms / cn / 2 : 1;
+      }
+      max_clusters[ki][cn] = n;
+    }
+    n_cl = max_clusters[ki][cn];
+  }
+  const int m_tiles = (M + kSBM - 1) / kSBM;
+  const int total = m_tiles * ((N / kSBN) / cn);
+  if (n_cl > total) n_cl = total;
+  OT_CHECK_CUDA(launch_kernel(kernel, dim3(static_cast<unsigned>(n_cl * cn)), dim3(kSThreads), kSSmem, stream, cn, ta, tb, g));
+  count_launch();
+  return OT_OK;
+}
+
+}  // namespace ot

@@ -76,6 +76,46 @@ __device__ __forceinline__ uint32_t quant_fast_bits(float y, float s, float r, b
   slow = slow || (fabsf(fabsf(q1 - n) - 0.5f) < 1.52587890625e-05f) || !(fabsf(q1) < 1024.0f);
   return __float_as_uint(t);
 }
+// The exact form of one element, out of line: rint(y / s) with the IEEE division, as the low byte of the result.
+static __device__ __noinline__ uint32_t quant_exact_bits(float y, float s) {
+  return static_cast<uint32_t>(__float2int_rn(rintf(__fdiv_rn(y, s))));
+}
+// Redo of a chunk whose fast pass raised `slow`: the test of quant_fast_bits is re-evaluated per element (same instructions, same
+// bits) and ONLY the elements that need it take the division.  A warp-chunk (512 elements) raises `slow` with probability ~1.5 %,
+// nearly always for a single element: the redo costs ~150 issue slots instead of 16 divisions per lane through local memory
+// (measured in ot_gemm_stream.cu: the old whole-chunk fallback made one warp in ~15 a 3-6 us straggler that the whole cluster then
+// waited for at the row-maximum exchange).
+template <int CW>
+__device__ __forceinline__ void quant_redo_chunk(const float (&y)[CW], float s, float r, bool all, uint32_t (&tb)[CW]) {
+#pragma unroll
+  for (int j = 0; j < CW; ++j) {
+    bool f = all;
+    (void)quant_fast_bits(y[j], s, r, f);
+    if (f) tb[j] = quant_exact_bits(y[j], s);
+  }
+}
+
+// Leaner fast pass for callers that have already established that y, s and r are plain finite numbers with |y / s| <= 127 + tiny
+// (the row's scale comes from the row's own maximum): q = y*r is within 2^-16 of y/s (r = RN(1/s): relative error 2^-24, the product
+// another 2^-24, |q| <= 127), so rint(q) == rint(RN(y/s)) unless q sits within 2^-15 of a half-integer -- exactly then `slow` is
+// raised and the element takes the true division (quant_redo_chunk2).  3 FP32 instructions fewer per element than quant_fast_bits.
+__device__ __forceinline__ uint32_t quant_fast2_bits(float y, float r, bool& slow) {
+  const float q = __fmul_rn(y, r);
+  const float t = __fadd_rn(q, 12582912.0f);
+  const float n = __fsub_rn(t, 12582912.0f);
+  slow = slow || (fabsf(fabsf(q - n) - 0.5f) < 3.0517578125e-05f);
+  return __float_as_uint(t);
+}
+template <int CW>
+__device__ __forceinline__ void quant_redo_chunk2(const float (&y)[CW], float s, float r, bool all, uint32_t (&tb)[CW]) {
+#pragma unroll
+  for (int j = 0; j < CW; ++j) {
+    bool f = all;
+    (void)quant_fast2_bits(y[j], r, f);
+    if (f) tb[j] = quant_exact_bits(y[j], s);
+  }
+}
+
 // pack4(quant_one(v.x, s), ...) of four values, same bits as the division form
 __device__ __forceinline__ uint32_t quant4_pack(float4 v, float s, float r) {
   bool slow = false;

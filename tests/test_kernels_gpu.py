@@ -68,6 +68,72 @@ def test_gemm_fused_requant_bit_exact(K, M, N, K_, group, relu):
     assert np.array_equal(q.cpu().numpy(), qr)
 
 
+@pytest.mark.parametrize("M,N,K_,group,relu,res", [(2100, 1536, 512, 512, False, False), (8192, 2048, 512, 2048, True, False), (3000, 512, 512, 0, False, True),
+                                                   (5000, 512, 2048, 0, False, True), (2048, 6144, 512, 512, False, False), (4096, 1024, 256, 256, True, False)])
+def test_gemm_stream_kernel_equals_tile_kernel_and_oracle(K, M, N, K_, group, relu, res):
+    """The persistent double-accumulator kernel (ot_gemm_stream.cu, M >= 2048) against the one-tile-per-CTA kernel bit for bit, and both
+    against the oracle on a row sample (ragged last tiles, clusters of 1 / 2 / 8, the 12-projection cross-K/V shape)."""
+    import os
+    rng = np.random.default_rng(31 + M + N)
+    a, w = rand_i8(rng, (M, K_)), rand_i8(rng, (N, K_))
+    sx = rng.uniform(1e-3, 5e-2, size=M).astype(np.float32)
+    sw = rng.uniform(1e-4, 1e-2, size=N).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    r = rng.normal(size=(M, N)).astype(np.float32) if res else None
+    ad, wd_, sxd, swd, bd, rd = dev(a), dev(w), dev(sx), dev(sw), dev(b), (dev(r) if res else None)
+
+    def run():
+        if group:
+            return K.linear_w8a8(ad, wd_, row_scale=sxd, col_scale=swd, bias=bd, relu=relu, out_kind=K.OUT_Q8, quant_group=group)
+        return (K.linear_w8a8(ad, wd_, row_scale=sxd, col_scale=swd, bias=bd, residual=rd, relu=relu, out_kind=K.OUT_F32),)
+    n0 = K._lib.launch_count()
+    new = run()
+    os.environ["OT_GEMM_STREAM"] = "0"
+    try:
+        old = run()
+    finally:
+        del os.environ["OT_GEMM_STREAM"]
+    assert K._lib.launch_count() == n0 + 2
+    for x, y in zip(new, old):
+        assert torch.equal(x, y)
+    rows = np.unique(np.concatenate([np.arange(0, 130), np.arange(M - 140, M), rng.integers(0, M, size=300)]))
+    yo = ox.linear_w8a8(a[rows], sx[rows], w, sw, b, relu, r[rows] if res else None)
+    if group:
+        qr, sr = ox.group_quant(yo, group)
+        assert np.array_equal(new[0].cpu().numpy()[rows], qr) and np.array_equal(new[1].cpu().numpy()[rows].view(np.uint32), sr.view(np.uint32))
+    else:
+        assert np.array_equal(new[0].cpu().numpy()[rows].view(np.uint32), yo.view(np.uint32))
+
+
+def test_gemm_stream_kernel_non_finite_inputs_take_the_exact_path(K):
+    """Rows with an infinite / NaN scale and a NaN bias column: same bytes as the tile kernel (whose chunk-wise slow path is exact)."""
+    import os
+    rng = np.random.default_rng(5)
+    M, N, K_ = 2048, 512, 512
+    a, w = rand_i8(rng, (M, K_)), rand_i8(rng, (N, K_))
+    sx = rng.uniform(1e-3, 5e-2, size=M).astype(np.float32)
+    sx[7], sx[300], sx[2047] = np.inf, np.nan, 3e38
+    sw = rng.uniform(1e-4, 1e-2, size=N).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    args = dict(row_scale=dev(sx), col_scale=dev(sw), bias=dev(b), out_kind=K.OUT_Q8, quant_group=512)
+    new = K.linear_w8a8(dev(a), dev(w), **args)
+    os.environ["OT_GEMM_STREAM"] = "0"
+    try:
+        old = K.linear_w8a8(dev(a), dev(w), **args)
+    finally:
+        del os.environ["OT_GEMM_STREAM"]
+    assert torch.equal(new[0], old[0]) and torch.equal(new[1].view(torch.int32), old[1].view(torch.int32))
+    b2 = b.copy(); b2[100] = np.nan
+    args["bias"] = dev(b2)
+    new = K.linear_w8a8(dev(a), dev(w), **args)
+    os.environ["OT_GEMM_STREAM"] = "0"
+    try:
+        old = K.linear_w8a8(dev(a), dev(w), **args)
+    finally:
+        del os.environ["OT_GEMM_STREAM"]
+    assert torch.equal(new[0], old[0]) and torch.equal(new[1].view(torch.int32), old[1].view(torch.int32))
+
+
 @pytest.mark.parametrize("M,N,group,relu", [(64, 1536, 512, False), (64, 512, 512, False), (64, 2048, 2048, True), (200, 1536, 512, False), (1, 512, 512, False)])
 def test_gemm_layernorm_prologue_equals_unfused(K, M, N, group, relu):
     """ot_ln_linear_w8a8 == ot_layernorm_quant followed by ot_linear_w8a8, bit for bit (same op order), and vs the oracle."""
