@@ -575,6 +575,8 @@ static int launch_attention(const AttnArgs& a, int tk_max, cudaStream_t stream) 
 
 OT_DEFINE_TL_SETTER(tl_set_attention)
 
+int launch_attention_tc(const AttnArgs& a, cudaStream_t stream);   // ot_attention_tc.cu
+
 }  // namespace ot
 
 using namespace ot;
@@ -634,6 +636,16 @@ extern "C" int ot_attention_q8_mf(const int8_t* q, int64_t ldq, const float* sq,
     OT_CHECK_CUDA(launch_kernel(attention_decode_kernel, dim3(B), dim3(256), 0, s, 1, a));
     count_launch();
     return OT_OK;
+  }
+  // encoder-size blocks (32 <= Tq <= 128, Tk <= 128), faulty or not: tensor-core kernel, one CTA per (sentence, head); the merged rows
+  // are complete only across the 8 head CTAs, so the RowQuant for the O-projection is a second launch
+  {
+    const int rc = launch_attention_tc(a, s);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if (ctx_q != nullptr) return ot_rowquant(ctx, ld_ctx, static_cast<int64_t>(B) * Tq, kDm, kDm, ctx_q, ctx_s, nullptr, stream);
+      return OT_OK;
+    }
   }
   if (Tq >= 32 && ctx != nullptr && a.fault.mode == OT_FAULT_NONE && a.mf_unit == nullptr && probs_q == nullptr && k_new == nullptr &&
       step_dev == nullptr && attn_heads_smem_bytes(Tq, Tk) <= 100 * 1024) {

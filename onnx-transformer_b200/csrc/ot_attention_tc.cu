@@ -1,0 +1,435 @@
+// Encoder-size quantized attention on the 5th-generation tensor cores (attention.py:23-36 as exported).
+//
+// One CTA per (sentence, head), 128 threads, thread i = query row i = TMEM lane i:
+//   1. Q, K head slices (int8, 64 bytes per row) are copied into the 128-byte-swizzled K-major operand layout; V is de-quantized
+//      (vhat = fl(float(vq) * sv[j]), the oracle's own fp32 value), scaled by a per-CTA power of two and split into fp16 hi + lo
+//      (22 significant bits), TRANSPOSED to [feature][key] so that it is a K-major B operand;
+//   2. scores: two tcgen05.mma.kind::i8 (M = 128 queries, N = keys, K = 2 x 32) -> exact int32 dot products in TMEM;
+//   3. softmax with one thread per query row: no shuffles.  The row's scores / exponentials do not fit in registers without
+//      unrolling, so they are stashed over their own TMEM columns between the passes (tcgen05.st):
+//        A: s = fl(fl(float(dot)*sq[i])*sk[j]) / 8, masked -> -1e9 (masked_fill), running max       -> stash s
+//        B: e = expf(s - max), running sum                                                          -> stash e
+//        C: p = e / sum (reciprocal + one Newton residual step: within 1 ulp), pq = rint(127 p) in {0..127} -> fp16 A operand
+//   4. context: tcgen05.mma.kind::f16, A = pq (exact in fp16), B = V hi then V lo, fp32 accumulation in TMEM:
+//        ctx[i, d] = (sum_j pq[i,j] * vhat[j,d]) / 127
+//      The V scale sits on the contraction axis (per key), so this product cannot be an int8 GEMM; the hi/lo split
+//      keeps it in the float tolerance class (observed max relative error vs the float64 oracle ~1e-6, tests/test_kernels_gpu.py).
+//   Fault hooks (App. D) are integer-exact patches of the affected scores / additive fp32 patches of the affected context elements,
+//   so a fault-free element of a faulty launch is bit-identical to the golden launch (same kernel, same data).
+// Replaces attention_heads_kernel (dp4a + fp32 FMA on CUDA cores: 700 us per cfg3 layer, profiles/r1_ncu_encoder_cfg3_layer.txt).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "ot_attention_decode.cuh"
+#include "ot_common.h"
+#include "ot_ptx.cuh"
+
+namespace ot {
+
+constexpr int kTcThreads = 128;
+constexpr int kTcOffQ = 0, kTcOffK = 16384, kTcOffVhi = 32768, kTcOffVlo = 49152;
+constexpr int kTcOffSk = 65536, kTcOffSv = kTcOffSk + 512, kTcOffKeep = kTcOffSv + 512, kTcOffRed = kTcOffKeep + 128, kTcOffBar = kTcOffRed + 32;
+constexpr int kTcSmem = kTcOffBar + 64 + 1024;
+
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 instruction descriptor: D = F32 (1 at [4,6)), A = B = F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void tc_tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tc_patch_f32(const OtFault& f, float v) {
+  uint32_t bits = __float_as_uint(v);
+  if (f.mode == OT_FAULT_RANDOM_BITFLIP) bits ^= (1u << f.bit);
+  else bits = f.value_bits;
+  const float r = __uint_as_float(bits);
+  return (r != r) ? 0.0f : r;
+}
+// byte (row, k) of a 128-byte-swizzled K-major operand tile
+__device__ __forceinline__ int tc_tile_byte(const uint8_t* tile, int row, int k) {
+  return static_cast<int8_t>(tile[row * 128 + ((((k >> 4) ^ (row & 7))) << 4) + (k & 15)]);
+}
+
+template <bool FAULT>
+__global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem + kTcOffQ;
+  uint8_t* sK = smem + kTcOffK;
+  uint8_t* sP = smem;                                   // overlays sQ | sK once the score MMAs have completed
+  uint8_t* sVhi = smem + kTcOffVhi;
+  uint8_t* sVlo = smem + kTcOffVlo;
+  float* sks = reinterpret_cast<float*>(smem + kTcOffSk);
+  float* svs = reinterpret_cast<float*>(smem + kTcOffSv);
+  uint8_t* keep = smem + kTcOffKeep;
+  float* sred = reinterpret_cast<float*>(smem + kTcOffRed);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int Tq = a.Tq, Tk = a.Tk;
+  const int Tkp = (Tk + 15) & ~15;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_init(smem_u32(&bars[0]), 1);
+      mbar_init(smem_u32(&bars[1]), 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 128);
+    tmem_relinquish();
+  }
+  pdl_wait();
+  pdl_trigger();
+
+  // ---- fault context (App. D); operand selector in fault.reserved
+  OtFault f = a.fault;
+  bool fault_here = false;
+  int fi = -1, fj = -1, fd = -1, fw0 = 0, fw1 = 0;
+  if (FAULT) {
+    if (a.mf_unit != nullptr) {
+      const int fidx = a.mf_unit[b];
+      if (fidx >= 0) f = a.mf_faults[fidx];
+      else f.mode = OT_FAULT_NONE;
+    }
+    if (f.mode != OT_FAULT_NONE) {
+      const int64_t idx = f.flat_index;
+      const int wl = f.window_len;
+      int fb = -1, fh = -1;
+      switch (f.reserved) {
+        case OPERAND_Q: {  // Round tensor [B,Tq,512]
+          fb = static_cast<int>(idx / (static_cast<int64_t>(Tq) * kDm));
+          fi = static_cast<int>((idx / kDm) % Tq);
+          fh = static_cast<int>(idx % kDm) / kDk; fd = static_cast<int>(idx % kDm) % kDk;
+          fw0 = wl > 0 ? f.window_start : 0; fw1 = wl > 0 ? min(Tk, f.window_start + wl) : Tk;       // key window
+        } break;
+        case OPERAND_K: case OPERAND_V: {  // Round tensor [B,Tk,512]
+          fb = static_cast<int>(idx / (static_cast<int64_t>(Tk) * kDm));
+          fj = static_cast<int>((idx / kDm) % Tk);
+          fh = static_cast<int>(idx % kDm) / kDk; fd = static_cast<int>(idx % kDm) % kDk;
+          fw0 = wl > 0 ? f.window_start : 0; fw1 = wl > 0 ? min(Tq, f.window_start + wl) : Tq;       // query window
+        } break;
+        case OPERAND_P: case OPERAND_SCORES: {  // [B,8,Tq,Tk]
+          fj = static_cast<int>(idx % Tk);
+          fi = static_cast<int>((idx / Tk) % Tq);
+          fh = static_cast<int>((idx / (static_cast<int64_t>(Tk) * Tq)) % kHeads);
+          fb = static_cast<int>(idx / (static_cast<int64_t>(Tk) * Tq * kHeads));
+          fw0 = wl > 0 ? f.window_start : 0; fw1 = wl > 0 ? min(kDk, f.window_start + wl) : kDk;     // feature window
+        } break;
+        default: {  // OPERAND_CTX: [B,8,Tq,64]
+          fd = static_cast<int>(idx % kDk);
+          fi = static_cast<int>((idx / kDk) % Tq);
+          fh = static_cast<int>((idx / (static_cast<int64_t>(kDk) * Tq)) % kHeads);
+          fb = static_cast<int>(idx / (static_cast<int64_t>(kDk) * Tq * kHeads));
+        } break;
+      }
+      if (a.mf_unit != nullptr) fb = b;   // batched faults address the sentence's own tensors
+      fault_here = (fb == b && fh == h);
+    }
+  }
+
+  // ---- stage Q and K head slices into the swizzled operand tiles (rows past Tq / Tk are zero)
+  for (int idx = tid; idx < 128 * 4; idx += kTcThreads) {
+    const int row = idx >> 2, c = idx & 3;
+    uint4 qv = make_uint4(0, 0, 0, 0), kv = make_uint4(0, 0, 0, 0);
+    if (row < Tq) qv = *reinterpret_cast<const uint4*>(a.q + (static_cast<int64_t>(b) * Tq + row) * a.ldq + h * kDk + c * 16);
+    if (row < Tk) kv = *reinterpret_cast<const uint4*>(a.k + (static_cast<int64_t>(b) * a.Tk_cap + row) * a.ldk + h * kDk + c * 16);
+    const int off = row * 128 + ((c ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(sQ + off) = qv;
+    *reinterpret_cast<uint4*>(sK + off) = kv;
+  }
+  // ---- key scales, mask; the largest |vhat| of the head bounds the fp16 range of the split
+  {
+    float s1 = 0.f, s2 = 0.f;
+    uint8_t kp = 0;
+    if (tid < Tk) {
+      const int64_t src = (static_cast<int64_t>(b) * a.Tk_cap + tid) * a.skv_stride;
+      s1 = a.sk[src];
+      s2 = a.sv[src];
+      kp = (a.mask_kind == 1) ? a.key_mask[static_cast<int64_t>(b) * a.mask_stride + tid] : 1;
+    }
+    sks[tid] = s1; svs[tid] = s2; keep[tid] = kp;
+    const float m = warp_max_f(fabsf(s2));
+    if (lane == 0) sred[warp] = m;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  float vscale, vinv;
+  {
+    const float vmax = __fmul_rn(fmaxf(fmaxf(sred[0], sred[1]), fmaxf(sred[2], sred[3])), 127.0f);
+    int e = static_cast<int>((__float_as_uint(vmax) >> 23) & 0xFFu) - 127;        // floor(log2(vmax)) for normal numbers
+    if (!(vmax > 1e-30f) || !(vmax < 1e30f)) e = 13;                              // degenerate scales: no pre-scaling
+    const int p = 13 - e;                                                          // 2^p * vmax < 2^14
+    vscale = __uint_as_float(static_cast<uint32_t>(127 + p) << 23);
+    vinv = __uint_as_float(static_cast<uint32_t>(127 - p) << 23);
+  }
+  // ---- V: de-quantize, scale, split hi/lo, transpose into [feature][key] K-major tiles (64 keys per 128-byte row, fp16)
+  {
+    const int jp = tid & 63, dh = tid >> 6;
+    const int j0 = 2 * jp, j1 = j0 + 1;
+    if (j0 < Tkp) {
+      uint32_t w0[8], w1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w0[u] = w1[u] = 0u;
+      float sv0 = 0.f, sv1 = 0.f;
+      if (j0 < Tk) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.v + (static_cast<int64_t>(b) * a.Tk_cap + j0) * a.ldk + h * kDk + 32 * dh);
+        const uint4 x = src[0], y = src[1];
+        w0[0] = x.x; w0[1] = x.y; w0[2] = x.z; w0[3] = x.w; w0[4] = y.x; w0[5] = y.y; w0[6] = y.z; w0[7] = y.w;
+        sv0 = svs[j0];
+      }
+      if (j1 < Tk) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.v + (static_cast<int64_t>(b) * a.Tk_cap + j1) * a.ldk + h * kDk + 32 * dh);
+        const uint4 x = src[0], y = src[1];
+        w1[0] = x.x; w1[1] = x.y; w1[2] = x.z; w1[3] = x.w; w1[4] = y.x; w1[5] = y.y; w1[6] = y.z; w1[7] = y.w;
+        sv1 = svs[j1];
+      }
+      const int kb = jp >> 5;
+      const int chunk = (jp & 31) >> 2, inner = 4 * (jp & 3);
+      uint8_t* hi_t = sVhi + kb * 8192;
+      uint8_t* lo_t = sVlo + kb * 8192;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const int d = 32 * dh + 4 * u + bb;
+          const float x0 = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int8_t>((w0[u] >> (8 * bb)) & 0xFFu)), sv0), vscale);
+          const float x1 = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int8_t>((w1[u] >> (8 * bb)) & 0xFFu)), sv1), vscale);
+          const __half2 hi = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(hi);
+          const __half2 lo = __floats2half2_rn(__fsub_rn(x0, hf.x), __fsub_rn(x1, hf.y));
+          const int off = d * 128 + ((chunk ^ (d & 7)) << 4) + inner;
+          *reinterpret_cast<__half2*>(hi_t + off) = hi;
+          *reinterpret_cast<__half2*>(lo_t + off) = lo;
+        }
+      }
+    }
+  }
+  fence_proxy_async_smem();      // generic-proxy writes of the operand tiles -> visible to the tensor core
+  __syncthreads();
+
+  // ---- scores: S[i, j] = sum_d Q[i, d] K[j, d], exact int32
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_i8(128, Tkp);
+    const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sQ));
+    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sK));
+    mma_i8_ss(tmem_base, a_desc, b_desc, idesc, 0u);
+    mma_i8_ss(tmem_base, a_desc + 2, b_desc + 2, idesc, 1u);
+    mma_commit(smem_u32(&bars[0]));
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&bars[0]), 0);
+  tc_fence_after();
+
+  const bool wactive = warp * 32 < Tq;                       // warps whose 32 rows are all past Tq only keep the barriers company
+  const int i = tid;
+  const bool row_ok = i < Tq;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  float pq_f = 0.f;                                           // quantized probability at column fj (P / V faults)
+  float inv_sum = 0.f, sum = 1.f;
+  if (wactive) {
+    const float sqi = row_ok ? a.sq[(static_cast<int64_t>(b) * Tq + i) * a.sq_stride] : 1.0f;
+    const int causal_last = (a.mask_kind == 2) ? a.q_pos0 + i : 0x7fffffff;
+    // ---- pass A: scaled, masked scores + row maximum
+    float mx = -INFINITY;
+    {
+      uint32_t r[16];
+#pragma unroll 1
+      for (int c = 0; c < Tkp; c += 16) {
+        tmem_ld_32x16(taddr + c, r);
+        tmem_wait_ld();
+        const uint4 kw = *reinterpret_cast<const uint4*>(keep + c);
+        const uint32_t kbytes[4] = {kw.x, kw.y, kw.z, kw.w};
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 sk4 = *reinterpret_cast<const float4*>(sks + c + 4 * q4);
+          const float skv[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            const int jj = 4 * q4 + bb, j = c + jj;
+            int dot = static_cast<int>(r[jj]);
+            if (FAULT && fault_here) {
+              if (f.reserved == OPERAND_Q && f.mode == OT_FAULT_INPUT && i == fi && j >= fw0 && j < fw1) {
+                const int qv = tc_tile_byte(sQ, i, fd);
+                dot += (flip_int8_bit(qv, f.bit) - qv) * tc_tile_byte(sK, j, fd);
+              } else if (f.reserved == OPERAND_K && f.mode == OT_FAULT_WEIGHT && j == fj && i >= fw0 && i < fw1) {
+                const int kv = tc_tile_byte(sK, j, fd);
+                dot += tc_tile_byte(sQ, i, fd) * (flip_int8_bit(kv, f.bit) - kv);
+              }
+            }
+            float mm = __fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), skv[bb]);                 // MatMul_k_out0
+            if (FAULT && fault_here && f.reserved == OPERAND_SCORES && i == fi && j == fj) mm = tc_patch_f32(f, mm);
+            float s = __fmul_rn(mm, 0.125f);                                                      // / sqrt(d_k) = / 8, exact
+            const bool visible = ((kbytes[q4] >> (8 * bb)) & 0xFFu) != 0u && j <= causal_last;
+            s = visible ? s : -1e9f;                                                              // masked_fill(mask == 0, -1e9)
+            s = (j < Tk) ? s : -INFINITY;                                                         // padding columns of the MMA tile: not keys
+            mx = fmaxf(mx, s);
+            r[jj] = __float_as_uint(s);
+          }
+        }
+        tc_tmem_st_32x16(taddr + c, r);
+        tc_tmem_wait_st();
+      }
+    }
+    // ---- pass B: exponentials + row sum
+    sum = 0.f;
+    {
+      uint32_t r[16];
+#pragma unroll 1
+      for (int c = 0; c < Tkp; c += 16) {
+        tmem_ld_32x16(taddr + c, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const float ev = expf(__fsub_rn(__uint_as_float(r[jj]), mx));
+          sum += ev;
+          r[jj] = __float_as_uint(ev);
+        }
+        tc_tmem_st_32x16(taddr + c, r);
+        tc_tmem_wait_st();
+      }
+    }
+    inv_sum = __frcp_rn(sum);
+  }
+  if (FAULT) __syncthreads();          // a faulty launch read sQ / sK in pass A: nobody overwrites them with P before everyone is done
+  if (wactive) {
+    // ---- pass C: p = e / sum, pq = rint(127 p) -> fp16 A operand of the context MMAs (row i, 64 keys per 128-byte swizzled row)
+    uint32_t r[16];
+#pragma unroll 1
+    for (int c = 0; c < Tkp; c += 16) {
+      tmem_ld_32x16(taddr + c, r);
+      tmem_wait_ld();
+      uint32_t packed[8];
+#pragma unroll
+      for (int jj = 0; jj < 16; jj += 2) {
+        float n2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float ev = __uint_as_float(r[jj + u]);
+          const float q0 = __fmul_rn(ev, inv_sum);
+          const float p = __fmaf_rn(__fmaf_rn(-q0, sum, ev), inv_sum, q0);                       // e / sum within 1 ulp
+          const float t = __fadd_rn(__fmul_rn(p, 127.0f), 12582912.0f);                          // Round(Mul(p, 127)), ties to even
+          n2[u] = __fsub_rn(t, 12582912.0f);
+          if (FAULT && fault_here && c + jj + u == fj) pq_f = n2[u];
+        }
+        const __half2 hp = __floats2half2_rn(n2[0], n2[1]);
+        packed[jj >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+        if (a.probs_q != nullptr && row_ok) {
+          uint8_t* pr = a.probs_q + ((static_cast<int64_t>(b) * kHeads + h) * Tq + i) * Tk;
+          if (c + jj < Tk) pr[c + jj] = static_cast<uint8_t>(n2[0]);
+          if (c + jj + 1 < Tk) pr[c + jj + 1] = static_cast<uint8_t>(n2[1]);
+        }
+      }
+      uint8_t* prow = sP + (c >> 6) * 16384 + i * 128;
+      const int ch = (c & 63) >> 3;
+      *reinterpret_cast<uint4*>(prow + (((ch) ^ (i & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ (i & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  // ---- context: ctx[i, d] = sum_j pq[i, j] (Vhi + Vlo)[d, j]   (fp32 accumulation, over the score columns that are no longer needed)
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_f16(128, 64);
+    const int ksteps = Tkp >> 4;                               // 16 keys (32 bytes of K) per instruction
+    uint32_t acc = 0u;
+    for (int part = 0; part < 2; ++part) {
+      const uint8_t* vt = part == 0 ? sVhi : sVlo;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int kb = ks >> 2, kk = ks & 3;
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sP + kb * 16384)) + static_cast<uint64_t>(kk * 2);
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(vt + kb * 8192)) + static_cast<uint64_t>(kk * 2);
+        mma_f16_ss(tmem_base, a_desc, b_desc, idesc, acc);
+        acc = 1u;
+      }
+    }
+    mma_commit(smem_u32(&bars[1]));
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&bars[1]), 0);
+  tc_fence_after();
+
+  if (wactive) {
+    uint32_t r[4][16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld_32x16(taddr + 16 * c, r[c]);
+    tmem_wait_ld();
+    float* orow = a.ctx + (static_cast<int64_t>(b) * Tq + i) * a.ld_ctx + h * kDk;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float y[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) y[jj] = __fdiv_rn(__fmul_rn(__uint_as_float(r[c][jj]), vinv), 127.0f);
+      if (FAULT && fault_here && row_ok) {
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int d = 16 * c + jj;
+          if (f.reserved == OPERAND_P && f.mode == OT_FAULT_INPUT && i == fi && d >= fw0 && d < fw1) {
+            const float pf = static_cast<float>(flip_int8_bit(static_cast<int>(pq_f), f.bit));
+            const int vq = a.v[(static_cast<int64_t>(b) * a.Tk_cap + fj) * a.ldk + h * kDk + d];
+            const float vhat = __fmul_rn(__int2float_rn(vq), svs[fj]);
+            y[jj] = __fadd_rn(y[jj], __fmul_rn(__fsub_rn(__fdiv_rn(pf, 127.0f), __fdiv_rn(pq_f, 127.0f)), vhat));
+          } else if (f.reserved == OPERAND_V && f.mode == OT_FAULT_WEIGHT && d == fd && i >= fw0 && i < fw1) {
+            const int vq = a.v[(static_cast<int64_t>(b) * a.Tk_cap + fj) * a.ldk + h * kDk + d];
+            const float dv = __fsub_rn(__fmul_rn(__int2float_rn(flip_int8_bit(vq, f.bit)), svs[fj]), __fmul_rn(__int2float_rn(vq), svs[fj]));
+            y[jj] = __fadd_rn(y[jj], __fmul_rn(__fdiv_rn(pq_f, 127.0f), dv));
+          } else if (f.reserved == OPERAND_CTX && (f.mode == OT_FAULT_RANDOM || f.mode == OT_FAULT_RANDOM_BITFLIP) && i == fi && d == fd) {
+            y[jj] = tc_patch_f32(f, y[jj]);
+          }
+        }
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          reinterpret_cast<float4*>(orow + 16 * c)[q4] = make_float4(y[4 * q4], y[4 * q4 + 1], y[4 * q4 + 2], y[4 * q4 + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// Launch for (B x 8) heads; returns 1 when the shape does not qualify (the caller falls back to the CUDA-core kernels).
+int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
+  const char* env = getenv("OT_ATTN_TC");
+  if (env && atoi(env) == 0) return 1;
+  if (a.Tq < 32 || a.Tq > 128 || a.Tk < 1 || a.Tk > 128 || a.ctx == nullptr || a.k_new != nullptr || a.step_dev != nullptr) return 1;
+  const bool faulty = a.fault.mode != OT_FAULT_NONE || a.mf_unit != nullptr;
+  auto kernel = faulty ? attention_tc_kernel<true> : attention_tc_kernel<false>;
+  static bool configured[2] = {false, false};
+  if (!configured[faulty ? 1 : 0]) {
+    OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+    configured[faulty ? 1 : 0] = true;
+  }
+  OT_CHECK_CUDA(launch_kernel(kernel, dim3(kHeads, a.B), dim3(kTcThreads), kTcSmem, stream, 1, a));
+  count_launch();
+  return OT_OK;
+}
+
+}  // namespace ot

@@ -371,3 +371,40 @@ def run_module(module, input_values, module_filepath, module_weight_dict, module
         module_weight_dict[k] = np.asarray(input_values[k])
     module_weight_dict.pop("__prov__", None)
     return inference(module_graph, module_weight_dict, module, inject_parameters, mode)
+
+
+def greedy_decode(float_weights, encoder_graph, decoder_graph, src_ids, src_mask, max_len, start_symbol=0, mode="ref-float", timings=None):
+    """8-bit_onnx_optimized_custom_inference.py:649-721 on this oracle's node walk (custom_decoder=True): host embedding
+    (embeddings.py:13, positional_encodings.py:24), run_module("Encoder"), then max_len - 1 x run_module("Decoder") on the FULL
+    prefix with subsequent_mask (utils.py:10-14), generator + arg-max (generator.py:14-15).  Returns (ys, margins)."""
+    import time
+    t0 = time.perf_counter()
+    B = src_ids.shape[0]
+    pe = ox.positional_encoding(max(max_len, src_ids.shape[1]) + 1)
+    src_float = ox.embed(src_ids, float_weights["src_embed.0.lut.weight"], pe)
+    enc_in = {"global_in": src_float, "global_in_1": np.asarray(src_mask)}
+    wd, _ = prepare_inference(encoder_graph, enc_in)
+    memory, _ = run_module("Encoder", enc_in, None, wd, encoder_graph, None, mode)
+    memory = memory[list(memory.keys())[0]]
+    ys = np.full((B, 1), start_symbol, dtype=np.int64)
+    dwd = None
+    margins = []
+    if timings is not None:
+        timings["encoder_s"] = time.perf_counter() - t0
+        timings["decoder_step_s"] = []
+    for _ in range(max_len - 1):
+        t1 = time.perf_counter()
+        T = ys.shape[1]
+        dec_in = {"global_in": ox.embed(ys, float_weights["tgt_embed.0.lut.weight"], pe), "global_in_1": memory, "global_in_2": np.asarray(src_mask),
+                  "global_in_3": (np.triu(np.ones((1, T, T)), k=1) == 0).astype(np.int64)}
+        if dwd is None:
+            dwd, _ = prepare_inference(decoder_graph, dec_in)
+        out, _ = run_module("Decoder", dec_in, None, dwd, decoder_graph, None, mode)
+        out = out[list(out.keys())[0]]
+        nxt, logits = ox.generator(out[:, -1], float_weights["generator.proj.weight"], float_weights["generator.proj.bias"])
+        srt = np.sort(logits, axis=-1)
+        margins.append(srt[:, -1] - srt[:, -2])
+        ys = np.concatenate([ys, nxt.reshape(B, 1).astype(np.int64)], axis=1)
+        if timings is not None:
+            timings["decoder_step_s"].append(time.perf_counter() - t1)
+    return ys, np.stack(margins, axis=1)

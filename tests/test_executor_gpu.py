@@ -119,3 +119,85 @@ def test_graph_file_roundtrip_and_numpy_inputs(setup, tmp_path):
     out2, _ = ex.run_module("Encoder", {"global_in": torch.from_numpy(x), "global_in_1": torch.from_numpy(mask)}, None, wd2, g2)
     assert torch.equal(out["global_out"], out2["global_out"])
     assert isinstance(ex.to_numpy(out)["global_out"], np.ndarray)
+
+
+@pytest.mark.parametrize("target,fault_model,bit,draws", [
+    ("MatMul_15", "INPUT", 6, {"target_indices": [1, 2, 77]}),                                   # self-attention QK^T, Q operand
+    ("MatMul_16", "WEIGHT16", 5, {"target_indices": [0, 1, 200], "window_start": 0, "window_len": 2}),   # self-attention P.V, V operand
+    ("MatMul_19", "WEIGHT", 7, {"target_indices": [1, 3, 130]}),                                 # cross-attention QK^T, K operand (memory side)
+    ("MatMul_20", "INPUT16", 4, {"target_indices": [0, 2, 1, 3], "window_start": 1}),            # cross-attention P.V, P operand
+    ("MatMul_22", "INPUT", 7, {"target_indices": [0, 2, 300]}),                                  # ffn1
+    ("MatMul_23", "WEIGHT", 6, {"target_indices": [100, 1500]}),                                 # ffn2
+    ("MatMul_22", "RANDOM_BITFLIP", None, {"target_indices": [1, 1, 900], "flip_bit": 29}),
+    ("MatMul_19", "RANDOM", None, {"target_indices": [0, 3, 2, 4], "random_bits": 0xc1a00000}),
+])
+def test_decoder_fault_hooks_match_oracle_trial_for_trial(setup, target, fault_model, bit, draws):
+    """The hooks with module == "Decoder" (targetted_module "Decoder/..."), incl. the memory-side operands of cross-attention."""
+    ex, w, enc, dec, x, mask = setup
+    memory = om.encode(w, x, mask, "int-exact", 2)
+    ys = np.array([[0, 7, 9], [0, 4, 33]])
+    temb = ox.embed(ys, w["tgt_embed.0.lut.weight"], ox.positional_encoding(32))
+    sub = (np.triu(np.ones((1, 3, 3)), k=1) == 0).astype(np.int64)
+    ins = {"global_in": temb, "global_in_1": memory, "global_in_2": mask, "global_in_3": sub}
+    t = [d for d in faults.targets_from_graph(dec, "Decoder") if d["target_layer"] == target][0]
+    assert t["module"].startswith("Decoder/")
+    p_gpu = faults.build_inject_parameters(dec, t, fault_model, bit, rng_draws=dict(draws))
+    p_ref = faults.build_inject_parameters(dec, t, fault_model, bit, rng_draws=dict(draws))
+    wd, g = ex.prepare_inference(dec, ins)
+    _, wdg = ex.run_module("Decoder", ins, None, wd, g, None)
+    golden_mm = wdg[t["output_tensor"]].clone()
+    wd2, g = ex.prepare_inference(dec, ins)
+    out, wd2 = ex.run_module("Decoder", ins, None, wd2, g, p_gpu)
+    rwd, rg = oe.prepare_inference(dec, ins)
+    _, rwdg = oe.run_module("Decoder", ins, None, rwd, rg, None, "int-exact")
+    r_golden_mm = rwdg[t["output_tensor"]].copy()
+    rwd2, rg = oe.prepare_inference(dec, ins)
+    rout, rwd2 = oe.run_module("Decoder", ins, None, rwd2, rg, p_ref, "int-exact")
+    assert p_gpu["faulty_trace"] in ([], None) and p_gpu["rng_draws_used"] == p_ref["rng_draws_used"]
+    d_gpu = (wd2[t["output_tensor"]] - golden_mm).cpu().numpy()
+    d_ref = rwd2[t["output_tensor"]] - r_golden_mm
+    if np.count_nonzero(d_ref) == 0:                     # e.g. a weight column that only meets ReLU zeros: no perturbation on either side
+        assert np.count_nonzero(d_gpu) == 0
+        return
+    assert np.count_nonzero((d_gpu != 0) != (d_ref != 0)) <= 2
+    # The perturbation is (q' - q) * scale * (the other operand): the decoder's operands sit behind LayerNorm / softmax / P.V float
+    # reductions, so single int8 elements of the other operand may differ by one LSB between the two walks (rounding-boundary flips,
+    # accounted for op by op in test_fullsize_parity_gpu.py) -- a few elements off by one quantisation step, everything else equal.
+    finite = np.isfinite(d_ref)
+    dg, dr = d_gpu[finite], d_ref[finite]
+    viol = np.abs(dg - dr) > (2e-3 * np.abs(dr) + 1e-5 * max(1.0, float(np.abs(dr).max())))
+    assert viol.mean() <= 0.02, float(viol.mean())
+    assert float(np.abs(dg - dr).max()) <= 0.05 * float(np.abs(dr).max()) + 1e-6
+    err = np.abs(out["global_out"].cpu().numpy() - rout["global_out"])
+    ok = np.isfinite(rout["global_out"])
+    assert err[ok].mean() < 1e-2 and np.percentile(err[ok], 99.5) < 0.15
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_greedy_decode_through_the_executor_matches_oracle(setup, B):
+    """BASELINE configs[0] in miniature: the reference's greedy_decode (8-bit_onnx_optimized_custom_inference.py:649-721) driving
+    run_module("Encoder") once and run_module("Decoder") on the full prefix every step -- product executor vs oracle executor."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import parity_helpers as ph
+    from onnx_transformer_b200 import decode as D
+    ex, w, enc2, dec2, x, mask2 = setup
+    enc, dec = (enc2, dec2) if B == 2 else (G.build_encoder_graph(w, batch=1, n_layers=2), G.build_decoder_graph(w, batch=1, n_layers=2))
+    ids, mask = W.synthetic_tokens(11, 2, 5, 67, min_len=3)
+    ids, mask = ids[:B], mask[:B]
+    model = D.HostModel(w, max_len=32)
+    timings = {}
+    ys = D.greedy_decode(model, ids, mask, 8, 0, enc, dec, timings=timings).cpu().numpy()
+    assert ys.shape == (B, 8) and np.all(ys[:, 0] == 0) and len(timings["decoder_step_s"]) == 7
+    ref, margins = oe.greedy_decode(w, enc, dec, ids, mask, 8, 0, "int-exact")
+    for b in range(B):
+        t = ph.first_divergence(ys[b], ref[b])
+        assert t < 0 or margins[b, t] < ph.margin_bound(), (b, t, margins[b, t])
+    # the fused engine decodes the same tokens (same arithmetic contract, KV cache instead of the full-prefix recompute)
+    from onnx_transformer_b200.engine import QuantizedTransformer
+    fw = W.init_float_weights(5, 67, 59, 2, randomize_norms=True)
+    eng = QuantizedTransformer(fw, n_layers=2, max_len=8)
+    ys_e = eng.greedy_decode(torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda(), 8).cpu().numpy()
+    for b in range(B):
+        t = ph.first_divergence(ys_e[b], ref[b])
+        assert t < 0 or margins[b, t] < ph.margin_bound(), (b, t, margins[b, t])

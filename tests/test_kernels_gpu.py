@@ -287,6 +287,88 @@ def test_attention(K, B, Tq, Tk, mask):
     assert np.array_equal(cs.cpu().numpy().view(np.uint32), sr.reshape(-1).view(np.uint32))
 
 
+@pytest.mark.parametrize("Tq,Tk", [(64, 64), (100, 128), (128, 40)])
+def test_attention_tensor_core_kernel_vs_cuda_core_kernel_and_oracle(K, Tq, Tk):
+    """ot_attention_tc.cu (tcgen05 scores + fp16 hi/lo context) against the dp4a / fp32-FMA kernel it replaces: the quantized
+    probabilities may differ only at verified rounding boundaries, the context within the float class; measured error vs the float64
+    oracle reported through the assertion bounds (P.V: hi/lo split of s_v*vq = 22 significant bits)."""
+    import os
+    rng = np.random.default_rng(Tq * 7 + Tk)
+    B = 3
+    qq, sq, kq, sk, vq, sv = _attn_inputs(rng, B, Tq, Tk)
+    sv[:, 3] *= 40.0                                   # a wide spread of V scales exercises the power-of-two pre-scaling of the split
+    sv[:, 5] *= 1e-3
+    lens = rng.integers(max(1, Tk // 3), Tk + 1, size=B)
+    key_mask = (np.arange(Tk)[None, :] < lens[:, None]).astype(np.uint8)
+    args = (dev(qq), dev(sq), dev(kq), dev(vq), dev(sk), dev(sv))
+    kw = dict(B=B, Tq=Tq, Tk=Tk, mask_kind=1, key_mask=dev(key_mask), want_ctx=True, want_q=True, want_probs=True)
+    ctx, cq, cs, probs = K.attention_q8(*args, **kw)
+    os.environ["OT_ATTN_TC"] = "0"
+    try:
+        ctx0, cq0, cs0, probs0 = K.attention_q8(*args, **kw)
+    finally:
+        del os.environ["OT_ATTN_TC"]
+    ctx, ctx0 = ctx.cpu().numpy().reshape(B, Tq, 512), ctx0.cpu().numpy().reshape(B, Tq, 512)
+    probs, probs0 = probs.cpu().numpy(), probs0.cpu().numpy()
+    worst = 0.0
+    for b in range(B):
+        rc, rpq, rp = ox.attention(qq[b], sq[b], kq[b], sk[b], vq[b], sv[b], key_mask[b], return_all=True)
+        _check_attn(ctx[b], probs[b], rc, rpq, rp)
+        _check_attn(ctx0[b], probs0[b], rc, rpq, rp)
+        same = (probs[b] == rpq).all(axis=2)                      # [8, Tq]: rows whose probabilities equal the oracle's
+        vmax = np.abs(vq[b].astype(np.float32) * sv[b].reshape(-1, 1)).reshape(Tk, 8, 64).max(axis=(0, 2))
+        err = np.abs(ctx[b] - rc).reshape(Tq, 8, 64) / vmax[None, :, None]
+        worst = max(worst, float(err[same.T].max()))
+    assert worst < 2e-6, worst                                     # relative to the head's largest |vhat|: fp32-class accuracy
+    assert (probs != probs0).mean() < 1e-4
+    qr, sr = ox.row_quant(ctx.reshape(B * Tq, 512))
+    assert np.array_equal(cq.cpu().numpy(), qr) and np.array_equal(cs.cpu().numpy().view(np.uint32), sr.reshape(-1).view(np.uint32))
+
+
+@pytest.mark.parametrize("case", ["q_input16", "k_weight", "scores_bitflip", "scores_random", "p_input16", "v_weight16", "ctx_bitflip"])
+def test_attention_tensor_core_kernel_faults(K, case):
+    """Fault hooks of ot_attention_tc.cu vs the oracle's integer-domain restatement; every element the fault does not
+    reach is bit-identical to the golden launch (same kernel, same data)."""
+    rng = np.random.default_rng(99)
+    B, T = 2, 64
+    qq, sq, kq, sk, vq, sv = _attn_inputs(rng, B, T, T)
+    args = (dev(qq), dev(sq), dev(kq), dev(vq), dev(sk), dev(sv))
+    kw = dict(B=B, Tq=T, Tk=T, mask_kind=0, want_ctx=True, want_q=False, want_probs=True)
+    g_ctx, _, _, g_probs = K.attention_q8(*args, **kw)
+    b, h, i, j, d, t = 1, 5, 17, 40, 33, 22
+    c = h * 64 + d
+    spec = {
+        "q_input16": (K.FAULT_INPUT, K.OPERAND_Q, (b * T + t) * 512 + c, 6, 32, 16, 0, dict(target="qk", type="INPUT16", index=(0, t, c))),
+        "k_weight": (K.FAULT_WEIGHT, K.OPERAND_K, (b * T + t) * 512 + c, 7, 0, 0, 0, dict(target="qk", type="WEIGHT", index=(0, t, c))),
+        "scores_bitflip": (K.FAULT_RANDOM_BITFLIP, K.OPERAND_SCORES, ((b * 8 + h) * T + i) * T + j, 30, 0, 0, 0, dict(target="qk", type="RANDOM_BITFLIP", index=(0, h, i, j))),
+        "scores_random": (K.FAULT_RANDOM, K.OPERAND_SCORES, ((b * 8 + h) * T + i) * T + j, 0, 0, 0, 0x42f00000, dict(target="qk", type="RANDOM", index=(0, h, i, j))),
+        "p_input16": (K.FAULT_INPUT, K.OPERAND_P, ((b * 8 + h) * T + i) * T + j, 6, 16, 16, 0, dict(target="pv", type="INPUT16", index=(0, h, i, j))),
+        "v_weight16": (K.FAULT_WEIGHT, K.OPERAND_V, (b * T + t) * 512 + c, 7, 16, 9, 0, dict(target="pv", type="WEIGHT16", index=(0, t, c))),
+        "ctx_bitflip": (K.FAULT_RANDOM_BITFLIP, K.OPERAND_CTX, ((b * 8 + h) * T + i) * 64 + d, 29, 0, 0, 0, dict(target="pv", type="RANDOM_BITFLIP", index=(0, h, i, d))),
+    }[case]
+    mode, operand, flat, bit, ws, wl, vbits, of = spec
+    fault = K.make_fault(mode, flat_index=flat, bit=bit, window_start=ws, window_len=wl, value_bits=vbits, operand=operand)
+    f_ctx, _, _, f_probs = K.attention_q8(*args, fault=fault, **kw)
+    g, fc = g_ctx.cpu().numpy().reshape(B, T, 512), f_ctx.cpu().numpy().reshape(B, T, 512)
+    assert np.array_equal(g[0].view(np.uint32), fc[0].view(np.uint32))                  # the other sentence: untouched
+    other_heads = np.ones(512, bool); other_heads[h * 64:(h + 1) * 64] = False
+    assert np.array_equal(g[1][:, other_heads].view(np.uint32), fc[1][:, other_heads].view(np.uint32))
+    of.update(bit=bit, window_start=ws, window_len=wl, value_bits=vbits)
+    rc, rpq, rp = ox.attention(qq[b], sq[b], kq[b], sk[b], vq[b], sv[b], None, return_all=True, fault=of)
+    rg = ox.attention(qq[b], sq[b], kq[b], sk[b], vq[b], sv[b], None)
+    assert not np.array_equal(rc, rg), "the oracle's fault must change something"
+    _check_attn(fc[1], f_probs.cpu().numpy()[1], rc, rpq, rp)
+    changed = np.abs(rc - rg) > 1e-4 * (1 + np.abs(rg))
+    assert np.all(np.abs(fc[1] - g[1])[changed] > 0), "the fault did not reach the elements the oracle changes"
+    # batched-trial entry point (one fault per sentence, indices relative to the sentence): same bits as the single-fault launch
+    rel = K.make_fault(mode, flat_index=flat - {K.OPERAND_Q: b * T * 512, K.OPERAND_K: b * T * 512, K.OPERAND_V: b * T * 512,
+                                                 K.OPERAND_P: b * 8 * T * T, K.OPERAND_SCORES: b * 8 * T * T, K.OPERAND_CTX: b * 8 * T * 64}[operand],
+                       bit=bit, window_start=ws, window_len=wl, value_bits=vbits, operand=operand)
+    unit = torch.tensor([-1, 0], dtype=torch.int32, device="cuda")
+    m_ctx, _, _, _ = K.attention_q8(*args, mf=(K.pack_faults([rel], "cuda"), unit), B=B, Tq=T, Tk=T, mask_kind=0, want_ctx=True, want_q=False)
+    assert torch.equal(m_ctx.view(torch.int32), f_ctx.view(torch.int32))
+
+
 def test_attention_kv_cache_append(K):
     """Decode-style: Tq=1, cache of capacity 72 holding t keys, the new key/value appended by the kernel."""
     rng = np.random.default_rng(42)
