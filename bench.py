@@ -116,13 +116,25 @@ def cpu_reference_sample(batch: int, src_len: int, greedy_steps: int, seed: int 
     return batch * greedy_steps / dt, dt
 
 
+def blas_threads(want: int) -> int:
+    """Give the numpy BLAS pool (and torch's intra-op pool) `want` threads -- torchrun exports OMP_NUM_THREADS=1 to its workers -- and
+    return the pool size actually in effect (threadpoolctl), which is what the cpu_baseline `cores` field reports."""
+    import torch
+    torch.set_num_threads(want)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=want)
+        sizes = [int(p.get("num_threads", 1)) for p in threadpool_info() if p.get("user_api") in ("blas", "openmp")]
+        return max(sizes) if sizes else 1
+    except Exception:
+        return 1
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import torch
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = blas_threads(os.cpu_count() or 1)
     sample_b, sample_steps = 16, 16          # ~3 s of CPU work per timed step on 16 cores
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_sample(2, args.src_len, 2)
@@ -131,8 +143,9 @@ def run_reference_arm(args):
         v, dt = cpu_reference_sample(sample_b, args.src_len, sample_steps)
         vals.append(v); secs.append(dt)
     value = float(np.mean(vals))
-    sample = ("oracle port (numpy, ref-float, full-prefix recompute, BLAS threads=%d): %d sentences x %d src tokens, first %d of 71 greedy steps "
-              "per timed step; early steps have the shortest prefixes, so this over-states the CPU's full-run rate" % (cores, sample_b, args.src_len, sample_steps))
+    sample = ("oracle port (numpy, ref-float, full-prefix recompute, %d BLAS threads in effect): %d sentences x %d src tokens, first %d of 71 "
+              "greedy steps per timed step -- a SAMPLE of cfg2, not the same config: early steps have the shortest prefixes, so this over-states "
+              "the CPU's full-run rate (the GPU/CPU ratio is conservative)" % (cores, sample_b, args.src_len, sample_steps))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(np.mean(secs) * 1e3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": "cfg2: greedy decode, batch 64 x src 64, 71 steps (bounded CPU sample)", "batch": args.batch,

@@ -103,6 +103,67 @@ def make_trials(n: int, seed: int, n_sentences: int, src_len: int, modules: Sequ
     return trials
 
 
+# ---------------------------------------------------------------------------------------------- target-directory campaigns
+def load_targets(directory: str) -> List[dict]:
+    """The fault-target descriptors of `--directory_name` (input/encoder/*.json x24, input/decoder/*.json x36; keys target_layer,
+    input_tensor, weight_tensor, bias_tensor, output_tensor, module, model_name), in os.listdir order made deterministic (sorted)."""
+    import json
+    out = []
+    for name in sorted(os.listdir(directory)):
+        if name.endswith(".json"):
+            with open(os.path.join(directory, name)) as f:
+                out.append(json.load(f))
+    return out
+
+
+def target_site(target: dict):
+    """(module, layer, role) of a descriptor, from the node-numbering contract of the 60 reference files: encoder
+    MatMul_{8l+k}, k = q,k,v,qk,pv,o,ffn1,ffn2; decoder MatMul_{0..11} = cross k,v of layers 0..5, MatMul_{12+12l+k}, k = q,k,v,qk,pv,o,
+    cq,cqk,cpv,co,ffn1,ffn2."""
+    module = target["module"].split("/")[0]
+    k = int(target["target_layer"].split("_")[1])
+    if module == "Encoder":
+        return module, k // 8, ["q", "k", "v", "qk", "pv", "o", "ffn1", "ffn2"][k % 8]
+    if k < 12:
+        return module, k // 2, ("ck", "cv")[k % 2]
+    k -= 12
+    return module, k // 12, ["q", "k", "v", "qk", "pv", "o", "cq", "cqk", "cpv", "co", "ffn1", "ffn2"][k % 12]
+
+
+def trials_from_targets(targets: Sequence[dict], seed: int, n_sentences: int, src_len: int, experiments: int = 5, n_bits: int = 8,
+                        fault_models: Sequence[str] = tuple(FAULT_MODELS)) -> List[Trial]:
+    """The campaign loop of parallelized_inject_onnx_transformer.py:794-861: for every target file x fault model (:805) x bit position
+    (:852, `range(8)`; RANDOM models run the loop too, with faulty_bit_position None) -> `total_experiments` = 5 (:830) sentences,
+    each with its own element / window / bit-pattern draws (explicit here, from default_rng(seed)).  The *16 models index shape[3] /
+    shape[2] of a 4-D output, so they exist for the attention MatMuls only (the reference raises IndexError on the FFN targets)."""
+    rng = np.random.default_rng(seed)
+    trials: List[Trial] = []
+    for target in targets:
+        module, layer, role = target_site(target)
+        if role not in (ENC_TARGETS if module == "Encoder" else DEC_TARGETS):
+            continue                       # projection MatMuls (q, k, v, o ...) are not in the reference's target directories
+        for ftype in fault_models:
+            if ftype in ("INPUT16", "WEIGHT16") and role in ("ffn1", "ffn2"):
+                continue
+            operand = "input" if ftype.startswith("INPUT") else ("weight" if ftype.startswith("WEIGHT") else "output")
+            shape = _tensor_shape(module, role, operand, src_len, 1)
+            out_shape = _tensor_shape(module, role, "output", src_len, 1)
+            for bit_position in range(n_bits):
+                for _ in range(experiments):
+                    idx = [int(rng.integers(0, d)) for d in shape]
+                    ws, wl = 0, 0
+                    if ftype == "INPUT16":
+                        blocks = out_shape[3] // 16
+                        ws, wl = (16 * int(rng.integers(0, blocks)) if blocks else 0), 16
+                    elif ftype == "WEIGHT16":
+                        blocks = out_shape[2] // 16
+                        ws, wl = (16 * int(rng.integers(0, blocks)) if blocks else 0), int(rng.integers(1, 16))
+                    bit = int(rng.integers(0, 32)) if ftype == "RANDOM_BITFLIP" else bit_position
+                    trials.append(Trial(len(trials), int(rng.integers(0, n_sentences)), module, layer, role, target["target_layer"], ftype, bit,
+                                        int(np.ravel_multi_index(idx, shape)), ws, wl, int(rng.integers(0, 2 ** 32)) if ftype == "RANDOM" else 0))
+    return trials
+
+
 # ---------------------------------------------------------------------------------------------- BLEU (nltk method4)
 def sentence_bleu_method4(reference: Sequence[int], hypothesis: Sequence[int]) -> float:
     """nltk.translate.bleu_score.sentence_bleu([reference], hypothesis, smoothing_function=SmoothingFunction().method4)
@@ -208,7 +269,11 @@ def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials
     ids = torch.from_numpy(src_ids).to(dev)
     mask = torch.from_numpy(src_mask).to(dev)
     golden = engine.greedy_decode(ids, mask).cpu().numpy()
-    mine = trials[rank::world]
+    from .parallel import shard
+    mine = shard(trials, rank, world)
+    if csv_path and os.path.exists(csv_path + ".ids"):
+        done = {int(x) for x in open(csv_path + ".ids").read().split()}     # resume: skip the trial ids whose rows are already written
+        mine = [t for t in mine if t.trial_id not in done]
     out = []
     # Two batches in flight: while the GPU decodes batch i (one long persistent-decoder launch), the host classifies batch i-1 and
     # launches the encoder / fault step of batch i+1.  Nothing in the loop synchronises the stream: index and result buffers are
@@ -229,6 +294,8 @@ def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials
             if csv_path:
                 with open(csv_path, "a") as f:
                     f.write(csv_row(trial, res))
+                with open(csv_path + ".ids", "a") as f:
+                    f.write("%d\n" % trial.trial_id)
 
     pending = None
     for i, c0 in enumerate(range(0, len(mine), batch)):
@@ -254,7 +321,12 @@ def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials
 
 
 def main(argv=None):
-    """Same three flags as the reference (parallelized_inject_onnx_transformer.py:47-52) plus --gpus/--batch/--seed/--trials."""
+    """Same three flags as the reference (parallelized_inject_onnx_transformer.py:47-52): `--directory_name` is the directory of
+    fault-target JSON files (input/encoder, input/decoder), iterated x 6 fault models x 8 bit positions x 5 experiments exactly like
+    :794-861; `--module` Encoder | Decoder; `--experiment_output_name` the CSV.  When the directory does not exist (the reference's
+    input/ tree is not shipped with this package) the same descriptors are re-created from the graph (faults.targets_from_graph:
+    equal to the 60 reference files, tests/test_graph_executor.py).  Extra flags: --batch/--src-len/--seed, --trials N (cfg5: N random
+    trials from make_trials instead of the directory loop), one process per GPU under torchrun (trials sharded by rank)."""
     ap = argparse.ArgumentParser()
     ap.add_argument("--directory_name", default="input/encoder")
     ap.add_argument("--module", default="Encoder")
@@ -262,30 +334,50 @@ def main(argv=None):
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--src-len", type=int, default=64)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--trials", type=int, default=100)
+    ap.add_argument("--trials", type=int, default=0)
+    ap.add_argument("--experiments", type=int, default=5)
     args = ap.parse_args(argv)
     import torch
-    import torch.distributed as dist
+    from . import parallel as P
     from .engine import QuantizedTransformer
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    if world > 1:
-        dist.init_process_group("nccl")
-    eng = QuantizedTransformer(W.init_float_weights(args.seed))
+    rank, world, local_rank = P.rank_world()
+    torch.cuda.set_device(local_rank)
+    P.init_process_group()
+    fw = W.init_float_weights(args.seed)
+    eng = QuantizedTransformer(fw)
     ids, mask = W.synthetic_tokens(args.seed, args.batch, args.src_len)
-    trials = make_trials(args.trials, args.seed, args.batch, args.src_len, modules=(args.module,))
+    if args.trials > 0:
+        trials = make_trials(args.trials, args.seed, args.batch, args.src_len, modules=(args.module,))
+    else:
+        if os.path.isdir(args.directory_name):
+            targets = load_targets(args.directory_name)
+        else:
+            from . import faults
+            from . import graph as G
+            from .engine import _Linear  # noqa: F401  (the engine's weights are the graph's: same state_dict)
+            builder = G.build_encoder_graph if args.module == "Encoder" else G.build_decoder_graph
+            targets = faults.targets_from_graph(builder(_fake_quantized(fw), batch=1), args.module)
+        targets = [t for t in targets if t["module"].split("/")[0] == args.module]
+        trials = trials_from_targets(targets, args.seed, args.batch, args.src_len, experiments=args.experiments)
     os.makedirs(os.path.dirname(args.experiment_output_name) or ".", exist_ok=True)
     path = args.experiment_output_name if world == 1 else "%s.rank%d" % (args.experiment_output_name, rank)
     res = run_trials_batched(eng, ids, mask, trials, args.batch, path, rank, world)
-    if world > 1:
-        gathered = [None] * world
-        dist.all_gather_object(gathered, [(r["trial_id"], r["outcome"]) for r in res])
-        res_all = sorted(x for part in gathered for x in part)
-        dist.destroy_process_group()
-    else:
-        res_all = sorted((r["trial_id"], r["outcome"]) for r in res)
+    res_all = P.gather_records([(r["trial_id"], r["outcome"]) for r in res], world)
+    P.destroy_process_group()
     if rank == 0:
-        print(Counter(o for _, o in res_all))
+        print(len(trials), "trials", Counter(o for _, o in res_all))
+
+
+def _fake_quantized(float_weights):
+    """W8A8Linear.from_float on the host (quant_linear.py:122-147: stored weight = round(W/s)*s per output channel), the state the
+    reference's exported graphs hold -- numpy fp32 in the op order of the exporter, for the graph builder only."""
+    out = dict(float_weights)
+    f32 = np.float32
+    for k, v in float_weights.items():
+        if k.endswith(".weight") and v.ndim == 2 and (".linears." in k or ".feed_forward." in k):
+            s = (np.maximum(np.max(np.abs(v), axis=-1, keepdims=True), f32(1e-5)) / f32(127.0)).astype(f32)
+            out[k] = (np.rint((v / s).astype(f32)) * s).astype(f32)
+    return out
 
 
 if __name__ == "__main__":

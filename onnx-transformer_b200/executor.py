@@ -51,6 +51,43 @@ def save_graph(graph: Graph, path: str) -> None:
         np.savez(f, __meta__=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **arrays)
 
 
+def save_pt_archive(path: str, weight_dict, graph: Graph) -> None:
+    """`torch.save((weight_dict, graph), path)` as the reference writes its weights/{encoder,decoder}.pt
+    (parallelized_inject_onnx_transformer.py:540,621): tensors go out as numpy arrays, the graph as a plain dict."""
+    nodes = [dict(name=n.name, op_type=n.op_type, input=n.input, output=n.output,
+                  attribute=[dict(name=a.name, f=a.f, i=a.i, ints=a.ints) for a in n.attribute]) for n in graph.node]
+    meta = dict(name=graph.name, node=nodes, roles=graph.roles,
+                input=[dict(name=v.name, shape=list(v.shape), dtype=v.dtype) for v in graph.input],
+                output=[dict(name=v.name, shape=list(v.shape), dtype=v.dtype) for v in graph.output],
+                value_info=[v.name for v in graph.value_info], initializer=[i.name for i in graph.initializer])
+    arrays = {"init_%d" % k: i.array for k, i in enumerate(graph.initializer)}
+    wd = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in weight_dict.items()
+          if k not in (META_KEY, HOST_KEY)}
+    torch.save((wd, {"__ot_graph__": meta, "arrays": arrays}), path)
+
+
+def load_pt_archive(path: str):
+    """(weight_dict on the device, graph) from a `.pt` archive: this package's own or the reference's pickled
+    (weight_dict, onnx GraphProto) pair (onnx_reader.load_pt_archive: no `onnx` package needed)."""
+    from . import onnx_reader
+    wd, graph = onnx_reader.load_pt_archive(path)
+    weight_dict = {k: _to_device(v) for k, v in wd.items()}
+    weight_dict[HOST_KEY] = {i.name: np.array(i.array) for i in graph.initializer if np.asarray(i.array).size <= 64}
+    return weight_dict, graph
+
+
+def _graph_from_dict(meta: dict, arrays) -> Graph:
+    g = Graph(meta["name"])
+    g.node = [Node(n["name"], n["op_type"], list(n["input"]), list(n["output"]),
+                   [Attribute(a["name"], a["f"], a["i"], a["ints"]) for a in n["attribute"]]) for n in meta["node"]]
+    g.roles = meta.get("roles", {})
+    g.input = [ValueInfo(v["name"], tuple(v["shape"]), v["dtype"]) for v in meta["input"]]
+    g.output = [ValueInfo(v["name"], tuple(v["shape"]), v["dtype"]) for v in meta["output"]]
+    g.value_info = [ValueInfo(n, ()) for n in meta["value_info"]]
+    g.initializer = [Initializer(n, np.asarray(arrays["init_%d" % k])) for k, n in enumerate(meta["initializer"])]
+    return g
+
+
 def load_graph(path: str) -> Graph:
     with open(path, "rb") as f:
         z = np.load(io.BytesIO(f.read()))
@@ -73,6 +110,9 @@ def _as_graph(module_path_or_graph) -> Graph:
         if module_path_or_graph.endswith((".onnx", ".onnx.gz")):
             from . import onnx_reader
             return onnx_reader.load_onnx(module_path_or_graph)
+        if module_path_or_graph.endswith(".pt"):
+            from . import onnx_reader
+            return onnx_reader.load_pt_archive(module_path_or_graph)[1]
         return load_graph(module_path_or_graph)
     return module_path_or_graph
 

@@ -204,15 +204,25 @@ def _node(buf: bytes, constants: Dict[str, np.ndarray]) -> Node:
     return node
 
 
-def read_model(data: bytes, name: Optional[str] = None) -> Graph:
-    """ModelProto bytes -> Graph (nodes in file order, initializers as numpy arrays).  `Constant` nodes are kept in `.node`;
-    their tensors are available to `cleanup`."""
+def model_graph_bytes(data: bytes) -> bytes:
+    """The serialized GraphProto (ModelProto field 7) of a serialized ModelProto."""
     graph_buf = None
     for f, wt, v in _fields(data):
         if f == 7 and wt == 2:
             graph_buf = v
     if graph_buf is None:
         raise OnnxFormatError("no GraphProto (ModelProto field 7) in the file")
+    return graph_buf
+
+
+def read_model(data: bytes, name: Optional[str] = None) -> Graph:
+    """ModelProto bytes -> Graph (nodes in file order, initializers as numpy arrays).  `Constant` nodes are kept in `.node`;
+    their tensors are available to `cleanup`."""
+    return read_graph(model_graph_bytes(data), name)
+
+
+def read_graph(graph_buf: bytes, name: Optional[str] = None) -> Graph:
+    """Serialized GraphProto -> Graph."""
     g = Graph(name or "onnx")
     constants: Dict[str, np.ndarray] = {}
     for f, _, v in _fields(graph_buf):
@@ -261,3 +271,57 @@ def load_onnx(path: str, clean: bool = True) -> Graph:
         data = f.read()
     g = read_model(data)
     return cleanup(g) if clean else g
+
+
+# ---------------------------------------------------------------------------------------------- weights/{encoder,decoder}.pt
+class _GraphProtoStub:
+    """Stand-in for onnx.onnx_ml_pb2.GraphProto while un-pickling: protobuf messages pickle as (class, state) with
+    state = {"serialized": bytes}; the bytes are parsed by the wire reader above, so the `onnx` package is not needed."""
+
+    def __init__(self, *args, **kwargs):
+        self.graph = None
+
+    def __setstate__(self, state):
+        data = state["serialized"] if isinstance(state, dict) else state
+        self.graph = cleanup(read_graph(bytes(data)))
+
+
+def load_pt_archive(path: str):
+    """The reference's `weights/encoder.pt` / `weights/decoder.pt` (parallelized_inject_onnx_transformer.py:540,621,772-774:
+    `weight_dict, main_graph = torch.load(...)`, written by inject_operations.py:198 / onnx_optimized_inference.py with
+    `torch.save((module_weight_dict, module_graph), ...)`): a pickled (dict name -> numpy array, onnx GraphProto) pair.  Also reads
+    the archives this package writes (save_pt_archive).  Returns (weight_dict of numpy arrays, Graph)."""
+    import pickle
+
+    import torch
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.startswith("onnx") and name == "GraphProto":
+                return _GraphProtoStub
+            return super().find_class(module, name)
+
+    class _PickleModule:
+        __name__ = "ot_pickle"
+        Unpickler = _Unpickler
+        load = staticmethod(lambda f, **kw: _Unpickler(f, **kw).load())
+
+    obj = torch.load(path, map_location="cpu", pickle_module=_PickleModule, weights_only=False)
+    if not (isinstance(obj, (tuple, list)) and len(obj) == 2):
+        raise OnnxFormatError("%s: expected a (weight_dict, graph) pair" % path)
+    a, b = obj
+    if isinstance(a, dict):
+        weight_dict, graph = a, b
+    else:
+        weight_dict, graph = b, a          # inject_main.py:405 unpacks `weight_dict, main_graph`, older scripts the other way round
+    if isinstance(graph, _GraphProtoStub):
+        graph = graph.graph
+    elif isinstance(graph, dict) and "__ot_graph__" in graph:
+        from .executor import _graph_from_dict
+        graph = _graph_from_dict(graph["__ot_graph__"], graph["arrays"])
+    if not isinstance(graph, Graph):
+        raise OnnxFormatError("%s: the second element is not a graph (%s)" % (path, type(graph).__name__))
+    out = {}
+    for k, v in weight_dict.items():
+        out[k] = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+    return out, graph

@@ -127,3 +127,49 @@ def test_product_executor_runs_the_real_onnx_file():
         got, want = ex.to_numpy({name: wd[name]})[name], wd_o[name]
         assert got.shape == want.shape
         assert np.mean(got != want) < 2e-3 and np.max(np.abs(got - want)) <= 1.0, name
+
+
+def test_reference_pt_archive_without_the_onnx_package(tmp_path):
+    """weights/{encoder,decoder}.pt of the reference = torch.save((weight_dict, GraphProto)) (parallelized_inject_onnx_transformer.py:
+    540,621): the pickled protobuf message is (class onnx.onnx_ml_pb2.GraphProto, state {"serialized": bytes}); the loader swaps the
+    class for a stub that parses the bytes with the wire reader.  The archive is produced here from the genuine ONNX export fixture by
+    a fake `onnx.onnx_ml_pb2` module with exactly that pickle protocol."""
+    import gzip
+    import pickle
+    import sys
+    import types
+
+    import torch
+    from onnx_transformer_b200 import onnx_reader as R
+
+    data = gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_encoder_tiny.onnx.gz"), "rb").read()
+    graph_bytes = R.model_graph_bytes(data)
+    want = R.cleanup(R.read_graph(graph_bytes))
+
+    class GraphProto:                                     # pickles like a protobuf message: copyreg.__newobj__ + {"serialized": ...}
+        def __init__(self):
+            self.blob = b""
+
+        def __getstate__(self):
+            return {"serialized": self.blob}
+
+        def __setstate__(self, state):
+            self.blob = state["serialized"]
+
+    mod_onnx, mod_pb = types.ModuleType("onnx"), types.ModuleType("onnx.onnx_ml_pb2")
+    GraphProto.__module__, GraphProto.__qualname__ = "onnx.onnx_ml_pb2", "GraphProto"
+    mod_pb.GraphProto = GraphProto
+    sys.modules["onnx"], sys.modules["onnx.onnx_ml_pb2"] = mod_onnx, mod_pb
+    try:
+        msg = GraphProto()
+        msg.blob = graph_bytes
+        weight_dict = {i.name: i.array for i in want.initializer}
+        path = str(tmp_path / "encoder.pt")
+        torch.save((weight_dict, msg), path)
+    finally:
+        del sys.modules["onnx"], sys.modules["onnx.onnx_ml_pb2"]
+    wd, g = R.load_pt_archive(path)                        # `onnx` is not importable here
+    assert [n.name for n in g.node] == [n.name for n in want.node] and [n.op_type for n in g.node] == [n.op_type for n in want.node]
+    assert set(wd) == {i.name for i in want.initializer}
+    k = want.initializer[3].name
+    assert np.array_equal(wd[k], want.initializer[3].array)
