@@ -221,7 +221,7 @@ __device__ __forceinline__ Chunk chunk_of(int j) {
 }
 __device__ __forceinline__ int slice_rows(int g) { return g == 0 ? 192 : (g >= 4 ? 256 : 64); }
 
-// loader thread: load weight chunk c.pn into its ring slot (the slot must be free)
+// loader WARP (all lanes keep c.pn; one elected lane issues): load weight chunk c.pn into its ring slot (the slot must be free)
 __device__ __forceinline__ void issue_chunk(Ctx& c) {
   const uint32_t n = c.pn;
   const int slot = n % kSlots;
@@ -230,12 +230,15 @@ __device__ __forceinline__ void issue_chunk(Ctx& c) {
   const CUtensorMap* map = &c.G->map_w[l][k.g];
   const uint32_t fb = smem_u32(&c.bars[slot]);
   const uint32_t dst = smem_u32(c.smem + kSmRing + slot * kSlotBytes);
-  mbar_arrive_expect_tx(fb, k.bytes);
-  if (k.g == 5) tma_load_3d(dst, map, fb, 0, 256 * (c.rank & 1), 4 * (c.rank >> 1) + k.kb0);
-  else tma_load_3d(dst, map, fb, 0, slice_rows(k.g) * c.rank, k.kb0);
+  if (elect_one()) {
+    mbar_arrive_expect_tx(fb, k.bytes);
+    if (k.g == 5) tma_load_3d(dst, map, fb, 0, 256 * (c.rank & 1), 4 * (c.rank >> 1) + k.kb0);
+    else tma_load_3d(dst, map, fb, 0, slice_rows(k.g) * c.rank, k.kb0);
+  }
+  __syncwarp();
   ++c.pn;
 }
-// loader thread: issue every chunk below `upto` (chunk n reuses the slot of chunk n - kSlots, free once that chunk's MMAs have
+// loader warp: issue every chunk below `upto` (chunk n reuses the slot of chunk n - kSlots, free once that chunk's MMAs have
 // completed: the wait below).  Called at the start of every GEMM phase with upto = kSlots chunks past the GEMM's last one: no GEMM
 // has more than kSlots chunks, so every GEMM starts with all of its weights in flight or resident.
 __device__ __forceinline__ void fill_until(Ctx& c, uint32_t upto) {
@@ -276,33 +279,48 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend, 
   }
   // consumes 512 operand bytes + the scale per sentence; FFN2: 8 rows x 256 hidden bytes from me and from my split-K partner
   xwait(c, kBarG, next_gather_bytes, c.g_parity, true);
-  if (tid == kIssuer) {
-    fence_proxy_async_smem();      // operand rows were written through the generic proxy (shared memory only: the narrow fence)
+  // Issuer and loader are WHOLE warps that elect one lane around the tcgen05 / TMA instructions.  With `tid == kIssuer` (a branch
+  // ptxas cannot prove warp-uniform) every UTCIMMA was wrapped in an ELECT / 4 x R2UR.BROADCAST / BRA.U.ANY loop: ~100 cycles per
+  // instruction whatever its shape (the "floor" of profiles/r1_mma_shape_microbench.txt; tools/bench_mma2.cu, profiles/r2_mma_issue_microbench.txt);
+  // in a uniform region the MMAs issue back to back and cost what the tensor pipe needs.  All lanes keep the ring counters.
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  if (warp_u == kIssuer / 32) {
     const uint32_t abase = smem_u32(c.smem + (g == 5 ? kSmBh : kSmBx));
     const uint32_t idesc = make_idesc_i8(64, rows);
     const bool by_rows = (g == 0 || g >= 4);
     const int nchunks = (g >= 1 && g <= 3) ? 1 : 4;
     const int kb_base = (g == 5) ? 4 * (c.rank >> 1) : 0;
+    if (elect_one()) fence_proxy_async_smem();      // operand rows were written through the generic proxy (shared memory only: the narrow fence)
     for (int ch = 0; ch < nchunks; ++ch) {
       const int slot = c.cn % kSlots;
       mbar_wait(smem_u32(&c.bars[slot]), (c.cn / kSlots) & 1);
       tc_fence_after();
       const uint32_t sbase = smem_u32(c.smem + kSmRing + slot * kSlotBytes);
-      const int nkb = by_rows ? 1 : 4;              // k-blocks held by this chunk
-#pragma unroll 1
-      for (int i = 0; i < nkb; ++i) {
-        const int kb = by_rows ? ch : 4 * ch + i;
-        const uint64_t a_desc = make_smem_desc_sw128(abase + (kb_base + kb) * 1024);
-        const uint64_t b_desc = make_smem_desc_sw128(sbase + i * 8192);
+      if (elect_one()) {
+        if (by_rows) {
+          const uint64_t a_desc = make_smem_desc_sw128(abase + (kb_base + ch) * 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(sbase);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_i8_ss(c.tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            mma_i8_ss(c.tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc, (ch | k) != 0 ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {           // one chunk = 4 k-blocks of 64 weight rows
+            const uint64_t a_desc = make_smem_desc_sw128(abase + i * 1024);
+            const uint64_t b_desc = make_smem_desc_sw128(sbase + i * 8192);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_i8_ss(c.tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        mma_commit(smem_u32(&c.bars[kBarEmpty + slot]));
       }
-      mma_commit(smem_u32(&c.bars[kBarEmpty + slot]));
+      __syncwarp();
       ++c.cn;
     }
-    mma_commit(smem_u32(&c.bars[kBarAcc]));
-  } else if (tid == kLoader) {
+    if (elect_one()) mma_commit(smem_u32(&c.bars[kBarAcc]));
+    __syncwarp();
+  } else if (warp_u == kLoader / 32) {
     // Refill the ring WHILE this GEMM's MMAs run: a slot is reloaded as soon as the MMAs that read it have completed (its `empty`
     // barrier), so all but the last chunk of the refill streams in during the MMA window.  Measured: a 128 KB TMA burst issued
     // after the last MMA stalls every shared-memory load of the SM for ~0.9 us -- exactly when the epilogue and the next row
@@ -985,7 +1003,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   c.fine = false;
   c.mark_slot = 0;
   c.t_step = 0;
-  if (tid == kLoader) fill_until(c, kSlots);
+  if (__shfl_sync(0xffffffffu, warp, 0) == kLoader / 32) fill_until(c, kSlots);
   if (tid == 0 && n_steps > 0) {       // first use of the gather / scatter barriers (the first step reads its token from ys: no token exchange)
     mbar_arrive_expect_tx(smem_u32(&c.bars[kBarG]), static_cast<uint32_t>(c.n_own) * (kD + 4));
     if (c.b >= 0) mbar_arrive_expect_tx(smem_u32(&c.bars[kBarS]), 3 * kD * 4);
