@@ -9,8 +9,11 @@
 constexpr int kIters = 512, kChains = 8;
 
 template <int OP>
-__global__ void __launch_bounds__(512) k(float* out, int seed, long long* cycles) {
+__global__ void __launch_bounds__(512) k(float* out, int seed, long long* cycles, unsigned long long ka, unsigned long long kb) {
   float f[kChains];
+  unsigned long long d[kChains];
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) d[c] = ka + c + seed;
   int i[kChains];
   unsigned p = 0;
 #pragma unroll
@@ -37,13 +40,15 @@ __global__ void __launch_bounds__(512) k(float* out, int seed, long long* cycles
       if (OP == 13) f[c] = __fdiv_rn(f[c], 1.0001f + f[(c + 1) % kChains] * 1e-9f);   // IEEE division
       if (OP == 14) { __half2 h = __floats2half2_rn(f[c], f[(c + 1) % kChains]); i[c] ^= *reinterpret_cast<int*>(&h); f[c] += 1.0f; }   // F2F.F16x2 pack
       if (OP == 15) f[c] = __fmul_rn(__fmul_rn(f[c], 1.0001f), 0.9999f);         // 2 x FMUL
+      if (OP == 16) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(d[c]) : "l"(ka), "l"(kb));   // FFMA2: two fp32 FMAs per lane
+      if (OP == 17) f[c] = fmaxf(fmaxf(f[c], fabsf(f[(c + 1) % kChains])), fabsf(f[(c + 3) % kChains]));   // FMNMX3
     }
   }
   const long long t1 = clock64();
   float acc = 0.f;
   int iacc = p;
 #pragma unroll
-  for (int c = 0; c < kChains; ++c) { acc += f[c]; iacc += i[c]; }
+  for (int c = 0; c < kChains; ++c) { acc += f[c]; iacc += i[c] + static_cast<int>(d[c] >> 3); }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc + iacc;
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -54,8 +59,8 @@ void run(const char* name, float inst_per_chain_step) {
   long long* cyc;
   cudaMalloc(&out, 148 * 512 * 4);
   cudaMalloc(&cyc, 148 * 8);
-  k<OP><<<148, 512>>>(out, 1, cyc);
-  k<OP><<<148, 512>>>(out, 2, cyc);
+  k<OP><<<148, 512>>>(out, 1, cyc, 0x3F8000013F800001ull, 0x3F0000003F000000ull);
+  k<OP><<<148, 512>>>(out, 2, cyc, 0x3F8000013F800001ull, 0x3F0000003F000000ull);
   cudaDeviceSynchronize();
   long long h[148];
   cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
@@ -70,6 +75,8 @@ void run(const char* name, float inst_per_chain_step) {
 
 int main() {
   run<0>("FFMA", 1);
+  run<16>("FFMA2 (fma.rn.f32x2)", 1);
+  run<17>("FMNMX3", 1);
   run<1>("FADD", 1);
   run<15>("2 x FMUL", 2);
   run<2>("I2F.S32 + LOP + IADD", 3);
