@@ -261,55 +261,125 @@ def persistent_phase_trace(eng, ws, B, S, t_mid=35):
     return {k: round(float(v), 2) for k, v in out.items()}, float(total)
 
 
-def extra_measurements(eng, dev):
-    """Side measurements for the other BASELINE.json configs (not the headline): cfg3 encoder-only forward at B=512 x S=128 and
-    cfg5 fault-injection trials/s (golden decode cached, one faulty B=1 decode per trial)."""
+def gemm_roofline(dev, M=65536):
+    """The metric's second half, "int8 GEMM % peak": the four linear-layer GEMMs of one cfg3 encoder layer (M = 512 x 128 tokens), each
+    event-timed on the launching stream as REPS back-to-back launches after an L2 flush (one launch between two events would also time
+    the host's launch path while the GPU idles).  achieved = 2 M N K / t; peak = 4.5 POPS nominal dense int8 (tcgen05 kind::i8) -- the
+    issue-rate microbenchmark of this repo measures 128 x 256 x 32 MACs per 132.5 clk per SM = 4.6 POPS at 1965 MHz
+    (profiles/r2_mma_issue_microbench.txt); MEASURED_PEAKS.json has no int8 figure."""
+    import torch
+    from onnx_transformer_b200 import kernels as K
+    g = torch.Generator(device=dev).manual_seed(0)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    shapes = [("qkv_to_q8", 1536, 512, dict(out_kind=K.OUT_Q8, quant_group=512), False, "ot_gemm_wres.cu"),
+              ("o_to_f32_residual", 512, 512, dict(out_kind=K.OUT_F32), True, "ot_gemm_stream.cu"),
+              ("ffn1_relu_to_q8", 2048, 512, dict(out_kind=K.OUT_Q8, quant_group=2048, relu=True), False, "ot_gemm_wres.cu"),
+              ("ffn2_to_f32_residual", 512, 2048, dict(out_kind=K.OUT_F32), True, "ot_gemm_stream.cu")]
+    out, reps = {}, 4
+    for name, N, Kd, kw, res, src in shapes:
+        a = torch.randint(-127, 128, (M, Kd), dtype=torch.int8, device=dev, generator=g)
+        w = torch.randint(-127, 128, (N, Kd), dtype=torch.int8, device=dev, generator=g)
+        sx = torch.rand(M, device=dev, generator=g) * 0.05 + 1e-3
+        sw = torch.rand(N, device=dev, generator=g) * 0.01 + 1e-4
+        b = torch.randn(N, device=dev, generator=g)
+        r = torch.randn(M, N, device=dev, generator=g) if res else None
+        for _ in range(2):
+            K.linear_w8a8(a, w, row_scale=sx, col_scale=sw, bias=b, residual=r, **kw)
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                K.linear_w8a8(a, w, row_scale=sx, col_scale=sw, bias=b, residual=r, **kw)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1) * 1e3 / reps)
+        us = float(np.median(ts))
+        ops = 2.0 * M * N * Kd
+        nbytes = M * Kd + N * Kd + (M * N * (8 if res else 0)) + (M * N * (4 if kw["out_kind"] == K.OUT_F32 else 1))
+        out[name] = {"M": M, "N": N, "K": Kd, "us": us, "achieved_top_per_s": ops / us / 1e6, "frac_of_4.5_POPS": ops / us / 1e6 / 4500.0,
+                     "algorithmic_gb_per_s": nbytes / us / 1e3, "kernel": src}
+        del a, w, r
+    del flush
+    torch.cuda.empty_cache()
+    return {"peak_top_per_s": 4500.0, "peak_source": "nominal dense int8; measured MMA issue rate 4.6 POPS (profiles/r2_mma_issue_microbench.txt)",
+            "timing": "median of 5 groups of %d back-to-back launches, CUDA events, 512 MB L2 flush before each group" % reps, "gemm": out}
+
+
+def sharded_measurements(eng, dev, rank, world):
+    """The other sharded BASELINE.json configs at this N (every rank runs its shard; times are the MAX over ranks):
+    cfg3 -- encoder-only forward, 512 x 128 in total, sentences block-partitioned over the ranks (STRONG scaling);
+    cfg5 -- fault-injection trials/s, 2048 single-fault trials sharded by rank (64 trials per faulty batch decode)."""
     import torch
     from onnx_transformer_b200 import campaign as C
+    from onnx_transformer_b200 import parallel as P
     from onnx_transformer_b200 import weights as W
     out = {}
     ids_np, mask_np = W.synthetic_tokens(7, 512, 128)
-    ids, mask = torch.from_numpy(ids_np).to(dev), torch.from_numpy(mask_np).to(dev)
+    lo, hi = P.shard_rows(512, rank, world)
+    ids, mask = torch.from_numpy(ids_np[lo:hi]).to(dev), torch.from_numpy(mask_np[lo:hi]).to(dev)
     for _ in range(2):
         eng.encode(ids, mask)
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
+    P.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     reps = 5
     for _ in range(reps):
         eng.encode(ids, mask)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    torch.cuda.synchronize(dev)
+    ms = P.max_over_ranks([e0.elapsed_time(e1) / reps], device=dev)[0]
     tokens = 512 * 128
     ops = tokens * 37.75e6 + 6 * 2 * (512 * 8 * 128 * 128 * 64)          # SURVEY.md 8d: linears + QK^T, 2 ops per MAC
-    out["cfg3_encoder_only"] = {"batch": 512, "src_len": 128, "ms": ms, "tokens_per_s": tokens / (ms * 1e-3),
-                                "int8_top_per_s": ops / (ms * 1e-3) / 1e12, "frac_of_4.5_POPS": ops / (ms * 1e-3) / 4.5e15}
+    out["cfg3_encoder_only"] = {"batch_total": 512, "batch_per_gpu": hi - lo, "src_len": 128, "n_gpus": world, "scaling": "strong", "ms": ms,
+                                "tokens_per_s": tokens / (ms * 1e-3), "int8_top_per_s": ops / (ms * 1e-3) / 1e12,
+                                "frac_of_4.5_POPS_per_gpu": ops / (ms * 1e-3) / 4.5e15 / world}
     del ids, mask
     eng._enc_ws = {}
     torch.cuda.empty_cache()
     ids_np, mask_np = W.synthetic_tokens(11, 64, 64)
     trials = C.make_trials(2048, 0, 64, 64)
-    C.run_trials_batched(eng, ids_np, mask_np, trials[:64], 64)            # warm-up
-    torch.cuda.synchronize()
+    C.run_trials_batched(eng, ids_np, mask_np, trials[:64 * world], 64, None, rank, world)            # warm-up
+    torch.cuda.synchronize(dev)
+    P.barrier()
     t0 = time.perf_counter()
-    res = C.run_trials_batched(eng, ids_np, mask_np, trials, 64)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    res = C.run_trials_batched(eng, ids_np, mask_np, trials, 64, None, rank, world)
+    torch.cuda.synchronize(dev)
+    dt = P.max_over_ranks([time.perf_counter() - t0], device=dev)[0]
     from collections import Counter
-    # cfg4: same architecture with 4-bit weights (per-channel scale amax/8), batch 64 greedy decode
+    counts = Counter(r["outcome"] for r in res)
+    names = sorted(set(counts) | {"masked", "changed", "no-EOS"})
+    tot = P.sum_over_ranks([counts.get(k, 0) for k in names], device=dev)
+    out["cfg5_fault_injection"] = {"trials": len(trials), "n_gpus": world, "trials_per_s": len(trials) / dt,
+                                   "outcomes": {k: int(v) for k, v in zip(names, tot) if v},
+                                   "note": "wall clock, max over ranks, incl. one golden batch decode per rank; 64 trials per faulty greedy decode "
+                                           "(one fault per batch row); random-init weights never emit </s> (tests/test_fullsize_parity_gpu.py "
+                                           "pins the three outcome classes on an EOS-capable model)"}
+    return out
+
+
+def rank0_measurements(eng, dev):
+    """Single-GPU side measurements (rank 0): cfg4 (4-bit weights) batch decode and cfg1 (the drop-in executor driven like the
+    reference's greedy_decode: B = 1, S = 72, 71 full-prefix decoder passes)."""
+    import torch
+    from onnx_transformer_b200 import weights as W
+    out = {}
+    ids_np, mask_np = W.synthetic_tokens(11, 64, 64)
     try:
         eng4 = type(eng)(W.init_float_weights(0), n_layers=6, max_len=MAX_LEN, weight_bits=4)
         i4, m4 = torch.from_numpy(ids_np).to(dev), torch.from_numpy(mask_np).to(dev)
         for _ in range(2):
             eng4.greedy_decode(i4, m4)
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(3):
             eng4.greedy_decode(i4, m4)
         e1.record()
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(dev)
         ms4 = e0.elapsed_time(e1) / 3
         out["cfg4_int4_weights_decode"] = {"batch": 64, "src_len": 64, "ms": ms4, "tokens_per_s": 64 * (MAX_LEN - 1) / (ms4 * 1e-3),
                                            "note": "encoder / cross-K/V GEMMs unpack packed int4 in shared memory; the cluster decoder reads the int8 copy of the 4-bit values"}
@@ -317,9 +387,60 @@ def extra_measurements(eng, dev):
         torch.cuda.empty_cache()
     except Exception as exc:      # side measurement: never fail the headline line
         out["cfg4_int4_weights_decode"] = {"error": str(exc)[:200]}
-    out["cfg5_fault_injection"] = {"trials": len(trials), "trials_per_s": len(trials) / dt, "outcomes": dict(Counter(r["outcome"] for r in res)),
-                                   "note": "wall clock incl. one golden batch decode; 64 trials per faulty greedy decode (one fault per batch row)"}
+    try:
+        out["cfg1_executor_greedy_decode"] = cfg1_executor_decode(dev)
+    except Exception as exc:
+        out["cfg1_executor_greedy_decode"] = {"error": str(exc)[:300]}
     return out
+
+
+def cfg1_graphs(seed=0):
+    from onnx_transformer_b200 import campaign as C
+    from onnx_transformer_b200 import graph as G
+    from onnx_transformer_b200 import weights as W
+    fw = W.init_float_weights(seed)
+    w = C._fake_quantized(fw)
+    return fw, G.build_encoder_graph(w, batch=1, n_layers=6), G.build_decoder_graph(w, batch=1, n_layers=6)
+
+
+def cfg1_executor_decode(dev):
+    """BASELINE.json configs[0] on the GPU: greedy_decode of 8-bit_onnx_optimized_custom_inference.py:649-721 (prepare_inference ->
+    run_module("Encoder") -> 71 x run_module("Decoder") on the full prefix) through this package's drop-in executor, B = 1, S = 72."""
+    import torch
+    from onnx_transformer_b200 import decode as D
+    from onnx_transformer_b200 import executor as X
+    from onnx_transformer_b200 import weights as W
+    fw, enc, dec = cfg1_graphs()
+    model = D.HostModel(fw, device=dev)
+    ids, mask = W.synthetic_tokens(1000, 1, 72)
+    D.greedy_decode(model, ids, mask, 4, 0, enc, dec, executor=X)          # warm-up (3 decoder passes)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    timings = {}
+    ys = D.greedy_decode(model, ids, mask, MAX_LEN, 0, enc, dec, executor=X, timings=timings)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    steps = timings["decoder_step_s"]
+    return {"batch": 1, "src_len": 72, "greedy_steps": MAX_LEN - 1, "seconds": dt, "tokens_per_s": (MAX_LEN - 1) / dt,
+            "encoder_s": timings["encoder_s"], "decoder_pass_ms_first_last": [steps[0] * 1e3, steps[-1] * 1e3], "nodes_per_decoder_pass": len(dec.node),
+            "tokens_head": [int(t) for t in ys[0, :8].tolist()],
+            "note": "wall clock of the Python node walk (one libot_b200.so handler per ONNX node, full-prefix recompute as in the reference); "
+                    "the fused engine (value / e2e) is the fast path"}
+
+
+def cfg1_cpu_walk(steps=6):
+    """The reference's CPU executor restated (oracle node walk, ref-float = the reference's own float MatMuls) on cfg1: B = 1, S = 72,
+    first `steps` of the 71 full-prefix decoder passes (the early passes have the shortest prefixes: this over-states the CPU rate)."""
+    from onnx_transformer_b200 import weights as W
+    from oracle import executor as oe
+    fw, enc, dec = cfg1_graphs()
+    ids, mask = W.synthetic_tokens(1000, 1, 72)
+    timings = {}
+    t0 = time.perf_counter()
+    oe.greedy_decode(fw, enc, dec, ids, mask, steps + 1, 0, "ref-float", timings=timings)
+    dt = time.perf_counter() - t0
+    return {"batch": 1, "src_len": 72, "greedy_steps_timed": steps, "seconds": dt, "tokens_per_s": steps / dt, "encoder_s": timings.get("encoder_s"),
+            "sample": "oracle node walk (numpy, ref-float), first %d of 71 decoder passes" % steps}
 
 
 # ----------------------------------------------------------------------------------------------- main (GPU arm)
@@ -342,67 +463,68 @@ def main():
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     import torch
-    import torch.distributed as dist
     from onnx_transformer_b200 import kernels as K
+    from onnx_transformer_b200 import parallel as P
     from onnx_transformer_b200 import weights as W
     from onnx_transformer_b200.engine import QuantizedTransformer
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     args.warmup = max(args.warmup, 3)
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local_rank = P.rank_world()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    P.init_process_group("nccl")
     B, S = args.batch, args.src_len
     eng = QuantizedTransformer(W.init_float_weights(0), n_layers=6, max_len=MAX_LEN)
     ids_np, mask_np = W.synthetic_tokens(1000 + rank, B, S)          # each rank: its own shard of sentences
     ids, mask = torch.from_numpy(ids_np).to(dev), torch.from_numpy(mask_np).to(dev)
     ids_pin, mask_pin = torch.from_numpy(ids_np).pin_memory(), torch.from_numpy(mask_np).pin_memory()
     ys_pin = torch.empty((B, MAX_LEN), dtype=torch.int64).pin_memory()
-    gathered = torch.empty((world * B, MAX_LEN), dtype=torch.int64, device=dev) if world > 1 else None
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    # The path's only collective is the gather of the decoded ids.  The K batches of a run are independent, so they are gathered ONCE,
+    # after the last decode and inside its timed bracket (parallel.gather_token_ids): a gather after every decode made every rank wait
+    # for the slowest one K times (sum of per-step maxima instead of the maximum of the per-rank sums: 2 % at 8 GPUs in round 1).
+    ys_all = torch.empty((max(args.steps, args.warmup, 2) * B, MAX_LEN), dtype=torch.int64, device=dev)
 
-    def one_step():
+    def one_step(i, last):
         ys = eng.greedy_decode(ids, mask)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, ys)   # the path's only collective: result gather
+        ys_all[i * B:(i + 1) * B].copy_(ys)
+        if last and world > 1:
+            P.gather_token_ids(ys_all[:(i + 1) * B], world)
         return ys
 
-    def one_step_e2e():
+    def one_step_e2e(i, last):
         d_ids = ids_pin.to(dev, non_blocking=True)
         d_mask = mask_pin.to(dev, non_blocking=True)
         ys = eng.greedy_decode(d_ids, d_mask)
         ys_pin.copy_(ys, non_blocking=True)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, ys)
+        ys_all[i * B:(i + 1) * B].copy_(ys)
+        if last and world > 1:
+            P.gather_token_ids(ys_all[:(i + 1) * B], world)
         return ys
 
     def sync_all():
-        if world > 1:
-            dist.barrier()
+        P.barrier()
         torch.cuda.synchronize(dev)
 
     def timed_loop(fn, steps):
-        total_ms = 0.0
-        for _ in range(steps):
+        per_step = []
+        for i in range(steps):
             flush.zero_()                                # evict L2 between timed iterations (untimed)
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            fn(i, i == steps - 1)
             e1.record()
             torch.cuda.synchronize(dev)
-            total_ms += e0.elapsed_time(e1)
-        return total_ms
+            per_step.append(e0.elapsed_time(e1))
+        return per_step
 
     sampler = ClockSampler(local_rank)
     sampler.start()                                      # before the warm-up: nvidia-smi needs ~100 ms to deliver its first sample
-    for _ in range(args.warmup):
-        one_step()
+    for i in range(args.warmup):
+        one_step(i, i == args.warmup - 1)
     sync_all()
     ws = eng._dec_workspace(B, S)
     persistent = ws.get("plan") is not None
@@ -411,20 +533,20 @@ def main():
     l0, r0 = K._lib.launch_count(), eng.graph_replays
     sync_all()
     sampler.mark_begin()
-    total_ms = timed_loop(one_step, args.steps)
+    step_ms = timed_loop(one_step, args.steps)
+    total_ms = float(sum(step_ms))
     sync_all()
     launches = (K._lib.launch_count() - l0) + (eng.graph_replays - r0) * launches_per_graph
     clocks = sampler.stop()
     dec_events, eng.decoder_events = eng.decoder_events, None
-    for _ in range(2):                                   # the host-buffer path has its own first-call costs (allocations, pinned copies)
-        one_step_e2e()
+    for i in range(2):                                   # the host-buffer path has its own first-call costs (allocations, pinned copies)
+        one_step_e2e(i, i == 1)
     sync_all()
-    e2e_ms = timed_loop(one_step_e2e, args.steps)
+    e2e_step_ms = timed_loop(one_step_e2e, args.steps)
+    e2e_ms = float(sum(e2e_step_ms))
     sync_all()
-    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms = P.max_over_ranks([total_ms, e2e_ms], device=dev)      # a multi-GPU number is the slowest rank's
+    sharded = {} if args.no_extra else sharded_measurements(eng, dev, rank, world)
     tokens = world * B * (MAX_LEN - 1) * args.steps
     value = tokens / (total_ms * 1e-3)
     e2e_value = tokens / (e2e_ms * 1e-3)
@@ -469,33 +591,41 @@ def main():
                         "us_per_launch": fam[dom]["us_per_launch"], "launches_per_step": fam[dom]["launches_per_step"],
                         "algorithmic_bytes_per_launch": nbytes[dom], "greedy_step_us": step_us, "families_us_per_greedy_step": share,
                         "note": "M=64 decode GEMMs are latency-bound (weights L2-resident); see DESIGN.md 4/7"}
-        extra = {}
+        extra = dict(sharded)
+        gemm = None
         if not args.no_extra:
-            extra = extra_measurements(eng, dev)
+            extra.update(rank0_measurements(eng, dev))
+            if world == 1:
+                gemm = gemm_roofline(dev)
         cpu = None
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
+        if not args.no_cpu_baseline and world == 1:
+            cores = blas_threads(os.cpu_count() or 1)
             v, dt = cpu_reference_sample(16, S, 32)            # ~10-15 s of CPU work
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "oracle port (numpy ref-float, full-prefix recompute, %d BLAS threads): 16 sentences x %d src tokens, first 32 of 71 "
-                             "greedy steps, %.1f s" % (cores, S, dt)}
+                   "sample": "oracle port (numpy ref-float, full-prefix recompute, %d BLAS threads in effect): 16 sentences x %d src tokens, first 32 "
+                             "of 71 greedy steps, %.1f s -- a SAMPLE of cfg2 (early steps have the shortest prefixes: over-states the CPU rate)" % (cores, S, dt)}
+            if not args.no_extra:
+                try:
+                    cpu["cfg1_node_walk"] = cfg1_cpu_walk()
+                except Exception as exc:
+                    cpu["cfg1_node_walk"] = {"error": str(exc)[:200]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+                "ms_per_step": total_ms / args.steps, "ms_per_step_min_median_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
                 "data": "synthetic",
                 "config": {"workload": "cfg2: 8-bit Transformer-base greedy decode, batch 64 x src len 64 per GPU, 71 steps, KV cache",
                            "batch_per_gpu": B, "src_len": S, "greedy_steps": MAX_LEN - 1, "parallelism": "sentence-sharded x%d" % world,
-                           "l2": "512 MB flush between timed iterations"},
+                           "l2": "512 MB flush between timed iterations",
+                           "result_gather": "one NCCL all_gather of the K decoded batches inside the last step's timed bracket" if world > 1 else "none (1 GPU)"},
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes + mask_np.nbytes), "d2h_bytes_per_step": int(B * MAX_LEN * 8)},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes + mask_np.nbytes), "d2h_bytes_per_step": int(B * MAX_LEN * 8),
+                        "ms_per_step_min_median_max": [float(np.min(e2e_step_ms)), float(np.median(e2e_step_ms)), float(np.max(e2e_step_ms))]},
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_gemm": gemm, "cpu_baseline": cpu, "extra": extra}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    P.destroy_process_group()
     return 0
 
 

@@ -28,8 +28,29 @@ def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr())
 
 
+try:      # the raw stream handle of the current device: two C calls instead of torch.cuda.current_stream()'s Python stack (17 us per launch)
+    _raw_stream, _cur_device = torch._C._cuda_getCurrentRawStream, torch._C._cuda_getDevice
+except AttributeError:    # pragma: no cover  (older / newer torch without these entry points)
+    _raw_stream = _cur_device = None
+
+
 def _stream():
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(_cur_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _broadcast(a, b):
+    """numpy-style broadcast of two shapes (torch.broadcast_shapes goes through the symbolic-shape machinery: 35 us per call)."""
+    ra, rb = len(a), len(b)
+    out = []
+    for i in range(max(ra, rb)):
+        da = a[ra - 1 - i] if i < ra else 1
+        db = b[rb - 1 - i] if i < rb else 1
+        if da != db and da != 1 and db != 1:
+            raise OtError("shapes %s and %s do not broadcast" % (tuple(a), tuple(b)))
+        out.append(db if da == 1 else da)
+    return tuple(reversed(out))
 
 
 def _req(t: torch.Tensor, dtype, name: str):
@@ -418,7 +439,7 @@ def binary(op: str, a: torch.Tensor, b: torch.Tensor):
     _req(b, torch.float32, "b")
     a = a.contiguous()
     b = b.contiguous()
-    out_shape = torch.broadcast_shapes(a.shape, b.shape)
+    out_shape = _broadcast(tuple(a.shape), tuple(b.shape))
     out = torch.empty(out_shape, dtype=torch.float32, device=a.device)
     rank = len(out_shape)
     ash = (1,) * (rank - a.dim()) + tuple(a.shape)
@@ -462,7 +483,7 @@ def where_scalar(cond: torch.Tensor, a_scalar: float, x: torch.Tensor):
     if cond.dtype == torch.bool:
         cond = cond.view(torch.uint8)
     x = x.contiguous()
-    out_shape = torch.broadcast_shapes(cond.shape, x.shape)
+    out_shape = _broadcast(tuple(cond.shape), tuple(x.shape))
     if tuple(out_shape) != tuple(x.shape):
         raise OtError("Where: x must already have the broadcast shape")
     out = torch.empty_like(x)
@@ -514,7 +535,7 @@ def matmul_f32(a: torch.Tensor, b: torch.Tensor):
     M, K = a.shape[-2], a.shape[-1]
     K2, N = b.shape[-2], b.shape[-1]
     assert K == K2
-    batch_shape = torch.broadcast_shapes(a.shape[:-2], b.shape[:-2])
+    batch_shape = _broadcast(tuple(a.shape[:-2]), tuple(b.shape[:-2]))
     batch = 1
     for s in batch_shape:
         batch *= s
