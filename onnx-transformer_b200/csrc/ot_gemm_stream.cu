@@ -37,7 +37,9 @@ constexpr int kSMaxCl = 8;
 constexpr int kSBarOff = kSStages * (kSA + kSB);                 // full[4] empty[4] tfull[2] tempty[2] xbar[2] + tmem slot
 constexpr int kSColOff = kSBarOff + 256;                         // float [16 warps][2 buffers][cs 64 | bias 64]
 constexpr int kSRowmaxOff = kSColOff + kSEpiWarps * 2 * 2 * kSColsPerWarp * 4;   // float rowmax[2][4*kSMaxCl][128]
-constexpr int kSSmem = kSRowmaxOff + 2 * 4 * kSMaxCl * 128 * 4 + 1024;
+constexpr int kSStageOff = kSRowmaxOff;                           // fp32 output: per-warp staging block [32 rows][128 B] x 16 warps (aliases rowmax)
+constexpr int kSSmem = kSRowmaxOff + 64 * 1024 + 1024;
+static_assert(2 * 4 * kSMaxCl * 128 * 4 <= 64 * 1024 && kSEpiWarps * 4096 <= 64 * 1024 && kSSmem <= 232448, "shared memory budget");
 
 struct StreamArgs {
   int M, N, K;
@@ -220,57 +222,69 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSBN + cq * kSColsPerWarp;
 
       if (!Q8) {
-        // ---- fp32 output.  These GEMMs are HBM-bound on the fp32 residual + output: the residual of two 16-column chunks (128 B per
-        // thread, 64 KB per SM) is always in flight, requested before the accumulator is waited for.
-        const bool has_res = g.residual != nullptr && row_ok;
-        float* orow = reinterpret_cast<float*>(g.out) + static_cast<int64_t>(row) * g.ldo + col0;
-        const float4* rrow = reinterpret_cast<const float4*>(g.residual + static_cast<int64_t>(has_res ? row : 0) * g.ldr + col0);
-        float4 res[4][4];
-        uint32_t r[4][16];
+        // ---- fp32 output (+ residual).  These GEMMs are bound by the memory path of the epilogue, not by the MMAs: with one thread
+        // per row, every 16-byte load / store instruction of a warp touched 32 different lines (profiles/r2_ncu_gemm_cfg3.txt: issue
+        // 13 %, DRAM 32 %).  Here a warp stages 32 rows x 32 columns of y in shared memory (thread = row, 16-byte chunks XOR-swizzled by
+        // the row) and reads them back transposed -- 8 lanes per row -- so that the residual loads and the output stores are full
+        // 128-byte lines, 4 lines per instruction.  The residual is added in the transposed domain (same fadd, same operands).
+        const bool has_res = g.residual != nullptr;
+        uint8_t* wst = smem + kSStageOff + e * 4096;
+        const int trow = lane >> 3, tch = lane & 7;                   // transposed role: row 4i + trow of the warp's 32, 16-byte chunk tch
+        const int row0 = m_tile * kSBM + quarter * 32;                // first row of this warp
+        float4 res[8];
+        auto load_res = [&](int blk) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-          if (has_res) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) res[c][j] = __ldg(rrow + 4 * c + j);
+          for (int i = 0; i < 8; ++i) {
+            const int grow = row0 + 4 * i + trow;
+            if (has_res && grow < g.M) res[i] = __ldg(reinterpret_cast<const float4*>(g.residual + static_cast<int64_t>(grow) * g.ldr + col0 + 32 * blk) + tch);
           }
+        };
+        load_res(0);                                                  // in flight before the accumulator is waited for
         mbar_wait(smem_u32(&tfull_bar[buf]), par);
         tc_fence_after();
-        tmem_ld_32x16(taddr, r[0]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int blk = 0; blk < 2; ++blk) {
+          uint32_t r[2][16];
+          tmem_ld_32x16(taddr + 32 * blk, r[0]);
+          tmem_ld_32x16(taddr + 32 * blk + 16, r[1]);
           tmem_wait_ld();
-          if (c + 1 < 4) tmem_ld_32x16(taddr + 16 * (c + 1), r[c + 1]);
-          if (c == 3) {
+          if (blk == 1) {
             // the whole accumulator slice is in registers: the MMAs of the tile after next may overwrite it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
           }
-          float y[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 c4 = *reinterpret_cast<const float4*>(cs + 16 * c + 4 * j);
-            const float4 b4 = *reinterpret_cast<const float4*>(bs + 16 * c + 4 * j);
-            const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-            const float rv[4] = {res[c][j].x, res[c][j].y, res[c][j].z, res[c][j].w};
+          for (int c = 0; c < 2; ++c) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              float v = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[c][4 * j + b])), sx), cv[b]);
-              const float vb = __fadd_rn(v, bv[b]);
-              v = has_bias ? vb : v;
-              const float vr = fmaxf(v, 0.0f);
-              v = relu ? vr : v;
-              y[4 * j + b] = has_res ? __fadd_rn(rv[b], v) : v;
+            for (int j = 0; j < 4; ++j) {
+              const float4 c4 = *reinterpret_cast<const float4*>(cs + 32 * blk + 16 * c + 4 * j);
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + 32 * blk + 16 * c + 4 * j);
+              const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+              float y[4];
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                float v = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[c][4 * j + b])), sx), cv[b]);
+                const float vb = __fadd_rn(v, bv[b]);
+                v = has_bias ? vb : v;
+                const float vr = fmaxf(v, 0.0f);
+                y[b] = relu ? vr : v;
+              }
+              *reinterpret_cast<float4*>(wst + lane * 128 + (((4 * c + j) ^ (lane & 7)) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
             }
           }
-          if (c + 2 < 4 && has_res) {
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) res[c + 2][j] = __ldg(rrow + 4 * (c + 2) + j);
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + trow, grow = row0 + rr;
+            float4 v = *reinterpret_cast<const float4*>(wst + rr * 128 + ((tch ^ (rr & 7)) << 4));
+            if (grow < g.M) {
+              if (has_res) v = make_float4(__fadd_rn(res[i].x, v.x), __fadd_rn(res[i].y, v.y), __fadd_rn(res[i].z, v.z), __fadd_rn(res[i].w, v.w));
+              reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<int64_t>(grow) * g.ldo + col0 + 32 * blk)[tch] = v;
+            }
           }
-          if (row_ok) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(orow + 16 * c)[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-          }
+          if (blk == 0) load_res(1);
+          __syncwarp();                                               // the staging block is rewritten by the next column block / tile
         }
       } else {
         if (e == 0 && lane == 0) strace(g, li, 0);
