@@ -575,7 +575,7 @@ static int launch_attention(const AttnArgs& a, int tk_max, cudaStream_t stream) 
 
 OT_DEFINE_TL_SETTER(tl_set_attention)
 
-int launch_attention_tc(const AttnArgs& a, cudaStream_t stream);   // ot_attention_tc.cu
+int launch_attention_tc(const AttnArgs& a, cudaStream_t stream, bool* fused_q);   // ot_attention_tc.cu
 
 }  // namespace ot
 
@@ -638,12 +638,14 @@ extern "C" int ot_attention_q8_mf(const int8_t* q, int64_t ldq, const float* sq,
     return OT_OK;
   }
   // encoder-size blocks (32 <= Tq <= 128, Tk <= 128), faulty or not: tensor-core kernel, one CTA per (sentence, head); the merged rows
-  // are complete only across the 8 head CTAs, so the RowQuant for the O-projection is a second launch
+  // are complete only across the 8 head CTAs, so the RowQuant for the O-projection is a second launch (or, without an fp32 context
+  // buffer / with OT_ATTN_FUSE_Q=1, a cluster exchange inside the kernel: slower, see ot_attention_tc.cu)
   {
-    const int rc = launch_attention_tc(a, s);
+    bool fused_q = false;
+    const int rc = launch_attention_tc(a, s, &fused_q);
     if (rc < 0) return rc;
     if (rc == 0) {
-      if (ctx_q != nullptr) return ot_rowquant(ctx, ld_ctx, static_cast<int64_t>(B) * Tq, kDm, kDm, ctx_q, ctx_s, nullptr, stream);
+      if (ctx_q != nullptr && !fused_q) return ot_rowquant(ctx, ld_ctx, static_cast<int64_t>(B) * Tq, kDm, kDm, ctx_q, ctx_s, nullptr, stream);
       return OT_OK;
     }
   }

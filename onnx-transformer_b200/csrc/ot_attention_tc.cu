@@ -14,6 +14,11 @@
 //        ctx[i, d] = (sum_j pq[i,j] * vhat[j,d]) / 127
 //      The V scale sits on the contraction axis (per key), so this product cannot be an int8 GEMM; the hi/lo split
 //      keeps it in the float tolerance class (observed max relative error vs the float64 oracle ~1e-6, tests/test_kernels_gpu.py).
+//   5. optional (OT_ATTN_FUSE_Q=1), with ctx_q requested: the RowQuant of the MERGED row (all 8 heads) inside this kernel -- the 8 head
+//      CTAs of a sentence form a thread-block cluster, exchange their per-row abs-maxima by st.async + mbarrier complete_tx, derive
+//      the same scale and write their 64 int8 bytes per row (rowquant_kernel's arithmetic: quant_scale_x + quant4_pack).  Measured
+//      at cfg3 (tools/bench_attention.py): 244 us fused vs 188 us + 35 us for the separate rowquant_kernel launch -- a cluster of 8
+//      needs 8 free CTA slots of one GPC at once and every CTA ends waiting for its slowest peer -- so the default stays two launches.
 //   Fault hooks (App. D) are integer-exact patches of the affected scores / additive fp32 patches of the affected context elements,
 //   so a fault-free element of a faulty launch is bit-identical to the golden launch (same kernel, same data).
 // Replaces attention_heads_kernel (dp4a + fp32 FMA on CUDA cores: 700 us per cfg3 layer, profiles/r1_ncu_encoder_cfg3_layer.txt).
@@ -23,13 +28,16 @@
 #include "ot_attention_decode.cuh"
 #include "ot_common.h"
 #include "ot_ptx.cuh"
+#include "ot_rowmath.cuh"
 
 namespace ot {
 
 constexpr int kTcThreads = 128;
 constexpr int kTcOffQ = 0, kTcOffK = 16384, kTcOffVhi = 32768, kTcOffVlo = 49152;
 constexpr int kTcOffSk = 65536, kTcOffSv = kTcOffSk + 512, kTcOffKeep = kTcOffSv + 512, kTcOffRed = kTcOffKeep + 128, kTcOffBar = kTcOffRed + 32;
-constexpr int kTcSmem = kTcOffBar + 64 + 1024;
+constexpr int kTcOffRq = kTcOffBar + 64;               // float [8 heads][128 rows]: per-head abs-maxima of the merged context rows (written by the cluster)
+constexpr int kTcSmem = kTcOffRq + 8 * 128 * 4 + 1024;
+static_assert(3 * (kTcSmem + 1024) <= 233472, "three CTAs per SM");
 
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -55,6 +63,9 @@ __device__ __forceinline__ void tc_tmem_st_32x16(uint32_t taddr, const uint32_t 
 }
 __device__ __forceinline__ void tc_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tc_st_async_f32(uint32_t addr, float v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)), "r"(mbar) : "memory");
+}
 __device__ __forceinline__ float tc_patch_f32(const OtFault& f, float v) {
   uint32_t bits = __float_as_uint(v);
   if (f.mode == OT_FAULT_RANDOM_BITFLIP) bits ^= (1u << f.bit);
@@ -82,9 +93,12 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
   uint8_t* keep = smem + kTcOffKeep;
   float* sred = reinterpret_cast<float*>(smem + kTcOffRed);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcOffBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);       // bars: 0 scores done, 1 context done, 2 row maxima of the 8 heads
+  float* rq = reinterpret_cast<float*>(smem + kTcOffRq);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);              // warp-uniform for the compiler (tcgen05 / elect regions)
+  const bool fuse_q = a.ctx_q != nullptr;                              // only when launched as clusters of the 8 head CTAs of a sentence
   const int h = blockIdx.x, b = blockIdx.y;
   const int Tq = a.Tq, Tk = a.Tk;
   const int Tkp = (Tk + 15) & ~15;
@@ -93,12 +107,15 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
     if (elect_one()) {
       mbar_init(smem_u32(&bars[0]), 1);
       mbar_init(smem_u32(&bars[1]), 1);
+      mbar_init(smem_u32(&bars[2]), 1);
+      if (fuse_q) mbar_arrive_expect_tx(smem_u32(&bars[2]), kHeads * 128 * 4);
       fence_mbar_init();
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), 128);
     tmem_relinquish();
   }
+  if (fuse_q) cluster_arrive_release();      // waited for just before the exchange at the very end: every peer's barrier is armed by then
   pdl_wait();
   pdl_trigger();
 
@@ -231,15 +248,17 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
   __syncthreads();
 
   // ---- scores: S[i, j] = sum_d Q[i, d] K[j, d], exact int32
-  if (tid == 0) {
-    const uint32_t idesc = make_idesc_i8(128, Tkp);
-    const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sQ));
-    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sK));
-    mma_i8_ss(tmem_base, a_desc, b_desc, idesc, 0u);
-    mma_i8_ss(tmem_base, a_desc + 2, b_desc + 2, idesc, 1u);
-    mma_commit(smem_u32(&bars[0]));
+  if (warp == 0) {            // a warp-uniform branch + elect: ptxas wraps every UTCxMMA of a `tid == 0` branch in an ELECT / R2UR / BRA.U.ANY loop
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_i8(128, Tkp);
+      const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sQ));
+      const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sK));
+      mma_i8_ss(tmem_base, a_desc, b_desc, idesc, 0u);
+      mma_i8_ss(tmem_base, a_desc + 2, b_desc + 2, idesc, 1u);
+      mma_commit(smem_u32(&bars[0]));
+    }
+    __syncwarp();
   }
-  __syncwarp();
   mbar_wait(smem_u32(&bars[0]), 0);
   tc_fence_after();
 
@@ -353,38 +372,48 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
   __syncthreads();
 
   // ---- context: ctx[i, d] = sum_j pq[i, j] (Vhi + Vlo)[d, j]   (fp32 accumulation, over the score columns that are no longer needed)
-  if (tid == 0) {
-    tc_fence_after();
-    const uint32_t idesc = make_idesc_f16(128, 64);
-    const int ksteps = Tkp >> 4;                               // 16 keys (32 bytes of K) per instruction
-    uint32_t acc = 0u;
-    for (int part = 0; part < 2; ++part) {
-      const uint8_t* vt = part == 0 ? sVhi : sVlo;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int kb = ks >> 2, kk = ks & 3;
-        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sP + kb * 16384)) + static_cast<uint64_t>(kk * 2);
-        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(vt + kb * 8192)) + static_cast<uint64_t>(kk * 2);
-        mma_f16_ss(tmem_base, a_desc, b_desc, idesc, acc);
-        acc = 1u;
+  if (warp == 0) {
+    if (elect_one()) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_f16(128, 64);
+      const int ksteps = Tkp >> 4;                               // 16 keys (32 bytes of K) per instruction
+      uint32_t acc = 0u;
+      for (int part = 0; part < 2; ++part) {
+        const uint8_t* vt = part == 0 ? sVhi : sVlo;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int kb = ks >> 2, kk = ks & 3;
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sP + kb * 16384)) + static_cast<uint64_t>(kk * 2);
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(vt + kb * 8192)) + static_cast<uint64_t>(kk * 2);
+          mma_f16_ss(tmem_base, a_desc, b_desc, idesc, acc);
+          acc = 1u;
+        }
       }
+      mma_commit(smem_u32(&bars[1]));
     }
-    mma_commit(smem_u32(&bars[1]));
+    __syncwarp();
   }
-  __syncwarp();
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
 
+  // ---- epilogue: thread = query row i, the head's 64 context features, 16 at a time in ROLLED loops (three CTAs at different phases
+  //      share the instruction cache: the unrolled form of this kernel stalled on instruction fetch).  With the fused RowQuant the
+  //      finished values wait in their own TMEM columns (tcgen05.st) for the row maximum of the other heads.
+  float amax = 0.f;
   if (wactive) {
-    uint32_t r[4][16];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld_32x16(taddr + 16 * c, r[c]);
-    tmem_wait_ld();
-    float* orow = a.ctx + (static_cast<int64_t>(b) * Tq + i) * a.ld_ctx + h * kDk;
-#pragma unroll
+    float* orow = a.ctx != nullptr ? a.ctx + (static_cast<int64_t>(b) * Tq + i) * a.ld_ctx + h * kDk : nullptr;
+    uint32_t r[16];
+#pragma unroll 1
     for (int c = 0; c < 4; ++c) {
+      tmem_ld_32x16(taddr + 16 * c, r);
+      tmem_wait_ld();
       float y[16];
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) y[jj] = __fdiv_rn(__fmul_rn(__uint_as_float(r[c][jj]), vinv), 127.0f);
+      for (int jj = 0; jj < 16; ++jj) {
+        // (acc * 2^-p) / 127 with the division as its exact FMA equivalent on the magnitude (div127_exact; the IEEE division
+        // takes its slow path for every zero dividend)
+        const float x = __fmul_rn(__uint_as_float(r[jj]), vinv);
+        y[jj] = copysignf(div127_exact(fabsf(x)), x);
+      }
       if (FAULT && fault_here && row_ok) {
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
@@ -403,11 +432,52 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
           }
         }
       }
-      if (row_ok) {
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        amax = fmaxf(amax, fabsf(y[jj]));
+        r[jj] = __float_as_uint(y[jj]);
+      }
+      if (fuse_q) {
+        tc_tmem_st_32x16(taddr + 16 * c, r);
+        tc_tmem_wait_st();
+      }
+      if (orow != nullptr && row_ok) {
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
           reinterpret_cast<float4*>(orow + 16 * c)[q4] = make_float4(y[4 * q4], y[4 * q4 + 1], y[4 * q4 + 2], y[4 * q4 + 3]);
       }
+    }
+  }
+  if (fuse_q) {
+    // ---- RowQuant of the merged context row: this head's abs-max of every row to the 8 head CTAs of the sentence (cluster)
+    if (!row_ok) amax = 0.f;
+    cluster_wait_acquire();                                  // (arrived at kernel start) every peer's barrier is armed
+    {
+      const uint32_t slot = smem_u32(rq + h * 128 + i), qb = smem_u32(&bars[2]);
+#pragma unroll
+      for (int peer = 0; peer < kHeads; ++peer) tc_st_async_f32(mapa_shared(slot, peer), amax, mapa_shared(qb, peer));
+    }
+    mbar_wait(smem_u32(&bars[2]), 0);
+    float rmax = 0.f;
+#pragma unroll
+    for (int p = 0; p < kHeads; ++p) rmax = fmaxf(rmax, rq[p * 128 + i]);
+    if (wactive) {
+      const float s = quant_scale_x(rmax);
+      const float s_rcp = __frcp_rn(s);
+      uint4* qrow = reinterpret_cast<uint4*>(a.ctx_q + (static_cast<int64_t>(b) * Tq + i) * kDm + h * kDk);
+      uint32_t r[16];
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_32x16(taddr + 16 * c, r);
+        tmem_wait_ld();
+        uint32_t w[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          w[q4] = quant4_pack(make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]), __uint_as_float(r[4 * q4 + 2]),
+                                          __uint_as_float(r[4 * q4 + 3])), s, s_rcp);
+        if (row_ok) qrow[c] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      if (row_ok && h == 0) a.ctx_s[static_cast<int64_t>(b) * Tq + i] = s;
     }
   }
   tc_fence_before();
@@ -416,10 +486,17 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
 }
 
 // Launch for (B x 8) heads; returns 1 when the shape does not qualify (the caller falls back to the CUDA-core kernels).
-int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
+// Returns 0 on success, 1 when the shape does not qualify (the caller falls back to the CUDA-core kernels), < 0 on error.  *fused_q is set
+// when the kernel quantized the merged rows itself (ctx_q / ctx_s written); otherwise the caller runs rowquant_kernel on the fp32 context.
+int launch_attention_tc(const AttnArgs& a0, cudaStream_t stream, bool* fused_q) {
+  *fused_q = false;
   const char* env = getenv("OT_ATTN_TC");
   if (env && atoi(env) == 0) return 1;
-  if (a.Tq < 32 || a.Tq > 128 || a.Tk < 1 || a.Tk > 128 || a.ctx == nullptr || a.k_new != nullptr || a.step_dev != nullptr) return 1;
+  AttnArgs a = a0;
+  if (a.Tq < 32 || a.Tq > 128 || a.Tk < 1 || a.Tk > 128 || (a.ctx == nullptr && a.ctx_q == nullptr) || a.k_new != nullptr || a.step_dev != nullptr) return 1;
+  const char* fenv = getenv("OT_ATTN_FUSE_Q");
+  const bool fuse = a.ctx_q != nullptr && (a.ctx == nullptr || (fenv && atoi(fenv) != 0));
+  if (!fuse) a.ctx_q = nullptr;        // the kernel fuses the RowQuant exactly when it sees ctx_q
   const bool faulty = a.fault.mode != OT_FAULT_NONE || a.mf_unit != nullptr;
   auto kernel = faulty ? attention_tc_kernel<true> : attention_tc_kernel<false>;
   static bool configured[2] = {false, false};
@@ -427,8 +504,10 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
     OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
     configured[faulty ? 1 : 0] = true;
   }
-  OT_CHECK_CUDA(launch_kernel(kernel, dim3(kHeads, a.B), dim3(kTcThreads), kTcSmem, stream, 1, a));
+  // with the fused RowQuant the 8 head CTAs of a sentence are one thread-block cluster (they exchange the row maxima)
+  OT_CHECK_CUDA(launch_kernel(kernel, dim3(kHeads, a.B), dim3(kTcThreads), kTcSmem, stream, fuse ? kHeads : 1, a));
   count_launch();
+  *fused_q = fuse;
   return OT_OK;
 }
 

@@ -302,6 +302,8 @@ def attention_q8(q, sq, k, v, sk, sv, *, B, Tq, Tk, Tk_cap=None, ldq=None, sq_st
     dev = q.device
     if want_ctx and ctx is None:
         ctx = torch.empty((B * Tq, 512), dtype=torch.float32, device=dev)
+    if not want_ctx:
+        ctx = None
     if want_q and ctx_q is None:
         ctx_q = torch.empty((B * Tq, 512), dtype=torch.int8, device=dev)
         ctx_s = torch.empty((B * Tq,), dtype=torch.float32, device=dev)

@@ -437,3 +437,21 @@ def test_elementwise_family(K):
     np.testing.assert_allclose(K.matmul_f32(dev(a), dev(b)).cpu().numpy(), a @ b, rtol=1e-4, atol=1e-4)
     w = rng.normal(size=(64, 20)).astype(np.float32)
     np.testing.assert_allclose(K.matmul_f32(dev(a), dev(w)).cpu().numpy(), a @ w, rtol=1e-4, atol=1e-4)
+
+
+def test_attention_tc_fused_rowquant_equals_two_launches(K):
+    """ot_attention_tc.cu with the RowQuant of the merged rows inside (cluster of the 8 head CTAs; taken when no fp32 context buffer is
+    passed) against the default two-launch path (fp32 context + rowquant_kernel): int8 rows and scales bit for bit, ragged lengths."""
+    rng = np.random.default_rng(77)
+    for B, S in ((3, 128), (2, 41)):
+        M = B * S
+        qkv = dev(rng.integers(-127, 128, size=(M, 1536), dtype=np.int8))
+        sqkv = dev(rng.uniform(1e-3, 2e-2, size=(M, 3)).astype(np.float32))
+        mask = np.ones((B, S), dtype=np.uint8)
+        mask[:, S - 5:] = 0
+        mask = dev(mask)
+        kw = dict(B=B, Tq=S, Tk=S, ldq=1536, sq_stride=3, ldk=1536, skv_stride=3, mask_kind=1, key_mask=mask, mask_stride=S)
+        args = (qkv, sqkv, qkv[:, 512:], qkv[:, 1024:], sqkv[:, 1:], sqkv[:, 2:])
+        _, q2, s2, _ = K.attention_q8(*args, want_ctx=True, want_q=True, **kw)
+        _, q1, s1, _ = K.attention_q8(*args, want_ctx=False, want_q=True, **kw)
+        assert torch.equal(q1, q2) and torch.equal(s1.view(torch.int32), s2.view(torch.int32))
