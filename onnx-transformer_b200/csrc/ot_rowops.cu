@@ -2,6 +2,8 @@
 // greedy-loop token append.  One warp per row, 128-bit coalesced accesses, warp-shuffle reductions.
 // fp32 op order follows SURVEY.md App. A (the order of the ops the reference exports); compiled with
 // -fmad=false, explicit *_rn intrinsics where the order matters for bit-exact integer results.
+#include <stdlib.h>
+
 #include "ot_common.h"
 #include "ot_rowmath.cuh"
 
@@ -41,6 +43,127 @@ __global__ void __launch_bounds__(256) layernorm_quant_kernel(const float* __res
     if (lane == 0) s_out[row] = s;
   }
   tl_mark(tl, 3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm + RowQuant of 512-feature rows at encoder sizes (rows >= 2048, int8 output only): the same op order as layernorm_row /
+// quant4_pack, two columns per instruction (fma.rn.f32x2) and without the IEEE divisions -- x / d and y / s are computed as
+// q0 = x * RN(1/d) followed by two FMA residual steps, which is RN(x / d) bit for bit for |x|, d in [1e-18, 1e18] (zero dividends
+// included; tools/check_div_exact.c and the LayerNorm-range run quoted in DESIGN.md 9).  The general kernel spent ~26 instructions
+// per element (10 of them in div.rn, 9 in the flagged quotient of the quantizer) and was instruction-bound at 36 % of the HBM rate.
+// Rows whose scale or deviation leaves that range (or is not finite) take layernorm_row / quant4_pack: same results by construction.
+// The neutral operands {-0,-0}, {1,1}, {1.5*2^23 x 2} arrive as kernel ARGUMENTS: ptxas folds literal ones (fma(x, y, -0) -> mul,
+// fma(x, 1, b) -> add) and then contracts mul + add into one FFMA2, whatever -fmad says.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t ln_pack2(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 ln_unpack2(f2_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f2_t ln_fma2(f2_t a, f2_t b, f2_t c) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+__global__ void __launch_bounds__(256) layernorm_quant512_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, int64_t rows, float eps,
+                                                                 int8_t* __restrict__ q_out, float* __restrict__ s_out,
+                                                                 const f2_t k_neg0, const f2_t k_one, const f2_t k_magic) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * 512);
+  float4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __ldg(xr + i * 32 + lane);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mu = __fmul_rn(warp_sum(sum), 0.001953125f);
+  const f2_t nmu2 = ln_pack2(-mu, -mu);
+  f2_t d[8];                                           // x - mu, pairs (x, y) and (z, w) of the 4 float4
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    d[2 * i] = ln_fma2(ln_pack2(v[i].x, v[i].y), k_one, nmu2);
+    d[2 * i + 1] = ln_fma2(ln_pack2(v[i].z, v[i].w), k_one, nmu2);
+    const float2 a = ln_unpack2(ln_fma2(d[2 * i], d[2 * i], k_neg0)), c = ln_unpack2(ln_fma2(d[2 * i + 1], d[2 * i + 1], k_neg0));
+    sq += (a.x + a.y) + (c.x + c.y);
+  }
+  const float tsq = warp_sum(sq);
+  float var = __fmul_rn(tsq, 0.001953125f);
+  var = div511_exact(__fmul_rn(var, 512.0f));
+  const float denom = __fadd_rn(__fsqrt_rn(var), eps);
+  const bool fast = denom >= 1e-15f && denom <= 1e15f && tsq <= 1e30f;       // warp-uniform (tsq, denom come out of warp reductions)
+  if (!fast) {
+    // out-of-range or non-finite rows: the general code (identical results where both apply)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __ldg(xr + i * 32 + lane);
+    const float amax = layernorm_row<4>(v, lane, 512, gamma, beta, eps);
+    const float s = quant_scale_x(warp_max_nonneg(amax));
+    const float s_rcp = __frcp_rn(s);
+    uint32_t* qr = reinterpret_cast<uint32_t*>(q_out + row * 512);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qr[i * 32 + lane] = quant4_pack(v[i], s, s_rcp);
+    if (lane == 0) s_out[row] = s;
+    return;
+  }
+  const float rd = __frcp_rn(denom);
+  const f2_t rd2 = ln_pack2(rd, rd), nd2 = ln_pack2(-denom, -denom);
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 g = g4[i * 32 + lane], b = b4[i * 32 + lane];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const f2_t gx = ln_fma2(hh ? ln_pack2(g.z, g.w) : ln_pack2(g.x, g.y), d[2 * i + hh], k_neg0);        // a * (x - mu)
+      const f2_t q0 = ln_fma2(gx, rd2, k_neg0);
+      const f2_t q1 = ln_fma2(ln_fma2(q0, nd2, gx), rd2, q0);
+      const f2_t q2 = ln_fma2(ln_fma2(q1, nd2, gx), rd2, q1);                                             // RN(gx / denom)
+      const f2_t y2 = ln_fma2(q2, k_one, hh ? ln_pack2(b.z, b.w) : ln_pack2(b.x, b.y));
+      const float2 y = ln_unpack2(y2);
+      amax = fmaxf(amax, fmaxf(fabsf(y.x), fabsf(y.y)));
+      d[2 * i + hh] = y2;
+    }
+  }
+  const float s = quant_scale_x(warp_max_nonneg(amax));
+  const float s_rcp = __frcp_rn(s);
+  const f2_t rs2 = ln_pack2(s_rcp, s_rcp), ns2 = ln_pack2(-s, -s);
+  uint32_t* qr = reinterpret_cast<uint32_t*>(q_out + row * 512);
+  if (!(amax <= 3.0e38f)) {                // a non-finite value in this lane's part of the row: the flagged quotient handles it as before
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = ln_unpack2(d[2 * i]), c = ln_unpack2(d[2 * i + 1]);
+      qr[i * 32 + lane] = quant4_pack(make_float4(a.x, a.y, c.x, c.y), s, s_rcp);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t tb[4];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const f2_t y2 = d[2 * i + hh];
+        const f2_t q0 = ln_fma2(y2, rs2, k_neg0);
+        const f2_t q1 = ln_fma2(ln_fma2(q0, ns2, y2), rs2, q0);
+        const f2_t q2 = ln_fma2(ln_fma2(q1, ns2, y2), rs2, q1);                                           // RN(y / s)
+        const f2_t t2 = ln_fma2(q2, k_one, k_magic);                                                      // rint, ties to even, in the low byte
+        tb[2 * hh] = static_cast<uint32_t>(t2 & 0xffffffffull);
+        tb[2 * hh + 1] = static_cast<uint32_t>(t2 >> 32);
+      }
+      qr[i * 32 + lane] = __byte_perm(__byte_perm(tb[0], tb[1], 0x0040), __byte_perm(tb[2], tb[3], 0x0040), 0x5410);
+    }
+  }
+  if (lane == 0) s_out[row] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -184,9 +307,17 @@ extern "C" int ot_layernorm_quant(const float* x, const float* gamma, const floa
   OT_REQUIRE(n % 128 == 0 && n >= 128 && n <= 2048, "n must be a multiple of 128 in [128, 2048]");
   OT_REQUIRE((q_out == nullptr) == (s_out == nullptr), "q_out and s_out go together");
   if (rows == 0) return OT_OK;
-  const int warps = 8;
+ const int warps = 8;
   const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
   cudaStream_t s = as_stream(stream);
+  const char* fenv = getenv("OT_LN512_MIN_ROWS");          // tests raise it to compare with the general kernel
+  const int64_t fast_min_rows = fenv ? atoll(fenv) : 2048;
+  if (n == 512 && y_out == nullptr && q_out != nullptr && rows >= fast_min_rows) {
+    OT_CHECK_CUDA(launch_kernel(layernorm_quant512_kernel, dim3(grid), dim3(warps * 32), 0, s, 1, x, gamma, beta, rows, eps, q_out, s_out,
+                                0x8000000080000000ull, 0x3F8000003F800000ull, 0x4B4000004B400000ull));
+    count_launch();
+    return OT_OK;
+  }
 #define OT_LN_CASE(V)                                                                                            \
   case V:                                                                                                        \
     OT_CHECK_CUDA(launch_kernel(layernorm_quant_kernel<V>, dim3(grid), dim3(warps * 32), 0, s, 1, x, gamma, beta, rows, n, eps, y_out, q_out, s_out)); \

@@ -455,3 +455,43 @@ def test_attention_tc_fused_rowquant_equals_two_launches(K):
         _, q2, s2, _ = K.attention_q8(*args, want_ctx=True, want_q=True, **kw)
         _, q1, s1, _ = K.attention_q8(*args, want_ctx=False, want_q=True, **kw)
         assert torch.equal(q1, q2) and torch.equal(s1.view(torch.int32), s2.view(torch.int32))
+
+
+def test_layernorm_quant512_fast_kernel_equals_general_kernel(K):
+    """layernorm_quant512_kernel (rows >= 2048: packed fp32 arithmetic, divisions as exact FMA quotients) against the general kernel
+    bit for bit -- int8 rows and scales -- on ordinary rows and on rows the fast path must hand back: all-zero, constant, tiny, huge,
+    infinite and NaN rows, zero gamma / beta columns."""
+    import os
+    rng = np.random.default_rng(12)
+    rows, n = 4100, 512
+    x = (rng.normal(size=(rows, n)) * rng.uniform(0.01, 30.0, size=(rows, 1)) + rng.normal(size=(rows, 1))).astype(np.float32)
+    x[5] = 0.0
+    x[6] = 3.25
+    x[7] *= 1e-30
+    x[8] *= 1e30
+    x[9, 100] = np.inf
+    x[10, 3] = np.nan
+    x[11] = 0.0; x[11, 0] = 1.0; x[11, 1] = -1.0; x[11, 2] = 1e-36
+    x[12] *= 1e-20
+    g = rng.normal(size=n).astype(np.float32)
+    b = rng.normal(size=n).astype(np.float32)
+    g[17] = 0.0
+    b[17] = 0.0
+    b[300:310] = 0.0
+    xd, gd, bd = dev(x), dev(g), dev(b)
+    n0 = K._lib.launch_count()
+    _, q1, s1 = K.layernorm_quant(xd, gd, bd, want_y=False, want_q=True)
+    os.environ["OT_LN512_MIN_ROWS"] = str(1 << 40)
+    try:
+        _, q0, s0 = K.layernorm_quant(xd, gd, bd, want_y=False, want_q=True)
+    finally:
+        del os.environ["OT_LN512_MIN_ROWS"]
+    assert K._lib.launch_count() == n0 + 2
+    assert torch.equal(s1.view(torch.int32), s0.view(torch.int32))
+    assert torch.equal(q1, q0)
+    # and against the oracle's LayerNorm + RowQuant with the boundary accounting of the float-reduction class
+    ref = ox.layer_norm(x[:4000], g, b)
+    qr, _ = ox.row_quant(ref)
+    ok = np.all(np.isfinite(x[:4000]), axis=1) & (np.abs(x[:4000]).max(axis=1) < 1e20) & (np.abs(x[:4000]).max(axis=1) > 1e-10)
+    diff = q1.cpu().numpy()[:4000][ok].astype(np.int32) - qr[ok].astype(np.int32)
+    assert np.abs(diff).max() <= 1 and np.count_nonzero(diff) < 1e-4 * diff.size
