@@ -14,11 +14,14 @@
 //        ctx[i, d] = (sum_j pq[i,j] * vhat[j,d]) / 127
 //      The V scale sits on the contraction axis (per key), so this product cannot be an int8 GEMM; the hi/lo split
 //      keeps it in the float tolerance class (observed max relative error vs the float64 oracle ~1e-6, tests/test_kernels_gpu.py).
-//   5. optional (OT_ATTN_FUSE_Q=1), with ctx_q requested: the RowQuant of the MERGED row (all 8 heads) inside this kernel -- the 8 head
-//      CTAs of a sentence form a thread-block cluster, exchange their per-row abs-maxima by st.async + mbarrier complete_tx, derive
-//      the same scale and write their 64 int8 bytes per row (rowquant_kernel's arithmetic: quant_scale_x + quant4_pack).  Measured
-//      at cfg3 (tools/bench_attention.py): 244 us fused vs 188 us + 35 us for the separate rowquant_kernel launch -- a cluster of 8
-//      needs 8 free CTA slots of one GPC at once and every CTA ends waiting for its slowest peer -- so the default stays two launches.
+//   5. with ctx_q requested and no fp32 context (or OT_ATTN_FUSE_Q=1): the RowQuant of the MERGED row (all 8 heads) inside this
+//      kernel -- the 8 head CTAs of a sentence form a thread-block cluster, exchange their per-row abs-maxima by st.async + mbarrier
+//      complete_tx, derive the same scale and write their 64 int8 bytes per row (rowquant_kernel's arithmetic: quant_scale_x +
+//      quant4_pack).  Measured at cfg3 (tools/bench_attention.py): 199 us fused vs 172 us + 35 us for the separate rowquant_kernel.
+//   Thread layout (round 2, third version): 256 threads, thread = (query row = TMEM lane, key half); the row's scores wait in their
+//   own TMEM columns between the three softmax passes and every pass is a ROLLED loop over 16-key chunks.  One thread per row (128
+//   threads) was 188 us; holding the scores in registers instead (fully unrolled, 6.4 k SASS instructions) 212 us: three CTAs at
+//   different phases share the instruction cache (ncu: 2.5 warps stalled on no_instruction per issue).
 //   Fault hooks (App. D) are integer-exact patches of the affected scores / additive fp32 patches of the affected context elements,
 //   so a fault-free element of a faulty launch is bit-identical to the golden launch (same kernel, same data).
 // Replaces attention_heads_kernel (dp4a + fp32 FMA on CUDA cores: 700 us per cfg3 layer, profiles/r1_ncu_encoder_cfg3_layer.txt).
@@ -32,10 +35,12 @@
 
 namespace ot {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;
 constexpr int kTcOffQ = 0, kTcOffK = 16384, kTcOffVhi = 32768, kTcOffVlo = 49152;
 constexpr int kTcOffSk = 65536, kTcOffSv = kTcOffSk + 512, kTcOffKeep = kTcOffSv + 512, kTcOffRed = kTcOffKeep + 128, kTcOffBar = kTcOffRed + 32;
-constexpr int kTcOffRq = kTcOffBar + 64;               // float [8 heads][128 rows]: per-head abs-maxima of the merged context rows (written by the cluster)
+constexpr int kTcOffXm = kTcOffBar + 64;               // float [2 key halves][128 rows]: row maxima, then row sums, then context abs-maxima
+constexpr int kTcOffPq = kTcOffXm + 1024;              // float [128]: quantized probability at the faulty column (P / V faults)
+constexpr int kTcOffRq = kTcOffPq + 512;               // float [8 heads][128 rows]: per-head abs-maxima of the merged context rows (written by the cluster)
 constexpr int kTcSmem = kTcOffRq + 8 * 128 * 4 + 1024;
 static_assert(3 * (kTcSmem + 1024) <= 233472, "three CTAs per SM");
 
@@ -79,7 +84,7 @@ __device__ __forceinline__ int tc_tile_byte(const uint8_t* tile, int row, int k)
 }
 
 template <bool FAULT>
-__global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -92,16 +97,19 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
   float* svs = reinterpret_cast<float*>(smem + kTcOffSv);
   uint8_t* keep = smem + kTcOffKeep;
   float* sred = reinterpret_cast<float*>(smem + kTcOffRed);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcOffBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);       // bars: 0 scores done, 1 context done, 2 row maxima of the 8 heads
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcOffBar);      // 0: scores done, 1: context done, 2: row maxima of the 8 heads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* xm = reinterpret_cast<float*>(smem + kTcOffXm);
+  float* spq = reinterpret_cast<float*>(smem + kTcOffPq);
   float* rq = reinterpret_cast<float*>(smem + kTcOffRq);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);              // warp-uniform for the compiler (tcgen05 / elect regions)
-  const bool fuse_q = a.ctx_q != nullptr;                              // only when launched as clusters of the 8 head CTAs of a sentence
+  const int quarter = warp & 3, hf = warp >> 2;                        // TMEM lane quarter (hardware: warp % 4), key / feature half
   const int h = blockIdx.x, b = blockIdx.y;
   const int Tq = a.Tq, Tk = a.Tk;
   const int Tkp = (Tk + 15) & ~15;
+  const bool fuse_q = a.ctx_q != nullptr;                              // only when launched as clusters of the 8 head CTAs of a sentence
 
   if (warp == 0) {
     if (elect_one()) {
@@ -115,7 +123,9 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
     tmem_alloc(smem_u32(tmem_slot), 128);
     tmem_relinquish();
   }
-  if (fuse_q) cluster_arrive_release();      // waited for just before the exchange at the very end: every peer's barrier is armed by then
+  if (fuse_q) {            // every head CTA of the sentence has its barrier armed before anyone stores into it (the exchange is at the very end)
+    cluster_arrive_release();
+  }
   pdl_wait();
   pdl_trigger();
 
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
     *reinterpret_cast<uint4*>(sK + off) = kv;
   }
   // ---- key scales, mask; the largest |vhat| of the head bounds the fp16 range of the split
-  {
+  if (tid < 128) {
     float s1 = 0.f, s2 = 0.f;
     uint8_t kp = 0;
     if (tid < Tk) {
@@ -188,6 +198,7 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
     sks[tid] = s1; svs[tid] = s2; keep[tid] = kp;
     const float m = warp_max_f(fabsf(s2));
     if (lane == 0) sred[warp] = m;
+    if (FAULT) spq[tid] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -202,25 +213,22 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
     vscale = __uint_as_float(static_cast<uint32_t>(127 + p) << 23);
     vinv = __uint_as_float(static_cast<uint32_t>(127 - p) << 23);
   }
-  // ---- V: de-quantize, scale, split hi/lo, transpose into [feature][key] K-major tiles (64 keys per 128-byte row, fp16)
+  // ---- V: de-quantize, scale, split hi/lo, transpose into [feature][key] K-major tiles (64 keys per 128-byte row, fp16);
+  //      thread = (key pair, 16 of the 64 features)
   {
-    const int jp = tid & 63, dh = tid >> 6;
+    const int jp = tid & 63, dq = tid >> 6;
     const int j0 = 2 * jp, j1 = j0 + 1;
     if (j0 < Tkp) {
-      uint32_t w0[8], w1[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) w0[u] = w1[u] = 0u;
+      uint32_t w0[4] = {0u, 0u, 0u, 0u}, w1[4] = {0u, 0u, 0u, 0u};
       float sv0 = 0.f, sv1 = 0.f;
       if (j0 < Tk) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.v + (static_cast<int64_t>(b) * a.Tk_cap + j0) * a.ldk + h * kDk + 32 * dh);
-        const uint4 x = src[0], y = src[1];
-        w0[0] = x.x; w0[1] = x.y; w0[2] = x.z; w0[3] = x.w; w0[4] = y.x; w0[5] = y.y; w0[6] = y.z; w0[7] = y.w;
+        const uint4 x = *reinterpret_cast<const uint4*>(a.v + (static_cast<int64_t>(b) * a.Tk_cap + j0) * a.ldk + h * kDk + 16 * dq);
+        w0[0] = x.x; w0[1] = x.y; w0[2] = x.z; w0[3] = x.w;
         sv0 = svs[j0];
       }
       if (j1 < Tk) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.v + (static_cast<int64_t>(b) * a.Tk_cap + j1) * a.ldk + h * kDk + 32 * dh);
-        const uint4 x = src[0], y = src[1];
-        w1[0] = x.x; w1[1] = x.y; w1[2] = x.z; w1[3] = x.w; w1[4] = y.x; w1[5] = y.y; w1[6] = y.z; w1[7] = y.w;
+        const uint4 x = *reinterpret_cast<const uint4*>(a.v + (static_cast<int64_t>(b) * a.Tk_cap + j1) * a.ldk + h * kDk + 16 * dq);
+        w1[0] = x.x; w1[1] = x.y; w1[2] = x.z; w1[3] = x.w;
         sv1 = svs[j1];
       }
       const int kb = jp >> 5;
@@ -228,15 +236,15 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
       uint8_t* hi_t = sVhi + kb * 8192;
       uint8_t* lo_t = sVlo + kb * 8192;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
-          const int d = 32 * dh + 4 * u + bb;
+          const int d = 16 * dq + 4 * u + bb;
           const float x0 = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int8_t>((w0[u] >> (8 * bb)) & 0xFFu)), sv0), vscale);
           const float x1 = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int8_t>((w1[u] >> (8 * bb)) & 0xFFu)), sv1), vscale);
           const __half2 hi = __floats2half2_rn(x0, x1);
-          const float2 hf = __half22float2(hi);
-          const __half2 lo = __floats2half2_rn(__fsub_rn(x0, hf.x), __fsub_rn(x1, hf.y));
+          const float2 hf2 = __half22float2(hi);
+          const __half2 lo = __floats2half2_rn(__fsub_rn(x0, hf2.x), __fsub_rn(x1, hf2.y));
           const int off = d * 128 + ((chunk ^ (d & 7)) << 4) + inner;
           *reinterpret_cast<__half2*>(hi_t + off) = hi;
           *reinterpret_cast<__half2*>(lo_t + off) = lo;
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
   __syncthreads();
 
   // ---- scores: S[i, j] = sum_d Q[i, d] K[j, d], exact int32
-  if (warp == 0) {            // a warp-uniform branch + elect: ptxas wraps every UTCxMMA of a `tid == 0` branch in an ELECT / R2UR / BRA.U.ANY loop
+  if (warp == 0) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_i8(128, Tkp);
       const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sQ));
@@ -262,83 +270,93 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
   mbar_wait(smem_u32(&bars[0]), 0);
   tc_fence_after();
 
-  const bool wactive = warp * 32 < Tq;                       // warps whose 32 rows are all past Tq only keep the barriers company
-  const int i = tid;
+  const bool wactive = quarter * 32 < Tq;                    // warps whose 32 rows are all past Tq only keep the barriers company
+  const int i = quarter * 32 + lane;
   const bool row_ok = i < Tq;
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  float pq_f = 0.f;                                           // quantized probability at column fj (P / V faults)
-  float inv_sum = 0.f, sum = 1.f;
-  if (wactive) {
+  const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+  const int c_base = 64 * hf;                                // first key column of this thread
+  const int n_chunks = min(4, max(0, (Tkp - c_base) >> 4));  // 16-key chunks of this thread (warp-uniform)
+  float mx = -INFINITY;
+  float pq_f_local = 0.f;
+  if (wactive && n_chunks > 0) {
     const float sqi = row_ok ? a.sq[(static_cast<int64_t>(b) * Tq + i) * a.sq_stride] : 1.0f;
     const int causal_last = (a.mask_kind == 2) ? a.q_pos0 + i : 0x7fffffff;
-    // ---- pass A: scaled, masked scores + row maximum
-    float mx = -INFINITY;
-    {
-      uint32_t r[16];
-#pragma unroll 1
-      for (int c = 0; c < Tkp; c += 16) {
-        tmem_ld_32x16(taddr + c, r);
-        tmem_wait_ld();
-        const uint4 kw = *reinterpret_cast<const uint4*>(keep + c);
-        const uint32_t kbytes[4] = {kw.x, kw.y, kw.z, kw.w};
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const float4 sk4 = *reinterpret_cast<const float4*>(sks + c + 4 * q4);
-          const float skv[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
-#pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            const int jj = 4 * q4 + bb, j = c + jj;
-            int dot = static_cast<int>(r[jj]);
-            if (FAULT && fault_here) {
-              if (f.reserved == OPERAND_Q && f.mode == OT_FAULT_INPUT && i == fi && j >= fw0 && j < fw1) {
-                const int qv = tc_tile_byte(sQ, i, fd);
-                dot += (flip_int8_bit(qv, f.bit) - qv) * tc_tile_byte(sK, j, fd);
-              } else if (f.reserved == OPERAND_K && f.mode == OT_FAULT_WEIGHT && j == fj && i >= fw0 && i < fw1) {
-                const int kv = tc_tile_byte(sK, j, fd);
-                dot += tc_tile_byte(sQ, i, fd) * (flip_int8_bit(kv, f.bit) - kv);
-              }
-            }
-            float mm = __fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), skv[bb]);                 // MatMul_k_out0
-            if (FAULT && fault_here && f.reserved == OPERAND_SCORES && i == fi && j == fj) mm = tc_patch_f32(f, mm);
-            float s = __fmul_rn(mm, 0.125f);                                                      // / sqrt(d_k) = / 8, exact
-            const bool visible = ((kbytes[q4] >> (8 * bb)) & 0xFFu) != 0u && j <= causal_last;
-            s = visible ? s : -1e9f;                                                              // masked_fill(mask == 0, -1e9)
-            s = (j < Tk) ? s : -INFINITY;                                                         // padding columns of the MMA tile: not keys
-            mx = fmaxf(mx, s);
-            r[jj] = __float_as_uint(s);
-          }
-        }
-        tc_tmem_st_32x16(taddr + c, r);
-        tc_tmem_wait_st();
-      }
-    }
-    // ---- pass B: exponentials + row sum
-    sum = 0.f;
-    {
-      uint32_t r[16];
-#pragma unroll 1
-      for (int c = 0; c < Tkp; c += 16) {
-        tmem_ld_32x16(taddr + c, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const float ev = expf(__fsub_rn(__uint_as_float(r[jj]), mx));
-          sum += ev;
-          r[jj] = __float_as_uint(ev);
-        }
-        tc_tmem_st_32x16(taddr + c, r);
-        tc_tmem_wait_st();
-      }
-    }
-    inv_sum = __frcp_rn(sum);
-  }
-  if (FAULT) __syncthreads();          // a faulty launch read sQ / sK in pass A: nobody overwrites them with P before everyone is done
-  if (wactive) {
-    // ---- pass C: p = e / sum, pq = rint(127 p) -> fp16 A operand of the context MMAs (row i, 64 keys per 128-byte swizzled row)
+    // ---- pass A: scaled, masked scores + row maximum of this key half; the scores wait in their own TMEM columns between the passes
+    //      (ROLLED loops over the 16-key chunks: three CTAs at different phases share the instruction cache)
     uint32_t r[16];
 #pragma unroll 1
-    for (int c = 0; c < Tkp; c += 16) {
-      tmem_ld_32x16(taddr + c, r);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int c0 = c_base + 16 * c;
+      tmem_ld_32x16(tlane + c0, r);
+      tmem_wait_ld();
+      const uint4 kw = *reinterpret_cast<const uint4*>(keep + c0);
+      const uint32_t kbytes[4] = {kw.x, kw.y, kw.z, kw.w};
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 sk4 = *reinterpret_cast<const float4*>(sks + c0 + 4 * q4);
+        const float skv[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const int jj = 4 * q4 + bb, j = c0 + jj;
+          int dot = static_cast<int>(r[jj]);
+          if (FAULT && fault_here) {
+            if (f.reserved == OPERAND_Q && f.mode == OT_FAULT_INPUT && i == fi && j >= fw0 && j < fw1) {
+              const int qv = tc_tile_byte(sQ, i, fd);
+              dot += (flip_int8_bit(qv, f.bit) - qv) * tc_tile_byte(sK, j, fd);
+            } else if (f.reserved == OPERAND_K && f.mode == OT_FAULT_WEIGHT && j == fj && i >= fw0 && i < fw1) {
+              const int kv = tc_tile_byte(sK, j, fd);
+              dot += tc_tile_byte(sQ, i, fd) * (flip_int8_bit(kv, f.bit) - kv);
+            }
+          }
+          float mm = __fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), skv[bb]);                 // MatMul_k_out0
+          if (FAULT && fault_here && f.reserved == OPERAND_SCORES && i == fi && j == fj) mm = tc_patch_f32(f, mm);
+          float sc = __fmul_rn(mm, 0.125f);                                                     // / sqrt(d_k) = / 8, exact
+          const bool visible = ((kbytes[q4] >> (8 * bb)) & 0xFFu) != 0u && j <= causal_last;
+          sc = visible ? sc : -1e9f;                                                            // masked_fill(mask == 0, -1e9)
+          sc = (j < Tk) ? sc : -INFINITY;                                                       // padding columns of the MMA tile: not keys
+          mx = fmaxf(mx, sc);
+          r[jj] = __float_as_uint(sc);
+        }
+      }
+      tc_tmem_st_32x16(tlane + c0, r);
+      tc_tmem_wait_st();
+    }
+  }
+  xm[hf * 128 + i] = mx;
+  __syncthreads();                     // also: every read of sQ / sK by a faulty launch is done before P overwrites them
+  mx = fmaxf(xm[i], xm[128 + i]);
+  __syncthreads();                     // xm is reused for the sums
+  // ---- pass B: exponentials + row sum of this key half
+  float sum = 0.f;
+  if (wactive && n_chunks > 0) {
+    uint32_t r[16];
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
+      const int c0 = c_base + 16 * c;
+      tmem_ld_32x16(tlane + c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const float ev = expf(__fsub_rn(__uint_as_float(r[jj]), mx));
+        sum += ev;
+        r[jj] = __float_as_uint(ev);
+      }
+      tc_tmem_st_32x16(tlane + c0, r);
+      tc_tmem_wait_st();
+    }
+  }
+  xm[hf * 128 + i] = sum;
+  __syncthreads();
+  sum = __fadd_rn(xm[i], xm[128 + i]);                       // fixed order: keys [0, 64) + keys [64, 128)
+  if (wactive && n_chunks > 0) {
+    const float inv_sum = __frcp_rn(sum);
+    // ---- pass C: p = e / sum, pq = rint(127 p) -> fp16 A operand of the context MMAs (row i, 64 keys per 128-byte swizzled row)
+    uint8_t* prow = sP + hf * 16384 + i * 128;
+    uint32_t r[16];
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
+      const int c0 = c_base + 16 * c;
+      tmem_ld_32x16(tlane + c0, r);
       tmem_wait_ld();
       uint32_t packed[8];
 #pragma unroll
@@ -351,21 +369,21 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
           const float p = __fmaf_rn(__fmaf_rn(-q0, sum, ev), inv_sum, q0);                       // e / sum within 1 ulp
           const float t = __fadd_rn(__fmul_rn(p, 127.0f), 12582912.0f);                          // Round(Mul(p, 127)), ties to even
           n2[u] = __fsub_rn(t, 12582912.0f);
-          if (FAULT && fault_here && c + jj + u == fj) pq_f = n2[u];
+          if (FAULT && fault_here && c0 + jj + u == fj) pq_f_local = n2[u];
         }
         const __half2 hp = __floats2half2_rn(n2[0], n2[1]);
         packed[jj >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
         if (a.probs_q != nullptr && row_ok) {
           uint8_t* pr = a.probs_q + ((static_cast<int64_t>(b) * kHeads + h) * Tq + i) * Tk;
-          if (c + jj < Tk) pr[c + jj] = static_cast<uint8_t>(n2[0]);
-          if (c + jj + 1 < Tk) pr[c + jj + 1] = static_cast<uint8_t>(n2[1]);
+          if (c0 + jj < Tk) pr[c0 + jj] = static_cast<uint8_t>(n2[0]);
+          if (c0 + jj + 1 < Tk) pr[c0 + jj + 1] = static_cast<uint8_t>(n2[1]);
         }
       }
-      uint8_t* prow = sP + (c >> 6) * 16384 + i * 128;
-      const int ch = (c & 63) >> 3;
+      const int ch = 2 * c;
       *reinterpret_cast<uint4*>(prow + (((ch) ^ (i & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
       *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ (i & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
     }
+    if (FAULT && fault_here && fj >= c_base && fj < c_base + 64) spq[i] = pq_f_local;
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -395,16 +413,17 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
 
-  // ---- epilogue: thread = query row i, the head's 64 context features, 16 at a time in ROLLED loops (three CTAs at different phases
-  //      share the instruction cache: the unrolled form of this kernel stalled on instruction fetch).  With the fused RowQuant the
-  //      finished values wait in their own TMEM columns (tcgen05.st) for the row maximum of the other heads.
+  // ---- epilogue: thread = (row i, features 32 hf .. 32 hf + 31 of head h), 16 at a time in a rolled loop; with the fused RowQuant the
+  //      finished values wait in their own TMEM columns for the row maximum of the other heads
   float amax = 0.f;
+  const uint32_t tctx = tlane + 32 * hf;
   if (wactive) {
-    float* orow = a.ctx != nullptr ? a.ctx + (static_cast<int64_t>(b) * Tq + i) * a.ld_ctx + h * kDk : nullptr;
+    float* orow = a.ctx != nullptr ? a.ctx + (static_cast<int64_t>(b) * Tq + i) * a.ld_ctx + h * kDk + 32 * hf : nullptr;
+    const float pq_f = FAULT ? spq[i] : 0.f;
     uint32_t r[16];
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      tmem_ld_32x16(taddr + 16 * c, r);
+    for (int c = 0; c < 2; ++c) {
+      tmem_ld_32x16(tctx + 16 * c, r);
       tmem_wait_ld();
       float y[16];
 #pragma unroll
@@ -417,7 +436,7 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
       if (FAULT && fault_here && row_ok) {
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-          const int d = 16 * c + jj;
+          const int d = 32 * hf + 16 * c + jj;
           if (f.reserved == OPERAND_P && f.mode == OT_FAULT_INPUT && i == fi && d >= fw0 && d < fw1) {
             const float pf = static_cast<float>(flip_int8_bit(static_cast<int>(pq_f), f.bit));
             const int vq = a.v[(static_cast<int64_t>(b) * a.Tk_cap + fj) * a.ldk + h * kDk + d];
@@ -438,7 +457,7 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
         r[jj] = __float_as_uint(y[jj]);
       }
       if (fuse_q) {
-        tc_tmem_st_32x16(taddr + 16 * c, r);
+        tc_tmem_st_32x16(tctx + 16 * c, r);
         tc_tmem_wait_st();
       }
       if (orow != nullptr && row_ok) {
@@ -449,13 +468,16 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
     }
   }
   if (fuse_q) {
-    // ---- RowQuant of the merged context row: this head's abs-max of every row to the 8 head CTAs of the sentence (cluster)
+    // ---- RowQuant of the merged context row: abs-max over this head's 64 features, then over the 8 heads (cluster exchange)
     if (!row_ok) amax = 0.f;
+    xm[hf * 128 + i] = amax;
+    __syncthreads();
     cluster_wait_acquire();                                  // (arrived at kernel start) every peer's barrier is armed
-    {
+    if (hf == 0) {
+      const float m = fmaxf(xm[i], xm[128 + i]);
       const uint32_t slot = smem_u32(rq + h * 128 + i), qb = smem_u32(&bars[2]);
 #pragma unroll
-      for (int peer = 0; peer < kHeads; ++peer) tc_st_async_f32(mapa_shared(slot, peer), amax, mapa_shared(qb, peer));
+      for (int peer = 0; peer < kHeads; ++peer) tc_st_async_f32(mapa_shared(slot, peer), m, mapa_shared(qb, peer));
     }
     mbar_wait(smem_u32(&bars[2]), 0);
     float rmax = 0.f;
@@ -464,11 +486,11 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
     if (wactive) {
       const float s = quant_scale_x(rmax);
       const float s_rcp = __frcp_rn(s);
-      uint4* qrow = reinterpret_cast<uint4*>(a.ctx_q + (static_cast<int64_t>(b) * Tq + i) * kDm + h * kDk);
+      uint4* qrow = reinterpret_cast<uint4*>(a.ctx_q + (static_cast<int64_t>(b) * Tq + i) * kDm + h * kDk + 32 * hf);
       uint32_t r[16];
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_32x16(taddr + 16 * c, r);
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x16(tctx + 16 * c, r);
         tmem_wait_ld();
         uint32_t w[4];
 #pragma unroll
@@ -477,7 +499,7 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
                                           __uint_as_float(r[4 * q4 + 3])), s, s_rcp);
         if (row_ok) qrow[c] = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      if (row_ok && h == 0) a.ctx_s[static_cast<int64_t>(b) * Tq + i] = s;
+      if (row_ok && h == 0 && hf == 0) a.ctx_s[static_cast<int64_t>(b) * Tq + i] = s;
     }
   }
   tc_fence_before();
@@ -485,7 +507,6 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const AttnArgs
   if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
-// Launch for (B x 8) heads; returns 1 when the shape does not qualify (the caller falls back to the CUDA-core kernels).
 // Returns 0 on success, 1 when the shape does not qualify (the caller falls back to the CUDA-core kernels), < 0 on error.  *fused_q is set
 // when the kernel quantized the merged rows itself (ctx_q / ctx_s written); otherwise the caller runs rowquant_kernel on the fp32 context.
 int launch_attention_tc(const AttnArgs& a0, cudaStream_t stream, bool* fused_q) {

@@ -324,7 +324,11 @@ class QuantizedTransformer:
             self._qkv(L["qkv"], ws["xq"], ws["sx"], ws["qkv"], ws["sqkv"], fk)
             K.attention_q8(ws["qkv"], ws["sqkv"], ws["qkv"][:, D:], ws["qkv"][:, 2 * D:], ws["sqkv"][:, 1:], ws["sqkv"][:, 2:],
                            B=B, Tq=S, Tk=S, ldq=3 * D, sq_stride=3, ldk=3 * D, skv_stride=3, mask_kind=1, key_mask=mask, mask_stride=S,
-                           want_ctx=True, ctx=ws["ctx"], want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"], **fk("qk", "pv"))
+                           # 32 <= S <= 128: the tensor-core kernel quantizes the merged rows itself when no fp32 context is asked for
+                           # (cluster of the 8 head CTAs: 199 us vs 172 + 35 us for attention + rowquant_kernel at cfg3); captures and
+                           # the CUDA-core kernels of other lengths go through the fp32 context
+                           want_ctx=(cp is not None) or not (32 <= S <= 128), ctx=ws["ctx"], want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"],
+                           **fk("qk", "pv"))
             self._cap(cp, qkv=ws["qkv"], sqkv=ws["sqkv"], ctx=ws["ctx"], cq=ws["cq"], cs=ws["cs"])
             L["o"].gemm(ws["cq"], ws["cs"], residual=x,
                           out_kind=K.OUT_F32, out=nxt, **fk("o"))
