@@ -257,6 +257,7 @@ def persistent_phase_trace(eng, ws, B, S, t_mid=35):
             out[n] = out.get(n, 0.0) + (t[2 * i + 1] - prev) / 1e3
             prev = t[2 * i + 1]
         total = (t[2 * len(names) - 1] - t[255]) / 1e3
+    eng._last_trace = t          # raw stamps (tools/spc_sweep.py prints the generator's internal marks)
     ws.pop("plan", None)      # drop the tracing plan: the next decode rebuilds the plain one
     return {k: round(float(v), 2) for k, v in out.items()}, float(total)
 

@@ -251,7 +251,10 @@ int ot_decoder_run(const void* plan_dev, unsigned int* bar_dev, int t0, int n_st
  * grid barriers.  Clusters are independent: any B, no co-residency requirement.  The plan is an opaque device-resident block
  * (ot_cdecoder_plan_size bytes, 256-byte aligned):
  *   layer_ptrs: n_layers x 28 device pointers, per layer, in the order of ot_decoder_plan_build
- *   ws_ptrs: 12 device pointers: ckv sckv mask fin_g fin_b gen_w4 gen_b tgt_lut pe ys trace(u64[256] or NULL) reserved(NULL)
+ *   ws_ptrs: 12 device pointers: ckv sckv mask fin_g fin_b gen_w4 gen_b tgt_lut pe ys trace(u64[256] or NULL) gen_w16(or NULL)
+ *       (gen_w16, optional: blob for the tensor-core screening generator = 1024-byte header whose first float is max_v ||w_v||_2 of
+ *        the generator weight, followed by its fp16 copy as [8 * 576][512] row-major, zero rows past the vocabulary; NULL = exact
+ *        fp32 generator only.  Tokens are identical either way: screened entries are re-evaluated with the exact fp32 chain.)
  *       (gen_w4: the generator weight re-laid out as [ceil(vocab/32)][128][32][4] = tile / k-quad / entry / k, zero padded)
  * S <= 96 source tokens, cap <= 96 cache positions, vocab <= 6144.  ot_cdecoder_run executes greedy steps t0 .. t0+n_steps-1:
  * reads ys[:, t0], writes ys[:, t0+1 .. t0+n_steps] and the self-attention KV-cache positions t0 .. t0+n_steps-1. */

@@ -23,6 +23,7 @@
 // Arithmetic is instruction-for-instruction that of the stand-alone kernels (ot_rowmath.cuh, ot_attention_decode.cuh,
 // ot_generator.cu), so tokens and KV caches are bit-identical to the per-op engine path (tests/test_decoder_gpu.py).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
@@ -52,7 +53,11 @@ constexpr int kChunks = 15;         // weight chunks per layer per CTA
 constexpr int kMaxLayers = 8;
 constexpr int kMaxKeys = 32 * kDecKeysPerLane;   // 96
 constexpr int kGenVT = 32;          // vocabulary entries per generator tile
-constexpr int kTmemCols = 256;      // accumulator: lanes 0..7 = sentences, columns = the CTA's output features of the GEMM (<= 256)
+constexpr int kTmemCols = 512;      // accumulator: lanes 0..7 = sentences, columns = the CTA's output features of the GEMM (<= 256);
+                                    // the screening generator double-buffers two 192-column accumulators at columns 0 and 256
+constexpr int kGenRows = 576;       // vocabulary rows per CTA in the screening generator: 3 row blocks of 192 (8 x 576 = 4608 >= vocab)
+constexpr int kGenRB = 192;
+constexpr int kGenChunks = 3 * 8;   // (row block, k-block of 64 fp16) chunks of 192 rows x 128 B per CTA and step
 
 // shared-memory map (dynamic, base aligned to 1024)
 constexpr int kSmRing = 0;                                  // weight ring
@@ -67,7 +72,10 @@ constexpr int kSmCtx = kSmRow + 2048;                       // 212992: epilogue 
 constexpr int kSmMisc = kSmCtx + 2048;                      // 215040: scales, reduction scratch, generator partials, hidden-row maxima (2 KB)
 constexpr int kSmHot = kSmMisc + 2048;                      // 217088: CdHot copy (<= 1920 B) + 128 B of barriers
 constexpr int kSmW2 = kSmHot + 2048;                        // 219136: FFN2 column scales + bias (2 x 512 floats), prefetched for the LayerNorm after it
-constexpr int kSmTotal = kSmW2 + 4096;                      // 223232
+constexpr int kSmGen = kSmW2 + 4096;                        // 223232: screening generator: logits of row block 2 (6 KB), gathered maxima, 13 mbarriers
+constexpr int kSmGenMax = kSmGen + 6144;                    // float [8 ranks][8 sentences] (written by peers)
+constexpr int kSmGenBars = kSmGenMax + 256;                 // gfull[4], gempty[4], gaccf[2], gacce[2], gmax
+constexpr int kSmTotal = kSmGen + 7168;                     // 230400
 static_assert(kSmTotal + 1024 <= 232448, "shared memory budget");
 // The M = 64 MMA reads 8 row groups (8 KB) from each operand k-block although only the first group (8 sentences) is real:
 // the over-read past Bh must stay inside the CTA's allocation.
@@ -104,11 +112,15 @@ struct alignas(16) CdHot {
   const float *tgt_lut, *pe;
   int64_t* ys; int64_t ys_ld;
   unsigned long long* trace;                  // optional [256]
+  float gen_eps;                              // screening generator: max_v ||w_v||_2 * 2^-9 (0 = exact generator only)
+  float gen_abs;                              //   + absolute term max_v ||w_v||_2 * 1e-6
+  int gen_tc, pad2;
 };
 static_assert(sizeof(CdHot) % 16 == 0 && sizeof(CdHot) <= 1920, "CdHot is copied to shared memory in 16-byte pieces");
 
 struct CdPlan {
   CUtensorMap map_w[kMaxLayers][6];           // qkv, o, cq, co, w1, w2: (128 B, row, k-block) views, box = one ring chunk
+  CUtensorMap map_g;                          // fp16 generator weight [4608][512]: (128 B = 64 k, row, k-block), box = 192 rows x 1 k-block
   CdHot hot;
 };
 
@@ -127,6 +139,7 @@ struct Ctx {
   int rank, n_own, b;    // cluster rank, sentences of this cluster, my sentence (or -1)
   uint32_t pn, cn, total;   // weight chunks issued (loader thread) / consumed (issuer thread) / to do
   uint32_t acc_parity, kv_parity, g_parity, s_parity, m_parity;
+  uint32_t gen_n, gen_acc[2], gen_max_parity;   // screening generator: chunks issued / consumed so far (same count in both roles), accumulator uses, exchange parity
   int trace_slot;
   bool trace_on;
   bool fine;                       // intra-phase marks of one layer (profiling aid, trace slots 150..249)
@@ -250,6 +263,26 @@ __device__ __forceinline__ void fill_until(Ctx& c, uint32_t upto) {
   }
 }
 
+// loader warp: generator chunk j of this step (row block j / 8, k-block j % 8) into ring slot (gen_n + j) % kSlots
+__device__ __forceinline__ void gen_issue_chunk(Ctx& c, int j) {
+  uint64_t* gb = reinterpret_cast<uint64_t*>(c.smem + kSmGenBars);
+  const uint32_t G = c.gen_n + j;
+  const int slot = G % kSlots;
+  if (j < kSlots) {
+    // the main ring's last use of this slot (the ring is drained: every chunk of this step has been issued)
+    const uint32_t N = c.pn;
+    const uint32_t m = N - 1 - ((N - 1 - slot) % kSlots);             // largest main chunk index < N with index % kSlots == slot
+    mbar_wait(smem_u32(&c.bars[kBarEmpty + slot]), (m / kSlots) & 1);
+  }
+  if (G >= kSlots) mbar_wait(smem_u32(&gb[4 + slot]), ((G / kSlots) - 1) & 1);
+  if (elect_one()) {
+    const uint32_t fb = smem_u32(&gb[slot]);
+    mbar_arrive_expect_tx(fb, kGenRB * 128);
+    tma_load_3d(smem_u32(c.smem + kSmRing + slot * kSlotBytes), &c.G->map_g, fb, 0, c.rank * kGenRows + (j >> 3) * kGenRB, j & 7);
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM phase
 // g: 0 qkv, 1 o, 2 cq, 3 co, 4 w1 (ReLU), 5 w2.  D[s][f] = sum_k a[s][k] * W[f][k] (rows s >= 8 of the M = 64 tile are whatever
 // follows the 8 operand rows in shared memory: never read back); then scatter y[s][f] to the owner of sentence s.
@@ -325,7 +358,14 @@ __device__ __forceinline__ void phase_gemm(Ctx& c, int l, int g, uint32_t gend, 
     // barrier), so all but the last chunk of the refill streams in during the MMA window.  Measured: a 128 KB TMA burst issued
     // after the last MMA stalls every shared-memory load of the SM for ~0.9 us -- exactly when the epilogue and the next row
     // phase need them -- while loads that land during the MMAs cost nothing (the MMA time is unchanged).
-    fill_until(c, gend + kSlots);
+    if (c.P->gen_tc && g == 5 && l == c.P->n_layers - 1) {
+      // the screening generator borrows the ring's slots: no run-ahead into the next step across it; its own first chunks (constants
+      // too) are requested right here, two phases before they are needed
+      fill_until(c, gend);
+      for (int j = 0; j < kSlots; ++j) gen_issue_chunk(c, j);
+    } else {
+      fill_until(c, gend + kSlots);
+    }
   }
   __syncwarp();
   if (epi) {
@@ -947,6 +987,234 @@ __device__ __forceinline__ void phase_generator(Ctx& c) {
     st_async_b32(mapa_shared(smem_u32(misc(c) + kMiGenI + c.rank), tid), static_cast<uint32_t>(bi), sbar);
   }
 }
+// ------------------------------------------------------------------------------------------------ generator, tensor-core screening
+// The exact generator above is FP32-bound (35.8 k FFMA2 per CTA >= 12 us) and streams 1.1 MB of fp32 weights per CTA and step.  Here
+// the tensor cores SCREEN the vocabulary and the fp32 chain only re-evaluates the entries that can still win:
+//   1. approximate logits of the CTA's 576 vocabulary rows for the 8 sentences: tcgen05.mma.kind::f16 (M = 64: the 8 sentences,
+//      N = 192, K = 16 per instruction) on fp16 copies of h and W, fp32 accumulation in TMEM; the fp16 weight slice (576 KB) streams
+//      through the weight ring's slots (the ring does not run ahead into the next step across this phase);
+//      (+ the fp32 bias, so that the screened quantity is the logit itself);
+//   2. |approx - exact| <= eps_s = ||h_s||_2 max_v||w_v||_2 2^-9 + ||h_s||_1 2^-24 + max_v||w_v||_2 1e-6 (fp16 rounding of both operands
+//      is 2^-10 relative to sum |h_k w_k| <= ||h|| ||w||; the other half of the 2^-9 covers the accumulation and the fp32 chain's own
+//      rounding; the absolute terms cover fp16 underflow of either operand).  The CTAs all-gather their per-sentence maxima; an entry
+//      can be the arg-max only if its approximate logit is within 2 eps_s of the largest approximate logit M_s;
+//   3. those entries (typically one or two per sentence and cluster) are evaluated EXACTLY -- k-ascending fmaf chain + bias, the
+//      arithmetic of generator_logits_kernel -- and compared by (logit, lowest index), so the token is the exact generator's token.
+// Anything not finite (NaN / Inf in h, fp16 overflow) makes every CTA of the cluster fall back to the exact generator for that step.
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 instruction descriptor: D = F32 (1 at [4,6)), A = B = F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ float* gen_logits(Ctx& c, int rb) {      // [8 sentences][192] approximate logits of row block rb
+  return reinterpret_cast<float*>(c.smem + (rb == 0 ? kSmRecv : rb == 1 ? kSmX : kSmGen));
+}
+
+__device__ __forceinline__ void phase_generator_tc(Ctx& c, bool more_steps) {
+  const CdHot& P = *c.P;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  uint64_t* gb = reinterpret_cast<uint64_t*>(c.smem + kSmGenBars);     // gfull[0..3] gempty[4..7] gaccf[8..9] gacce[10..11] gmax[12]
+  const float* hb = reinterpret_cast<const float*>(c.smem + kSmHb);
+  // ---- a. fp16 A operand (8 sentence rows per k-block of 64, 128-byte swizzle) + the norms of my warp's sentence
+  float eps_s;
+  {
+    const int srow = warp;                                              // warp = sentence
+    const float4* h4 = reinterpret_cast<const float4*>(hb + srow * kD + lane * 16);
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float4 x = h4[q]; v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w; }
+    float ss = 0.f, sa = 0.f;
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ss = fmaf(v[2 * j], v[2 * j], fmaf(v[2 * j + 1], v[2 * j + 1], ss));
+      sa += fabsf(v[2 * j]) + fabsf(v[2 * j + 1]);
+      const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    ss = warp_sum(ss);
+    sa = warp_sum(sa);
+    eps_s = fmaf(sqrtf(ss) * 1.0001f, P.gen_eps, fmaf(sa, 5.9604645e-08f, P.gen_abs));
+    const int kb = lane >> 2, c16 = (2 * lane) & 7;
+    uint8_t* arow = c.smem + kSmBh + kb * 1024 + srow * 128;
+    *reinterpret_cast<uint4*>(arow + ((c16 ^ (srow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(arow + (((c16 + 1) ^ (srow & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+  if (tid == 0) mbar_arrive_expect_tx(smem_u32(&gb[12]), kCS * kCS * 4);      // the gathered maxima of this step
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (c.trace_on && tid == 0) P.trace[240] = tl_now();
+  // ---- b. approximate logits: loader warp / issuer warp / two epilogue warps (TMEM lanes 0..15 belong to warps 0 and 4)
+  const uint32_t G0 = c.gen_n;
+  if (warp_u == kLoader / 32) {
+    for (int j = kSlots; j < kGenChunks; ++j) gen_issue_chunk(c, j);       // chunks 0..3 were issued behind the last FFN2 (phase_gemm)
+    // hand the slots back to the layer weights: the last generator chunk of every slot has been consumed, then the ring runs ahead again
+    for (int j = kGenChunks - kSlots; j < kGenChunks; ++j) {
+      const uint32_t G = G0 + j;
+      mbar_wait(smem_u32(&gb[4 + G % kSlots]), (G / kSlots) & 1);
+    }
+    if (more_steps) fill_until(c, c.pn + kSlots);
+  } else if (warp_u == kIssuer / 32) {
+    const uint32_t idesc = make_idesc_f16(64, kGenRB);
+    const uint32_t abase = smem_u32(c.smem + kSmBh);
+    for (int rb = 0; rb < 3; ++rb) {
+      const int buf = rb & 1;
+      const uint32_t use = c.gen_acc[buf] + (rb >> 1);                   // buffer 0 is used twice per step
+      if (use > 0) { mbar_wait(smem_u32(&gb[10 + buf]), (use - 1) & 1); tc_fence_after(); }
+      for (int kb = 0; kb < 8; ++kb) {
+        const uint32_t G = G0 + rb * 8 + kb;
+        const int slot = G % kSlots;
+        mbar_wait(smem_u32(&gb[slot]), (G / kSlots) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a_desc = make_smem_desc_sw128(abase + kb * 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(c.smem + kSmRing + slot * kSlotBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_f16_ss(c.tmem + buf * 256, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          mma_commit(smem_u32(&gb[4 + slot]));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) mma_commit(smem_u32(&gb[8 + buf]));
+      __syncwarp();
+    }
+  } else if ((warp & 3) == 0) {
+    const int col0 = (warp >> 2) * 96, srow = lane >> 2;
+    for (int rb = 0; rb < 3; ++rb) {
+      const int buf = rb & 1;
+      const uint32_t use = c.gen_acc[buf] + (rb >> 1);
+      mbar_wait(smem_u32(&gb[8 + buf]), use & 1);
+      tc_fence_after();
+      float* L = gen_logits(c, rb) + srow * kGenRB + col0;
+#pragma unroll
+      for (int gq = 0; gq < 3; ++gq) {
+        uint32_t r[16];
+        tmem_ld_16x256b_x4(c.tmem + buf * 256 + col0 + 32 * gq, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float2*>(L + 32 * gq + 8 * i + 2 * (lane & 3)) = make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&gb[10 + buf]));
+    }
+  }
+  c.gen_n += kGenChunks;
+  c.gen_acc[0] += 2;
+  c.gen_acc[1] += 1;
+  __syncthreads();
+  if (c.trace_on && tid == 0) P.trace[241] = tl_now();
+  // ---- c. per-sentence maximum of my 576 approximate logits -> all-gather (warp = sentence, lane p sends to CTA p)
+  const int srow = warp;
+  float lmax = -INFINITY;
+  bool lbad = false;
+  {
+    // + bias (the exact logit has it), coalesced and all in flight at once; rows past the vocabulary become -Inf: never candidates
+    float bias[kGenRows / 32];
+#pragma unroll
+    for (int q = 0; q < kGenRows / 32; ++q) {
+      const int v = c.rank * kGenRows + q * 32 + lane;
+      bias[q] = (P.gen_b && v < P.vocab) ? __ldg(P.gen_b + v) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < kGenRows / 32; ++q) {
+      const int col = q * 32 + lane;
+      float* L = gen_logits(c, col / kGenRB) + srow * kGenRB + col % kGenRB;
+      const float x = (c.rank * kGenRows + col < P.vocab) ? __fadd_rn(*L, bias[q]) : -INFINITY;
+      *L = x;
+      lbad = lbad || (x != x) || (x > 3.0e38f);          // NaN / +Inf
+      lmax = fmaxf(lmax, x);
+    }
+  }
+  lmax = warp_max_any(lmax);
+  lbad = __any_sync(0xffffffffu, lbad);
+  if (lbad) lmax = __uint_as_float(0x7fc00000u);
+  float* gm = reinterpret_cast<float*>(c.smem + kSmGenMax);
+  if (lane < kCS) st_async_b32(mapa_shared(smem_u32(gm + c.rank * kCS + srow), lane), __float_as_uint(lmax), mapa_shared(smem_u32(&gb[12]), lane));
+  mbar_wait(smem_u32(&gb[12]), c.gen_max_parity);
+  c.gen_max_parity ^= 1u;
+  if (c.trace_on && tid == 0) P.trace[242] = tl_now();
+  float M = (lane < kCS) ? gm[lane * kCS + srow] : -INFINITY;
+  bool bad = (lane < kCS) && !(fabsf(M) <= 3.0e38f);
+  bad = __any_sync(0xffffffffu, bad) || !(eps_s <= 3.0e38f);
+  M = warp_max_any(M);
+  // cluster-uniform decision: every CTA sees the same 64 maxima and the same eps_s
+  int* flag = reinterpret_cast<int*>(misc(c) + kMiRed);
+  if (tid == 0) *flag = 0;
+  __syncthreads();
+  if (bad && lane == 0 && srow < c.n_own) atomicOr(flag, 1);
+  __syncthreads();
+  if (*flag != 0) {
+    __syncthreads();
+    phase_generator(c);                  // exact generator for this step (h is still in place)
+    return;
+  }
+  if (c.trace_on && tid == 0) P.trace[243] = tl_now();
+  // ---- d. exact re-evaluation of the entries within 2 eps of the maximum; first arg-max by (logit, lowest index)
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  if (srow < c.n_own) {
+    const float thr = M - 2.0f * eps_s;
+    const float4* hrow = reinterpret_cast<const float4*>(hb + srow * kD);
+#pragma unroll 1
+    for (int q = 0; q < kGenRows / 32; ++q) {
+      const int col = q * 32 + lane;                                      // 0..575 within my slice
+      const float x = gen_logits(c, col / kGenRB)[srow * kGenRB + col % kGenRB];
+      const int v = c.rank * kGenRows + col;
+      unsigned todo = __ballot_sync(0xffffffffu, x >= thr && v < P.vocab);
+      while (todo != 0u) {
+        // one candidate at a time, the whole warp on it: the 2 KB weight row arrives with ONE L2 round trip (lane l fetches k-quads
+        // l, l + 32, l + 64, l + 96) and is staged in this warp's 2 KB of shared memory; then every lane runs the k-ascending fmaf
+        // chain of generator_logits_kernel on broadcast loads (512 dependent FMAs: ~1 us; shuffling the weights instead cost 3 us)
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const int vv = __shfl_sync(0xffffffffu, v, src);
+        const float4* wp = reinterpret_cast<const float4*>(P.gen_w4) + static_cast<int64_t>(vv >> 5) * 128 * 32 + (vv & 31);
+        float4* wrow = reinterpret_cast<float4*>(c.smem + kSmHb + kCS * kD * 4) + warp * 128;      // the exact generator's hT region
+        {
+          float4 wreg[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) wreg[j] = __ldg(wp + (lane + 32 * j) * 32);
+          __syncwarp();                                                    // the previous candidate's chain has read the row
+#pragma unroll
+          for (int j = 0; j < 4; ++j) wrow[lane + 32 * j] = wreg[j];
+        }
+        const float bias = P.gen_b ? __ldg(P.gen_b + vv) : 0.f;
+        __syncwarp();
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k4 = 0; k4 < 128; ++k4) {
+          const float4 w = wrow[k4];
+          const float4 hv = hrow[k4];
+          acc = __fmaf_rn(hv.x, w.x, acc);
+          acc = __fmaf_rn(hv.y, w.y, acc);
+          acc = __fmaf_rn(hv.z, w.z, acc);
+          acc = __fmaf_rn(hv.w, w.w, acc);
+        }
+        float lg = __fadd_rn(acc, bias);
+        if (lg != lg) lg = INFINITY;
+        if (lg > best || (lg == best && vv < bidx)) { best = lg; bidx = vv; }       // uniform across the warp
+      }
+    }
+    if (lane == 0) {
+      const uint32_t sbar = mapa_shared(smem_u32(&c.bars[kBarS]), srow);
+      st_async_b32(mapa_shared(smem_u32(misc(c) + kMiGenV + c.rank), srow), __float_as_uint(best), sbar);
+      st_async_b32(mapa_shared(smem_u32(misc(c) + kMiGenI + c.rank), srow), static_cast<uint32_t>(bidx), sbar);
+    }
+  }
+}
 // owner, warp 0: first arg-max over the 8 vocabulary slices
 __device__ __forceinline__ int generator_pick(Ctx& c, int lane) {
   const float* gv = misc(c) + kMiGenV;
@@ -979,6 +1247,10 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   if (warp == 7) {
     if (lane == 0) {
       for (int i = 0; i <= kBarM; ++i) mbar_init(smem_u32(&c.bars[i]), 1);
+      {
+        uint64_t* gb = reinterpret_cast<uint64_t*>(c.smem + kSmGenBars);
+        for (int i = 0; i < 13; ++i) mbar_init(smem_u32(&gb[i]), (i == 10 || i == 11) ? 2 : 1);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -998,6 +1270,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
   c.pn = c.cn = 0;
   c.total = static_cast<uint32_t>(n_steps) * nl * kChunks;
   c.acc_parity = c.kv_parity = c.g_parity = c.s_parity = c.m_parity = 0;
+  c.gen_n = c.gen_acc[0] = c.gen_acc[1] = c.gen_max_parity = 0;
   c.trace_slot = 0;
   c.trace_on = false;
   c.fine = false;
@@ -1081,7 +1354,8 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
     }
     c.fine = false;
     xwait(c, kBarG, t < t_last ? static_cast<uint32_t>(c.n_own) * (kD + 4) : 0u, c.g_parity, true);
-    phase_generator(c);
+    if (P.gen_tc) phase_generator_tc(c, t < t_last);
+    else phase_generator(c);
     if (c.trace_on && tid == 0) P.trace[254] = tl_now();
   }
   // the last step's token
@@ -1149,6 +1423,17 @@ extern "C" int ot_cdecoder_plan_build(void* plan_dev, int n_layers, int B, int S
     const int box_kb[6] = {1, 4, 4, 4, 1, 1};                // k-blocks of a ring chunk
     for (int w = 0; w < 6; ++w)
       if ((rc = get_tensor_map_kblocks(&plan.map_w[l][w], p[6 + 3 * w], wn[w], wk[w], wk[w], box_rows[w], box_kb[w]))) return rc;
+  }
+  // screening generator (ws_ptrs[11], optional): a device blob = 1024-byte header (float max_v ||w_v||_2) + fp16 weight [8 * 576][512]
+  if (ws_ptrs[11] != nullptr && !(getenv("OT_CD_GEN_TC") && atoi(getenv("OT_CD_GEN_TC")) == 0)) {
+    OT_REQUIRE(vocab <= kCS * kGenRows, "screening generator: vocabulary > 4608");
+    float wnorm = 0.f;
+    OT_CHECK_CUDA(cudaMemcpy(&wnorm, ws_ptrs[11], sizeof(float), cudaMemcpyDeviceToHost));
+    OT_REQUIRE(wnorm > 0.f && wnorm < 1e30f, "screening generator: bad weight norm");
+    if ((rc = get_tensor_map_kblocks(&plan.map_g, static_cast<const uint8_t*>(ws_ptrs[11]) + 1024, kCS * kGenRows, 2 * kD, 2 * kD, kGenRB, 1))) return rc;
+    h.gen_tc = 1;
+    h.gen_eps = wnorm * 1.001f * 0.001953125f;      // 2^-9
+    h.gen_abs = wnorm * 1e-6f;
   }
   OT_CHECK_CUDA(cudaMemcpy(plan_dev, &plan, sizeof(plan), cudaMemcpyHostToDevice));
   return OT_OK;

@@ -436,7 +436,16 @@ class QuantizedTransformer:
                 wpad = torch.zeros((n_tiles * 32, D), dtype=torch.float32, device=self.dev)
                 wpad[: self.vocab] = self.gen_w
                 self._gen_w4 = wpad.reshape(n_tiles, 32, D // 4, 4).permute(0, 2, 1, 3).contiguous()
-            wst = [ws["ckv"], ws["sckv"], ws["mask"], self.dec_norm[0], self.dec_norm[1], self._gen_w4, self.gen_b, self.tgt_lut, self.pe]
+            if getattr(self, "_gen_w16", None) is None and self.vocab <= 8 * 576:
+                # screening generator of the cluster decoder: fp16 copy of the weight, 8 x 576 rows (zero past the vocabulary), behind a
+                # 1024-byte header holding max_v ||w_v||_2 (the bound on |fp16 tensor-core logit - exact logit| scales with it)
+                blob = torch.zeros(1024 + 8 * 576 * D * 2, dtype=torch.uint8, device=self.dev)
+                blob[:4].view(torch.float32)[0] = float(torch.linalg.vector_norm(self.gen_w.double(), dim=1).max())
+                w16 = blob[1024:].view(torch.float16).reshape(8 * 576, D)
+                w16[: self.vocab] = self.gen_w.to(torch.float16)
+                self._gen_w16 = blob
+            wst = [ws["ckv"], ws["sckv"], ws["mask"], self.dec_norm[0], self.dec_norm[1], self._gen_w4, self.gen_b, self.tgt_lut, self.pe,
+                   getattr(self, "_gen_w16", None)]
             plan = K.ClusterDecoderPlan(layers, wst, n_layers=self.n_layers, B=B, S=S, cap=self.max_len, vocab=self.vocab, ys=ws["ys"],
                                         spc=self.sentences_per_cluster, trace=trace)
             ws["plan"] = plan

@@ -393,7 +393,7 @@ class ClusterDecoderPlan:
         self.trace = torch.zeros(256, dtype=torch.int64, device=dev) if trace else None
         flat_l = [t for layer in layers for t in layer]
         assert len(flat_l) == 28 * n_layers
-        ws_all = list(ws_tensors) + [ys, self.trace, None]
+        ws_all = list(ws_tensors[:9]) + [ys, self.trace, ws_tensors[9] if len(ws_tensors) > 9 else None]
         assert len(ws_all) == 12
         for t in flat_l + ws_all:
             if t is not None and not t.is_contiguous() and t.dim() > 1 and t.stride(-1) != 1:

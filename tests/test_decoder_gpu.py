@@ -107,3 +107,38 @@ def test_persistent_decoder_with_an_injected_step(decoder):
         assert torch.equal(ys_p[:, :step + 1], golden[:, :step + 1])
         differs += int(not torch.equal(ys_p, golden))
     assert ep.persistent_steps > 0
+
+
+@pytest.mark.parametrize("kind", ["fp16_overflow", "nan_bias", "near_ties", "exact_only"])
+def test_screening_generator_corner_cases(kind, monkeypatch):
+    """The cluster decoder's generator screens the vocabulary on the tensor cores (fp16) and re-evaluates the entries within the error
+    bound of the maximum with the exact fp32 chain (ot_cdecoder.cu phase_generator_tc): tokens must equal the per-op path's
+      * when the fp16 copy overflows (huge generator weights: every CTA of a cluster falls back to the exact generator),
+      * when a logit is NaN (a NaN bias entry ranks above every number, as torch.max / np.argmax),
+      * when MANY entries sit within the bound (duplicated weight rows: exact ties -> lowest index wins; near ties),
+      * and with the screening switched off (OT_CD_GEN_TC=0)."""
+    from onnx_transformer_b200.engine import QuantizedTransformer
+    fw = W.init_float_weights(3, 211, 197, 2, randomize_norms=True)
+    gw, gb = fw["generator.proj.weight"].copy(), fw["generator.proj.bias"].copy()
+    if kind == "fp16_overflow":
+        gw *= 3.0e6
+    elif kind == "nan_bias":
+        gb[77] = np.nan
+    elif kind == "near_ties":
+        gw[10:60] = gw[5]                        # 51 identical rows: exact ties
+        gb[10:60] = gb[5]
+        gw[100:140] = gw[5] * (1.0 + 1e-4)       # and 40 rows within the screening bound
+        gb[100:140] = gb[5]
+    else:
+        monkeypatch.setenv("OT_CD_GEN_TC", "0")
+    fw["generator.proj.weight"], fw["generator.proj.bias"] = gw, gb
+    ep = QuantizedTransformer(fw, n_layers=2, max_len=12, persistent=True, decoder="cluster")
+    eg = QuantizedTransformer(fw, n_layers=2, max_len=12, persistent=False)
+    for B, S in ((11, 17), (8, 9)):
+        ids, mask = W.synthetic_tokens(B * S, B, S, 211, min_len=4)
+        idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+        ys_p = ep.greedy_decode(idt, mt, 12)
+        ys_g = eg.greedy_decode(idt, mt, 12)
+        assert torch.equal(ys_p, ys_g), kind
+    if kind == "nan_bias":
+        assert bool((ys_p[:, 1:] == 77).all())

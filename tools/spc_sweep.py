@@ -31,4 +31,7 @@ for spc in [int(x) for x in (sys.argv[1:] or ["8", "6", "5", "4"])]:
     phases, step_us = bench.persistent_phase_trace(eng, ws, 64, 64)
     print("spc=%d clusters=%d  %.3f ms per decode  %.1f us/step (traced %.1f)  tokens_equal=%s" % (spc, (64 + spc - 1) // spc, ms, ms * 1e3 / 71, step_us, bool(torch.equal(ys, ref))))
     print("   ", phases, flush=True)
+    tr = eng._last_trace
+    if tr[240] > 0:      # gen marks: operands ready, MMA + epilogue done, maxima gathered, decision made, phase end (us since the step began)
+        print("    generator marks (us):", [round((int(tr[k]) - int(tr[255])) / 1e3, 2) for k in (240, 241, 242, 243, 254)])
     del eng
