@@ -580,7 +580,9 @@ def main():
                         "algorithmic_bytes_per_greedy_step": parts, "share_of_step": kernel_ms / (total_ms / args.steps),
                         "greedy_step_us": kernel_ms * 1e3 / n_dec, "traced_greedy_step_us": step_us, "phase_us_per_greedy_step": phases,
                         "note": "working set (weights 31 MB + K/V caches 54 MB) is L2-resident; a greedy step at batch 64 is a chain of "
-                                "~68 dependent phases, each bound by exchange + instruction latency, not by bandwidth (DESIGN.md 4/7)"}
+                                "~68 dependent phases, each bound by exchange + instruction latency, not by bandwidth (DESIGN.md 4/7); "
+                                "algorithmic bytes keep round 1's definition (every weight once per step incl. the fp32 generator matrix) "
+                                "although the screening generator now reads an fp16 copy (4.7 MB) + a few fp32 rows per step"}
         else:
             fam, step_us = decode_family_timeline(eng, ws, B, S)
             nbytes = decode_family_bytes(eng, B, S)

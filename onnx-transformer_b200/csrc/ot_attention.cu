@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256, QT <= 8 ? 2 : 1) attention_q8_kernel(cons
   const int step = a.step_dev ? *a.step_dev : 0;
   const int Tk = a.step_dev ? step + a.Tq : a.Tk;
   const int q_pos0 = a.step_dev ? step : a.q_pos0;
+  if (a.step_dev && (step < 0 || step + a.Tq > a.Tk_cap)) return;      // a device-side step past the cache capacity: never append out of bounds
   const int Tk_pad = (Tk + 31) & ~31;
 
   int8_t* Ks = reinterpret_cast<int8_t*>(smem);                        // [Tk][kKPitch]
@@ -534,6 +535,7 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(const AttnArgs a)
   const int step = a.step_dev ? *a.step_dev : 0;
   const int Tk = a.step_dev ? step + 1 : a.Tk;
   const int q_pos0 = a.step_dev ? step : a.q_pos0;
+  if (a.step_dev && (step < 0 || step + 1 > a.Tk_cap)) return;         // a device-side step past the cache capacity: never append out of bounds
   const int b = blockIdx.x;
   AttnDecRow r;
   r.q = a.q + static_cast<int64_t>(b) * a.ldq;

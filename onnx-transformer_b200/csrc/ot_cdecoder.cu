@@ -1378,6 +1378,17 @@ __global__ void __launch_bounds__(kThreads, 1) cdecoder_kernel(const CdPlan* __r
 using namespace ot;
 using namespace ot::cd;
 
+#include <mutex>
+#include <unordered_map>
+
+// Host-side record of what a device plan was built for: ot_cdecoder_run checks its arguments against it (a mismatching B / spc would
+// change the cluster count and the indexing; t0 + n_steps past the cache capacity would write the KV caches and ys out of bounds).
+namespace {
+struct CdPlanInfo { int B, spc, cap; };
+std::mutex g_plan_mu;
+std::unordered_map<const void*, CdPlanInfo> g_plans;
+}  // namespace
+
 extern "C" int ot_cdecoder_plan_size(void) { return static_cast<int>(sizeof(CdPlan)); }
 
 // layer_ptrs: n_layers x 28 device pointers in the order
@@ -1436,6 +1447,10 @@ extern "C" int ot_cdecoder_plan_build(void* plan_dev, int n_layers, int B, int S
     h.gen_abs = wnorm * 1e-6f;
   }
   OT_CHECK_CUDA(cudaMemcpy(plan_dev, &plan, sizeof(plan), cudaMemcpyHostToDevice));
+  {
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    g_plans[plan_dev] = CdPlanInfo{B, spc, cap};
+  }
   return OT_OK;
 }
 
@@ -1443,11 +1458,20 @@ extern "C" int ot_cdecoder_plan_build(void* plan_dev, int n_layers, int B, int S
 extern "C" int ot_cdecoder_run(const void* plan_dev, int B, int spc, int t0, int n_steps, void* stream) {
   OT_REQUIRE_DEVICE();
   OT_REQUIRE(plan_dev && B >= 1 && spc >= 1 && spc <= kCS && t0 >= 0 && n_steps >= 0, "bad arguments");
+  {
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    auto it = g_plans.find(plan_dev);
+    OT_REQUIRE(it != g_plans.end(), "plan_dev was not built by ot_cdecoder_plan_build in this process");
+    OT_REQUIRE(it->second.B == B && it->second.spc == spc, "B / spc differ from what the plan was built for");
+    OT_REQUIRE(t0 + n_steps <= it->second.cap - 1, "t0 + n_steps exceeds the KV-cache capacity of the plan (cap - 1 greedy steps)");
+  }
   if (n_steps == 0) return OT_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};          // cudaFuncSetAttribute applies per device
+  int dev = 0;
+  OT_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     OT_CHECK_CUDA(cudaFuncSetAttribute(cdecoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal + 1024));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int n_clusters = (B + spc - 1) / spc;
   cudaLaunchConfig_t cfg = {};

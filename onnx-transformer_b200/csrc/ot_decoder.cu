@@ -873,6 +873,13 @@ extern "C" int ot_decoder_plan_size(void) { return static_cast<int>(sizeof(MkPla
 //   ln1_g ln1_b ln2_g ln2_b ln3_g ln3_b | qkv_w qkv_sw qkv_b | o_w o_sw o_b | cq_w cq_sw cq_b | co_w co_sw co_b |
 //   w1_w w1_sw w1_b | w2_w w2_sw w2_b | kc vc skc svc
 // ws_ptrs: x xq sx acc cq cs hq sh rowmax ckv sckv mask fin_g fin_b houtT gen_wt gen_b gen_pv gen_pi tgt_lut pe ys bar trace
+#include <mutex>
+#include <unordered_map>
+namespace {
+std::mutex g_mk_mu;
+std::unordered_map<const void*, int> g_mk_caps;      // plan -> KV-cache capacity it was built for (checked by ot_decoder_run)
+}  // namespace
+
 extern "C" int ot_decoder_plan_build(void* plan_dev, int n_layers, int B, int S, int cap, int vocab, int64_t ys_ld,
                                      const void* const* layer_ptrs, const void* const* ws_ptrs) {
   OT_REQUIRE_DEVICE();
@@ -921,6 +928,10 @@ extern "C" int ot_decoder_plan_build(void* plan_dev, int n_layers, int B, int S,
       if ((rc = get_tensor_map(&plan.map_w[l][w], p[6 + 3 * w], wn[w], wk[w], wk[w], kMkBN, 128, true))) return rc;
   }
   OT_CHECK_CUDA(cudaMemcpy(plan_dev, &plan, sizeof(plan), cudaMemcpyHostToDevice));
+  {
+    std::lock_guard<std::mutex> lock(g_mk_mu);
+    g_mk_caps[plan_dev] = cap;
+  }
   return OT_OK;
 }
 
@@ -928,11 +939,20 @@ extern "C" int ot_decoder_plan_build(void* plan_dev, int n_layers, int B, int S,
 extern "C" int ot_decoder_run(const void* plan_dev, unsigned int* bar_dev, int t0, int n_steps, void* stream) {
   OT_REQUIRE_DEVICE();
   OT_REQUIRE(plan_dev && bar_dev && t0 >= 0 && n_steps >= 0, "bad arguments");
+  {
+    std::lock_guard<std::mutex> lock(g_mk_mu);
+    auto it = g_mk_caps.find(plan_dev);
+    OT_REQUIRE(it != g_mk_caps.end(), "plan_dev was not built by ot_decoder_plan_build in this process");
+    OT_REQUIRE(t0 + n_steps <= it->second - 1, "t0 + n_steps exceeds the KV-cache capacity of the plan (cap - 1 greedy steps)");
+  }
   if (n_steps == 0) return OT_OK;
-  static int grid = 0;
+  static int grids[64] = {};              // per device: cudaFuncSetAttribute and the SM count are per device
+  int dev = 0;
+  OT_CHECK_CUDA(cudaGetDevice(&dev));
+  OT_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  int& grid = grids[dev];
   if (grid == 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    OT_CHECK_CUDA(cudaGetDevice(&dev));
+    int sms = 0, per_sm = 0;
     OT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     OT_CHECK_CUDA(cudaFuncSetAttribute(decoder_steps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal + 1024));
     OT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decoder_steps_kernel, kMkThreads, kSmemTotal + 1024));

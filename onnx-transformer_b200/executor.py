@@ -175,8 +175,12 @@ def _h_binary(op):
 
 def _h_round(node, ins, wd):
     out = K.unary("Round", ins[0])
-    # integer-valued result: keep an int8 copy for the tensor-core path (values of dialect A lie in [-127, 127])
-    _meta(wd)[node.output[0]] = ("q", K.cast(out, torch.int8))
+    # integer-valued result: keep an int8 copy for the tensor-core path -- only behind the quantizer pattern of dialect A
+    # (Round of a Div / Clip output: x / (max(|x|, 1e-5) / 127) lies in [-127, 127]); a Round of anything else (arbitrary .onnx
+    # files: values may leave the int8 range) stays on the fp32 MatMul
+    prod = _meta(wd).setdefault("__producers__", {}).get(node.input[0])
+    if prod in ("Div", "Clip"):
+        _meta(wd)[node.output[0]] = ("q", K.cast(out, torch.int8))
     return out
 
 
@@ -465,7 +469,10 @@ def run_node(node, input_tensors: List[Optional[torch.Tensor]], weight_dict) -> 
     handler = HANDLERS.get(node.op_type)
     if handler is None:
         raise K.OtError("no CUDA handler for op %r (node %s): this executor has no CPU fallback" % (node.op_type, node.name))
-    return handler(node, input_tensors, weight_dict)
+    out = handler(node, input_tensors, weight_dict)
+    if node.output:
+        _meta(weight_dict).setdefault("__producers__", {})[node.output[0]] = node.op_type      # provenance for _h_round
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- reference API
