@@ -531,13 +531,15 @@ def main():
     persistent = ws.get("plan") is not None
     eng.decoder_events = [] if persistent else None     # CUDA events around every decoder_steps_kernel launch of the timed region
     launches_per_graph = ws.get("graph_launches", 0)
-    l0, r0 = K._lib.launch_count(), eng.graph_replays
+    l0, r0, f0 = K._lib.launch_count(), eng.graph_replays, eng.front_replays
+    front_launches = (ws.get("front") or {}).get("launches", 0)
     sync_all()
     sampler.mark_begin()
     step_ms = timed_loop(one_step, args.steps)
     total_ms = float(sum(step_ms))
     sync_all()
-    launches = (K._lib.launch_count() - l0) + (eng.graph_replays - r0) * launches_per_graph
+    # kernels launched directly + kernels replayed by the CUDA graphs (per-op greedy step; encoder + cross-K/V front graph)
+    launches = (K._lib.launch_count() - l0) + (eng.graph_replays - r0) * launches_per_graph + (eng.front_replays - f0) * front_launches
     clocks = sampler.stop()
     dec_events, eng.decoder_events = eng.decoder_events, None
     for i in range(2):                                   # the host-buffer path has its own first-call costs (allocations, pinned copies)

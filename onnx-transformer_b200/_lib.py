@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libot_b200.so")
+# OT_B200_LIB: a development override (A/B builds of one kernel, tools/build_variant.py); the library must exist either way
+LIB_PATH = os.environ.get("OT_B200_LIB") or os.path.join(HERE, "libot_b200.so")
 
 OT_OK, OT_EINVAL, OT_ECUDA, OT_ENODEV = 0, -1, -2, -3
 

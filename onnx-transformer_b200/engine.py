@@ -22,6 +22,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -200,6 +202,13 @@ class QuantizedTransformer:
         # parity hook (tests/test_fullsize_parity_gpu.py): when a dict, encode() / the per-op greedy step store a clone of the operands and
         # results of every launch site under "<module><layer>.<name>" so each MatMul can be re-checked on the model's own operands
         self.capture: Optional[dict] = None
+        # encoder attention: RowQuant of the merged context rows inside the tensor-core kernel (cluster of the 8 head CTAs) instead of a
+        # second launch over an fp32 context buffer (bit-identical; tests/test_kernels_gpu.py)
+        self.fuse_ctx_quant = os.environ.get("OT_ENC_FUSE_CTXQ", "1") != "0"
+        # fault-free decodes replay encoder + cross-K/V projection + decode-state reset as ONE CUDA graph (~50 launches whose host
+        # side, ~15 us each through ctypes, was 7 % of a batch-64 decode); the persistent decoder kernel follows as a plain launch
+        self.front_graph = os.environ.get("OT_FRONT_GRAPH", "1") != "0"
+        self.front_replays = 0
         torch.cuda.synchronize(self.dev)
 
     def _cap(self, prefix: str, **tensors):
@@ -327,7 +336,7 @@ class QuantizedTransformer:
                            # 32 <= S <= 128: the tensor-core kernel quantizes the merged rows itself when no fp32 context is asked for
                            # (cluster of the 8 head CTAs: 199 us vs 172 + 35 us for attention + rowquant_kernel at cfg3); captures and
                            # the CUDA-core kernels of other lengths go through the fp32 context
-                           want_ctx=(cp is not None) or not (32 <= S <= 128), ctx=ws["ctx"], want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"],
+                           want_ctx=(self.capture is not None) or not self.fuse_ctx_quant or not (32 <= S <= 128), ctx=ws["ctx"], want_q=True, ctx_q=ws["cq"], ctx_s=ws["cs"],
                            **fk("qk", "pv"))
             self._cap(cp, qkv=ws["qkv"], sqkv=ws["sqkv"], ctx=ws["ctx"], cq=ws["cq"], cs=ws["cs"])
             L["o"].gemm(ws["cq"], ws["cs"], residual=x,
@@ -550,6 +559,37 @@ class QuantizedTransformer:
         self._cap("dec", x_final=x, hout=ws["hout"], logits=ws["logits"], next=ws["next"])
         K.append_token(ws["ys"], ws["next"], step)
 
+    def _front(self, ws: dict, B: int, S: int, src_ids: torch.Tensor, src_mask: torch.Tensor, start_symbol: int):
+        """Everything of a fault-free batch decode in front of the persistent decoder -- embedding, 6 encoder layers, final norm, the
+        cross-attention K/V projection, the reset of ys / step -- as one CUDA-graph replay over static buffers."""
+        fr = ws.get("front")
+        if fr is None or fr["start"] != start_symbol:
+            fr = dict(start=start_symbol, ids=torch.empty((B, S), dtype=torch.int64, device=self.dev), graph=None)
+            ws["front"] = fr
+
+        def body():
+            memory = self.encode(fr["ids"], ws["mask"])
+            self._prepare_cross_kv(ws, memory, None)
+            ws["ys"].zero_()
+            ws["ys"][:, 0] = start_symbol
+            ws["step"].zero_()
+            return memory
+
+        fr["ids"].copy_(src_ids)
+        ws["mask"].copy_(src_mask.reshape(B, S))          # bool / uint8 -> uint8 in the copy kernel
+        if fr["graph"] is None:
+            body()                                           # eager once: function attributes, TMA descriptor cache, workspaces
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            n0 = K._lib.launch_count()
+            with torch.cuda.graph(g):
+                fr["memory"] = body()
+            fr["launches"] = K._lib.launch_count() - n0
+            fr["keep"] = self._enc_workspace(B * S)          # the graph holds raw pointers into these buffers
+            fr["graph"] = g
+        fr["graph"].replay()
+        self.front_replays += 1
+
     def greedy_decode(self, src_ids: torch.Tensor, src_mask: torch.Tensor, max_len: Optional[int] = None, start_symbol: int = W.BOS_ID,
                       fault: Optional[FaultSpec] = None, use_graph: bool = True, memory: Optional[torch.Tensor] = None,
                       return_margins: bool = False, per_op_step: Optional[int] = None):
@@ -560,9 +600,25 @@ class QuantizedTransformer:
         B, S = src_ids.shape
         if fault is not None and not isinstance(fault, (FaultSpec, _FaultBatch)):
             fault = _FaultBatch(fault)
+        ws = self._dec_workspace(B, S)
+        if (self.front_graph and memory is None and fault is None and self.capture is None and use_graph and not return_margins
+                and per_op_step is None):
+            plan = self._decoder_plan(ws, B, S)
+            if plan is not None:
+                self._front(ws, B, S, src_ids, src_mask, start_symbol)
+                n = max_len - 1
+                if self.decoder_events is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    plan.run(0, n)
+                    e1.record()
+                    self.decoder_events.append((e0, e1))
+                else:
+                    plan.run(0, n)
+                self.persistent_steps += n
+                return ws["ys"][:, :max_len].clone()
         if memory is None:
             memory = self.encode(src_ids, src_mask, fault=fault)
-        ws = self._dec_workspace(B, S)
         ws["mask"].copy_(src_mask.reshape(B, S).to(torch.uint8))
         self._prepare_cross_kv(ws, memory, fault)
         ws["ys"].zero_()

@@ -133,3 +133,27 @@ def test_cluster_decoder_any_batch_size():
     idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
     assert torch.equal(ep.greedy_decode(idt, mt, 12), eg.greedy_decode(idt, mt, 12))
     assert ep.persistent_steps == 11
+
+
+def test_front_graph_and_fused_context_quant_are_bit_identical():
+    """The CUDA-graph replay of encoder + cross-K/V + state reset (static buffers) against the eager launches, on changing inputs and
+    shapes; the in-kernel RowQuant of the attention context against the two-launch form."""
+    from onnx_transformer_b200.engine import QuantizedTransformer
+    fw = W.init_float_weights(5, 211, 197, 2, randomize_norms=True)
+    eg = QuantizedTransformer(fw, n_layers=2, max_len=12)
+    ee = QuantizedTransformer(fw, n_layers=2, max_len=12)
+    ee.front_graph = False
+    ee.fuse_ctx_quant = False
+    assert eg.front_graph and eg.fuse_ctx_quant
+    shapes = [(9, 40, 1), (9, 40, 2), (5, 33, 3), (9, 40, 4), (9, 40, 1)]
+    for B, S, seed in shapes:
+        ids, mask = W.synthetic_tokens(seed, B, S, 211, min_len=3)
+        idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+        a, b = eg.greedy_decode(idt, mt), ee.greedy_decode(idt, mt)
+        assert torch.equal(a, b), (B, S, seed)
+        assert torch.equal(eg.encode(idt, mt), ee.encode(idt, mt))
+    assert eg.front_replays == len(shapes) and ee.front_replays == 0
+    # a start symbol other than the captured one rebuilds the graph
+    ids, mask = W.synthetic_tokens(7, 9, 40, 211, min_len=3)
+    idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    assert torch.equal(eg.greedy_decode(idt, mt, start_symbol=3), ee.greedy_decode(idt, mt, start_symbol=3))
