@@ -422,11 +422,59 @@ def cfg1_executor_decode(dev):
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     steps = timings["decoder_step_s"]
-    return {"batch": 1, "src_len": 72, "greedy_steps": MAX_LEN - 1, "seconds": dt, "tokens_per_s": (MAX_LEN - 1) / dt,
+    # the same decode with whole-pass CUDA-graph replay in run_module (executor.enable_graph_replay): the first sweep over the 71 prefix
+    # lengths captures one graph per length, the following sweeps replay them -- the steady state of a caller that decodes many sentences
+    replay = None
+    try:
+        X.enable_graph_replay(True)
+        replay = {"note": "the reference's greedy loop with the two prepared weight_dicts kept across sentences (a captured pass belongs to "
+                          "its weight_dict); sweep 0 walks / captures one graph per prefix length, sweep 3 (timed: tokens_per_s) replays"}
+        replay.update(cfg1_replay_loop(model, ids, mask, enc, dec, dev))
+        replay["tokens_equal_to_node_walk"] = bool(torch.equal(replay.pop("ys"), ys))
+    except Exception as exc:       # noqa: BLE001
+        replay = {"error": str(exc)[:300]}
+    finally:
+        X.enable_graph_replay(False)
+    return {"batch": 1, "src_len": 72, "greedy_steps": MAX_LEN - 1, "seconds": dt, "tokens_per_s": (MAX_LEN - 1) / dt, "graph_replay": replay,
             "encoder_s": timings["encoder_s"], "decoder_pass_ms_first_last": [steps[0] * 1e3, steps[-1] * 1e3], "nodes_per_decoder_pass": len(dec.node),
             "tokens_head": [int(t) for t in ys[0, :8].tolist()],
             "note": "wall clock of the Python node walk (one libot_b200.so handler per ONNX node, full-prefix recompute as in the reference); "
                     "the fused engine (value / e2e) is the fast path"}
+
+
+def cfg1_replay_loop(model, ids, mask, enc, dec, dev):
+    """The reference's greedy loop (8-bit_onnx_optimized_custom_inference.py:649-721) with the two prepared weight_dicts kept across
+    sentences: sweep 0 walks / captures, sweeps 1-2 replay; the last sweep is timed."""
+    import torch
+    from onnx_transformer_b200 import decode as D
+    from onnx_transformer_b200 import executor as X
+    src = torch.from_numpy(ids).to(dev)
+    m = torch.from_numpy(mask).to(dev)
+    enc_wd = dec_wd = None
+    out = {}
+    for sweep in range(4):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        enc_in = {"global_in": model.get_src_embed(src), "global_in_1": m}
+        if enc_wd is None:
+            enc_wd, enc_g = X.prepare_inference(enc, enc_in)
+        memory, _ = X.run_module("Encoder", enc_in, enc, enc_wd, enc_g)
+        memory = memory[list(memory.keys())[0]]
+        ys = torch.full((1, 1), 0, dtype=torch.int64, device=dev)
+        for i in range(MAX_LEN - 1):
+            dec_in = {"global_in": model.get_tgt_embed(ys), "global_in_1": memory, "global_in_2": m,
+                      "global_in_3": torch.from_numpy(D.subsequent_mask(ys.shape[1])).to(dev)}
+            if dec_wd is None:
+                dec_wd, dec_g = X.prepare_inference(dec, dec_in)
+            o, _ = X.run_module("Decoder", dec_in, dec, dec_wd, dec_g)
+            o = o[list(o.keys())[0]]
+            ys = torch.cat([ys, model.next_word(o[:, -1]).reshape(1, 1)], dim=1)
+        torch.cuda.synchronize(dev)
+        out["sweep%d_s" % sweep] = time.perf_counter() - t0
+    out["tokens_per_s"] = (MAX_LEN - 1) / out["sweep3_s"]
+    out["stats"] = dict(X.replay_stats)
+    out["ys"] = ys
+    return out
 
 
 def cfg1_cpu_walk(steps=6):

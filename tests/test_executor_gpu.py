@@ -201,3 +201,54 @@ def test_greedy_decode_through_the_executor_matches_oracle(setup, B):
     for b in range(B):
         t = ph.first_divergence(ys_e[b], ref[b])
         assert t < 0 or margins[b, t] < ph.margin_bound(), (b, t, margins[b, t])
+
+
+def test_graph_replay_of_whole_passes_equals_the_node_walk(setup):
+    """run_module with CUDA-graph replay enabled: captured / replayed passes return the node walk's output bit for bit, on changing
+    input values and input shapes; fault passes and the eager default are untouched."""
+    ex, w, enc, dec, x, mask = setup
+    from onnx_transformer_b200 import decode as D
+    rng = np.random.default_rng(3)
+    ins0 = {"global_in": x, "global_in_1": mask}
+    wd_e, g_e = ex.prepare_inference(enc, ins0)            # eager twin
+    wd_r, g_r = ex.prepare_inference(enc, ins0)
+    stats0 = dict(ex.replay_stats)
+    ex.enable_graph_replay(True)
+    try:
+        for k in range(5):
+            xin = (x + np.float32(0.25 * k) * rng.standard_normal(x.shape).astype(np.float32)) if k else x
+            ins = {"global_in": xin, "global_in_1": mask}
+            out_r, wd_r = ex.run_module("Encoder", ins, None, wd_r, g_r, None)
+            ex.enable_graph_replay(False)
+            out_e, wd_e = ex.run_module("Encoder", ins, None, wd_e, g_e, None)
+            ex.enable_graph_replay(True)
+            assert torch.equal(out_r["global_out"], out_e["global_out"]), k
+        # pass 0 walked (warm-up), pass 1 captured, passes 2-4 replayed
+        d = {k: ex.replay_stats[k] - stats0[k] for k in stats0}
+        assert d == {"eager": 1, "captured": 1, "replayed": 3, "failed": 0}, d
+        # a fault pass on the same weight_dict takes the node walk and sees every intermediate
+        p = {"inject_type": "RANDOM", "faulty_operation_name": "MatMul_6", "faulty_tensor_name": "", "faulty_trace": [], "faulty_bit_position": 3,
+             "targetted_module": "Encoder",
+             "rng_draws": {"target_indices": [1, 2, 77], "value": 3.5}}
+        _, wd_r = ex.run_module("Encoder", ins0, None, wd_r, g_r, p)
+        assert all(n.output[0] in wd_r for n in enc.node)
+        # the decoder over growing prefixes (one captured graph per prefix length), twice: second sweep replays every length
+        memory = om.encode(w, x, mask, "int-exact", 2)
+        ys = np.array([[0, 7, 9, 3, 11], [0, 4, 33, 2, 5]])
+        wd_d = wd_de = None
+        for sweep in range(3):
+            for T in range(1, 5):
+                temb = ox.embed(ys[:, :T], w["tgt_embed.0.lut.weight"], ox.positional_encoding(32))
+                ins = {"global_in": temb, "global_in_1": memory, "global_in_2": mask, "global_in_3": D.subsequent_mask(T)}
+                if wd_d is None:
+                    wd_d, g_d = ex.prepare_inference(dec, ins)
+                    wd_de, g_de = ex.prepare_inference(dec, ins)
+                out_r, wd_d = ex.run_module("Decoder", ins, None, wd_d, g_d, None)
+                ex.enable_graph_replay(False)
+                out_e, wd_de = ex.run_module("Decoder", ins, None, wd_de, g_de, None)
+                ex.enable_graph_replay(True)
+                assert torch.equal(out_r["global_out"], out_e["global_out"]), (sweep, T)
+        assert ex.replay_stats["failed"] == stats0["failed"]
+        assert len(wd_d[ex.REPLAY_KEY]["records"]) == 4
+    finally:
+        ex.enable_graph_replay(False)
