@@ -71,19 +71,12 @@ __device__ __forceinline__ f2_t ln_fma2(f2_t a, f2_t b, f2_t c) {
   return r;
 }
 
-__global__ void __launch_bounds__(256) layernorm_quant512_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                                 const float* __restrict__ beta, int64_t rows, float eps,
-                                                                 int8_t* __restrict__ q_out, float* __restrict__ s_out,
-                                                                 const f2_t k_neg0, const f2_t k_one, const f2_t k_magic) {
-  pdl_wait();
-  pdl_trigger();
-  const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * 512);
-  float4 v[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = __ldg(xr + i * 32 + lane);
+// One row per warp and pass; a warp walks rows warp, warp + W, ... (W = warps of the grid) with the NEXT row's 2 KB requested before the
+// current row's arithmetic starts: a warp that loads, computes and exits leaves the memory pipe idle during its ~0.5 us of dependent
+// reductions and quotients (cfg3: 49 us per launch = 3.4 TB/s; the loads of row i+1 now fly under the arithmetic of row i).
+__device__ __forceinline__ void ln512_row(float4 (&v)[4], const float4* xr, int lane, int64_t row, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, float eps, int8_t* __restrict__ q_out, float* __restrict__ s_out,
+                                          const f2_t k_neg0, const f2_t k_one, const f2_t k_magic) {
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
   float sum = 0.f;
@@ -164,6 +157,31 @@ __global__ void __launch_bounds__(256) layernorm_quant512_kernel(const float* __
     }
   }
   if (lane == 0) s_out[row] = s;
+}
+
+__global__ void __launch_bounds__(256) layernorm_quant512_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, int64_t rows, float eps,
+                                                                 int8_t* __restrict__ q_out, float* __restrict__ s_out,
+                                                                 const f2_t k_neg0, const f2_t k_one, const f2_t k_magic) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[4], vn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(x + row * 512) + i * 32 + lane);
+  for (; row < rows; row += stride) {
+    const int64_t nrow = row + stride;
+    if (nrow < rows) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vn[i] = __ldg(reinterpret_cast<const float4*>(x + nrow * 512) + i * 32 + lane);
+    }
+    ln512_row(v, reinterpret_cast<const float4*>(x + row * 512), lane, row, gamma, beta, eps, q_out, s_out, k_neg0, k_one, k_magic);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = vn[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,7 +331,10 @@ extern "C" int ot_layernorm_quant(const float* x, const float* gamma, const floa
   const char* fenv = getenv("OT_LN512_MIN_ROWS");          // tests raise it to compare with the general kernel
   const int64_t fast_min_rows = fenv ? atoll(fenv) : 2048;
   if (n == 512 && y_out == nullptr && q_out != nullptr && rows >= fast_min_rows) {
-    OT_CHECK_CUDA(launch_kernel(layernorm_quant512_kernel, dim3(grid), dim3(warps * 32), 0, s, 1, x, gamma, beta, rows, eps, q_out, s_out,
+    // persistent walk: at most 148 SMs x 3 resident CTAs of 8 warps (72 registers) (OT_LN512_CTAS_PER_SM for experiments); small launches keep one row per warp
+    static const int ctas_per_sm = getenv("OT_LN512_CTAS_PER_SM") ? atoi(getenv("OT_LN512_CTAS_PER_SM")) : 3;
+    const unsigned pgrid = std::min<unsigned>(grid, 148u * static_cast<unsigned>(std::max(1, ctas_per_sm)));
+    OT_CHECK_CUDA(launch_kernel(layernorm_quant512_kernel, dim3(pgrid), dim3(warps * 32), 0, s, 1, x, gamma, beta, rows, eps, q_out, s_out,
                                 0x8000000080000000ull, 0x3F8000003F800000ull, 0x4B4000004B400000ull));
     count_launch();
     return OT_OK;
