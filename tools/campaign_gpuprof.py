@@ -44,3 +44,4 @@ for c0 in range(0, 640, 64):
     for k, name in enumerate(["encoder", "cross_kv+reset", "fault_step", "decoder_70"]):
         acc[name] = acc.get(name, 0.0) + ev[k].elapsed_time(ev[k + 1])
 print("GPU ms per faulty batch (OT_MF_PATCH=%s):" % os.environ.get("OT_MF_PATCH", "1"), {k: round(v / 10, 3) for k, v in acc.items()}, "sum %.2f" % (sum(acc.values()) / 10))
+
