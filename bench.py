@@ -342,22 +342,24 @@ def sharded_measurements(eng, dev, rank, world):
     eng._enc_ws = {}
     torch.cuda.empty_cache()
     ids_np, mask_np = W.synthetic_tokens(11, 64, 64)
-    trials = C.make_trials(2048, 0, 64, 64)
-    C.run_trials_batched(eng, ids_np, mask_np, trials[:64 * world], 64, None, rank, world)            # warm-up
+    tpd = C.trials_per_decode(eng)          # one wave of decoder clusters: 120 trials per faulty decode on a B200
+    trials = C.make_trials(64 * tpd, 0, 64, 64)
+    C.run_trials_batched(eng, ids_np, mask_np, trials[:tpd * world], tpd, None, rank, world)            # warm-up
     torch.cuda.synchronize(dev)
     P.barrier()
     t0 = time.perf_counter()
-    res = C.run_trials_batched(eng, ids_np, mask_np, trials, 64, None, rank, world)
+    res = C.run_trials_batched(eng, ids_np, mask_np, trials, tpd, None, rank, world)
     torch.cuda.synchronize(dev)
     dt = P.max_over_ranks([time.perf_counter() - t0], device=dev)[0]
     from collections import Counter
     counts = Counter(r["outcome"] for r in res)
     names = sorted(set(counts) | {"masked", "changed", "no-EOS"})
     tot = P.sum_over_ranks([counts.get(k, 0) for k in names], device=dev)
-    out["cfg5_fault_injection"] = {"trials": len(trials), "n_gpus": world, "trials_per_s": len(trials) / dt,
+    out["cfg5_fault_injection"] = {"trials": len(trials), "n_gpus": world, "trials_per_s": len(trials) / dt, "trials_per_decode": tpd,
                                    "outcomes": {k: int(v) for k, v in zip(names, tot) if v},
-                                   "note": "wall clock, max over ranks, incl. one golden batch decode per rank; 64 trials per faulty greedy decode "
-                                           "(one fault per batch row); random-init weights never emit </s> (tests/test_fullsize_parity_gpu.py "
+                                   "note": "wall clock, max over ranks, incl. one golden batch decode per rank; trials_per_decode trials per faulty greedy "
+                                           "decode (one fault per batch row; one wave of decoder clusters: the step time does not depend on how many of the "
+                                           "15 co-resident clusters are in use); random-init weights never emit </s> (tests/test_fullsize_parity_gpu.py "
                                            "pins the three outcome classes on an EOS-capable model)"}
     return out
 
@@ -388,6 +390,27 @@ def rank0_measurements(eng, dev):
         torch.cuda.empty_cache()
     except Exception as exc:      # side measurement: never fail the headline line
         out["cfg4_int4_weights_decode"] = {"error": str(exc)[:200]}
+    try:
+        # NOT the headline configuration (BASELINE names batch 64): the same greedy decode with one full wave of decoder clusters in use
+        from onnx_transformer_b200 import kernels as K
+        bw = K.cdecoder_max_sentences()
+        iw_np, mw_np = W.synthetic_tokens(1000, bw, 64)
+        iw, mw = torch.from_numpy(iw_np).to(dev), torch.from_numpy(mw_np).to(dev)
+        for _ in range(2):
+            eng.greedy_decode(iw, mw)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            eng.greedy_decode(iw, mw)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        msw = e0.elapsed_time(e1) / 3
+        out["decode_one_cluster_wave"] = {"batch": bw, "src_len": 64, "ms": msw, "tokens_per_s": bw * (MAX_LEN - 1) / (msw * 1e-3),
+                                          "note": "not the headline config: batch = 8 sentences x the decoder clusters one GPU keeps resident (15 on a B200); a greedy step "
+                                                  "takes the same time for 8 clusters (batch 64) as for 15"}
+    except Exception as exc:
+        out["decode_one_cluster_wave"] = {"error": str(exc)[:200]}
     try:
         out["cfg1_executor_greedy_decode"] = cfg1_executor_decode(dev)
     except Exception as exc:

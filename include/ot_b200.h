@@ -262,6 +262,10 @@ int ot_cdecoder_plan_size(void);
 int ot_cdecoder_plan_build(void* plan_dev, int n_layers, int B, int S, int cap, int vocab, int spc, int64_t ys_ld,
                            const void* const* layer_ptrs, const void* const* ws_ptrs);
 int ot_cdecoder_run(const void* plan_dev, int B, int spc, int t0, int n_steps, void* stream);
+/* Number of 8-CTA decoder clusters the current device keeps resident at once (15 on a 148-SM B200).  A greedy step takes the same
+ * time whether one or all of them are in use: callers that choose their own batch (fault-trial campaigns) get the most out of a
+ * launch at 8 x *n_out sentences; one cluster more and the launch runs in two waves. */
+int ot_cdecoder_max_clusters(int* n_out);
 
 /* ---- elementwise / shape op family: one CUDA handler per remaining ONNX op name of SURVEY.md 8a -----
  * Unary  (op: 0 Abs 1 Relu 2 Sqrt 3 Round 4 Neg 5 Exp 6 Identity), fp32, n elements. */

@@ -74,6 +74,7 @@ SIGNATURES = {
     "ot_cdecoder_plan_size": (_i, []),
     "ot_cdecoder_plan_build": (_i, [_p, _i, _i, _i, _i, _i, _i, _l, C.POINTER(_p), C.POINTER(_p)]),
     "ot_cdecoder_run": (_i, [_p, _i, _i, _i, _i, _p]),
+    "ot_cdecoder_max_clusters": (_i, [C.POINTER(C.c_int)]),
     "ot_unary_f32": (_i, [_i, _p, _p, _l, _p]),
     "ot_binary_f32": (_i, [_i, _p, _I4, _p, _I4, _p, _I4, _p]),
     "ot_clip_f32": (_i, [_p, _f, _f, _p, _l, _p]),

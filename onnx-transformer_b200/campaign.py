@@ -258,14 +258,27 @@ def run_trials(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials: List[T
     return out
 
 
-def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials: List[Trial], batch: int = 64,
+def trials_per_decode(engine) -> int:
+    """The batch that fills ONE wave of the cluster-resident decoder on this GPU: 8 sentences per co-resident 8-CTA cluster (15
+    clusters = 120 trials on a B200).  A greedy step takes the same time for 1 cluster as for 15 (the chain of exchanges sets it, not
+    the work), so 120 trials decode in the time of 64: 5.1 k -> 8.4 k trials/s on one GPU (tools/campaign_batch_sweep.py); at 128 the
+    launch needs a second wave and the rate halves."""
+    from . import kernels as K
+    if getattr(engine, "decoder", "cluster") != "cluster" or not getattr(engine, "persistent", True):
+        return 64
+    return K.cdecoder_max_sentences()
+
+
+def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials: List[Trial], batch: Optional[int] = None,
                        csv_path: Optional[str] = None, rank: int = 0, world: int = 1, return_tokens: bool = False) -> List[Dict[str, object]]:
-    """Same outcomes as run_trials, `batch` trials per greedy decode: row b of a batch re-decodes trial b's sentence with
-    trial b's fault (one fault per batch unit: ot_linear_w8a8_mf / ot_attention_q8_mf).  The kernels are batch-invariant,
-    so every row equals the batch-1 decode the reference would run."""
+    """Same outcomes as run_trials, `batch` trials per greedy decode (default: trials_per_decode(engine)): row b of a batch re-decodes
+    trial b's sentence with trial b's fault (one fault per batch unit: ot_linear_w8a8_mf / ot_attention_q8_mf).  The kernels are
+    batch-invariant, so every row equals the batch-1 decode the reference would run."""
     import torch
     from .engine import FaultSpec
     dev = engine.dev
+    if batch is None:
+        batch = trials_per_decode(engine)
     ids = torch.from_numpy(src_ids).to(dev)
     mask = torch.from_numpy(src_mask).to(dev)
     golden = engine.greedy_decode(ids, mask).cpu().numpy()
@@ -331,7 +344,8 @@ def main(argv=None):
     ap.add_argument("--directory_name", default="input/encoder")
     ap.add_argument("--module", default="Encoder")
     ap.add_argument("--experiment_output_name", default="results_fault_injection/results.csv")
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=64, help="source sentences the trials draw from")
+    ap.add_argument("--trials-per-decode", type=int, default=0, help="trials per batched faulty decode (0: one wave of decoder clusters, 120 on a B200)")
     ap.add_argument("--src-len", type=int, default=64)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--trials", type=int, default=0)
@@ -361,7 +375,7 @@ def main(argv=None):
         trials = trials_from_targets(targets, args.seed, args.batch, args.src_len, experiments=args.experiments)
     os.makedirs(os.path.dirname(args.experiment_output_name) or ".", exist_ok=True)
     path = args.experiment_output_name if world == 1 else "%s.rank%d" % (args.experiment_output_name, rank)
-    res = run_trials_batched(eng, ids, mask, trials, args.batch, path, rank, world)
+    res = run_trials_batched(eng, ids, mask, trials, args.trials_per_decode or None, path, rank, world)
     res_all = P.gather_records([(r["trial_id"], r["outcome"]) for r in res], world)
     P.destroy_process_group()
     if rank == 0:

@@ -1391,6 +1391,29 @@ std::unordered_map<const void*, CdPlanInfo> g_plans;
 
 extern "C" int ot_cdecoder_plan_size(void) { return static_cast<int>(sizeof(CdPlan)); }
 
+// How many of the decoder's 8-CTA clusters the current device keeps resident at once (cudaOccupancyMaxActiveClusters: 15 on a
+// 148-SM B200 -- clusters live inside GPCs).  A greedy step takes the same time whether 1 or all of them are in use, so callers that
+// choose their own batch (fault-trial campaigns: independent trials) get the most out of a launch at 8 x this many sentences; one
+// cluster more and the launch runs in two waves.
+extern "C" int ot_cdecoder_max_clusters(int* n_out) {
+  OT_REQUIRE_DEVICE();
+  OT_REQUIRE(n_out != nullptr, "null argument");
+  OT_CHECK_CUDA(cudaFuncSetAttribute(cdecoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal + 1024));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kCS * 64);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmTotal + 1024;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  OT_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, cdecoder_kernel, &cfg));
+  *n_out = n;
+  return OT_OK;
+}
+
 // layer_ptrs: n_layers x 28 device pointers in the order
 //   ln1_g ln1_b ln2_g ln2_b ln3_g ln3_b | qkv_w qkv_sw qkv_b | o_w o_sw o_b | cq_w cq_sw cq_b | co_w co_sw co_b |
 //   w1_w w1_sw w1_b | w2_w w2_sw w2_b | kc vc skc svc

@@ -377,6 +377,14 @@ class DecoderPlan:
         _lib.check(rc, "ot_decoder_run")
 
 
+def cdecoder_max_sentences() -> int:
+    """Sentences the cluster-resident decoder advances in ONE wave of thread-block clusters on the current device: 8 per co-resident
+    cluster (ot_cdecoder_max_clusters: 15 clusters = 120 sentences on a B200).  The step time does not depend on how many are in use."""
+    n = C.c_int(0)
+    _lib.check(_lib.load().ot_cdecoder_max_clusters(C.byref(n)), "ot_cdecoder_max_clusters")
+    return 8 * max(1, int(n.value))
+
+
 class ClusterDecoderPlan:
     """Device-resident plan of the cluster-resident greedy decoder (ot_cdecoder_plan_build): groups of `spc` sentences, one
     8-CTA cluster each.  Keeps every tensor it points to alive."""

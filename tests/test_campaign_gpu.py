@@ -115,3 +115,20 @@ def test_pipelined_batched_trials_are_deterministic_and_path_independent():
     assert ep.persistent_steps > 0
     g = run(QuantizedTransformer(fw, persistent=False))
     assert [k for k in a if a[k] != g[k]] == []
+    # (c) with one full wave of decoder clusters per decode (120 trials on a B200) instead of 64: the rows are independent
+    tpd = C.trials_per_decode(ep)
+    assert tpd >= 64 and tpd % 8 == 0
+    hashes = {}
+    orig = C.classify
+
+    def spy(golden, faulty):
+        r = orig(golden, faulty)
+        r["hash"] = hashlib.md5(np.ascontiguousarray(faulty).tobytes()).hexdigest()
+        return r
+    C.classify = spy
+    try:
+        for r in C.run_trials_batched(ep, ids, mask, trials):
+            hashes[r["trial_id"]] = r["hash"]
+    finally:
+        C.classify = orig
+    assert hashes == a

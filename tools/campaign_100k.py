@@ -24,12 +24,13 @@ if world > 1:
 eng = QuantizedTransformer(W.init_float_weights(0))
 ids, mask = W.synthetic_tokens(11, 64, 64)
 trials = C.make_trials(n, 0, 64, 64)
-C.run_trials_batched(eng, ids, mask, trials[:64], 64)
+tpd = int(os.environ.get("OT_TRIALS_PER_DECODE", "0")) or C.trials_per_decode(eng)
+C.run_trials_batched(eng, ids, mask, trials[:2 * tpd], tpd)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
-res = C.run_trials_batched(eng, ids, mask, trials, 64, None, rank, world)
+res = C.run_trials_batched(eng, ids, mask, trials, tpd, None, rank, world)
 torch.cuda.synchronize()
 hist = Counter(r["outcome"] for r in res)
 hist["tokens_changed"] = sum(1 for r in res if not r["tokens_equal"])
@@ -43,7 +44,7 @@ if world > 1:
     dist.barrier()
 dt = time.perf_counter() - t0
 if rank == 0:
-    print(json.dumps({"trials": n, "n_gpus": world, "wall_s": dt, "trials_per_s": n / dt, "outcomes": dict(hist),
+    print(json.dumps({"trials": n, "n_gpus": world, "trials_per_decode": tpd, "wall_s": dt, "trials_per_s": n / dt, "outcomes": dict(hist),
                       "rank0_targets": {"%s/%s" % k: v for k, v in mods.items()}}))
 if world > 1:
     dist.destroy_process_group()
