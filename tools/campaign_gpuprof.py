@@ -11,18 +11,19 @@ from onnx_transformer_b200.engine import FaultSpec, QuantizedTransformer, _Fault
 
 eng = QuantizedTransformer(W.init_float_weights(0))
 ids_np, mask_np = W.synthetic_tokens(11, 64, 64)
-trials = C.make_trials(640, 0, 64, 64)
+trials = C.make_trials(1280, 0, 64, 64)
+B_ = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 dev = eng.dev
 ids, mask = torch.from_numpy(ids_np).to(dev), torch.from_numpy(mask_np).to(dev)
 eng.greedy_decode(ids, mask)
-C.run_trials_batched(eng, ids_np, mask_np, trials[:128], 64)
+C.run_trials_batched(eng, ids_np, mask_np, trials[:2 * B_], B_)
 torch.cuda.synchronize()
-B, S = 64, 64
+B, S = (int(sys.argv[1]) if len(sys.argv) > 1 else 64), 64
 ws = eng._dec_workspace(B, S)
 plan = eng._decoder_plan(ws, B, S)
 acc = {}
-for c0 in range(0, 640, 64):
-    chunk = trials[c0:c0 + 64]
+for c0 in range(0, 10 * B_, B_):
+    chunk = trials[c0:c0 + B_]
     fb = _FaultBatch([FaultSpec(t.module, t.layer, t.target, t.inject_type, t.bit, t.flat_index, t.window_start, t.window_len, t.value_bits, step=0) for t in chunk])
     rows = torch.tensor([t.sentence for t in chunk], dtype=torch.int64, device=dev)
     a, b = ids[rows].contiguous(), mask[rows].contiguous()
