@@ -310,9 +310,18 @@ def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials
                 with open(csv_path + ".ids", "a") as f:
                     f.write("%d\n" % trial.trial_id)
 
+    # Batches of ONE kind (when the shard mixes modules; a directory-driven campaign has one module anyway).  A batch of Encoder-target
+    # trials has no injected decoder step: all of its greedy steps run inside the persistent decoder.  A batch of Decoder-target trials
+    # needs no encoder pass: the encoder output of its rows is the golden one, computed once for the source sentences (as run_trials
+    # does per sentence).  Rows are appended to the CSV as their batch completes; the returned list keeps the order of `trials`.
+    position = {t.trial_id: k for k, t in enumerate(mine)}
+    enc_part = [t for t in mine if t.module != "Decoder"]
+    dec_part = [t for t in mine if t.module == "Decoder"]
+    golden_memory = engine.encode(ids, mask).clone() if dec_part else None
+    chunks = [(enc_part[c0:c0 + batch], False) for c0 in range(0, len(enc_part), batch)]
+    chunks += [(dec_part[c0:c0 + batch], True) for c0 in range(0, len(dec_part), batch)]
     pending = None
-    for i, c0 in enumerate(range(0, len(mine), batch)):
-        chunk = mine[c0:c0 + batch]
+    for i, (chunk, dec_only) in enumerate(chunks):
         specs = [FaultSpec(t.module, t.layer, t.target, t.inject_type, t.bit, t.flat_index, t.window_start, t.window_len, t.value_bits, step=0)
                  for t in chunk]
         rp = rows_pin[i % 2]
@@ -320,7 +329,8 @@ def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials
         rp[:len(chunk)] = torch.tensor([t.sentence for t in chunk], dtype=torch.int64)
         specs = specs + [None] * (batch - len(chunk))
         rows = rp.to(dev, non_blocking=True)
-        ys = engine.greedy_decode(ids[rows].contiguous(), mask[rows].contiguous(), fault=specs)
+        ys = engine.greedy_decode(ids[rows].contiguous(), mask[rows].contiguous(), fault=specs,
+                                  memory=golden_memory[rows] if dec_only else None)
         buf = ys_pin[i % 2]
         buf[:, :ys.shape[1]].copy_(ys, non_blocking=True)
         ev = torch.cuda.Event()
@@ -330,6 +340,7 @@ def run_trials_batched(engine, src_ids: np.ndarray, src_mask: np.ndarray, trials
         pending = (chunk, buf, ev)
     if pending is not None:
         finish(pending)
+    out.sort(key=lambda r: position[r["trial_id"]])
     return out
 
 
