@@ -669,6 +669,7 @@ def prepare_inference(module_path, module_input_values):
 # captured walk live in a memory pool shared by all captured passes (0.6 GB for the full-size decoder instead of 0.6 GB per prefix
 # length) and are not left in weight_dict.  Passes with inject_parameters always take the node walk.
 REPLAY_KEY = "__ot_replay__"
+REPLAY_MAX_GRAPHS = 512       # captured passes kept per weight_dict (one per distinct set of input shapes)
 _replay_enabled = os.environ.get("OT_EXEC_REPLAY", "0") == "1"
 replay_stats = {"eager": 0, "captured": 0, "replayed": 0, "failed": 0}
 
@@ -715,6 +716,8 @@ def _replay_pass(module, input_values, wd, graph):
         if cache["pool"] is None:
             cache["pool"] = g.pool()
         name = list(out_tensors.keys())[0]
+        if len(cache["records"]) >= REPLAY_MAX_GRAPHS:            # bounded: drop the oldest captured pass (dicts keep insertion order)
+            cache["records"].pop(next(iter(cache["records"])))
         rec = cache["records"][sig] = {"graph": g, "inputs": static_in, "out_name": name, "out": out_tensors[name]}
         del out_tensors
         for node in graph.node:                     # the captured intermediates belong to the shared pool: no reference survives
