@@ -41,7 +41,8 @@ constexpr int kTcOffSk = 65536, kTcOffSv = kTcOffSk + 512, kTcOffKeep = kTcOffSv
 constexpr int kTcOffXm = kTcOffBar + 64;               // float [2 key halves][128 rows]: row maxima, then row sums, then context abs-maxima
 constexpr int kTcOffPq = kTcOffXm + 1024;              // float [128]: quantized probability at the faulty column (P / V faults)
 constexpr int kTcOffRq = kTcOffPq + 512;               // float [8 heads][128 rows]: per-head abs-maxima of the merged context rows (written by the cluster)
-constexpr int kTcSmem = kTcOffRq + 8 * 128 * 4 + 1024;
+constexpr int kTcOffKm = kTcOffRq + 8 * 128 * 4;       // float [128]: per key 0 (visible) | -1e9 (masked_fill) | -inf (padding column of the MMA tile)
+constexpr int kTcSmem = kTcOffKm + 512 + 1024;
 static_assert(3 * (kTcSmem + 1024) <= 233472, "three CTAs per SM");
 
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -70,6 +71,11 @@ __device__ __forceinline__ void tc_tmem_wait_st() { asm volatile("tcgen05.wait::
 
 __device__ __forceinline__ void tc_st_async_f32(uint32_t addr, float v, uint32_t mbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ float tc_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ float tc_patch_f32(const OtFault& f, float v) {
   uint32_t bits = __float_as_uint(v);
@@ -102,6 +108,7 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
   float* xm = reinterpret_cast<float*>(smem + kTcOffXm);
   float* spq = reinterpret_cast<float*>(smem + kTcOffPq);
   float* rq = reinterpret_cast<float*>(smem + kTcOffRq);
+  float* kmf = reinterpret_cast<float*>(smem + kTcOffKm);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);              // warp-uniform for the compiler (tcgen05 / elect regions)
@@ -195,7 +202,9 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
       s2 = a.sv[src];
       kp = (a.mask_kind == 1) ? a.key_mask[static_cast<int64_t>(b) * a.mask_stride + tid] : 1;
     }
-    sks[tid] = s1; svs[tid] = s2; keep[tid] = kp;
+    // 1/sqrt(d_k) = 1/8 rides on the key scale: fl(fl(d*sq)*sk)/8 == fl(fl(d*sq)*(sk/8)), a power of two commutes with the rounding
+    sks[tid] = __fmul_rn(s1, 0.125f); svs[tid] = s2; keep[tid] = kp;
+    kmf[tid] = (tid >= Tk) ? -INFINITY : (kp != 0 ? 0.0f : -1e9f);
     const float m = warp_max_f(fabsf(s2));
     if (lane == 0) sred[warp] = m;
     if (FAULT) spq[tid] = 0.f;
@@ -280,7 +289,8 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
   float pq_f_local = 0.f;
   if (wactive && n_chunks > 0) {
     const float sqi = row_ok ? a.sq[(static_cast<int64_t>(b) * Tq + i) * a.sq_stride] : 1.0f;
-    const int causal_last = (a.mask_kind == 2) ? a.q_pos0 + i : 0x7fffffff;
+    const bool causal = a.mask_kind == 2;
+    const int causal_last = causal ? a.q_pos0 + i : 0x7fffffff;
     // ---- pass A: scaled, masked scores + row maximum of this key half; the scores wait in their own TMEM columns between the passes
     //      (ROLLED loops over the 16-key chunks: three CTAs at different phases share the instruction cache)
     uint32_t r[16];
@@ -289,12 +299,12 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
       const int c0 = c_base + 16 * c;
       tmem_ld_32x16(tlane + c0, r);
       tmem_wait_ld();
-      const uint4 kw = *reinterpret_cast<const uint4*>(keep + c0);
-      const uint32_t kbytes[4] = {kw.x, kw.y, kw.z, kw.w};
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
-        const float4 sk4 = *reinterpret_cast<const float4*>(sks + c0 + 4 * q4);
+        const float4 sk4 = *reinterpret_cast<const float4*>(sks + c0 + 4 * q4);      // sk[j] / 8
+        const float4 km4 = *reinterpret_cast<const float4*>(kmf + c0 + 4 * q4);
         const float skv[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
+        const float kmv[4] = {km4.x, km4.y, km4.z, km4.w};
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
           const int jj = 4 * q4 + bb, j = c0 + jj;
@@ -308,16 +318,20 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
               dot += tc_tile_byte(sQ, i, fd) * (flip_int8_bit(kv, f.bit) - kv);
             }
           }
-          float mm = __fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), skv[bb]);                 // MatMul_k_out0
-          if (FAULT && fault_here && f.reserved == OPERAND_SCORES && i == fi && j == fj) mm = tc_patch_f32(f, mm);
-          float sc = __fmul_rn(mm, 0.125f);                                                     // / sqrt(d_k) = / 8, exact
-          const bool visible = ((kbytes[q4] >> (8 * bb)) & 0xFFu) != 0u && j <= causal_last;
-          sc = visible ? sc : -1e9f;                                                            // masked_fill(mask == 0, -1e9)
-          sc = (j < Tk) ? sc : -INFINITY;                                                       // padding columns of the MMA tile: not keys
-          mx = fmaxf(mx, sc);
+          float sc = __fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), skv[bb]);                  // MatMul_k_out0 / sqrt(d_k)
+          if (FAULT && fault_here && f.reserved == OPERAND_SCORES && i == fi && j == fj)        // the patch addresses MatMul_k_out0 itself
+            sc = __fmul_rn(tc_patch_f32(f, __fmul_rn(sc, 8.0f)), 0.125f);
+          sc = (kmv[bb] == 0.0f) ? sc : kmv[bb];               // masked_fill(mask == 0, -1e9); padding columns of the MMA tile: -inf
           r[jj] = __float_as_uint(sc);
         }
       }
+      if (causal && c0 + 15 > causal_last) {                   // warp-uniform test on the launch kind, then per row
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj)
+          if (c0 + jj > causal_last && c0 + jj < Tk) r[jj] = __float_as_uint(-1e9f);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) mx = fmaxf(mx, __uint_as_float(r[jj]));
       tc_tmem_st_32x16(tlane + c0, r);
       tc_tmem_wait_st();
     }
@@ -337,7 +351,7 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
       tmem_wait_ld();
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) {
-        const float ev = expf(__fsub_rn(__uint_as_float(r[jj]), mx));
+        const float ev = tc_ex2(__fmul_rn(__fsub_rn(__uint_as_float(r[jj]), mx), 1.4426950408889634f));   // exp(s - max): FADD, FMUL, MUFU
         sum += ev;
         r[jj] = __float_as_uint(ev);
       }
@@ -349,7 +363,7 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
   __syncthreads();
   sum = __fadd_rn(xm[i], xm[128 + i]);                       // fixed order: keys [0, 64) + keys [64, 128)
   if (wactive && n_chunks > 0) {
-    const float inv_sum = __frcp_rn(sum);
+    const float inv127 = __fmul_rn(__frcp_rn(sum), 127.0f);
     // ---- pass C: p = e / sum, pq = rint(127 p) -> fp16 A operand of the context MMAs (row i, 64 keys per 128-byte swizzled row)
     uint8_t* prow = sP + hf * 16384 + i * 128;
     uint32_t r[16];
@@ -364,10 +378,8 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
         float n2[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const float ev = __uint_as_float(r[jj + u]);
-          const float q0 = __fmul_rn(ev, inv_sum);
-          const float p = __fmaf_rn(__fmaf_rn(-q0, sum, ev), inv_sum, q0);                       // e / sum within 1 ulp
-          const float t = __fadd_rn(__fmul_rn(p, 127.0f), 12582912.0f);                          // Round(Mul(p, 127)), ties to even
+          // pq = Round(Mul(p, 127)), p = e / sum: e * (127 / sum) + 1.5 * 2^23 in ONE rounding (ties to even)
+          const float t = __fmaf_rn(__uint_as_float(r[jj + u]), inv127, 12582912.0f);
           n2[u] = __fsub_rn(t, 12582912.0f);
           if (FAULT && fault_here && c0 + jj + u == fj) pq_f_local = n2[u];
         }
@@ -412,6 +424,7 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
   }
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
+  const float vinv127 = __fmul_rn(vinv, 0.007874015718698502f);      // exact: vinv is a power of two
 
   // ---- epilogue: thread = (row i, features 32 hf .. 32 hf + 31 of head h), 16 at a time in a rolled loop; with the fused RowQuant the
   //      finished values wait in their own TMEM columns for the row maximum of the other heads
@@ -430,8 +443,7 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
       for (int jj = 0; jj < 16; ++jj) {
         // (acc * 2^-p) / 127 with the division as its exact FMA equivalent on the magnitude (div127_exact; the IEEE division
         // takes its slow path for every zero dividend)
-        const float x = __fmul_rn(__uint_as_float(r[jj]), vinv);
-        y[jj] = copysignf(div127_exact(fabsf(x)), x);
+        y[jj] = __fmul_rn(__uint_as_float(r[jj]), vinv127);              // (acc * 2^-p) / 127: one multiplication by 2^-p * RN(1/127)
       }
       if (FAULT && fault_here && row_ok) {
 #pragma unroll
