@@ -72,6 +72,36 @@ __device__ __forceinline__ void tc_tmem_wait_st() { asm volatile("tcgen05.wait::
 __device__ __forceinline__ void tc_st_async_f32(uint32_t addr, float v, uint32_t mbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)), "r"(mbar) : "memory");
 }
+typedef unsigned long long tc_f2;     // two fp32 values in a 64-bit register (lo = first): fma.rn.f32x2 issues two lanes per slot
+__device__ __forceinline__ tc_f2 tc_pack2(float lo, float hi) {
+  tc_f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 tc_unpack2(tc_f2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ tc_f2 tc_fma2(tc_f2 a, tc_f2 b, tc_f2 c) {
+  tc_f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ tc_f2 tc_mul2(tc_f2 a, tc_f2 b) {
+  tc_f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ tc_f2 tc_add2(tc_f2 a, tc_f2 b) {
+  tc_f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// float(int8) of byte bb of w (w = the int8 bytes XOR 0x80): 2^23 + u as a bit pattern, minus 2^23 + 128 -- exact, no conversion pipe
+__device__ __forceinline__ float tc_s8f(uint32_t w, int bb) {
+  return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + bb)), 8388736.0f);
+}
 __device__ __forceinline__ float tc_ex2(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -182,6 +212,28 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
     }
   }
 
+#ifndef OT_TC_PF
+#define OT_TC_PF 48
+#endif
+#if OT_TC_PF > 0
+  // ---- L2 prefetch for the CTA that will follow this one on the SM (CTAs are handed out in blockIdx order, ~3 x 148 at a time:
+  //      sentence b + OT_TC_PF is the one whose operands this SM asks for next): its Q / K / V head slices are on their way from
+  //      HBM while this CTA computes
+  {
+    const int b2 = b + OT_TC_PF;
+    if (b2 < a.B) {
+      for (int idx = tid; idx < 3 * 128; idx += kTcThreads) {
+        const int which = idx >> 7, row = idx & 127;
+        const int8_t* ptr = nullptr;
+        if (which == 0 && row < Tq) ptr = a.q + (static_cast<int64_t>(b2) * Tq + row) * a.ldq + h * kDk;
+        if (which == 1 && row < Tk) ptr = a.k + (static_cast<int64_t>(b2) * a.Tk_cap + row) * a.ldk + h * kDk;
+        if (which == 2 && row < Tk) ptr = a.v + (static_cast<int64_t>(b2) * a.Tk_cap + row) * a.ldk + h * kDk;
+        if (ptr != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+      }
+    }
+  }
+#endif
+  const int vjp = tid & 63, vdq = tid >> 6;            // V staging: thread = (key pair, 16 of the 64 features)
   // ---- stage Q and K head slices into the swizzled operand tiles (rows past Tq / Tk are zero)
   for (int idx = tid; idx < 128 * 4; idx += kTcThreads) {
     const int row = idx >> 2, c = idx & 3;
@@ -225,35 +277,38 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
   // ---- V: de-quantize, scale, split hi/lo, transpose into [feature][key] K-major tiles (64 keys per 128-byte row, fp16);
   //      thread = (key pair, 16 of the 64 features)
   {
-    const int jp = tid & 63, dq = tid >> 6;
-    const int j0 = 2 * jp, j1 = j0 + 1;
+    const int jp = vjp, dq = vdq;
+    const int j0 = 2 * jp;
+    // (requesting these rows before the Q / K staging was measured 4 % SLOWER: the score MMAs wait for Q and K, not for V)
+    uint4 vraw0 = make_uint4(0u, 0u, 0u, 0u), vraw1 = make_uint4(0u, 0u, 0u, 0u);
+    float vsv0 = 0.f, vsv1 = 0.f;
+    if (2 * vjp < Tk) {
+      vraw0 = *reinterpret_cast<const uint4*>(a.v + (static_cast<int64_t>(b) * a.Tk_cap + 2 * vjp) * a.ldk + h * kDk + 16 * vdq);
+      vsv0 = svs[2 * vjp];
+    }
+    if (2 * vjp + 1 < Tk) {
+      vraw1 = *reinterpret_cast<const uint4*>(a.v + (static_cast<int64_t>(b) * a.Tk_cap + 2 * vjp + 1) * a.ldk + h * kDk + 16 * vdq);
+      vsv1 = svs[2 * vjp + 1];
+    }
     if (j0 < Tkp) {
-      uint32_t w0[4] = {0u, 0u, 0u, 0u}, w1[4] = {0u, 0u, 0u, 0u};
-      float sv0 = 0.f, sv1 = 0.f;
-      if (j0 < Tk) {
-        const uint4 x = *reinterpret_cast<const uint4*>(a.v + (static_cast<int64_t>(b) * a.Tk_cap + j0) * a.ldk + h * kDk + 16 * dq);
-        w0[0] = x.x; w0[1] = x.y; w0[2] = x.z; w0[3] = x.w;
-        sv0 = svs[j0];
-      }
-      if (j1 < Tk) {
-        const uint4 x = *reinterpret_cast<const uint4*>(a.v + (static_cast<int64_t>(b) * a.Tk_cap + j1) * a.ldk + h * kDk + 16 * dq);
-        w1[0] = x.x; w1[1] = x.y; w1[2] = x.z; w1[3] = x.w;
-        sv1 = svs[j1];
-      }
+      const uint32_t w0[4] = {vraw0.x, vraw0.y, vraw0.z, vraw0.w}, w1[4] = {vraw1.x, vraw1.y, vraw1.z, vraw1.w};
+      // fl(fl(vq * sv) * 2^p) == fl(vq * (sv * 2^p)): the power of two rides on the scale
+      const float sv0 = __fmul_rn(vsv0, vscale), sv1 = __fmul_rn(vsv1, vscale);
       const int kb = jp >> 5;
       const int chunk = (jp & 31) >> 2, inner = 4 * (jp & 3);
       uint8_t* hi_t = sVhi + kb * 8192;
       uint8_t* lo_t = sVlo + kb * 8192;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
+        const uint32_t x0 = w0[u] ^ 0x80808080u, x1 = w1[u] ^ 0x80808080u;
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
           const int d = 16 * dq + 4 * u + bb;
-          const float x0 = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int8_t>((w0[u] >> (8 * bb)) & 0xFFu)), sv0), vscale);
-          const float x1 = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int8_t>((w1[u] >> (8 * bb)) & 0xFFu)), sv1), vscale);
-          const __half2 hi = __floats2half2_rn(x0, x1);
+          const float v0 = __fmul_rn(tc_s8f(x0, bb), sv0);
+          const float v1 = __fmul_rn(tc_s8f(x1, bb), sv1);
+          const __half2 hi = __floats2half2_rn(v0, v1);
           const float2 hf2 = __half22float2(hi);
-          const __half2 lo = __floats2half2_rn(__fsub_rn(x0, hf2.x), __fsub_rn(x1, hf2.y));
+          const __half2 lo = __floats2half2_rn(__fsub_rn(v0, hf2.x), __fsub_rn(v1, hf2.y));
           const int off = d * 128 + ((chunk ^ (d & 7)) << 4) + inner;
           *reinterpret_cast<__half2*>(hi_t + off) = hi;
           *reinterpret_cast<__half2*>(lo_t + off) = lo;
@@ -299,30 +354,41 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
       const int c0 = c_base + 16 * c;
       tmem_ld_32x16(tlane + c0, r);
       tmem_wait_ld();
+      const tc_f2 sq2 = tc_pack2(sqi, sqi);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
-        const float4 sk4 = *reinterpret_cast<const float4*>(sks + c0 + 4 * q4);      // sk[j] / 8
+        const ulonglong2 sk4 = *reinterpret_cast<const ulonglong2*>(sks + c0 + 4 * q4);     // sk[j] / 8, two packed pairs
         const float4 km4 = *reinterpret_cast<const float4*>(kmf + c0 + 4 * q4);
-        const float skv[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
         const float kmv[4] = {km4.x, km4.y, km4.z, km4.w};
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const int jj = 4 * q4 + bb, j = c0 + jj;
-          int dot = static_cast<int>(r[jj]);
-          if (FAULT && fault_here) {
-            if (f.reserved == OPERAND_Q && f.mode == OT_FAULT_INPUT && i == fi && j >= fw0 && j < fw1) {
-              const int qv = tc_tile_byte(sQ, i, fd);
-              dot += (flip_int8_bit(qv, f.bit) - qv) * tc_tile_byte(sK, j, fd);
-            } else if (f.reserved == OPERAND_K && f.mode == OT_FAULT_WEIGHT && j == fj && i >= fw0 && i < fw1) {
-              const int kv = tc_tile_byte(sK, j, fd);
-              dot += tc_tile_byte(sQ, i, fd) * (flip_int8_bit(kv, f.bit) - kv);
+        for (int hh = 0; hh < 2; ++hh) {
+          int dot[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int jj = 4 * q4 + 2 * hh + u, j = c0 + jj;
+            dot[u] = static_cast<int>(r[jj]);
+            if (FAULT && fault_here) {
+              if (f.reserved == OPERAND_Q && f.mode == OT_FAULT_INPUT && i == fi && j >= fw0 && j < fw1) {
+                const int qv = tc_tile_byte(sQ, i, fd);
+                dot[u] += (flip_int8_bit(qv, f.bit) - qv) * tc_tile_byte(sK, j, fd);
+              } else if (f.reserved == OPERAND_K && f.mode == OT_FAULT_WEIGHT && j == fj && i >= fw0 && i < fw1) {
+                const int kv = tc_tile_byte(sK, j, fd);
+                dot[u] += tc_tile_byte(sQ, i, fd) * (flip_int8_bit(kv, f.bit) - kv);
+              }
             }
           }
-          float sc = __fmul_rn(__fmul_rn(__int2float_rn(dot), sqi), skv[bb]);                  // MatMul_k_out0 / sqrt(d_k)
-          if (FAULT && fault_here && f.reserved == OPERAND_SCORES && i == fi && j == fj)        // the patch addresses MatMul_k_out0 itself
-            sc = __fmul_rn(tc_patch_f32(f, __fmul_rn(sc, 8.0f)), 0.125f);
-          sc = (kmv[bb] == 0.0f) ? sc : kmv[bb];               // masked_fill(mask == 0, -1e9); padding columns of the MMA tile: -inf
-          r[jj] = __float_as_uint(sc);
+          // MatMul_k_out0 / sqrt(d_k) = fl(fl(float(dot) * sq) * (sk / 8)), two keys per issue slot
+          const float2 sc2 = tc_unpack2(tc_mul2(tc_mul2(tc_pack2(__int2float_rn(dot[0]), __int2float_rn(dot[1])), sq2), hh ? sk4.y : sk4.x));
+          float scv[2] = {sc2.x, sc2.y};
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int jj = 4 * q4 + 2 * hh + u, j = c0 + jj;
+            float sc = scv[u];
+            if (FAULT && fault_here && f.reserved == OPERAND_SCORES && i == fi && j == fj)      // the patch addresses MatMul_k_out0 itself
+              sc = __fmul_rn(tc_patch_f32(f, __fmul_rn(sc, 8.0f)), 0.125f);
+            sc = (kmv[2 * hh + u] == 0.0f) ? sc : kmv[2 * hh + u];   // masked_fill(mask == 0, -1e9); padding columns of the MMA tile: -inf
+            r[jj] = __float_as_uint(sc);
+          }
         }
       }
       if (causal && c0 + 15 > causal_last) {                   // warp-uniform test on the launch kind, then per row
@@ -343,6 +409,8 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
   // ---- pass B: exponentials + row sum of this key half
   float sum = 0.f;
   if (wactive && n_chunks > 0) {
+    const tc_f2 nmx2 = tc_pack2(-mx, -mx), l2e2 = tc_pack2(1.4426950408889634f, 1.4426950408889634f);
+    tc_f2 sum2 = tc_pack2(0.f, 0.f);                      // even keys | odd keys, added at the end (fixed order)
     uint32_t r[16];
 #pragma unroll 1
     for (int c = 0; c < n_chunks; ++c) {
@@ -350,20 +418,26 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
       tmem_ld_32x16(tlane + c0, r);
       tmem_wait_ld();
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) {
-        const float ev = tc_ex2(__fmul_rn(__fsub_rn(__uint_as_float(r[jj]), mx), 1.4426950408889634f));   // exp(s - max): FADD, FMUL, MUFU
-        sum += ev;
-        r[jj] = __float_as_uint(ev);
+      for (int jj = 0; jj < 16; jj += 2) {
+        // exp(s - max) = 2^((s - max) * log2 e): one packed add, one packed multiply, two MUFU.EX2
+        const float2 t2 = tc_unpack2(tc_mul2(tc_add2(tc_pack2(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1])), nmx2), l2e2));
+        const float e0 = tc_ex2(t2.x), e1 = tc_ex2(t2.y);
+        sum2 = tc_add2(sum2, tc_pack2(e0, e1));
+        r[jj] = __float_as_uint(e0);
+        r[jj + 1] = __float_as_uint(e1);
       }
       tc_tmem_st_32x16(tlane + c0, r);
       tc_tmem_wait_st();
     }
+    const float2 sp = tc_unpack2(sum2);
+    sum = __fadd_rn(sp.x, sp.y);
   }
   xm[hf * 128 + i] = sum;
   __syncthreads();
   sum = __fadd_rn(xm[i], xm[128 + i]);                       // fixed order: keys [0, 64) + keys [64, 128)
   if (wactive && n_chunks > 0) {
     const float inv127 = __fmul_rn(__frcp_rn(sum), 127.0f);
+    const tc_f2 inv127_2 = tc_pack2(inv127, inv127), magic2 = tc_pack2(12582912.0f, 12582912.0f), nmagic2 = tc_pack2(-12582912.0f, -12582912.0f);
     // ---- pass C: p = e / sum, pq = rint(127 p) -> fp16 A operand of the context MMAs (row i, 64 keys per 128-byte swizzled row)
     uint8_t* prow = sP + hf * 16384 + i * 128;
     uint32_t r[16];
@@ -375,14 +449,12 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
       uint32_t packed[8];
 #pragma unroll
       for (int jj = 0; jj < 16; jj += 2) {
-        float n2[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          // pq = Round(Mul(p, 127)), p = e / sum: e * (127 / sum) + 1.5 * 2^23 in ONE rounding (ties to even)
-          const float t = __fmaf_rn(__uint_as_float(r[jj + u]), inv127, 12582912.0f);
-          n2[u] = __fsub_rn(t, 12582912.0f);
-          if (FAULT && fault_here && c0 + jj + u == fj) pq_f_local = n2[u];
-        }
+        // pq = Round(Mul(p, 127)), p = e / sum: e * (127 / sum) + 1.5 * 2^23 in ONE rounding (ties to even), two keys per issue slot
+        const tc_f2 t2 = tc_fma2(tc_pack2(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1])), inv127_2, magic2);
+        const float2 nn = tc_unpack2(tc_add2(t2, nmagic2));
+        const float n2[2] = {nn.x, nn.y};
+        if (FAULT && fault_here && c0 + jj == fj) pq_f_local = n2[0];
+        if (FAULT && fault_here && c0 + jj + 1 == fj) pq_f_local = n2[1];
         const __half2 hp = __floats2half2_rn(n2[0], n2[1]);
         packed[jj >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
         if (a.probs_q != nullptr && row_ok) {
@@ -429,10 +501,12 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
   // ---- epilogue: thread = (row i, features 32 hf .. 32 hf + 31 of head h), 16 at a time in a rolled loop; with the fused RowQuant the
   //      finished values wait in their own TMEM columns for the row maximum of the other heads
   float amax = 0.f;
+  tc_f2 chk2 = tc_pack2(0.f, 0.f);           // stays 0 unless one of this thread's context values is not finite (then NaN)
   const uint32_t tctx = tlane + 32 * hf;
   if (wactive) {
     float* orow = a.ctx != nullptr ? a.ctx + (static_cast<int64_t>(b) * Tq + i) * a.ld_ctx + h * kDk + 32 * hf : nullptr;
     const float pq_f = FAULT ? spq[i] : 0.f;
+    const tc_f2 vinv127_2 = tc_pack2(vinv127, vinv127), zero2 = tc_pack2(0.f, 0.f);
     uint32_t r[16];
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
@@ -440,10 +514,11 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
       tmem_wait_ld();
       float y[16];
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) {
-        // (acc * 2^-p) / 127 with the division as its exact FMA equivalent on the magnitude (div127_exact; the IEEE division
-        // takes its slow path for every zero dividend)
-        y[jj] = __fmul_rn(__uint_as_float(r[jj]), vinv127);              // (acc * 2^-p) / 127: one multiplication by 2^-p * RN(1/127)
+      for (int jj = 0; jj < 16; jj += 2) {
+        // (acc * 2^-p) / 127: one multiplication by 2^-p * RN(1/127), two features per issue slot
+        const float2 y2 = tc_unpack2(tc_mul2(tc_pack2(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1])), vinv127_2));
+        y[jj] = y2.x;
+        y[jj + 1] = y2.y;
       }
       if (FAULT && fault_here && row_ok) {
 #pragma unroll
@@ -464,9 +539,11 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
         }
       }
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) {
-        amax = fmaxf(amax, fabsf(y[jj]));
+      for (int jj = 0; jj < 16; jj += 2) {
+        amax = fmaxf(amax, fmaxf(fabsf(y[jj]), fabsf(y[jj + 1])));
+        if (fuse_q) chk2 = tc_fma2(tc_pack2(y[jj], y[jj + 1]), zero2, chk2);
         r[jj] = __float_as_uint(y[jj]);
+        r[jj + 1] = __float_as_uint(y[jj + 1]);
       }
       if (fuse_q) {
         tc_tmem_st_32x16(tctx + 16 * c, r);
@@ -498,6 +575,17 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
     if (wactive) {
       const float s = quant_scale_x(rmax);
       const float s_rcp = __frcp_rn(s);
+      // The quotient y / s is EXACT and branch-free when the row is made of plain finite numbers with |y| <= rmax <= 1e6 (the
+      // domain tools/check_div_exact.c covers: r = RN(1/s), q0 = y*r, two FMA residual steps give RN(y/s) bit for bit, and
+      // q2 + 1.5*2^23 holds rint(q2), ties to even, in its low byte); any other row takes rowquant_kernel's own quant4_pack.
+      const float2 ck = tc_unpack2(chk2);
+      const bool row_slow = !(rmax <= 1.0e6f) || !(ck.x == 0.0f) || !(ck.y == 0.0f);
+#ifdef OT_TC_SLOWQ
+      const bool warp_slow = true;
+#else
+      const bool warp_slow = __any_sync(0xffffffffu, row_slow);
+#endif
+      const tc_f2 rr2 = tc_pack2(s_rcp, s_rcp), ns2 = tc_pack2(-s, -s), magic2 = tc_pack2(12582912.0f, 12582912.0f);
       uint4* qrow = reinterpret_cast<uint4*>(a.ctx_q + (static_cast<int64_t>(b) * Tq + i) * kDm + h * kDk + 32 * hf);
       uint32_t r[16];
 #pragma unroll 1
@@ -505,10 +593,27 @@ __global__ void __launch_bounds__(kTcThreads, 3) attention_tc_kernel(const AttnA
         tmem_ld_32x16(tctx + 16 * c, r);
         tmem_wait_ld();
         uint32_t w[4];
+        if (warp_slow) {
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          w[q4] = quant4_pack(make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]), __uint_as_float(r[4 * q4 + 2]),
-                                          __uint_as_float(r[4 * q4 + 3])), s, s_rcp);
+          for (int q4 = 0; q4 < 4; ++q4)
+            w[q4] = quant4_pack(make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]), __uint_as_float(r[4 * q4 + 2]),
+                                            __uint_as_float(r[4 * q4 + 3])), s, s_rcp);
+        } else {
+          uint32_t tb[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 2) {
+            const tc_f2 y2 = tc_pack2(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1]));
+            const tc_f2 q0 = tc_mul2(y2, rr2);
+            const tc_f2 q1 = tc_fma2(tc_fma2(q0, ns2, y2), rr2, q0);
+            const tc_f2 q2 = tc_fma2(tc_fma2(q1, ns2, y2), rr2, q1);
+            const tc_f2 t2 = tc_add2(q2, magic2);
+            tb[jj] = static_cast<uint32_t>(t2 & 0xffffffffull);
+            tb[jj + 1] = static_cast<uint32_t>(t2 >> 32);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            w[q4] = __byte_perm(__byte_perm(tb[4 * q4], tb[4 * q4 + 1], 0x0040), __byte_perm(tb[4 * q4 + 2], tb[4 * q4 + 3], 0x0040), 0x5410);
+        }
         if (row_ok) qrow[c] = make_uint4(w[0], w[1], w[2], w[3]);
       }
       if (row_ok && h == 0 && hf == 0) a.ctx_s[static_cast<int64_t>(b) * Tq + i] = s;
