@@ -299,7 +299,7 @@ def gemm_roofline(dev, M=65536):
             ts.append(e0.elapsed_time(e1) * 1e3 / reps)
         us = float(np.median(ts))
         ops = 2.0 * M * N * Kd
-        nbytes = M * Kd + N * Kd + (M * N * (8 if res else 0)) + (M * N * (4 if kw["out_kind"] == K.OUT_F32 else 1))
+        nbytes = M * Kd + N * Kd + (M * N * (4 if res else 0)) + (M * N * (4 if kw["out_kind"] == K.OUT_F32 else 1))
         out[name] = {"M": M, "N": N, "K": Kd, "us": us, "achieved_top_per_s": ops / us / 1e6, "frac_of_4.5_POPS": ops / us / 1e6 / 4500.0,
                      "algorithmic_gb_per_s": nbytes / us / 1e3, "kernel": src}
         del a, w, r

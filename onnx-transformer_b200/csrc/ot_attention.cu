@@ -564,11 +564,8 @@ static int launch_attention(const AttnArgs& a, int tk_max, cudaStream_t stream) 
   const size_t smem = attn_smem_bytes<QT>(tk_max);
   OT_REQUIRE(smem <= 227 * 1024, "attention tile does not fit in shared memory");
   auto kernel = attention_q8_kernel<QT>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
+  static DeviceOnce configured;
+  if (configured.need(smem)) OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid((a.Tq + QT - 1) / QT, a.B, 1);
   OT_CHECK_CUDA(launch_kernel(kernel, grid, dim3(256), smem, stream, 1, a));
   count_launch();
@@ -654,11 +651,9 @@ extern "C" int ot_attention_q8_mf(const int8_t* q, int64_t ldq, const float* sq,
   if (Tq >= 32 && ctx != nullptr && a.fault.mode == OT_FAULT_NONE && a.mf_unit == nullptr && probs_q == nullptr && k_new == nullptr &&
       step_dev == nullptr && attn_heads_smem_bytes(Tq, Tk) <= 100 * 1024) {
     const size_t smem = attn_heads_smem_bytes(Tq, Tk);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static DeviceOnce configured;
+    if (configured.need(smem))
       OT_CHECK_CUDA(cudaFuncSetAttribute(attention_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured = smem;
-    }
     OT_CHECK_CUDA(launch_kernel(attention_heads_kernel, dim3(kHeads, B), dim3(256), smem, s, 1, a));
     count_launch();
     if (ctx_q != nullptr)     // the merged rows are complete only across the 8 head CTAs: RowQuant as a second launch

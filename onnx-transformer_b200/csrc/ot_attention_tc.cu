@@ -637,11 +637,9 @@ int launch_attention_tc(const AttnArgs& a0, cudaStream_t stream, bool* fused_q) 
   if (!fuse) a.ctx_q = nullptr;        // the kernel fuses the RowQuant exactly when it sees ctx_q
   const bool faulty = a.fault.mode != OT_FAULT_NONE || a.mf_unit != nullptr;
   auto kernel = faulty ? attention_tc_kernel<true> : attention_tc_kernel<false>;
-  static bool configured[2] = {false, false};
-  if (!configured[faulty ? 1 : 0]) {
+  static DeviceOnce configured[2];
+  if (configured[faulty ? 1 : 0].need())
     OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-    configured[faulty ? 1 : 0] = true;
-  }
   // with the fused RowQuant the 8 head CTAs of a sentence are one thread-block cluster (they exchange the row maxima)
   OT_CHECK_CUDA(launch_kernel(kernel, dim3(kHeads, a.B), dim3(kTcThreads), kTcSmem, stream, fuse ? kHeads : 1, a));
   count_launch();

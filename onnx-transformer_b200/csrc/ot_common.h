@@ -109,6 +109,19 @@ static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim
 }
 #endif
 
+// "Configure this kernel once": cudaFuncSetAttribute applies to the CURRENT device only, so the once-flag is per device
+// (one process per GPU is the normal deployment; a process that drives several devices must not skip the attribute on the second).
+struct DeviceOnce {
+  size_t level[64] = {};
+  // true when the attribute has not been set on the current device yet, or was set for less than `want`
+  bool need(size_t want = 1) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (level[dev] >= want) return false;
+    level[dev] = want;
+    return true;
+  }
+};
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // 8-bit two's-complement bit flip with wrap, as inject_utils/layers.py:61-68 (flip_int8_bit).

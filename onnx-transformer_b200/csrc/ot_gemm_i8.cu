@@ -864,11 +864,10 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
 
   auto kernel = gemm_i8_kernel<BLOCK_N, STAGES, MODE>;
   const int smem = W4 ? L::TOTAL_W4 : L::TOTAL_W8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
   }
   OT_CHECK_CUDA(launch_kernel(kernel, dim3(g.N / BLOCK_N, (g.M + kBlockM - 1) / kBlockM, 1), dim3(kGemmThreads, 1, 1), smem, stream, g.cluster_n,
                               ta, tb, g));

@@ -41,6 +41,23 @@ constexpr int kSStageOff = kSRowmaxOff;                           // fp32 output
 constexpr int kSSmem = kSRowmaxOff + 64 * 1024 + 1024;
 static_assert(2 * 4 * kSMaxCl * 128 * 4 <= 64 * 1024 && kSEpiWarps * 4096 <= 64 * 1024 && kSSmem <= 232448, "shared memory budget");
 
+typedef unsigned long long sf2;     // two fp32 values in a 64-bit register (lo = first)
+__device__ __forceinline__ sf2 s_pack2(float lo, float hi) {
+  sf2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 s_unpack2(sf2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ sf2 s_fma2(sf2 a, sf2 b, sf2 c) {
+  sf2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 struct StreamArgs {
   int M, N, K;
   const float* row_scale;
@@ -54,6 +71,9 @@ struct StreamArgs {
   float* out_scale;
   int cluster_n;   // CTAs per quant group (Q8), 1 for fp32 output
   unsigned long long* trace;   // profiling aid (OT_GEMM_STREAM_TRACE): CTA 0 stamps %globaltimer per tile and role
+  // {-0,-0}, {1,1} as ARGUMENTS: ptxas rewrites fma(x, y, -0) -> mul and fma(x, 1, b) -> add when it can see the constants and then
+  // contracts the mul / add pair into ONE FFMA2 (a different rounding), -fmad=false or not (see ot_gemm_wres.cu)
+  unsigned long long neg0, one;
 };
 
 // trace layout: [tile li < 32][slot]: 0 epi tile start, 1 accumulator ready, 2 pass 1 done, 3 exchange done, 4 pass 2 done (epilogue warp 0);
@@ -228,6 +248,8 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         // the row) and reads them back transposed -- 8 lanes per row -- so that the residual loads and the output stores are full
         // 128-byte lines, 4 lines per instruction.  The residual is added in the transposed domain (same fadd, same operands).
         const bool has_res = g.residual != nullptr;
+        const bool plain = has_bias && !relu;
+        const sf2 kNeg0 = g.neg0, kOne = g.one, sx2 = s_pack2(sx, sx);
         uint8_t* wst = smem + kSStageOff + e * 4096;
         const int trow = lane >> 3, tch = lane & 7;                   // transposed role: row 4i + trow of the warp's 32, 16-byte chunk tch
         const int row0 = m_tile * kSBM + quarter * 32;                // first row of this warp
@@ -240,6 +262,21 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         };
         load_res(0);                                                  // in flight before the accumulator is waited for
+#ifndef OT_GS_NOPF
+        // the residual block this warp adds in its NEXT tile (32 rows x 256 bytes = 64 lines): on its way from HBM to L2 a whole tile
+        // (~10 us) ahead, so that the next tile's load_res sees L2 latency instead of HBM latency
+        if (has_res && g.K <= 512 && it + n_clusters < total) {   // (K = 2048: the prefetch competes with the 134 MB activation stream: +9 %)
+          const int it2 = it + n_clusters;
+          const int m2 = it2 / groups, n2 = (it2 % groups) * cn + static_cast<int>(rank);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int idx = lane + 32 * k;
+            const int prow = m2 * kSBM + quarter * 32 + (idx >> 1);
+            if (prow < g.M)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(g.residual + static_cast<int64_t>(prow) * g.ldr + n2 * kSBN + cq * kSColsPerWarp + 32 * (idx & 1)));
+          }
+        }
+#endif
         mbar_wait(smem_u32(&tfull_bar[buf]), par);
         tc_fence_after();
 #pragma unroll
@@ -262,13 +299,24 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               const float4 b4 = *reinterpret_cast<const float4*>(bs + 32 * blk + 16 * c + 4 * j);
               const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
               float y[4];
+              if (plain) {
+                // bias, no ReLU (every fp32-output linear of the model): fl(fl(float(acc) * sx) * sw) + b, two columns per issue slot
 #pragma unroll
-              for (int b = 0; b < 4; ++b) {
-                float v = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[c][4 * j + b])), sx), cv[b]);
-                const float vb = __fadd_rn(v, bv[b]);
-                v = has_bias ? vb : v;
-                const float vr = fmaxf(v, 0.0f);
-                y[b] = relu ? vr : v;
+                for (int b = 0; b < 4; b += 2) {
+                  const sf2 a2 = s_pack2(__int2float_rn(static_cast<int>(r[c][4 * j + b])), __int2float_rn(static_cast<int>(r[c][4 * j + b + 1])));
+                  const float2 v2 = s_unpack2(s_fma2(s_fma2(s_fma2(a2, sx2, kNeg0), s_pack2(cv[b], cv[b + 1]), kNeg0), kOne, s_pack2(bv[b], bv[b + 1])));
+                  y[b] = v2.x;
+                  y[b + 1] = v2.y;
+                }
+              } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                  float v = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[c][4 * j + b])), sx), cv[b]);
+                  const float vb = __fadd_rn(v, bv[b]);
+                  v = has_bias ? vb : v;
+                  const float vr = fmaxf(v, 0.0f);
+                  y[b] = relu ? vr : v;
+                }
               }
               *reinterpret_cast<float4*>(wst + lane * 128 + (((4 * c + j) ^ (lane & 7)) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
             }
@@ -279,7 +327,11 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const int rr = 4 * i + trow, grow = row0 + rr;
             float4 v = *reinterpret_cast<const float4*>(wst + rr * 128 + ((tch ^ (rr & 7)) << 4));
             if (grow < g.M) {
-              if (has_res) v = make_float4(__fadd_rn(res[i].x, v.x), __fadd_rn(res[i].y, v.y), __fadd_rn(res[i].z, v.z), __fadd_rn(res[i].w, v.w));
+              if (has_res) {
+                const float2 lo = s_unpack2(s_fma2(s_pack2(res[i].x, res[i].y), kOne, s_pack2(v.x, v.y)));      // res + y, the same fadd
+                const float2 hi = s_unpack2(s_fma2(s_pack2(res[i].z, res[i].w), kOne, s_pack2(v.z, v.w)));
+                v = make_float4(lo.x, lo.y, hi.x, hi.y);
+              }
               reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<int64_t>(grow) * g.ldo + col0 + 32 * blk)[tch] = v;
             }
           }
@@ -412,18 +464,16 @@ int launch_gemm_stream(const int8_t* A, int64_t lda, const int8_t* W, int64_t ld
   rc = get_tensor_map(&ta, A, M, K, lda, kSBM, kSBK, true);
   if (rc) return rc;
   StreamArgs g = {};
+  g.neg0 = 0x8000000080000000ull; g.one = 0x3F8000003F800000ull;
   g.M = M; g.N = N; g.K = K;
   g.row_scale = row_scale; g.col_scale = col_scale; g.bias = bias; g.residual = residual; g.ldr = ldr;
   g.relu = relu; g.out = out; g.ldo = ldo; g.out_scale = out_scale; g.cluster_n = cn;
   if (const char* tr = getenv("OT_GEMM_STREAM_TRACE")) g.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16));
   auto kernel = out_kind == OT_OUT_Q8 ? gemm_stream_kernel<true> : gemm_stream_kernel<false>;
-  static bool attr_set[2] = {false, false};
+  static DeviceOnce attr_set[2];
   static int max_clusters[2][kSMaxCl + 1] = {};
   const int ki = out_kind == OT_OUT_Q8 ? 1 : 0;
-  if (!attr_set[ki]) {
-    OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmem));
-    attr_set[ki] = true;
-  }
+  if (attr_set[ki].need()) OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmem));
   int sms = 148;
   {
     int dev = 0;

@@ -436,13 +436,10 @@ int launch_gemm_wres(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw,
   if (const char* tr = getenv("OT_GEMM_WRES_TRACE")) g.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16));
   auto kernel = relu ? gemm_wres_kernel<true> : gemm_wres_kernel<false>;
   const int ki = relu ? 1 : 0;
-  static bool attr_set[2] = {false, false};
+  static DeviceOnce attr_set[2];
   static int max_clusters_k[2][kMaxCl + 1] = {};
   int* max_clusters = max_clusters_k[ki];
-  if (!attr_set[ki]) {
-    OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set[ki] = true;
-  }
+  if (attr_set[ki].need()) OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   int sms = 148;
   {
     int dev = 0;

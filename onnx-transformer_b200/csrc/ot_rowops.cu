@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(256) residual_add_kernel(const float4* __restr
 
 // ------------------------------------------------------------------------------------------------
 // out[r,:] = table[id_r,:] * scale + pe[pos_r,:]   (embeddings.py:13, positional_encodings.py:24)
+constexpr int kEmbRows = 4;
 __global__ void __launch_bounds__(128) embed_pe_kernel(const int64_t* __restrict__ ids, int64_t ids_stride,
                                                        const float* __restrict__ table, const float* __restrict__ pe,
                                                        int64_t rows, int seq_len, int d, int pos0,
@@ -240,18 +241,36 @@ __global__ void __launch_bounds__(128) embed_pe_kernel(const int64_t* __restrict
   pdl_wait();      // upstream results are complete and visible from here on
   pdl_trigger();   // now let exactly one successor start its launch + prologue (look-ahead depth 1)
   tl_mark(tl, 2);
-  const int64_t row = blockIdx.x;
-  if (row >= rows) return;
+  // kEmbRows rows per CTA, all of a thread's id / table / PE loads in flight before the first use: one row per 128-thread CTA was a
+  // chain of dependent loads with 2 KB in flight per CTA (1.9 TB/s at 65,536 rows: profiles/r2_launches_encoder_cfg3_v3.txt)
   const int dyn = pos_dev ? *pos_dev : 0;
-  const int64_t id = pos_dev ? ids[row * ids_stride + dyn] : ids[row * ids_stride];
-  const int pos = (pos_dev ? dyn : pos0) + static_cast<int>(row % seq_len);
-  const float4* t = reinterpret_cast<const float4*>(table + id * d);
-  const float4* p = reinterpret_cast<const float4*>(pe + static_cast<int64_t>(pos) * d);
-  float4* o = reinterpret_cast<float4*>(out + row * d);
-  for (int i = threadIdx.x; i < (d >> 2); i += blockDim.x) {
-    const float4 e = __ldg(t + i), q = __ldg(p + i);
-    o[i] = make_float4(__fadd_rn(__fmul_rn(e.x, scale), q.x), __fadd_rn(__fmul_rn(e.y, scale), q.y),
-                       __fadd_rn(__fmul_rn(e.z, scale), q.z), __fadd_rn(__fmul_rn(e.w, scale), q.w));
+  const int d4 = d >> 2;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kEmbRows;
+  int64_t id[kEmbRows];
+#pragma unroll
+  for (int r = 0; r < kEmbRows; ++r) {
+    const int64_t row = row0 + r;
+    id[r] = row < rows ? (pos_dev ? ids[row * ids_stride + dyn] : ids[row * ids_stride]) : 0;
+  }
+  for (int i = threadIdx.x; i < d4; i += blockDim.x) {
+    float4 e[kEmbRows], q[kEmbRows];
+#pragma unroll
+    for (int r = 0; r < kEmbRows; ++r) {
+      const int64_t row = row0 + r;
+      const int pos = (pos_dev ? dyn : pos0) + static_cast<int>(row % seq_len);
+      if (row < rows) {
+        e[r] = __ldg(reinterpret_cast<const float4*>(table + id[r] * d) + i);
+        q[r] = __ldg(reinterpret_cast<const float4*>(pe + static_cast<int64_t>(pos) * d) + i);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kEmbRows; ++r) {
+      const int64_t row = row0 + r;
+      if (row < rows)
+        reinterpret_cast<float4*>(out + row * d)[i] =
+            make_float4(__fadd_rn(__fmul_rn(e[r].x, scale), q[r].x), __fadd_rn(__fmul_rn(e[r].y, scale), q[r].y),
+                        __fadd_rn(__fmul_rn(e[r].z, scale), q[r].z), __fadd_rn(__fmul_rn(e[r].w, scale), q[r].w));
+    }
   }
 }
 
@@ -395,7 +414,7 @@ extern "C" int ot_embed_pe(const int64_t* ids, int64_t ids_stride, const float* 
   OT_REQUIRE_DEVICE();
   OT_REQUIRE(ids && table && pe && out && rows >= 0 && seq_len > 0 && d % 4 == 0, "bad embed_pe arguments");
   if (rows == 0) return OT_OK;
-  OT_CHECK_CUDA(launch_kernel(embed_pe_kernel, dim3(static_cast<unsigned>(rows)), dim3(128), 0, as_stream(stream), 1, ids, ids_stride, table, pe,
+  OT_CHECK_CUDA(launch_kernel(embed_pe_kernel, dim3(static_cast<unsigned>((rows + kEmbRows - 1) / kEmbRows)), dim3(128), 0, as_stream(stream), 1, ids, ids_stride, table, pe,
                               rows, seq_len, d, pos0, pos_dev, scale, out));
   count_launch();
   return OT_OK;

@@ -53,7 +53,7 @@ for name, N, Kd, kw, res in shapes:
             ts.append(e0.elapsed_time(e1) * 1e3 / REPS)
         us = sorted(ts)[len(ts) // 2]
         ops = 2.0 * M * N * Kd
-        nbytes = M * Kd + N * Kd + (M * N * (8 if res else 0)) + (M * N * (4 if kw["out_kind"] == K.OUT_F32 else 1))
+        nbytes = M * Kd + N * Kd + (M * N * (4 if res else 0)) + (M * N * (4 if kw["out_kind"] == K.OUT_F32 else 1))
         rec[mode] = {"us": us, "TOPs": ops / us / 1e6, "frac_4.5POPS": ops / us / 1e6 / 4500.0, "GBs": nbytes / us / 1e3}
     os.environ.pop("OT_GEMM_STREAM", None)
     os.environ.pop("OT_GEMM_WRES", None)
