@@ -791,11 +791,16 @@ struct MapKeyHash {
 };
 
 // 2-D byte tensor [rows, cols] with row pitch ld; box = [box_rows, box_cols]; cached per (ptr, shape).
+int get_tensor_map_sw(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, int swizzle);
 int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                           uint32_t box_cols, bool swizzle128) {
+  return get_tensor_map_sw(out, ptr, rows, cols, ld, box_rows, box_cols, swizzle128 ? 1 : 0);
+}
+// swizzle: 0 none, 1 = 128-byte, 2 = 64-byte (byte-typed 2-D view [rows][cols] with row pitch ld)
+int get_tensor_map_sw(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, int swizzle) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, rows, cols, ld, box_rows, box_cols, swizzle128 ? 1 : 0};
+  MapKey key{ptr, rows, cols, ld, box_rows, box_cols, swizzle};
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
@@ -814,7 +819,8 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estride[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstride, box, estride,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %llu cols %llu ld %llu box %u x %u)", (int)r, ptr,

@@ -26,6 +26,7 @@
 namespace ot {
 
 int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, bool swizzle128);
+int get_tensor_map_sw(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, int swizzle);
 int launch_gemm_wres(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K, const float* row_scale, const float* col_scale,
                      const float* bias, int relu, void* out, int64_t ldo, float* out_scale, int quant_group, cudaStream_t stream);
 
@@ -37,8 +38,9 @@ constexpr int kSMaxCl = 8;
 constexpr int kSBarOff = kSStages * (kSA + kSB);                 // full[4] empty[4] tfull[2] tempty[2] xbar[2] + tmem slot
 constexpr int kSColOff = kSBarOff + 256;                         // float [16 warps][2 buffers][cs 64 | bias 64]
 constexpr int kSRowmaxOff = kSColOff + kSEpiWarps * 2 * 2 * kSColsPerWarp * 4;   // float rowmax[2][4*kSMaxCl][128]
-constexpr int kSStageOff = kSRowmaxOff;                           // fp32 output: per-warp staging block [32 rows][128 B] x 16 warps (aliases rowmax)
-constexpr int kSSmem = kSRowmaxOff + 64 * 1024 + 1024;
+constexpr int kSStageOff = (kSRowmaxOff + 1023) & ~1023;           // fp32 output: per-warp staging block, 4 KB x 16 warps (aliases rowmax; 1024-byte aligned: TMA swizzle)
+constexpr int kSResBarOff = kSStageOff + 64 * 1024;             // fp32 output through TMA: uint64 resbar[16 warps][2 buffers]
+constexpr int kSSmem = kSResBarOff + 256 + 1024;
 static_assert(2 * 4 * kSMaxCl * 128 * 4 <= 64 * 1024 && kSEpiWarps * 4096 <= 64 * 1024 && kSSmem <= 232448, "shared memory budget");
 
 typedef unsigned long long sf2;     // two fp32 values in a 64-bit register (lo = first)
@@ -58,6 +60,15 @@ __device__ __forceinline__ sf2 s_fma2(sf2 a, sf2 b, sf2 c) {
   return r;
 }
 
+__device__ __forceinline__ void s_tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void s_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void s_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void s_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void s_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 struct StreamArgs {
   int M, N, K;
   const float* row_scale;
@@ -74,6 +85,7 @@ struct StreamArgs {
   // {-0,-0}, {1,1} as ARGUMENTS: ptxas rewrites fma(x, y, -0) -> mul and fma(x, 1, b) -> add when it can see the constants and then
   // contracts the mul / add pair into ONE FFMA2 (a different rounding), -fmad=false or not (see ot_gemm_wres.cu)
   unsigned long long neg0, one;
+  int tma_epi;     // fp32 output: residual in / result out through per-warp TMA boxes (tmap_r / tmap_o are valid)
 };
 
 // trace layout: [tile li < 32][slot]: 0 epi tile start, 1 accumulator ready, 2 pass 1 done, 3 exchange done, 4 pass 2 done (epilogue warp 0);
@@ -108,7 +120,8 @@ __device__ __forceinline__ void st_async_f32(uint32_t addr, float v, uint32_t mb
 
 template <bool Q8>
 __global__ void __launch_bounds__(kSThreads, 1)
-gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ StreamArgs g) {
+gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_r,
+                   const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ StreamArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -123,6 +136,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
   float* s_col = reinterpret_cast<float*>(smem + kSColOff);       // per-warp column parameters
   float* rowmax = reinterpret_cast<float*>(smem + kSRowmaxOff);   // [xb][4*kSMaxCl][128]
+  uint64_t* resbar = reinterpret_cast<uint64_t*>(smem + kSResBarOff);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) / 32, 0);
   const int lane = threadIdx.x & 31;
@@ -149,6 +163,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         mbar_init(smem_u32(&tempty_bar[b]), kSEpiWarps);
         mbar_init(smem_u32(&xbar[b]), 1);
       }
+      for (int i = 0; i < 2 * kSEpiWarps; ++i) mbar_init(smem_u32(&resbar[i]), 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -241,7 +256,108 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const float sx = (g.row_scale && row_ok) ? __ldg(g.row_scale + row) : 1.0f;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSBN + cq * kSColsPerWarp;
 
-      if (!Q8) {
+      if (!Q8 && g.tma_epi) {
+        // ---- fp32 output (+ residual) through TMA.  The LSU form below spends the tile in three phases that do not overlap (ablation,
+        // profiles/r2_cdecoder_ab_experiments.txt: O-projection 37 us of compute path + 10 us of residual loads + 21 us of stores = 68 us):
+        // 16 warps wait for their loads and push their stores at the same time.  Here every warp owns two 2 KB buffers [32 rows][64 B]
+        // (64-byte swizzle = the layout a thread-per-row 16-byte access pattern reads and writes without bank conflicts): the residual
+        // of a 16-column sub-block ARRIVES there by TMA two sub-blocks ahead, the row's thread adds its y in place, and the buffer LEAVES
+        // by a TMA store -- no residual registers, no transposed read-back, no LSU global traffic, nothing waits for a store.
+        const bool has_res = g.residual != nullptr;
+        const bool plain = has_bias && !relu;
+        const sf2 kNeg0 = g.neg0, kOne = g.one, sx2 = s_pack2(sx, sx);
+        uint8_t* wbuf = smem + kSStageOff + e * 4096;
+        uint64_t* rbar = resbar + 2 * e;
+        const int row0 = m_tile * kSBM + quarter * 32;                // first row of this warp
+        const bool has_next = it + n_clusters < total;
+        int nrow0 = 0, ncol0 = 0;
+        if (has_next) {
+          const int it2 = it + n_clusters;
+          nrow0 = (it2 / groups) * kSBM + quarter * 32;
+          ncol0 = ((it2 % groups) * cn + static_cast<int>(rank)) * kSBN + cq * kSColsPerWarp;
+        }
+        if (li == 0 && has_res && lane == 0) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            mbar_arrive_expect_tx(smem_u32(&rbar[b]), 2048);
+            tma_load_2d(smem_u32(wbuf + b * 2048), &tmap_r, smem_u32(&rbar[b]), (col0 + 16 * b) * 4, row0);
+          }
+        }
+        // (prefetch.global.L2 of the next tile's residual block, which helps the LSU form below, made this one 5 % slower: 66.7 vs 62.4 us)
+        mbar_wait(smem_u32(&tfull_bar[buf]), par);
+        tc_fence_after();
+#pragma unroll
+        for (int sb = 0; sb < 4; ++sb) {
+          const uint32_t n = li * 4u + sb, b = sb & 1u;
+          uint8_t* mybuf = wbuf + b * 2048 + lane * 64;
+          uint32_t r[16];
+          tmem_ld_32x16(taddr + 16 * sb, r);
+          tmem_wait_ld();
+          if (sb == 3) {
+            // the whole accumulator slice is in registers: the MMAs of the tile after next may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+          }
+          float y[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cs + 16 * sb + 4 * j);
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + 16 * sb + 4 * j);
+            const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            if (plain) {
+#pragma unroll
+              for (int q = 0; q < 4; q += 2) {
+                const sf2 a2 = s_pack2(__int2float_rn(static_cast<int>(r[4 * j + q])), __int2float_rn(static_cast<int>(r[4 * j + q + 1])));
+                const float2 v2 = s_unpack2(s_fma2(s_fma2(s_fma2(a2, sx2, kNeg0), s_pack2(cv[q], cv[q + 1]), kNeg0), kOne, s_pack2(bv[q], bv[q + 1])));
+                y[4 * j + q] = v2.x;
+                y[4 * j + q + 1] = v2.y;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float v = __fmul_rn(__fmul_rn(__int2float_rn(static_cast<int>(r[4 * j + q])), sx), cv[q]);
+                const float vb = __fadd_rn(v, bv[q]);
+                v = has_bias ? vb : v;
+                const float vr = fmaxf(v, 0.0f);
+                y[4 * j + q] = relu ? vr : v;
+              }
+            }
+          }
+          if (has_res) {
+            mbar_wait(smem_u32(&rbar[b]), (n >> 1) & 1u);             // the residual of this sub-block has landed in the buffer
+          } else if (n >= 2) {
+            if (lane == 0) s_bulk_wait_read1();                       // the store that last used this buffer has read it
+            __syncwarp();
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float4* slot = reinterpret_cast<float4*>(mybuf + ((c ^ ((lane >> 1) & 3)) << 4));
+            float4 v = make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]);
+            if (has_res) {
+              const float4 rs = *slot;
+              const float2 lo = s_unpack2(s_fma2(s_pack2(rs.x, rs.y), kOne, s_pack2(v.x, v.y)));      // res + y, the same fadd
+              const float2 hi = s_unpack2(s_fma2(s_pack2(rs.z, rs.w), kOne, s_pack2(v.z, v.w)));
+              v = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+            *slot = v;
+          }
+          fence_proxy_async_smem();                                   // generic-proxy writes of the buffer -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            s_tma_store_2d(&tmap_o, smem_u32(wbuf + b * 2048), (col0 + 16 * sb) * 4, row0);
+            s_bulk_commit();
+            // the buffer's next residual: sub-block sb + 2 of this tile, or sub-block sb - 2 of the next one
+            if (has_res && (sb < 2 || has_next)) {
+              s_bulk_wait_read0();                                    // the store has read the buffer
+              mbar_arrive_expect_tx(smem_u32(&rbar[b]), 2048);
+              if (sb < 2) tma_load_2d(smem_u32(wbuf + b * 2048), &tmap_r, smem_u32(&rbar[b]), (col0 + 16 * (sb + 2)) * 4, row0);
+              else tma_load_2d(smem_u32(wbuf + b * 2048), &tmap_r, smem_u32(&rbar[b]), (ncol0 + 16 * (sb - 2)) * 4, nrow0);
+            }
+          }
+          __syncwarp();
+        }
+      } else if (!Q8) {
         // ---- fp32 output (+ residual).  These GEMMs are bound by the memory path of the epilogue, not by the MMAs: with one thread
         // per row, every 16-byte load / store instruction of a warp touched 32 different lines (profiles/r2_ncu_gemm_cfg3.txt: issue
         // 13 %, DRAM 32 %).  Here a warp stages 32 rows x 32 columns of y in shared memory (thread = row, 16-byte chunks XOR-swizzled by
@@ -258,7 +374,12 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int grow = row0 + 4 * i + trow;
-            if (has_res && grow < g.M) res[i] = __ldg(reinterpret_cast<const float4*>(g.residual + static_cast<int64_t>(grow) * g.ldr + col0 + 32 * blk) + tch);
+#if defined(OT_GS_ABL) && (OT_GS_ABL & 1)
+            if (has_res && grow < 0) res[i] = __ldg(
+#else
+            if (has_res && grow < g.M) res[i] = __ldg(
+#endif
+                reinterpret_cast<const float4*>(g.residual + static_cast<int64_t>(grow) * g.ldr + col0 + 32 * blk) + tch);
           }
         };
         load_res(0);                                                  // in flight before the accumulator is waited for
@@ -326,7 +447,11 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + trow, grow = row0 + rr;
             float4 v = *reinterpret_cast<const float4*>(wst + rr * 128 + ((tch ^ (rr & 7)) << 4));
+#if defined(OT_GS_ABL) && (OT_GS_ABL & 2)
+            if (grow < g.M && g.ldo < 0) {
+#else
             if (grow < g.M) {
+#endif
               if (has_res) {
                 const float2 lo = s_unpack2(s_fma2(s_pack2(res[i].x, res[i].y), kOne, s_pack2(v.x, v.y)));      // res + y, the same fadd
                 const float2 hi = s_unpack2(s_fma2(s_pack2(res[i].z, res[i].w), kOne, s_pack2(v.z, v.w)));
@@ -435,6 +560,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   }
 
+  if (!Q8 && g.tma_epi && warp_idx >= 2 && lane == 0) s_bulk_wait0();     // this warp's TMA stores have left shared memory and are complete
   tc_fence_before();
   if (cn > 1) cluster_sync_all();
   else __syncthreads();
@@ -468,6 +594,23 @@ int launch_gemm_stream(const int8_t* A, int64_t lda, const int8_t* W, int64_t ld
   g.M = M; g.N = N; g.K = K;
   g.row_scale = row_scale; g.col_scale = col_scale; g.bias = bias; g.residual = residual; g.ldr = ldr;
   g.relu = relu; g.out = out; g.ldo = ldo; g.out_scale = out_scale; g.cluster_n = cn;
+  CUtensorMap tr_map = ta, to_map = ta;
+  {
+    static const int tma_epi = getenv("OT_GEMM_STREAM_TMA_EPI") ? atoi(getenv("OT_GEMM_STREAM_TMA_EPI")) : 1;
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (ldo % 4 == 0) &&
+                         (residual == nullptr || ((reinterpret_cast<uintptr_t>(residual) % 16 == 0) && (ldr % 4 == 0)));
+    // K > 512 (FFN2) keeps the LSU epilogue: its tiles are bound by the TMA operand stream (768 KB per tile), and epilogue boxes queued
+    // behind it made the tile 4 % slower (93.7 vs 89.7 us); K <= 512 (O-projection, cross-K/V): 68.7 -> 60.9 us
+    if (tma_epi && out_kind == OT_OUT_F32 && aligned && (K <= 512 || tma_epi > 1)) {
+      rc = get_tensor_map_sw(&to_map, out, M, static_cast<uint64_t>(N) * 4, static_cast<uint64_t>(ldo) * 4, 32, 64, 2);
+      if (rc) return rc;
+      if (residual != nullptr) {
+        rc = get_tensor_map_sw(&tr_map, residual, M, static_cast<uint64_t>(N) * 4, static_cast<uint64_t>(ldr) * 4, 32, 64, 2);
+        if (rc) return rc;
+      }
+      g.tma_epi = 1;
+    }
+  }
   if (const char* tr = getenv("OT_GEMM_STREAM_TRACE")) g.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16));
   auto kernel = out_kind == OT_OUT_Q8 ? gemm_stream_kernel<true> : gemm_stream_kernel<false>;
   static DeviceOnce attr_set[2];
@@ -505,7 +648,7 @@ int launch_gemm_stream(const int8_t* A, int64_t lda, const int8_t* W, int64_t ld
   const int m_tiles = (M + kSBM - 1) / kSBM;
   const int total = m_tiles * ((N / kSBN) / cn);
   if (n_cl > total) n_cl = total;
-  OT_CHECK_CUDA(launch_kernel(kernel, dim3(static_cast<unsigned>(n_cl * cn)), dim3(kSThreads), kSSmem, stream, cn, ta, tb, g));
+  OT_CHECK_CUDA(launch_kernel(kernel, dim3(static_cast<unsigned>(n_cl * cn)), dim3(kSThreads), kSSmem, stream, cn, ta, tb, tr_map, to_map, g));
   count_launch();
   return OT_OK;
 }
