@@ -69,6 +69,36 @@ __device__ __forceinline__ void s_bulk_wait_read0() { asm volatile("cp.async.bul
 __device__ __forceinline__ void s_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void s_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- CTA pair (cta_group::2): one 256-row MMA over two SMs, each CTA holding 128 rows of A and HALF of the weight block
+__device__ __forceinline__ void s_tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void s_tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void s_tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void s_mma_i8_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far, signalled on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void s_mma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are credited to a barrier of the pair's leader (a shared::cluster address)
+__device__ __forceinline__ void s_tma_load_2d_2cta(uint32_t dst_smem, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void s_mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
 struct StreamArgs {
   int M, N, K;
   const float* row_scale;
@@ -85,6 +115,7 @@ struct StreamArgs {
   // {-0,-0}, {1,1} as ARGUMENTS: ptxas rewrites fma(x, y, -0) -> mul and fma(x, 1, b) -> add when it can see the constants and then
   // contracts the mul / add pair into ONE FFMA2 (a different rounding), -fmad=false or not (see ot_gemm_wres.cu)
   unsigned long long neg0, one;
+  int pair;        // fp32 output, K > 512: CTA pairs (cta_group::2); tmap_b then has a 128-row box (half a weight block per CTA)
   int tma_epi;     // fp32 output: residual in / result out through per-warp TMA boxes (tmap_r / tmap_o are valid)
 };
 
@@ -118,7 +149,8 @@ __device__ __forceinline__ void st_async_f32(uint32_t addr, float v, uint32_t mb
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)), "r"(mbar) : "memory");
 }
 
-template <bool Q8>
+// PAIR: the cta_group::2 form (a separate instantiation: a kernel that CONTAINS cta_group::2 instructions cannot be launched without clusters)
+template <bool Q8, bool PAIR = false>
 __global__ void __launch_bounds__(kSThreads, 1)
 gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_r,
                    const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ StreamArgs g) {
@@ -128,9 +160,13 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* sA = smem;
   uint8_t* sB = smem + kSStages * kSA;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSBarOff);
+  // PAIR: a stage holds 128 rows of A + HALF a weight block (32 KB instead of 48): the same shared memory makes a ring of 4
+  constexpr int NST = PAIR ? 4 : kSStages;
+  constexpr int kStA = PAIR ? 32768 : kSA, kStB = PAIR ? 32768 : kSB;      // stage strides of the A / W rings
+  if (PAIR) sB = smem + kSA;
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kSStages;
-  uint64_t* tfull_bar = bars + 2 * kSStages;
+  uint64_t* empty_bar = bars + NST;
+  uint64_t* tfull_bar = bars + 2 * NST;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* xbar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
@@ -142,10 +178,13 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int lane = threadIdx.x & 31;
   const int cn = g.cluster_n;
   const uint32_t rank = cn > 1 ? cluster_ctarank() : 0u;
-  const int cluster_id = blockIdx.x / cn, n_clusters = gridDim.x / cn;
+  constexpr bool pair = PAIR;                                        // cluster of 2 = one MMA pair; cn == 1, fp32 output
+  const uint32_t prank = pair ? cluster_ctarank() : 0u;
+  const int unit = pair ? 2 : cn;
+  const int cluster_id = blockIdx.x / unit, n_clusters = gridDim.x / unit;
   const int m_tiles = (g.M + kSBM - 1) / kSBM;
   const int groups = (g.N / kSBN) / cn;
-  const int total = m_tiles * groups;
+  const int total = pair ? ((m_tiles + 1) / 2) * groups : m_tiles * groups;   // pair: a unit of work is TWO 128-row tiles of one column tile
   const int nkb = g.K / kSBK;
 
   if (warp_idx == 0 && elect_one()) {
@@ -154,24 +193,29 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
   if (warp_idx == 1) {
     if (elect_one()) {
-      for (int s = 0; s < kSStages; ++s) {
+      for (int s = 0; s < NST; ++s) {
         mbar_init(smem_u32(&full_bar[s]), 1);
         mbar_init(smem_u32(&empty_bar[s]), 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(smem_u32(&tfull_bar[b]), 1);
-        mbar_init(smem_u32(&tempty_bar[b]), kSEpiWarps);
+        mbar_init(smem_u32(&tempty_bar[b]), pair ? 2 * kSEpiWarps : kSEpiWarps);   // pair: the leader's MMAs wait for both epilogues
         mbar_init(smem_u32(&xbar[b]), 1);
       }
       for (int i = 0; i < 2 * kSEpiWarps; ++i) mbar_init(smem_u32(&resbar[i]), 1);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(tmem_slot), 512);
-    tmem_relinquish();
+    if (pair) {
+      s_tmem_alloc2(smem_u32(tmem_slot), 512);
+      s_tmem_relinquish2();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  if (cn > 1) cluster_sync_all();   // every CTA of the cluster has initialised its barriers before anyone stores into it
+  if (cn > 1 || pair) cluster_sync_all();   // every CTA of the cluster has initialised its barriers before anyone stores into it
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -183,11 +227,20 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (elect_one()) {
       uint32_t cnt = 0, li = 0;
       for (int it = cluster_id; it < total; it += n_clusters, ++li) {
-        const int m_tile = it / groups, n_tile = (it % groups) * cn + static_cast<int>(rank);
+        const int m_tile = pair ? 2 * (it / groups) + static_cast<int>(prank) : it / groups;
+        const int n_tile = (it % groups) * cn + static_cast<int>(rank);
         for (int kb = 0; kb < nkb; ++kb, ++cnt) {
-          const uint32_t s = cnt % kSStages, ph = (cnt / kSStages) & 1u;
+          const uint32_t s = cnt % NST, ph = (cnt / NST) & 1u;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
           const uint32_t fb = smem_u32(&full_bar[s]);
+          if (pair) {
+            // each CTA brings its 128 rows of A and its HALF of the 256-row weight block; all four boxes are credited to the leader's barrier
+            const uint32_t lfb = mapa_shared(fb, 0);
+            if (prank == 0) mbar_arrive_expect_tx(fb, 2 * (kSA + kSB / 2));
+            s_tma_load_2d_2cta(smem_u32(sA + s * kStA), &tmap_a, lfb, kb * kSBK, m_tile * kSBM);
+            s_tma_load_2d_2cta(smem_u32(sB + s * kStB), &tmap_b, lfb, kb * kSBK, n_tile * kSBN + static_cast<int>(prank) * (kSBN / 2));
+            continue;
+          }
           mbar_arrive_expect_tx(fb, kSA + kSB);
           tma_load_2d(smem_u32(sA + s * kSA), &tmap_a, fb, kb * kSBK, m_tile * kSBM);
           tma_load_2d(smem_u32(sB + s * kSB), &tmap_b, fb, kb * kSBK, n_tile * kSBN);
@@ -199,8 +252,11 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     __syncwarp();
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (elect_one()) {
+    if (pair && prank != 0) {
+      // the leader issues for both CTAs
+    } else if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_i8(kSBM, kSBN);
+      constexpr uint32_t idesc2 = make_idesc_i8(2 * kSBM, kSBN);
       uint32_t cnt = 0, li = 0;
       for (int it = cluster_id; it < total; it += n_clusters, ++li) {
         const uint32_t buf = li & 1u;
@@ -209,17 +265,25 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         strace(g, li, 8);
         const uint32_t d_tmem = tmem_base + buf * kSBN;
         for (int kb = 0; kb < nkb; ++kb, ++cnt) {
-          const uint32_t s = cnt % kSStages, ph = (cnt / kSStages) & 1u;
+          const uint32_t s = cnt % NST, ph = (cnt / NST) & 1u;
           mbar_wait(smem_u32(&full_bar[s]), ph);
           tc_fence_after();
-          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + s * kSA));
-          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sB + s * kSB));
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + s * kStA));
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sB + s * kStB));
+          if (pair) {
+#pragma unroll
+            for (int k = 0; k < kSBK / 32; ++k)
+              s_mma_i8_ss_2cta(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc2, (kb | k) != 0 ? 1u : 0u);
+            s_mma_commit_2cta(smem_u32(&empty_bar[s]));
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < kSBK / 32; ++k)
             mma_i8_ss(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           mma_commit(smem_u32(&empty_bar[s]));
         }
-        mma_commit(smem_u32(&tfull_bar[buf]));
+        if (pair) s_mma_commit_2cta(smem_u32(&tfull_bar[buf]));
+        else mma_commit(smem_u32(&tfull_bar[buf]));
         strace(g, li, 9);
       }
     }
@@ -238,7 +302,8 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint32_t li = 0;
     for (int it = cluster_id; it < total; it += n_clusters, ++li) {
       const uint32_t buf = li & 1u, par = (li >> 1) & 1u;
-      const int m_tile = it / groups, grp = it % groups, n_tile = grp * cn + static_cast<int>(rank);
+      const int grp = it % groups, n_tile = grp * cn + static_cast<int>(rank);
+      const int m_tile = pair ? 2 * (it / groups) + static_cast<int>(prank) : it / groups;
       const int row = m_tile * kSBM + row_in_tile;
       const bool row_ok = row < g.M;
       const int col0 = n_tile * kSBN + cq * kSColsPerWarp;           // first of this warp's 64 columns
@@ -273,7 +338,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         int nrow0 = 0, ncol0 = 0;
         if (has_next) {
           const int it2 = it + n_clusters;
-          nrow0 = (it2 / groups) * kSBM + quarter * 32;
+          nrow0 = (pair ? 2 * (it2 / groups) + static_cast<int>(prank) : it2 / groups) * kSBM + quarter * 32;
           ncol0 = ((it2 % groups) * cn + static_cast<int>(rank)) * kSBN + cq * kSColsPerWarp;
         }
         if (li == 0 && has_res && lane == 0) {
@@ -297,7 +362,10 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             // the whole accumulator slice is in registers: the MMAs of the tile after next may overwrite it
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+            if (lane == 0) {
+              if (pair && prank != 0) s_mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[buf]), 0));
+              else mbar_arrive(smem_u32(&tempty_bar[buf]));
+            }
           }
           float y[16];
 #pragma unroll
@@ -410,7 +478,10 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             // the whole accumulator slice is in registers: the MMAs of the tile after next may overwrite it
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+            if (lane == 0) {
+              if (pair && prank != 0) s_mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[buf]), 0));   // the leader's MMA warp owns both accumulators
+              else mbar_arrive(smem_u32(&tempty_bar[buf]));
+            }
           }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -562,9 +633,12 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   if (!Q8 && g.tma_epi && warp_idx >= 2 && lane == 0) s_bulk_wait0();     // this warp's TMA stores have left shared memory and are complete
   tc_fence_before();
-  if (cn > 1) cluster_sync_all();
+  if (cn > 1 || pair) cluster_sync_all();
   else __syncthreads();
-  if (warp_idx == 1) tmem_dealloc(tmem_base, 512);
+  if (warp_idx == 1) {
+    if (pair) s_tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // Launch when the problem qualifies; returns 1 if it does not (caller falls back to gemm_i8_kernel), 0 on success, < 0 on error.
@@ -611,12 +685,22 @@ int launch_gemm_stream(const int8_t* A, int64_t lda, const int8_t* W, int64_t ld
       g.tma_epi = 1;
     }
   }
+  {
+    // K > 512 (FFN2): the tile is bound by the L2 -> SM operand stream (A 256 KB + W 512 KB per 128 x 256 tile at ~43 B/clk per SM).  A CTA
+    // pair shares the weight block (each CTA brings half of it, one cta_group::2 MMA of M = 256 reads both halves): 640 instead of 768 KB
+    static const int pair_env = getenv("OT_GEMM_STREAM_PAIR") ? atoi(getenv("OT_GEMM_STREAM_PAIR")) : 1;
+    if (pair_env && out_kind == OT_OUT_F32 && (K > 512 || pair_env > 1) && M >= 2 * kSBM * 8) {
+      rc = get_tensor_map(&tb, W, N, K, ldw, kSBN / 2, kSBK, true);
+      if (rc) return rc;
+      g.pair = 1;
+    }
+  }
   if (const char* tr = getenv("OT_GEMM_STREAM_TRACE")) g.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16));
-  auto kernel = out_kind == OT_OUT_Q8 ? gemm_stream_kernel<true> : gemm_stream_kernel<false>;
-  static DeviceOnce attr_set[2];
+  auto kernel = out_kind == OT_OUT_Q8 ? gemm_stream_kernel<true> : (g.pair ? gemm_stream_kernel<false, true> : gemm_stream_kernel<false>);
+  static DeviceOnce attr_set[3];
   static int max_clusters[2][kSMaxCl + 1] = {};
   const int ki = out_kind == OT_OUT_Q8 ? 1 : 0;
-  if (attr_set[ki].need()) OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmem));
+  if (attr_set[g.pair ? 2 : ki].need()) OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmem));
   int sms = 148;
   {
     int dev = 0;
@@ -624,7 +708,9 @@ int launch_gemm_stream(const int8_t* A, int64_t lda, const int8_t* W, int64_t ld
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int n_cl;
-  if (cn == 1) {
+  if (g.pair) {
+    n_cl = sms / 2;      // CTA pairs; launched as clusters of 2 below
+  } else if (cn == 1) {
     n_cl = sms;
   } else {
     if (max_clusters[ki][cn] == 0) {
@@ -646,9 +732,10 @@ int launch_gemm_stream(const int8_t* A, int64_t lda, const int8_t* W, int64_t ld
     n_cl = max_clusters[ki][cn];
   }
   const int m_tiles = (M + kSBM - 1) / kSBM;
-  const int total = m_tiles * ((N / kSBN) / cn);
+  const int total = g.pair ? ((m_tiles + 1) / 2) * (N / kSBN) : m_tiles * ((N / kSBN) / cn);
   if (n_cl > total) n_cl = total;
-  OT_CHECK_CUDA(launch_kernel(kernel, dim3(static_cast<unsigned>(n_cl * cn)), dim3(kSThreads), kSSmem, stream, cn, ta, tb, tr_map, to_map, g));
+  const int unit = g.pair ? 2 : cn;
+  OT_CHECK_CUDA(launch_kernel(kernel, dim3(static_cast<unsigned>(n_cl * unit)), dim3(kSThreads), kSSmem, stream, unit, ta, tb, tr_map, to_map, g));
   count_launch();
   return OT_OK;
 }
