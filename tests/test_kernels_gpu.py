@@ -69,10 +69,16 @@ def test_gemm_fused_requant_bit_exact(K, M, N, K_, group, relu):
 
 
 @pytest.mark.parametrize("M,N,K_,group,relu,res", [(2100, 1536, 512, 512, False, False), (8192, 2048, 512, 2048, True, False), (3000, 512, 512, 0, False, True),
-                                                   (5000, 512, 2048, 0, False, True), (2048, 6144, 512, 512, False, False), (4096, 1024, 256, 256, True, False)])
+                                                   (5000, 512, 2048, 0, False, True), (2048, 6144, 512, 512, False, False), (4096, 1024, 256, 256, True, False),
+                                                   # fp32 output through per-warp TMA boxes (K <= 512), without / with a residual, ragged rows
+                                                   (2500, 512, 512, 0, False, False), (2049, 768, 256, 0, True, True),
+                                                   # CTA pairs (cta_group::2, K > 512): an odd number of 128-row tiles (the peer's last tile is empty),
+                                                   # one column tile, ReLU without a residual
+                                                   (2176, 1024, 1024, 0, False, True), (2048, 256, 2048, 0, True, False)])
 def test_gemm_stream_kernel_equals_tile_kernel_and_oracle(K, M, N, K_, group, relu, res):
     """The persistent double-accumulator kernel (ot_gemm_stream.cu, M >= 2048) against the one-tile-per-CTA kernel bit for bit, and both
-    against the oracle on a row sample (ragged last tiles, clusters of 1 / 2 / 8, the 12-projection cross-K/V shape)."""
+    against the oracle on a row sample (ragged last tiles, clusters of 1 / 2 / 8, the 12-projection cross-K/V shape, the TMA epilogue of
+    the K <= 512 fp32 GEMMs, the CTA-pair form of the K > 512 ones)."""
     import os
     rng = np.random.default_rng(31 + M + N)
     a, w = rand_i8(rng, (M, K_)), rand_i8(rng, (N, K_))
