@@ -14,19 +14,30 @@ GCC = shutil.which("gcc")
 pytestmark = pytest.mark.skipif(GCC is None, reason="gcc not available")
 
 
-def _build(tmp_path, src, extra_src=None):
+def _build(tmp_path, src, extra_src=None, flags=()):
     exe = str(tmp_path / "check")
     path = os.path.join(ROOT, "tools", src) if extra_src is None else str(tmp_path / src)
     if extra_src is not None:
         with open(path, "w") as f:
             f.write(extra_src)
-    subprocess.run([GCC, "-O2", "-ffp-contract=off", "-o", exe, path, "-lm"], check=True)
+    subprocess.run([GCC, "-O2", "-ffp-contract=off", *flags, "-o", exe, path, "-lm"], check=True)
     return exe
 
 
 def test_quant_bits_matches_rint_of_true_division(tmp_path):
     exe = _build(tmp_path, "check_quant_bits.c")
     res = subprocess.run([exe, "3000000"], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "0 mismatches" in res.stdout
+
+
+@pytest.mark.parametrize("flags", [(), ("-DSEQ4",)])
+def test_branch_free_exact_quotient_of_the_requant_epilogues(tmp_path, flags):
+    """tools/check_div_exact.c: the FMA-residual quotient of the fused RowQuant epilogues (ot_gemm_wres.cu, ot_attention_tc.cu) equals the
+    IEEE division bit for bit on random and adversarial (near half-integer) cases -- the two-step form the kernels use and the
+    four-operation form (-DSEQ4) that was measured against it; a bounded sample of the 8e9-case runs quoted in the tool's header."""
+    exe = _build(tmp_path, "check_div_exact.c", flags=flags)
+    res = subprocess.run([exe, "30000000"], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "0 mismatches" in res.stdout
 

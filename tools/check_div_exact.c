@@ -5,7 +5,10 @@
 // in [1e-5, 1e6], |y| <= amax(1 + 2^-20), a quarter of the cases within a few ulps of (m + 1/2) s, plus scales whose significand is all
 // ones / a power of two.  For dividends below s/4 (incl. zeros and denormals, where the residuals underflow)
 // only the byte is compared (it is 0 either way).  Also checks that the FINAL byte (low byte of q2 + 1.5*2^23) equals (int8) rint(y / s).
-// Build: gcc -O2 -ffp-contract=off -fopenmp -o tools/bin/check_div_exact tools/check_div_exact.c -lm
+// -DSEQ4: a four-operation form (r_lo = RN((1 - s r) r) per row; t = RN(y r_lo), qb = RN(y r + t), one residual step): 8e9 cases, 0
+// mismatches.  One FFMA2 fewer per column pair, but in ot_gemm_wres.cu the extra per-row value tips the 96-register epilogue into spills
+// (QKV 92.3 -> 95.6 us, FFN1 137.5 -> 143.6 us): measured and not adopted; the kernels keep the two-step form.  -DSEQ3: one step from the plain product (NOT proven; kept to show what the checker sees).
+// Build: gcc -O2 -ffp-contract=off -fopenmp [-DSEQ4] -o tools/bin/check_div_exact tools/check_div_exact.c -lm
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -17,9 +20,21 @@ static float from_bits(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 static int check(float y, float s, int small) {
   const float r = 1.0f / s;
+#ifdef SEQ4
+  // four operations: r_lo = RN((1 - s r) r) per ROW; per element t = RN(y r_lo), qb = RN(y r + t) (one rounding of the almost exact
+  // quotient: faithful), then ONE Markstein step
+  const float r_lo = fmaf(-s, r, 1.0f) * r;
+  const float t0 = y * r_lo;
+  const float qb = fmaf(y, r, t0);
+  const float q2 = fmaf(fmaf(-qb, s, y), r, qb);
+#elif defined(SEQ3)
+  const float q0 = y * r;
+  const float q2 = fmaf(fmaf(-q0, s, y), r, q0);       // one step from the plain product: NOT exact (the checker must find cases)
+#else
   const float q0 = y * r;
   const float q1 = fmaf(fmaf(-q0, s, y), r, q0);
   const float q2 = fmaf(fmaf(-q1, s, y), r, q1);
+#endif
   const float x = y / s;
   if (!small && bits(q2) != bits(x) && !(q2 == 0.0f && x == 0.0f)) { printf("quotient mismatch y=%a s=%a q2=%a y/s=%a\n", y, s, q2, x); return 0; }
   const float t = q2 + 12582912.0f;
