@@ -941,6 +941,8 @@ static int dispatch_gemm(GemmArgs& g, int quant_group, cudaStream_t stream) {
   }
 }
 
+int launch_gemm_wres(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K, const float* row_scale, const float* col_scale,
+                     const float* bias, int relu, void* out, int64_t ldo, float* out_scale, int quant_group, cudaStream_t stream, int w4);
 int launch_gemm_stream(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K, const float* row_scale,
                        const float* col_scale, const float* bias, const float* residual, int64_t ldr, int relu, int out_kind, void* out,
                        int64_t ldo, float* out_scale, int quant_group, cudaStream_t stream);
@@ -1015,6 +1017,12 @@ static int linear_common(bool w4, const int8_t* A, int64_t lda, const void* W, i
   if (stream_on && !w4 && fault == nullptr && mf_unit == nullptr && zp == nullptr && !getenv("OT_GEMM_TRACE")) {
     const int rc = launch_gemm_stream(A, lda, reinterpret_cast<const int8_t*>(W), ldw, M, N, K, row_scale, col_scale, bias, residual, ldr, relu, out_kind,
                                       out, ldo, out_scale, quant_group, s);
+    if (rc <= 0) return rc;
+  }
+  // packed int4 weights at encoder sizes with the requantization fused: the weight-stationary kernel unpacks its tile once per launch
+  if (stream_on && w4 && fault == nullptr && mf_unit == nullptr && zp == nullptr && out_kind == OT_OUT_Q8 && residual == nullptr && !getenv("OT_GEMM_TRACE")) {
+    const int rc = launch_gemm_wres(A, lda, reinterpret_cast<const int8_t*>(W), ldw, M, N, K, row_scale, col_scale, bias, relu, out, ldo, out_scale,
+                                    quant_group, s, 1);
     if (rc <= 0) return rc;
   }
   return w4 ? dispatch_gemm<1>(g, quant_group, s) : dispatch_gemm<0>(g, quant_group, s);

@@ -28,7 +28,7 @@ namespace ot {
 int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, bool swizzle128);
 int get_tensor_map_sw(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, int swizzle);
 int launch_gemm_wres(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K, const float* row_scale, const float* col_scale,
-                     const float* bias, int relu, void* out, int64_t ldo, float* out_scale, int quant_group, cudaStream_t stream);
+                     const float* bias, int relu, void* out, int64_t ldo, float* out_scale, int quant_group, cudaStream_t stream, int w4);
 
 constexpr int kSBM = 128, kSBN = 256, kSBK = 128, kSStages = 3;
 constexpr int kSEpiWarps = 16, kSEpiThreads = kSEpiWarps * 32, kSThreads = 64 + kSEpiThreads;
@@ -649,7 +649,7 @@ int launch_gemm_stream(const int8_t* A, int64_t lda, const int8_t* W, int64_t ld
   if (M < min_m || N % kSBN != 0 || K % kSBK != 0 || K < kSBK) return 1;
   if (out_kind != OT_OUT_F32 && out_kind != OT_OUT_Q8) return 1;
   if (out_kind == OT_OUT_Q8 && residual == nullptr) {     // K <= 512: the weight-stationary kernel (ot_gemm_wres.cu)
-    const int rc = launch_gemm_wres(A, lda, W, ldw, M, N, K, row_scale, col_scale, bias, relu, out, ldo, out_scale, quant_group, stream);
+    const int rc = launch_gemm_wres(A, lda, W, ldw, M, N, K, row_scale, col_scale, bias, relu, out, ldo, out_scale, quant_group, stream, 0);
     if (rc != 1) return rc;
   }
   int cn = 1;

@@ -96,7 +96,10 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
   return r;
 }
 
-template <bool RELU>
+// W4 (cfg4): the weight tile arrives as PACKED int4 (two values per byte, even k in the low nibble: 64 KB instead of 128 KB from HBM / L2),
+// is unpacked ONCE into the resident swizzled int8 tile by the epilogue warps, and the launch then runs exactly like the int8 one -- the
+// place where 4-bit weights cost nothing at encoder sizes (a separate instantiation: the int8 kernel's register allocation is untouched).
+template <bool RELU, bool W4 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_o,
                  const __grid_constant__ Args g) {
@@ -119,7 +122,8 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* xbar = tempty_bar + 2;            // [buf][row quarter]
   uint64_t* sfull = xbar + 8;                 // staging tile written (16 epilogue warps)
   uint64_t* sempty = sfull + 1;               // staging tile read by the TMA stores
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 1);
+  uint64_t* wready = sempty + 1;              // W4: the weight tile has been unpacked (16 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wready + 1);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) / 32, 0);
   const int lane = threadIdx.x & 31;
@@ -141,6 +145,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp_idx == 1) {
     if (elect_one()) {
       mbar_init(smem_u32(wfull), 1);
+      mbar_init(smem_u32(wready), kEpiWarps);
       for (int s = 0; s < kStages; ++s) {
         mbar_init(smem_u32(&full_bar[s]), 1);
         mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -183,8 +188,15 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== TMA producer =====================
     if (elect_one()) {
       const uint32_t wb = smem_u32(wfull);
-      mbar_arrive_expect_tx(wb, static_cast<uint32_t>(nkb) * kWkb);
-      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem_u32(sW + kb * kWkb), &tmap_w, wb, kb * kBK, n_tile * kBN);
+      if (W4) {
+        // packed k-blocks [256 rows][64 B] into the (still idle) activation ring + staging tile: 16 KB each, unpacked by the epilogue warps
+        mbar_arrive_expect_tx(wb, static_cast<uint32_t>(nkb) * (kWkb / 2));
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem_u32(sA + kb * (kWkb / 2)), &tmap_w, wb, kb * (kBK / 2), n_tile * kBN);
+        mbar_wait(smem_u32(wready), 0);           // the ring is free again
+      } else {
+        mbar_arrive_expect_tx(wb, static_cast<uint32_t>(nkb) * kWkb);
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem_u32(sW + kb * kWkb), &tmap_w, wb, kb * kBK, n_tile * kBN);
+      }
       uint32_t cnt = 0;
       for (int i = 0; i < (m_tiles - ci + ng - 1) / ng; ++i) {
         const int m_tile = ci + i * ng;
@@ -202,7 +214,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_i8(kBM, kBN);
-      mbar_wait(smem_u32(wfull), 0);
+      mbar_wait(smem_u32(W4 ? wready : wfull), 0);
       uint32_t cnt = 0;
       for (int i = 0; i < (m_tiles - ci + ng - 1) / ng; ++i) {
         const uint32_t buf = i & 1u;
@@ -254,6 +266,29 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     bool cols_bad = false;
     for (int j = lane; j < 64; j += 32) cols_bad = cols_bad || !(fabsf(cs[j]) < 3.0e38f) || !(fabsf(bs[j]) < 3.0e38f);
     cols_bad = __any_sync(0xffffffffu, cols_bad);
+    if (W4) {
+      // ---- unpack the packed weight tile once: task = (k-block, row, 16-byte chunk of the int8 row) <- 8 packed bytes
+      mbar_wait(smem_u32(wfull), 0);
+      const int te = e * 32 + lane;
+      for (int task = te; task < nkb * 2048; task += kEpiThreads) {
+        const int kb = task >> 11, row = (task >> 3) & 255, c = task & 7;
+        const uint2 pk = *reinterpret_cast<const uint2*>(sA + kb * (kWkb / 2) + row * 64 + c * 8);
+        uint32_t o[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t w = h ? pk.y : pk.x;
+          uint32_t lo = w & 0x0F0F0F0Fu, hi = (w >> 4) & 0x0F0F0F0Fu;               // even-k / odd-k nibbles of 4 packed bytes
+          lo |= (lo & 0x08080808u) * 0x1Eu;                                          // sign extension per byte: bit 3 -> bits 4..7
+          hi |= (hi & 0x08080808u) * 0x1Eu;
+          o[2 * h] = __byte_perm(lo, hi, 0x5140);                                    // k = 0, 1, 2, 3 of this word
+          o[2 * h + 1] = __byte_perm(lo, hi, 0x7362);                                // k = 4 .. 7
+        }
+        *reinterpret_cast<uint4*>(sW + kb * kWkb + row * 128 + ((c ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async_smem();                   // generic-proxy writes of the weight tile -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(wready));
+    }
     // staging address of this thread's 64 bytes: half cq>>1, row, 16-byte chunks 4*(cq&1) .. +3 XOR-swizzled by the row (the layout
     // CU_TENSOR_MAP_SWIZZLE_128B expects of a [128][128 B] box)
     uint8_t* srow = stage + (cq >> 1) * (kBM * 128) + row_in_tile * 128;
@@ -411,7 +446,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 // Launch when the problem qualifies; returns 1 if it does not (the caller falls back to the streaming / tile kernels), 0 on success.
 int launch_gemm_wres(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw, int M, int N, int K, const float* row_scale, const float* col_scale,
-                     const float* bias, int relu, void* out, int64_t ldo, float* out_scale, int quant_group, cudaStream_t stream) {
+                     const float* bias, int relu, void* out, int64_t ldo, float* out_scale, int quant_group, cudaStream_t stream, int w4) {
   using namespace wres;
   const char* env = getenv("OT_GEMM_WRES");      // "0": A/B runs against the streaming kernel (tests, tools/bench_gemm.py)
   const int enabled = env ? atoi(env) : 1;
@@ -423,7 +458,8 @@ int launch_gemm_wres(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw,
   if ((cn & (cn - 1)) != 0) return 1;
   const int groups = N / quant_group;
   CUtensorMap ta, tw, to;
-  int rc = get_tensor_map(&tw, W, N, K, ldw, kBN, kBK, true);
+  // W4: W is the packed matrix [N][K / 2] (row pitch ldw bytes); boxes of 256 rows x 64 bytes, no swizzle (the unpacker re-lays them out)
+  int rc = w4 ? get_tensor_map(&tw, W, N, K / 2, ldw, kBN, kBK / 2, false) : get_tensor_map(&tw, W, N, K, ldw, kBN, kBK, true);
   if (rc) return rc;
   rc = get_tensor_map(&ta, A, M, K, lda, kBM, kBK, true);
   if (rc) return rc;
@@ -434,10 +470,10 @@ int launch_gemm_wres(const int8_t* A, int64_t lda, const int8_t* W, int64_t ldw,
   g.row_scale = row_scale; g.col_scale = col_scale; g.bias = bias; g.relu = relu; g.out_scale = out_scale; g.cluster_n = cn; g.groups = groups;
   g.neg0 = 0x8000000080000000ull; g.one = 0x3F8000003F800000ull; g.magic = 0x4B4000004B400000ull;
   if (const char* tr = getenv("OT_GEMM_WRES_TRACE")) g.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16));
-  auto kernel = relu ? gemm_wres_kernel<true> : gemm_wres_kernel<false>;
-  const int ki = relu ? 1 : 0;
-  static DeviceOnce attr_set[2];
-  static int max_clusters_k[2][kMaxCl + 1] = {};
+  auto kernel = w4 ? (relu ? gemm_wres_kernel<true, true> : gemm_wres_kernel<false, true>) : (relu ? gemm_wres_kernel<true> : gemm_wres_kernel<false>);
+  const int ki = (relu ? 1 : 0) + (w4 ? 2 : 0);
+  static DeviceOnce attr_set[4];
+  static int max_clusters_k[4][kMaxCl + 1] = {};
   int* max_clusters = max_clusters_k[ki];
   if (attr_set[ki].need()) OT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   int sms = 148;

@@ -175,6 +175,27 @@ def test_gemm_w4_bit_exact(K):
     assert np.array_equal(out, ox.int_matmul(a, w))
 
 
+@pytest.mark.parametrize("M,N,K_,group,relu", [(4096, 1536, 512, 512, False), (2100, 2048, 512, 2048, True), (2048, 512, 256, 512, False)])
+def test_gemm_w4_weight_stationary_requant_bit_exact(K, M, N, K_, group, relu):
+    """cfg4 at encoder sizes: packed int4 weights through the weight-stationary requant kernel (gemm_wres_kernel<.., W4>: the tile is
+    unpacked once per launch into the resident swizzled int8 layout) == the same GEMM on the unpacked int8 copy == the oracle, bit for bit."""
+    rng = np.random.default_rng(M + N)
+    a = rand_i8(rng, (M, K_))
+    w = rng.integers(-8, 8, size=(N, K_), dtype=np.int8)
+    packed = ((w[:, 0::2].astype(np.uint8) & 0xF) | ((w[:, 1::2].astype(np.uint8) & 0xF) << 4)).astype(np.uint8)
+    sx = rng.uniform(1e-3, 5e-2, size=M).astype(np.float32)
+    sw = rng.uniform(1e-3, 1e-1, size=N).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    n0 = K._lib.launch_count()
+    q4, s4 = K.linear_w8a8(dev(a), dev(packed), row_scale=dev(sx), col_scale=dev(sw), bias=dev(b), relu=relu, out_kind=K.OUT_Q8, quant_group=group, w4=True)
+    assert K._lib.launch_count() == n0 + 1
+    q8, s8 = K.linear_w8a8(dev(a), dev(w), row_scale=dev(sx), col_scale=dev(sw), bias=dev(b), relu=relu, out_kind=K.OUT_Q8, quant_group=group)
+    assert torch.equal(q4, q8) and torch.equal(s4, s8)
+    rows = np.unique(np.concatenate([np.arange(0, 130), np.arange(M - 140, M), rng.integers(0, M, size=200)]))
+    qr, sr = ox.group_quant(ox.linear_w8a8(a[rows], sx[rows], w, sw, b, relu, None), group)
+    assert np.array_equal(q4.cpu().numpy()[rows], qr) and np.array_equal(s4.cpu().numpy()[rows].view(np.uint32), sr.view(np.uint32))
+
+
 def test_gemm_faults(K):
     rng = np.random.default_rng(9)
     M, N, K_ = 96, 512, 512
