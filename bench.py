@@ -385,7 +385,8 @@ def rank0_measurements(eng, dev):
         torch.cuda.synchronize(dev)
         ms4 = e0.elapsed_time(e1) / 3
         out["cfg4_int4_weights_decode"] = {"batch": 64, "src_len": 64, "ms": ms4, "tokens_per_s": 64 * (MAX_LEN - 1) / (ms4 * 1e-3),
-                                           "note": "encoder / cross-K/V GEMMs unpack packed int4 in shared memory; the cluster decoder reads the int8 copy of the 4-bit values"}
+                                           "note": "encoder / cross-K/V: the requant GEMMs take the packed int4 tile and unpack it once per launch in shared memory (weight-stationary kernel), "
+                                                   "the fp32-output GEMMs run on a per-launch unpacked int8 scratch; the cluster decoder reads the int8 copy of the 4-bit values"}
         del eng4
         torch.cuda.empty_cache()
     except Exception as exc:      # side measurement: never fail the headline line

@@ -107,7 +107,21 @@ class _Linear:
     def gemm(self, a_q, row_scale, **kw):
         """a_q @ W^T through the tcgen05 GEMM with this layer's scales and bias (w8 or packed-w4 weights; a WEIGHT fault on packed
         int4 weights flips one of 4 bits: flip_int4_bit, inject_utils/layers.py:48-59)."""
+        if (self.w4 and a_q.shape[0] >= 2048 and kw.get("out_kind", K.OUT_F32) == K.OUT_F32 and kw.get("fault") is None
+                and kw.get("mf") is None):
+            # fp32-output GEMMs at encoder sizes re-stream their weight block with every 128-row tile, so unpacking it in shared memory
+            # costs per tile (8.55 ms per 512 x 128 encoder pass).  The packed matrix (<= 0.5 MB) is expanded ONCE per launch into an
+            # L2-resident int8 scratch (~2 us) and the int8 streaming kernel runs on that; the requant GEMMs take the nibbles directly
+            # (gemm_wres_kernel<.., W4> unpacks its resident tile once).  Same int32 accumulators, same scales: same bits.
+            key = (self.wq.device, self.N, self.K)
+            scratch = _Linear._w4_scratch.get(key)
+            if scratch is None:
+                scratch = _Linear._w4_scratch[key] = torch.empty((self.N, self.K), dtype=torch.int8, device=self.wq.device)
+            K.unpack_int4(self.wq, out=scratch)
+            return K.linear_w8a8(a_q, scratch, row_scale=row_scale, col_scale=self.sw, bias=self.bias, **kw)
         return K.linear_w8a8(a_q, self.wq, row_scale=row_scale, col_scale=self.sw, bias=self.bias, w4=self.w4, **kw)
+
+    _w4_scratch: dict = {}
 
 
 class _FaultBatch:

@@ -212,10 +212,14 @@ def ln_linear_w8a8(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, w_q
     return (out, out_scale) if out_kind == OUT_Q8 else out
 
 
-def unpack_int4(w4: torch.Tensor) -> torch.Tensor:
+def unpack_int4(w4: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req(w4, torch.uint8, "w4")
     rows, half = w4.shape
-    out = torch.empty((rows, half * 2), dtype=torch.int8, device=w4.device)
+    if out is None:
+        out = torch.empty((rows, half * 2), dtype=torch.int8, device=w4.device)
+    else:
+        _req(out, torch.int8, "out")
+        assert out.shape == (rows, half * 2)
     _lib.check(_lib.load().ot_unpack_int4(_ptr(w4), _ptr(out), rows, half * 2, _stream()), "ot_unpack_int4")
     return out
 

@@ -107,6 +107,22 @@ def test_int4_weight_engine_matches_oracle():
                 break
 
 
+def test_int4_weight_encoder_at_encoder_sizes_equals_its_small_batch_path():
+    """cfg4 at encoder sizes (>= 2048 rows): the requant GEMMs take the packed nibbles through the weight-stationary kernel, the
+    fp32-output GEMMs run the streaming int8 kernels on a per-launch unpacked scratch.  A sentence's rows must not depend on the batch it
+    is in: 40 sentences x 64 tokens (2560 rows, the large-M kernels) == the same sentences 8 at a time (512 rows, the packed-int4 tile
+    kernel), bit for bit."""
+    from onnx_transformer_b200.engine import QuantizedTransformer
+    fw = W.init_float_weights(5, 211, 197, 2, randomize_norms=True)
+    eng = QuantizedTransformer(fw, n_layers=2, max_len=9, weight_bits=4)
+    ids, mask = W.synthetic_tokens(5, 40, 64, 211, min_len=20)
+    idt, mt = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    big = eng.encode(idt, mt).clone()
+    for lo in range(0, 40, 8):
+        small = eng.encode(idt[lo:lo + 8], mt[lo:lo + 8])
+        assert torch.equal(big[lo:lo + 8], small), lo
+
+
 def test_cfg3_full_size_encoder_is_sentence_shardable():
     """BASELINE config #3 (encoder only, 512 sentences x 128 source tokens): the size-independent property the multi-GPU partition
     rests on -- a sentence's memory rows do not depend on which other sentences share its batch, bit for bit (no cross-sentence op)."""
